@@ -1,0 +1,358 @@
+/*
+ * oracle/interval_oracle.c -- CPU ORACLE for the interval-join hot path.
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, the smoke check in
+ * __graft_entry__.py and bench.py's cpu_baseline / --impl reference legs may load it.
+ * The product path (polars_bio_b200 + libpbgpu.so) never links or calls anything here.
+ *
+ * What it restates.  The reference (biodatageeks/polars-bio @ f32af94) delegates the
+ * arithmetic of pb.overlap / pb.count_overlaps / pb.nearest / pb.coverage to the
+ * un-vendored crate datafusion-bio-function-ranges v0.11.0 (Cargo.toml:65, Cargo.lock:1830-1842)
+ * which indexes the build side in coitrees 0.4.0 (Cargo.lock:1091-1094): one augmented
+ * interval tree per contig (nodes ordered by start, every node carrying the maximum end of
+ * its subtree), queried once per probe row.  That source is not under /root/reference, so
+ * the published algorithm is restated here from its call sites and in-repo specification:
+ *   - predicate               docs/developers.md:549-552 (Strict: a.start <  b.end && a.end >  b.start,
+ *                                                        Weak:   a.start <= b.end && a.end >= b.start)
+ *   - FilterOp numbering      src/option.rs:96-99  (Weak = 0, Strict = 1)
+ *   - build / probe roles     docs/developers.md:629-649, src/operation.rs:143-158, 253-263, 316-340
+ *   - count identity          polars_bio/range_op.py:548-594 (starts-rank minus ends-rank)
+ *   - nearest distance        tests/_expected.py:162 ([100,200] vs [234,300] -> 34), bioframe parity
+ *                             tests/test_bioframe.py:171-186 (distance only, partner ties arbitrary)
+ *   - coverage adjacency      tests/test_coordinate_system_metadata.py:1577-1623
+ * Pinned by tests/test_oracle_golden.py against every fixture listed in SURVEY.md 8(c).
+ *
+ * Parity unpinned (no reference test constrains it; choices documented in DESIGN.md):
+ *   nearest tie-break (here: overlapping partners first, then (distance, start, row));
+ *   rows with a negative contig code (null key) never match;  start > end rows are
+ *   evaluated by the bare predicate.
+ *
+ * Layout: every table is three int32 columns (contig code, start, end); row ids are
+ * positions in those columns.  Contig codes come from a dictionary shared by both sides.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define PBO_API __attribute__((visibility("default")))
+
+typedef struct {
+  int64_t m;          /* indexed (build) rows kept: contig code >= 0                          */
+  int32_t n_contigs;  /* contig codes are 0 .. n_contigs-1                                   */
+  int64_t *seg;       /* [n_contigs+1] segment offsets into the sorted arrays                 */
+  int32_t *st;        /* starts, sorted by (contig, start, row)                               */
+  int32_t *en;        /* ends in the same order                                               */
+  uint32_t *row;      /* original row ids in the same order                                   */
+  int32_t *sub_max;   /* augmented key: max end over the implicit subtree rooted at this slot */
+  int32_t *en_sorted; /* ends sorted by (contig, end, start, row)                             */
+  uint32_t *en_pos;   /* position in st/en/row order of each en_sorted entry                  */
+} pbo_index;
+
+typedef struct { int32_t c, s, e; uint32_t r; } pbo_rec;
+
+static int cmp_start(const void *a, const void *b) {
+  const pbo_rec *x = (const pbo_rec *)a, *y = (const pbo_rec *)b;
+  if (x->c != y->c) return x->c < y->c ? -1 : 1;
+  if (x->s != y->s) return x->s < y->s ? -1 : 1;
+  return x->r < y->r ? -1 : (x->r > y->r);
+}
+typedef struct { int32_t c, e, s; uint32_t r, pos; } pbo_erec;
+static int cmp_end(const void *a, const void *b) {
+  const pbo_erec *x = (const pbo_erec *)a, *y = (const pbo_erec *)b;
+  if (x->c != y->c) return x->c < y->c ? -1 : 1;
+  if (x->e != y->e) return x->e < y->e ? -1 : 1;
+  if (x->s != y->s) return x->s < y->s ? -1 : 1;
+  return x->r < y->r ? -1 : (x->r > y->r);
+}
+
+/* Implicit balanced tree over a sorted slice [lo,hi): root = midpoint, children = the two
+ * halves.  sub_max[mid] = max end over [lo,hi)  (the COITrees/IITree augmentation).        */
+static int32_t build_aug(const int32_t *en, int32_t *sub_max, int64_t lo, int64_t hi) {
+  if (lo >= hi) return INT32_MIN;
+  int64_t mid = lo + ((hi - lo) >> 1);
+  int32_t m = en[mid];
+  int32_t l = build_aug(en, sub_max, lo, mid);
+  int32_t r = build_aug(en, sub_max, mid + 1, hi);
+  if (l > m) m = l;
+  if (r > m) m = r;
+  sub_max[mid] = m;
+  return m;
+}
+
+PBO_API void pbo_index_free(pbo_index *ix) {
+  if (!ix) return;
+  free(ix->seg); free(ix->st); free(ix->en); free(ix->row);
+  free(ix->sub_max); free(ix->en_sorted); free(ix->en_pos); free(ix);
+}
+
+PBO_API pbo_index *pbo_index_build(const int32_t *c, const int32_t *s, const int32_t *e,
+                                   int64_t m_in, int32_t n_contigs) {
+  pbo_index *ix = (pbo_index *)calloc(1, sizeof(pbo_index));
+  pbo_rec *rec = (pbo_rec *)malloc(sizeof(pbo_rec) * (size_t)(m_in > 0 ? m_in : 1));
+  int64_t m = 0;
+  for (int64_t i = 0; i < m_in; ++i)
+    if (c[i] >= 0 && c[i] < n_contigs) { rec[m].c = c[i]; rec[m].s = s[i]; rec[m].e = e[i]; rec[m].r = (uint32_t)i; ++m; }
+  qsort(rec, (size_t)m, sizeof(pbo_rec), cmp_start);
+  ix->m = m; ix->n_contigs = n_contigs;
+  size_t mm = (size_t)(m > 0 ? m : 1);
+  ix->seg = (int64_t *)calloc((size_t)n_contigs + 1, sizeof(int64_t));
+  ix->st = (int32_t *)malloc(4 * mm); ix->en = (int32_t *)malloc(4 * mm);
+  ix->row = (uint32_t *)malloc(4 * mm); ix->sub_max = (int32_t *)malloc(4 * mm);
+  ix->en_sorted = (int32_t *)malloc(4 * mm); ix->en_pos = (uint32_t *)malloc(4 * mm);
+  pbo_erec *er = (pbo_erec *)malloc(sizeof(pbo_erec) * mm);
+  for (int64_t i = 0; i < m; ++i) {
+    ix->st[i] = rec[i].s; ix->en[i] = rec[i].e; ix->row[i] = rec[i].r;
+    ix->seg[rec[i].c + 1]++;
+    er[i].c = rec[i].c; er[i].e = rec[i].e; er[i].s = rec[i].s; er[i].r = rec[i].r; er[i].pos = (uint32_t)i;
+  }
+  for (int32_t k = 0; k < n_contigs; ++k) ix->seg[k + 1] += ix->seg[k];
+  for (int32_t k = 0; k < n_contigs; ++k) build_aug(ix->en, ix->sub_max, ix->seg[k], ix->seg[k + 1]);
+  qsort(er, (size_t)m, sizeof(pbo_erec), cmp_end);
+  for (int64_t i = 0; i < m; ++i) { ix->en_sorted[i] = er[i].e; ix->en_pos[i] = er[i].pos; }
+  free(er); free(rec);
+  return ix;
+}
+
+static inline int hit(int strict, int32_t as, int32_t ae, int32_t bs, int32_t be) {
+  return strict ? (as < be && ae > bs) : (as <= be && ae >= bs);
+}
+
+/* Tree query: visit every indexed interval of the contig slice that satisfies the predicate,
+ * in (start,row) order.  cb_pos receives positions in sorted order; returns count.          */
+typedef struct { int64_t lo, hi; } pbo_span;
+static int64_t tree_query(const pbo_index *ix, int64_t lo0, int64_t hi0, int strict,
+                          int32_t qs, int32_t qe, uint32_t *out_pos, int64_t cap) {
+  /* explicit stack; depth <= 64.  In-order traversal so results come out start-sorted. */
+  struct { int64_t lo, hi; int stage; } stk[70];
+  int sp = 0; int64_t n = 0;
+  stk[sp].lo = lo0; stk[sp].hi = hi0; stk[sp].stage = 0; ++sp;
+  while (sp > 0) {
+    int64_t lo = stk[sp - 1].lo, hi = stk[sp - 1].hi; int stage = stk[sp - 1].stage;
+    if (lo >= hi) { --sp; continue; }
+    int64_t mid = lo + ((hi - lo) >> 1);
+    if (stage == 0) {
+      /* prune: nothing in this subtree ends after (at) the query start */
+      int32_t mx = ix->sub_max[mid];
+      if (strict ? (mx <= qs) : (mx < qs)) { --sp; continue; }
+      stk[sp - 1].stage = 1;
+      stk[sp].lo = lo; stk[sp].hi = mid; stk[sp].stage = 0; ++sp;   /* left subtree first */
+      continue;
+    }
+    --sp;
+    /* node itself, then right subtree, only if node start is still before the query end */
+    int32_t bs = ix->st[mid];
+    if (strict ? (bs < qe) : (bs <= qe)) {
+      if (hit(strict, qs, qe, bs, ix->en[mid])) { if (out_pos && n < cap) out_pos[n] = (uint32_t)mid; ++n; }
+      stk[sp].lo = mid + 1; stk[sp].hi = hi; stk[sp].stage = 0; ++sp;
+    }
+  }
+  return n;
+}
+
+/* ---- count_overlaps: per iterated row, number of indexed rows that overlap it ------------ */
+PBO_API void pbo_count_overlaps(const pbo_index *ix, const int32_t *c, const int32_t *s, const int32_t *e,
+                                int64_t n, int strict, int64_t *counts, int threads) {
+#ifdef _OPENMP
+  if (threads > 0) omp_set_num_threads(threads);
+#pragma omp parallel for schedule(dynamic, 4096)
+#endif
+  for (int64_t i = 0; i < n; ++i) {
+    int32_t cc = c[i];
+    if (cc < 0 || cc >= ix->n_contigs) { counts[i] = 0; continue; }
+    counts[i] = tree_query(ix, ix->seg[cc], ix->seg[cc + 1], strict, s[i], e[i], NULL, 0);
+  }
+}
+
+/* ---- overlap: all (probe_row, build_row) pairs -------------------------------------------
+ * Two-phase (count, prefix, fill) so the parallel version writes disjoint ranges.
+ * Returns the total pair count; writes min(total, cap) pairs ordered by probe row, then
+ * by (start,row) of the indexed partner.                                                    */
+PBO_API int64_t pbo_overlap_pairs(const pbo_index *ix, const int32_t *c, const int32_t *s, const int32_t *e,
+                                  int64_t n, int strict, uint32_t *out_probe, uint32_t *out_build,
+                                  int64_t cap, int threads) {
+  int64_t *off = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n + 1));
+#ifdef _OPENMP
+  if (threads > 0) omp_set_num_threads(threads);
+#pragma omp parallel for schedule(dynamic, 4096)
+#endif
+  for (int64_t i = 0; i < n; ++i) {
+    int32_t cc = c[i];
+    off[i + 1] = (cc < 0 || cc >= ix->n_contigs) ? 0
+               : tree_query(ix, ix->seg[cc], ix->seg[cc + 1], strict, s[i], e[i], NULL, 0);
+  }
+  off[0] = 0;
+  for (int64_t i = 0; i < n; ++i) off[i + 1] += off[i];
+  int64_t total = off[n];
+  if (out_probe && out_build) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 4096)
+#endif
+    for (int64_t i = 0; i < n; ++i) {
+      int64_t k = off[i + 1] - off[i];
+      if (k == 0 || off[i] >= cap) continue;
+      int64_t room = cap - off[i]; if (room > k) room = k;
+      int32_t cc = c[i];
+      uint32_t *dst = out_build + off[i];
+      tree_query(ix, ix->seg[cc], ix->seg[cc + 1], strict, s[i], e[i], dst, room);
+      for (int64_t j = 0; j < room; ++j) { dst[j] = ix->row[dst[j]]; out_probe[off[i] + j] = (uint32_t)i; }
+    }
+  }
+  free(off);
+  return total;
+}
+
+/* ---- coverage: per iterated row, positions covered by the union of indexed rows ----------
+ * Strict (half-open): sum of max(0, min(ae,be') - max(as,bs')) over merged runs.
+ * Weak (closed):      sum of max(0, min(ae,be') - max(as,bs') + 1).
+ * Pinned by tests/test_coordinate_system_metadata.py:1577-1623 (adjacency: 0 vs 1).         */
+PBO_API void pbo_coverage(const pbo_index *ix, const int32_t *c, const int32_t *s, const int32_t *e,
+                          int64_t n, int strict, int64_t *cov, int threads) {
+#ifdef _OPENMP
+  if (threads > 0) omp_set_num_threads(threads);
+#pragma omp parallel
+#endif
+  {
+    int64_t cap = 1024; uint32_t *buf = (uint32_t *)malloc(4 * (size_t)cap);
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 1024)
+#endif
+    for (int64_t i = 0; i < n; ++i) {
+      int32_t cc = c[i]; cov[i] = 0;
+      if (cc < 0 || cc >= ix->n_contigs) continue;
+      int64_t k = tree_query(ix, ix->seg[cc], ix->seg[cc + 1], strict, s[i], e[i], buf, cap);
+      if (k > cap) { cap = k; buf = (uint32_t *)realloc(buf, 4 * (size_t)cap);
+                     tree_query(ix, ix->seg[cc], ix->seg[cc + 1], strict, s[i], e[i], buf, cap); }
+      /* hits arrive start-sorted: sweep and merge clipped pieces */
+      int64_t total = 0, cur_s = 0, cur_e = 0; int open = 0;
+      for (int64_t j = 0; j < k; ++j) {
+        int64_t bs = ix->st[buf[j]], be = ix->en[buf[j]];
+        if (bs < s[i]) bs = s[i];
+        if (be > e[i]) be = e[i];
+        if (!strict) be += 1;            /* closed -> half-open in 64-bit, no overflow */
+        if (be <= bs) continue;
+        if (!open) { cur_s = bs; cur_e = be; open = 1; }
+        else if (bs <= cur_e) { if (be > cur_e) cur_e = be; }
+        else { total += cur_e - cur_s; cur_s = bs; cur_e = be; }
+      }
+      if (open) total += cur_e - cur_s;
+      cov[i] = total;
+    }
+    free(buf);
+  }
+}
+
+/* ---- nearest ------------------------------------------------------------------------------
+ * For every iterated row: up to k indexed rows of the same contig ordered by
+ *   (overlapping first [if include_overlaps], then distance, then start, then row)
+ * distance = 0 for overlapping partners, else max(b.start - a.end, a.start - b.end) (>= 0).
+ * out_build[i*k + j] = indexed row id or UINT32_MAX (no partner); out_dist likewise / -1.    */
+static inline int64_t gap(int32_t as, int32_t ae, int32_t bs, int32_t be) {
+  int64_t d1 = (int64_t)bs - (int64_t)ae, d2 = (int64_t)as - (int64_t)be;
+  int64_t d = d1 > d2 ? d1 : d2;
+  return d > 0 ? d : 0;
+}
+
+PBO_API void pbo_nearest(const pbo_index *ix, const int32_t *c, const int32_t *s, const int32_t *e,
+                         int64_t n, int strict, int64_t k, int include_overlaps,
+                         uint32_t *out_build, int64_t *out_dist, int threads) {
+#ifdef _OPENMP
+  if (threads > 0) omp_set_num_threads(threads);
+#pragma omp parallel
+#endif
+  {
+    uint32_t *buf = (uint32_t *)malloc(4 * (size_t)(k > 0 ? k : 1));
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 4096)
+#endif
+    for (int64_t i = 0; i < n; ++i) {
+      uint32_t *ob = out_build + i * k; int64_t *od = out_dist + i * k;
+      for (int64_t j = 0; j < k; ++j) { ob[j] = UINT32_MAX; od[j] = -1; }
+      int32_t cc = c[i];
+      if (cc < 0 || cc >= ix->n_contigs) continue;
+      int64_t lo = ix->seg[cc], hi = ix->seg[cc + 1];
+      if (lo >= hi) continue;
+      int32_t qs = s[i], qe = e[i];
+      int64_t got = 0;
+      if (include_overlaps) {
+        int64_t h = tree_query(ix, lo, hi, strict, qs, qe, buf, k);
+        if (h > k) h = k;
+        for (int64_t j = 0; j < h; ++j) { ob[j] = ix->row[buf[j]]; od[j] = 0; }
+        got = h;
+      }
+      if (got >= k) continue;
+      /* right stream: first position (start,row order) whose start is past the query end.
+       * Entries past the end can still overlap only if inverted; skip overlapping ones.       */
+      int64_t a = lo, b = hi;
+      while (a < b) { int64_t mid = a + ((b - a) >> 1);
+        if (strict ? (ix->st[mid] < qe) : (ix->st[mid] <= qe)) a = mid + 1; else b = mid; }
+      int64_t rp = a;
+      /* left stream: en_sorted positions with end before (at) the query start, walked by
+       * descending end; inside one end-value group ascending (start,row).                    */
+      a = lo; b = hi;
+      while (a < b) { int64_t mid = a + ((b - a) >> 1);
+        if (strict ? (ix->en_sorted[mid] <= qs) : (ix->en_sorted[mid] < qs)) a = mid + 1; else b = mid; }
+      int64_t lend = a;           /* en_sorted[lo..lend) are left candidates */
+      int64_t lg_hi = lend, lg_lo = lend, lcur = lend; /* current group [lg_lo,lg_hi), cursor lcur */
+      /* advance helpers inline */
+      for (;;) {
+        /* settle the left cursor on a non-overlapping entry */
+        int have_l = 0, have_r = 0; int64_t lpos = 0, ld = 0, rd = 0;
+        for (;;) {
+          if (lcur >= lg_hi) {              /* open next (smaller end) group */
+            if (lg_lo <= lo) break;
+            lg_hi = lg_lo; int32_t v = ix->en_sorted[lg_hi - 1];
+            int64_t g = lg_hi - 1; while (g > lo && ix->en_sorted[g - 1] == v) --g;
+            lg_lo = g; lcur = g;
+          }
+          lpos = ix->en_pos[lcur];
+          if (hit(strict, qs, qe, ix->st[lpos], ix->en[lpos])) { ++lcur; continue; }
+          have_l = 1; ld = gap(qs, qe, ix->st[lpos], ix->en[lpos]); break;
+        }
+        /* skip overlapping entries and degenerate ones already owned by the left stream */
+        while (rp < hi && (hit(strict, qs, qe, ix->st[rp], ix->en[rp]) ||
+                           (strict ? (ix->en[rp] <= qs) : (ix->en[rp] < qs)))) ++rp;
+        if (rp < hi) { have_r = 1; rd = gap(qs, qe, ix->st[rp], ix->en[rp]); }
+        if (!have_l && !have_r) break;
+        int take_left;
+        if (have_l && have_r) {
+          if (ld != rd) take_left = ld < rd;
+          else if (ix->st[lpos] != ix->st[rp]) take_left = ix->st[lpos] < ix->st[rp];
+          else take_left = ix->row[lpos] < ix->row[rp];
+        } else take_left = have_l;
+        if (take_left) { ob[got] = ix->row[lpos]; od[got] = ld; ++lcur; }
+        else { ob[got] = ix->row[rp]; od[got] = rd; ++rp; }
+        if (++got >= k) break;
+      }
+    }
+    free(buf);
+  }
+}
+
+/* ---- brute force (ground truth for the ground truth; O(N*M); tiny inputs only) ---------- */
+PBO_API int64_t pbo_brute_pairs(const int32_t *lc, const int32_t *ls, const int32_t *le, int64_t n,
+                                const int32_t *rc, const int32_t *rs, const int32_t *re, int64_t m,
+                                int strict, uint32_t *out_probe, uint32_t *out_build, int64_t cap) {
+  int64_t p = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    if (lc[i] < 0) continue;
+    for (int64_t j = 0; j < m; ++j) {
+      if (rc[j] != lc[i]) continue;
+      if (hit(strict, ls[i], le[i], rs[j], re[j])) {
+        if (p < cap && out_probe) { out_probe[p] = (uint32_t)i; out_build[p] = (uint32_t)j; }
+        ++p;
+      }
+    }
+  }
+  return p;
+}
+
+PBO_API int pbo_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
