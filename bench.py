@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py -- overlap-pairs/sec of the interval-join hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port)
+
+Workload at N=1: BASELINE.json configs[1] -- synthetic 10M reads x 1M variants on one contig (chr1,
+L=248,956,422; reads 150 bp uniform seed 1; SNVs 1 bp uniform seed 2; Strict / 0-based), SURVEY.md 8(d).
+One step = one pass of the whole hot path over that batch:
+    index build (contig radix partition + start sort + aux arrays)  ->  count_overlaps (int64 per read)
+    -> overlap pass 1 (count + offsets) -> overlap pass 2 (emit exact-sized (read,variant) pair buffer).
+`value`  : pairs emitted per second with the int32 columns already resident in HBM (CUDA events, L2 flushed
+           between steps).
+`e2e`    : the same through the public host-facing call with HOST buffers: pinned host columns -> H2D ->
+           the same pass -> D2H of the pair buffer and counts, all inside the timed region.
+`roofline`: the dominant kernel's algorithmic bytes / its CUDA-event duration vs the measured HBM copy peak.
+`cpu_baseline`: oracle/ (port of the reference's interval-tree algorithm) on the host cores, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CHR1_LEN = 248_956_422
+METRIC = "overlap-pairs/sec"
+
+
+def make_config2(n_reads: int = 10_000_000, n_variants: int = 1_000_000, seed_shift: int = 0):
+    """BASELINE configs[1] (SURVEY.md 8d 'Config 2')."""
+    r1 = np.random.default_rng(1 + seed_shift)
+    r2 = np.random.default_rng(2 + seed_shift)
+    ps = r1.integers(0, CHR1_LEN - 150, n_reads, dtype=np.int64).astype(np.int32)
+    pe = (ps + 150).astype(np.int32)
+    bs = r2.integers(0, CHR1_LEN - 1, n_variants, dtype=np.int64).astype(np.int32)
+    be = (bs + 1).astype(np.int32)
+    return (np.zeros(n_reads, np.int32), ps, pe), (np.zeros(n_variants, np.int32), bs, be), 1
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(probe, build, nc, sample_reads: int, threads: int, steps: int = 1, warmup: int = 0):
+    """Times the oracle (port of the reference's per-contig interval-tree build + per-row query) on host cores.
+    One step = index build over ALL variants + count_overlaps + full pair emit over `sample_reads` reads."""
+    import oracle
+
+    pc, ps, pe = (x[:sample_reads] for x in probe)
+    times, pairs = [], 0
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        ix = oracle.Index(*build, nc)
+        cnt = ix.count_overlaps(pc, ps, pe, True, threads=threads)
+        a, b = ix.overlap_pairs(pc, ps, pe, True, threads=threads)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+        pairs = len(a)
+        assert int(cnt.sum()) == pairs
+        del ix
+    return pairs, float(np.mean(times))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    import oracle
+
+    n_reads, n_var = args.reads, args.variants
+    probe, build, nc = make_config2(n_reads, n_var)
+    threads = oracle.max_threads()
+    sample = min(n_reads, args.cpu_sample)
+    pairs, sec = cpu_reference_run(probe, build, nc, sample, threads, steps=args.steps, warmup=args.warmup)
+    v = pairs / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": f"config2: {n_reads} reads x {n_var} variants, chr1, Strict; count_overlaps + pair emit",
+                   "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
+                         "sample": f"index over all {n_var} variants + count_overlaps + pair emit for the first {sample} reads per step"},
+        "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--reads", type=int, default=10_000_000)
+    ap.add_argument("--variants", type=int, default=1_000_000)
+    ap.add_argument("--cpu-sample", type=int, default=2_000_000, help="reads per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from polars_bio_b200 import _native, engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback in the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # weak scaling: every rank owns an independent config-2 batch (contigs shard; no data-path collective)
+    probe, build, nc = make_config2(args.reads, args.variants, seed_shift=100 * rank)
+    n, m = args.reads, args.variants
+    h = [torch.from_numpy(x).pin_memory() for x in (*probe, *build)]
+    dpc, dps, dpe, dbc, dbs, dbe = (x.to(dev, non_blocking=True) for x in h)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    torch.cuda.synchronize()
+    FO = engine.FILTER_STRICT
+
+    def step_device(ev=None):
+        ix = engine.DeviceIndex(dbc, dbs, dbe, nc)
+        if ev: ev[1].record()
+        cnt = ix.count_overlaps(dpc, dps, dpe, FO)
+        if ev: ev[2].record()
+        a, b = ix.overlap_pairs(dpc, dps, dpe, FO)
+        if ev: ev[3].record()
+        ix.close()
+        return cnt, a, b
+
+    def step_e2e():
+        c = [x.to(dev, non_blocking=True) for x in h]
+        ix = engine.DeviceIndex(c[3], c[4], c[5], nc)
+        cnt = ix.count_overlaps(c[0], c[1], c[2], FO)
+        a, b = ix.overlap_pairs(c[0], c[1], c[2], FO)
+        ha, hb, hc = a.cpu(), b.cpu(), cnt.cpu()
+        ix.close()
+        return ha.numel(), ha.numel() * 8 + hc.numel() * 8
+
+    for _ in range(max(args.warmup, 3)):
+        cnt, a, b = step_device()
+    pairs = a.numel()
+    assert int(cnt.sum()) == pairs
+    del cnt, a, b
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    launches0 = _native.launch_count()
+    step_ms, stage_ms = [], []
+    for _ in range(args.steps):
+        flush.fill_(1)  # L2 flush, outside the event bracket
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        ev[0].record()
+        cnt, a, b = step_device(ev)
+        ev[4].record()
+        ev[4].synchronize()
+        step_ms.append(ev[0].elapsed_time(ev[4]))
+        stage_ms.append([ev[i].elapsed_time(ev[i + 1]) for i in range(3)])
+        del cnt, a, b
+    launches = _native.launch_count() - launches0
+    barrier()
+    clocks = sampler.stop()
+    total_ms = float(np.sum(step_ms))
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        pt = torch.tensor([pairs], device=dev, dtype=torch.float64)
+        dist.all_reduce(pt, op=dist.ReduceOp.SUM)
+        pairs_all = float(pt.item())
+    else:
+        pairs_all = float(pairs)
+    ms_per_step = total_ms / args.steps
+    value = pairs_all / (ms_per_step * 1e-3)
+
+    # per-kernel roofline: pass 2 (one launch of overlap_emit_kernel per step) and count_overlaps (one launch)
+    stage = np.mean(np.array(stage_ms), axis=0)  # build, count_overlaps, overlap(count+scan+emit)
+    peak, peak_src = measured_peak_gbs()
+
+    # e2e (host buffers, copies inside the timed region)
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        p_e2e, d2h = step_e2e()
+    torch.cuda.synchronize()
+    e2e_sec = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_sec], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_sec = float(t.item())
+    h2d = sum(x.numel() * 4 for x in h)
+
+    # dominant-kernel timing: emit alone, events on the launching stream
+    ix = engine.DeviceIndex(dbc, dbs, dbe, nc)
+    kern = time_kernels(engine, ix, (dpc, dps, dpe), FO, flush, reps=max(5, args.steps))
+    ix.close()
+    b_overlap = 12.0 * (n + m) + 8.0 * pairs
+    b_count = 12.0 * (n + m) + 8.0 * n
+    cands = {
+        "overlap_emit_kernel": (b_overlap, kern["emit_ms"]),
+        "count_overlaps_kernel": (b_count, kern["count_overlaps_ms"]),
+        "overlap_count_kernel": (12.0 * (n + m) + 4.0 * n, kern["pass1_ms"]),
+    }
+    dom = max(cands, key=lambda k: cands[k][1])
+    ach = cands[dom][0] / (cands[dom][1] * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": None, "peak_source": peak_src, "algorithmic_bytes": cands[dom][0], "kernel_ms": cands[dom][1],
+            "all_kernels": {k: {"ms": v[1], "algorithmic_bytes": v[0], "GBps": v[0] / (v[1] * 1e-3) / 1e9} for k, v in cands.items()},
+            "step_stage_ms": {"index_build": float(stage[0]), "count_overlaps": float(stage[1]), "overlap_two_pass": float(stage[2])}}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": f"config2: {n} reads x {m} variants per GPU, chr1, Strict; index build + count_overlaps + two-pass pair emit",
+                   "pairs_per_step": pairs_all, "l2": "flushed between timed steps (256 MiB write)",
+                   "parallelism": f"contig-sharded x{world}" if world > 1 else "single GPU"},
+        "clocks": clocks,
+        "e2e": {"value": pairs_all / e2e_sec, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_sec * 1e3},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle
+
+        thr = oracle.max_threads()
+        sample = min(n, args.cpu_sample)
+        cp, csec = cpu_reference_run(probe, build, nc, sample, thr, steps=1, warmup=0)
+        line["cpu_baseline"] = {"value": cp / csec, "unit": "pairs/s", "cores": thr, "kind": "port",
+                                "sample": f"index over all {m} variants + count_overlaps + pair emit for the first {sample} reads, 1 run ({csec:.2f} s)"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def time_kernels(engine, ix, probe, fo, flush, reps=5):
+    """CUDA-event durations of the single-launch stages on the launching (torch current) stream."""
+    import ctypes
+
+    import torch
+
+    from polars_bio_b200._native import check
+
+    dpc, dps, dpe = probe
+    n = dpc.numel()
+    L = ix._L
+    sp = engine._stream_ptr(ix.device)
+    out = torch.empty(n, dtype=torch.int64, device=ix.device)
+    res = {"count_overlaps_ms": [], "pass1_ms": [], "emit_ms": []}
+    for _ in range(reps + 1):
+        flush.fill_(2)
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        e[0].record()
+        check(L.pbgpu_count_overlaps(ix._h, dpc.data_ptr(), dps.data_ptr(), dpe.data_ptr(), n, fo, out.data_ptr(), sp))
+        e[1].record()
+        flush.fill_(3)
+        plan = ctypes.c_void_p(); total = ctypes.c_int64(0)
+        e[2].record()
+        check(L.pbgpu_overlap_count(ix._h, dpc.data_ptr(), dps.data_ptr(), dpe.data_ptr(), n, fo, sp, ctypes.byref(plan), ctypes.byref(total)))
+        e[3].record()
+        a = torch.empty(total.value, dtype=torch.int32, device=ix.device)
+        b = torch.empty(total.value, dtype=torch.int32, device=ix.device)
+        flush.fill_(4)
+        e[4].record()
+        check(L.pbgpu_overlap_emit(plan, a.data_ptr(), b.data_ptr(), sp))
+        e[5].record()
+        e[5].synchronize()
+        L.pbgpu_overlap_plan_free(plan)
+        res["count_overlaps_ms"].append(e[0].elapsed_time(e[1]))
+        res["pass1_ms"].append(e[2].elapsed_time(e[3]))
+        res["emit_ms"].append(e[4].elapsed_time(e[5]))
+    return {k: float(np.mean(v[1:])) for k, v in res.items()}
+
+
+if __name__ == "__main__":
+    main()

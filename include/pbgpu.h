@@ -1,0 +1,183 @@
+/*
+ * pbgpu.h -- C ABI of libpbgpu.so, the B200-native interval-join engine.
+ *
+ * This is the drop-in boundary for the reference's hot path:
+ * the three providers that polars-bio's plan builder constructs from the un-vendored crate
+ * datafusion-bio-function-ranges v0.11.0,
+ *     OverlapProvider::new_with_output_mode   /root/reference/src/operation.rs:253-263
+ *     NearestProvider::new                    /root/reference/src/operation.rs:146-158
+ *     CountOverlapsProvider::new              /root/reference/src/operation.rs:331-340
+ * and the PyO3 entry points above them,
+ *     range_operation_frame / _lazy / _scan   /root/reference/src/lib.rs:79-88,154-166,216-228.
+ * Plain pointers and sizes only: no torch / Arrow C++ / STL types cross this boundary.
+ * Every function returns 0 on success or a PBGPU_E* code; pbgpu_last_error() has the text.
+ * Nothing here aborts or throws (the reference's .unwrap() panics, operation.rs:106-107,269,
+ * are not reproduced).
+ *
+ * Two levels:
+ *   (1) device level  -- columns already resident in HBM (int32 contig code, start, end);
+ *                        what a long-lived Rust ExecutionPlan or torch caller drives, and what
+ *                        bench.py's `value` times.
+ *   (2) Arrow level   -- ArrowArrayStream in, ArrowArrayStream out (host buffers, H2D/D2H
+ *                        inside); what range_operation_frame binds; bench.py's `e2e`.
+ *
+ * Enum values mirror /root/reference/src/option.rs:89-112.
+ */
+#ifndef PBGPU_H
+#define PBGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBGPU_API __attribute__((visibility("default")))
+
+/* ---- status codes ---------------------------------------------------------------------- */
+#define PBGPU_OK 0
+#define PBGPU_EINVAL 1   /* bad argument / unsupported option                                 */
+#define PBGPU_ECUDA 2    /* CUDA runtime error (text in pbgpu_last_error)                      */
+#define PBGPU_ENOMEM 3   /* device or host allocation failed                                  */
+#define PBGPU_ERANGE 4   /* coordinate outside the int32 domain (reference limit,             */
+                         /* docs/features/operations.md:37) or > 2^32-1 rows                  */
+#define PBGPU_ESCHEMA 5  /* Arrow schema problem: missing column, unsupported type            */
+#define PBGPU_ESTREAM 6  /* an input ArrowArrayStream callback failed                         */
+
+/* ---- option enums (src/option.rs) ------------------------------------------------------ */
+enum { PBGPU_FILTER_WEAK = 0, PBGPU_FILTER_STRICT = 1 };             /* option.rs:96-99   */
+enum { PBGPU_OP_OVERLAP = 0, PBGPU_OP_NEAREST = 3, PBGPU_OP_COVERAGE = 4,
+       PBGPU_OP_COUNT_OVERLAPS_NAIVE = 6 };                           /* option.rs:103-112 */
+enum { PBGPU_OUT_JOIN = 0, PBGPU_OUT_LEFT = 1, PBGPU_OUT_LEFT_DISTINCT = 2 }; /* operation.rs:229-233 */
+
+#define PBGPU_NO_PARTNER 0xFFFFFFFFu
+
+PBGPU_API const char *pbgpu_last_error(void);          /* thread-local, never NULL            */
+PBGPU_API const char *pbgpu_version(void);
+PBGPU_API int pbgpu_device_count(int *count);
+/* number of this library's kernels launched by the calling process so far (bench evidence) */
+PBGPU_API uint64_t pbgpu_launch_count(void);
+
+/* =========================================================================================
+ * (1) Device level.  All d_* pointers are device memory on the current CUDA device; `stream`
+ * is a cudaStream_t passed as void* (NULL = legacy default stream).  Work is enqueued on
+ * `stream`; functions that return a host scalar synchronise that stream before returning.
+ * Rows whose contig code is < 0 or >= n_contigs are null-keyed: they never match.
+ * Row ids are uint32 (at most 2^32-2 rows per table).
+ * ========================================================================================= */
+
+/* Search structure over the indexed ("build") table -- replaces the per-contig COITrees that
+ * OverlapProvider / NearestProvider / CountOverlapsProvider build from their indexed side.
+ * Layout in HBM: rows radix-partitioned by contig and sorted by start (st, en, row), the
+ * running maximum of `en` per contig (window lower bound), and the ends sorted per contig
+ * (rank identity, nearest upstream candidate).                                              */
+typedef struct pbgpu_index pbgpu_index;
+
+PBGPU_API int pbgpu_index_build(const int32_t *d_contig, const int32_t *d_start, const int32_t *d_end,
+                                int64_t m, int32_t n_contigs, void *stream, pbgpu_index **out);
+PBGPU_API void pbgpu_index_free(pbgpu_index *ix);
+PBGPU_API int64_t pbgpu_index_rows(const pbgpu_index *ix);     /* rows kept (non-null keys)   */
+PBGPU_API size_t pbgpu_index_bytes(const pbgpu_index *ix);     /* HBM held by the index       */
+
+/* CountOverlapsProvider (operation.rs:331-340), coverage=false: for every iterated row the
+ * number of indexed rows on the same contig satisfying the FilterOp predicate
+ * (docs/developers.md:549-552).  d_counts: int64[n] (the reference's `count` column type,
+ * range_op_helpers.py:315-316).                                                             */
+PBGPU_API int pbgpu_count_overlaps(const pbgpu_index *ix, const int32_t *d_contig, const int32_t *d_start,
+                                   const int32_t *d_end, int64_t n, int filter_op, int64_t *d_counts,
+                                   void *stream);
+
+/* CountOverlapsProvider, coverage=true: positions of every iterated row covered by the union
+ * of the indexed rows (Strict: half-open lengths; Weak: closed lengths).  int64[n].         */
+PBGPU_API int pbgpu_coverage(const pbgpu_index *ix, const int32_t *d_contig, const int32_t *d_start,
+                             const int32_t *d_end, int64_t n, int filter_op, int64_t *d_coverage,
+                             void *stream);
+
+/* OverlapProvider (operation.rs:253-263) as two passes so the pair buffer is exact-sized:
+ *   pass 1  pbgpu_overlap_count  -> plan + total number of pairs (host scalar; syncs stream)
+ *   pass 2  pbgpu_overlap_emit   -> (probe_row, build_row) uint32 pairs, SoA, ordered by
+ *                                   probe row, then by (start, row) of the indexed partner.
+ * The plan borrows the probe columns and the index: keep them alive until the plan is freed. */
+typedef struct pbgpu_overlap_plan pbgpu_overlap_plan;
+
+PBGPU_API int pbgpu_overlap_count(const pbgpu_index *ix, const int32_t *d_contig, const int32_t *d_start,
+                                  const int32_t *d_end, int64_t n, int filter_op, void *stream,
+                                  pbgpu_overlap_plan **plan, int64_t *total_pairs);
+PBGPU_API int pbgpu_overlap_emit(const pbgpu_overlap_plan *plan, uint32_t *d_probe_rows,
+                                 uint32_t *d_build_rows, void *stream);
+/* per-probe pair counts of pass 1 (uint32[n], device; valid until the plan is freed) -- the
+ * Left / LeftDistinct output modes (operation.rs:229-233) are filters over these.           */
+PBGPU_API const uint32_t *pbgpu_overlap_plan_counts(const pbgpu_overlap_plan *plan);
+PBGPU_API void pbgpu_overlap_plan_free(pbgpu_overlap_plan *plan);
+
+/* NearestProvider (operation.rs:146-158): for every iterated row up to k indexed rows of the
+ * same contig ordered by (overlapping first when include_overlaps, distance, start, row);
+ * distance = 0 for overlapping partners else max(b.start-a.end, a.start-b.end) (>= 0)
+ * (tests/_expected.py:162).  d_partner: uint32[n*k] (PBGPU_NO_PARTNER = none),
+ * d_distance: int64[n*k] (-1 = none) or NULL when compute_distance is off.                  */
+PBGPU_API int pbgpu_nearest(const pbgpu_index *ix, const int32_t *d_contig, const int32_t *d_start,
+                            const int32_t *d_end, int64_t n, int filter_op, int64_t k, int include_overlaps,
+                            uint32_t *d_partner, int64_t *d_distance, void *stream);
+
+/* Multi-GPU plumbing: bucket rows by owning rank before the NCCL all-to-all.
+ * d_owner: int32[n_contigs] contig -> rank table.  Writes per-rank row counts into
+ * d_rank_counts (int64[n_ranks]) and, stably grouped by destination rank, 16-byte records
+ * (contig, start, end, row_id_base + row) into d_packed (int32[4*n]; only the first
+ * sum(d_rank_counts) records are meaningful -- null-keyed rows sort behind them).           */
+PBGPU_API int pbgpu_pack_by_owner(const int32_t *d_contig, const int32_t *d_start, const int32_t *d_end,
+                                  int64_t n, const int32_t *d_owner, int32_t n_contigs, int32_t n_ranks,
+                                  uint32_t row_id_base, int32_t *d_packed, int64_t *d_rank_counts,
+                                  void *stream);
+
+/* CUDA-event timings (ns) of the stages of the most recent index build / overlap on this
+ * thread when PBGPU_PROFILE=1 is set in the environment; zeros otherwise.                   */
+typedef struct {
+  uint64_t partition_sort_ns; /* contig radix partition + start sort + aux arrays            */
+  uint64_t count_ns;          /* pass 1                                                      */
+  uint64_t scan_ns;           /* offsets                                                     */
+  uint64_t emit_ns;           /* pass 2                                                      */
+} pbgpu_stage_times;
+PBGPU_API int pbgpu_last_stage_times(pbgpu_stage_times *out);
+
+/* =========================================================================================
+ * (2) Arrow level -- the binding target of range_operation_frame / _lazy (src/lib.rs:79-88,
+ * 154-166) and of a DataFusion ExecutionPlan adapter.
+ * Arrow C Data / C Stream Interface structs as defined by the Arrow specification.
+ * ========================================================================================= */
+struct ArrowArrayStream;
+
+typedef struct {                 /* mirrors RangeOptions, src/option.rs:8-41                  */
+  int32_t range_op;              /* PBGPU_OP_*                                                */
+  int32_t filter_op;             /* PBGPU_FILTER_*                                            */
+  int32_t output_mode;           /* PBGPU_OUT_* (overlap only)                                */
+  int32_t emit;                  /* 0 = materialised rows (reference column contract,        */
+                                 /*     operation.rs:170-195,272-299); 1 = index pairs:       */
+                                 /*     overlap -> (left_row u32, right_row u32)              */
+                                 /*     nearest -> (left_row u32, right_row u32 nullable,     */
+                                 /*                 distance i64 nullable)                    */
+  const char *cols1[3];          /* contig, start, end column names of `left`  (columns_1)    */
+  const char *cols2[3];          /* contig, start, end column names of `right` (columns_2)    */
+  const char *suffixes[2];       /* NULL -> "_1","_2"                                         */
+  uint64_t nearest_k;            /* 0 -> 1                                                    */
+  int32_t include_overlaps;      /* nearest                                                   */
+  int32_t compute_distance;      /* nearest                                                   */
+  uint64_t limit;                /* 0 = none (src/lib.rs:120-131)                             */
+  uint32_t max_batch_rows;       /* 0 -> 1<<20; low_memory / batch_size cap (range_op.py:168) */
+  int32_t device;                /* CUDA device ordinal, -1 = current                         */
+} PbRangeOptions;
+
+/* `left` / `right` are df1 / df2 exactly as the Python facade passes them to
+ * range_operation_frame (so for count_overlaps / coverage the facade has already swapped
+ * them, range_op.py:407-409,511; for nearest the engine swaps roles internally the way
+ * do_nearest does, operation.rs:143-158).
+ * Ownership: the callee MOVES left/right (calls their release exactly once, on the calling
+ * thread, before returning -- the GIL rule of src/lib.rs:63-72); the caller owns `out` and
+ * calls out->release.  out->get_next may be called from another thread, not concurrently.   */
+PBGPU_API int pbgpu_range_op(struct ArrowArrayStream *left, struct ArrowArrayStream *right,
+                             const PbRangeOptions *opts, struct ArrowArrayStream *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBGPU_H */

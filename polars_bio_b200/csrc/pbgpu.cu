@@ -1,0 +1,414 @@
+// pbgpu.cu -- device-level C ABI of libpbgpu.so (see include/pbgpu.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 (see __graft_entry__.build()).
+#include <stdarg.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "index.cuh"
+#include "radix_sort.cuh"
+#include "scan.cuh"
+#include "sweep.cuh"
+
+namespace pbgpu {
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+static thread_local pbgpu_stage_times g_times = {0, 0, 0, 0};
+
+int set_error(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+static bool profiling() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("PBGPU_PROFILE");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+static std::once_flag g_pool_once[64];
+static void tune_pool(int dev) {
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;  // keep freed scratch cached in the pool between calls
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+}
+
+int dev_alloc(void **p, size_t bytes, cudaStream_t s) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64) std::call_once(g_pool_once[dev], tune_pool, dev);
+  cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 1, s);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(e == cudaErrorMemoryAllocation ? PBGPU_ENOMEM : PBGPU_ECUDA, "cudaMallocAsync(%zu) failed: %s", bytes,
+                     cudaGetErrorString(e));
+  }
+  return PBGPU_OK;
+}
+void dev_free(void *p, cudaStream_t s) {
+  if (p) cudaFreeAsync(p, s);
+}
+
+// CUDA-event stage timer (only when PBGPU_PROFILE=1; otherwise no events are created)
+struct StageTimer {
+  cudaStream_t s;
+  cudaEvent_t a = nullptr, b = nullptr;
+  bool on;
+  explicit StageTimer(cudaStream_t st) : s(st), on(profiling()) {
+    if (on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s); }
+  }
+  uint64_t stop_ns() {
+    if (!on) return 0;
+    cudaEventRecord(b, s);
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventRecord(a, s);
+    return (uint64_t)(ms * 1e6);
+  }
+  ~StageTimer() {
+    if (on) { cudaEventDestroy(a); cudaEventDestroy(b); }
+  }
+};
+
+}  // namespace pbgpu
+
+using namespace pbgpu;
+
+extern "C" {
+
+const char *pbgpu_last_error(void) { return g_err; }
+const char *pbgpu_version(void) { return "pbgpu 0.1.0 (sm_100a)"; }
+uint64_t pbgpu_launch_count(void) { return g_launches.load(); }
+
+int pbgpu_device_count(int *count) {
+  if (!count) return set_error(PBGPU_EINVAL, "count is NULL");
+  PB_CUDA(cudaGetDeviceCount(count));
+  return PBGPU_OK;
+}
+
+int pbgpu_last_stage_times(pbgpu_stage_times *out) {
+  if (!out) return set_error(PBGPU_EINVAL, "out is NULL");
+  *out = g_times;
+  return PBGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+void pbgpu_index_free(pbgpu_index *ix) {
+  if (!ix) return;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (cur != ix->device) cudaSetDevice(ix->device);
+  cudaFree(ix->seg); cudaFree(ix->st); cudaFree(ix->en); cudaFree(ix->pmax);
+  cudaFree(ix->en_sorted); cudaFree(ix->row); cudaFree(ix->en_pos);
+  if (cur != ix->device) cudaSetDevice(cur);
+  delete ix;
+}
+
+int64_t pbgpu_index_rows(const pbgpu_index *ix) { return ix ? ix->m : 0; }
+size_t pbgpu_index_bytes(const pbgpu_index *ix) { return ix ? ix->bytes : 0; }
+
+static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *d_s, const int32_t *d_e, int64_t m_in,
+                            int32_t n_contigs, cudaStream_t s) {
+  ix->m_in = m_in;
+  ix->n_contigs = n_contigs;
+  PB_CUDA(cudaGetDevice(&ix->device));
+  PB_CUDA(cudaMalloc(&ix->seg, sizeof(int32_t) * ((size_t)n_contigs + 2)));
+  ix->bytes = sizeof(int32_t) * ((size_t)n_contigs + 2);
+  if (m_in == 0) {
+    PB_CUDA(cudaMemsetAsync(ix->seg, 0, sizeof(int32_t) * ((size_t)n_contigs + 2), s));
+    return PBGPU_OK;
+  }
+  StageTimer tm(s);
+  Scratch sc(s);
+  // 1. domain of the coordinates (decides key width and whether the rank identity is safe)
+  BuildStats *d_stats = nullptr;
+  PB_TRY(sc.get(&d_stats, 1));
+  BuildStats h0 = {INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN, 0ull, 0ull};
+  PB_CUDA(cudaMemcpyAsync(d_stats, &h0, sizeof(h0), cudaMemcpyHostToDevice, s));
+  {
+    int64_t grid = cdiv(m_in, 256);
+    if (grid > kSMs * 16) grid = kSMs * 16;
+    PB_LAUNCH(build_stats_kernel, (unsigned)grid, 256, 0, s, d_c, d_s, d_e, m_in, n_contigs, d_stats);
+    PB_CHECK_LAUNCH();
+  }
+  BuildStats hs;
+  PB_CUDA(cudaMemcpyAsync(&hs, d_stats, sizeof(hs), cudaMemcpyDeviceToHost, s));
+  PB_CUDA(cudaStreamSynchronize(s));
+  const int64_t m = (int64_t)hs.valid;
+  ix->m = m;
+  ix->has_inverted = hs.inverted != 0;
+  if (m == 0) {
+    PB_CUDA(cudaMemsetAsync(ix->seg, 0, sizeof(int32_t) * ((size_t)n_contigs + 2), s));
+    return PBGPU_OK;
+  }
+  const int mn = hs.min_start < hs.min_end ? hs.min_start : hs.min_end;
+  const int mx = hs.max_start > hs.max_end ? hs.max_start : hs.max_end;
+  uint32_t bias = 0;
+  int pos_bits;
+  if (mn >= 0) { pos_bits = bit_length_u32((uint32_t)mx); if (pos_bits < 1) pos_bits = 1; }
+  else { bias = 0x80000000u; pos_bits = 32; }
+  const int contig_bits = bit_length_u32((uint32_t)n_contigs);  // codes 0..n_contigs (sentinel included)
+
+  // 2. radix partition by contig + sort by start: one stable LSD sort of (contig|start) keys
+  uint64_t *keys = nullptr, *vals = nullptr;
+  PB_TRY(sc.get(&keys, (size_t)m_in));
+  PB_TRY(sc.get(&vals, (size_t)m_in));
+  PB_LAUNCH(make_start_keys_kernel, (unsigned)cdiv(m_in, 256), 256, 0, s, d_c, d_s, d_e, m_in, n_contigs, pos_bits, bias, keys, vals);
+  PB_CHECK_LAUNCH();
+  PB_TRY(radix_sort_pairs(keys, vals, m_in, pos_bits + contig_bits, s));
+  PB_LAUNCH(find_segments_kernel, (unsigned)cdiv(n_contigs + 1, 64), 64, 0, s, keys, m_in, pos_bits, n_contigs, ix->seg);
+  PB_CHECK_LAUNCH();
+
+  // 3. unpack + auxiliary arrays
+  const size_t mb = sizeof(int32_t) * (size_t)m;
+  PB_CUDA(cudaMalloc(&ix->st, mb)); PB_CUDA(cudaMalloc(&ix->en, mb)); PB_CUDA(cudaMalloc(&ix->pmax, mb));
+  PB_CUDA(cudaMalloc(&ix->en_sorted, mb)); PB_CUDA(cudaMalloc(&ix->row, mb)); PB_CUDA(cudaMalloc(&ix->en_pos, mb));
+  ix->bytes += 6 * mb;
+  uint64_t *pm_keys = nullptr, *ekeys = nullptr, *evals = nullptr;
+  PB_TRY(sc.get(&pm_keys, (size_t)m));
+  PB_TRY(sc.get(&ekeys, (size_t)m));
+  PB_TRY(sc.get(&evals, (size_t)m));
+  PB_LAUNCH(unpack_sorted_kernel, (unsigned)cdiv(m, 256), 256, 0, s, keys, vals, m, pos_bits, bias, bias, ix->st, ix->en, ix->row,
+            pm_keys, ekeys, evals);
+  PB_CHECK_LAUNCH();
+  PB_TRY((device_scan<MaxU64, true>((const unsigned long long *)pm_keys, (unsigned long long *)pm_keys, m, nullptr, s)));
+  PB_LAUNCH(unpack_pmax_kernel, (unsigned)cdiv(m, 256), 256, 0, s, pm_keys, m, ix->pmax);
+  PB_CHECK_LAUNCH();
+  // 4. ends sorted per contig (stable over the start order -> ties keep (start,row) order)
+  PB_TRY(radix_sort_pairs(ekeys, evals, m, pos_bits + contig_bits, s));
+  PB_LAUNCH(unpack_ends_kernel, (unsigned)cdiv(m, 256), 256, 0, s, ekeys, evals, m, pos_bits, bias, ix->en_sorted, ix->en_pos);
+  PB_CHECK_LAUNCH();
+  g_times.partition_sort_ns = tm.stop_ns();
+  return PBGPU_OK;
+}
+
+int pbgpu_index_build(const int32_t *d_contig, const int32_t *d_start, const int32_t *d_end, int64_t m, int32_t n_contigs,
+                      void *stream, pbgpu_index **out) {
+  if (!out) return set_error(PBGPU_EINVAL, "out is NULL");
+  *out = nullptr;
+  if (m < 0 || n_contigs < 0) return set_error(PBGPU_EINVAL, "negative size");
+  if (m > 0 && (!d_contig || !d_start || !d_end)) return set_error(PBGPU_EINVAL, "NULL column");
+  if (m >= (int64_t)INT32_MAX) return set_error(PBGPU_ERANGE, "indexed table has %lld rows; limit is 2^31-2", (long long)m);
+  if (n_contigs >= (1 << 30)) return set_error(PBGPU_ERANGE, "too many contigs");
+  pbgpu_index *ix = new (std::nothrow) pbgpu_index();
+  if (!ix) return set_error(PBGPU_ENOMEM, "host allocation failed");
+  int rc = index_build_impl(ix, d_contig, d_start, d_end, m, n_contigs, (cudaStream_t)stream);
+  if (rc != PBGPU_OK) {
+    pbgpu_index_free(ix);
+    return rc;
+  }
+  *out = ix;
+  return PBGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int check_probe_args(const pbgpu_index *ix, const int32_t *c, const int32_t *s, const int32_t *e, int64_t n, int filter_op) {
+  if (!ix) return set_error(PBGPU_EINVAL, "index is NULL");
+  if (n < 0) return set_error(PBGPU_EINVAL, "negative row count");
+  if (n > 0 && (!c || !s || !e)) return set_error(PBGPU_EINVAL, "NULL column");
+  if (n >= 0xFFFFFFFFll) return set_error(PBGPU_ERANGE, "iterated table has %lld rows; limit is 2^32-2", (long long)n);
+  if (filter_op != PBGPU_FILTER_WEAK && filter_op != PBGPU_FILTER_STRICT) return set_error(PBGPU_EINVAL, "bad filter_op %d", filter_op);
+  return PBGPU_OK;
+}
+
+int pbgpu_count_overlaps(const pbgpu_index *ix, const int32_t *d_contig, const int32_t *d_start, const int32_t *d_end, int64_t n,
+                         int filter_op, int64_t *d_counts, void *stream) {
+  PB_TRY(check_probe_args(ix, d_contig, d_start, d_end, n, filter_op));
+  if (n == 0) return PBGPU_OK;
+  if (!d_counts) return set_error(PBGPU_EINVAL, "d_counts is NULL");
+  cudaStream_t s = (cudaStream_t)stream;
+  StageTimer tm(s);
+  const unsigned grid = (unsigned)cdiv(n, kSweepThreads);
+  if (filter_op == PBGPU_FILTER_STRICT)
+    PB_LAUNCH(count_overlaps_kernel<true>, grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, d_counts);
+  else
+    PB_LAUNCH(count_overlaps_kernel<false>, grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, d_counts);
+  PB_CHECK_LAUNCH();
+  g_times.count_ns = tm.stop_ns();
+  return PBGPU_OK;
+}
+
+int pbgpu_coverage(const pbgpu_index *ix, const int32_t *d_contig, const int32_t *d_start, const int32_t *d_end, int64_t n,
+                   int filter_op, int64_t *d_coverage, void *stream) {
+  PB_TRY(check_probe_args(ix, d_contig, d_start, d_end, n, filter_op));
+  if (n == 0) return PBGPU_OK;
+  if (!d_coverage) return set_error(PBGPU_EINVAL, "d_coverage is NULL");
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)cdiv(n, kSweepThreads);
+  if (filter_op == PBGPU_FILTER_STRICT)
+    PB_LAUNCH(coverage_kernel<true>, grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, d_coverage);
+  else
+    PB_LAUNCH(coverage_kernel<false>, grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, d_coverage);
+  PB_CHECK_LAUNCH();
+  return PBGPU_OK;
+}
+
+}  // extern "C"
+
+struct pbgpu_overlap_plan {
+  const pbgpu_index *ix;
+  const int32_t *pc, *ps, *pe;
+  int64_t n;
+  int filter_op;
+  int device;
+  int64_t nblk;
+  uint32_t *counts;                 // [n]
+  unsigned long long *block_base;   // [nblk] exclusive-scanned block totals
+  int64_t total;
+};
+
+extern "C" {
+
+void pbgpu_overlap_plan_free(pbgpu_overlap_plan *p) {
+  if (!p) return;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (cur != p->device) cudaSetDevice(p->device);
+  cudaFree(p->counts);
+  cudaFree(p->block_base);
+  if (cur != p->device) cudaSetDevice(cur);
+  delete p;
+}
+
+const uint32_t *pbgpu_overlap_plan_counts(const pbgpu_overlap_plan *plan) { return plan ? plan->counts : nullptr; }
+
+int pbgpu_overlap_count(const pbgpu_index *ix, const int32_t *d_contig, const int32_t *d_start, const int32_t *d_end, int64_t n,
+                        int filter_op, void *stream, pbgpu_overlap_plan **plan, int64_t *total_pairs) {
+  PB_TRY(check_probe_args(ix, d_contig, d_start, d_end, n, filter_op));
+  if (!plan || !total_pairs) return set_error(PBGPU_EINVAL, "plan/total_pairs is NULL");
+  *plan = nullptr;
+  *total_pairs = 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  pbgpu_overlap_plan *p = new (std::nothrow) pbgpu_overlap_plan();
+  if (!p) return set_error(PBGPU_ENOMEM, "host allocation failed");
+  *p = pbgpu_overlap_plan{ix, d_contig, d_start, d_end, n, filter_op, 0, cdiv(n, kSweepThreads), nullptr, nullptr, 0};
+  cudaGetDevice(&p->device);
+  auto fail = [&](int rc) { pbgpu_overlap_plan_free(p); return rc; };
+  if (n == 0) { *plan = p; return PBGPU_OK; }
+  if (cudaMalloc(&p->counts, sizeof(uint32_t) * (size_t)n) != cudaSuccess ||
+      cudaMalloc(&p->block_base, sizeof(unsigned long long) * (size_t)(p->nblk + 1)) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(set_error(PBGPU_ENOMEM, "cudaMalloc for overlap plan failed (n=%lld)", (long long)n));
+  }
+  StageTimer tm(s);
+  const unsigned grid = (unsigned)p->nblk;
+  if (filter_op == PBGPU_FILTER_STRICT)
+    PB_LAUNCH(overlap_count_kernel<true>, grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->block_base);
+  else
+    PB_LAUNCH(overlap_count_kernel<false>, grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->block_base);
+  if (cudaGetLastError() != cudaSuccess) return fail(set_error(PBGPU_ECUDA, "overlap_count_kernel launch failed"));
+  g_times.count_ns = tm.stop_ns();
+  unsigned long long *d_total = p->block_base + p->nblk;
+  int rc = device_scan<SumU64, false>(p->block_base, p->block_base, p->nblk, d_total, s);
+  if (rc != PBGPU_OK) return fail(rc);
+  unsigned long long h_total = 0;
+  if (cudaMemcpyAsync(&h_total, d_total, sizeof(h_total), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+      cudaStreamSynchronize(s) != cudaSuccess)
+    return fail(set_error(PBGPU_ECUDA, "overlap pass 1 failed: %s", cudaGetErrorString(cudaGetLastError())));
+  g_times.scan_ns = tm.stop_ns();
+  p->total = (int64_t)h_total;
+  *total_pairs = p->total;
+  *plan = p;
+  return PBGPU_OK;
+}
+
+int pbgpu_overlap_emit(const pbgpu_overlap_plan *p, uint32_t *d_probe_rows, uint32_t *d_build_rows, void *stream) {
+  if (!p) return set_error(PBGPU_EINVAL, "plan is NULL");
+  if (p->n == 0 || p->total == 0) return PBGPU_OK;
+  if (!d_probe_rows || !d_build_rows) return set_error(PBGPU_EINVAL, "output buffer is NULL");
+  cudaStream_t s = (cudaStream_t)stream;
+  StageTimer tm(s);
+  const unsigned grid = (unsigned)p->nblk;
+  if (p->filter_op == PBGPU_FILTER_STRICT)
+    PB_LAUNCH(overlap_emit_kernel<true>, grid, kSweepThreads, 0, s, view_of(p->ix), p->pc, p->ps, p->pe, p->n, p->counts,
+              p->block_base, d_probe_rows, d_build_rows);
+  else
+    PB_LAUNCH(overlap_emit_kernel<false>, grid, kSweepThreads, 0, s, view_of(p->ix), p->pc, p->ps, p->pe, p->n, p->counts,
+              p->block_base, d_probe_rows, d_build_rows);
+  PB_CHECK_LAUNCH();
+  g_times.emit_ns = tm.stop_ns();
+  return PBGPU_OK;
+}
+
+int pbgpu_nearest(const pbgpu_index *ix, const int32_t *d_contig, const int32_t *d_start, const int32_t *d_end, int64_t n,
+                  int filter_op, int64_t k, int include_overlaps, uint32_t *d_partner, int64_t *d_distance, void *stream) {
+  PB_TRY(check_probe_args(ix, d_contig, d_start, d_end, n, filter_op));
+  if (k < 1) return set_error(PBGPU_EINVAL, "k must be >= 1");
+  if (n == 0) return PBGPU_OK;
+  if (!d_partner) return set_error(PBGPU_EINVAL, "d_partner is NULL");
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)cdiv(n, kSweepThreads);
+  if (filter_op == PBGPU_FILTER_STRICT)
+    PB_LAUNCH(nearest_kernel<true>, grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, k, include_overlaps,
+              d_partner, d_distance);
+  else
+    PB_LAUNCH(nearest_kernel<false>, grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, k, include_overlaps,
+              d_partner, d_distance);
+  PB_CHECK_LAUNCH();
+  return PBGPU_OK;
+}
+
+}  // extern "C"
+
+// ---- multi-GPU plumbing: bucket rows by owning rank ---------------------------------------------
+namespace pbgpu {
+
+__global__ void __launch_bounds__(256) owner_keys_kernel(const int32_t *__restrict__ c, int64_t n, const int32_t *__restrict__ owner,
+                                                         int32_t n_contigs, int32_t n_ranks, uint64_t *__restrict__ keys,
+                                                         uint64_t *__restrict__ vals, unsigned long long *__restrict__ rank_counts) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int32_t cc = c[i];
+  int32_t r = (cc >= 0 && cc < n_contigs) ? owner[cc] : n_ranks;
+  if (r < 0 || r > n_ranks) r = n_ranks;
+  keys[i] = (uint64_t)r;
+  vals[i] = (uint64_t)i;
+  if (r < n_ranks) atomicAdd(rank_counts + r, 1ull);
+}
+
+__global__ void __launch_bounds__(256) pack_records_kernel(const uint64_t *__restrict__ perm, int64_t kept, const int32_t *__restrict__ c,
+                                                           const int32_t *__restrict__ s, const int32_t *__restrict__ e,
+                                                           uint32_t row_id_base, int4 *__restrict__ packed) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kept) return;
+  const uint64_t r = perm[i];
+  packed[i] = make_int4(c[r], s[r], e[r], (int)(row_id_base + (uint32_t)r));
+}
+
+}  // namespace pbgpu
+
+extern "C" int pbgpu_pack_by_owner(const int32_t *d_contig, const int32_t *d_start, const int32_t *d_end, int64_t n,
+                                   const int32_t *d_owner, int32_t n_contigs, int32_t n_ranks, uint32_t row_id_base,
+                                   int32_t *d_packed, int64_t *d_rank_counts, void *stream) {
+  if (n < 0 || n_ranks < 1 || n_ranks > 255) return set_error(PBGPU_EINVAL, "bad n / n_ranks");
+  if (!d_rank_counts || !d_owner) return set_error(PBGPU_EINVAL, "NULL argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  PB_CUDA(cudaMemsetAsync(d_rank_counts, 0, sizeof(int64_t) * (size_t)n_ranks, s));
+  if (n == 0) return PBGPU_OK;
+  Scratch sc(s);
+  uint64_t *keys = nullptr, *vals = nullptr;
+  PB_TRY(sc.get(&keys, (size_t)n));
+  PB_TRY(sc.get(&vals, (size_t)n));
+  PB_LAUNCH(owner_keys_kernel, (unsigned)cdiv(n, 256), 256, 0, s, d_contig, n, d_owner, n_contigs, n_ranks, keys, vals,
+            (unsigned long long *)d_rank_counts);
+  PB_CHECK_LAUNCH();
+  PB_TRY(radix_sort_pairs(keys, vals, n, 8, s));
+  if (d_packed) {
+    // kept rows = everything whose key < n_ranks; they sit at the front after the sort, so packing all n
+    // rows is safe only up to `kept`; compute it from the counts on the host side of the caller, or pack
+    // the full prefix here: the caller allocates 4*n int32 and reads only sum(rank_counts) records.
+    PB_LAUNCH(pack_records_kernel, (unsigned)cdiv(n, 256), 256, 0, s, vals, n, d_contig, d_start, d_end, row_id_base, (int4 *)d_packed);
+    PB_CHECK_LAUNCH();
+  }
+  return PBGPU_OK;
+}

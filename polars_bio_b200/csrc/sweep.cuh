@@ -1,0 +1,264 @@
+// sweep.cuh -- probe-side kernels: count (pass 1), emit (pass 2), count_overlaps, coverage,
+// nearest.  One thread per probe row, coalesced int32 loads of (contig,start,end); every
+// search is bounded to the probe's contig segment of the index.
+//
+// Predicate (docs/developers.md:549-552), never rewritten as end+1 (int32 domain):
+//   Strict  hit <=> b.start <  a.end && b.end >  a.start
+//   Weak    hit <=> b.start <= a.end && b.end >= a.start
+#pragma once
+#include "common.cuh"
+#include "index.cuh"
+#include "scan.cuh"
+
+namespace pbgpu {
+
+constexpr int kSweepThreads = 256;
+constexpr int kHeavyWindow = 64;  // windows at least this long are walked by the whole warp
+
+template <bool STRICT>
+__device__ __forceinline__ bool end_hits(int32_t b_end, int32_t a_start) {
+  return STRICT ? (b_end > a_start) : (b_end >= a_start);
+}
+template <bool STRICT>
+__device__ __forceinline__ bool is_hit(int32_t as, int32_t ae, int32_t bs, int32_t be) {
+  return STRICT ? (as < be && ae > bs) : (as <= be && ae >= bs);
+}
+
+// Candidate window [lo,hi) of a probe in (st,en,row) order: hi = first start past the probe
+// end, lo = first position whose running max end reaches past the probe start.
+template <bool STRICT>
+__device__ __forceinline__ void probe_window(const IndexView &ix, int32_t seg_lo, int32_t seg_hi, int32_t s, int32_t e,
+                                             int32_t &lo, int32_t &hi) {
+  hi = STRICT ? lower_bound_i32(ix.st, seg_lo, seg_hi, e) : upper_bound_i32(ix.st, seg_lo, seg_hi, e);
+  lo = STRICT ? upper_bound_i32(ix.pmax, seg_lo, hi, s) : lower_bound_i32(ix.pmax, seg_lo, hi, s);
+}
+
+template <bool STRICT>
+__device__ __forceinline__ uint32_t probe_count(const IndexView &ix, int32_t c, int32_t s, int32_t e) {
+  if (c < 0 || c >= ix.n_contigs) return 0;
+  const int32_t seg_lo = ix.seg[c], seg_hi = ix.seg[c + 1];
+  if (seg_lo >= seg_hi) return 0;
+  const bool proper = STRICT ? (s < e) : (s <= e);
+  if (proper && !ix.has_inverted) {
+    // rank identity: every indexed row ending before the probe starts also starts before it ends
+    const int32_t hi = STRICT ? lower_bound_i32(ix.st, seg_lo, seg_hi, e) : upper_bound_i32(ix.st, seg_lo, seg_hi, e);
+    const int32_t re = STRICT ? upper_bound_i32(ix.en_sorted, seg_lo, seg_hi, s) : lower_bound_i32(ix.en_sorted, seg_lo, seg_hi, s);
+    return (uint32_t)(hi - re);
+  }
+  int32_t lo, hi;
+  probe_window<STRICT>(ix, seg_lo, seg_hi, s, e, lo, hi);
+  uint32_t n = 0;
+  for (int32_t j = lo; j < hi; ++j) n += end_hits<STRICT>(__ldg(ix.en + j), s);
+  return n;
+}
+
+// ---- count_overlaps: int64 count per iterated row -------------------------------------------
+template <bool STRICT>
+__global__ void __launch_bounds__(kSweepThreads) count_overlaps_kernel(IndexView ix, const int32_t *__restrict__ pc,
+                                                                       const int32_t *__restrict__ ps,
+                                                                       const int32_t *__restrict__ pe, int64_t n,
+                                                                       int64_t *__restrict__ counts) {
+  int64_t i = (int64_t)blockIdx.x * kSweepThreads + threadIdx.x;
+  if (i >= n) return;
+  counts[i] = (int64_t)probe_count<STRICT>(ix, pc[i], ps[i], pe[i]);
+}
+
+// ---- overlap pass 1: uint32 count per probe + uint64 total per block -------------------------
+template <bool STRICT>
+__global__ void __launch_bounds__(kSweepThreads) overlap_count_kernel(IndexView ix, const int32_t *__restrict__ pc,
+                                                                      const int32_t *__restrict__ ps,
+                                                                      const int32_t *__restrict__ pe, int64_t n,
+                                                                      uint32_t *__restrict__ counts,
+                                                                      unsigned long long *__restrict__ block_totals) {
+  __shared__ unsigned long long wt[kSweepThreads / 32];
+  int64_t i = (int64_t)blockIdx.x * kSweepThreads + threadIdx.x;
+  uint32_t cnt = 0;
+  if (i < n) {
+    cnt = probe_count<STRICT>(ix, pc[i], ps[i], pe[i]);
+    counts[i] = cnt;
+  }
+  unsigned long long v = cnt;
+#pragma unroll
+  for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  if ((threadIdx.x & 31) == 0) wt[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+#pragma unroll
+    for (int w = 0; w < kSweepThreads / 32; ++w) t += wt[w];
+    block_totals[blockIdx.x] = t;
+  }
+}
+
+// ---- overlap pass 2: write (probe_row, build_row) pairs at exact offsets ---------------------
+// Offsets = scanned block base + in-block exclusive scan of the pass-1 counts.  Short windows
+// are walked by their own thread; long ones by the whole warp with ballot compaction so the
+// stores of one probe are contiguous.
+template <bool STRICT>
+__global__ void __launch_bounds__(kSweepThreads) overlap_emit_kernel(IndexView ix, const int32_t *__restrict__ pc,
+                                                                     const int32_t *__restrict__ ps,
+                                                                     const int32_t *__restrict__ pe, int64_t n,
+                                                                     const uint32_t *__restrict__ counts,
+                                                                     const unsigned long long *__restrict__ block_base,
+                                                                     uint32_t *__restrict__ out_probe,
+                                                                     uint32_t *__restrict__ out_build) {
+  __shared__ unsigned long long wt[kSweepThreads / 32 + 1];
+  const int64_t i = (int64_t)blockIdx.x * kSweepThreads + threadIdx.x;
+  const bool in_range = i < n;
+  const uint32_t cnt = in_range ? counts[i] : 0u;
+  unsigned long long pos = block_base[blockIdx.x] + block_exclusive<SumU64, kSweepThreads>((unsigned long long)cnt, wt);
+
+  int32_t lo = 0, hi = 0, s = 0;
+  if (cnt) {
+    const int32_t c = pc[i];
+    s = ps[i];
+    probe_window<STRICT>(ix, ix.seg[c], ix.seg[c + 1], s, pe[i], lo, hi);
+  }
+  const bool heavy = cnt && (hi - lo) >= kHeavyWindow;
+  if (cnt && !heavy) {
+    for (int32_t j = lo; j < hi; ++j) {
+      if (end_hits<STRICT>(__ldg(ix.en + j), s)) {
+        out_probe[pos] = (uint32_t)i;
+        out_build[pos] = __ldg(ix.row + j);
+        ++pos;
+      }
+    }
+  }
+  unsigned hm = __ballot_sync(0xffffffffu, heavy);
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = lanemask_lt();
+  while (hm) {
+    const int src = __ffs(hm) - 1;
+    hm &= hm - 1;
+    const int32_t l = __shfl_sync(0xffffffffu, lo, src), h = __shfl_sync(0xffffffffu, hi, src);
+    const int32_t ss = __shfl_sync(0xffffffffu, s, src);
+    unsigned long long p = __shfl_sync(0xffffffffu, pos, src);
+    const uint32_t pi = (uint32_t)__shfl_sync(0xffffffffu, (unsigned long long)i, src);
+    for (int32_t j0 = l; j0 < h; j0 += 32) {
+      const int32_t j = j0 + lane;
+      const bool ok = j < h && end_hits<STRICT>(__ldg(ix.en + j), ss);
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      if (ok) {
+        const unsigned long long k = p + __popc(m & lt);
+        out_probe[k] = pi;
+        out_build[k] = __ldg(ix.row + j);
+      }
+      p += __popc(m);
+    }
+  }
+}
+
+// ---- coverage: positions of the probe covered by the union of indexed rows -------------------
+template <bool STRICT>
+__global__ void __launch_bounds__(kSweepThreads) coverage_kernel(IndexView ix, const int32_t *__restrict__ pc,
+                                                                 const int32_t *__restrict__ ps,
+                                                                 const int32_t *__restrict__ pe, int64_t n,
+                                                                 int64_t *__restrict__ cov) {
+  int64_t i = (int64_t)blockIdx.x * kSweepThreads + threadIdx.x;
+  if (i >= n) return;
+  const int32_t c = pc[i];
+  long long total = 0;
+  if (c >= 0 && c < ix.n_contigs) {
+    const int32_t s = ps[i], e = pe[i];
+    int32_t lo, hi;
+    probe_window<STRICT>(ix, ix.seg[c], ix.seg[c + 1], s, e, lo, hi);
+    long long cs = 0, ce = 0;
+    bool open = false;
+    for (int32_t j = lo; j < hi; ++j) {  // hits arrive start-sorted: merge clipped pieces on the fly
+      const int32_t be_raw = __ldg(ix.en + j);
+      if (!end_hits<STRICT>(be_raw, s)) continue;
+      long long bs = __ldg(ix.st + j), be = be_raw;
+      if (bs < s) bs = s;
+      if (be > e) be = e;
+      if (!STRICT) be += 1;  // closed -> half-open in 64 bit
+      if (be <= bs) continue;
+      if (!open) { cs = bs; ce = be; open = true; }
+      else if (bs <= ce) { if (be > ce) ce = be; }
+      else { total += ce - cs; cs = bs; ce = be; }
+    }
+    if (open) total += ce - cs;
+  }
+  cov[i] = total;
+}
+
+// ---- nearest ------------------------------------------------------------------------------
+// Ordering: overlapping partners first (when included) in (start,row) order, then the merge of
+//   upstream   rows ending before the probe starts, by descending end; equal ends in (start,row) order
+//   downstream rows starting after the probe ends, in (start,row) order
+// by (distance, start, row).  Mirrors oracle/interval_oracle.c:pbo_nearest decision for decision.
+__device__ __forceinline__ long long gap_of(int32_t as, int32_t ae, int32_t bs, int32_t be) {
+  long long d1 = (long long)bs - (long long)ae, d2 = (long long)as - (long long)be;
+  long long d = d1 > d2 ? d1 : d2;
+  return d > 0 ? d : 0;
+}
+
+template <bool STRICT>
+__global__ void __launch_bounds__(kSweepThreads) nearest_kernel(IndexView ix, const int32_t *__restrict__ pc,
+                                                                const int32_t *__restrict__ ps,
+                                                                const int32_t *__restrict__ pe, int64_t n, int64_t k,
+                                                                int include_overlaps, uint32_t *__restrict__ partner,
+                                                                int64_t *__restrict__ dist) {
+  const int64_t i = (int64_t)blockIdx.x * kSweepThreads + threadIdx.x;
+  if (i >= n) return;
+  uint32_t *ob = partner + i * k;
+  int64_t *od = dist ? dist + i * k : nullptr;
+  for (int64_t j = 0; j < k; ++j) { ob[j] = PBGPU_NO_PARTNER; if (od) od[j] = -1; }
+  const int32_t c = pc[i];
+  if (c < 0 || c >= ix.n_contigs) return;
+  const int32_t seg_lo = ix.seg[c], seg_hi = ix.seg[c + 1];
+  if (seg_lo >= seg_hi) return;
+  const int32_t qs = ps[i], qe = pe[i];
+  int32_t lo, hi;
+  probe_window<STRICT>(ix, seg_lo, seg_hi, qs, qe, lo, hi);
+  int64_t got = 0;
+  if (include_overlaps) {
+    for (int32_t j = lo; j < hi && got < k; ++j) {
+      if (end_hits<STRICT>(__ldg(ix.en + j), qs)) { ob[got] = __ldg(ix.row + j); if (od) od[got] = 0; ++got; }
+    }
+  }
+  if (got >= k) return;
+  int32_t rp = hi;  // downstream cursor: first start past the probe end
+  const int32_t lend = STRICT ? upper_bound_i32(ix.en_sorted, seg_lo, seg_hi, qs)
+                              : lower_bound_i32(ix.en_sorted, seg_lo, seg_hi, qs);
+  int32_t lg_hi = lend, lg_lo = lend, lcur = lend;  // current equal-end group [lg_lo,lg_hi), cursor lcur
+  for (;;) {
+    bool have_l = false, have_r = false;
+    int32_t lpos = 0;
+    long long ld = 0, rd = 0;
+    for (;;) {
+      if (lcur >= lg_hi) {  // open the next (smaller end) group
+        if (lg_lo <= seg_lo) break;
+        lg_hi = lg_lo;
+        const int32_t v = __ldg(ix.en_sorted + lg_hi - 1);
+        lg_lo = lower_bound_i32(ix.en_sorted, seg_lo, lg_hi, v);
+        lcur = lg_lo;
+      }
+      lpos = (int32_t)__ldg(ix.en_pos + lcur);
+      const int32_t bs = __ldg(ix.st + lpos), be = __ldg(ix.en + lpos);
+      if (is_hit<STRICT>(qs, qe, bs, be)) { ++lcur; continue; }
+      have_l = true;
+      ld = gap_of(qs, qe, bs, be);
+      break;
+    }
+    while (rp < seg_hi) {
+      const int32_t bs = __ldg(ix.st + rp), be = __ldg(ix.en + rp);
+      if (is_hit<STRICT>(qs, qe, bs, be) || (STRICT ? (be <= qs) : (be < qs))) { ++rp; continue; }
+      have_r = true;
+      rd = gap_of(qs, qe, bs, be);
+      break;
+    }
+    if (!have_l && !have_r) break;
+    bool take_left;
+    if (have_l && have_r) {
+      const int32_t lst = __ldg(ix.st + lpos), rst = __ldg(ix.st + rp);
+      if (ld != rd) take_left = ld < rd;
+      else if (lst != rst) take_left = lst < rst;
+      else take_left = __ldg(ix.row + lpos) < __ldg(ix.row + rp);
+    } else take_left = have_l;
+    if (take_left) { ob[got] = __ldg(ix.row + lpos); if (od) od[got] = ld; ++lcur; }
+    else { ob[got] = __ldg(ix.row + rp); if (od) od[got] = rd; ++rp; }
+    if (++got >= k) break;
+  }
+}
+
+}  // namespace pbgpu

@@ -1,0 +1,122 @@
+"""Device-level driver: HBM-resident int32 columns in, torch tensors out.
+
+torch is plumbing here (device memory, the current CUDA stream, ``torch.distributed`` for the
+multi-GPU exchange); every computation is a kernel of libpbgpu.so reached through the C ABI of
+``include/pbgpu.h``.  The classes mirror the three providers polars-bio's plan builder
+constructs (/root/reference/src/operation.rs:146-158, 253-263, 331-340): an index over the
+"indexed" table plus one method per provider.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _native
+from ._native import check
+
+FILTER_WEAK = 0    # FilterOp::Weak   (src/option.rs:97) 1-based closed intervals
+FILTER_STRICT = 1  # FilterOp::Strict (src/option.rs:98) 0-based half-open intervals
+NO_PARTNER = 0xFFFFFFFF
+
+
+def _stream_ptr(device) -> int:
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _col(t: torch.Tensor, device) -> torch.Tensor:
+    if t.dtype != torch.int32 or not t.is_cuda or not t.is_contiguous():
+        raise TypeError("device-level API takes contiguous int32 CUDA tensors")
+    if t.device != device:
+        raise ValueError(f"column on {t.device}, index on {device}")
+    return t
+
+
+class DeviceIndex:
+    """Search structure over the indexed (build) table -- the COITrees replacement.
+
+    ``contig`` holds dictionary codes shared with the probe side (0..n_contigs-1; anything else
+    is a null key that never matches); ``start``/``end`` are int32 coordinates.
+    """
+
+    def __init__(self, contig: torch.Tensor, start: torch.Tensor, end: torch.Tensor, n_contigs: int):
+        if not torch.cuda.is_available():
+            raise RuntimeError("polars_bio_b200 needs a CUDA device (no CPU fallback)")
+        self.device = contig.device
+        self._L = _native.lib()
+        self._h = ctypes.c_void_p()
+        self.n_contigs = int(n_contigs)
+        c, s, e = (_col(x, self.device) for x in (contig, start, end))
+        with torch.cuda.device(self.device):
+            check(self._L.pbgpu_index_build(c.data_ptr(), s.data_ptr(), e.data_ptr(), c.numel(), self.n_contigs,
+                                            _stream_ptr(self.device), ctypes.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.pbgpu_index_free(self._h)
+            self._h = ctypes.c_void_p()
+
+    __del__ = close
+
+    @property
+    def rows(self) -> int:
+        return int(self._L.pbgpu_index_rows(self._h))
+
+    @property
+    def nbytes(self) -> int:
+        return int(self._L.pbgpu_index_bytes(self._h))
+
+    # -- CountOverlapsProvider ---------------------------------------------------------------
+    def count_overlaps(self, contig, start, end, filter_op: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        c, s, e = (_col(x, self.device) for x in (contig, start, end))
+        n = c.numel()
+        if out is None:
+            out = torch.empty(n, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self._L.pbgpu_count_overlaps(self._h, c.data_ptr(), s.data_ptr(), e.data_ptr(), n, filter_op,
+                                               out.data_ptr(), _stream_ptr(self.device)))
+        return out
+
+    def coverage(self, contig, start, end, filter_op: int) -> torch.Tensor:
+        c, s, e = (_col(x, self.device) for x in (contig, start, end))
+        n = c.numel()
+        out = torch.empty(n, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self._L.pbgpu_coverage(self._h, c.data_ptr(), s.data_ptr(), e.data_ptr(), n, filter_op,
+                                         out.data_ptr(), _stream_ptr(self.device)))
+        return out
+
+    # -- OverlapProvider ---------------------------------------------------------------------
+    def overlap_pairs(self, contig, start, end, filter_op: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Two-pass count-then-emit.  Returns (probe_rows, build_rows): int32 tensors holding
+        uint32 row ids, ordered by probe row then (start,row) of the indexed partner."""
+        c, s, e = (_col(x, self.device) for x in (contig, start, end))
+        n = c.numel()
+        plan = ctypes.c_void_p()
+        total = ctypes.c_int64(0)
+        with torch.cuda.device(self.device):
+            sp = _stream_ptr(self.device)
+            check(self._L.pbgpu_overlap_count(self._h, c.data_ptr(), s.data_ptr(), e.data_ptr(), n, filter_op, sp,
+                                              ctypes.byref(plan), ctypes.byref(total)))
+            try:
+                p = torch.empty(total.value, dtype=torch.int32, device=self.device)
+                b = torch.empty(total.value, dtype=torch.int32, device=self.device)
+                check(self._L.pbgpu_overlap_emit(plan, p.data_ptr(), b.data_ptr(), sp))
+                torch.cuda.current_stream(self.device).synchronize()  # plan scratch is read by the emit kernel
+            finally:
+                self._L.pbgpu_overlap_plan_free(plan)
+        return p, b
+
+    # -- NearestProvider ---------------------------------------------------------------------
+    def nearest(self, contig, start, end, filter_op: int, k: int = 1, include_overlaps: bool = True,
+                compute_distance: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        c, s, e = (_col(x, self.device) for x in (contig, start, end))
+        n = c.numel()
+        partner = torch.empty((n, k), dtype=torch.int32, device=self.device)
+        dist = torch.empty((n, k), dtype=torch.int64, device=self.device) if compute_distance else None
+        with torch.cuda.device(self.device):
+            check(self._L.pbgpu_nearest(self._h, c.data_ptr(), s.data_ptr(), e.data_ptr(), n, filter_op, k,
+                                        int(include_overlaps), partner.data_ptr(),
+                                        dist.data_ptr() if dist is not None else None, _stream_ptr(self.device)))
+        return partner, dist

@@ -1,0 +1,190 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI of include/pbgpu.h, driven via
+polars_bio_b200.engine) against the CPU oracle on the same seeded inputs, against the committed
+golden fixtures, and -- at BASELINE.json sizes -- through size-independent properties.
+Bit-exact: integer / index work only."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+import oracle  # noqa: E402
+from tests._golden import exons_fbrain, fixtures, synth  # noqa: E402
+
+FX = fixtures()
+
+
+def _engine():
+    from polars_bio_b200 import engine
+
+    return engine
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to("cuda:0")
+
+
+def _u32(t):
+    return t.cpu().numpy().view(np.uint32)
+
+
+def _run_all(pc, ps, pe, bc, bs, be, nc, strict, ks=((1, True), (3, True), (1, False), (4, False))):
+    eng = _engine()
+    fo = eng.FILTER_STRICT if strict else eng.FILTER_WEAK
+    ix = eng.DeviceIndex(_dev(bc), _dev(bs), _dev(be), nc)
+    oix = oracle.Index(bc, bs, be, nc)
+    dpc, dps, dpe = _dev(pc), _dev(ps), _dev(pe)
+    cnt = ix.count_overlaps(dpc, dps, dpe, fo).cpu().numpy()
+    assert np.array_equal(cnt, oix.count_overlaps(pc, ps, pe, strict))
+    a, b = ix.overlap_pairs(dpc, dps, dpe, fo)
+    oa, ob = oix.overlap_pairs(pc, ps, pe, strict)
+    assert len(a) == len(oa)
+    assert np.array_equal(_u32(a), oa) and np.array_equal(_u32(b), ob)  # same order too: (probe, start, row)
+    cov = ix.coverage(dpc, dps, dpe, fo).cpu().numpy()
+    assert np.array_equal(cov, oix.coverage(pc, ps, pe, strict))
+    for k, inc in ks:
+        p, d = ix.nearest(dpc, dps, dpe, fo, k=k, include_overlaps=inc)
+        op, od = oix.nearest(pc, ps, pe, strict, k=k, include_overlaps=inc)
+        assert np.array_equal(d.cpu().numpy(), od), (k, inc)
+        assert np.array_equal(_u32(p), op), (k, inc)
+    ix.close()
+    return cnt
+
+
+@pytest.mark.parametrize("strict", [True, False])
+def test_golden_csv_fixtures(strict):
+    # tests/data/overlap/{reads,targets}.csv (reference tests/test_native.py:32-52): 16 pairs in Weak mode
+    fx = FX["overlap"]
+    lc, rc, names = oracle.encode_contigs(fx["df1"]["contig"], fx["df2"]["contig"])
+    cnt = _run_all(lc, np.array(fx["df1"]["pos_start"], np.int32), np.array(fx["df1"]["pos_end"], np.int32),
+                   rc, np.array(fx["df2"]["pos_start"], np.int32), np.array(fx["df2"]["pos_end"], np.int32),
+                   len(names), strict)
+    if not strict:
+        assert cnt.sum() == 16
+
+
+def test_golden_count_and_nearest_values():
+    eng = _engine()
+    fx = FX["count_overlaps"]
+    lc, rc, names = oracle.encode_contigs(fx["df1"]["contig"], fx["df2"]["contig"])
+    ix = eng.DeviceIndex(_dev(rc), _dev(fx["df2"]["pos_start"]), _dev(fx["df2"]["pos_end"]), len(names))
+    cnt = ix.count_overlaps(_dev(lc), _dev(fx["df1"]["pos_start"]), _dev(fx["df1"]["pos_end"]), eng.FILTER_WEAK)
+    # tests/_expected.py:183-202 (rows are in input order there too)
+    assert cnt.cpu().tolist() == [2, 2, 2, 1, 1, 2, 2, 2, 1, 1, 0]
+    p, d = ix.nearest(_dev(lc), _dev(fx["df1"]["pos_start"]), _dev(fx["df1"]["pos_end"]), eng.FILTER_WEAK)
+    assert sorted(d[:, 0].cpu().tolist()) == sorted(FX["nearest"]["expected"]["distance"])  # incl. the 34
+
+
+@pytest.mark.parametrize("kat", FX["overlap_kats"])
+def test_boundary_kats(kat):
+    # tests/test_coordinate_system_metadata.py:735-818
+    eng = _engine()
+    z = np.zeros(1, np.int32)
+    fo = eng.FILTER_STRICT if kat["zero_based"] else eng.FILTER_WEAK
+    ix = eng.DeviceIndex(_dev(z), _dev([kat["b"][0]]), _dev([kat["b"][1]]), 1)
+    a, _ = ix.overlap_pairs(_dev(z), _dev([kat["a"][0]]), _dev([kat["a"][1]]), fo)
+    assert a.numel() == kat["rows"]
+    assert int(ix.count_overlaps(_dev(z), _dev([kat["a"][0]]), _dev([kat["a"][1]]), fo)[0]) == kat["rows"]
+
+
+@pytest.mark.parametrize("kat", FX["coverage_kats"])
+def test_coverage_kats(kat):
+    eng = _engine()
+    z = np.zeros(1, np.int32)
+    fo = eng.FILTER_STRICT if kat["zero_based"] else eng.FILTER_WEAK
+    ix = eng.DeviceIndex(_dev(z), _dev([kat["b"][0]]), _dev([kat["b"][1]]), 1)
+    assert int(ix.coverage(_dev(z), _dev([kat["a"][0]]), _dev([kat["a"][1]]), fo)[0]) == kat["coverage"]
+
+
+@pytest.mark.parametrize("strict", [True, False])
+def test_exons_fbrain_54246(strict):
+    # docs/supplement.md:108,149 published pair count; both join directions; full pair parity
+    z = exons_fbrain()
+    nc = len(z["contigs"])
+    ec, es, ee = z["exons_chrom"].astype(np.int32), z["exons_start"], z["exons_end"]
+    fc, fs, fe = z["fbrain_chrom"].astype(np.int32), z["fbrain_start"], z["fbrain_end"]
+    want = FX["exons_fbrain_pairs"]["strict" if strict else "weak"]
+    cnt = _run_all(ec, es, ee, fc, fs, fe, nc, strict, ks=((1, True), (2, False)))
+    assert cnt.sum() == want
+    cnt2 = _run_all(fc, fs, fe, ec, es, ee, nc, strict, ks=((1, True),))
+    assert cnt2.sum() == want
+
+
+@pytest.mark.parametrize("strict", [True, False])
+@pytest.mark.parametrize("seed", [0, 1])
+def test_random_ragged(strict, seed):
+    # zero-length intervals, contigs on one side only, null keys (-1 / out of range), long shadowing intervals
+    pc, ps, pe = synth(5000, 6, 50_000, 200, seed, zero_len_frac=0.05)
+    bc, bs, be = synth(3000, 5, 50_000, 5000, 10 + seed, zero_len_frac=0.05)
+    pc[::97] = -1
+    bc[::89] = 7
+    _run_all(pc, ps, pe, bc, bs, be, 6, strict)
+
+
+@pytest.mark.parametrize("strict", [True, False])
+def test_inverted_and_negative_coordinates(strict):
+    # start > end rows are evaluated by the bare predicate (rank identity must switch itself off);
+    # negative coordinates exercise the biased radix keys
+    rng = np.random.default_rng(5)
+    pc, ps, pe = synth(2000, 2, 4000, 100, 3)
+    bc, bs, be = synth(1500, 2, 4000, 300, 4)
+    ps -= 2000; pe -= 2000; bs -= 2000; be -= 2000
+    inv = rng.random(1500) < 0.1
+    bs2, be2 = np.where(inv, be, bs), np.where(inv, bs, be)
+    inv = rng.random(2000) < 0.1
+    ps2, pe2 = np.where(inv, pe, ps), np.where(inv, ps, pe)
+    _run_all(pc, ps2.astype(np.int32), pe2.astype(np.int32), bc, bs2.astype(np.int32), be2.astype(np.int32), 2, strict,
+             ks=((1, True),))
+
+
+def test_empty_inputs():
+    eng = _engine()
+    e = np.zeros(0, np.int32)
+    ix = eng.DeviceIndex(_dev(e), _dev(e), _dev(e), 3)
+    c, s, en = synth(100, 3, 1000, 50, 1)
+    assert ix.count_overlaps(_dev(c), _dev(s), _dev(en), eng.FILTER_STRICT).sum().item() == 0
+    a, b = ix.overlap_pairs(_dev(c), _dev(s), _dev(en), eng.FILTER_STRICT)
+    assert a.numel() == 0 and b.numel() == 0
+    p, d = ix.nearest(_dev(c), _dev(s), _dev(en), eng.FILTER_STRICT)
+    assert (_u32(p) == 0xFFFFFFFF).all() and (d.cpu().numpy() == -1).all()
+    ix2 = eng.DeviceIndex(_dev(c), _dev(s), _dev(en), 3)
+    a, b = ix2.overlap_pairs(_dev(e), _dev(e), _dev(e), eng.FILTER_WEAK)
+    assert a.numel() == 0
+    assert ix2.count_overlaps(_dev(e), _dev(e), _dev(e), eng.FILTER_WEAK).numel() == 0
+
+
+def test_heavy_windows_skewed_output():
+    # few long indexed intervals x many probes inside them: the warp-cooperative emit path (window >= 64)
+    rng = np.random.default_rng(11)
+    m = 4000
+    bc = np.zeros(m, np.int32); bs = rng.integers(0, 10_000, m).astype(np.int32)
+    be = (bs + rng.integers(5_000, 20_000, m)).astype(np.int32)
+    n = 3000
+    pc = np.zeros(n, np.int32); ps = rng.integers(0, 30_000, n).astype(np.int32)
+    pe = (ps + rng.integers(1, 150, n)).astype(np.int32)
+    cnt = _run_all(pc, ps, pe, bc, bs, be, 1, True, ks=((1, True), (5, True)))
+    assert cnt.max() >= 64
+
+
+def test_full_size_properties_config2():
+    """BASELINE config 2 (10M reads x 1M variants, one contig) through size-independent properties:
+    sum(count_overlaps) == emitted pairs; every emitted pair satisfies the predicate; pairs sorted by probe
+    row; per-probe multiplicity == count; oracle agreement on a 200k-probe slice."""
+    eng = _engine()
+    from bench import make_config2
+
+    (pc, ps, pe), (bc, bs, be), nc = make_config2(10_000_000, 1_000_000)
+    ix = eng.DeviceIndex(_dev(bc), _dev(bs), _dev(be), nc)
+    dpc, dps, dpe = _dev(pc), _dev(ps), _dev(pe)
+    cnt = ix.count_overlaps(dpc, dps, dpe, eng.FILTER_STRICT)
+    a, b = ix.overlap_pairs(dpc, dps, dpe, eng.FILTER_STRICT)
+    assert int(cnt.sum()) == a.numel() > 5_000_000
+    al, bl = a.long(), b.long()
+    dbs, dbe = _dev(bs), _dev(be)
+    assert bool(((dps[al] < dbe[bl]) & (dpe[al] > dbs[bl])).all())
+    assert bool((al[1:] >= al[:-1]).all())
+    assert torch.equal(torch.bincount(al, minlength=len(pc)), cnt)
+    sl = slice(4_000_000, 4_200_000)
+    oc = oracle.Index(bc, bs, be, nc).count_overlaps(pc[sl], ps[sl], pe[sl], True, threads=4)
+    assert np.array_equal(cnt[sl].cpu().numpy(), oc)
