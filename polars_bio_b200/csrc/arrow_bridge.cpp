@@ -1,10 +1,953 @@
-// arrow_bridge.cpp -- Arrow C Stream level of the C ABI (pbgpu_range_op).  Placeholder until the
-// ingest / materialise path lands: returns PBGPU_EINVAL without touching the streams' contents.
+// arrow_bridge.cpp -- Arrow C Stream level of the C ABI: pbgpu_range_op (include/pbgpu.h).
+//
+// This is what the reference's PyO3 entry points range_operation_frame / _lazy
+// (/root/reference/src/lib.rs:79-88,154-166) and plan builder do_range_operation
+// (/root/reference/src/operation.rs:27-98) do around the providers, restated for the GPU engine:
+//   drain both ArrowArrayStreams (the callee moves them: released before returning, lib.rs:63-72)
+//   -> dictionary-encode the contig columns over a shared dictionary, narrow positions to int32
+//      (reference domain limit, docs/features/operations.md:37) into cached pinned staging
+//   -> H2D, pbgpu_index_build over the indexed side, provider kernel, D2H of row-id results
+//   -> an output ArrowArrayStream that materialises the reference's column contract batch by
+//      batch (operation.rs:170-195 nearest, :272-299 overlap, :347 count/coverage) or hands out
+//      the raw index pairs (emit = 1).
+// Host-side only; every device computation goes through the device-level C ABI in pbgpu.cu.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <string_view>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
 #include "../../include/pbgpu.h"
+#include "arrow_c_abi.h"
 
-namespace pbgpu { int set_error(int code, const char *fmt, ...); }
+namespace pbgpu {
+int set_error(int code, const char *fmt, ...);
+extern thread_local char g_err[512];
+}  // namespace pbgpu
+using pbgpu::set_error;
 
-extern "C" int pbgpu_range_op(struct ArrowArrayStream *, struct ArrowArrayStream *, const PbRangeOptions *,
-                              struct ArrowArrayStream *) {
-  return pbgpu::set_error(PBGPU_EINVAL, "pbgpu_range_op: Arrow-level entry point not built yet");
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// tiny persistent thread pool: parallel_for over [0,n) in chunks
+class Pool {
+ public:
+  static Pool &get() {
+    static Pool p;
+    return p;
+  }
+  int size() const { return (int)workers_.size() + 1; }
+  void parallel_for(int64_t n_tasks, const std::function<void(int64_t)> &fn) {
+    if (n_tasks <= 0) return;
+    if (n_tasks == 1 || workers_.empty()) {
+      for (int64_t i = 0; i < n_tasks; ++i) fn(i);
+      return;
+    }
+    std::unique_lock<std::mutex> run_lock(run_mu_);  // one parallel_for at a time
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      fn_ = &fn;
+      next_.store(0);
+      total_ = n_tasks;
+      pending_ = (int)workers_.size();
+      ++epoch_;
+    }
+    cv_.notify_all();
+    work();
+    std::unique_lock<std::mutex> lk(mu_);
+    done_cv_.wait(lk, [&] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  Pool() {
+    unsigned hc = std::thread::hardware_concurrency();
+    int n = (int)std::min<unsigned>(hc ? hc : 4, 32);
+    const char *e = getenv("PBGPU_HOST_THREADS");
+    if (e && atoi(e) > 0) n = atoi(e);
+    for (int i = 1; i < n; ++i) workers_.emplace_back([this] { loop(); });
+  }
+  ~Pool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+      ++epoch_;
+    }
+    cv_.notify_all();
+    for (auto &t : workers_) t.join();
+  }
+  void work() {
+    for (;;) {
+      int64_t i = next_.fetch_add(1);
+      if (i >= total_) break;
+      (*fn_)(i);
+    }
+  }
+  void loop() {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return epoch_ != seen; });
+        seen = epoch_;
+        if (stop_) return;
+      }
+      work();
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (--pending_ == 0) done_cv_.notify_all();
+      }
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex mu_, run_mu_;
+  std::condition_variable cv_, done_cv_;
+  const std::function<void(int64_t)> *fn_ = nullptr;
+  std::atomic<int64_t> next_{0};
+  int64_t total_ = 0;
+  int pending_ = 0;
+  uint64_t epoch_ = 0;
+  bool stop_ = false;
+};
+
+constexpr int64_t kChunk = 1 << 17;  // rows per host task
+
+// ---------------------------------------------------------------------------------------------
+// cached pinned staging (cudaHostAlloc is milliseconds per 100 MB: never on the per-call path twice)
+struct PinnedBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  bool busy = false;
+};
+std::mutex g_pin_mu;
+std::vector<PinnedBuf> g_pin;
+
+void *pinned_get(size_t bytes) {
+  if (bytes == 0) bytes = 1;
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  int best = -1;
+  for (int i = 0; i < (int)g_pin.size(); ++i)
+    if (!g_pin[i].busy && g_pin[i].cap >= bytes && (best < 0 || g_pin[i].cap < g_pin[best].cap)) best = i;
+  if (best >= 0) {
+    g_pin[best].busy = true;
+    return g_pin[best].p;
+  }
+  PinnedBuf b;
+  size_t cap = (bytes + (1 << 20) - 1) & ~(size_t)((1 << 20) - 1);
+  if (cudaHostAlloc(&b.p, cap, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  b.cap = cap;
+  b.busy = true;
+  g_pin.push_back(b);
+  return b.p;
+}
+void pinned_put(void *p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  for (auto &b : g_pin)
+    if (b.p == p) b.busy = false;
+}
+struct PinnedHold {  // returns its buffers to the cache on destruction
+  std::vector<void *> v;
+  template <typename T>
+  T *get(size_t count) {
+    void *p = pinned_get(count * sizeof(T));
+    if (p) v.push_back(p);
+    return (T *)p;
+  }
+  ~PinnedHold() {
+    for (void *p : v) pinned_put(p);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+inline bool bit_get(const uint8_t *bits, int64_t i) { return (bits[i >> 3] >> (i & 7)) & 1; }
+inline void bit_set(uint8_t *bits, int64_t i) { bits[i >> 3] |= (uint8_t)(1u << (i & 7)); }
+
+size_t metadata_size(const char *md) {
+  if (!md) return 0;
+  const char *p = md;
+  int32_t n;
+  memcpy(&n, p, 4);
+  p += 4;
+  for (int32_t i = 0; i < n; ++i) {
+    int32_t l;
+    memcpy(&l, p, 4); p += 4 + l;
+    memcpy(&l, p, 4); p += 4 + l;
+  }
+  return (size_t)(p - md);
+}
+
+// An input table: the drained stream (schema + batches), owned.
+struct Table {
+  ArrowSchema schema{};
+  std::vector<ArrowArray> batches;
+  std::vector<int64_t> start;  // prefix sums of batch lengths, size nb+1
+  int64_t rows = 0;
+  int key[3] = {-1, -1, -1};
+  Table() = default;
+  Table(const Table &) = delete;
+  Table &operator=(const Table &) = delete;
+  ~Table() {
+    for (auto &b : batches)
+      if (b.release) b.release(&b);
+    if (schema.release) schema.release(&schema);
+  }
+  int64_t n_cols() const { return schema.n_children; }
+  // (batch, index inside batch) of a global row
+  inline void locate(uint32_t row, int &b, int64_t &i) const {
+    if (batches.size() == 1) { b = 0; i = row; return; }
+    auto it = std::upper_bound(start.begin(), start.end(), (int64_t)row);
+    b = (int)(it - start.begin()) - 1;
+    i = (int64_t)row - start[b];
+  }
+};
+
+int drain(ArrowArrayStream *s, Table &t, const char *side) {
+  if (!s || !s->get_schema || !s->get_next) return set_error(PBGPU_EINVAL, "%s stream is NULL/invalid", side);
+  if (s->get_schema(s, &t.schema) != 0) {
+    const char *m = s->get_last_error ? s->get_last_error(s) : nullptr;
+    return set_error(PBGPU_ESTREAM, "%s stream get_schema failed: %s", side, m ? m : "?");
+  }
+  if (!t.schema.format || strcmp(t.schema.format, "+s") != 0)
+    return set_error(PBGPU_ESCHEMA, "%s stream must yield struct (record batch) arrays, got format '%s'", side,
+                     t.schema.format ? t.schema.format : "?");
+  t.start.push_back(0);
+  for (;;) {
+    ArrowArray a{};
+    if (s->get_next(s, &a) != 0) {
+      const char *m = s->get_last_error ? s->get_last_error(s) : nullptr;
+      return set_error(PBGPU_ESTREAM, "%s stream get_next failed: %s", side, m ? m : "?");
+    }
+    if (!a.release) break;  // end of stream
+    if (a.n_children != t.schema.n_children) {
+      a.release(&a);
+      return set_error(PBGPU_ESCHEMA, "%s stream: batch has %lld children, schema %lld", side, (long long)a.n_children,
+                       (long long)t.schema.n_children);
+    }
+    if (a.length == 0) { a.release(&a); continue; }
+    t.rows += a.length;
+    t.start.push_back(t.rows);
+    t.batches.push_back(a);
+  }
+  if (t.rows >= 0xFFFFFFFFll) return set_error(PBGPU_ERANGE, "%s table has %lld rows; limit is 2^32-2", side, (long long)t.rows);
+  return PBGPU_OK;
+}
+
+int find_col(const Table &t, const char *name, const char *side, int *out) {
+  if (!name) return set_error(PBGPU_EINVAL, "NULL column name for %s", side);
+  for (int64_t i = 0; i < t.schema.n_children; ++i)
+    if (t.schema.children[i]->name && strcmp(t.schema.children[i]->name, name) == 0) { *out = (int)i; return PBGPU_OK; }
+  return set_error(PBGPU_ESCHEMA, "column '%s' not found in %s table", name, side);
+}
+
+// ---- contig dictionary shared by both sides ----------------------------------------------------
+struct ContigDict {
+  std::mutex mu;
+  std::unordered_map<std::string, int32_t> map;
+  int32_t intern(std::string_view sv) {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = map.find(std::string(sv));
+    if (it != map.end()) return it->second;
+    int32_t c = (int32_t)map.size();
+    map.emplace(std::string(sv), c);
+    return c;
+  }
+};
+
+enum class StrKind { Utf8, LargeUtf8, View, None };
+StrKind str_kind(const char *f) {
+  if (!strcmp(f, "u") || !strcmp(f, "z")) return StrKind::Utf8;
+  if (!strcmp(f, "U") || !strcmp(f, "Z")) return StrKind::LargeUtf8;
+  if (!strcmp(f, "vu") || !strcmp(f, "vz")) return StrKind::View;
+  return StrKind::None;
+}
+
+// string at physical index j of a (non-dictionary) string array
+inline std::string_view str_at(const ArrowArray *a, StrKind k, int64_t j) {
+  switch (k) {
+    case StrKind::Utf8: {
+      const int32_t *o = (const int32_t *)a->buffers[1];
+      return std::string_view((const char *)a->buffers[2] + o[j], (size_t)(o[j + 1] - o[j]));
+    }
+    case StrKind::LargeUtf8: {
+      const int64_t *o = (const int64_t *)a->buffers[1];
+      return std::string_view((const char *)a->buffers[2] + o[j], (size_t)(o[j + 1] - o[j]));
+    }
+    case StrKind::View: {
+      const uint8_t *v = (const uint8_t *)a->buffers[1] + 16 * j;
+      int32_t len;
+      memcpy(&len, v, 4);
+      if (len <= 12) return std::string_view((const char *)v + 4, (size_t)len);
+      int32_t bi, off;
+      memcpy(&bi, v + 8, 4);
+      memcpy(&off, v + 12, 4);
+      return std::string_view((const char *)a->buffers[2 + bi] + off, (size_t)len);
+    }
+    default: return {};
+  }
+}
+
+inline int64_t int_at(const void *buf, char f, int64_t j) {
+  switch (f) {
+    case 'c': return ((const int8_t *)buf)[j];
+    case 'C': return ((const uint8_t *)buf)[j];
+    case 's': return ((const int16_t *)buf)[j];
+    case 'S': return ((const uint16_t *)buf)[j];
+    case 'i': return ((const int32_t *)buf)[j];
+    case 'I': return ((const uint32_t *)buf)[j];
+    case 'l': return ((const int64_t *)buf)[j];
+    case 'L': { uint64_t v = ((const uint64_t *)buf)[j]; return v > (uint64_t)INT64_MAX ? INT64_MAX : (int64_t)v; }
+    default: return 0;
+  }
+}
+inline bool is_int_format(const char *f) { return f && f[0] && !f[1] && strchr("cCsSiIlL", f[0]); }
+
+// Encode the three key columns of a table into int32 staging (code = -1 for null keys).
+int encode_keys(const Table &t, const char *side, ContigDict &dict, int32_t *code, int32_t *st, int32_t *en) {
+  const ArrowSchema *fc = t.schema.children[t.key[0]];
+  const ArrowSchema *fs = t.schema.children[t.key[1]];
+  const ArrowSchema *fe = t.schema.children[t.key[2]];
+  const bool is_dict = fc->dictionary != nullptr;
+  const StrKind sk = str_kind(is_dict ? fc->dictionary->format : fc->format);
+  if (sk == StrKind::None || (is_dict && !is_int_format(fc->format)))
+    return set_error(PBGPU_ESCHEMA, "%s contig column '%s' has unsupported type '%s' (want utf8 / large_utf8 / utf8_view / dictionary of those)",
+                     side, fc->name, fc->format);
+  if (!is_int_format(fs->format) || !is_int_format(fe->format))
+    return set_error(PBGPU_ESCHEMA, "%s position columns must be integers, got '%s' / '%s'", side, fs->format, fe->format);
+  const char sf = fs->format[0], ef = fe->format[0];
+
+  struct Task { int b; int64_t lo, hi; };
+  std::vector<Task> tasks;
+  for (int b = 0; b < (int)t.batches.size(); ++b)
+    for (int64_t lo = 0; lo < t.batches[b].length; lo += kChunk) tasks.push_back({b, lo, std::min(lo + kChunk, t.batches[b].length)});
+  std::atomic<int> range_err{0};
+  Pool::get().parallel_for((int64_t)tasks.size(), [&](int64_t ti) {
+    const Task &tk = tasks[ti];
+    const ArrowArray &ba = t.batches[tk.b];
+    const ArrowArray *ac = ba.children[t.key[0]], *as = ba.children[t.key[1]], *ae = ba.children[t.key[2]];
+    const int64_t oc = ac->offset + ba.offset, os = as->offset + ba.offset, oe = ae->offset + ba.offset;
+    const uint8_t *vc = ac->null_count != 0 ? (const uint8_t *)ac->buffers[0] : nullptr;
+    const uint8_t *vs = as->null_count != 0 ? (const uint8_t *)as->buffers[0] : nullptr;
+    const uint8_t *ve = ae->null_count != 0 ? (const uint8_t *)ae->buffers[0] : nullptr;
+    const int64_t g0 = t.start[tk.b];
+    std::unordered_map<std::string_view, int32_t> local;  // views into Arrow buffers (alive for the call)
+    std::string_view prev;
+    int32_t prev_code = -1;
+    bool have_prev = false;
+    std::vector<int32_t> dict_codes;
+    if (is_dict) {  // map this batch's dictionary values once
+      const ArrowArray *d = ac->dictionary;
+      dict_codes.resize((size_t)d->length);
+      const uint8_t *vd = d->null_count != 0 ? (const uint8_t *)d->buffers[0] : nullptr;
+      for (int64_t j = 0; j < d->length; ++j)
+        dict_codes[j] = (vd && !bit_get(vd, j + d->offset)) ? -1 : dict.intern(str_at(d, sk, j + d->offset));
+    }
+    for (int64_t i = tk.lo; i < tk.hi; ++i) {
+      int32_t c;
+      if (vc && !bit_get(vc, i + oc)) c = -1;
+      else if (is_dict) {
+        int64_t k = int_at(ac->buffers[1], fc->format[0], i + oc);
+        c = (k >= 0 && k < (int64_t)dict_codes.size()) ? dict_codes[k] : -1;
+      } else {
+        std::string_view sv = str_at(ac, sk, i + oc);
+        if (have_prev && sv.size() == prev.size() && memcmp(sv.data(), prev.data(), sv.size()) == 0) c = prev_code;
+        else {
+          auto it = local.find(sv);
+          if (it != local.end()) c = it->second;
+          else { c = dict.intern(sv); local.emplace(sv, c); }
+          prev = sv; prev_code = c; have_prev = true;
+        }
+      }
+      int64_t s = int_at(as->buffers[1], sf, i + os), e = int_at(ae->buffers[1], ef, i + oe);
+      if ((vs && !bit_get(vs, i + os)) || (ve && !bit_get(ve, i + oe))) { c = -1; s = 0; e = 0; }
+      if (s < INT32_MIN || s > INT32_MAX || e < INT32_MIN || e > INT32_MAX) { range_err.store(1); c = -1; s = 0; e = 0; }
+      code[g0 + i] = c;
+      st[g0 + i] = (int32_t)s;
+      en[g0 + i] = (int32_t)e;
+    }
+  });
+  if (range_err.load())
+    return set_error(PBGPU_ERANGE, "%s table has a coordinate outside the int32 domain (reference limit: contigs < 2 Gb)", side);
+  return PBGPU_OK;
+}
+
+// ---- output construction ------------------------------------------------------------------------
+struct OwnedArray {  // private_data of every ArrowArray we produce
+  std::vector<void *> bufs;        // malloc'd, freed on release
+  std::vector<const void *> bptr;  // the `buffers` array
+  std::vector<ArrowArray> kids;
+  std::vector<ArrowArray *> kptr;
+};
+void release_array(ArrowArray *a) {
+  if (!a || !a->release) return;
+  OwnedArray *o = (OwnedArray *)a->private_data;
+  for (auto &k : o->kids)
+    if (k.release) k.release(&k);
+  for (void *p : o->bufs) free(p);
+  delete o;
+  a->release = nullptr;
+}
+ArrowArray finish_array(OwnedArray *o, int64_t length, int64_t null_count) {
+  ArrowArray a{};
+  a.length = length;
+  a.null_count = null_count;
+  a.offset = 0;
+  a.n_buffers = (int64_t)o->bptr.size();
+  a.buffers = o->bptr.data();
+  o->kptr.clear();
+  for (auto &k : o->kids) o->kptr.push_back(&k);
+  a.n_children = (int64_t)o->kptr.size();
+  a.children = o->kptr.empty() ? nullptr : o->kptr.data();
+  a.dictionary = nullptr;
+  a.release = release_array;
+  a.private_data = o;
+  return a;
+}
+
+struct OwnedSchema {
+  std::string format, name, metadata;
+  bool has_md = false;
+  std::vector<ArrowSchema> kids;
+  std::vector<ArrowSchema *> kptr;
+};
+void release_schema(ArrowSchema *s) {
+  if (!s || !s->release) return;
+  OwnedSchema *o = (OwnedSchema *)s->private_data;
+  for (auto &k : o->kids)
+    if (k.release) k.release(&k);
+  delete o;
+  s->release = nullptr;
+}
+ArrowSchema make_schema(const std::string &format, const std::string &name, const char *metadata, int64_t flags,
+                        std::vector<ArrowSchema> &&kids = {}) {
+  OwnedSchema *o = new OwnedSchema();
+  o->format = format;
+  o->name = name;
+  if (metadata) { o->metadata.assign(metadata, metadata_size(metadata)); o->has_md = true; }
+  o->kids = std::move(kids);
+  for (auto &k : o->kids) o->kptr.push_back(&k);
+  ArrowSchema s{};
+  s.format = o->format.c_str();
+  s.name = o->name.c_str();
+  s.metadata = o->has_md ? o->metadata.data() : nullptr;
+  s.flags = flags;
+  s.n_children = (int64_t)o->kptr.size();
+  s.children = o->kptr.empty() ? nullptr : o->kptr.data();
+  s.dictionary = nullptr;
+  s.release = release_schema;
+  s.private_data = o;
+  return s;
+}
+
+// byte width of fixed-width primitive formats (0 = not fixed width / unsupported)
+int fixed_width(const char *f) {
+  if (!f || !f[0]) return 0;
+  if (!f[1]) switch (f[0]) {
+      case 'c': case 'C': return 1;
+      case 's': case 'S': case 'e': return 2;
+      case 'i': case 'I': case 'f': return 4;
+      case 'l': case 'L': case 'g': return 8;
+      default: return 0;
+    }
+  if (f[0] == 't') {
+    if (!strncmp(f, "tdD", 3)) return 4;
+    if (!strncmp(f, "tdm", 3)) return 8;
+    if (!strncmp(f, "tts", 3) || !strncmp(f, "ttm", 3)) return 4;
+    if (!strncmp(f, "ttu", 3) || !strncmp(f, "ttn", 3)) return 8;
+    if (!strncmp(f, "ts", 2) || !strncmp(f, "tD", 2)) return 8;
+    if (!strncmp(f, "tiM", 3)) return 4;
+    if (!strncmp(f, "tiD", 3)) return 8;
+    if (!strncmp(f, "tin", 3)) return 16;
+    return 0;
+  }
+  if (f[0] == 'd' && f[1] == ':') {  // decimal: d:p,s[,bits]
+    int p = 0, s = 0, bits = 128;
+    if (sscanf(f, "d:%d,%d,%d", &p, &s, &bits) >= 2) return bits / 8;
+    return 0;
+  }
+  if (f[0] == 'w' && f[1] == ':') return atoi(f + 2);
+  return 0;
+}
+
+// output format of an input field (string views and dictionary-encoded strings come out as large_utf8)
+std::string out_format(const ArrowSchema *f, bool *ok) {
+  *ok = true;
+  if (f->dictionary) {
+    if (str_kind(f->dictionary->format) != StrKind::None && is_int_format(f->format)) return "U";
+    *ok = false;
+    return "";
+  }
+  StrKind k = str_kind(f->format);
+  if (k == StrKind::View) return f->format[1] == 'u' ? "U" : "Z";
+  if (k != StrKind::None) return f->format;
+  if (!strcmp(f->format, "b") || !strcmp(f->format, "n") || fixed_width(f->format) > 0) return f->format;
+  *ok = false;
+  return "";
+}
+
+// Gather rows of one column into a fresh owned array.  rows[i] == PBGPU_NO_PARTNER -> null.
+int gather_column(const Table &t, int col, const uint32_t *rows, int64_t n, ArrowArray *out) {
+  const ArrowSchema *f = t.schema.children[col];
+  std::unique_ptr<OwnedArray> o(new OwnedArray());
+  const int64_t nchunks = (n + kChunk - 1) / kChunk;
+  const size_t vbytes = (size_t)((n + 7) / 8);
+  uint8_t *valid = (uint8_t *)calloc(vbytes ? vbytes : 1, 1);
+  if (!valid) return set_error(PBGPU_ENOMEM, "host allocation failed");
+  o->bufs.push_back(valid);
+  std::vector<int64_t> chunk_nulls((size_t)std::max<int64_t>(nchunks, 1), 0);
+  const bool is_dict = f->dictionary != nullptr;
+  const StrKind sk = str_kind(is_dict ? f->dictionary->format : f->format);
+  const int w = (!is_dict && sk == StrKind::None) ? fixed_width(f->format) : 0;
+  const bool is_bool = !is_dict && !strcmp(f->format, "b");
+  const bool is_null_type = !is_dict && !strcmp(f->format, "n");
+
+  auto src_valid = [&](const ArrowArray *a, int64_t j) -> bool {
+    return a->null_count == 0 || !a->buffers[0] || bit_get((const uint8_t *)a->buffers[0], j);
+  };
+
+  if (is_null_type) {
+    o->bptr = {};  // null arrays carry no buffers
+    ArrowArray a = finish_array(o.release(), n, n);
+    *out = a;
+    return PBGPU_OK;
+  }
+  if (w > 0 || is_bool) {
+    uint8_t *vals = (uint8_t *)(is_bool ? calloc(vbytes ? vbytes : 1, 1) : malloc((size_t)n * w + 1));
+    if (!vals) return set_error(PBGPU_ENOMEM, "host allocation failed");
+    o->bufs.push_back(vals);
+    // chunk boundaries are multiples of 8 rows, so bitmap bytes are private to a chunk
+    Pool::get().parallel_for(nchunks, [&](int64_t ci) {
+      const int64_t lo = ci * kChunk, hi = std::min(n, lo + kChunk);
+      int64_t nulls = 0;
+      for (int64_t i = lo; i < hi; ++i) {
+        const uint32_t r = rows[i];
+        if (r == PBGPU_NO_PARTNER) { ++nulls; if (!is_bool) memset(vals + (size_t)i * w, 0, w); continue; }
+        int b; int64_t li;
+        t.locate(r, b, li);
+        const ArrowArray &ba = t.batches[b];
+        const ArrowArray *a = ba.children[col];
+        const int64_t j = li + a->offset + ba.offset;
+        if (!src_valid(a, j)) { ++nulls; if (!is_bool) memset(vals + (size_t)i * w, 0, w); continue; }
+        bit_set(valid, i);
+        if (is_bool) { if (bit_get((const uint8_t *)a->buffers[1], j)) bit_set(vals, i); }
+        else memcpy(vals + (size_t)i * w, (const uint8_t *)a->buffers[1] + (size_t)j * w, w);
+      }
+      chunk_nulls[ci] = nulls;
+    });
+    int64_t nulls = 0;
+    for (auto v : chunk_nulls) nulls += v;
+    o->bptr = {nulls ? (const void *)valid : nullptr, vals};
+    *out = finish_array(o.release(), n, nulls);
+    return PBGPU_OK;
+  }
+  if (sk != StrKind::None) {
+    const bool large = is_dict || sk != StrKind::Utf8;  // views / dictionaries come out as large_utf8
+    // pass 1: lengths
+    std::vector<int64_t> chunk_bytes((size_t)std::max<int64_t>(nchunks, 1), 0);
+    std::vector<uint32_t> lens((size_t)n);
+    auto fetch = [&](uint32_t r, std::string_view *sv) -> bool {
+      if (r == PBGPU_NO_PARTNER) return false;
+      int b; int64_t li;
+      t.locate(r, b, li);
+      const ArrowArray &ba = t.batches[b];
+      const ArrowArray *a = ba.children[col];
+      const int64_t j = li + a->offset + ba.offset;
+      if (!src_valid(a, j)) return false;
+      if (is_dict) {
+        const ArrowArray *d = a->dictionary;
+        const int64_t k = int_at(a->buffers[1], f->format[0], j);
+        if (k < 0 || k >= d->length || !src_valid(d, k + d->offset)) return false;
+        *sv = str_at(d, sk, k + d->offset);
+      } else *sv = str_at(a, sk, j);
+      return true;
+    };
+    Pool::get().parallel_for(nchunks, [&](int64_t ci) {
+      const int64_t lo = ci * kChunk, hi = std::min(n, lo + kChunk);
+      int64_t nulls = 0, bytes = 0;
+      for (int64_t i = lo; i < hi; ++i) {
+        std::string_view sv;
+        if (fetch(rows[i], &sv)) { bit_set(valid, i); lens[i] = (uint32_t)sv.size(); bytes += (int64_t)sv.size(); }
+        else { ++nulls; lens[i] = 0; }
+      }
+      chunk_nulls[ci] = nulls;
+      chunk_bytes[ci] = bytes;
+    });
+    int64_t total = 0, nulls = 0;
+    std::vector<int64_t> chunk_off((size_t)std::max<int64_t>(nchunks, 1), 0);
+    for (int64_t ci = 0; ci < nchunks; ++ci) { chunk_off[ci] = total; total += chunk_bytes[ci]; nulls += chunk_nulls[ci]; }
+    if (!large && total > INT32_MAX)
+      return set_error(PBGPU_ERANGE, "utf8 column '%s' would exceed 2 GiB in one output batch; lower max_batch_rows or use large_utf8", f->name);
+    void *offs = malloc((size_t)(n + 1) * (large ? 8 : 4));
+    char *data = (char *)malloc((size_t)total + 1);
+    if (!offs || !data) { free(offs); free(data); return set_error(PBGPU_ENOMEM, "host allocation failed"); }
+    o->bufs.push_back(offs);
+    o->bufs.push_back(data);
+    Pool::get().parallel_for(nchunks, [&](int64_t ci) {
+      const int64_t lo = ci * kChunk, hi = std::min(n, lo + kChunk);
+      int64_t pos = chunk_off[ci];
+      for (int64_t i = lo; i < hi; ++i) {
+        if (large) ((int64_t *)offs)[i] = pos; else ((int32_t *)offs)[i] = (int32_t)pos;
+        if (lens[i]) {
+          std::string_view sv;
+          fetch(rows[i], &sv);
+          memcpy(data + pos, sv.data(), sv.size());
+          pos += (int64_t)sv.size();
+        }
+      }
+    });
+    if (large) ((int64_t *)offs)[n] = total; else ((int32_t *)offs)[n] = (int32_t)total;
+    o->bptr = {nulls ? (const void *)valid : nullptr, offs, data};
+    *out = finish_array(o.release(), n, nulls);
+    return PBGPU_OK;
+  }
+  return set_error(PBGPU_ESCHEMA, "payload column '%s' has unsupported Arrow type '%s' for materialised output (use emit=1 index pairs)",
+                   f->name, f->format);
+}
+
+template <typename T>
+int plain_column(const T *src, int64_t n, const uint8_t *null_if_zero_flag, ArrowArray *out) {
+  (void)null_if_zero_flag;
+  std::unique_ptr<OwnedArray> o(new OwnedArray());
+  T *v = (T *)malloc(sizeof(T) * (size_t)(n ? n : 1));
+  if (!v) return set_error(PBGPU_ENOMEM, "host allocation failed");
+  memcpy(v, src, sizeof(T) * (size_t)n);
+  o->bufs.push_back(v);
+  o->bptr = {nullptr, v};
+  *out = finish_array(o.release(), n, 0);
+  return PBGPU_OK;
+}
+
+// int64 column where value < 0 means null (nearest distance)
+int nullable_i64_column(const int64_t *src, int64_t n, ArrowArray *out) {
+  std::unique_ptr<OwnedArray> o(new OwnedArray());
+  int64_t *v = (int64_t *)malloc(8 * (size_t)(n ? n : 1));
+  uint8_t *valid = (uint8_t *)calloc((size_t)((n + 7) / 8) + 1, 1);
+  if (!v || !valid) { free(v); free(valid); return set_error(PBGPU_ENOMEM, "host allocation failed"); }
+  o->bufs.push_back(valid);
+  o->bufs.push_back(v);
+  int64_t nulls = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    if (src[i] < 0) { v[i] = 0; ++nulls; }
+    else { v[i] = src[i]; bit_set(valid, i); }
+  }
+  o->bptr = {nulls ? (const void *)valid : nullptr, v};
+  *out = finish_array(o.release(), n, nulls);
+  return PBGPU_OK;
+}
+
+int nullable_u32_column(const uint32_t *src, int64_t n, ArrowArray *out) {
+  std::unique_ptr<OwnedArray> o(new OwnedArray());
+  uint32_t *v = (uint32_t *)malloc(4 * (size_t)(n ? n : 1));
+  uint8_t *valid = (uint8_t *)calloc((size_t)((n + 7) / 8) + 1, 1);
+  if (!v || !valid) { free(v); free(valid); return set_error(PBGPU_ENOMEM, "host allocation failed"); }
+  o->bufs.push_back(valid);
+  o->bufs.push_back(v);
+  int64_t nulls = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    if (src[i] == PBGPU_NO_PARTNER) { v[i] = 0; ++nulls; }
+    else { v[i] = src[i]; bit_set(valid, i); }
+  }
+  o->bptr = {nulls ? (const void *)valid : nullptr, v};
+  *out = finish_array(o.release(), n, nulls);
+  return PBGPU_OK;
+}
+
+// ---- the output stream ---------------------------------------------------------------------------
+struct OutStream {
+  std::unique_ptr<Table> left, right;
+  PbRangeOptions opt{};
+  std::string suffix1 = "_1", suffix2 = "_2";
+  PinnedHold pins;           // result arrays live in cached pinned memory until release
+  int64_t n_out = 0;         // result rows
+  const uint32_t *lrow = nullptr;  // per result row: row of `left`  (may be NULL when not needed)
+  const uint32_t *rrow = nullptr;  // per result row: row of `right` (PBGPU_NO_PARTNER = null)
+  const int64_t *extra = nullptr;  // count / coverage / distance (distance < 0 = null)
+  std::vector<uint32_t> own_l, own_r;  // host-built row lists (nearest expansion, distinct)
+  std::vector<int64_t> own_x;
+  int64_t cursor = 0;
+  uint32_t batch_rows = 1 << 20;
+  std::string last_error;
+};
+
+bool want_distance(const PbRangeOptions &o) { return o.range_op == PBGPU_OP_NEAREST && o.compute_distance; }
+
+int out_get_schema(ArrowArrayStream *s, ArrowSchema *out) {
+  OutStream *st = (OutStream *)s->private_data;
+  const PbRangeOptions &o = st->opt;
+  std::vector<ArrowSchema> kids;
+  auto add_table = [&](const Table &t, const std::string &suffix, bool force_nullable) -> int {
+    for (int64_t i = 0; i < t.schema.n_children; ++i) {
+      const ArrowSchema *f = t.schema.children[i];
+      bool ok;
+      std::string fmt = out_format(f, &ok);
+      if (!ok) { st->last_error = std::string("unsupported payload type '") + f->format + "' in column '" + f->name + "'"; return 1; }
+      int64_t flags = f->flags | (force_nullable ? ARROW_FLAG_NULLABLE : 0);
+      kids.push_back(make_schema(fmt, std::string(f->name) + suffix, f->metadata, flags));
+    }
+    return 0;
+  };
+  int rc = 0;
+  if (o.emit == 1) {
+    kids.push_back(make_schema("I", "left_row", nullptr, 0));
+    kids.push_back(make_schema("I", "right_row", nullptr, o.range_op == PBGPU_OP_NEAREST ? ARROW_FLAG_NULLABLE : 0));
+    if (want_distance(o)) kids.push_back(make_schema("l", "distance", nullptr, ARROW_FLAG_NULLABLE));
+  } else if (o.range_op == PBGPU_OP_OVERLAP) {
+    if (o.output_mode == PBGPU_OUT_JOIN) { rc = add_table(*st->left, st->suffix1, false); if (!rc) rc = add_table(*st->right, st->suffix2, false); }
+    else rc = add_table(*st->left, "", false);
+  } else if (o.range_op == PBGPU_OP_NEAREST) {
+    rc = add_table(*st->left, st->suffix1, false);
+    if (!rc) rc = add_table(*st->right, st->suffix2, true);
+    if (!rc && want_distance(o)) kids.push_back(make_schema("l", "distance", nullptr, ARROW_FLAG_NULLABLE));
+  } else {  // count_overlaps / coverage: the iterated table's rows + one int64 column (operation.rs:316-347)
+    rc = add_table(*st->right, "", false);
+    if (!rc) kids.push_back(make_schema("l", o.range_op == PBGPU_OP_COVERAGE ? "coverage" : "count", nullptr, 0));
+  }
+  if (rc) {
+    for (auto &k : kids) k.release(&k);
+    return 22;  // EINVAL
+  }
+  *out = make_schema("+s", "", nullptr, 0, std::move(kids));
+  return 0;
+}
+
+int out_get_next(ArrowArrayStream *s, ArrowArray *out) {
+  OutStream *st = (OutStream *)s->private_data;
+  const PbRangeOptions &o = st->opt;
+  memset(out, 0, sizeof(*out));
+  if (st->cursor >= st->n_out) return 0;  // end of stream: released (release == NULL) array
+  const int64_t lo = st->cursor, n = std::min<int64_t>(st->batch_rows, st->n_out - lo);
+  std::unique_ptr<OwnedArray> top(new OwnedArray());
+  int rc = PBGPU_OK;
+  auto push = [&](ArrowArray &&a) { top->kids.push_back(a); };
+  auto add_table = [&](const Table &t, const uint32_t *rows) {
+    for (int c = 0; c < (int)t.n_cols() && rc == PBGPU_OK; ++c) {
+      ArrowArray a{};
+      rc = gather_column(t, c, rows + lo, n, &a);
+      if (rc == PBGPU_OK) push(std::move(a));
+    }
+  };
+  std::vector<uint32_t> iota;
+  if (o.emit == 1) {
+    ArrowArray a{};
+    rc = plain_column<uint32_t>(st->lrow + lo, n, nullptr, &a);
+    if (rc == PBGPU_OK) { push(std::move(a)); ArrowArray b{}; rc = o.range_op == PBGPU_OP_NEAREST ? nullable_u32_column(st->rrow + lo, n, &b) : plain_column<uint32_t>(st->rrow + lo, n, nullptr, &b); if (rc == PBGPU_OK) push(std::move(b)); }
+    if (rc == PBGPU_OK && want_distance(o)) { ArrowArray d{}; rc = nullable_i64_column(st->extra + lo, n, &d); if (rc == PBGPU_OK) push(std::move(d)); }
+  } else if (o.range_op == PBGPU_OP_OVERLAP) {
+    add_table(*st->left, st->lrow);
+    if (o.output_mode == PBGPU_OUT_JOIN) add_table(*st->right, st->rrow);
+  } else if (o.range_op == PBGPU_OP_NEAREST) {
+    add_table(*st->left, st->lrow);
+    add_table(*st->right, st->rrow);
+    if (rc == PBGPU_OK && want_distance(o)) { ArrowArray d{}; rc = nullable_i64_column(st->extra + lo, n, &d); if (rc == PBGPU_OK) push(std::move(d)); }
+  } else {
+    iota.resize((size_t)n);
+    for (int64_t i = 0; i < n; ++i) iota[i] = (uint32_t)(lo + i);
+    add_table(*st->right, iota.data() - lo);
+    if (rc == PBGPU_OK) { ArrowArray d{}; rc = plain_column<int64_t>(st->extra + lo, n, nullptr, &d); if (rc == PBGPU_OK) push(std::move(d)); }
+  }
+  if (rc != PBGPU_OK) {
+    st->last_error = pbgpu::g_err;
+    for (auto &k : top->kids) if (k.release) k.release(&k);
+    return 5;  // EIO
+  }
+  top->bptr = {nullptr};  // struct validity
+  *out = finish_array(top.release(), n, 0);
+  st->cursor += n;
+  return 0;
+}
+
+const char *out_last_error(ArrowArrayStream *s) {
+  OutStream *st = (OutStream *)s->private_data;
+  return st->last_error.empty() ? nullptr : st->last_error.c_str();
+}
+void out_release(ArrowArrayStream *s) {
+  if (!s || !s->release) return;
+  delete (OutStream *)s->private_data;
+  s->release = nullptr;
+}
+
+struct DevBufs {  // device scratch of one call, freed stream-ordered
+  cudaStream_t s;
+  std::vector<void *> v;
+  template <typename T>
+  T *get(size_t count) {
+    void *p = nullptr;
+    if (cudaMallocAsync(&p, sizeof(T) * (count ? count : 1), s) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    v.push_back(p);
+    return (T *)p;
+  }
+  ~DevBufs() { for (void *p : v) cudaFreeAsync(p, s); }
+};
+
+#define BR_CUDA(expr)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess) return set_error(PBGPU_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+#define BR_TRY(expr) do { int _rc = (expr); if (_rc != PBGPU_OK) return _rc; } while (0)
+
+int run(Table *L, Table *R, OutStream *os) {
+  const PbRangeOptions &o = os->opt;
+  // roles: which table is indexed, which is iterated (see pbgpu.h)
+  //   overlap: probe/iterate = left (df1), index = right (df2)             operation.rs:253-263
+  //   nearest: iterate = left (df1), index = right (df2)                   operation.rs:143-158
+  //   count/coverage: index = left (s1), iterate = right (s2), rows of right returned   operation.rs:316-340
+  const bool iter_is_left = (o.range_op == PBGPU_OP_OVERLAP || o.range_op == PBGPU_OP_NEAREST);
+  Table *IT = iter_is_left ? L : R, *IX = iter_is_left ? R : L;
+  ContigDict dict;
+  PinnedHold stage;  // input staging: returned to the cache when this call ends
+  const int64_t n = IT->rows, m = IX->rows;
+  int32_t *hc_i = stage.get<int32_t>(n), *hs_i = stage.get<int32_t>(n), *he_i = stage.get<int32_t>(n);
+  int32_t *hc_x = stage.get<int32_t>(m), *hs_x = stage.get<int32_t>(m), *he_x = stage.get<int32_t>(m);
+  if (!hc_i || !hs_i || !he_i || !hc_x || !hs_x || !he_x) return set_error(PBGPU_ENOMEM, "pinned staging allocation failed");
+  BR_TRY(encode_keys(*IX, iter_is_left ? "right" : "left", dict, hc_x, hs_x, he_x));
+  BR_TRY(encode_keys(*IT, iter_is_left ? "left" : "right", dict, hc_i, hs_i, he_i));
+  const int32_t n_contigs = (int32_t)dict.map.size();
+
+  int prev_dev = -1;
+  if (o.device >= 0) { BR_CUDA(cudaGetDevice(&prev_dev)); BR_CUDA(cudaSetDevice(o.device)); }
+  struct DevRestore { int d; ~DevRestore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev};
+  cudaStream_t s;
+  BR_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamSynchronize(s); cudaStreamDestroy(s); } } sg{s};
+  DevBufs dev{s, {}};
+  int32_t *dc_x = dev.get<int32_t>(m), *ds_x = dev.get<int32_t>(m), *de_x = dev.get<int32_t>(m);
+  int32_t *dc_i = dev.get<int32_t>(n), *ds_i = dev.get<int32_t>(n), *de_i = dev.get<int32_t>(n);
+  if (!dc_x || !ds_x || !de_x || !dc_i || !ds_i || !de_i) return set_error(PBGPU_ENOMEM, "device allocation failed");
+  BR_CUDA(cudaMemcpyAsync(dc_x, hc_x, 4 * (size_t)m, cudaMemcpyHostToDevice, s));
+  BR_CUDA(cudaMemcpyAsync(ds_x, hs_x, 4 * (size_t)m, cudaMemcpyHostToDevice, s));
+  BR_CUDA(cudaMemcpyAsync(de_x, he_x, 4 * (size_t)m, cudaMemcpyHostToDevice, s));
+  BR_CUDA(cudaMemcpyAsync(dc_i, hc_i, 4 * (size_t)n, cudaMemcpyHostToDevice, s));
+  BR_CUDA(cudaMemcpyAsync(ds_i, hs_i, 4 * (size_t)n, cudaMemcpyHostToDevice, s));
+  BR_CUDA(cudaMemcpyAsync(de_i, he_i, 4 * (size_t)n, cudaMemcpyHostToDevice, s));
+
+  pbgpu_index *ix = nullptr;
+  BR_TRY(pbgpu_index_build(dc_x, ds_x, de_x, m, n_contigs, s, &ix));
+  struct IxGuard { pbgpu_index *p; ~IxGuard() { pbgpu_index_free(p); } } ig{ix};
+  const uint64_t limit = o.limit;
+
+  if (o.range_op == PBGPU_OP_COUNT_OVERLAPS_NAIVE || o.range_op == PBGPU_OP_COVERAGE) {
+    int64_t *d_out = dev.get<int64_t>(n);
+    int64_t *h_out = os->pins.get<int64_t>(n);
+    if (!d_out || !h_out) return set_error(PBGPU_ENOMEM, "allocation failed");
+    if (o.range_op == PBGPU_OP_COVERAGE) BR_TRY(pbgpu_coverage(ix, dc_i, ds_i, de_i, n, o.filter_op, d_out, s));
+    else BR_TRY(pbgpu_count_overlaps(ix, dc_i, ds_i, de_i, n, o.filter_op, d_out, s));
+    BR_CUDA(cudaMemcpyAsync(h_out, d_out, 8 * (size_t)n, cudaMemcpyDeviceToHost, s));
+    BR_CUDA(cudaStreamSynchronize(s));
+    os->extra = h_out;
+    os->n_out = n;
+  } else if (o.range_op == PBGPU_OP_OVERLAP && o.output_mode == PBGPU_OUT_LEFT_DISTINCT) {
+    int64_t *d_out = dev.get<int64_t>(n);
+    int64_t *h_out = stage.get<int64_t>(n);
+    if (!d_out || !h_out) return set_error(PBGPU_ENOMEM, "allocation failed");
+    BR_TRY(pbgpu_count_overlaps(ix, dc_i, ds_i, de_i, n, o.filter_op, d_out, s));
+    BR_CUDA(cudaMemcpyAsync(h_out, d_out, 8 * (size_t)n, cudaMemcpyDeviceToHost, s));
+    BR_CUDA(cudaStreamSynchronize(s));
+    for (int64_t i = 0; i < n; ++i) if (h_out[i] > 0) os->own_l.push_back((uint32_t)i);
+    os->lrow = os->own_l.data();
+    os->rrow = os->own_l.data();  // unused in Left modes; keeps emit=1 well defined
+    os->n_out = (int64_t)os->own_l.size();
+  } else if (o.range_op == PBGPU_OP_OVERLAP) {
+    pbgpu_overlap_plan *plan = nullptr;
+    int64_t total = 0;
+    BR_TRY(pbgpu_overlap_count(ix, dc_i, ds_i, de_i, n, o.filter_op, s, &plan, &total));
+    struct PlanGuard { pbgpu_overlap_plan *p; ~PlanGuard() { pbgpu_overlap_plan_free(p); } } pg{plan};
+    uint32_t *d_p = dev.get<uint32_t>((size_t)total), *d_b = dev.get<uint32_t>((size_t)total);
+    uint32_t *h_p = os->pins.get<uint32_t>((size_t)total), *h_b = os->pins.get<uint32_t>((size_t)total);
+    if (!d_p || !d_b || !h_p || !h_b) return set_error(PBGPU_ENOMEM, "allocation failed for %lld pairs", (long long)total);
+    BR_TRY(pbgpu_overlap_emit(plan, d_p, d_b, s));
+    BR_CUDA(cudaMemcpyAsync(h_p, d_p, 4 * (size_t)total, cudaMemcpyDeviceToHost, s));
+    BR_CUDA(cudaMemcpyAsync(h_b, d_b, 4 * (size_t)total, cudaMemcpyDeviceToHost, s));
+    BR_CUDA(cudaStreamSynchronize(s));
+    os->lrow = h_p;
+    os->rrow = h_b;
+    os->n_out = total;
+  } else if (o.range_op == PBGPU_OP_NEAREST) {
+    const int64_t k = o.nearest_k ? (int64_t)o.nearest_k : 1;
+    uint32_t *d_p = dev.get<uint32_t>((size_t)(n * k));
+    int64_t *d_d = dev.get<int64_t>((size_t)(n * k));
+    uint32_t *h_p = stage.get<uint32_t>((size_t)(n * k));
+    int64_t *h_d = stage.get<int64_t>((size_t)(n * k));
+    if (!d_p || !d_d || !h_p || !h_d) return set_error(PBGPU_ENOMEM, "allocation failed");
+    BR_TRY(pbgpu_nearest(ix, dc_i, ds_i, de_i, n, o.filter_op, k, o.include_overlaps, d_p, d_d, s));
+    BR_CUDA(cudaMemcpyAsync(h_p, d_p, 4 * (size_t)(n * k), cudaMemcpyDeviceToHost, s));
+    BR_CUDA(cudaMemcpyAsync(h_d, d_d, 8 * (size_t)(n * k), cudaMemcpyDeviceToHost, s));
+    BR_CUDA(cudaStreamSynchronize(s));
+    // expand: one row per found partner; a probe row with no partner at all yields one null-partner row
+    os->own_l.reserve((size_t)n); os->own_r.reserve((size_t)n); os->own_x.reserve((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+      bool any = false;
+      for (int64_t j = 0; j < k; ++j) {
+        if (h_p[i * k + j] == PBGPU_NO_PARTNER) break;
+        os->own_l.push_back((uint32_t)i); os->own_r.push_back(h_p[i * k + j]); os->own_x.push_back(h_d[i * k + j]);
+        any = true;
+      }
+      if (!any) { os->own_l.push_back((uint32_t)i); os->own_r.push_back(PBGPU_NO_PARTNER); os->own_x.push_back(-1); }
+    }
+    os->lrow = os->own_l.data(); os->rrow = os->own_r.data(); os->extra = os->own_x.data();
+    os->n_out = (int64_t)os->own_l.size();
+  } else {
+    return set_error(PBGPU_EINVAL, "unsupported range_op %d", o.range_op);
+  }
+  if (limit && (uint64_t)os->n_out > limit) os->n_out = (int64_t)limit;
+  return PBGPU_OK;
+}
+
+}  // namespace
+
+extern "C" int pbgpu_range_op(struct ArrowArrayStream *left, struct ArrowArrayStream *right, const PbRangeOptions *opts,
+                              struct ArrowArrayStream *out) {
+  // The inputs are moved: whatever happens below, both are released exactly once before returning.
+  struct Releaser { ArrowArrayStream *s; ~Releaser() { if (s && s->release) s->release(s); } } rl{left}, rr{right};
+  if (!opts || !out) return set_error(PBGPU_EINVAL, "opts/out is NULL");
+  if (opts->filter_op != PBGPU_FILTER_WEAK && opts->filter_op != PBGPU_FILTER_STRICT) return set_error(PBGPU_EINVAL, "bad filter_op %d", opts->filter_op);
+  if (opts->range_op != PBGPU_OP_OVERLAP && opts->range_op != PBGPU_OP_NEAREST && opts->range_op != PBGPU_OP_COVERAGE &&
+      opts->range_op != PBGPU_OP_COUNT_OVERLAPS_NAIVE)
+    return set_error(PBGPU_EINVAL, "range_op %d is not on the GPU hot path (overlap=0, nearest=3, coverage=4, count_overlaps=6)", opts->range_op);
+  if (opts->output_mode < PBGPU_OUT_JOIN || opts->output_mode > PBGPU_OUT_LEFT_DISTINCT) return set_error(PBGPU_EINVAL, "bad output_mode %d", opts->output_mode);
+  try {
+    std::unique_ptr<OutStream> os(new OutStream());
+    os->opt = *opts;
+    if (opts->suffixes[0]) os->suffix1 = opts->suffixes[0];
+    if (opts->suffixes[1]) os->suffix2 = opts->suffixes[1];
+    os->opt.suffixes[0] = os->opt.suffixes[1] = nullptr;
+    if (opts->max_batch_rows) os->batch_rows = opts->max_batch_rows;
+    os->batch_rows = (os->batch_rows + 7u) & ~7u;  // keep bitmap bytes chunk-private
+    os->left.reset(new Table());
+    os->right.reset(new Table());
+    int rc = drain(left, *os->left, "left");
+    if (rc == PBGPU_OK) rc = drain(right, *os->right, "right");
+    for (int i = 0; i < 3 && rc == PBGPU_OK; ++i) rc = find_col(*os->left, opts->cols1[i], "left", &os->left->key[i]);
+    for (int i = 0; i < 3 && rc == PBGPU_OK; ++i) rc = find_col(*os->right, opts->cols2[i], "right", &os->right->key[i]);
+    if (rc != PBGPU_OK) return rc;
+    os->opt.cols1[0] = os->opt.cols1[1] = os->opt.cols1[2] = nullptr;  // caller strings are not retained
+    os->opt.cols2[0] = os->opt.cols2[1] = os->opt.cols2[2] = nullptr;
+    rc = run(os->left.get(), os->right.get(), os.get());
+    if (rc != PBGPU_OK) return rc;
+    out->get_schema = out_get_schema;
+    out->get_next = out_get_next;
+    out->get_last_error = out_last_error;
+    out->release = out_release;
+    out->private_data = os.release();
+    return PBGPU_OK;
+  } catch (const std::bad_alloc &) {
+    return set_error(PBGPU_ENOMEM, "host allocation failed");
+  } catch (const std::exception &e) {
+    return set_error(PBGPU_EINVAL, "internal error: %s", e.what());
+  }
 }
