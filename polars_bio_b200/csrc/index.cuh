@@ -11,10 +11,32 @@
 //   en_sorted         ends sorted by (contig, end, start, row)  (rank identity:
 //                     count(a) = |{st < a.end}| - |{en <= a.start}|, range_op.py:548-594)
 //   en_pos            position in (st,en,row) order of every en_sorted entry (nearest upstream)
+// Fast path (no inverted rows, total coordinate span < 2^32): every contig is shifted to its own slice of
+// one global uint32 axis (G(c,p) = off[c] + clamp(p, lo_c-1, hi_c+1) - (lo_c-1)), which makes the two sorted
+// arrays globally monotone, and each gets a bucketed *rank directory*:
+//   gs, ge            global-axis starts (start order) / ends (end order), uint32[m]
+//   dir_s, dir_e      one 32-byte record per 2^shift-wide bucket of the axis: {rank of the bucket's first
+//                     entry | overflow flag, the bucket's first 7 keys (0xFFFFFFFF padded)}
+//                     -> rank(x) = base + #{keys < x}: ONE 32-byte sector per query instead of a 20-step
+//                     binary search; buckets holding more than 7 keys fall back to a search inside the bucket.
 #pragma once
 #include "common.cuh"
 #include "radix_sort.cuh"
 #include "scan.cuh"
+
+namespace pbgpu {
+struct ContigMap {   // per contig: position of its slice on the global axis
+  long long lo_m1;   // (smallest indexed coordinate) - 1
+  long long hi_p1;   // (largest indexed coordinate) + 1
+  uint32_t off;      // global coordinate of lo_m1
+  int32_t has;       // contig has indexed rows
+};
+struct alignas(32) DirRec {
+  uint32_t base;     // rank of the first entry of the bucket; bit 31 = bucket holds more than 7 entries
+  uint32_t key[7];
+};
+constexpr uint32_t kDirPad = 0xFFFFFFFFu;
+}  // namespace pbgpu
 
 struct pbgpu_index {
   int64_t m = 0;  // valid rows
@@ -25,12 +47,26 @@ struct pbgpu_index {
   int32_t *seg = nullptr;
   int32_t *st = nullptr, *en = nullptr, *pmax = nullptr, *en_sorted = nullptr;
   uint32_t *row = nullptr, *en_pos = nullptr;
+  // fast path
+  int fast = 0;
+  int shift = 0;
+  uint32_t n_buckets = 0;
+  pbgpu::ContigMap *cmap = nullptr;
+  uint32_t *gs = nullptr, *ge = nullptr;
+  pbgpu::DirRec *dir_s = nullptr, *dir_e = nullptr;
+  void *slab = nullptr, *slab2 = nullptr;  // two stream-ordered allocations back every array above
   size_t bytes = 0;
 };
 
 namespace pbgpu {
 
 struct IndexView {
+  const ContigMap *__restrict__ cmap;
+  const uint32_t *__restrict__ gs;
+  const uint32_t *__restrict__ ge;
+  const DirRec *__restrict__ dir_s;
+  const DirRec *__restrict__ dir_e;
+  int shift;
   const int32_t *__restrict__ seg;
   const int32_t *__restrict__ st;
   const int32_t *__restrict__ en;
@@ -43,7 +79,7 @@ struct IndexView {
 };
 
 inline IndexView view_of(const pbgpu_index *ix) {
-  return IndexView{ix->seg, ix->st, ix->en, ix->pmax, ix->en_sorted, ix->row, ix->en_pos, ix->n_contigs, ix->has_inverted};
+  return IndexView{ix->cmap, ix->gs, ix->ge, ix->dir_s, ix->dir_e, ix->shift, ix->seg, ix->st, ix->en, ix->pmax, ix->en_sorted, ix->row, ix->en_pos, ix->n_contigs, ix->has_inverted};
 }
 
 struct BuildStats {  // device-side reduction target
@@ -54,6 +90,8 @@ struct BuildStats {  // device-side reduction target
 __global__ void __launch_bounds__(256) build_stats_kernel(const int32_t *__restrict__ c, const int32_t *__restrict__ s,
                                                           const int32_t *__restrict__ e, int64_t n, int32_t n_contigs,
                                                           BuildStats *st) {
+  __shared__ int sm[4][8];
+  __shared__ unsigned su[2][8];
   int mn_s = INT32_MAX, mx_s = INT32_MIN, mn_e = INT32_MAX, mx_e = INT32_MIN;
   unsigned inv = 0, val = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -74,11 +112,19 @@ __global__ void __launch_bounds__(256) build_stats_kernel(const int32_t *__restr
     inv += __shfl_xor_sync(0xffffffffu, inv, d);
     val += __shfl_xor_sync(0xffffffffu, val, d);
   }
-  if ((threadIdx.x & 31) == 0) {
-    atomicMin(&st->min_start, mn_s); atomicMax(&st->max_start, mx_s);
-    atomicMin(&st->min_end, mn_e); atomicMax(&st->max_end, mx_e);
-    atomicAdd(&st->inverted, (unsigned long long)inv);
-    atomicAdd(&st->valid, (unsigned long long)val);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { sm[0][w] = mn_s; sm[1][w] = mx_s; sm[2][w] = mn_e; sm[3][w] = mx_e; su[0][w] = inv; su[1][w] = val; }
+  __syncthreads();
+  if (threadIdx.x == 0) {  // one set of atomics per block (per-warp atomics on six shared addresses cost 80 us at 1M rows)
+    for (int k = 1; k < 8; ++k) {
+      sm[0][0] = min(sm[0][0], sm[0][k]); sm[1][0] = max(sm[1][0], sm[1][k]);
+      sm[2][0] = min(sm[2][0], sm[2][k]); sm[3][0] = max(sm[3][0], sm[3][k]);
+      su[0][0] += su[0][k]; su[1][0] += su[1][k];
+    }
+    atomicMin(&st->min_start, sm[0][0]); atomicMax(&st->max_start, sm[1][0]);
+    atomicMin(&st->min_end, sm[2][0]); atomicMax(&st->max_end, sm[3][0]);
+    if (su[0][0]) atomicAdd(&st->inverted, (unsigned long long)su[0][0]);
+    atomicAdd(&st->valid, (unsigned long long)su[1][0]);
   }
 }
 
@@ -145,6 +191,73 @@ __global__ void __launch_bounds__(256) unpack_ends_kernel(const uint64_t *__rest
   if (i >= m) return;
   en_sorted[i] = (int32_t)((uint32_t)(ekeys[i] & ((1ull << pos_bits) - 1ull)) ^ bias_e);
   en_pos[i] = (uint32_t)evals[i];
+}
+
+// ---- fast-path construction ------------------------------------------------------------------
+// per contig: coordinate range of its indexed rows -> width of its slice on the global axis
+__global__ void __launch_bounds__(128) contig_span_kernel(const int32_t *__restrict__ seg, const int32_t *__restrict__ st,
+                                                          const int32_t *__restrict__ pmax, int32_t n_contigs,
+                                                          ContigMap *__restrict__ cmap, unsigned long long *__restrict__ span) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_contigs) return;
+  const int32_t lo = seg[c], hi = seg[c + 1];
+  ContigMap m;
+  m.off = 0;
+  if (lo >= hi) { m.lo_m1 = 0; m.hi_p1 = 0; m.has = 0; span[c] = 0; }
+  else {
+    m.lo_m1 = (long long)st[lo] - 1;          // rows are not inverted on this path: min coordinate = min start
+    m.hi_p1 = (long long)pmax[hi - 1] + 1;    // max coordinate = max end
+    m.has = 1;
+    span[c] = (unsigned long long)(m.hi_p1 - m.lo_m1 + 1);
+  }
+  cmap[c] = m;
+}
+__global__ void __launch_bounds__(128) contig_off_kernel(const unsigned long long *__restrict__ off, int32_t n_contigs,
+                                                         ContigMap *__restrict__ cmap) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n_contigs) cmap[c].off = (uint32_t)off[c];
+}
+// count positions where the running max differs from the end itself (0 <=> ends already sorted in start order)
+__global__ void __launch_bounds__(256) count_nested_kernel(const int32_t *__restrict__ en, const int32_t *__restrict__ pmax,
+                                                           int64_t m, unsigned long long *__restrict__ out) {
+  unsigned c = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) c += en[i] != pmax[i];
+#pragma unroll
+  for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
+}
+__global__ void __launch_bounds__(256) iota_ends_kernel(const int32_t *__restrict__ en, int64_t m, int32_t *__restrict__ en_sorted,
+                                                        uint32_t *__restrict__ en_pos) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) { en_sorted[i] = en[i]; en_pos[i] = (uint32_t)i; }
+}
+// global-axis coordinate of every sorted key (contig taken from the packed sort key)
+__global__ void __launch_bounds__(256) global_coord_kernel(const uint64_t *__restrict__ keys, int pos_bits, const int32_t *__restrict__ pos,
+                                                           int64_t m, const ContigMap *__restrict__ cmap, uint32_t *__restrict__ g) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const ContigMap cm = cmap[keys[i] >> pos_bits];
+  g[i] = cm.off + (uint32_t)((long long)pos[i] - cm.lo_m1);
+}
+// one thread per bucket: rank of its first entry by binary search (neighbouring buckets share their search
+// path, so the loads coalesce), then its first 7 keys
+__global__ void __launch_bounds__(256) build_dir_kernel(const uint32_t *__restrict__ g, int64_t m, int shift, uint32_t n_buckets,
+                                                        DirRec *__restrict__ dir) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > n_buckets) return;  // record n_buckets is the sentinel
+  DirRec r;
+  if (b == n_buckets) { r.base = (uint32_t)m; for (int k = 0; k < 7; ++k) r.key[k] = kDirPad; dir[b] = r; return; }
+  const uint64_t lo_key = (uint64_t)b << shift;
+  int64_t lo = 0, hi = m;
+  while (lo < hi) { int64_t mid = lo + ((hi - lo) >> 1); if ((uint64_t)g[mid] < lo_key) lo = mid + 1; else hi = mid; }
+  r.base = (uint32_t)lo;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    uint32_t v = (lo + k < m) ? g[lo + k] : kDirPad;
+    r.key[k] = (v != kDirPad && (v >> shift) == b) ? v : kDirPad;
+  }
+  if (lo + 7 < m && (g[lo + 7] >> shift) == b) r.base |= 0x80000000u;
+  dir[b] = r;
 }
 
 static inline int bit_length_u32(uint32_t x) {

@@ -108,8 +108,10 @@ void pbgpu_index_free(pbgpu_index *ix) {
   int cur = 0;
   cudaGetDevice(&cur);
   if (cur != ix->device) cudaSetDevice(ix->device);
-  cudaFree(ix->seg); cudaFree(ix->st); cudaFree(ix->en); cudaFree(ix->pmax);
-  cudaFree(ix->en_sorted); cudaFree(ix->row); cudaFree(ix->en_pos);
+  // stream-ordered free on the legacy default stream: ordered after everything blocking streams have queued;
+  // users of non-blocking streams synchronise before freeing (pbgpu.h)
+  if (ix->slab) cudaFreeAsync(ix->slab, 0);
+  if (ix->slab2) cudaFreeAsync(ix->slab2, 0);
   if (cur != ix->device) cudaSetDevice(cur);
   delete ix;
 }
@@ -117,36 +119,43 @@ void pbgpu_index_free(pbgpu_index *ix) {
 int64_t pbgpu_index_rows(const pbgpu_index *ix) { return ix ? ix->m : 0; }
 size_t pbgpu_index_bytes(const pbgpu_index *ix) { return ix ? ix->bytes : 0; }
 
+static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
 static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *d_s, const int32_t *d_e, int64_t m_in,
                             int32_t n_contigs, cudaStream_t s) {
   ix->m_in = m_in;
   ix->n_contigs = n_contigs;
   PB_CUDA(cudaGetDevice(&ix->device));
-  PB_CUDA(cudaMalloc(&ix->seg, sizeof(int32_t) * ((size_t)n_contigs + 2)));
-  ix->bytes = sizeof(int32_t) * ((size_t)n_contigs + 2);
-  if (m_in == 0) {
-    PB_CUDA(cudaMemsetAsync(ix->seg, 0, sizeof(int32_t) * ((size_t)n_contigs + 2), s));
-    return PBGPU_OK;
-  }
   StageTimer tm(s);
   Scratch sc(s);
   // 1. domain of the coordinates (decides key width and whether the rank identity is safe)
-  BuildStats *d_stats = nullptr;
-  PB_TRY(sc.get(&d_stats, 1));
-  BuildStats h0 = {INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN, 0ull, 0ull};
-  PB_CUDA(cudaMemcpyAsync(d_stats, &h0, sizeof(h0), cudaMemcpyHostToDevice, s));
-  {
-    int64_t grid = cdiv(m_in, 256);
-    if (grid > kSMs * 16) grid = kSMs * 16;
+  BuildStats hs = {INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN, 0ull, 0ull};
+  if (m_in > 0) {
+    BuildStats *d_stats = nullptr;
+    PB_TRY(sc.get(&d_stats, 1));
+    PB_CUDA(cudaMemcpyAsync(d_stats, &hs, sizeof(hs), cudaMemcpyHostToDevice, s));
+    int64_t grid = cdiv(m_in, 256 * 8);
+    if (grid > kSMs * 8) grid = kSMs * 8;
     PB_LAUNCH(build_stats_kernel, (unsigned)grid, 256, 0, s, d_c, d_s, d_e, m_in, n_contigs, d_stats);
     PB_CHECK_LAUNCH();
+    PB_CUDA(cudaMemcpyAsync(&hs, d_stats, sizeof(hs), cudaMemcpyDeviceToHost, s));
+    PB_CUDA(cudaStreamSynchronize(s));
   }
-  BuildStats hs;
-  PB_CUDA(cudaMemcpyAsync(&hs, d_stats, sizeof(hs), cudaMemcpyDeviceToHost, s));
-  PB_CUDA(cudaStreamSynchronize(s));
   const int64_t m = (int64_t)hs.valid;
   ix->m = m;
   ix->has_inverted = hs.inverted != 0;
+  // slab 1: seg + the six sorted arrays
+  const size_t seg_b = align_up(sizeof(int32_t) * ((size_t)n_contigs + 2)), arr_b = align_up(sizeof(int32_t) * (size_t)(m ? m : 1));
+  PB_TRY(dev_alloc(&ix->slab, seg_b + 6 * arr_b, s));
+  ix->bytes = seg_b + 6 * arr_b;
+  char *base = (char *)ix->slab;
+  ix->seg = (int32_t *)base;
+  ix->st = (int32_t *)(base + seg_b);
+  ix->en = (int32_t *)(base + seg_b + arr_b);
+  ix->pmax = (int32_t *)(base + seg_b + 2 * arr_b);
+  ix->en_sorted = (int32_t *)(base + seg_b + 3 * arr_b);
+  ix->row = (uint32_t *)(base + seg_b + 4 * arr_b);
+  ix->en_pos = (uint32_t *)(base + seg_b + 5 * arr_b);
   if (m == 0) {
     PB_CUDA(cudaMemsetAsync(ix->seg, 0, sizeof(int32_t) * ((size_t)n_contigs + 2), s));
     return PBGPU_OK;
@@ -169,11 +178,7 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
   PB_LAUNCH(find_segments_kernel, (unsigned)cdiv(n_contigs + 1, 64), 64, 0, s, keys, m_in, pos_bits, n_contigs, ix->seg);
   PB_CHECK_LAUNCH();
 
-  // 3. unpack + auxiliary arrays
-  const size_t mb = sizeof(int32_t) * (size_t)m;
-  PB_CUDA(cudaMalloc(&ix->st, mb)); PB_CUDA(cudaMalloc(&ix->en, mb)); PB_CUDA(cudaMalloc(&ix->pmax, mb));
-  PB_CUDA(cudaMalloc(&ix->en_sorted, mb)); PB_CUDA(cudaMalloc(&ix->row, mb)); PB_CUDA(cudaMalloc(&ix->en_pos, mb));
-  ix->bytes += 6 * mb;
+  // 3. unpack + running max of the ends
   uint64_t *pm_keys = nullptr, *ekeys = nullptr, *evals = nullptr;
   PB_TRY(sc.get(&pm_keys, (size_t)m));
   PB_TRY(sc.get(&ekeys, (size_t)m));
@@ -184,10 +189,68 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
   PB_TRY((device_scan<MaxU64, true>((const unsigned long long *)pm_keys, (unsigned long long *)pm_keys, m, nullptr, s)));
   PB_LAUNCH(unpack_pmax_kernel, (unsigned)cdiv(m, 256), 256, 0, s, pm_keys, m, ix->pmax);
   PB_CHECK_LAUNCH();
-  // 4. ends sorted per contig (stable over the start order -> ties keep (start,row) order)
-  PB_TRY(radix_sort_pairs(ekeys, evals, m, pos_bits + contig_bits, s));
-  PB_LAUNCH(unpack_ends_kernel, (unsigned)cdiv(m, 256), 256, 0, s, ekeys, evals, m, pos_bits, bias, ix->en_sorted, ix->en_pos);
+
+  // 4. one host round trip decides two things: are the ends already sorted in start order (no nested
+  //    intervals -> skip the second sort), and does the global axis fit 32 bits (fast path)?
+  const bool try_fast = !ix->has_inverted;
+  unsigned long long *d_meta = nullptr;  // [0] nested count, [1] total span
+  unsigned long long *d_span = nullptr;
+  PB_TRY(sc.get(&d_meta, 2));
+  PB_TRY(sc.get(&d_span, (size_t)n_contigs + 1));
+  ContigMap *d_cmap_tmp = nullptr;
+  PB_TRY(sc.get(&d_cmap_tmp, (size_t)n_contigs + 1));
+  PB_CUDA(cudaMemsetAsync(d_meta, 0, 2 * sizeof(unsigned long long), s));
+  {
+    int64_t grid = cdiv(m, 256 * 8);
+    if (grid > kSMs * 8) grid = kSMs * 8;
+    PB_LAUNCH(count_nested_kernel, (unsigned)grid, 256, 0, s, ix->en, ix->pmax, m, d_meta);
+    if (try_fast) {
+      PB_LAUNCH(contig_span_kernel, (unsigned)cdiv(n_contigs, 128), 128, 0, s, ix->seg, ix->st, ix->pmax, n_contigs, d_cmap_tmp, d_span);
+      PB_TRY((device_scan<SumU64, false>(d_span, d_span, n_contigs, d_meta + 1, s)));
+    }
+    PB_CHECK_LAUNCH();
+  }
+  unsigned long long h_meta[2] = {0, 0};
+  PB_CUDA(cudaMemcpyAsync(h_meta, d_meta, sizeof(h_meta), cudaMemcpyDeviceToHost, s));
+  PB_CUDA(cudaStreamSynchronize(s));
+  const bool nested = h_meta[0] != 0;
+
+  // 5. ends sorted per contig (stable over the start order -> ties keep (start,row) order)
+  if (nested) {
+    PB_TRY(radix_sort_pairs(ekeys, evals, m, pos_bits + contig_bits, s));
+    PB_LAUNCH(unpack_ends_kernel, (unsigned)cdiv(m, 256), 256, 0, s, ekeys, evals, m, pos_bits, bias, ix->en_sorted, ix->en_pos);
+  } else {
+    PB_LAUNCH(iota_ends_kernel, (unsigned)cdiv(m, 256), 256, 0, s, ix->en, m, ix->en_sorted, ix->en_pos);
+  }
   PB_CHECK_LAUNCH();
+
+  // 6. fast path: global axis + rank directories
+  const unsigned long long total_span = h_meta[1];
+  if (try_fast && total_span > 0 && total_span < 0xFFFFFFF0ull) {
+    int shift = 0;
+    while (shift < 31 && (total_span >> shift) > (unsigned long long)m) ++shift;  // about one indexed row per bucket
+    const uint32_t nb = (uint32_t)(total_span >> shift) + 1;
+    const size_t cm_b = align_up(sizeof(ContigMap) * ((size_t)n_contigs + 1)), g_b = align_up(4 * (size_t)m);
+    const size_t d_b = align_up(sizeof(DirRec) * ((size_t)nb + 1));
+    PB_TRY(dev_alloc(&ix->slab2, cm_b + 2 * g_b + 2 * d_b, s));
+    ix->bytes += cm_b + 2 * g_b + 2 * d_b;
+    char *b2 = (char *)ix->slab2;
+    ix->cmap = (ContigMap *)b2;
+    ix->gs = (uint32_t *)(b2 + cm_b);
+    ix->ge = (uint32_t *)(b2 + cm_b + g_b);
+    ix->dir_s = (DirRec *)(b2 + cm_b + 2 * g_b);
+    ix->dir_e = (DirRec *)(b2 + cm_b + 2 * g_b + d_b);
+    ix->shift = shift;
+    ix->n_buckets = nb;
+    PB_CUDA(cudaMemcpyAsync(ix->cmap, d_cmap_tmp, sizeof(ContigMap) * (size_t)n_contigs, cudaMemcpyDeviceToDevice, s));
+    PB_LAUNCH(contig_off_kernel, (unsigned)cdiv(n_contigs, 128), 128, 0, s, d_span, n_contigs, ix->cmap);
+    PB_LAUNCH(global_coord_kernel, (unsigned)cdiv(m, 256), 256, 0, s, keys, pos_bits, ix->st, m, ix->cmap, ix->gs);
+    PB_LAUNCH(global_coord_kernel, (unsigned)cdiv(m, 256), 256, 0, s, ekeys, pos_bits, ix->en_sorted, m, ix->cmap, ix->ge);
+    PB_LAUNCH(build_dir_kernel, (unsigned)cdiv((int64_t)nb + 1, 256), 256, 0, s, ix->gs, m, shift, nb, ix->dir_s);
+    PB_LAUNCH(build_dir_kernel, (unsigned)cdiv((int64_t)nb + 1, 256), 256, 0, s, ix->ge, m, shift, nb, ix->dir_e);
+    PB_CHECK_LAUNCH();
+    ix->fast = 1;
+  }
   g_times.partition_sort_ns = tm.stop_ns();
   return PBGPU_OK;
 }
@@ -229,7 +292,12 @@ int pbgpu_count_overlaps(const pbgpu_index *ix, const int32_t *d_contig, const i
   cudaStream_t s = (cudaStream_t)stream;
   StageTimer tm(s);
   const unsigned grid = (unsigned)cdiv(n, kSweepThreads);
-  if (filter_op == PBGPU_FILTER_STRICT)
+  if (ix->fast) {
+    if (filter_op == PBGPU_FILTER_STRICT)
+      PB_LAUNCH(count_overlaps_fast_kernel<true>, grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, d_counts);
+    else
+      PB_LAUNCH(count_overlaps_fast_kernel<false>, grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, d_counts);
+  } else if (filter_op == PBGPU_FILTER_STRICT)
     PB_LAUNCH(count_overlaps_kernel<true>, grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, d_counts);
   else
     PB_LAUNCH(count_overlaps_kernel<false>, grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, d_counts);
@@ -263,7 +331,9 @@ struct pbgpu_overlap_plan {
   int device;
   int64_t nblk;
   uint32_t *counts;                 // [n]
+  uint32_t *his;                    // [n] start-rank of every probe (fast path only)
   unsigned long long *block_base;   // [nblk] exclusive-scanned block totals
+  void *slab;                       // one stream-ordered allocation behind the three arrays
   int64_t total;
 };
 
@@ -274,8 +344,7 @@ void pbgpu_overlap_plan_free(pbgpu_overlap_plan *p) {
   int cur = 0;
   cudaGetDevice(&cur);
   if (cur != p->device) cudaSetDevice(p->device);
-  cudaFree(p->counts);
-  cudaFree(p->block_base);
+  if (p->slab) cudaFreeAsync(p->slab, 0);  // legacy stream: ordered after the emit kernel of blocking streams
   if (cur != p->device) cudaSetDevice(cur);
   delete p;
 }
@@ -291,18 +360,26 @@ int pbgpu_overlap_count(const pbgpu_index *ix, const int32_t *d_contig, const in
   cudaStream_t s = (cudaStream_t)stream;
   pbgpu_overlap_plan *p = new (std::nothrow) pbgpu_overlap_plan();
   if (!p) return set_error(PBGPU_ENOMEM, "host allocation failed");
-  *p = pbgpu_overlap_plan{ix, d_contig, d_start, d_end, n, filter_op, 0, cdiv(n, kSweepThreads), nullptr, nullptr, 0};
+  *p = pbgpu_overlap_plan{ix, d_contig, d_start, d_end, n, filter_op, 0, cdiv(n, kSweepThreads), nullptr, nullptr, nullptr, nullptr, 0};
   cudaGetDevice(&p->device);
   auto fail = [&](int rc) { pbgpu_overlap_plan_free(p); return rc; };
   if (n == 0) { *plan = p; return PBGPU_OK; }
-  if (cudaMalloc(&p->counts, sizeof(uint32_t) * (size_t)n) != cudaSuccess ||
-      cudaMalloc(&p->block_base, sizeof(unsigned long long) * (size_t)(p->nblk + 1)) != cudaSuccess) {
-    cudaGetLastError();
-    return fail(set_error(PBGPU_ENOMEM, "cudaMalloc for overlap plan failed (n=%lld)", (long long)n));
+  {
+    const size_t cb = align_up(sizeof(uint32_t) * (size_t)n), bb = align_up(sizeof(unsigned long long) * (size_t)(p->nblk + 1));
+    int rc0 = dev_alloc(&p->slab, 2 * cb + bb, s);
+    if (rc0 != PBGPU_OK) return fail(rc0);
+    p->counts = (uint32_t *)p->slab;
+    p->his = (uint32_t *)((char *)p->slab + cb);
+    p->block_base = (unsigned long long *)((char *)p->slab + 2 * cb);
   }
   StageTimer tm(s);
   const unsigned grid = (unsigned)p->nblk;
-  if (filter_op == PBGPU_FILTER_STRICT)
+  if (ix->fast) {
+    if (filter_op == PBGPU_FILTER_STRICT)
+      PB_LAUNCH(overlap_count_fast_kernel<true>, grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->his, p->block_base);
+    else
+      PB_LAUNCH(overlap_count_fast_kernel<false>, grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->his, p->block_base);
+  } else if (filter_op == PBGPU_FILTER_STRICT)
     PB_LAUNCH(overlap_count_kernel<true>, grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->block_base);
   else
     PB_LAUNCH(overlap_count_kernel<false>, grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->block_base);
@@ -329,7 +406,14 @@ int pbgpu_overlap_emit(const pbgpu_overlap_plan *p, uint32_t *d_probe_rows, uint
   cudaStream_t s = (cudaStream_t)stream;
   StageTimer tm(s);
   const unsigned grid = (unsigned)p->nblk;
-  if (p->filter_op == PBGPU_FILTER_STRICT)
+  if (p->ix->fast) {
+    if (p->filter_op == PBGPU_FILTER_STRICT)
+      PB_LAUNCH(overlap_emit_fast_kernel<true>, grid, kSweepThreads, 0, s, view_of(p->ix), p->pc, p->ps, p->pe, p->n, p->counts,
+                p->his, p->block_base, d_probe_rows, d_build_rows);
+    else
+      PB_LAUNCH(overlap_emit_fast_kernel<false>, grid, kSweepThreads, 0, s, view_of(p->ix), p->pc, p->ps, p->pe, p->n, p->counts,
+                p->his, p->block_base, d_probe_rows, d_build_rows);
+  } else if (p->filter_op == PBGPU_FILTER_STRICT)
     PB_LAUNCH(overlap_emit_kernel<true>, grid, kSweepThreads, 0, s, view_of(p->ix), p->pc, p->ps, p->pe, p->n, p->counts,
               p->block_base, d_probe_rows, d_build_rows);
   else

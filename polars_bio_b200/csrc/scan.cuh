@@ -124,12 +124,52 @@ __global__ void __launch_bounds__(kScanThreads) scan_final_kernel(const typename
   }
 }
 
+// whole scan in one block (one launch instead of three) for arrays up to a few hundred thousand entries:
+// the radix-sort digit tables of a ~1M-row index are 63K entries and sit on the launch-bound critical path
+template <typename Op, bool INCLUSIVE>
+__global__ void __launch_bounds__(1024) scan_single_block_kernel(const typename Op::T *__restrict__ in, typename Op::T *__restrict__ out,
+                                                                 int64_t n, typename Op::T *__restrict__ total_out) {
+  using T = typename Op::T;
+  constexpr int ITEMS = 4;
+  __shared__ T wt[1024 / 32 + 1];
+  __shared__ T carry_s;
+  if (threadIdx.x == 0) carry_s = Op::id();
+  __syncthreads();
+  for (int64_t base = 0; base < n; base += 1024 * ITEMS) {
+    T v[ITEMS];
+    T acc = Op::id();
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      const int64_t i = base + (int64_t)threadIdx.x * ITEMS + j;
+      v[j] = i < n ? in[i] : Op::id();
+      acc = Op::op(acc, v[j]);
+    }
+    T run = Op::op(carry_s, block_exclusive<Op, 1024>(acc, wt));
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      const int64_t i = base + (int64_t)threadIdx.x * ITEMS + j;
+      const T nxt = Op::op(run, v[j]);
+      if (i < n) out[i] = INCLUSIVE ? nxt : run;
+      run = nxt;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = Op::op(carry_s, wt[1024 / 32]);
+    __syncthreads();
+  }
+  if (total_out && threadIdx.x == 0) *total_out = carry_s;
+}
+
 // out may alias in.  d_total (optional, device) receives the grand total.
 template <typename Op, bool INCLUSIVE>
 int device_scan(const typename Op::T *in, typename Op::T *out, int64_t n, typename Op::T *d_total, cudaStream_t s) {
   using T = typename Op::T;
   if (n <= 0) {
     if (d_total) PB_CUDA(cudaMemsetAsync(d_total, 0, sizeof(T), s));
+    return PBGPU_OK;
+  }
+  if (n <= (1 << 18)) {
+    PB_LAUNCH((scan_single_block_kernel<Op, INCLUSIVE>), 1, 1024, 0, s, in, out, n, d_total);
+    PB_CHECK_LAUNCH();
     return PBGPU_OK;
   }
   const int64_t nblk = cdiv(n, kScanTile);

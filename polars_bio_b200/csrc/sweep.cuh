@@ -148,6 +148,162 @@ __global__ void __launch_bounds__(kSweepThreads) overlap_emit_kernel(IndexView i
   }
 }
 
+
+// =============================================================================================
+// Fast path: rank directory over the global coordinate axis (index.cuh).  One 32-byte sector per
+// rank query; the count is the sweep-line identity  |{st < a.end}| - |{en <= a.start}|  (Strict)
+// /  |{st <= a.end}| - |{en < a.start}|  (Weak)  (polars_bio/range_op.py:548-594).
+// =============================================================================================
+template <bool LE>  // LE: number of keys <= x ; else number of keys < x
+__device__ __forceinline__ uint32_t dir_rank(const DirRec *__restrict__ dir, const uint32_t *__restrict__ g, int shift, uint32_t x) {
+  const uint32_t b = x >> shift;
+  const uint4 lo = __ldg(reinterpret_cast<const uint4 *>(dir + b));
+  const uint4 hi = __ldg(reinterpret_cast<const uint4 *>(dir + b) + 1);
+  if (!(lo.x & 0x80000000u)) {
+    uint32_t n;
+    if (LE) n = (lo.y <= x) + (lo.z <= x) + (lo.w <= x) + (hi.x <= x) + (hi.y <= x) + (hi.z <= x) + (hi.w <= x);
+    else n = (lo.y < x) + (lo.z < x) + (lo.w < x) + (hi.x < x) + (hi.y < x) + (hi.z < x) + (hi.w < x);
+    return lo.x + n;
+  }
+  uint32_t a = lo.x & 0x7fffffffu, e = __ldg(&dir[b + 1].base) & 0x7fffffffu;  // crowded bucket: search inside it
+  while (a < e) {
+    const uint32_t mid = a + ((e - a) >> 1);
+    const uint32_t v = __ldg(g + mid);
+    if (LE ? (v <= x) : (v < x)) a = mid + 1; else e = mid;
+  }
+  return a;
+}
+
+constexpr uint32_t kGenericProbe = 0xFFFFFFFFu;  // pass-1 marker: this probe must take the generic window path
+
+// count of one probe on the fast path; hi_out = its rank among the starts (end of its candidate window)
+template <bool STRICT>
+__device__ __forceinline__ uint32_t fast_count(const IndexView &ix, int32_t c, int32_t s, int32_t e, uint32_t &hi_out) {
+  hi_out = 0;
+  if (c < 0 || c >= ix.n_contigs) return 0;
+  const ContigMap cm = ix.cmap[c];
+  if (!cm.has) return 0;
+  if (!(STRICT ? (s < e) : (s <= e))) {  // empty / inverted probe: identity not valid, bare predicate instead
+    hi_out = kGenericProbe;
+    return probe_count<STRICT>(ix, c, s, e);
+  }
+  long long ls = s, le = e;  // clamp into the contig's slice: order against every indexed coordinate is preserved
+  ls = ls < cm.lo_m1 ? cm.lo_m1 : (ls > cm.hi_p1 ? cm.hi_p1 : ls);
+  le = le < cm.lo_m1 ? cm.lo_m1 : (le > cm.hi_p1 ? cm.hi_p1 : le);
+  const uint32_t g_s = cm.off + (uint32_t)(ls - cm.lo_m1), g_e = cm.off + (uint32_t)(le - cm.lo_m1);
+  const uint32_t hi = STRICT ? dir_rank<false>(ix.dir_s, ix.gs, ix.shift, g_e) : dir_rank<true>(ix.dir_s, ix.gs, ix.shift, g_e);
+  const uint32_t re = STRICT ? dir_rank<true>(ix.dir_e, ix.ge, ix.shift, g_s) : dir_rank<false>(ix.dir_e, ix.ge, ix.shift, g_s);
+  hi_out = hi;
+  return hi - re;
+}
+
+template <bool STRICT>
+__global__ void __launch_bounds__(kSweepThreads) count_overlaps_fast_kernel(IndexView ix, const int32_t *__restrict__ pc,
+                                                                            const int32_t *__restrict__ ps,
+                                                                            const int32_t *__restrict__ pe, int64_t n,
+                                                                            int64_t *__restrict__ counts) {
+  int64_t i = (int64_t)blockIdx.x * kSweepThreads + threadIdx.x;
+  if (i >= n) return;
+  uint32_t hi;
+  counts[i] = (int64_t)fast_count<STRICT>(ix, pc[i], ps[i], pe[i], hi);
+}
+
+template <bool STRICT>
+__global__ void __launch_bounds__(kSweepThreads) overlap_count_fast_kernel(IndexView ix, const int32_t *__restrict__ pc,
+                                                                           const int32_t *__restrict__ ps,
+                                                                           const int32_t *__restrict__ pe, int64_t n,
+                                                                           uint32_t *__restrict__ counts, uint32_t *__restrict__ his,
+                                                                           unsigned long long *__restrict__ block_totals) {
+  __shared__ unsigned long long wt[kSweepThreads / 32];
+  int64_t i = (int64_t)blockIdx.x * kSweepThreads + threadIdx.x;
+  uint32_t cnt = 0;
+  if (i < n) {
+    uint32_t hi;
+    cnt = fast_count<STRICT>(ix, pc[i], ps[i], pe[i], hi);
+    counts[i] = cnt;
+    his[i] = hi;
+  }
+  unsigned long long v = cnt;
+#pragma unroll
+  for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  if ((threadIdx.x & 31) == 0) wt[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+#pragma unroll
+    for (int w = 0; w < kSweepThreads / 32; ++w) t += wt[w];
+    block_totals[blockIdx.x] = t;
+  }
+}
+
+// pass 2 on the fast path: the hits of a probe are the `cnt` entries below its start-rank `hi` whose end
+// reaches past the probe start, so walk down from hi-1 until cnt of them are found (exactly cnt steps when
+// the indexed intervals do not nest) and write them back to front: output stays ordered by (start,row).
+constexpr uint32_t kHeavyCount = 32;
+template <bool STRICT>
+__global__ void __launch_bounds__(kSweepThreads) overlap_emit_fast_kernel(IndexView ix, const int32_t *__restrict__ pc,
+                                                                          const int32_t *__restrict__ ps,
+                                                                          const int32_t *__restrict__ pe, int64_t n,
+                                                                          const uint32_t *__restrict__ counts,
+                                                                          const uint32_t *__restrict__ his,
+                                                                          const unsigned long long *__restrict__ block_base,
+                                                                          uint32_t *__restrict__ out_probe,
+                                                                          uint32_t *__restrict__ out_build) {
+  __shared__ unsigned long long wt[kSweepThreads / 32 + 1];
+  const int64_t i = (int64_t)blockIdx.x * kSweepThreads + threadIdx.x;
+  const uint32_t cnt = i < n ? counts[i] : 0u;
+  const unsigned long long pos = block_base[blockIdx.x] + block_exclusive<SumU64, kSweepThreads>((unsigned long long)cnt, wt);
+  uint32_t hi = 0;
+  int32_t s = 0;
+  if (cnt) { hi = his[i]; s = ps[i]; }
+  const bool generic = cnt && hi == kGenericProbe;
+  const bool heavy = cnt >= kHeavyCount && !generic;
+  if (generic) {  // rare: empty / inverted probe interval
+    int32_t lo, h2;
+    const int32_t c = pc[i];
+    probe_window<STRICT>(ix, ix.seg[c], ix.seg[c + 1], s, pe[i], lo, h2);
+    unsigned long long p = pos;
+    for (int32_t j = lo; j < h2; ++j)
+      if (end_hits<STRICT>(__ldg(ix.en + j), s)) { out_probe[p] = (uint32_t)i; out_build[p] = __ldg(ix.row + j); ++p; }
+  } else if (cnt && !heavy) {
+    uint32_t k = 0;
+    for (int64_t j = (int64_t)hi - 1; k < cnt && j >= 0; --j) {
+      if (end_hits<STRICT>(__ldg(ix.en + j), s)) {
+        const unsigned long long p = pos + (cnt - 1 - k);
+        out_probe[p] = (uint32_t)i;
+        out_build[p] = __ldg(ix.row + j);
+        ++k;
+      }
+    }
+  }
+  unsigned hm = __ballot_sync(0xffffffffu, heavy);
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = lanemask_lt();
+  while (hm) {  // many hits: the whole warp walks the window, 32 candidates per step, ballot-compacted stores
+    const int src = __ffs(hm) - 1;
+    hm &= hm - 1;
+    const uint32_t h = __shfl_sync(0xffffffffu, hi, src), c_all = __shfl_sync(0xffffffffu, cnt, src);
+    const int32_t ss = __shfl_sync(0xffffffffu, s, src);
+    const unsigned long long p0 = __shfl_sync(0xffffffffu, pos, src);
+    const uint32_t pi = (uint32_t)__shfl_sync(0xffffffffu, (unsigned long long)i, src);
+    uint32_t found = 0;
+    for (int64_t top = (int64_t)h - 1; found < c_all && top >= 0; top -= 32) {
+      const int64_t j = top - lane;  // lane 0 = highest position
+      const bool ok = j >= 0 && end_hits<STRICT>(__ldg(ix.en + j), ss);
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      if (ok) {
+        const uint32_t k = found + __popc(m & lt);
+        if (k < c_all) {
+          const unsigned long long p = p0 + (c_all - 1 - k);
+          out_probe[p] = pi;
+          out_build[p] = __ldg(ix.row + j);
+        }
+      }
+      found += __popc(m);
+    }
+  }
+}
+
 // ---- coverage: positions of the probe covered by the union of indexed rows -------------------
 template <bool STRICT>
 __global__ void __launch_bounds__(kSweepThreads) coverage_kernel(IndexView ix, const int32_t *__restrict__ pc,

@@ -138,6 +138,53 @@ def test_inverted_and_negative_coordinates(strict):
              ks=((1, True),))
 
 
+@pytest.mark.parametrize("strict", [True, False])
+def test_rank_directory_crowded_buckets_and_contig_edges(strict):
+    """Fast path specifics: many indexed rows per directory bucket (>7 -> in-bucket search), probes hanging over
+    the first/last indexed coordinate of a contig (clamping onto the global axis), neighbouring contigs whose
+    slices touch, and empty / inverted probe intervals (generic path inside the fast kernels)."""
+    rng = np.random.default_rng(21)
+    m = 6000
+    bc = rng.integers(0, 4, m).astype(np.int32)
+    centers = rng.choice([1000, 1010, 50_000, 50_003, 900_000], m)          # heavy clustering -> crowded buckets
+    bs = (centers + rng.integers(0, 6, m)).astype(np.int32)
+    be = (bs + rng.integers(1, 40, m)).astype(np.int32)
+    n = 8000
+    pc = rng.integers(0, 5, n).astype(np.int32)                              # contig 4 has no indexed rows
+    ps = rng.choice([0, 900, 995, 1040, 49_990, 899_990, 900_050, 2_000_000], n).astype(np.int32) + rng.integers(0, 30, n).astype(np.int32)
+    pe = (ps + rng.integers(0, 60, n)).astype(np.int32)                      # includes empty probes
+    pe[::13] = ps[::13] - 5                                                  # inverted probes
+    cnt = _run_all(pc, ps, pe, bc, bs, be, 5, strict, ks=((1, True), (2, False)))
+    assert cnt.max() > 64
+
+
+def test_span_beyond_32_bits_takes_generic_path():
+    # three contigs spanning ~2^31 each: the global axis does not fit uint32, the index must fall back
+    rng = np.random.default_rng(3)
+    m, n = 3000, 4000
+    bc = rng.integers(0, 3, m).astype(np.int32)
+    bs = rng.integers(0, 2**31 - 5000, m).astype(np.int32)
+    bs[:3] = 0; bs[3:6] = 2**31 - 4000
+    be = (bs + rng.integers(1, 3000, m)).astype(np.int32)
+    pc = rng.integers(0, 3, n).astype(np.int32)
+    ps = rng.integers(0, 2**31 - 5000, n).astype(np.int32)
+    pe = (ps + rng.integers(1, 4_000_000, n).clip(max=2**31 - 1 - ps.astype(np.int64))).astype(np.int32)
+    _run_all(pc, ps, pe, bc, bs, be, 3, True, ks=((1, True),))
+
+
+def test_int32_extremes():
+    # coordinates at the edge of the int32 domain: no end+1 / start-1 arithmetic may overflow
+    lo, hi = -2**31, 2**31 - 1
+    bc = np.zeros(6, np.int32)
+    bs = np.array([lo, lo, hi - 10, hi - 1, 0, hi], np.int32)
+    be = np.array([lo + 5, hi, hi, hi, 10, hi], np.int32)
+    pc = np.zeros(7, np.int32)
+    ps = np.array([lo, lo, hi - 5, hi, -5, hi - 1, lo + 5], np.int32)
+    pe = np.array([lo, lo + 1, hi, hi, 5, hi, lo + 6], np.int32)
+    for strict in (True, False):
+        _run_all(pc, ps, pe, bc, bs, be, 1, strict, ks=((1, True), (3, False)))
+
+
 def test_empty_inputs():
     eng = _engine()
     e = np.zeros(0, np.int32)
