@@ -166,6 +166,7 @@ def main():
     ap.add_argument("--variants", type=int, default=1_000_000)
     ap.add_argument("--cpu-sample", type=int, default=2_000_000, help="reads per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -204,15 +205,6 @@ def main():
         ix.close()
         return cnt, a, b
 
-    def step_e2e():
-        c = [x.to(dev, non_blocking=True) for x in h]
-        ix = engine.DeviceIndex(c[3], c[4], c[5], nc)
-        cnt = ix.count_overlaps(c[0], c[1], c[2], FO)
-        a, b = ix.overlap_pairs(c[0], c[1], c[2], FO)
-        ha, hb, hc = a.cpu(), b.cpu(), cnt.cpu()
-        ix.close()
-        return ha.numel(), ha.numel() * 8 + hc.numel() * 8
-
     for _ in range(max(args.warmup, 3)):
         cnt, a, b = step_device()
     pairs = a.numel()
@@ -228,7 +220,7 @@ def main():
     barrier()
     sampler.start()
     launches0 = _native.launch_count()
-    step_ms, stage_ms = [], []
+    step_ms, stage_ms, kern_ns = [], [], []
     for _ in range(args.steps):
         flush.fill_(1)  # L2 flush, outside the event bracket
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
@@ -238,6 +230,7 @@ def main():
         ev[4].synchronize()
         step_ms.append(ev[0].elapsed_time(ev[4]))
         stage_ms.append([ev[i].elapsed_time(ev[i + 1]) for i in range(3)])
+        kern_ns.append(_native.stage_times())  # the library's own events around each kernel of this step
         del cnt, a, b
     launches = _native.launch_count() - launches0
     barrier()
@@ -255,43 +248,64 @@ def main():
     ms_per_step = total_ms / args.steps
     value = pairs_all / (ms_per_step * 1e-3)
 
-    # per-kernel roofline: pass 2 (one launch of overlap_emit_kernel per step) and count_overlaps (one launch)
-    stage = np.mean(np.array(stage_ms), axis=0)  # build, count_overlaps, overlap(count+scan+emit)
+    # per-kernel roofline from the library's CUDA events (launching stream, inside the timed steps)
+    stage = np.mean(np.array(stage_ms), axis=0)  # build, count_overlaps, overlap(count+scan+sync+emit)
+    km = {k: float(np.mean([d[k] for d in kern_ns])) * 1e-6 for k in kern_ns[0]}  # ms
     peak, peak_src = measured_peak_gbs()
-
-    # e2e (host buffers, copies inside the timed region)
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps = max(3, min(args.steps, 5))
-    for _ in range(e2e_steps):
-        p_e2e, d2h = step_e2e()
-    torch.cuda.synchronize()
-    e2e_sec = (time.perf_counter() - t0) / e2e_steps
-    if world > 1:
-        t = torch.tensor([e2e_sec], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_sec = float(t.item())
-    h2d = sum(x.numel() * 4 for x in h)
-
-    # dominant-kernel timing: emit alone, events on the launching stream
-    ix = engine.DeviceIndex(dbc, dbs, dbe, nc)
-    kern = time_kernels(engine, ix, (dpc, dps, dpe), FO, flush, reps=max(5, args.steps))
-    ix.close()
     b_overlap = 12.0 * (n + m) + 8.0 * pairs
     b_count = 12.0 * (n + m) + 8.0 * n
     cands = {
-        "overlap_emit_kernel": (b_overlap, kern["emit_ms"]),
-        "count_overlaps_kernel": (b_count, kern["count_overlaps_ms"]),
-        "overlap_count_kernel": (12.0 * (n + m) + 4.0 * n, kern["pass1_ms"]),
+        "overlap_emit_fast_kernel (pass 2)": (b_overlap, km["emit_ns"]),
+        "count_overlaps_fast_kernel": (b_count, km["count_overlaps_ns"]),
+        "overlap_count_fast_kernel (pass 1)": (12.0 * (n + m) + 8.0 * n, km["count_ns"]),
     }
     dom = max(cands, key=lambda k: cands[k][1])
     ach = cands[dom][0] / (cands[dom][1] * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
             "traffic": None, "peak_source": peak_src, "algorithmic_bytes": cands[dom][0], "kernel_ms": cands[dom][1],
             "all_kernels": {k: {"ms": v[1], "algorithmic_bytes": v[0], "GBps": v[0] / (v[1] * 1e-3) / 1e9} for k, v in cands.items()},
+            "index_build_ms": km["partition_sort_ns"], "offset_scan_ms": km["scan_ns"],
             "step_stage_ms": {"index_build": float(stage[0]), "count_overlaps": float(stage[1]), "overlap_two_pass": float(stage[2])}}
+
+    # e2e: the public, reference-facing API (pb.count_overlaps + pb.overlap -> pbgpu_range_op) on HOST Arrow tables:
+    # contig strings are dictionary-encoded, columns staged to pinned memory, copied H2D, joined, pairs copied D2H and
+    # the reference's output frames (df1 rows + count; all df1/df2 columns suffixed) materialised on the host.
+    e2e = None
+    if not args.skip_e2e:
+        import pyarrow as pa
+
+        import polars_bio_b200 as pb
+
+        def table(cols):
+            c, s_, e_ = cols
+            t = pa.table({"contig": pa.array(np.full(len(c), "chr1")), "pos_start": pa.array(s_), "pos_end": pa.array(e_)})
+            return pb.set_coordinate_system(t, True)
+
+        reads_t, vars_t = table(probe), table(build)
+        cols = ("contig", "pos_start", "pos_end")
+
+        def step_api():
+            c = pb.count_overlaps(reads_t, vars_t, cols1=cols, cols2=cols, output_type="pyarrow.Table")
+            o = pb.overlap(reads_t, vars_t, cols1=cols, cols2=cols, output_type="pyarrow.Table")
+            return c.num_rows, o.num_rows
+
+        for _ in range(2):
+            step_api()
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps = max(3, min(args.steps, 5))
+        for _ in range(e2e_steps):
+            rows_c, rows_o = step_api()
+        torch.cuda.synchronize()
+        e2e_sec = (time.perf_counter() - t0) / e2e_steps
+        assert rows_o == pairs and rows_c == n
+        if world > 1:
+            t = torch.tensor([e2e_sec], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_sec = float(t.item())
+        e2e = {"value": pairs_all / e2e_sec, "unit": "pairs/s", "h2d_bytes_per_step": 2 * 12 * (n + m),
+               "d2h_bytes_per_step": 8 * n + 8 * pairs, "ms_per_step": e2e_sec * 1e3,
+               "api": "pb.count_overlaps + pb.overlap on host pyarrow Tables (utf8 contig), materialised pyarrow.Table outputs"}
 
     line = {
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
@@ -301,8 +315,7 @@ def main():
                    "pairs_per_step": pairs_all, "l2": "flushed between timed steps (256 MiB write)",
                    "parallelism": f"contig-sharded x{world}" if world > 1 else "single GPU"},
         "clocks": clocks,
-        "e2e": {"value": pairs_all / e2e_sec, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_sec * 1e3},
+        "e2e": e2e,
         "gpu_launches": int(launches),
         "roofline": roof,
     }
@@ -318,45 +331,6 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
-
-
-def time_kernels(engine, ix, probe, fo, flush, reps=5):
-    """CUDA-event durations of the single-launch stages on the launching (torch current) stream."""
-    import ctypes
-
-    import torch
-
-    from polars_bio_b200._native import check
-
-    dpc, dps, dpe = probe
-    n = dpc.numel()
-    L = ix._L
-    sp = engine._stream_ptr(ix.device)
-    out = torch.empty(n, dtype=torch.int64, device=ix.device)
-    res = {"count_overlaps_ms": [], "pass1_ms": [], "emit_ms": []}
-    for _ in range(reps + 1):
-        flush.fill_(2)
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
-        e[0].record()
-        check(L.pbgpu_count_overlaps(ix._h, dpc.data_ptr(), dps.data_ptr(), dpe.data_ptr(), n, fo, out.data_ptr(), sp))
-        e[1].record()
-        flush.fill_(3)
-        plan = ctypes.c_void_p(); total = ctypes.c_int64(0)
-        e[2].record()
-        check(L.pbgpu_overlap_count(ix._h, dpc.data_ptr(), dps.data_ptr(), dpe.data_ptr(), n, fo, sp, ctypes.byref(plan), ctypes.byref(total)))
-        e[3].record()
-        a = torch.empty(total.value, dtype=torch.int32, device=ix.device)
-        b = torch.empty(total.value, dtype=torch.int32, device=ix.device)
-        flush.fill_(4)
-        e[4].record()
-        check(L.pbgpu_overlap_emit(plan, a.data_ptr(), b.data_ptr(), sp))
-        e[5].record()
-        e[5].synchronize()
-        L.pbgpu_overlap_plan_free(plan)
-        res["count_overlaps_ms"].append(e[0].elapsed_time(e[1]))
-        res["pass1_ms"].append(e[2].elapsed_time(e[3]))
-        res["emit_ms"].append(e[4].elapsed_time(e[5]))
-    return {k: float(np.mean(v[1:])) for k, v in res.items()}
 
 
 if __name__ == "__main__":

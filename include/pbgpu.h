@@ -130,13 +130,15 @@ PBGPU_API int pbgpu_pack_by_owner(const int32_t *d_contig, const int32_t *d_star
                                   uint32_t row_id_base, int32_t *d_packed, int64_t *d_rank_counts,
                                   void *stream);
 
-/* CUDA-event timings (ns) of the stages of the most recent index build / overlap on this
- * thread when PBGPU_PROFILE=1 is set in the environment; zeros otherwise.                   */
+/* CUDA-event durations (ns) of the most recent index build / provider kernels issued by the calling
+ * thread, measured on the stream they were launched on (events are recorded on every call; this function
+ * waits for the last one).  A stage that has not run yet reads 0.                              */
 typedef struct {
-  uint64_t partition_sort_ns; /* contig radix partition + start sort + aux arrays            */
-  uint64_t count_ns;          /* pass 1                                                      */
-  uint64_t scan_ns;           /* offsets                                                     */
-  uint64_t emit_ns;           /* pass 2                                                      */
+  uint64_t partition_sort_ns;  /* pbgpu_index_build: contig partition + start sort + aux arrays + directories */
+  uint64_t count_ns;           /* overlap pass 1 kernel                                        */
+  uint64_t scan_ns;            /* pair-offset scan of pass 1                                   */
+  uint64_t emit_ns;            /* overlap pass 2 kernel                                        */
+  uint64_t count_overlaps_ns;  /* pbgpu_count_overlaps kernel                                  */
 } pbgpu_stage_times;
 PBGPU_API int pbgpu_last_stage_times(pbgpu_stage_times *out);
 

@@ -117,12 +117,14 @@ class Index:
         c, s, e = _c(chrom), _c(start), _c(end)
         lib = _load()
         args = (self._h, _p(c, _i32p), _p(s, _i32p), _p(e, _i32p), len(c), int(strict))
-        total = int(lib.pbo_overlap_pairs(*args, None, None, 0, threads))
-        a = np.empty(total, dtype=np.uint32)
-        b = np.empty(total, dtype=np.uint32)
-        if total:
-            lib.pbo_overlap_pairs(*args, _p(a, _u32p), _p(b, _u32p), total, threads)
-        return a, b
+        cap = max(1024, 2 * len(c))  # one pass when the guess holds; the C side reports the true total
+        while True:
+            a = np.empty(cap, dtype=np.uint32)
+            b = np.empty(cap, dtype=np.uint32)
+            total = int(lib.pbo_overlap_pairs(*args, _p(a, _u32p), _p(b, _u32p), cap, threads))
+            if total <= cap:
+                return a[:total], b[:total]
+            cap = total
 
     def nearest(self, chrom, start, end, strict: bool, k: int = 1, include_overlaps: bool = True,
                 threads: int = 1) -> Tuple[np.ndarray, np.ndarray]:

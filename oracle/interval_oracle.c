@@ -51,21 +51,27 @@ typedef struct {
   uint32_t *en_pos;   /* position in st/en/row order of each en_sorted entry                  */
 } pbo_index;
 
-typedef struct { int32_t c, s, e; uint32_t r; } pbo_rec;
-
-static int cmp_start(const void *a, const void *b) {
-  const pbo_rec *x = (const pbo_rec *)a, *y = (const pbo_rec *)b;
-  if (x->c != y->c) return x->c < y->c ? -1 : 1;
-  if (x->s != y->s) return x->s < y->s ? -1 : 1;
-  return x->r < y->r ? -1 : (x->r > y->r);
-}
-typedef struct { int32_t c, e, s; uint32_t r, pos; } pbo_erec;
-static int cmp_end(const void *a, const void *b) {
-  const pbo_erec *x = (const pbo_erec *)a, *y = (const pbo_erec *)b;
-  if (x->c != y->c) return x->c < y->c ? -1 : 1;
-  if (x->e != y->e) return x->e < y->e ? -1 : 1;
-  if (x->s != y->s) return x->s < y->s ? -1 : 1;
-  return x->r < y->r ? -1 : (x->r > y->r);
+/* Stable LSD radix sort of records by a 64-bit key (8 passes of 8 bits, skipping constant bytes).  The
+ * reference sorts its nodes once per contig when it builds a COITree; a comparison qsort here would make
+ * the CPU baseline needlessly slow. */
+typedef struct { uint64_t key; uint32_t a, b, c; } pbo_srec; /* a,b,c: payload */
+static void radix_sort_srec(pbo_srec *v, int64_t n) {
+  if (n < 2) return;
+  pbo_srec *tmp = (pbo_srec *)malloc(sizeof(pbo_srec) * (size_t)n), *src = v, *dst = tmp;
+  for (int pass = 0; pass < 8; ++pass) {
+    int64_t cnt[256] = {0};
+    const int sh = pass * 8;
+    for (int64_t i = 0; i < n; ++i) cnt[(src[i].key >> sh) & 0xff]++;
+    int skip = 0;
+    for (int d = 0; d < 256; ++d) if (cnt[d] == n) { skip = 1; break; }
+    if (skip) continue;
+    int64_t run = 0;
+    for (int d = 0; d < 256; ++d) { int64_t t = cnt[d]; cnt[d] = run; run += t; }
+    for (int64_t i = 0; i < n; ++i) dst[cnt[(src[i].key >> sh) & 0xff]++] = src[i];
+    pbo_srec *t = src; src = dst; dst = t;
+  }
+  if (src != v) memcpy(v, src, sizeof(pbo_srec) * (size_t)n);
+  free(tmp);
 }
 
 /* Implicit balanced tree over a sorted slice [lo,hi): root = midpoint, children = the two
@@ -91,28 +97,34 @@ PBO_API void pbo_index_free(pbo_index *ix) {
 PBO_API pbo_index *pbo_index_build(const int32_t *c, const int32_t *s, const int32_t *e,
                                    int64_t m_in, int32_t n_contigs) {
   pbo_index *ix = (pbo_index *)calloc(1, sizeof(pbo_index));
-  pbo_rec *rec = (pbo_rec *)malloc(sizeof(pbo_rec) * (size_t)(m_in > 0 ? m_in : 1));
+  pbo_srec *rec = (pbo_srec *)malloc(sizeof(pbo_srec) * (size_t)(m_in > 0 ? m_in : 1));
   int64_t m = 0;
   for (int64_t i = 0; i < m_in; ++i)
-    if (c[i] >= 0 && c[i] < n_contigs) { rec[m].c = c[i]; rec[m].s = s[i]; rec[m].e = e[i]; rec[m].r = (uint32_t)i; ++m; }
-  qsort(rec, (size_t)m, sizeof(pbo_rec), cmp_start);
+    if (c[i] >= 0 && c[i] < n_contigs) {   /* key = (contig, start biased to unsigned); stable => ties keep row order */
+      rec[m].key = ((uint64_t)(uint32_t)c[i] << 32) | ((uint32_t)s[i] ^ 0x80000000u);
+      rec[m].a = (uint32_t)s[i]; rec[m].b = (uint32_t)e[i]; rec[m].c = (uint32_t)i; ++m;
+    }
+  radix_sort_srec(rec, m);
   ix->m = m; ix->n_contigs = n_contigs;
   size_t mm = (size_t)(m > 0 ? m : 1);
   ix->seg = (int64_t *)calloc((size_t)n_contigs + 1, sizeof(int64_t));
   ix->st = (int32_t *)malloc(4 * mm); ix->en = (int32_t *)malloc(4 * mm);
   ix->row = (uint32_t *)malloc(4 * mm); ix->sub_max = (int32_t *)malloc(4 * mm);
   ix->en_sorted = (int32_t *)malloc(4 * mm); ix->en_pos = (uint32_t *)malloc(4 * mm);
-  pbo_erec *er = (pbo_erec *)malloc(sizeof(pbo_erec) * mm);
   for (int64_t i = 0; i < m; ++i) {
-    ix->st[i] = rec[i].s; ix->en[i] = rec[i].e; ix->row[i] = rec[i].r;
-    ix->seg[rec[i].c + 1]++;
-    er[i].c = rec[i].c; er[i].e = rec[i].e; er[i].s = rec[i].s; er[i].r = rec[i].r; er[i].pos = (uint32_t)i;
+    ix->st[i] = (int32_t)rec[i].a; ix->en[i] = (int32_t)rec[i].b; ix->row[i] = rec[i].c;
+    ix->seg[(rec[i].key >> 32) + 1]++;
   }
   for (int32_t k = 0; k < n_contigs; ++k) ix->seg[k + 1] += ix->seg[k];
   for (int32_t k = 0; k < n_contigs; ++k) build_aug(ix->en, ix->sub_max, ix->seg[k], ix->seg[k + 1]);
-  qsort(er, (size_t)m, sizeof(pbo_erec), cmp_end);
-  for (int64_t i = 0; i < m; ++i) { ix->en_sorted[i] = er[i].e; ix->en_pos[i] = er[i].pos; }
-  free(er); free(rec);
+  /* end order: stable sort of the start-ordered records by (contig, end) => ties keep (start,row) order */
+  for (int64_t i = 0; i < m; ++i) {
+    rec[i].key = (rec[i].key & 0xffffffff00000000ull) | (rec[i].b ^ 0x80000000u);
+    rec[i].c = (uint32_t)i; /* position in start order */
+  }
+  radix_sort_srec(rec, m);
+  for (int64_t i = 0; i < m; ++i) { ix->en_sorted[i] = (int32_t)rec[i].b; ix->en_pos[i] = rec[i].c; }
+  free(rec);
   return ix;
 }
 
@@ -167,40 +179,75 @@ PBO_API void pbo_count_overlaps(const pbo_index *ix, const int32_t *c, const int
 }
 
 /* ---- overlap: all (probe_row, build_row) pairs -------------------------------------------
- * Two-phase (count, prefix, fill) so the parallel version writes disjoint ranges.
- * Returns the total pair count; writes min(total, cap) pairs ordered by probe row, then
- * by (start,row) of the indexed partner.                                                    */
+ * One tree query per probe row, the way the reference's probe loop works (docs/developers.md:629-649):
+ * every thread walks a contiguous slice of the probe rows and appends its hits to a growable buffer;
+ * slices are concatenated in order, so pairs come out ordered by probe row, then by (start,row) of
+ * the indexed partner.  Returns the total pair count; writes min(total, cap) pairs.  With NULL output
+ * buffers it only counts.                                                                     */
+typedef struct { uint32_t *p, *b; int64_t n, cap; } pbo_buf;
+static void buf_reserve(pbo_buf *o, int64_t extra) {
+  if (o->n + extra <= o->cap) return;
+  int64_t nc = o->cap ? o->cap * 2 : 4096;
+  while (nc < o->n + extra) nc *= 2;
+  o->p = (uint32_t *)realloc(o->p, 4 * (size_t)nc);
+  o->b = (uint32_t *)realloc(o->b, 4 * (size_t)nc);
+  o->cap = nc;
+}
 PBO_API int64_t pbo_overlap_pairs(const pbo_index *ix, const int32_t *c, const int32_t *s, const int32_t *e,
                                   int64_t n, int strict, uint32_t *out_probe, uint32_t *out_build,
                                   int64_t cap, int threads) {
-  int64_t *off = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n + 1));
+  int nt = 1;
 #ifdef _OPENMP
   if (threads > 0) omp_set_num_threads(threads);
-#pragma omp parallel for schedule(dynamic, 4096)
+  nt = omp_get_max_threads();
 #endif
-  for (int64_t i = 0; i < n; ++i) {
-    int32_t cc = c[i];
-    off[i + 1] = (cc < 0 || cc >= ix->n_contigs) ? 0
-               : tree_query(ix, ix->seg[cc], ix->seg[cc + 1], strict, s[i], e[i], NULL, 0);
-  }
-  off[0] = 0;
-  for (int64_t i = 0; i < n; ++i) off[i + 1] += off[i];
-  int64_t total = off[n];
-  if (out_probe && out_build) {
+  const int want = out_probe && out_build;
+  pbo_buf *bufs = (pbo_buf *)calloc((size_t)nt, sizeof(pbo_buf));
+  int64_t *tot = (int64_t *)calloc((size_t)nt + 1, sizeof(int64_t));
 #ifdef _OPENMP
-#pragma omp parallel for schedule(dynamic, 4096)
+#pragma omp parallel num_threads(nt)
 #endif
-    for (int64_t i = 0; i < n; ++i) {
-      int64_t k = off[i + 1] - off[i];
-      if (k == 0 || off[i] >= cap) continue;
-      int64_t room = cap - off[i]; if (room > k) room = k;
-      int32_t cc = c[i];
-      uint32_t *dst = out_build + off[i];
-      tree_query(ix, ix->seg[cc], ix->seg[cc + 1], strict, s[i], e[i], dst, room);
-      for (int64_t j = 0; j < room; ++j) { dst[j] = ix->row[dst[j]]; out_probe[off[i] + j] = (uint32_t)i; }
+  {
+    int t = 0;
+#ifdef _OPENMP
+    t = omp_get_thread_num();
+#endif
+    const int64_t lo = n * t / nt, hi = n * (t + 1) / nt;
+    pbo_buf *o = &bufs[t];
+    int64_t count = 0;
+    for (int64_t i = lo; i < hi; ++i) {
+      const int32_t cc = c[i];
+      if (cc < 0 || cc >= ix->n_contigs) continue;
+      if (!want) { count += tree_query(ix, ix->seg[cc], ix->seg[cc + 1], strict, s[i], e[i], NULL, 0); continue; }
+      buf_reserve(o, 64);
+      int64_t k = tree_query(ix, ix->seg[cc], ix->seg[cc + 1], strict, s[i], e[i], o->b + o->n, o->cap - o->n);
+      if (k > o->cap - o->n) {  /* more hits than room: grow and repeat this probe */
+        buf_reserve(o, k);
+        k = tree_query(ix, ix->seg[cc], ix->seg[cc + 1], strict, s[i], e[i], o->b + o->n, o->cap - o->n);
+      }
+      for (int64_t j = 0; j < k; ++j) { o->b[o->n + j] = ix->row[o->b[o->n + j]]; o->p[o->n + j] = (uint32_t)i; }
+      o->n += k;
+      count += k;
+    }
+    tot[t + 1] = count;
+  }
+  for (int t = 0; t < nt; ++t) tot[t + 1] += tot[t];
+  const int64_t total = tot[nt];
+  if (want) {
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(nt) schedule(static, 1)
+#endif
+    for (int t = 0; t < nt; ++t) {
+      int64_t off = tot[t], k = bufs[t].n;
+      if (off < cap) {
+        if (off + k > cap) k = cap - off;
+        memcpy(out_probe + off, bufs[t].p, 4 * (size_t)k);
+        memcpy(out_build + off, bufs[t].b, 4 * (size_t)k);
+      }
     }
   }
-  free(off);
+  for (int t = 0; t < nt; ++t) { free(bufs[t].p); free(bufs[t].b); }
+  free(bufs); free(tot);
   return total;
 }
 

@@ -48,7 +48,7 @@ class PbRangeOptions(ctypes.Structure):
 
 class StageTimes(ctypes.Structure):
     _fields_ = [("partition_sort_ns", ctypes.c_uint64), ("count_ns", ctypes.c_uint64),
-                ("scan_ns", ctypes.c_uint64), ("emit_ns", ctypes.c_uint64)]
+                ("scan_ns", ctypes.c_uint64), ("emit_ns", ctypes.c_uint64), ("count_overlaps_ns", ctypes.c_uint64)]
 
 
 def lib() -> ctypes.CDLL:

@@ -14,7 +14,6 @@ namespace pbgpu {
 
 thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
-static thread_local pbgpu_stage_times g_times = {0, 0, 0, 0};
 
 int set_error(int code, const char *fmt, ...) {
   va_list ap;
@@ -22,15 +21,6 @@ int set_error(int code, const char *fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return code;
-}
-
-static bool profiling() {
-  static int v = -1;
-  if (v < 0) {
-    const char *e = getenv("PBGPU_PROFILE");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
 }
 
 static std::once_flag g_pool_once[64];
@@ -58,27 +48,33 @@ void dev_free(void *p, cudaStream_t s) {
   if (p) cudaFreeAsync(p, s);
 }
 
-// CUDA-event stage timer (only when PBGPU_PROFILE=1; otherwise no events are created)
-struct StageTimer {
-  cudaStream_t s;
-  cudaEvent_t a = nullptr, b = nullptr;
-  bool on;
-  explicit StageTimer(cudaStream_t st) : s(st), on(profiling()) {
-    if (on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s); }
+// CUDA-event stage marks, always on (an event record is ~1 us of host time and no device sync): pairs of
+// events bracket the index build and each provider kernel on the launching stream; pbgpu_last_stage_times()
+// turns them into durations after the fact.  One set per host thread and device.
+enum { EV_BUILD0, EV_BUILD1, EV_COUNT0, EV_COUNT1, EV_P1_0, EV_P1_1, EV_SCAN1, EV_EMIT0, EV_EMIT1, EV_N };
+struct StageEvents {
+  cudaEvent_t ev[EV_N] = {};
+  bool set[EV_N] = {};
+  int device = -1;
+  void mark(int which, cudaStream_t s) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != device) {
+      for (int i = 0; i < EV_N; ++i) { if (ev[i]) cudaEventDestroy(ev[i]); ev[i] = nullptr; set[i] = false; }
+      device = dev;
+    }
+    if (!ev[which] && cudaEventCreate(&ev[which]) != cudaSuccess) { cudaGetLastError(); ev[which] = nullptr; return; }
+    set[which] = cudaEventRecord(ev[which], s) == cudaSuccess;
   }
-  uint64_t stop_ns() {
-    if (!on) return 0;
-    cudaEventRecord(b, s);
-    cudaEventSynchronize(b);
+  uint64_t span_ns(int a, int b) {
+    if (!set[a] || !set[b]) return 0;
+    if (cudaEventSynchronize(ev[b]) != cudaSuccess) { cudaGetLastError(); return 0; }
     float ms = 0;
-    cudaEventElapsedTime(&ms, a, b);
-    cudaEventRecord(a, s);
-    return (uint64_t)(ms * 1e6);
-  }
-  ~StageTimer() {
-    if (on) { cudaEventDestroy(a); cudaEventDestroy(b); }
+    if (cudaEventElapsedTime(&ms, ev[a], ev[b]) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return (uint64_t)(ms * 1e6f);
   }
 };
+static thread_local StageEvents g_ev;
 
 }  // namespace pbgpu
 
@@ -98,7 +94,11 @@ int pbgpu_device_count(int *count) {
 
 int pbgpu_last_stage_times(pbgpu_stage_times *out) {
   if (!out) return set_error(PBGPU_EINVAL, "out is NULL");
-  *out = g_times;
+  out->partition_sort_ns = g_ev.span_ns(EV_BUILD0, EV_BUILD1);
+  out->count_ns = g_ev.span_ns(EV_P1_0, EV_P1_1);
+  out->scan_ns = g_ev.span_ns(EV_P1_1, EV_SCAN1);
+  out->emit_ns = g_ev.span_ns(EV_EMIT0, EV_EMIT1);
+  out->count_overlaps_ns = g_ev.span_ns(EV_COUNT0, EV_COUNT1);
   return PBGPU_OK;
 }
 
@@ -126,7 +126,8 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
   ix->m_in = m_in;
   ix->n_contigs = n_contigs;
   PB_CUDA(cudaGetDevice(&ix->device));
-  StageTimer tm(s);
+  g_ev.mark(EV_BUILD0, s);
+  struct MarkEnd { cudaStream_t s; ~MarkEnd() { g_ev.mark(EV_BUILD1, s); } } mark_end{s};
   Scratch sc(s);
   // 1. domain of the coordinates (decides key width and whether the rank identity is safe)
   BuildStats hs = {INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN, 0ull, 0ull};
@@ -251,7 +252,6 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
     PB_CHECK_LAUNCH();
     ix->fast = 1;
   }
-  g_times.partition_sort_ns = tm.stop_ns();
   return PBGPU_OK;
 }
 
@@ -290,7 +290,7 @@ int pbgpu_count_overlaps(const pbgpu_index *ix, const int32_t *d_contig, const i
   if (n == 0) return PBGPU_OK;
   if (!d_counts) return set_error(PBGPU_EINVAL, "d_counts is NULL");
   cudaStream_t s = (cudaStream_t)stream;
-  StageTimer tm(s);
+  g_ev.mark(EV_COUNT0, s);
   const unsigned grid = (unsigned)cdiv(n, kSweepThreads);
   if (ix->fast) {
     if (filter_op == PBGPU_FILTER_STRICT)
@@ -302,7 +302,7 @@ int pbgpu_count_overlaps(const pbgpu_index *ix, const int32_t *d_contig, const i
   else
     PB_LAUNCH(count_overlaps_kernel<false>, grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, d_counts);
   PB_CHECK_LAUNCH();
-  g_times.count_ns = tm.stop_ns();
+  g_ev.mark(EV_COUNT1, s);
   return PBGPU_OK;
 }
 
@@ -372,7 +372,7 @@ int pbgpu_overlap_count(const pbgpu_index *ix, const int32_t *d_contig, const in
     p->his = (uint32_t *)((char *)p->slab + cb);
     p->block_base = (unsigned long long *)((char *)p->slab + 2 * cb);
   }
-  StageTimer tm(s);
+  g_ev.mark(EV_P1_0, s);
   const unsigned grid = (unsigned)p->nblk;
   if (ix->fast) {
     if (filter_op == PBGPU_FILTER_STRICT)
@@ -384,15 +384,15 @@ int pbgpu_overlap_count(const pbgpu_index *ix, const int32_t *d_contig, const in
   else
     PB_LAUNCH(overlap_count_kernel<false>, grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->block_base);
   if (cudaGetLastError() != cudaSuccess) return fail(set_error(PBGPU_ECUDA, "overlap_count_kernel launch failed"));
-  g_times.count_ns = tm.stop_ns();
+  g_ev.mark(EV_P1_1, s);
   unsigned long long *d_total = p->block_base + p->nblk;
   int rc = device_scan<SumU64, false>(p->block_base, p->block_base, p->nblk, d_total, s);
   if (rc != PBGPU_OK) return fail(rc);
+  g_ev.mark(EV_SCAN1, s);
   unsigned long long h_total = 0;
   if (cudaMemcpyAsync(&h_total, d_total, sizeof(h_total), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
       cudaStreamSynchronize(s) != cudaSuccess)
     return fail(set_error(PBGPU_ECUDA, "overlap pass 1 failed: %s", cudaGetErrorString(cudaGetLastError())));
-  g_times.scan_ns = tm.stop_ns();
   p->total = (int64_t)h_total;
   *total_pairs = p->total;
   *plan = p;
@@ -404,7 +404,7 @@ int pbgpu_overlap_emit(const pbgpu_overlap_plan *p, uint32_t *d_probe_rows, uint
   if (p->n == 0 || p->total == 0) return PBGPU_OK;
   if (!d_probe_rows || !d_build_rows) return set_error(PBGPU_EINVAL, "output buffer is NULL");
   cudaStream_t s = (cudaStream_t)stream;
-  StageTimer tm(s);
+  g_ev.mark(EV_EMIT0, s);
   const unsigned grid = (unsigned)p->nblk;
   if (p->ix->fast) {
     if (p->filter_op == PBGPU_FILTER_STRICT)
@@ -420,7 +420,7 @@ int pbgpu_overlap_emit(const pbgpu_overlap_plan *p, uint32_t *d_probe_rows, uint
     PB_LAUNCH(overlap_emit_kernel<false>, grid, kSweepThreads, 0, s, view_of(p->ix), p->pc, p->ps, p->pe, p->n, p->counts,
               p->block_base, d_probe_rows, d_build_rows);
   PB_CHECK_LAUNCH();
-  g_times.emit_ns = tm.stop_ns();
+  g_ev.mark(EV_EMIT1, s);
   return PBGPU_OK;
 }
 
