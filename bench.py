@@ -129,15 +129,27 @@ def cpu_reference_run(probe, build, nc, sample_reads: int, threads: int, steps: 
     return pairs, float(np.mean(times))
 
 
+def pick_threads(probe, build, nc):
+    """All host threads the port can use: try every logical CPU and every physical core (half), keep the faster."""
+    import oracle
+
+    ncpu = os.cpu_count() or 1
+    best, best_t = None, None
+    small = tuple(x[:500_000] for x in probe)
+    for thr in sorted({ncpu, max(1, ncpu // 2)}, reverse=True):
+        _, sec = cpu_reference_run(small, build, nc, len(small[0]), thr, steps=1, warmup=1)
+        if best is None or sec < best:
+            best, best_t = sec, thr
+    return best_t
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # rank 0 alone runs the CPU arm
-    import oracle
-
     n_reads, n_var = args.reads, args.variants
     probe, build, nc = make_config2(n_reads, n_var)
-    threads = oracle.max_threads()
+    threads = pick_threads(probe, build, nc)
     sample = min(n_reads, args.cpu_sample)
     pairs, sec = cpu_reference_run(probe, build, nc, sample, threads, steps=args.steps, warmup=args.warmup)
     v = pairs / sec
@@ -145,10 +157,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": f"config2: {n_reads} reads x {n_var} variants, chr1, Strict; count_overlaps + pair emit",
+        "config": {"workload": f"config2: {n_reads} reads x {n_var} variants, chr1, Strict; index build + count_overlaps + pair emit",
                    "l2": "n/a (CPU)"},
         "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
-                         "sample": f"index over all {n_var} variants + count_overlaps + pair emit for the first {sample} reads per step"},
+                         "sample": f"per step: interval-tree build over all {n_var} variants + count_overlaps + pair emit for {sample} of {n_reads} reads"},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -164,7 +176,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--reads", type=int, default=10_000_000)
     ap.add_argument("--variants", type=int, default=1_000_000)
-    ap.add_argument("--cpu-sample", type=int, default=2_000_000, help="reads per CPU-baseline step")
+    ap.add_argument("--cpu-sample", type=int, default=10_000_000, help="reads per CPU-baseline step (default: the whole batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     args = ap.parse_args()
@@ -322,11 +334,11 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle
 
-        thr = oracle.max_threads()
+        thr = pick_threads(probe, build, nc)
         sample = min(n, args.cpu_sample)
         cp, csec = cpu_reference_run(probe, build, nc, sample, thr, steps=1, warmup=0)
         line["cpu_baseline"] = {"value": cp / csec, "unit": "pairs/s", "cores": thr, "kind": "port",
-                                "sample": f"index over all {m} variants + count_overlaps + pair emit for the first {sample} reads, 1 run ({csec:.2f} s)"}
+                                "sample": f"interval-tree build over all {m} variants + count_overlaps + pair emit for {sample} of {n} reads, 1 run ({csec:.2f} s)"}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -14,11 +14,13 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <memory>
@@ -39,6 +41,23 @@ extern thread_local char g_err[512];
 using pbgpu::set_error;
 
 namespace {
+
+// PBGPU_TRACE=1: host-stage wall times of every pbgpu_range_op call on stderr (tuning aid)
+struct Trace {
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  Trace() {
+    const char *e = getenv("PBGPU_TRACE");
+    on = e && e[0] == '1';
+    t0 = std::chrono::steady_clock::now();
+  }
+  void lap(const char *what) {
+    if (!on) return;
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[pbgpu] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
 
 // ---------------------------------------------------------------------------------------------
 // tiny persistent thread pool: parallel_for over [0,n) in chunks
@@ -122,7 +141,8 @@ class Pool {
   bool stop_ = false;
 };
 
-constexpr int64_t kChunk = 1 << 17;  // rows per host task
+constexpr int64_t kChunk = 1 << 17;        // rows per key-encoding task
+constexpr int64_t kGatherChunk = 1 << 14;  // rows per gather task (multiple of 8: validity bytes stay task-private)
 
 // ---------------------------------------------------------------------------------------------
 // cached pinned staging (cudaHostAlloc is milliseconds per 100 MB: never on the per-call path twice)
@@ -424,12 +444,14 @@ struct OwnedSchema {
   bool has_md = false;
   std::vector<ArrowSchema> kids;
   std::vector<ArrowSchema *> kptr;
+  std::unique_ptr<ArrowSchema> dict;
 };
 void release_schema(ArrowSchema *s) {
   if (!s || !s->release) return;
   OwnedSchema *o = (OwnedSchema *)s->private_data;
   for (auto &k : o->kids)
     if (k.release) k.release(&k);
+  if (o->dict && o->dict->release) o->dict->release(o->dict.get());
   delete o;
   s->release = nullptr;
 }
@@ -504,7 +526,7 @@ std::string out_format(const ArrowSchema *f, bool *ok) {
 int gather_column(const Table &t, int col, const uint32_t *rows, int64_t n, ArrowArray *out) {
   const ArrowSchema *f = t.schema.children[col];
   std::unique_ptr<OwnedArray> o(new OwnedArray());
-  const int64_t nchunks = (n + kChunk - 1) / kChunk;
+  const int64_t nchunks = (n + kGatherChunk - 1) / kGatherChunk;
   const size_t vbytes = (size_t)((n + 7) / 8);
   uint8_t *valid = (uint8_t *)calloc(vbytes ? vbytes : 1, 1);
   if (!valid) return set_error(PBGPU_ENOMEM, "host allocation failed");
@@ -532,7 +554,7 @@ int gather_column(const Table &t, int col, const uint32_t *rows, int64_t n, Arro
     o->bufs.push_back(vals);
     // chunk boundaries are multiples of 8 rows, so bitmap bytes are private to a chunk
     Pool::get().parallel_for(nchunks, [&](int64_t ci) {
-      const int64_t lo = ci * kChunk, hi = std::min(n, lo + kChunk);
+      const int64_t lo = ci * kGatherChunk, hi = std::min(n, lo + kGatherChunk);
       int64_t nulls = 0;
       for (int64_t i = lo; i < hi; ++i) {
         const uint32_t r = rows[i];
@@ -577,7 +599,7 @@ int gather_column(const Table &t, int col, const uint32_t *rows, int64_t n, Arro
       return true;
     };
     Pool::get().parallel_for(nchunks, [&](int64_t ci) {
-      const int64_t lo = ci * kChunk, hi = std::min(n, lo + kChunk);
+      const int64_t lo = ci * kGatherChunk, hi = std::min(n, lo + kGatherChunk);
       int64_t nulls = 0, bytes = 0;
       for (int64_t i = lo; i < hi; ++i) {
         std::string_view sv;
@@ -598,7 +620,7 @@ int gather_column(const Table &t, int col, const uint32_t *rows, int64_t n, Arro
     o->bufs.push_back(offs);
     o->bufs.push_back(data);
     Pool::get().parallel_for(nchunks, [&](int64_t ci) {
-      const int64_t lo = ci * kChunk, hi = std::min(n, lo + kChunk);
+      const int64_t lo = ci * kGatherChunk, hi = std::min(n, lo + kGatherChunk);
       int64_t pos = chunk_off[ci];
       for (int64_t i = lo; i < hi; ++i) {
         if (large) ((int64_t *)offs)[i] = pos; else ((int32_t *)offs)[i] = (int32_t)pos;
@@ -667,9 +689,40 @@ int nullable_u32_column(const uint32_t *src, int64_t n, ArrowArray *out) {
   return PBGPU_OK;
 }
 
+// ---- zero-copy re-export of input columns (count_overlaps / coverage return the iterated table's rows
+// unchanged plus one column: operation.rs:316-347) ----------------------------------------------------
+struct ViewPriv { std::shared_ptr<Table> keep; };
+void release_view(ArrowArray *a) {
+  if (!a || !a->release) return;
+  delete (ViewPriv *)a->private_data;  // buffers / children / dictionary stay owned by the Table
+  a->release = nullptr;
+}
+ArrowArray view_column(const std::shared_ptr<Table> &t, int batch, int col, int64_t off, int64_t len) {
+  const ArrowArray &ba = t->batches[batch];
+  const ArrowArray *c = ba.children[col];
+  ArrowArray v = *c;
+  v.offset = c->offset + ba.offset + off;
+  v.length = len;
+  v.null_count = c->null_count == 0 ? 0 : -1;  // unknown for a slice
+  v.release = release_view;
+  v.private_data = new ViewPriv{t};
+  return v;
+}
+ArrowSchema copy_schema(const ArrowSchema *f, const std::string &name) {
+  std::vector<ArrowSchema> kids;
+  for (int64_t i = 0; i < f->n_children; ++i) kids.push_back(copy_schema(f->children[i], f->children[i]->name ? f->children[i]->name : ""));
+  ArrowSchema s = make_schema(f->format, name, f->metadata, f->flags, std::move(kids));
+  if (f->dictionary) {
+    OwnedSchema *o = (OwnedSchema *)s.private_data;
+    o->dict.reset(new ArrowSchema(copy_schema(f->dictionary, f->dictionary->name ? f->dictionary->name : "")));
+    s.dictionary = o->dict.get();
+  }
+  return s;
+}
+
 // ---- the output stream ---------------------------------------------------------------------------
 struct OutStream {
-  std::unique_ptr<Table> left, right;
+  std::shared_ptr<Table> left, right;  // shared with zero-copy output views of their columns
   PbRangeOptions opt{};
   std::string suffix1 = "_1", suffix2 = "_2";
   PinnedHold pins;           // result arrays live in cached pinned memory until release
@@ -680,6 +733,8 @@ struct OutStream {
   std::vector<uint32_t> own_l, own_r;  // host-built row lists (nearest expansion, distinct)
   std::vector<int64_t> own_x;
   int64_t cursor = 0;
+  int view_batch = 0;        // pass-through modes: input batch being re-exported
+  int64_t view_off = 0;      //   and the offset inside it
   uint32_t batch_rows = 1 << 20;
   std::string last_error;
 };
@@ -714,8 +769,9 @@ int out_get_schema(ArrowArrayStream *s, ArrowSchema *out) {
     if (!rc) rc = add_table(*st->right, st->suffix2, true);
     if (!rc && want_distance(o)) kids.push_back(make_schema("l", "distance", nullptr, ARROW_FLAG_NULLABLE));
   } else {  // count_overlaps / coverage: the iterated table's rows + one int64 column (operation.rs:316-347)
-    rc = add_table(*st->right, "", false);
-    if (!rc) kids.push_back(make_schema("l", o.range_op == PBGPU_OP_COVERAGE ? "coverage" : "count", nullptr, 0));
+    for (int64_t i = 0; i < st->right->schema.n_children; ++i)  // columns are re-exported untouched, any Arrow type
+      kids.push_back(copy_schema(st->right->schema.children[i], st->right->schema.children[i]->name ? st->right->schema.children[i]->name : ""));
+    kids.push_back(make_schema("l", o.range_op == PBGPU_OP_COVERAGE ? "coverage" : "count", nullptr, 0));
   }
   if (rc) {
     for (auto &k : kids) k.release(&k);
@@ -730,6 +786,8 @@ int out_get_next(ArrowArrayStream *s, ArrowArray *out) {
   const PbRangeOptions &o = st->opt;
   memset(out, 0, sizeof(*out));
   if (st->cursor >= st->n_out) return 0;  // end of stream: released (release == NULL) array
+  Trace tr;
+  struct LapEnd { Trace &t; ~LapEnd() { t.lap("get_next (materialise batch)"); } } lap_end{tr};
   const int64_t lo = st->cursor, n = std::min<int64_t>(st->batch_rows, st->n_out - lo);
   std::unique_ptr<OwnedArray> top(new OwnedArray());
   int rc = PBGPU_OK;
@@ -741,7 +799,6 @@ int out_get_next(ArrowArrayStream *s, ArrowArray *out) {
       if (rc == PBGPU_OK) push(std::move(a));
     }
   };
-  std::vector<uint32_t> iota;
   if (o.emit == 1) {
     ArrowArray a{};
     rc = plain_column<uint32_t>(st->lrow + lo, n, nullptr, &a);
@@ -755,10 +812,22 @@ int out_get_next(ArrowArrayStream *s, ArrowArray *out) {
     add_table(*st->right, st->rrow);
     if (rc == PBGPU_OK && want_distance(o)) { ArrowArray d{}; rc = nullable_i64_column(st->extra + lo, n, &d); if (rc == PBGPU_OK) push(std::move(d)); }
   } else {
-    iota.resize((size_t)n);
-    for (int64_t i = 0; i < n; ++i) iota[i] = (uint32_t)(lo + i);
-    add_table(*st->right, iota.data() - lo);
-    if (rc == PBGPU_OK) { ArrowArray d{}; rc = plain_column<int64_t>(st->extra + lo, n, nullptr, &d); if (rc == PBGPU_OK) push(std::move(d)); }
+    // zero-copy: slice the current input batch (output batches follow the input batch boundaries)
+    const Table &t = *st->right;
+    while (st->view_batch < (int)t.batches.size() && st->view_off >= t.batches[st->view_batch].length) { ++st->view_batch; st->view_off = 0; }
+    const int64_t avail = t.batches[st->view_batch].length - st->view_off;
+    const int64_t len = std::min<int64_t>(std::min<int64_t>(n, avail), st->n_out - lo);
+    for (int c = 0; c < (int)t.n_cols(); ++c) push(view_column(st->right, st->view_batch, c, st->view_off, len));
+    ArrowArray d{};
+    rc = plain_column<int64_t>(st->extra + lo, len, nullptr, &d);
+    if (rc == PBGPU_OK) push(std::move(d));
+    if (rc == PBGPU_OK) {
+      top->bptr = {nullptr};
+      *out = finish_array(top.release(), len, 0);
+      st->cursor += len;
+      st->view_off += len;
+      return 0;
+    }
   }
   if (rc != PBGPU_OK) {
     st->last_error = pbgpu::g_err;
@@ -809,6 +878,7 @@ int run(Table *L, Table *R, OutStream *os) {
   //   count/coverage: index = left (s1), iterate = right (s2), rows of right returned   operation.rs:316-340
   const bool iter_is_left = (o.range_op == PBGPU_OP_OVERLAP || o.range_op == PBGPU_OP_NEAREST);
   Table *IT = iter_is_left ? L : R, *IX = iter_is_left ? R : L;
+  Trace tr;
   ContigDict dict;
   PinnedHold stage;  // input staging: returned to the cache when this call ends
   const int64_t n = IT->rows, m = IX->rows;
@@ -818,6 +888,7 @@ int run(Table *L, Table *R, OutStream *os) {
   BR_TRY(encode_keys(*IX, iter_is_left ? "right" : "left", dict, hc_x, hs_x, he_x));
   BR_TRY(encode_keys(*IT, iter_is_left ? "left" : "right", dict, hc_i, hs_i, he_i));
   const int32_t n_contigs = (int32_t)dict.map.size();
+  tr.lap("encode keys -> pinned");
 
   int prev_dev = -1;
   if (o.device >= 0) { BR_CUDA(cudaGetDevice(&prev_dev)); BR_CUDA(cudaSetDevice(o.device)); }
@@ -840,6 +911,7 @@ int run(Table *L, Table *R, OutStream *os) {
   BR_TRY(pbgpu_index_build(dc_x, ds_x, de_x, m, n_contigs, s, &ix));
   struct IxGuard { pbgpu_index *p; ~IxGuard() { pbgpu_index_free(p); } } ig{ix};
   const uint64_t limit = o.limit;
+  tr.lap("H2D enqueue + index build");
 
   if (o.range_op == PBGPU_OP_COUNT_OVERLAPS_NAIVE || o.range_op == PBGPU_OP_COVERAGE) {
     int64_t *d_out = dev.get<int64_t>(n);
@@ -905,6 +977,7 @@ int run(Table *L, Table *R, OutStream *os) {
     return set_error(PBGPU_EINVAL, "unsupported range_op %d", o.range_op);
   }
   if (limit && (uint64_t)os->n_out > limit) os->n_out = (int64_t)limit;
+  tr.lap("provider kernels + D2H");
   return PBGPU_OK;
 }
 
@@ -928,10 +1001,12 @@ extern "C" int pbgpu_range_op(struct ArrowArrayStream *left, struct ArrowArraySt
     os->opt.suffixes[0] = os->opt.suffixes[1] = nullptr;
     if (opts->max_batch_rows) os->batch_rows = opts->max_batch_rows;
     os->batch_rows = (os->batch_rows + 7u) & ~7u;  // keep bitmap bytes chunk-private
-    os->left.reset(new Table());
-    os->right.reset(new Table());
+    os->left = std::make_shared<Table>();
+    os->right = std::make_shared<Table>();
+    Trace tr;
     int rc = drain(left, *os->left, "left");
     if (rc == PBGPU_OK) rc = drain(right, *os->right, "right");
+    tr.lap("drain input streams");
     for (int i = 0; i < 3 && rc == PBGPU_OK; ++i) rc = find_col(*os->left, opts->cols1[i], "left", &os->left->key[i]);
     for (int i = 0; i < 3 && rc == PBGPU_OK; ++i) rc = find_col(*os->right, opts->cols2[i], "right", &os->right->key[i]);
     if (rc != PBGPU_OK) return rc;

@@ -1,7 +1,8 @@
 // radix_sort.cuh -- hand-written stable LSD radix sort of (uint64 key, uint64 value) pairs.
 //
-// One pass = 8 key bits: per-tile digit histogram -> device-wide exclusive scan of the
-// [digit][tile] counts -> stable scatter.  The scatter ranks keys inside a tile with
+// One pass = 8 key bits: per-tile digit histogram (+ per-digit totals by atomics) -> offsets kernel (one
+// warp per digit: base = sum of the smaller digits' totals, then a running scan along its [digit][tile] row;
+// replaces a device-wide scan that was 35 us per pass at 1M rows) -> stable scatter.  The scatter ranks keys inside a tile with
 // warp-level __match_any_sync multisplit (one shared-memory counter row per warp), so equal
 // digits keep their input order; that stability is what makes the composite
 // (contig | start) sort double as "radix partition by contig + segmented sort by start"
@@ -21,7 +22,8 @@ constexpr int kRsTile = kRsThreads * kRsItems;
 constexpr int kRsRadix = 256;
 
 __global__ void __launch_bounds__(kRsThreads) rs_hist_kernel(const uint64_t *__restrict__ keys, int64_t n, int shift,
-                                                             uint32_t *__restrict__ hist /*[256][nblk]*/, int64_t nblk) {
+                                                             uint32_t *__restrict__ hist /*[256][nblk]*/, int64_t nblk,
+                                                             uint32_t *__restrict__ digit_totals /*[256], zeroed*/) {
   __shared__ uint32_t h[kRsRadix];
   for (int i = threadIdx.x; i < kRsRadix; i += kRsThreads) h[i] = 0;
   __syncthreads();
@@ -32,7 +34,38 @@ __global__ void __launch_bounds__(kRsThreads) rs_hist_kernel(const uint64_t *__r
     if (i < n) atomicAdd(&h[(keys[i] >> shift) & 0xff], 1u);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < kRsRadix; i += kRsThreads) hist[(int64_t)i * nblk + blockIdx.x] = h[i];
+  for (int i = threadIdx.x; i < kRsRadix; i += kRsThreads) {
+    hist[(int64_t)i * nblk + blockIdx.x] = h[i];
+    if (h[i]) atomicAdd(digit_totals + i, h[i]);
+  }
+}
+
+// one warp per digit: turn its row of per-tile counts into global scatter offsets (in place)
+__global__ void __launch_bounds__(256) rs_offsets_kernel(uint32_t *__restrict__ hist, int64_t nblk,
+                                                         const uint32_t *__restrict__ digit_totals) {
+  const int lane = threadIdx.x & 31;
+  const int d = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (d >= kRsRadix) return;
+  uint32_t base = 0;
+  for (int k = lane; k < d; k += 32) base += digit_totals[k];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) base += __shfl_xor_sync(0xffffffffu, base, o);
+  uint32_t *row = hist + (int64_t)d * nblk;
+  uint32_t run = base;
+  for (int64_t b0 = 0; b0 < nblk; b0 += 32 * 4) {
+    uint32_t v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const int64_t b = b0 + j * 32 + lane; v[j] = b < nblk ? row[b] : 0u; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t incl = v[j];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+      const int64_t b = b0 + j * 32 + lane;
+      if (b < nblk) row[b] = run + incl - v[j];
+      run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kRsThreads) rs_scatter_kernel(const uint64_t *__restrict__ keys_in,
@@ -105,10 +138,15 @@ inline int radix_sort_pairs(uint64_t *keys, uint64_t *vals, int64_t n, int bits,
   PB_TRY(sc.get(&k2, (size_t)n));
   PB_TRY(sc.get(&v2, (size_t)n));
   PB_TRY(sc.get(&hist, (size_t)(nblk * kRsRadix)));
+  uint32_t *totals = nullptr;
+  const int passes = (bits + 7) / 8;
+  PB_TRY(sc.get(&totals, (size_t)passes * kRsRadix));
+  PB_CUDA(cudaMemsetAsync(totals, 0, sizeof(uint32_t) * (size_t)passes * kRsRadix, s));
   uint64_t *ki = keys, *vi = vals, *ko = k2, *vo = v2;
-  for (int shift = 0; shift < bits; shift += 8) {
-    PB_LAUNCH(rs_hist_kernel, (unsigned)nblk, kRsThreads, 0, s, ki, n, shift, hist, nblk);
-    PB_TRY((device_scan<SumU32, false>(hist, hist, nblk * kRsRadix, nullptr, s)));
+  for (int shift = 0, pass = 0; shift < bits; shift += 8, ++pass) {
+    uint32_t *tot = totals + pass * kRsRadix;
+    PB_LAUNCH(rs_hist_kernel, (unsigned)nblk, kRsThreads, 0, s, ki, n, shift, hist, nblk, tot);
+    PB_LAUNCH(rs_offsets_kernel, kRsRadix / 8, 256, 0, s, hist, nblk, tot);
     PB_LAUNCH(rs_scatter_kernel, (unsigned)nblk, kRsThreads, 0, s, ki, vi, ko, vo, n, shift, hist, nblk);
     PB_CHECK_LAUNCH();
     uint64_t *t = ki; ki = ko; ko = t;

@@ -124,8 +124,8 @@ __global__ void __launch_bounds__(kScanThreads) scan_final_kernel(const typename
   }
 }
 
-// whole scan in one block (one launch instead of three) for arrays up to a few hundred thousand entries:
-// the radix-sort digit tables of a ~1M-row index are 63K entries and sit on the launch-bound critical path
+// whole scan in one block (one launch instead of three) for small arrays (contig tables, a few thousand
+// block totals); its serial loop costs ~2 us per 4096 entries, so larger inputs take the three-kernel path
 template <typename Op, bool INCLUSIVE>
 __global__ void __launch_bounds__(1024) scan_single_block_kernel(const typename Op::T *__restrict__ in, typename Op::T *__restrict__ out,
                                                                  int64_t n, typename Op::T *__restrict__ total_out) {
@@ -167,7 +167,7 @@ int device_scan(const typename Op::T *in, typename Op::T *out, int64_t n, typena
     if (d_total) PB_CUDA(cudaMemsetAsync(d_total, 0, sizeof(T), s));
     return PBGPU_OK;
   }
-  if (n <= (1 << 18)) {
+  if (n <= 8192) {
     PB_LAUNCH((scan_single_block_kernel<Op, INCLUSIVE>), 1, 1024, 0, s, in, out, n, d_total);
     PB_CHECK_LAUNCH();
     return PBGPU_OK;

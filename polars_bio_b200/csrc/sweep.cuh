@@ -157,15 +157,19 @@ __global__ void __launch_bounds__(kSweepThreads) overlap_emit_kernel(IndexView i
 template <bool LE>  // LE: number of keys <= x ; else number of keys < x
 __device__ __forceinline__ uint32_t dir_rank(const DirRec *__restrict__ dir, const uint32_t *__restrict__ g, int shift, uint32_t x) {
   const uint32_t b = x >> shift;
-  const uint4 lo = __ldg(reinterpret_cast<const uint4 *>(dir + b));
-  const uint4 hi = __ldg(reinterpret_cast<const uint4 *>(dir + b) + 1);
-  if (!(lo.x & 0x80000000u)) {
+  // one 256-bit request per record (LDG.E.256): two 128-bit loads cost two L2 sector requests each time the
+  // first is still in flight; no L1 allocation -- the directory is touched at random, nothing is reused
+  uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+               : "l"(dir + b));
+  if (!(r0 & 0x80000000u)) {
     uint32_t n;
-    if (LE) n = (lo.y <= x) + (lo.z <= x) + (lo.w <= x) + (hi.x <= x) + (hi.y <= x) + (hi.z <= x) + (hi.w <= x);
-    else n = (lo.y < x) + (lo.z < x) + (lo.w < x) + (hi.x < x) + (hi.y < x) + (hi.z < x) + (hi.w < x);
-    return lo.x + n;
+    if (LE) n = (r1 <= x) + (r2 <= x) + (r3 <= x) + (r4 <= x) + (r5 <= x) + (r6 <= x) + (r7 <= x);
+    else n = (r1 < x) + (r2 < x) + (r3 < x) + (r4 < x) + (r5 < x) + (r6 < x) + (r7 < x);
+    return r0 + n;
   }
-  uint32_t a = lo.x & 0x7fffffffu, e = __ldg(&dir[b + 1].base) & 0x7fffffffu;  // crowded bucket: search inside it
+  uint32_t a = r0 & 0x7fffffffu, e = __ldg(&dir[b + 1].base) & 0x7fffffffu;  // crowded bucket: search inside it
   while (a < e) {
     const uint32_t mid = a + ((e - a) >> 1);
     const uint32_t v = __ldg(g + mid);
