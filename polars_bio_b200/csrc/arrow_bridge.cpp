@@ -93,7 +93,7 @@ class Pool {
  private:
   Pool() {
     unsigned hc = std::thread::hardware_concurrency();
-    int n = (int)std::min<unsigned>(hc ? hc : 4, 32);
+    int n = (int)std::min<unsigned>(hc ? hc : 4, 64);
     const char *e = getenv("PBGPU_HOST_THREADS");
     if (e && atoi(e) > 0) n = atoi(e);
     for (int i = 1; i < n; ++i) workers_.emplace_back([this] { loop(); });
@@ -150,28 +150,30 @@ struct PinnedBuf {
   void *p = nullptr;
   size_t cap = 0;
   bool busy = false;
+  bool wc = false;  // write-combined: H2D staging only (CPU writes, never reads)
 };
 std::mutex g_pin_mu;
 std::vector<PinnedBuf> g_pin;
 
-void *pinned_get(size_t bytes) {
+void *pinned_get(size_t bytes, bool wc = false) {
   if (bytes == 0) bytes = 1;
   std::lock_guard<std::mutex> lk(g_pin_mu);
   int best = -1;
   for (int i = 0; i < (int)g_pin.size(); ++i)
-    if (!g_pin[i].busy && g_pin[i].cap >= bytes && (best < 0 || g_pin[i].cap < g_pin[best].cap)) best = i;
+    if (!g_pin[i].busy && g_pin[i].wc == wc && g_pin[i].cap >= bytes && (best < 0 || g_pin[i].cap < g_pin[best].cap)) best = i;
   if (best >= 0) {
     g_pin[best].busy = true;
     return g_pin[best].p;
   }
   PinnedBuf b;
   size_t cap = (bytes + (1 << 20) - 1) & ~(size_t)((1 << 20) - 1);
-  if (cudaHostAlloc(&b.p, cap, cudaHostAllocPortable) != cudaSuccess) {
+  if (cudaHostAlloc(&b.p, cap, cudaHostAllocPortable | (wc ? cudaHostAllocWriteCombined : 0)) != cudaSuccess) {
     cudaGetLastError();
     return nullptr;
   }
   b.cap = cap;
   b.busy = true;
+  b.wc = wc;
   g_pin.push_back(b);
   return b.p;
 }
@@ -183,9 +185,10 @@ void pinned_put(void *p) {
 }
 struct PinnedHold {  // returns its buffers to the cache on destruction
   std::vector<void *> v;
+  bool wc = false;
   template <typename T>
   T *get(size_t count) {
-    void *p = pinned_get(count * sizeof(T));
+    void *p = pinned_get(count * sizeof(T), wc);
     if (p) v.push_back(p);
     return (T *)p;
   }
@@ -338,7 +341,8 @@ inline int64_t int_at(const void *buf, char f, int64_t j) {
 inline bool is_int_format(const char *f) { return f && f[0] && !f[1] && strchr("cCsSiIlL", f[0]); }
 
 // Encode the three key columns of a table into int32 staging (code = -1 for null keys).
-int encode_keys(const Table &t, const char *side, ContigDict &dict, int32_t *code, int32_t *st, int32_t *en) {
+int encode_keys(const Table &t, const char *side, ContigDict &dict, int32_t *code, int32_t *st, int32_t *en,
+                int64_t row_lo = 0, int64_t row_hi = INT64_MAX) {
   const ArrowSchema *fc = t.schema.children[t.key[0]];
   const ArrowSchema *fs = t.schema.children[t.key[1]];
   const ArrowSchema *fe = t.schema.children[t.key[2]];
@@ -353,8 +357,10 @@ int encode_keys(const Table &t, const char *side, ContigDict &dict, int32_t *cod
 
   struct Task { int b; int64_t lo, hi; };
   std::vector<Task> tasks;
-  for (int b = 0; b < (int)t.batches.size(); ++b)
-    for (int64_t lo = 0; lo < t.batches[b].length; lo += kChunk) tasks.push_back({b, lo, std::min(lo + kChunk, t.batches[b].length)});
+  for (int b = 0; b < (int)t.batches.size(); ++b) {  // the part of every batch inside [row_lo,row_hi), in kChunk pieces
+    const int64_t b_lo = std::max<int64_t>(0, row_lo - t.start[b]), b_hi = std::min<int64_t>(t.batches[b].length, row_hi - t.start[b]);
+    for (int64_t lo = b_lo; lo < b_hi; lo += kChunk) tasks.push_back({b, lo, std::min(lo + kChunk, b_hi)});
+  }
   std::atomic<int> range_err{0};
   Pool::get().parallel_for((int64_t)tasks.size(), [&](int64_t ti) {
     const Task &tk = tasks[ti];
@@ -522,105 +528,106 @@ std::string out_format(const ArrowSchema *f, bool *ok) {
   return "";
 }
 
-// Gather rows of one column into a fresh owned array.  rows[i] == PBGPU_NO_PARTNER -> null.
-int gather_column(const Table &t, int col, const uint32_t *rows, int64_t n, ArrowArray *out) {
-  const ArrowSchema *f = t.schema.children[col];
-  std::unique_ptr<OwnedArray> o(new OwnedArray());
-  const int64_t nchunks = (n + kGatherChunk - 1) / kGatherChunk;
-  const size_t vbytes = (size_t)((n + 7) / 8);
-  uint8_t *valid = (uint8_t *)calloc(vbytes ? vbytes : 1, 1);
-  if (!valid) return set_error(PBGPU_ENOMEM, "host allocation failed");
-  o->bufs.push_back(valid);
-  std::vector<int64_t> chunk_nulls((size_t)std::max<int64_t>(nchunks, 1), 0);
-  const bool is_dict = f->dictionary != nullptr;
-  const StrKind sk = str_kind(is_dict ? f->dictionary->format : f->format);
-  const int w = (!is_dict && sk == StrKind::None) ? fixed_width(f->format) : 0;
-  const bool is_bool = !is_dict && !strcmp(f->format, "b");
-  const bool is_null_type = !is_dict && !strcmp(f->format, "n");
+// Gather of one output column, split in two phases so that every column of a batch can share the same two
+// parallel_for sweeps (tasks = columns x 16K-row chunks): pass 1 sizes variable-width data, pass 2 copies.
+// rows[i] == PBGPU_NO_PARTNER -> null.
+struct ColGather {
+  const Table *t = nullptr;
+  int col = 0;
+  const uint32_t *rows = nullptr;
+  int64_t n = 0, nchunks = 0;
+  const ArrowSchema *f = nullptr;
+  bool is_dict = false, is_bool = false, is_null_type = false, large = false;
+  StrKind sk = StrKind::None;
+  int w = 0;
+  std::unique_ptr<OwnedArray> o;
+  uint8_t *valid = nullptr, *vals = nullptr;
+  void *offs = nullptr;
+  char *data = nullptr;
+  std::vector<int64_t> chunk_nulls, chunk_bytes, chunk_off;
+  std::vector<uint32_t> lens;
+  int64_t total = 0;
 
-  auto src_valid = [&](const ArrowArray *a, int64_t j) -> bool {
+  int init(const Table &tab, int c, const uint32_t *r, int64_t count) {
+    t = &tab; col = c; rows = r; n = count;
+    nchunks = (n + kGatherChunk - 1) / kGatherChunk;
+    f = tab.schema.children[c];
+    o.reset(new OwnedArray());
+    is_dict = f->dictionary != nullptr;
+    sk = str_kind(is_dict ? f->dictionary->format : f->format);
+    w = (!is_dict && sk == StrKind::None) ? fixed_width(f->format) : 0;
+    is_bool = !is_dict && !strcmp(f->format, "b");
+    is_null_type = !is_dict && !strcmp(f->format, "n");
+    if (is_null_type) return PBGPU_OK;
+    if (!(w > 0 || is_bool || sk != StrKind::None))
+      return set_error(PBGPU_ESCHEMA, "payload column '%s' has unsupported Arrow type '%s' for materialised output (use emit=1 index pairs)",
+                       f->name, f->format);
+    const size_t vbytes = (size_t)((n + 7) / 8);
+    valid = (uint8_t *)calloc(vbytes ? vbytes : 1, 1);
+    if (!valid) return set_error(PBGPU_ENOMEM, "host allocation failed");
+    o->bufs.push_back(valid);
+    chunk_nulls.assign((size_t)std::max<int64_t>(nchunks, 1), 0);
+    if (sk != StrKind::None) {
+      large = is_dict || sk != StrKind::Utf8;  // views / dictionaries come out as large_utf8
+      chunk_bytes.assign(chunk_nulls.size(), 0);
+      chunk_off.assign(chunk_nulls.size(), 0);
+      lens.resize((size_t)n);
+    } else {
+      vals = (uint8_t *)(is_bool ? calloc(vbytes ? vbytes : 1, 1) : malloc((size_t)n * w + 1));
+      if (!vals) return set_error(PBGPU_ENOMEM, "host allocation failed");
+      o->bufs.push_back(vals);
+    }
+    return PBGPU_OK;
+  }
+  static inline bool src_valid(const ArrowArray *a, int64_t j) {
     return a->null_count == 0 || !a->buffers[0] || bit_get((const uint8_t *)a->buffers[0], j);
-  };
-
-  if (is_null_type) {
-    o->bptr = {};  // null arrays carry no buffers
-    ArrowArray a = finish_array(o.release(), n, n);
-    *out = a;
-    return PBGPU_OK;
   }
-  if (w > 0 || is_bool) {
-    uint8_t *vals = (uint8_t *)(is_bool ? calloc(vbytes ? vbytes : 1, 1) : malloc((size_t)n * w + 1));
-    if (!vals) return set_error(PBGPU_ENOMEM, "host allocation failed");
-    o->bufs.push_back(vals);
-    // chunk boundaries are multiples of 8 rows, so bitmap bytes are private to a chunk
-    Pool::get().parallel_for(nchunks, [&](int64_t ci) {
-      const int64_t lo = ci * kGatherChunk, hi = std::min(n, lo + kGatherChunk);
-      int64_t nulls = 0;
-      for (int64_t i = lo; i < hi; ++i) {
-        const uint32_t r = rows[i];
-        if (r == PBGPU_NO_PARTNER) { ++nulls; if (!is_bool) memset(vals + (size_t)i * w, 0, w); continue; }
-        int b; int64_t li;
-        t.locate(r, b, li);
-        const ArrowArray &ba = t.batches[b];
-        const ArrowArray *a = ba.children[col];
-        const int64_t j = li + a->offset + ba.offset;
-        if (!src_valid(a, j)) { ++nulls; if (!is_bool) memset(vals + (size_t)i * w, 0, w); continue; }
-        bit_set(valid, i);
-        if (is_bool) { if (bit_get((const uint8_t *)a->buffers[1], j)) bit_set(vals, i); }
-        else memcpy(vals + (size_t)i * w, (const uint8_t *)a->buffers[1] + (size_t)j * w, w);
-      }
-      chunk_nulls[ci] = nulls;
-    });
-    int64_t nulls = 0;
-    for (auto v : chunk_nulls) nulls += v;
-    o->bptr = {nulls ? (const void *)valid : nullptr, vals};
-    *out = finish_array(o.release(), n, nulls);
-    return PBGPU_OK;
+  inline bool fetch(uint32_t r, std::string_view *sv) const {
+    if (r == PBGPU_NO_PARTNER) return false;
+    int b; int64_t li;
+    t->locate(r, b, li);
+    const ArrowArray &ba = t->batches[b];
+    const ArrowArray *a = ba.children[col];
+    const int64_t j = li + a->offset + ba.offset;
+    if (!src_valid(a, j)) return false;
+    if (is_dict) {
+      const ArrowArray *d = a->dictionary;
+      const int64_t k = int_at(a->buffers[1], f->format[0], j);
+      if (k < 0 || k >= d->length || !src_valid(d, k + d->offset)) return false;
+      *sv = str_at(d, sk, k + d->offset);
+    } else *sv = str_at(a, sk, j);
+    return true;
   }
-  if (sk != StrKind::None) {
-    const bool large = is_dict || sk != StrKind::Utf8;  // views / dictionaries come out as large_utf8
-    // pass 1: lengths
-    std::vector<int64_t> chunk_bytes((size_t)std::max<int64_t>(nchunks, 1), 0);
-    std::vector<uint32_t> lens((size_t)n);
-    auto fetch = [&](uint32_t r, std::string_view *sv) -> bool {
-      if (r == PBGPU_NO_PARTNER) return false;
-      int b; int64_t li;
-      t.locate(r, b, li);
-      const ArrowArray &ba = t.batches[b];
-      const ArrowArray *a = ba.children[col];
-      const int64_t j = li + a->offset + ba.offset;
-      if (!src_valid(a, j)) return false;
-      if (is_dict) {
-        const ArrowArray *d = a->dictionary;
-        const int64_t k = int_at(a->buffers[1], f->format[0], j);
-        if (k < 0 || k >= d->length || !src_valid(d, k + d->offset)) return false;
-        *sv = str_at(d, sk, k + d->offset);
-      } else *sv = str_at(a, sk, j);
-      return true;
-    };
-    Pool::get().parallel_for(nchunks, [&](int64_t ci) {
-      const int64_t lo = ci * kGatherChunk, hi = std::min(n, lo + kGatherChunk);
-      int64_t nulls = 0, bytes = 0;
-      for (int64_t i = lo; i < hi; ++i) {
-        std::string_view sv;
-        if (fetch(rows[i], &sv)) { bit_set(valid, i); lens[i] = (uint32_t)sv.size(); bytes += (int64_t)sv.size(); }
-        else { ++nulls; lens[i] = 0; }
-      }
-      chunk_nulls[ci] = nulls;
-      chunk_bytes[ci] = bytes;
-    });
-    int64_t total = 0, nulls = 0;
-    std::vector<int64_t> chunk_off((size_t)std::max<int64_t>(nchunks, 1), 0);
-    for (int64_t ci = 0; ci < nchunks; ++ci) { chunk_off[ci] = total; total += chunk_bytes[ci]; nulls += chunk_nulls[ci]; }
+  void pass1(int64_t ci) {  // strings: lengths + validity
+    if (sk == StrKind::None || is_null_type) return;
+    const int64_t lo = ci * kGatherChunk, hi = std::min(n, lo + kGatherChunk);
+    int64_t nulls = 0, bytes = 0;
+    for (int64_t i = lo; i < hi; ++i) {
+      std::string_view sv;
+      if (fetch(rows[i], &sv)) { bit_set(valid, i); lens[i] = (uint32_t)sv.size(); bytes += (int64_t)sv.size(); }
+      else { ++nulls; lens[i] = 0; }
+    }
+    chunk_nulls[ci] = nulls;
+    chunk_bytes[ci] = bytes;
+  }
+  int alloc() {  // between the passes: offsets of the chunks, data buffers
+    if (sk == StrKind::None || is_null_type) return PBGPU_OK;
+    total = 0;
+    for (int64_t ci = 0; ci < nchunks; ++ci) { chunk_off[ci] = total; total += chunk_bytes[ci]; }
     if (!large && total > INT32_MAX)
       return set_error(PBGPU_ERANGE, "utf8 column '%s' would exceed 2 GiB in one output batch; lower max_batch_rows or use large_utf8", f->name);
-    void *offs = malloc((size_t)(n + 1) * (large ? 8 : 4));
-    char *data = (char *)malloc((size_t)total + 1);
+    offs = malloc((size_t)(n + 1) * (large ? 8 : 4));
+    data = (char *)malloc((size_t)total + 1);
     if (!offs || !data) { free(offs); free(data); return set_error(PBGPU_ENOMEM, "host allocation failed"); }
     o->bufs.push_back(offs);
     o->bufs.push_back(data);
-    Pool::get().parallel_for(nchunks, [&](int64_t ci) {
-      const int64_t lo = ci * kGatherChunk, hi = std::min(n, lo + kGatherChunk);
+    if (large) ((int64_t *)offs)[n] = total; else ((int32_t *)offs)[n] = (int32_t)total;
+    return PBGPU_OK;
+  }
+  void pass2(int64_t ci) {
+    if (is_null_type) return;
+    const int64_t lo = ci * kGatherChunk, hi = std::min(n, lo + kGatherChunk);
+    if (sk != StrKind::None) {
       int64_t pos = chunk_off[ci];
       for (int64_t i = lo; i < hi; ++i) {
         if (large) ((int64_t *)offs)[i] = pos; else ((int32_t *)offs)[i] = (int32_t)pos;
@@ -631,14 +638,50 @@ int gather_column(const Table &t, int col, const uint32_t *rows, int64_t n, Arro
           pos += (int64_t)sv.size();
         }
       }
-    });
-    if (large) ((int64_t *)offs)[n] = total; else ((int32_t *)offs)[n] = (int32_t)total;
-    o->bptr = {nulls ? (const void *)valid : nullptr, offs, data};
-    *out = finish_array(o.release(), n, nulls);
-    return PBGPU_OK;
+      return;
+    }
+    int64_t nulls = 0;
+    const bool one = t->batches.size() == 1;
+    for (int64_t i = lo; i < hi; ++i) {
+      const uint32_t r = rows[i];
+      if (r == PBGPU_NO_PARTNER) { ++nulls; if (!is_bool) memset(vals + (size_t)i * w, 0, w); continue; }
+      int b = 0; int64_t li = r;
+      if (!one) t->locate(r, b, li);
+      const ArrowArray &ba = t->batches[b];
+      const ArrowArray *a = ba.children[col];
+      const int64_t j = li + a->offset + ba.offset;
+      if (!src_valid(a, j)) { ++nulls; if (!is_bool) memset(vals + (size_t)i * w, 0, w); continue; }
+      bit_set(valid, i);
+      if (is_bool) { if (bit_get((const uint8_t *)a->buffers[1], j)) bit_set(vals, i); }
+      else if (w == 4) ((uint32_t *)vals)[i] = ((const uint32_t *)a->buffers[1])[j];
+      else if (w == 8) ((uint64_t *)vals)[i] = ((const uint64_t *)a->buffers[1])[j];
+      else memcpy(vals + (size_t)i * w, (const uint8_t *)a->buffers[1] + (size_t)j * w, w);
+    }
+    chunk_nulls[ci] = nulls;
   }
-  return set_error(PBGPU_ESCHEMA, "payload column '%s' has unsupported Arrow type '%s' for materialised output (use emit=1 index pairs)",
-                   f->name, f->format);
+  ArrowArray finish() {
+    if (is_null_type) { o->bptr = {}; return finish_array(o.release(), n, n); }
+    int64_t nulls = 0;
+    for (auto v : chunk_nulls) nulls += v;
+    if (sk != StrKind::None) o->bptr = {nulls ? (const void *)valid : nullptr, offs, data};
+    else o->bptr = {nulls ? (const void *)valid : nullptr, vals};
+    return finish_array(o.release(), n, nulls);
+  }
+};
+
+// gather several (table, column, row list) jobs of one output batch together
+struct GatherJob { const Table *t; int col; const uint32_t *rows; };
+int gather_columns(const std::vector<GatherJob> &jobs, int64_t n, std::vector<ArrowArray> *out) {
+  std::vector<ColGather> g(jobs.size());
+  for (size_t k = 0; k < jobs.size(); ++k) { int rc = g[k].init(*jobs[k].t, jobs[k].col, jobs[k].rows, n); if (rc != PBGPU_OK) return rc; }
+  const int64_t nchunks = (n + kGatherChunk - 1) / kGatherChunk, nj = (int64_t)jobs.size();
+  bool any_str = false;
+  for (auto &c : g) any_str |= c.sk != StrKind::None;
+  if (any_str) Pool::get().parallel_for(nj * nchunks, [&](int64_t ti) { g[ti / nchunks].pass1(ti % nchunks); });
+  for (auto &c : g) { int rc = c.alloc(); if (rc != PBGPU_OK) return rc; }
+  Pool::get().parallel_for(nj * nchunks, [&](int64_t ti) { g[ti / nchunks].pass2(ti % nchunks); });
+  for (auto &c : g) out->push_back(c.finish());
+  return PBGPU_OK;
 }
 
 template <typename T>
@@ -708,6 +751,24 @@ ArrowArray view_column(const std::shared_ptr<Table> &t, int batch, int col, int6
   v.private_data = new ViewPriv{t};
   return v;
 }
+// zero-copy view of a slice of an engine result buffer (pinned, owned by the stream via `keep`)
+struct BufViewPriv { std::shared_ptr<void> keep; const void *bufs[2]; };
+void release_buf_view(ArrowArray *a) {
+  if (!a || !a->release) return;
+  delete (BufViewPriv *)a->private_data;
+  a->release = nullptr;
+}
+ArrowArray view_buffer(const std::shared_ptr<void> &keep, const void *data, int64_t len) {
+  BufViewPriv *p = new BufViewPriv{keep, {nullptr, data}};
+  ArrowArray v{};
+  v.length = len;
+  v.null_count = 0;
+  v.n_buffers = 2;
+  v.buffers = p->bufs;
+  v.release = release_buf_view;
+  v.private_data = p;
+  return v;
+}
 ArrowSchema copy_schema(const ArrowSchema *f, const std::string &name) {
   std::vector<ArrowSchema> kids;
   for (int64_t i = 0; i < f->n_children; ++i) kids.push_back(copy_schema(f->children[i], f->children[i]->name ? f->children[i]->name : ""));
@@ -725,7 +786,7 @@ struct OutStream {
   std::shared_ptr<Table> left, right;  // shared with zero-copy output views of their columns
   PbRangeOptions opt{};
   std::string suffix1 = "_1", suffix2 = "_2";
-  PinnedHold pins;           // result arrays live in cached pinned memory until release
+  std::shared_ptr<PinnedHold> pins = std::make_shared<PinnedHold>();  // result arrays: cached pinned memory, shared with zero-copy output views
   int64_t n_out = 0;         // result rows
   const uint32_t *lrow = nullptr;  // per result row: row of `left`  (may be NULL when not needed)
   const uint32_t *rrow = nullptr;  // per result row: row of `right` (PBGPU_NO_PARTNER = null)
@@ -792,24 +853,35 @@ int out_get_next(ArrowArrayStream *s, ArrowArray *out) {
   std::unique_ptr<OwnedArray> top(new OwnedArray());
   int rc = PBGPU_OK;
   auto push = [&](ArrowArray &&a) { top->kids.push_back(a); };
+  std::vector<GatherJob> jobs;
   auto add_table = [&](const Table &t, const uint32_t *rows) {
-    for (int c = 0; c < (int)t.n_cols() && rc == PBGPU_OK; ++c) {
-      ArrowArray a{};
-      rc = gather_column(t, c, rows + lo, n, &a);
-      if (rc == PBGPU_OK) push(std::move(a));
-    }
+    for (int c = 0; c < (int)t.n_cols(); ++c) jobs.push_back(GatherJob{&t, c, rows + lo});
   };
+  auto run_jobs = [&]() {
+    std::vector<ArrowArray> cols;
+    rc = gather_columns(jobs, n, &cols);
+    if (rc == PBGPU_OK) for (auto &a : cols) push(std::move(a));
+    else for (auto &a : cols) if (a.release) a.release(&a);
+  };
+  const std::shared_ptr<void> keep = st->pins;
+  const bool pinned_rows = st->own_l.empty();  // row lists straight from the engine (pinned) vs host-built vectors
   if (o.emit == 1) {
-    ArrowArray a{};
-    rc = plain_column<uint32_t>(st->lrow + lo, n, nullptr, &a);
-    if (rc == PBGPU_OK) { push(std::move(a)); ArrowArray b{}; rc = o.range_op == PBGPU_OP_NEAREST ? nullable_u32_column(st->rrow + lo, n, &b) : plain_column<uint32_t>(st->rrow + lo, n, nullptr, &b); if (rc == PBGPU_OK) push(std::move(b)); }
+    if (pinned_rows) push(view_buffer(keep, st->lrow + lo, n));
+    else { ArrowArray a{}; rc = plain_column<uint32_t>(st->lrow + lo, n, nullptr, &a); if (rc == PBGPU_OK) push(std::move(a)); }
+    if (rc == PBGPU_OK) {
+      if (o.range_op == PBGPU_OP_NEAREST) { ArrowArray b{}; rc = nullable_u32_column(st->rrow + lo, n, &b); if (rc == PBGPU_OK) push(std::move(b)); }
+      else if (pinned_rows) push(view_buffer(keep, st->rrow + lo, n));
+      else { ArrowArray b{}; rc = plain_column<uint32_t>(st->rrow + lo, n, nullptr, &b); if (rc == PBGPU_OK) push(std::move(b)); }
+    }
     if (rc == PBGPU_OK && want_distance(o)) { ArrowArray d{}; rc = nullable_i64_column(st->extra + lo, n, &d); if (rc == PBGPU_OK) push(std::move(d)); }
   } else if (o.range_op == PBGPU_OP_OVERLAP) {
     add_table(*st->left, st->lrow);
     if (o.output_mode == PBGPU_OUT_JOIN) add_table(*st->right, st->rrow);
+    run_jobs();
   } else if (o.range_op == PBGPU_OP_NEAREST) {
     add_table(*st->left, st->lrow);
     add_table(*st->right, st->rrow);
+    run_jobs();
     if (rc == PBGPU_OK && want_distance(o)) { ArrowArray d{}; rc = nullable_i64_column(st->extra + lo, n, &d); if (rc == PBGPU_OK) push(std::move(d)); }
   } else {
     // zero-copy: slice the current input batch (output batches follow the input batch boundaries)
@@ -818,9 +890,7 @@ int out_get_next(ArrowArrayStream *s, ArrowArray *out) {
     const int64_t avail = t.batches[st->view_batch].length - st->view_off;
     const int64_t len = std::min<int64_t>(std::min<int64_t>(n, avail), st->n_out - lo);
     for (int c = 0; c < (int)t.n_cols(); ++c) push(view_column(st->right, st->view_batch, c, st->view_off, len));
-    ArrowArray d{};
-    rc = plain_column<int64_t>(st->extra + lo, len, nullptr, &d);
-    if (rc == PBGPU_OK) push(std::move(d));
+    push(view_buffer(keep, st->extra + lo, len));  // the count / coverage column: a view of the D2H buffer
     if (rc == PBGPU_OK) {
       top->bptr = {nullptr};
       *out = finish_array(top.release(), len, 0);
@@ -880,15 +950,13 @@ int run(Table *L, Table *R, OutStream *os) {
   Table *IT = iter_is_left ? L : R, *IX = iter_is_left ? R : L;
   Trace tr;
   ContigDict dict;
-  PinnedHold stage;  // input staging: returned to the cache when this call ends
+  PinnedHold stage;     // D2H landing buffers the host reads (returned to the cache when this call ends)
+  PinnedHold stage_wc;  // H2D staging: write-combined pinned memory, written once by the encoders, read by DMA
+  stage_wc.wc = true;
   const int64_t n = IT->rows, m = IX->rows;
-  int32_t *hc_i = stage.get<int32_t>(n), *hs_i = stage.get<int32_t>(n), *he_i = stage.get<int32_t>(n);
-  int32_t *hc_x = stage.get<int32_t>(m), *hs_x = stage.get<int32_t>(m), *he_x = stage.get<int32_t>(m);
+  int32_t *hc_i = stage_wc.get<int32_t>(n), *hs_i = stage_wc.get<int32_t>(n), *he_i = stage_wc.get<int32_t>(n);
+  int32_t *hc_x = stage_wc.get<int32_t>(m), *hs_x = stage_wc.get<int32_t>(m), *he_x = stage_wc.get<int32_t>(m);
   if (!hc_i || !hs_i || !he_i || !hc_x || !hs_x || !he_x) return set_error(PBGPU_ENOMEM, "pinned staging allocation failed");
-  BR_TRY(encode_keys(*IX, iter_is_left ? "right" : "left", dict, hc_x, hs_x, he_x));
-  BR_TRY(encode_keys(*IT, iter_is_left ? "left" : "right", dict, hc_i, hs_i, he_i));
-  const int32_t n_contigs = (int32_t)dict.map.size();
-  tr.lap("encode keys -> pinned");
 
   int prev_dev = -1;
   if (o.device >= 0) { BR_CUDA(cudaGetDevice(&prev_dev)); BR_CUDA(cudaSetDevice(o.device)); }
@@ -900,22 +968,38 @@ int run(Table *L, Table *R, OutStream *os) {
   int32_t *dc_x = dev.get<int32_t>(m), *ds_x = dev.get<int32_t>(m), *de_x = dev.get<int32_t>(m);
   int32_t *dc_i = dev.get<int32_t>(n), *ds_i = dev.get<int32_t>(n), *de_i = dev.get<int32_t>(n);
   if (!dc_x || !ds_x || !de_x || !dc_i || !ds_i || !de_i) return set_error(PBGPU_ENOMEM, "device allocation failed");
+
+  // indexed side first: encode -> H2D -> index build.  Contigs that only occur on the iterated side get codes
+  // >= n_contigs of the index and are treated as null keys by the kernels (they cannot match anything anyway).
+  BR_TRY(encode_keys(*IX, iter_is_left ? "right" : "left", dict, hc_x, hs_x, he_x));
+  const int32_t n_contigs = (int32_t)dict.map.size();
   BR_CUDA(cudaMemcpyAsync(dc_x, hc_x, 4 * (size_t)m, cudaMemcpyHostToDevice, s));
   BR_CUDA(cudaMemcpyAsync(ds_x, hs_x, 4 * (size_t)m, cudaMemcpyHostToDevice, s));
   BR_CUDA(cudaMemcpyAsync(de_x, he_x, 4 * (size_t)m, cudaMemcpyHostToDevice, s));
-  BR_CUDA(cudaMemcpyAsync(dc_i, hc_i, 4 * (size_t)n, cudaMemcpyHostToDevice, s));
-  BR_CUDA(cudaMemcpyAsync(ds_i, hs_i, 4 * (size_t)n, cudaMemcpyHostToDevice, s));
-  BR_CUDA(cudaMemcpyAsync(de_i, he_i, 4 * (size_t)n, cudaMemcpyHostToDevice, s));
-
+  tr.lap("encode + H2D indexed side");
   pbgpu_index *ix = nullptr;
   BR_TRY(pbgpu_index_build(dc_x, ds_x, de_x, m, n_contigs, s, &ix));
+  tr.lap("index build");
+  // iterated side in slices: the DMA of slice k runs while the host encodes slice k+1
+  {
+    const int64_t slice = std::max<int64_t>(1 << 20, (n + 7) / 8);
+    for (int64_t lo = 0; lo < n; lo += slice) {
+      const int64_t hi = std::min(n, lo + slice);
+      int rc = encode_keys(*IT, iter_is_left ? "left" : "right", dict, hc_i, hs_i, he_i, lo, hi);
+      if (rc != PBGPU_OK) { pbgpu_index_free(ix); return rc; }
+      cudaMemcpyAsync(dc_i + lo, hc_i + lo, 4 * (size_t)(hi - lo), cudaMemcpyHostToDevice, s);
+      cudaMemcpyAsync(ds_i + lo, hs_i + lo, 4 * (size_t)(hi - lo), cudaMemcpyHostToDevice, s);
+      cudaMemcpyAsync(de_i + lo, he_i + lo, 4 * (size_t)(hi - lo), cudaMemcpyHostToDevice, s);
+    }
+    if (cudaGetLastError() != cudaSuccess) { pbgpu_index_free(ix); return set_error(PBGPU_ECUDA, "H2D copy of the iterated table failed"); }
+  }
+  tr.lap("encode + H2D iterated side");
   struct IxGuard { pbgpu_index *p; ~IxGuard() { pbgpu_index_free(p); } } ig{ix};
   const uint64_t limit = o.limit;
-  tr.lap("H2D enqueue + index build");
 
   if (o.range_op == PBGPU_OP_COUNT_OVERLAPS_NAIVE || o.range_op == PBGPU_OP_COVERAGE) {
     int64_t *d_out = dev.get<int64_t>(n);
-    int64_t *h_out = os->pins.get<int64_t>(n);
+    int64_t *h_out = os->pins->get<int64_t>(n);
     if (!d_out || !h_out) return set_error(PBGPU_ENOMEM, "allocation failed");
     if (o.range_op == PBGPU_OP_COVERAGE) BR_TRY(pbgpu_coverage(ix, dc_i, ds_i, de_i, n, o.filter_op, d_out, s));
     else BR_TRY(pbgpu_count_overlaps(ix, dc_i, ds_i, de_i, n, o.filter_op, d_out, s));
@@ -940,7 +1024,7 @@ int run(Table *L, Table *R, OutStream *os) {
     BR_TRY(pbgpu_overlap_count(ix, dc_i, ds_i, de_i, n, o.filter_op, s, &plan, &total));
     struct PlanGuard { pbgpu_overlap_plan *p; ~PlanGuard() { pbgpu_overlap_plan_free(p); } } pg{plan};
     uint32_t *d_p = dev.get<uint32_t>((size_t)total), *d_b = dev.get<uint32_t>((size_t)total);
-    uint32_t *h_p = os->pins.get<uint32_t>((size_t)total), *h_b = os->pins.get<uint32_t>((size_t)total);
+    uint32_t *h_p = os->pins->get<uint32_t>((size_t)total), *h_b = os->pins->get<uint32_t>((size_t)total);
     if (!d_p || !d_b || !h_p || !h_b) return set_error(PBGPU_ENOMEM, "allocation failed for %lld pairs", (long long)total);
     BR_TRY(pbgpu_overlap_emit(plan, d_p, d_b, s));
     BR_CUDA(cudaMemcpyAsync(h_p, d_p, 4 * (size_t)total, cudaMemcpyDeviceToHost, s));
