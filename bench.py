@@ -198,7 +198,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    # weak scaling: every rank owns an independent config-2 batch (contigs shard; no data-path collective)
+    if world > 1:
+        return run_sharded(args, world, rank, dev)
     probe, build, nc = make_config2(args.reads, args.variants, seed_shift=100 * rank)
     n, m = args.reads, args.variants
     h = [torch.from_numpy(x).pin_memory() for x in (*probe, *build)]

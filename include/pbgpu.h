@@ -130,6 +130,14 @@ PBGPU_API int pbgpu_pack_by_owner(const int32_t *d_contig, const int32_t *d_star
                                   uint32_t row_id_base, int32_t *d_packed, int64_t *d_rank_counts,
                                   void *stream);
 
+/* After the all-to-all: split received 16-byte records back into columns (d_row = global row ids).     */
+PBGPU_API int pbgpu_unpack_records(const int32_t *d_packed, int64_t n, int32_t *d_contig, int32_t *d_start,
+                                   int32_t *d_end, uint32_t *d_row, void *stream);
+/* Pair buffers of a shard hold positions in the shard's received columns; map them to global row ids:
+ * d_out[i] = d_global_of_local[d_local[i]]  (PBGPU_NO_PARTNER passes through).  d_out may alias d_local. */
+PBGPU_API int pbgpu_translate_rows(const uint32_t *d_local, int64_t n, const uint32_t *d_global_of_local,
+                                   uint32_t *d_out, void *stream);
+
 /* CUDA-event durations (ns) of the most recent index build / provider kernels issued by the calling
  * thread, measured on the stream they were launched on (events are recorded on every call; this function
  * waits for the last one).  A stage that has not run yet reads 0.                              */

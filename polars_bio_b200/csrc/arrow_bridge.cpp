@@ -141,7 +141,7 @@ class Pool {
   bool stop_ = false;
 };
 
-constexpr int64_t kChunk = 1 << 17;        // rows per key-encoding task
+constexpr int64_t kChunk = 1 << 14;        // rows per key-encoding task (small: a 1M-row H2D slice still feeds 64 threads)
 constexpr int64_t kGatherChunk = 1 << 14;  // rows per gather task (multiple of 8: validity bytes stay task-private)
 
 // ---------------------------------------------------------------------------------------------
@@ -196,6 +196,26 @@ struct PinnedHold {  // returns its buffers to the cache on destruction
     for (void *p : v) pinned_put(p);
   }
 };
+
+// Result arrays handed to the consumer live in plain host memory (they may outlive the call by a long time, and
+// pinned memory is a scarce, slow-to-allocate resource): D2H lands in a cached pinned buffer, then the pool copies
+// it out in parallel and the pinned buffer goes straight back to the cache.
+struct HostBufs {
+  std::vector<void *> v;
+  ~HostBufs() { for (void *p : v) free(p); }
+};
+void *copy_out(HostBufs &hb, const void *pinned, size_t bytes) {
+  void *dst = nullptr;
+  if (posix_memalign(&dst, 64, bytes ? bytes : 64) != 0) return nullptr;
+  hb.v.push_back(dst);
+  const size_t chunk = (size_t)4 << 20;
+  const int64_t nt = (int64_t)((bytes + chunk - 1) / chunk);
+  Pool::get().parallel_for(nt, [&](int64_t i) {
+    const size_t off = (size_t)i * chunk;
+    memcpy((char *)dst + off, (const char *)pinned + off, std::min(chunk, bytes - off));
+  });
+  return dst;
+}
 
 // ---------------------------------------------------------------------------------------------
 inline bool bit_get(const uint8_t *bits, int64_t i) { return (bits[i >> 3] >> (i & 7)) & 1; }
@@ -786,7 +806,7 @@ struct OutStream {
   std::shared_ptr<Table> left, right;  // shared with zero-copy output views of their columns
   PbRangeOptions opt{};
   std::string suffix1 = "_1", suffix2 = "_2";
-  std::shared_ptr<PinnedHold> pins = std::make_shared<PinnedHold>();  // result arrays: cached pinned memory, shared with zero-copy output views
+  std::shared_ptr<HostBufs> pins = std::make_shared<HostBufs>();  // result arrays (host memory), shared with the zero-copy output views
   int64_t n_out = 0;         // result rows
   const uint32_t *lrow = nullptr;  // per result row: row of `left`  (may be NULL when not needed)
   const uint32_t *rrow = nullptr;  // per result row: row of `right` (PBGPU_NO_PARTNER = null)
@@ -999,13 +1019,14 @@ int run(Table *L, Table *R, OutStream *os) {
 
   if (o.range_op == PBGPU_OP_COUNT_OVERLAPS_NAIVE || o.range_op == PBGPU_OP_COVERAGE) {
     int64_t *d_out = dev.get<int64_t>(n);
-    int64_t *h_out = os->pins->get<int64_t>(n);
+    int64_t *h_out = stage.get<int64_t>(n);
     if (!d_out || !h_out) return set_error(PBGPU_ENOMEM, "allocation failed");
     if (o.range_op == PBGPU_OP_COVERAGE) BR_TRY(pbgpu_coverage(ix, dc_i, ds_i, de_i, n, o.filter_op, d_out, s));
     else BR_TRY(pbgpu_count_overlaps(ix, dc_i, ds_i, de_i, n, o.filter_op, d_out, s));
     BR_CUDA(cudaMemcpyAsync(h_out, d_out, 8 * (size_t)n, cudaMemcpyDeviceToHost, s));
     BR_CUDA(cudaStreamSynchronize(s));
-    os->extra = h_out;
+    os->extra = (const int64_t *)copy_out(*os->pins, h_out, 8 * (size_t)n);
+    if (!os->extra) return set_error(PBGPU_ENOMEM, "host allocation failed");
     os->n_out = n;
   } else if (o.range_op == PBGPU_OP_OVERLAP && o.output_mode == PBGPU_OUT_LEFT_DISTINCT) {
     int64_t *d_out = dev.get<int64_t>(n);
@@ -1024,14 +1045,15 @@ int run(Table *L, Table *R, OutStream *os) {
     BR_TRY(pbgpu_overlap_count(ix, dc_i, ds_i, de_i, n, o.filter_op, s, &plan, &total));
     struct PlanGuard { pbgpu_overlap_plan *p; ~PlanGuard() { pbgpu_overlap_plan_free(p); } } pg{plan};
     uint32_t *d_p = dev.get<uint32_t>((size_t)total), *d_b = dev.get<uint32_t>((size_t)total);
-    uint32_t *h_p = os->pins->get<uint32_t>((size_t)total), *h_b = os->pins->get<uint32_t>((size_t)total);
+    uint32_t *h_p = stage.get<uint32_t>((size_t)total), *h_b = stage.get<uint32_t>((size_t)total);
     if (!d_p || !d_b || !h_p || !h_b) return set_error(PBGPU_ENOMEM, "allocation failed for %lld pairs", (long long)total);
     BR_TRY(pbgpu_overlap_emit(plan, d_p, d_b, s));
     BR_CUDA(cudaMemcpyAsync(h_p, d_p, 4 * (size_t)total, cudaMemcpyDeviceToHost, s));
     BR_CUDA(cudaMemcpyAsync(h_b, d_b, 4 * (size_t)total, cudaMemcpyDeviceToHost, s));
     BR_CUDA(cudaStreamSynchronize(s));
-    os->lrow = h_p;
-    os->rrow = h_b;
+    os->lrow = (const uint32_t *)copy_out(*os->pins, h_p, 4 * (size_t)total);
+    os->rrow = (const uint32_t *)copy_out(*os->pins, h_b, 4 * (size_t)total);
+    if (!os->lrow || !os->rrow) return set_error(PBGPU_ENOMEM, "host allocation failed");
     os->n_out = total;
   } else if (o.range_op == PBGPU_OP_NEAREST) {
     const int64_t k = o.nearest_k ? (int64_t)o.nearest_k : 1;

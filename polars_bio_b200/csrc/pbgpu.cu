@@ -471,6 +471,40 @@ __global__ void __launch_bounds__(256) pack_records_kernel(const uint64_t *__res
 
 }  // namespace pbgpu
 
+namespace pbgpu {
+__global__ void __launch_bounds__(256) unpack_records_kernel(const int4 *__restrict__ rec, int64_t n, int32_t *__restrict__ c,
+                                                             int32_t *__restrict__ s, int32_t *__restrict__ e, uint32_t *__restrict__ row) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int4 r = rec[i];
+  c[i] = r.x; s[i] = r.y; e[i] = r.z; row[i] = (uint32_t)r.w;
+}
+__global__ void __launch_bounds__(256) translate_rows_kernel(const uint32_t *__restrict__ idx, int64_t n, const uint32_t *__restrict__ table,
+                                                             uint32_t *__restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const uint32_t k = idx[i]; out[i] = k == PBGPU_NO_PARTNER ? PBGPU_NO_PARTNER : table[k]; }
+}
+}  // namespace pbgpu
+
+extern "C" int pbgpu_unpack_records(const int32_t *d_packed, int64_t n, int32_t *d_contig, int32_t *d_start, int32_t *d_end,
+                                    uint32_t *d_row, void *stream) {
+  if (n < 0) return set_error(PBGPU_EINVAL, "negative n");
+  if (n == 0) return PBGPU_OK;
+  if (!d_packed || !d_contig || !d_start || !d_end || !d_row) return set_error(PBGPU_EINVAL, "NULL argument");
+  PB_LAUNCH(unpack_records_kernel, (unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream, (const int4 *)d_packed, n, d_contig, d_start, d_end, d_row);
+  PB_CHECK_LAUNCH();
+  return PBGPU_OK;
+}
+
+extern "C" int pbgpu_translate_rows(const uint32_t *d_local, int64_t n, const uint32_t *d_global_of_local, uint32_t *d_out, void *stream) {
+  if (n < 0) return set_error(PBGPU_EINVAL, "negative n");
+  if (n == 0) return PBGPU_OK;
+  if (!d_local || !d_global_of_local || !d_out) return set_error(PBGPU_EINVAL, "NULL argument");
+  PB_LAUNCH(translate_rows_kernel, (unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream, d_local, n, d_global_of_local, d_out);
+  PB_CHECK_LAUNCH();
+  return PBGPU_OK;
+}
+
 extern "C" int pbgpu_pack_by_owner(const int32_t *d_contig, const int32_t *d_start, const int32_t *d_end, int64_t n,
                                    const int32_t *d_owner, int32_t n_contigs, int32_t n_ranks, uint32_t row_id_base,
                                    int32_t *d_packed, int64_t *d_rank_counts, void *stream) {
