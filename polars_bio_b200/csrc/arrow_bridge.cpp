@@ -197,16 +197,71 @@ struct PinnedHold {  // returns its buffers to the cache on destruction
   }
 };
 
+// ---------------------------------------------------------------------------------------------
+// Host buffer cache for everything handed to the consumer (result columns, gathered payload).  Large result
+// buffers are otherwise mmap'ed, page-faulted on first touch and munmap'ed on release by glibc on every call
+// (tens of ms per 100 MB): the same allocator sensitivity the reference notes for mimalloc/jemalloc
+// (Cargo.toml:9-11).  Freed blocks >= 64 KiB are kept (up to PBGPU_HOST_CACHE_MB, default 4096) and reused.
+struct HostCache {
+  std::mutex mu;
+  std::unordered_map<size_t, std::vector<void *>> free_;
+  size_t cached = 0, limit = (size_t)4096 << 20;
+  HostCache() {
+    const char *e = getenv("PBGPU_HOST_CACHE_MB");
+    if (e) limit = (size_t)atoll(e) << 20;
+  }
+  ~HostCache() {
+    for (auto &kv : free_) for (void *p : kv.second) free(p);
+  }
+};
+HostCache &host_cache() { static HostCache c; return c; }
+constexpr size_t kHdr = 64;
+inline size_t size_class(size_t bytes) {
+  size_t need = bytes + kHdr;
+  if (need <= ((size_t)64 << 10)) return need;                                  // small: not cached
+  if (need <= ((size_t)1 << 20)) { size_t c = (size_t)64 << 10; while (c < need) c <<= 1; return c; }
+  return (need + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);           // multiples of 1 MiB
+}
+void *hmalloc(size_t bytes) {
+  const size_t cap = size_class(bytes ? bytes : 1);
+  void *base = nullptr;
+  if (cap > ((size_t)64 << 10)) {
+    HostCache &c = host_cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    auto it = c.free_.find(cap);
+    if (it != c.free_.end() && !it->second.empty()) { base = it->second.back(); it->second.pop_back(); c.cached -= cap; }
+  }
+  if (!base && posix_memalign(&base, 64, cap) != 0) return nullptr;
+  *(size_t *)base = cap;
+  return (char *)base + kHdr;
+}
+void *hcalloc(size_t bytes) {
+  void *p = hmalloc(bytes);
+  if (p) memset(p, 0, bytes);
+  return p;
+}
+void hfree(void *p) {
+  if (!p) return;
+  void *base = (char *)p - kHdr;
+  const size_t cap = *(size_t *)base;
+  if (cap > ((size_t)64 << 10)) {
+    HostCache &c = host_cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (c.cached + cap <= c.limit) { c.free_[cap].push_back(base); c.cached += cap; return; }
+  }
+  free(base);
+}
+
 // Result arrays handed to the consumer live in plain host memory (they may outlive the call by a long time, and
 // pinned memory is a scarce, slow-to-allocate resource): D2H lands in a cached pinned buffer, then the pool copies
 // it out in parallel and the pinned buffer goes straight back to the cache.
 struct HostBufs {
   std::vector<void *> v;
-  ~HostBufs() { for (void *p : v) free(p); }
+  ~HostBufs() { for (void *p : v) hfree(p); }
 };
 void *copy_out(HostBufs &hb, const void *pinned, size_t bytes) {
-  void *dst = nullptr;
-  if (posix_memalign(&dst, 64, bytes ? bytes : 64) != 0) return nullptr;
+  void *dst = hmalloc(bytes);
+  if (!dst) return nullptr;
   hb.v.push_back(dst);
   const size_t chunk = (size_t)4 << 20;
   const int64_t nt = (int64_t)((bytes + chunk - 1) / chunk);
@@ -444,7 +499,7 @@ void release_array(ArrowArray *a) {
   OwnedArray *o = (OwnedArray *)a->private_data;
   for (auto &k : o->kids)
     if (k.release) k.release(&k);
-  for (void *p : o->bufs) free(p);
+  for (void *p : o->bufs) hfree(p);
   delete o;
   a->release = nullptr;
 }
@@ -583,7 +638,7 @@ struct ColGather {
       return set_error(PBGPU_ESCHEMA, "payload column '%s' has unsupported Arrow type '%s' for materialised output (use emit=1 index pairs)",
                        f->name, f->format);
     const size_t vbytes = (size_t)((n + 7) / 8);
-    valid = (uint8_t *)calloc(vbytes ? vbytes : 1, 1);
+    valid = (uint8_t *)hcalloc(vbytes ? vbytes : 1);
     if (!valid) return set_error(PBGPU_ENOMEM, "host allocation failed");
     o->bufs.push_back(valid);
     chunk_nulls.assign((size_t)std::max<int64_t>(nchunks, 1), 0);
@@ -593,7 +648,7 @@ struct ColGather {
       chunk_off.assign(chunk_nulls.size(), 0);
       lens.resize((size_t)n);
     } else {
-      vals = (uint8_t *)(is_bool ? calloc(vbytes ? vbytes : 1, 1) : malloc((size_t)n * w + 1));
+      vals = (uint8_t *)(is_bool ? hcalloc(vbytes ? vbytes : 1) : hmalloc((size_t)n * w + 1));
       if (!vals) return set_error(PBGPU_ENOMEM, "host allocation failed");
       o->bufs.push_back(vals);
     }
@@ -636,9 +691,9 @@ struct ColGather {
     for (int64_t ci = 0; ci < nchunks; ++ci) { chunk_off[ci] = total; total += chunk_bytes[ci]; }
     if (!large && total > INT32_MAX)
       return set_error(PBGPU_ERANGE, "utf8 column '%s' would exceed 2 GiB in one output batch; lower max_batch_rows or use large_utf8", f->name);
-    offs = malloc((size_t)(n + 1) * (large ? 8 : 4));
-    data = (char *)malloc((size_t)total + 1);
-    if (!offs || !data) { free(offs); free(data); return set_error(PBGPU_ENOMEM, "host allocation failed"); }
+    offs = hmalloc((size_t)(n + 1) * (large ? 8 : 4));
+    data = (char *)hmalloc((size_t)total + 1);
+    if (!offs || !data) { hfree(offs); hfree(data); return set_error(PBGPU_ENOMEM, "host allocation failed"); }
     o->bufs.push_back(offs);
     o->bufs.push_back(data);
     if (large) ((int64_t *)offs)[n] = total; else ((int32_t *)offs)[n] = (int32_t)total;
@@ -708,7 +763,7 @@ template <typename T>
 int plain_column(const T *src, int64_t n, const uint8_t *null_if_zero_flag, ArrowArray *out) {
   (void)null_if_zero_flag;
   std::unique_ptr<OwnedArray> o(new OwnedArray());
-  T *v = (T *)malloc(sizeof(T) * (size_t)(n ? n : 1));
+  T *v = (T *)hmalloc(sizeof(T) * (size_t)(n ? n : 1));
   if (!v) return set_error(PBGPU_ENOMEM, "host allocation failed");
   memcpy(v, src, sizeof(T) * (size_t)n);
   o->bufs.push_back(v);
@@ -720,9 +775,9 @@ int plain_column(const T *src, int64_t n, const uint8_t *null_if_zero_flag, Arro
 // int64 column where value < 0 means null (nearest distance)
 int nullable_i64_column(const int64_t *src, int64_t n, ArrowArray *out) {
   std::unique_ptr<OwnedArray> o(new OwnedArray());
-  int64_t *v = (int64_t *)malloc(8 * (size_t)(n ? n : 1));
-  uint8_t *valid = (uint8_t *)calloc((size_t)((n + 7) / 8) + 1, 1);
-  if (!v || !valid) { free(v); free(valid); return set_error(PBGPU_ENOMEM, "host allocation failed"); }
+  int64_t *v = (int64_t *)hmalloc(8 * (size_t)(n ? n : 1));
+  uint8_t *valid = (uint8_t *)hcalloc((size_t)((n + 7) / 8) + 1);
+  if (!v || !valid) { hfree(v); hfree(valid); return set_error(PBGPU_ENOMEM, "host allocation failed"); }
   o->bufs.push_back(valid);
   o->bufs.push_back(v);
   int64_t nulls = 0;
@@ -737,9 +792,9 @@ int nullable_i64_column(const int64_t *src, int64_t n, ArrowArray *out) {
 
 int nullable_u32_column(const uint32_t *src, int64_t n, ArrowArray *out) {
   std::unique_ptr<OwnedArray> o(new OwnedArray());
-  uint32_t *v = (uint32_t *)malloc(4 * (size_t)(n ? n : 1));
-  uint8_t *valid = (uint8_t *)calloc((size_t)((n + 7) / 8) + 1, 1);
-  if (!v || !valid) { free(v); free(valid); return set_error(PBGPU_ENOMEM, "host allocation failed"); }
+  uint32_t *v = (uint32_t *)hmalloc(4 * (size_t)(n ? n : 1));
+  uint8_t *valid = (uint8_t *)hcalloc((size_t)((n + 7) / 8) + 1);
+  if (!v || !valid) { hfree(v); hfree(valid); return set_error(PBGPU_ENOMEM, "host allocation failed"); }
   o->bufs.push_back(valid);
   o->bufs.push_back(v);
   int64_t nulls = 0;
