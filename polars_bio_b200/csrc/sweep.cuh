@@ -201,6 +201,28 @@ __device__ __forceinline__ uint32_t fast_count(const IndexView &ix, int32_t c, i
   return hi - re;
 }
 
+// Candidate window [lo,hi) and end-rank `lend` of one probe via the rank directories (nearest / coverage).
+// hi and lend are global positions == positions in the start-ordered / end-ordered arrays.  The window start is
+// hi-cnt when nothing below it reaches past the probe start (no nested intervals there: one load), else a search
+// over the running max inside the contig segment.  Returns false when the probe must take the generic path.
+template <bool STRICT>
+__device__ __forceinline__ bool fast_window(const IndexView &ix, int32_t c, int32_t s, int32_t e, int32_t seg_lo,
+                                            int32_t &lo, int32_t &hi, int32_t &lend) {
+  if (!ix.dir_s || !(STRICT ? (s < e) : (s <= e))) return false;
+  const ContigMap cm = ix.cmap[c];
+  long long ls = s, le = e;
+  ls = ls < cm.lo_m1 ? cm.lo_m1 : (ls > cm.hi_p1 ? cm.hi_p1 : ls);
+  le = le < cm.lo_m1 ? cm.lo_m1 : (le > cm.hi_p1 ? cm.hi_p1 : le);
+  const uint32_t g_s = cm.off + (uint32_t)(ls - cm.lo_m1), g_e = cm.off + (uint32_t)(le - cm.lo_m1);
+  hi = (int32_t)(STRICT ? dir_rank<false>(ix.dir_s, ix.gs, ix.shift, g_e) : dir_rank<true>(ix.dir_s, ix.gs, ix.shift, g_e));
+  lend = (int32_t)(STRICT ? dir_rank<true>(ix.dir_e, ix.ge, ix.shift, g_s) : dir_rank<false>(ix.dir_e, ix.ge, ix.shift, g_s));
+  const int32_t p = lend;  // = hi - cnt
+  if (p >= hi) { lo = hi; return true; }
+  if (p <= seg_lo || !end_hits<STRICT>(__ldg(ix.pmax + p - 1), s)) lo = p;
+  else lo = STRICT ? upper_bound_i32(ix.pmax, seg_lo, p, s) : lower_bound_i32(ix.pmax, seg_lo, p, s);
+  return true;
+}
+
 template <bool STRICT>
 __global__ void __launch_bounds__(kSweepThreads) count_overlaps_fast_kernel(IndexView ix, const int32_t *__restrict__ pc,
                                                                             const int32_t *__restrict__ ps,
@@ -320,8 +342,10 @@ __global__ void __launch_bounds__(kSweepThreads) coverage_kernel(IndexView ix, c
   long long total = 0;
   if (c >= 0 && c < ix.n_contigs) {
     const int32_t s = ps[i], e = pe[i];
-    int32_t lo, hi;
-    probe_window<STRICT>(ix, ix.seg[c], ix.seg[c + 1], s, e, lo, hi);
+    int32_t lo, hi, lend;
+    const int32_t seg_lo = ix.seg[c], seg_hi = ix.seg[c + 1];
+    if (seg_lo >= seg_hi) { cov[i] = 0; return; }
+    if (!fast_window<STRICT>(ix, c, s, e, seg_lo, lo, hi, lend)) probe_window<STRICT>(ix, seg_lo, seg_hi, s, e, lo, hi);
     long long cs = 0, ce = 0;
     bool open = false;
     for (int32_t j = lo; j < hi; ++j) {  // hits arrive start-sorted: merge clipped pieces on the fly
@@ -368,8 +392,11 @@ __global__ void __launch_bounds__(kSweepThreads) nearest_kernel(IndexView ix, co
   const int32_t seg_lo = ix.seg[c], seg_hi = ix.seg[c + 1];
   if (seg_lo >= seg_hi) return;
   const int32_t qs = ps[i], qe = pe[i];
-  int32_t lo, hi;
-  probe_window<STRICT>(ix, seg_lo, seg_hi, qs, qe, lo, hi);
+  int32_t lo, hi, lend;
+  if (!fast_window<STRICT>(ix, c, qs, qe, seg_lo, lo, hi, lend)) {
+    probe_window<STRICT>(ix, seg_lo, seg_hi, qs, qe, lo, hi);
+    lend = STRICT ? upper_bound_i32(ix.en_sorted, seg_lo, seg_hi, qs) : lower_bound_i32(ix.en_sorted, seg_lo, seg_hi, qs);
+  }
   int64_t got = 0;
   if (include_overlaps) {
     for (int32_t j = lo; j < hi && got < k; ++j) {
@@ -378,8 +405,6 @@ __global__ void __launch_bounds__(kSweepThreads) nearest_kernel(IndexView ix, co
   }
   if (got >= k) return;
   int32_t rp = hi;  // downstream cursor: first start past the probe end
-  const int32_t lend = STRICT ? upper_bound_i32(ix.en_sorted, seg_lo, seg_hi, qs)
-                              : lower_bound_i32(ix.en_sorted, seg_lo, seg_hi, qs);
   int32_t lg_hi = lend, lg_lo = lend, lcur = lend;  // current equal-end group [lg_lo,lg_hi), cursor lcur
   for (;;) {
     bool have_l = false, have_r = false;
@@ -390,7 +415,12 @@ __global__ void __launch_bounds__(kSweepThreads) nearest_kernel(IndexView ix, co
         if (lg_lo <= seg_lo) break;
         lg_hi = lg_lo;
         const int32_t v = __ldg(ix.en_sorted + lg_hi - 1);
-        lg_lo = lower_bound_i32(ix.en_sorted, seg_lo, lg_hi, v);
+        int32_t g = lg_hi - 1;  // start of the equal-end group: groups are tiny, walk back before searching
+        for (int st = 0; g > seg_lo && __ldg(ix.en_sorted + g - 1) == v; ) {
+          --g;
+          if (++st == 8) { g = lower_bound_i32(ix.en_sorted, seg_lo, g, v); break; }
+        }
+        lg_lo = g;
         lcur = lg_lo;
       }
       lpos = (int32_t)__ldg(ix.en_pos + lcur);
