@@ -192,13 +192,10 @@ def run_sharded(args, world, rank, dev):
     FO = engine.FILTER_STRICT
     nc = world
 
-    def step(ev=None):
-        hist = pbd.contig_histogram(dp[0], nc) + pbd.contig_histogram(db[0], nc)
-        owner = pbd.owner_table(hist, world)
-        pbase, _ = pbd.row_id_base(n, dev)
-        bbase, _ = pbd.row_id_base(m, dev)
-        qc, qs, qe, qrow = pbd.shard_table(*dp, nc, owner, pbase)
-        xc, xs, xe, xrow = pbd.shard_table(*db, nc, owner, bbase)
+    def step(ev=None, trace=None):
+        (q, x), owner = pbd.shard_tables([tuple(dp), tuple(db)], nc, trace=trace)
+        qc, qs, qe, qrow = q
+        xc, xs, xe, xrow = x
         if ev: ev[1].record()
         ix = engine.DeviceIndex(xc, xs, xe, nc)
         cnt = ix.count_overlaps(qc, qs, qe, FO)
@@ -227,6 +224,8 @@ def run_sharded(args, world, rank, dev):
         del cnt, a, b
     launches = _native.launch_count() - launches0
     km = _native.stage_times()
+    xtrace = []
+    step(trace=xtrace)  # one extra, untimed step with host-side laps of the exchange
     dist.barrier(); torch.cuda.synchronize()
     clocks = sampler.stop()
     t = torch.tensor([float(np.sum(step_ms)), float(np.sum(xchg_ms))], device=dev, dtype=torch.float64)
@@ -247,6 +246,7 @@ def run_sharded(args, world, rank, dev):
                    "pairs_per_step": pairs_all, "l2": "flushed between timed steps (256 MiB write)",
                    "parallelism": f"contig-sharded x{world}, NCCL all-to-all of 16-byte records",
                    "exchange_ms_per_step": float(t[1].item()) / args.steps,
+                   "exchange_host_laps_ms": {k: round(v * 1e3, 3) for k, v in xtrace},
                    "exchange_bytes_per_gpu": 16 * (n + m)},
         "clocks": clocks,
         "e2e": None,

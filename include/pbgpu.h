@@ -130,6 +130,14 @@ PBGPU_API int pbgpu_pack_by_owner(const int32_t *d_contig, const int32_t *d_star
                                   uint32_t row_id_base, int32_t *d_packed, int64_t *d_rank_counts,
                                   void *stream);
 
+/* d_out[i] = d_src[d_rows[i]] (0 where d_rows[i] == PBGPU_NO_PARTNER): materialises the key columns
+ * (contig code, start, end) of result rows on the device, where they already live, so the host does not have
+ * to gather them from the input tables (the first step of payload materialisation).   */
+PBGPU_API int pbgpu_gather_i32(const int32_t *d_src, const uint32_t *d_rows, int64_t n, int32_t *d_out, void *stream);
+/* Rows per contig, ADDED onto d_hist (int64[n_contigs]; zero it first); null keys are ignored.  Feeds the
+ * owner table (LPT bin packing) of the multi-GPU exchange.                                               */
+PBGPU_API int pbgpu_contig_histogram(const int32_t *d_contig, int64_t n, int32_t n_contigs, int64_t *d_hist,
+                                     void *stream);
 /* After the all-to-all: split received 16-byte records back into columns (d_row = global row ids).     */
 PBGPU_API int pbgpu_unpack_records(const int32_t *d_packed, int64_t n, int32_t *d_contig, int32_t *d_start,
                                    int32_t *d_end, uint32_t *d_row, void *stream);

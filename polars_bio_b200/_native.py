@@ -83,6 +83,8 @@ def lib() -> ctypes.CDLL:
     L.pbgpu_overlap_plan_free.restype = None
     L.pbgpu_nearest.argtypes = [vp, vp, vp, vp, i64, ctypes.c_int, i64, ctypes.c_int, vp, vp, vp]
     L.pbgpu_pack_by_owner.argtypes = [vp, vp, vp, i64, vp, i32, i32, u32, vp, vp, vp]
+    L.pbgpu_gather_i32.argtypes = [vp, vp, i64, vp, vp]
+    L.pbgpu_contig_histogram.argtypes = [vp, i64, i32, vp, vp]
     L.pbgpu_unpack_records.argtypes = [vp, i64, vp, vp, vp, vp, vp]
     L.pbgpu_translate_rows.argtypes = [vp, i64, vp, vp, vp]
     L.pbgpu_last_stage_times.argtypes = [ctypes.POINTER(StageTimes)]

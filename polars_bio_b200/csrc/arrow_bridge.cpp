@@ -856,6 +856,86 @@ ArrowSchema copy_schema(const ArrowSchema *f, const std::string &name) {
   return s;
 }
 
+// ---- key columns rebuilt from device-gathered int32 values ----------------------------------------------
+// position column: the input dtype is preserved (Int32 in -> Int32 out, docs/supplement.md:328-333); result rows
+// never carry null keys, so no validity bitmap
+int pos_column(const std::shared_ptr<void> &keep, const int32_t *src, int64_t n, const char *fmt, ArrowArray *out) {
+  const char f = fmt[0];
+  if (f == 'i' || f == 'I') { *out = view_buffer(keep, src, n); return PBGPU_OK; }  // same 4-byte pattern (values >= 0 for 'I')
+  const int w = fixed_width(fmt);
+  std::unique_ptr<OwnedArray> o(new OwnedArray());
+  uint8_t *v = (uint8_t *)hmalloc((size_t)n * w + 1);
+  if (!v) return set_error(PBGPU_ENOMEM, "host allocation failed");
+  o->bufs.push_back(v);
+  const int64_t nch = (n + kGatherChunk - 1) / kGatherChunk;
+  Pool::get().parallel_for(nch, [&](int64_t ci) {
+    const int64_t lo = ci * kGatherChunk, hi = std::min(n, lo + kGatherChunk);
+    switch (f) {
+      case 'l': case 'L': for (int64_t i = lo; i < hi; ++i) ((int64_t *)v)[i] = src[i]; break;
+      case 's': case 'S': for (int64_t i = lo; i < hi; ++i) ((int16_t *)v)[i] = (int16_t)src[i]; break;
+      default: for (int64_t i = lo; i < hi; ++i) ((int8_t *)v)[i] = (int8_t)src[i]; break;
+    }
+  });
+  o->bptr = {nullptr, v};
+  *out = finish_array(o.release(), n, 0);
+  return PBGPU_OK;
+}
+
+// contig column from dictionary codes: offsets + data filled sequentially (no random reads of the source table);
+// the buffers are shared by the left and right contig columns of a join batch (equal by the join condition)
+struct StrBufs { std::shared_ptr<HostBufs> keep; void *offs = nullptr; char *data = nullptr; bool large = false; };
+int contig_buffers(const int32_t *codes, int64_t n, const std::vector<std::string> &names, bool large, StrBufs *sb) {
+  sb->keep = std::make_shared<HostBufs>();
+  sb->large = large;
+  const int64_t nch = (n + kGatherChunk - 1) / kGatherChunk;
+  std::vector<int64_t> bytes((size_t)std::max<int64_t>(nch, 1), 0), off((size_t)std::max<int64_t>(nch, 1), 0);
+  std::vector<uint32_t> len(names.size());
+  for (size_t k = 0; k < names.size(); ++k) len[k] = (uint32_t)names[k].size();
+  Pool::get().parallel_for(nch, [&](int64_t ci) {
+    const int64_t lo = ci * kGatherChunk, hi = std::min(n, lo + kGatherChunk);
+    int64_t b = 0;
+    for (int64_t i = lo; i < hi; ++i) b += len[codes[i]];
+    bytes[ci] = b;
+  });
+  int64_t total = 0;
+  for (int64_t ci = 0; ci < nch; ++ci) { off[ci] = total; total += bytes[ci]; }
+  if (!large && total > INT32_MAX) return set_error(PBGPU_ERANGE, "utf8 contig column would exceed 2 GiB in one output batch; lower max_batch_rows");
+  sb->offs = hmalloc((size_t)(n + 1) * (large ? 8 : 4));
+  sb->data = (char *)hmalloc((size_t)total + 16);
+  if (!sb->offs || !sb->data) { hfree(sb->offs); hfree(sb->data); return set_error(PBGPU_ENOMEM, "host allocation failed"); }
+  sb->keep->v.push_back(sb->offs);
+  sb->keep->v.push_back(sb->data);
+  Pool::get().parallel_for(nch, [&](int64_t ci) {
+    const int64_t lo = ci * kGatherChunk, hi = std::min(n, lo + kGatherChunk);
+    int64_t pos = off[ci];
+    for (int64_t i = lo; i < hi; ++i) {
+      if (large) ((int64_t *)sb->offs)[i] = pos; else ((int32_t *)sb->offs)[i] = (int32_t)pos;
+      const std::string &nm = names[codes[i]];
+      memcpy(sb->data + pos, nm.data(), nm.size());
+      pos += (int64_t)nm.size();
+    }
+  });
+  if (large) ((int64_t *)sb->offs)[n] = total; else ((int32_t *)sb->offs)[n] = (int32_t)total;
+  return PBGPU_OK;
+}
+struct StrViewPriv { std::shared_ptr<HostBufs> keep; const void *bufs[3]; };
+void release_str_view(ArrowArray *a) {
+  if (!a || !a->release) return;
+  delete (StrViewPriv *)a->private_data;
+  a->release = nullptr;
+}
+ArrowArray str_view(const StrBufs &sb, int64_t n) {
+  StrViewPriv *p = new StrViewPriv{sb.keep, {nullptr, sb.offs, sb.data}};
+  ArrowArray v{};
+  v.length = n;
+  v.null_count = 0;
+  v.n_buffers = 3;
+  v.buffers = p->bufs;
+  v.release = release_str_view;
+  v.private_data = p;
+  return v;
+}
+
 // ---- the output stream ---------------------------------------------------------------------------
 struct OutStream {
   std::shared_ptr<Table> left, right;  // shared with zero-copy output views of their columns
@@ -868,6 +948,9 @@ struct OutStream {
   const int64_t *extra = nullptr;  // count / coverage / distance (distance < 0 = null)
   std::vector<uint32_t> own_l, own_r;  // host-built row lists (nearest expansion, distinct)
   std::vector<int64_t> own_x;
+  // overlap, materialised: key columns of the result rows gathered on the device (NULL = not available)
+  const int32_t *k_code = nullptr, *k_ls = nullptr, *k_le = nullptr, *k_rs = nullptr, *k_re = nullptr;
+  std::vector<std::string> contig_names;  // dictionary: code -> contig string
   int64_t cursor = 0;
   int view_batch = 0;        // pass-through modes: input batch being re-exported
   int64_t view_off = 0;      //   and the offset inside it
@@ -949,6 +1032,36 @@ int out_get_next(ArrowArrayStream *s, ArrowArray *out) {
       else { ArrowArray b{}; rc = plain_column<uint32_t>(st->rrow + lo, n, nullptr, &b); if (rc == PBGPU_OK) push(std::move(b)); }
     }
     if (rc == PBGPU_OK && want_distance(o)) { ArrowArray d{}; rc = nullable_i64_column(st->extra + lo, n, &d); if (rc == PBGPU_OK) push(std::move(d)); }
+  } else if (o.range_op == PBGPU_OP_OVERLAP && st->k_code) {
+    // key columns come from the device-gathered int32 arrays; only true payload columns are gathered on the host
+    struct Slot { int kind; const Table *t; int col; const int32_t *pos; const uint32_t *rows; };  // 0 contig, 1 position, 2 payload
+    std::vector<Slot> slots;
+    auto plan_table = [&](const Table &t, const uint32_t *rows, const int32_t *ks, const int32_t *ke) {
+      for (int c = 0; c < (int)t.n_cols(); ++c) {
+        if (c == t.key[0]) slots.push_back({0, &t, c, nullptr, nullptr});
+        else if (c == t.key[1]) slots.push_back({1, &t, c, ks + lo, nullptr});
+        else if (c == t.key[2]) slots.push_back({1, &t, c, ke + lo, nullptr});
+        else { slots.push_back({2, &t, c, nullptr, rows + lo}); jobs.push_back(GatherJob{&t, c, rows + lo}); }
+      }
+    };
+    plan_table(*st->left, st->lrow, st->k_ls, st->k_le);
+    if (o.output_mode == PBGPU_OUT_JOIN) plan_table(*st->right, st->rrow, st->k_rs, st->k_re);
+    std::vector<ArrowArray> payload;
+    if (!jobs.empty()) rc = gather_columns(jobs, n, &payload);
+    StrBufs sb_small, sb_large;
+    size_t next_payload = 0;
+    for (size_t k = 0; k < slots.size() && rc == PBGPU_OK; ++k) {
+      const Slot &sl = slots[k];
+      const ArrowSchema *f = sl.t->schema.children[sl.col];
+      if (sl.kind == 2) { push(std::move(payload[next_payload++])); continue; }
+      if (sl.kind == 1) { ArrowArray a{}; rc = pos_column(keep, sl.pos, n, f->format, &a); if (rc == PBGPU_OK) push(std::move(a)); continue; }
+      bool ok;
+      const bool large = out_format(f, &ok)[0] == 'U';
+      StrBufs &sb = large ? sb_large : sb_small;
+      if (!sb.keep) rc = contig_buffers(st->k_code + lo, n, st->contig_names, large, &sb);
+      if (rc == PBGPU_OK) push(str_view(sb, n));
+    }
+    for (; next_payload < payload.size(); ++next_payload) if (payload[next_payload].release) payload[next_payload].release(&payload[next_payload]);
   } else if (o.range_op == PBGPU_OP_OVERLAP) {
     add_table(*st->left, st->lrow);
     if (o.output_mode == PBGPU_OUT_JOIN) add_table(*st->right, st->rrow);
@@ -1100,15 +1213,40 @@ int run(Table *L, Table *R, OutStream *os) {
     BR_TRY(pbgpu_overlap_count(ix, dc_i, ds_i, de_i, n, o.filter_op, s, &plan, &total));
     struct PlanGuard { pbgpu_overlap_plan *p; ~PlanGuard() { pbgpu_overlap_plan_free(p); } } pg{plan};
     uint32_t *d_p = dev.get<uint32_t>((size_t)total), *d_b = dev.get<uint32_t>((size_t)total);
-    uint32_t *h_p = stage.get<uint32_t>((size_t)total), *h_b = stage.get<uint32_t>((size_t)total);
-    if (!d_p || !d_b || !h_p || !h_b) return set_error(PBGPU_ENOMEM, "allocation failed for %lld pairs", (long long)total);
+    if (!d_p || !d_b) return set_error(PBGPU_ENOMEM, "device allocation failed for %lld pairs", (long long)total);
     BR_TRY(pbgpu_overlap_emit(plan, d_p, d_b, s));
-    BR_CUDA(cudaMemcpyAsync(h_p, d_p, 4 * (size_t)total, cudaMemcpyDeviceToHost, s));
-    BR_CUDA(cudaMemcpyAsync(h_b, d_b, 4 * (size_t)total, cudaMemcpyDeviceToHost, s));
-    BR_CUDA(cudaStreamSynchronize(s));
-    os->lrow = (const uint32_t *)copy_out(*os->pins, h_p, 4 * (size_t)total);
-    os->rrow = (const uint32_t *)copy_out(*os->pins, h_b, 4 * (size_t)total);
-    if (!os->lrow || !os->rrow) return set_error(PBGPU_ENOMEM, "host allocation failed");
+    const bool join = o.output_mode == PBGPU_OUT_JOIN;
+    auto has_payload = [](const Table &t) { for (int c = 0; c < (int)t.n_cols(); ++c) if (c != t.key[0] && c != t.key[1] && c != t.key[2]) return true; return false; };
+    const bool mat = o.emit == 0;
+    const bool need_l = !mat || has_payload(*L), need_r = !mat || (join && has_payload(*R));
+    // D2H of one uint32/int32 result array through a pinned landing buffer into cached host memory
+    auto fetch = [&](const void *d_src, const void **dst) -> int {
+      void *h = stage.get<uint32_t>((size_t)total);
+      if (!h) return set_error(PBGPU_ENOMEM, "pinned allocation failed");
+      BR_CUDA(cudaMemcpyAsync(h, d_src, 4 * (size_t)total, cudaMemcpyDeviceToHost, s));
+      BR_CUDA(cudaStreamSynchronize(s));
+      *dst = copy_out(*os->pins, h, 4 * (size_t)total);
+      pinned_put(h);
+      stage.v.erase(std::find(stage.v.begin(), stage.v.end(), h));
+      return *dst ? PBGPU_OK : set_error(PBGPU_ENOMEM, "host allocation failed");
+    };
+    if (mat) {  // key columns of the result rows: gathered where they already live
+      int32_t *d_k = dev.get<int32_t>((size_t)total);
+      if (!d_k) return set_error(PBGPU_ENOMEM, "device allocation failed");
+      struct G { const int32_t *src; const uint32_t *rows; const int32_t **dst; bool on; };
+      const G gs[5] = {{dc_i, d_p, &os->k_code, true}, {ds_i, d_p, &os->k_ls, true}, {de_i, d_p, &os->k_le, true},
+                       {ds_x, d_b, &os->k_rs, join}, {de_x, d_b, &os->k_re, join}};
+      for (const G &g : gs) {
+        if (!g.on) continue;
+        BR_TRY(pbgpu_gather_i32(g.src, g.rows, total, d_k, s));
+        BR_TRY(fetch(d_k, (const void **)g.dst));
+      }
+      os->contig_names.resize(dict.map.size());
+      for (auto &kv : dict.map) os->contig_names[(size_t)kv.second] = kv.first;
+    }
+    if (need_l) BR_TRY(fetch(d_p, (const void **)&os->lrow));
+    if (need_r) BR_TRY(fetch(d_b, (const void **)&os->rrow));
+    if (!os->rrow) os->rrow = os->lrow;  // never dereferenced in this case; keeps emit=1 paths well defined
     os->n_out = total;
   } else if (o.range_op == PBGPU_OP_NEAREST) {
     const int64_t k = o.nearest_k ? (int64_t)o.nearest_k : 1;

@@ -486,6 +486,54 @@ __global__ void __launch_bounds__(256) translate_rows_kernel(const uint32_t *__r
 }
 }  // namespace pbgpu
 
+namespace pbgpu {
+// rows per contig (null keys ignored), added onto hist: block-private shared-memory bins, one flush per block
+__global__ void __launch_bounds__(256) contig_hist_kernel(const int32_t *__restrict__ c, int64_t n, int32_t n_contigs,
+                                                          unsigned long long *__restrict__ hist) {
+  extern __shared__ unsigned int bins[];
+  const bool use_smem = n_contigs <= 4096;
+  if (use_smem) { for (int i = threadIdx.x; i < n_contigs; i += blockDim.x) bins[i] = 0; __syncthreads(); }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t cc = c[i];
+    if (cc < 0 || cc >= n_contigs) continue;
+    if (use_smem) atomicAdd(&bins[cc], 1u); else atomicAdd(hist + cc, 1ull);
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_contigs; i += blockDim.x) if (bins[i]) atomicAdd(hist + i, (unsigned long long)bins[i]);
+  }
+}
+}  // namespace pbgpu
+
+namespace pbgpu {
+__global__ void __launch_bounds__(256) gather_i32_kernel(const int32_t *__restrict__ src, const uint32_t *__restrict__ rows, int64_t n,
+                                                         int32_t *__restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const uint32_t r = rows[i]; out[i] = r == PBGPU_NO_PARTNER ? 0 : __ldg(src + r); }
+}
+}  // namespace pbgpu
+
+extern "C" int pbgpu_gather_i32(const int32_t *d_src, const uint32_t *d_rows, int64_t n, int32_t *d_out, void *stream) {
+  if (n < 0) return set_error(PBGPU_EINVAL, "negative n");
+  if (n == 0) return PBGPU_OK;
+  if (!d_src || !d_rows || !d_out) return set_error(PBGPU_EINVAL, "NULL argument");
+  PB_LAUNCH(gather_i32_kernel, (unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream, d_src, d_rows, n, d_out);
+  PB_CHECK_LAUNCH();
+  return PBGPU_OK;
+}
+
+extern "C" int pbgpu_contig_histogram(const int32_t *d_contig, int64_t n, int32_t n_contigs, int64_t *d_hist, void *stream) {
+  if (n < 0 || n_contigs < 0) return set_error(PBGPU_EINVAL, "negative size");
+  if (n == 0 || n_contigs == 0) return PBGPU_OK;
+  if (!d_contig || !d_hist) return set_error(PBGPU_EINVAL, "NULL argument");
+  int64_t grid = cdiv(n, 256 * 16);
+  if (grid > kSMs * 8) grid = kSMs * 8;
+  const size_t smem = n_contigs <= 4096 ? sizeof(unsigned int) * (size_t)n_contigs : 0;
+  PB_LAUNCH(contig_hist_kernel, (unsigned)grid, 256, smem, (cudaStream_t)stream, d_contig, n, n_contigs, (unsigned long long *)d_hist);
+  PB_CHECK_LAUNCH();
+  return PBGPU_OK;
+}
+
 extern "C" int pbgpu_unpack_records(const int32_t *d_packed, int64_t n, int32_t *d_contig, int32_t *d_start, int32_t *d_end,
                                     uint32_t *d_row, void *stream) {
   if (n < 0) return set_error(PBGPU_EINVAL, "negative n");

@@ -98,6 +98,76 @@ def shard_table(contig: torch.Tensor, start: torch.Tensor, end: torch.Tensor, n_
     return c2, s2, e2, row2
 
 
+def shard_tables(tables, n_contigs: int, group=None, trace: Optional[list] = None):
+    """Exchange several tables at once (typically the probe and the build side) with as few host round trips as
+    possible: ONE all_reduce (per-contig histogram of all tables + slice sizes), ONE count all-to-all, one payload
+    all-to-all per table.  ``tables``: list of (contig, start, end) int32 CUDA columns (this rank's slices).
+    Returns (list of (contig, start, end, global_row) owned columns, owner table)."""
+    import ctypes
+    import time
+
+    from . import _native
+    from .engine import _stream_ptr
+
+    L = _native.lib()
+    dev = tables[0][0].device
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    T = len(tables)
+    t0 = time.perf_counter()
+    with torch.cuda.device(dev):
+        sp = _stream_ptr(dev)
+        # [hist (n_contigs) | slice sizes (T x world)] -> one all_reduce
+        meta = torch.zeros(n_contigs + T * world, dtype=torch.int64, device=dev)
+        for t, (c, _, _) in enumerate(tables):
+            _native.check(L.pbgpu_contig_histogram(c.data_ptr(), c.numel(), n_contigs, meta.data_ptr(), sp))
+            meta[n_contigs + t * world + rank] = c.numel()
+        if world > 1:
+            dist.all_reduce(meta, group=group)
+        meta_h = meta.cpu()
+        owner = owner_table(meta_h[:n_contigs], world)
+        sizes = meta_h[n_contigs:].view(T, world)
+        bases = [int(sizes[t, :rank].sum()) for t in range(T)]
+        owner_d = owner.to(dev, non_blocking=True)
+        if trace is not None: trace.append(("histogram+owner", time.perf_counter() - t0)); t0 = time.perf_counter()
+        packed, counts = [], torch.empty((T, world), dtype=torch.int64, device=dev)
+        for t, (c, s, e) in enumerate(tables):
+            n = c.numel()
+            pk = torch.empty((max(n, 1), 4), dtype=torch.int32, device=dev)
+            _native.check(L.pbgpu_pack_by_owner(c.data_ptr(), s.data_ptr(), e.data_ptr(), n, owner_d.data_ptr(), n_contigs, world,
+                                                ctypes.c_uint32(bases[t]), pk.data_ptr(), counts[t].data_ptr(), sp))
+            packed.append(pk)
+        if world > 1:
+            recv_counts = torch.empty_like(counts)
+            # counts[t, r] -> rank r ; as one all-to-all over the transposed [world, T] layout
+            send_t = counts.t().contiguous()
+            recv_t = torch.empty_like(send_t)
+            dist.all_to_all_single(recv_t, send_t, group=group)
+            both = torch.stack([send_t, recv_t]).cpu()  # one D2H
+            send_l, recv_l = both[0].t().tolist(), both[1].t().tolist()  # [T][world]
+        else:
+            send_l = counts.cpu().tolist()
+            recv_l = send_l
+        if trace is not None: trace.append(("pack+counts", time.perf_counter() - t0)); t0 = time.perf_counter()
+        out = []
+        for t in range(T):
+            kept, r = int(sum(send_l[t])), int(sum(recv_l[t]))
+            if world > 1:
+                recv = torch.empty((max(r, 1), 4), dtype=torch.int32, device=dev)
+                dist.all_to_all_single(recv[:r], packed[t][:kept], output_split_sizes=[int(x) for x in recv_l[t]],
+                                       input_split_sizes=[int(x) for x in send_l[t]], group=group)
+            else:
+                recv = packed[t]
+            c2 = torch.empty(r, dtype=torch.int32, device=dev); s2 = torch.empty_like(c2); e2 = torch.empty_like(c2)
+            row2 = torch.empty_like(c2)
+            _native.check(L.pbgpu_unpack_records(recv.data_ptr(), r, c2.data_ptr(), s2.data_ptr(), e2.data_ptr(), row2.data_ptr(), sp))
+            out.append((c2, s2, e2, row2))
+        if trace is not None:
+            torch.cuda.synchronize(dev)
+            trace.append(("all-to-all+unpack", time.perf_counter() - t0))
+    return out, owner
+
+
 def translate(local_rows: torch.Tensor, global_of_local: torch.Tensor) -> torch.Tensor:
     """Pair buffer positions -> global row ids (in place)."""
     from . import _native

@@ -29,13 +29,22 @@ def main():
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     lp = [t(sl(x, N)) for x in (pc, ps, pe)]
     lb = [t(sl(x, M)) for x in (bc, bs, be)]
+    # path 1: table-at-a-time primitives
     hist = pbd.contig_histogram(lp[0], n_contigs) + pbd.contig_histogram(lb[0], n_contigs)
     owner = pbd.owner_table(hist, world)
     pbase, ptotal = pbd.row_id_base(lp[0].numel(), dev)
     bbase, btotal = pbd.row_id_base(lb[0].numel(), dev)
     assert ptotal == N and btotal == M
-    qc, qs, qe, qrow = pbd.shard_table(*lp, n_contigs, owner, pbase)
-    xc, xs, xe, xrow = pbd.shard_table(*lb, n_contigs, owner, bbase)
+    q1 = pbd.shard_table(*lp, n_contigs, owner, pbase)
+    x1 = pbd.shard_table(*lb, n_contigs, owner, bbase)
+    # path 2: the fused exchange (one all_reduce, one count all-to-all) must deliver the same rows
+    (q2, x2), owner2 = pbd.shard_tables([tuple(lp), tuple(lb)], n_contigs)
+    assert torch.equal(owner, owner2)
+    for u, v in ((q1, q2), (x1, x2)):
+        for col_u, col_v in zip(u, v):
+            assert torch.equal(col_u, col_v)
+    qc, qs, qe, qrow = q2
+    xc, xs, xe, xrow = x2
     ix = engine.DeviceIndex(xc, xs, xe, n_contigs)
     a, b = ix.overlap_pairs(qc, qs, qe, engine.FILTER_STRICT)
     cnt = ix.count_overlaps(qc, qs, qe, engine.FILTER_STRICT)
