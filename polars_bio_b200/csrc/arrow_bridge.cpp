@@ -34,9 +34,12 @@
 #include "../../include/pbgpu.h"
 #include "arrow_c_abi.h"
 
+struct pbgpu_index;
 namespace pbgpu {
 int set_error(int code, const char *fmt, ...);
 extern thread_local char g_err[512];
+int count_overlaps_u32(const pbgpu_index *ix, const int32_t *c, const int32_t *s, const int32_t *e, int64_t n, int filter_op,
+                       uint32_t *d_counts, void *stream);  // pbgpu.cu (internal)
 }  // namespace pbgpu
 using pbgpu::set_error;
 
@@ -1186,14 +1189,32 @@ int run(Table *L, Table *R, OutStream *os) {
   const uint64_t limit = o.limit;
 
   if (o.range_op == PBGPU_OP_COUNT_OVERLAPS_NAIVE || o.range_op == PBGPU_OP_COVERAGE) {
-    int64_t *d_out = dev.get<int64_t>(n);
-    int64_t *h_out = stage.get<int64_t>(n);
-    if (!d_out || !h_out) return set_error(PBGPU_ENOMEM, "allocation failed");
-    if (o.range_op == PBGPU_OP_COVERAGE) BR_TRY(pbgpu_coverage(ix, dc_i, ds_i, de_i, n, o.filter_op, d_out, s));
-    else BR_TRY(pbgpu_count_overlaps(ix, dc_i, ds_i, de_i, n, o.filter_op, d_out, s));
-    BR_CUDA(cudaMemcpyAsync(h_out, d_out, 8 * (size_t)n, cudaMemcpyDeviceToHost, s));
-    BR_CUDA(cudaStreamSynchronize(s));
-    os->extra = (const int64_t *)copy_out(*os->pins, h_out, 8 * (size_t)n);
+    if (o.range_op == PBGPU_OP_COVERAGE) {
+      int64_t *d_out = dev.get<int64_t>(n);
+      int64_t *h_out = stage.get<int64_t>(n);
+      if (!d_out || !h_out) return set_error(PBGPU_ENOMEM, "allocation failed");
+      BR_TRY(pbgpu_coverage(ix, dc_i, ds_i, de_i, n, o.filter_op, d_out, s));
+      BR_CUDA(cudaMemcpyAsync(h_out, d_out, 8 * (size_t)n, cudaMemcpyDeviceToHost, s));
+      BR_CUDA(cudaStreamSynchronize(s));
+      os->extra = (const int64_t *)copy_out(*os->pins, h_out, 8 * (size_t)n);
+    } else {  // counts fit 32 bits (< 2^31 indexed rows): half the D2H bytes, widened to the Int64 column on the host
+      uint32_t *d_out = dev.get<uint32_t>(n);
+      uint32_t *h_out = stage.get<uint32_t>(n);
+      if (!d_out || !h_out) return set_error(PBGPU_ENOMEM, "allocation failed");
+      BR_TRY(pbgpu::count_overlaps_u32(ix, dc_i, ds_i, de_i, n, o.filter_op, d_out, s));
+      BR_CUDA(cudaMemcpyAsync(h_out, d_out, 4 * (size_t)n, cudaMemcpyDeviceToHost, s));
+      BR_CUDA(cudaStreamSynchronize(s));
+      int64_t *wide = (int64_t *)hmalloc(8 * (size_t)(n ? n : 1));
+      if (wide) {
+        os->pins->v.push_back(wide);
+        const int64_t nch = (n + kGatherChunk - 1) / kGatherChunk;
+        Pool::get().parallel_for(nch, [&](int64_t ci) {
+          const int64_t lo = ci * kGatherChunk, hi = std::min(n, lo + kGatherChunk);
+          for (int64_t i = lo; i < hi; ++i) wide[i] = (int64_t)h_out[i];
+        });
+      }
+      os->extra = wide;
+    }
     if (!os->extra) return set_error(PBGPU_ENOMEM, "host allocation failed");
     os->n_out = n;
   } else if (o.range_op == PBGPU_OP_OVERLAP && o.output_mode == PBGPU_OUT_LEFT_DISTINCT) {
@@ -1219,33 +1240,38 @@ int run(Table *L, Table *R, OutStream *os) {
     auto has_payload = [](const Table &t) { for (int c = 0; c < (int)t.n_cols(); ++c) if (c != t.key[0] && c != t.key[1] && c != t.key[2]) return true; return false; };
     const bool mat = o.emit == 0;
     const bool need_l = !mat || has_payload(*L), need_r = !mat || (join && has_payload(*R));
-    // D2H of one uint32/int32 result array through a pinned landing buffer into cached host memory
-    auto fetch = [&](const void *d_src, const void **dst) -> int {
+    // all result arrays: device gathers + D2H enqueued back to back, ONE stream sync, then parallel copies out of the
+    // pinned landing buffers into cached host memory
+    struct Fetch { const void *d_src; const void **dst; void *h; };
+    std::vector<Fetch> fetches;
+    auto enqueue = [&](const void *d_src, const void **dst) -> int {
       void *h = stage.get<uint32_t>((size_t)total);
       if (!h) return set_error(PBGPU_ENOMEM, "pinned allocation failed");
       BR_CUDA(cudaMemcpyAsync(h, d_src, 4 * (size_t)total, cudaMemcpyDeviceToHost, s));
-      BR_CUDA(cudaStreamSynchronize(s));
-      *dst = copy_out(*os->pins, h, 4 * (size_t)total);
-      pinned_put(h);
-      stage.v.erase(std::find(stage.v.begin(), stage.v.end(), h));
-      return *dst ? PBGPU_OK : set_error(PBGPU_ENOMEM, "host allocation failed");
+      fetches.push_back({d_src, dst, h});
+      return PBGPU_OK;
     };
     if (mat) {  // key columns of the result rows: gathered where they already live
-      int32_t *d_k = dev.get<int32_t>((size_t)total);
-      if (!d_k) return set_error(PBGPU_ENOMEM, "device allocation failed");
       struct G { const int32_t *src; const uint32_t *rows; const int32_t **dst; bool on; };
       const G gs[5] = {{dc_i, d_p, &os->k_code, true}, {ds_i, d_p, &os->k_ls, true}, {de_i, d_p, &os->k_le, true},
                        {ds_x, d_b, &os->k_rs, join}, {de_x, d_b, &os->k_re, join}};
       for (const G &g : gs) {
         if (!g.on) continue;
+        int32_t *d_k = dev.get<int32_t>((size_t)total);
+        if (!d_k) return set_error(PBGPU_ENOMEM, "device allocation failed");
         BR_TRY(pbgpu_gather_i32(g.src, g.rows, total, d_k, s));
-        BR_TRY(fetch(d_k, (const void **)g.dst));
+        BR_TRY(enqueue(d_k, (const void **)g.dst));
       }
       os->contig_names.resize(dict.map.size());
       for (auto &kv : dict.map) os->contig_names[(size_t)kv.second] = kv.first;
     }
-    if (need_l) BR_TRY(fetch(d_p, (const void **)&os->lrow));
-    if (need_r) BR_TRY(fetch(d_b, (const void **)&os->rrow));
+    if (need_l) BR_TRY(enqueue(d_p, (const void **)&os->lrow));
+    if (need_r) BR_TRY(enqueue(d_b, (const void **)&os->rrow));
+    BR_CUDA(cudaStreamSynchronize(s));
+    for (auto &f : fetches) {
+      *f.dst = copy_out(*os->pins, f.h, 4 * (size_t)total);
+      if (!*f.dst) return set_error(PBGPU_ENOMEM, "host allocation failed");
+    }
     if (!os->rrow) os->rrow = os->lrow;  // never dereferenced in this case; keeps emit=1 paths well defined
     os->n_out = total;
   } else if (o.range_op == PBGPU_OP_NEAREST) {

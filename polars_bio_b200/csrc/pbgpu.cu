@@ -284,26 +284,41 @@ static int check_probe_args(const pbgpu_index *ix, const int32_t *c, const int32
   return PBGPU_OK;
 }
 
-int pbgpu_count_overlaps(const pbgpu_index *ix, const int32_t *d_contig, const int32_t *d_start, const int32_t *d_end, int64_t n,
-                         int filter_op, int64_t *d_counts, void *stream) {
+}  // extern "C"
+
+namespace pbgpu {
+template <typename OutT>
+int count_overlaps_impl(const pbgpu_index *ix, const int32_t *d_contig, const int32_t *d_start, const int32_t *d_end, int64_t n,
+                        int filter_op, OutT *d_counts, cudaStream_t s) {
   PB_TRY(check_probe_args(ix, d_contig, d_start, d_end, n, filter_op));
   if (n == 0) return PBGPU_OK;
   if (!d_counts) return set_error(PBGPU_EINVAL, "d_counts is NULL");
-  cudaStream_t s = (cudaStream_t)stream;
   g_ev.mark(EV_COUNT0, s);
   const unsigned grid = (unsigned)cdiv(n, kSweepThreads);
+  const bool strict = filter_op == PBGPU_FILTER_STRICT;
   if (ix->fast) {
-    if (filter_op == PBGPU_FILTER_STRICT)
-      PB_LAUNCH(count_overlaps_fast_kernel<true>, grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, d_counts);
-    else
-      PB_LAUNCH(count_overlaps_fast_kernel<false>, grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, d_counts);
-  } else if (filter_op == PBGPU_FILTER_STRICT)
-    PB_LAUNCH(count_overlaps_kernel<true>, grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, d_counts);
-  else
-    PB_LAUNCH(count_overlaps_kernel<false>, grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, d_counts);
+    if (strict) PB_LAUNCH((count_overlaps_fast_kernel<true, OutT>), grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, d_counts);
+    else PB_LAUNCH((count_overlaps_fast_kernel<false, OutT>), grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, d_counts);
+  } else {
+    if (strict) PB_LAUNCH((count_overlaps_kernel<true, OutT>), grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, d_counts);
+    else PB_LAUNCH((count_overlaps_kernel<false, OutT>), grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, d_counts);
+  }
   PB_CHECK_LAUNCH();
   g_ev.mark(EV_COUNT1, s);
   return PBGPU_OK;
+}
+// internal (same .so, not part of the C ABI): 32-bit counts for the Arrow bridge, widened on the host
+int count_overlaps_u32(const pbgpu_index *ix, const int32_t *c, const int32_t *s_, const int32_t *e, int64_t n, int filter_op,
+                       uint32_t *d_counts, void *stream) {
+  return count_overlaps_impl<uint32_t>(ix, c, s_, e, n, filter_op, d_counts, (cudaStream_t)stream);
+}
+}  // namespace pbgpu
+
+extern "C" {
+
+int pbgpu_count_overlaps(const pbgpu_index *ix, const int32_t *d_contig, const int32_t *d_start, const int32_t *d_end, int64_t n,
+                         int filter_op, int64_t *d_counts, void *stream) {
+  return count_overlaps_impl<int64_t>(ix, d_contig, d_start, d_end, n, filter_op, d_counts, (cudaStream_t)stream);
 }
 
 int pbgpu_coverage(const pbgpu_index *ix, const int32_t *d_contig, const int32_t *d_start, const int32_t *d_end, int64_t n,
@@ -450,14 +465,19 @@ namespace pbgpu {
 __global__ void __launch_bounds__(256) owner_keys_kernel(const int32_t *__restrict__ c, int64_t n, const int32_t *__restrict__ owner,
                                                          int32_t n_contigs, int32_t n_ranks, uint64_t *__restrict__ keys,
                                                          uint64_t *__restrict__ vals, unsigned long long *__restrict__ rank_counts) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int32_t cc = c[i];
-  int32_t r = (cc >= 0 && cc < n_contigs) ? owner[cc] : n_ranks;
-  if (r < 0 || r > n_ranks) r = n_ranks;
-  keys[i] = (uint64_t)r;
-  vals[i] = (uint64_t)i;
-  if (r < n_ranks) atomicAdd(rank_counts + r, 1ull);
+  __shared__ unsigned int bins[256];  // per-block rank histogram: one global atomic per rank per block
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) bins[i] = 0;
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int32_t cc = c[i];
+    int32_t r = (cc >= 0 && cc < n_contigs) ? owner[cc] : n_ranks;
+    if (r < 0 || r > n_ranks) r = n_ranks;
+    keys[i] = (uint64_t)r;
+    vals[i] = (uint64_t)i;
+    if (r < n_ranks) atomicAdd(&bins[r], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_ranks; i += blockDim.x) if (bins[i]) atomicAdd(rank_counts + i, (unsigned long long)bins[i]);
 }
 
 __global__ void __launch_bounds__(256) pack_records_kernel(const uint64_t *__restrict__ perm, int64_t kept, const int32_t *__restrict__ c,
@@ -565,8 +585,12 @@ extern "C" int pbgpu_pack_by_owner(const int32_t *d_contig, const int32_t *d_sta
   uint64_t *keys = nullptr, *vals = nullptr;
   PB_TRY(sc.get(&keys, (size_t)n));
   PB_TRY(sc.get(&vals, (size_t)n));
-  PB_LAUNCH(owner_keys_kernel, (unsigned)cdiv(n, 256), 256, 0, s, d_contig, n, d_owner, n_contigs, n_ranks, keys, vals,
-            (unsigned long long *)d_rank_counts);
+  {
+    int64_t grid = cdiv(n, 256 * 8);
+    if (grid > kSMs * 16) grid = kSMs * 16;
+    PB_LAUNCH(owner_keys_kernel, (unsigned)grid, 256, 0, s, d_contig, n, d_owner, n_contigs, n_ranks, keys, vals,
+              (unsigned long long *)d_rank_counts);
+  }
   PB_CHECK_LAUNCH();
   PB_TRY(radix_sort_pairs(keys, vals, n, 8, s));
   if (d_packed) {

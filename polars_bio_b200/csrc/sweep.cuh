@@ -53,14 +53,14 @@ __device__ __forceinline__ uint32_t probe_count(const IndexView &ix, int32_t c, 
 }
 
 // ---- count_overlaps: int64 count per iterated row -------------------------------------------
-template <bool STRICT>
+template <bool STRICT, typename OutT>
 __global__ void __launch_bounds__(kSweepThreads) count_overlaps_kernel(IndexView ix, const int32_t *__restrict__ pc,
                                                                        const int32_t *__restrict__ ps,
                                                                        const int32_t *__restrict__ pe, int64_t n,
-                                                                       int64_t *__restrict__ counts) {
+                                                                       OutT *__restrict__ counts) {
   int64_t i = (int64_t)blockIdx.x * kSweepThreads + threadIdx.x;
   if (i >= n) return;
-  counts[i] = (int64_t)probe_count<STRICT>(ix, pc[i], ps[i], pe[i]);
+  counts[i] = (OutT)probe_count<STRICT>(ix, pc[i], ps[i], pe[i]);
 }
 
 // ---- overlap pass 1: uint32 count per probe + uint64 total per block -------------------------
@@ -223,15 +223,15 @@ __device__ __forceinline__ bool fast_window(const IndexView &ix, int32_t c, int3
   return true;
 }
 
-template <bool STRICT>
+template <bool STRICT, typename OutT>  // OutT: int64_t (the ABI's count column) or uint32_t (half the D2H for the Arrow bridge)
 __global__ void __launch_bounds__(kSweepThreads) count_overlaps_fast_kernel(IndexView ix, const int32_t *__restrict__ pc,
                                                                             const int32_t *__restrict__ ps,
                                                                             const int32_t *__restrict__ pe, int64_t n,
-                                                                            int64_t *__restrict__ counts) {
+                                                                            OutT *__restrict__ counts) {
   int64_t i = (int64_t)blockIdx.x * kSweepThreads + threadIdx.x;
   if (i >= n) return;
   uint32_t hi;
-  counts[i] = (int64_t)fast_count<STRICT>(ix, pc[i], ps[i], pe[i], hi);
+  counts[i] = (OutT)fast_count<STRICT>(ix, pc[i], ps[i], pe[i], hi);
 }
 
 template <bool STRICT>
