@@ -57,6 +57,19 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(kernel_label: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel from the committed ncu capture."""
+    p = os.path.join(ROOT, "profiles", "r01c_traffic.json")
+    try:
+        t = json.load(open(p))
+        for name, v in t.items():
+            if name in kernel_label:
+                return v["traffic_bytes"]
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -367,7 +380,8 @@ def main():
     dom = max(cands, key=lambda k: cands[k][1])
     ach = cands[dom][0] / (cands[dom][1] * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "traffic": None, "peak_source": peak_src, "algorithmic_bytes": cands[dom][0], "kernel_ms": cands[dom][1],
+            "traffic": ncu_traffic(dom), "traffic_source": "profiles/r01c_traffic.json (ncu --set full, cold-cache replay, per launch)",
+            "peak_source": peak_src, "algorithmic_bytes": cands[dom][0], "kernel_ms": cands[dom][1],
             "all_kernels": {k: {"ms": v[1], "algorithmic_bytes": v[0], "GBps": v[0] / (v[1] * 1e-3) / 1e9} for k, v in cands.items()},
             "index_build_ms": km["partition_sort_ns"], "offset_scan_ms": km["scan_ns"],
             "step_stage_ms": {"index_build": float(stage[0]), "count_overlaps": float(stage[1]), "overlap_two_pass": float(stage[2])}}
