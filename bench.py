@@ -47,6 +47,19 @@ def make_config2(n_reads: int = 10_000_000, n_variants: int = 1_000_000, seed_sh
     return (np.zeros(n_reads, np.int32), ps, pe), (np.zeros(n_variants, np.int32), bs, be), 1
 
 
+def make_sharded_slice(rank: int, world: int, n_reads: int, n_variants: int):
+    """Rank `rank`'s slice of the N-GPU workload: N copies of config 2 (contig k = copy k of chr1), rows of all
+    contigs mixed.  The union over ranks is the global job; `--impl reference` joins that union on the CPU."""
+    rng = np.random.default_rng(1000 + rank)
+    pc = rng.integers(0, world, n_reads).astype(np.int32)
+    ps = rng.integers(0, CHR1_LEN - 150, n_reads, dtype=np.int64).astype(np.int32)
+    pe = (ps + 150).astype(np.int32)
+    bc = rng.integers(0, world, n_variants).astype(np.int32)
+    bs = rng.integers(0, CHR1_LEN - 1, n_variants, dtype=np.int64).astype(np.int32)
+    be = (bs + 1).astype(np.int32)
+    return (pc, ps, pe), (bc, bs, be)
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -161,19 +174,27 @@ def run_reference(args):
     if rank != 0:
         return  # rank 0 alone runs the CPU arm
     n_reads, n_var = args.reads, args.variants
-    probe, build, nc = make_config2(n_reads, n_var)
+    world = max(1, args.gpus)
+    if world == 1:
+        probe, build, nc = make_config2(n_reads, n_var)
+        wl = f"config2: {n_reads} reads x {n_var} variants, chr1, Strict"
+    else:  # the same global job the GPU arm shards: the union of every rank's slice
+        parts = [make_sharded_slice(r, world, n_reads, n_var) for r in range(world)]
+        probe = tuple(np.concatenate([p[0][k] for p in parts]) for k in range(3))
+        build = tuple(np.concatenate([p[1][k] for p in parts]) for k in range(3))
+        nc = world
+        wl = f"{world} x config2 (contig k = copy k of chr1): {world * n_reads} reads x {world * n_var} variants, Strict"
     threads = pick_threads(probe, build, nc)
-    sample = min(n_reads, args.cpu_sample)
+    sample = len(probe[0]) if args.cpu_sample >= n_reads else min(len(probe[0]), args.cpu_sample)
     pairs, sec = cpu_reference_run(probe, build, nc, sample, threads, steps=args.steps, warmup=args.warmup)
     v = pairs / sec
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": f"config2: {n_reads} reads x {n_var} variants, chr1, Strict; index build + count_overlaps + pair emit",
-                   "l2": "n/a (CPU)"},
+        "config": {"workload": wl + "; interval-tree build + count_overlaps + pair emit", "l2": "n/a (CPU)"},
         "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
-                         "sample": f"per step: interval-tree build over all {n_var} variants + count_overlaps + pair emit for {sample} of {n_reads} reads"},
+                         "sample": f"per step: interval-tree build over all {len(build[0])} variants + count_overlaps + pair emit for {sample} of {len(probe[0])} reads"},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -192,13 +213,7 @@ def run_sharded(args, world, rank, dev):
     from polars_bio_b200 import _native, dist as pbd, engine
 
     n, m = args.reads, args.variants
-    rng = np.random.default_rng(1000 + rank)
-    pc = rng.integers(0, world, n).astype(np.int32)
-    ps = rng.integers(0, CHR1_LEN - 150, n, dtype=np.int64).astype(np.int32)
-    pe = (ps + 150).astype(np.int32)
-    bc = rng.integers(0, world, m).astype(np.int32)
-    bs = rng.integers(0, CHR1_LEN - 1, m, dtype=np.int64).astype(np.int32)
-    be = (bs + 1).astype(np.int32)
+    (pc, ps, pe), (bc, bs, be) = make_sharded_slice(rank, world, n, m)
     dp = [torch.from_numpy(x).to(dev) for x in (pc, ps, pe)]
     db = [torch.from_numpy(x).to(dev) for x in (bc, bs, be)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)

@@ -71,13 +71,16 @@ class Pool {
     return p;
   }
   int size() const { return (int)workers_.size() + 1; }
-  void parallel_for(int64_t n_tasks, const std::function<void(int64_t)> &fn) {
-    if (n_tasks <= 0) return;
+  // Returns false when a task threw (std::bad_alloc in practice): nothing may unwind out of a worker thread or
+  // across the C ABI, so the failure is latched and reported to the caller instead.
+  bool parallel_for(int64_t n_tasks, const std::function<void(int64_t)> &fn) {
+    if (n_tasks <= 0) return true;
     if (n_tasks == 1 || workers_.empty()) {
-      for (int64_t i = 0; i < n_tasks; ++i) fn(i);
-      return;
+      try { for (int64_t i = 0; i < n_tasks; ++i) fn(i); } catch (...) { return false; }
+      return true;
     }
     std::unique_lock<std::mutex> run_lock(run_mu_);  // one parallel_for at a time
+    failed_.store(false);
     {
       std::lock_guard<std::mutex> lk(mu_);
       fn_ = &fn;
@@ -91,6 +94,7 @@ class Pool {
     std::unique_lock<std::mutex> lk(mu_);
     done_cv_.wait(lk, [&] { return pending_ == 0; });
     fn_ = nullptr;
+    return !failed_.load();
   }
 
  private:
@@ -114,7 +118,7 @@ class Pool {
     for (;;) {
       int64_t i = next_.fetch_add(1);
       if (i >= total_) break;
-      (*fn_)(i);
+      try { (*fn_)(i); } catch (...) { failed_.store(true); }
     }
   }
   void loop() {
@@ -138,6 +142,7 @@ class Pool {
   std::condition_variable cv_, done_cv_;
   const std::function<void(int64_t)> *fn_ = nullptr;
   std::atomic<int64_t> next_{0};
+  std::atomic<bool> failed_{false};
   int64_t total_ = 0;
   int pending_ = 0;
   uint64_t epoch_ = 0;
@@ -180,11 +185,25 @@ void *pinned_get(size_t bytes, bool wc = false) {
   g_pin.push_back(b);
   return b.p;
 }
+size_t pinned_cap_bytes() {
+  static size_t cap = [] { const char *e = getenv("PBGPU_PINNED_CACHE_MB"); return (size_t)(e ? atoll(e) : 8192) << 20; }();
+  return cap;
+}
 void pinned_put(void *p) {
   if (!p) return;
   std::lock_guard<std::mutex> lk(g_pin_mu);
-  for (auto &b : g_pin)
-    if (b.p == p) b.busy = false;
+  size_t total = 0;
+  for (auto &b : g_pin) { if (b.p == p) b.busy = false; total += b.cap; }
+  // keep the cache bounded (PBGPU_PINNED_CACHE_MB, default 8 GiB): release idle buffers, largest first
+  while (total > pinned_cap_bytes()) {
+    int victim = -1;
+    for (int i = 0; i < (int)g_pin.size(); ++i)
+      if (!g_pin[i].busy && (victim < 0 || g_pin[i].cap > g_pin[victim].cap)) victim = i;
+    if (victim < 0) break;
+    cudaFreeHost(g_pin[victim].p);
+    total -= g_pin[victim].cap;
+    g_pin.erase(g_pin.begin() + victim);
+  }
 }
 struct PinnedHold {  // returns its buffers to the cache on destruction
   std::vector<void *> v;
@@ -440,7 +459,7 @@ int encode_keys(const Table &t, const char *side, ContigDict &dict, int32_t *cod
     for (int64_t lo = b_lo; lo < b_hi; lo += kChunk) tasks.push_back({b, lo, std::min(lo + kChunk, b_hi)});
   }
   std::atomic<int> range_err{0};
-  Pool::get().parallel_for((int64_t)tasks.size(), [&](int64_t ti) {
+  const bool pool_ok = Pool::get().parallel_for((int64_t)tasks.size(), [&](int64_t ti) {
     const Task &tk = tasks[ti];
     const ArrowArray &ba = t.batches[tk.b];
     const ArrowArray *ac = ba.children[t.key[0]], *as = ba.children[t.key[1]], *ae = ba.children[t.key[2]];
@@ -485,6 +504,7 @@ int encode_keys(const Table &t, const char *side, ContigDict &dict, int32_t *cod
       en[g0 + i] = (int32_t)e;
     }
   });
+  if (!pool_ok) return set_error(PBGPU_ENOMEM, "host allocation failed while encoding the %s table", side);
   if (range_err.load())
     return set_error(PBGPU_ERANGE, "%s table has a coordinate outside the int32 domain (reference limit: contigs < 2 Gb)", side);
   return PBGPU_OK;
@@ -755,9 +775,11 @@ int gather_columns(const std::vector<GatherJob> &jobs, int64_t n, std::vector<Ar
   const int64_t nchunks = (n + kGatherChunk - 1) / kGatherChunk, nj = (int64_t)jobs.size();
   bool any_str = false;
   for (auto &c : g) any_str |= c.sk != StrKind::None;
-  if (any_str) Pool::get().parallel_for(nj * nchunks, [&](int64_t ti) { g[ti / nchunks].pass1(ti % nchunks); });
+  bool ok = true;
+  if (any_str) ok = Pool::get().parallel_for(nj * nchunks, [&](int64_t ti) { g[ti / nchunks].pass1(ti % nchunks); });
   for (auto &c : g) { int rc = c.alloc(); if (rc != PBGPU_OK) return rc; }
-  Pool::get().parallel_for(nj * nchunks, [&](int64_t ti) { g[ti / nchunks].pass2(ti % nchunks); });
+  ok = Pool::get().parallel_for(nj * nchunks, [&](int64_t ti) { g[ti / nchunks].pass2(ti % nchunks); }) && ok;
+  if (!ok) return set_error(PBGPU_ENOMEM, "host allocation failed while gathering payload columns");
   for (auto &c : g) out->push_back(c.finish());
   return PBGPU_OK;
 }
@@ -1177,15 +1199,16 @@ int run(Table *L, Table *R, OutStream *os) {
     for (int64_t lo = 0; lo < n; lo += slice) {
       const int64_t hi = std::min(n, lo + slice);
       int rc = encode_keys(*IT, iter_is_left ? "left" : "right", dict, hc_i, hs_i, he_i, lo, hi);
-      if (rc != PBGPU_OK) { pbgpu_index_free(ix); return rc; }
+      if (rc != PBGPU_OK) { cudaStreamSynchronize(s); pbgpu_index_free(ix); return rc; }
       cudaMemcpyAsync(dc_i + lo, hc_i + lo, 4 * (size_t)(hi - lo), cudaMemcpyHostToDevice, s);
       cudaMemcpyAsync(ds_i + lo, hs_i + lo, 4 * (size_t)(hi - lo), cudaMemcpyHostToDevice, s);
       cudaMemcpyAsync(de_i + lo, he_i + lo, 4 * (size_t)(hi - lo), cudaMemcpyHostToDevice, s);
     }
-    if (cudaGetLastError() != cudaSuccess) { pbgpu_index_free(ix); return set_error(PBGPU_ECUDA, "H2D copy of the iterated table failed"); }
+    if (cudaGetLastError() != cudaSuccess) { cudaStreamSynchronize(s); pbgpu_index_free(ix); return set_error(PBGPU_ECUDA, "H2D copy of the iterated table failed"); }
   }
   tr.lap("encode + H2D iterated side");
-  struct IxGuard { pbgpu_index *p; ~IxGuard() { pbgpu_index_free(p); } } ig{ix};
+  // the index is freed on the legacy stream: make sure nothing on this call's (non-blocking) stream still reads it
+  struct IxGuard { pbgpu_index *p; cudaStream_t s; ~IxGuard() { cudaStreamSynchronize(s); pbgpu_index_free(p); } } ig{ix, s};
   const uint64_t limit = o.limit;
 
   if (o.range_op == PBGPU_OP_COUNT_OVERLAPS_NAIVE || o.range_op == PBGPU_OP_COVERAGE) {
@@ -1232,7 +1255,7 @@ int run(Table *L, Table *R, OutStream *os) {
     pbgpu_overlap_plan *plan = nullptr;
     int64_t total = 0;
     BR_TRY(pbgpu_overlap_count(ix, dc_i, ds_i, de_i, n, o.filter_op, s, &plan, &total));
-    struct PlanGuard { pbgpu_overlap_plan *p; ~PlanGuard() { pbgpu_overlap_plan_free(p); } } pg{plan};
+    struct PlanGuard { pbgpu_overlap_plan *p; cudaStream_t s; ~PlanGuard() { cudaStreamSynchronize(s); pbgpu_overlap_plan_free(p); } } pg{plan, s};
     uint32_t *d_p = dev.get<uint32_t>((size_t)total), *d_b = dev.get<uint32_t>((size_t)total);
     if (!d_p || !d_b) return set_error(PBGPU_ENOMEM, "device allocation failed for %lld pairs", (long long)total);
     BR_TRY(pbgpu_overlap_emit(plan, d_p, d_b, s));
