@@ -54,7 +54,8 @@ struct pbgpu_index {
   pbgpu::ContigMap *cmap = nullptr;
   uint32_t *gs = nullptr, *ge = nullptr;
   pbgpu::DirRec *dir_s = nullptr, *dir_e = nullptr;
-  void *slab = nullptr, *slab2 = nullptr;  // two stream-ordered allocations back every array above
+  void *slab = nullptr, *slab2 = nullptr, *slab_n = nullptr;  // stream-ordered allocations backing every array above
+  // without nested intervals pmax and en_sorted alias `en` and en_pos is NULL (= identity)
   size_t bytes = 0;
 };
 
@@ -85,15 +86,16 @@ inline IndexView view_of(const pbgpu_index *ix) {
 struct BuildStats {  // device-side reduction target
   int min_start, max_start, min_end, max_end;
   unsigned long long inverted, valid;
+  unsigned long long max_len;  // longest (end - start) over the non-inverted rows
 };
 
 __global__ void __launch_bounds__(256) build_stats_kernel(const int32_t *__restrict__ c, const int32_t *__restrict__ s,
                                                           const int32_t *__restrict__ e, int64_t n, int32_t n_contigs,
                                                           BuildStats *st) {
   __shared__ int sm[4][8];
-  __shared__ unsigned su[2][8];
+  __shared__ unsigned su[3][8];
   int mn_s = INT32_MAX, mx_s = INT32_MIN, mn_e = INT32_MAX, mx_e = INT32_MIN;
-  unsigned inv = 0, val = 0;
+  unsigned inv = 0, val = 0, mlen = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     int32_t cc = c[i];
     if (cc < 0 || cc >= n_contigs) continue;
@@ -101,10 +103,12 @@ __global__ void __launch_bounds__(256) build_stats_kernel(const int32_t *__restr
     mn_s = min(mn_s, ss); mx_s = max(mx_s, ss);
     mn_e = min(mn_e, ee); mx_e = max(mx_e, ee);
     inv += ss > ee;
+    if (ee >= ss) mlen = max(mlen, (unsigned)((long long)ee - (long long)ss));
     ++val;
   }
 #pragma unroll
   for (int d = 16; d; d >>= 1) {
+    mlen = max(mlen, __shfl_xor_sync(0xffffffffu, mlen, d));
     mn_s = min(mn_s, __shfl_xor_sync(0xffffffffu, mn_s, d));
     mx_s = max(mx_s, __shfl_xor_sync(0xffffffffu, mx_s, d));
     mn_e = min(mn_e, __shfl_xor_sync(0xffffffffu, mn_e, d));
@@ -113,18 +117,19 @@ __global__ void __launch_bounds__(256) build_stats_kernel(const int32_t *__restr
     val += __shfl_xor_sync(0xffffffffu, val, d);
   }
   const int w = threadIdx.x >> 5;
-  if ((threadIdx.x & 31) == 0) { sm[0][w] = mn_s; sm[1][w] = mx_s; sm[2][w] = mn_e; sm[3][w] = mx_e; su[0][w] = inv; su[1][w] = val; }
+  if ((threadIdx.x & 31) == 0) { sm[0][w] = mn_s; sm[1][w] = mx_s; sm[2][w] = mn_e; sm[3][w] = mx_e; su[0][w] = inv; su[1][w] = val; su[2][w] = mlen; }
   __syncthreads();
   if (threadIdx.x == 0) {  // one set of atomics per block (per-warp atomics on six shared addresses cost 80 us at 1M rows)
     for (int k = 1; k < 8; ++k) {
       sm[0][0] = min(sm[0][0], sm[0][k]); sm[1][0] = max(sm[1][0], sm[1][k]);
       sm[2][0] = min(sm[2][0], sm[2][k]); sm[3][0] = max(sm[3][0], sm[3][k]);
-      su[0][0] += su[0][k]; su[1][0] += su[1][k];
+      su[0][0] += su[0][k]; su[1][0] += su[1][k]; su[2][0] = max(su[2][0], su[2][k]);
     }
     atomicMin(&st->min_start, sm[0][0]); atomicMax(&st->max_start, sm[1][0]);
     atomicMin(&st->min_end, sm[2][0]); atomicMax(&st->max_end, sm[3][0]);
     if (su[0][0]) atomicAdd(&st->inverted, (unsigned long long)su[0][0]);
     atomicAdd(&st->valid, (unsigned long long)su[1][0]);
+    atomicMax(&st->max_len, (unsigned long long)su[2][0]);
   }
 }
 
@@ -144,35 +149,44 @@ __global__ void __launch_bounds__(256) make_start_keys_kernel(const int32_t *__r
   vals[i] = ((uint64_t)(uint32_t)e[i] << 32) | (uint32_t)i;
 }
 
-__global__ void __launch_bounds__(64) find_segments_kernel(const uint64_t *__restrict__ keys, int64_t n, int pos_bits,
-                                                           int32_t n_contigs, int32_t *__restrict__ seg) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c > n_contigs) return;
-  const uint64_t target = (uint64_t)c << pos_bits;
-  int64_t lo = 0, hi = n;
-  while (lo < hi) {
-    int64_t mid = lo + ((hi - lo) >> 1);
-    if (keys[mid] < target) lo = mid + 1; else hi = mid;
+// unpack the start-sorted pairs into SoA, find the contig segments (boundary detection: the thread that sees a
+// contig change writes seg[] for every contig in between, empty ones included) and count end inversions
+// (en[i] < en[i-1] inside a contig; 0 <=> no nested intervals <=> ends are already sorted in start order).
+__global__ void __launch_bounds__(256) unpack_sorted_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ vals,
+                                                            int64_t m, int pos_bits, uint32_t bias_s, int32_t n_contigs,
+                                                            int32_t *__restrict__ st, int32_t *__restrict__ en,
+                                                            uint32_t *__restrict__ row, int32_t *__restrict__ seg,
+                                                            unsigned long long *__restrict__ inversions) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned inv = 0;
+  if (i < m) {
+    const uint64_t k = keys[i], v = vals[i];
+    const long long contig = (long long)(k >> pos_bits);
+    const uint32_t sp = (uint32_t)(k & ((1ull << pos_bits) - 1ull));
+    const int32_t e = (int32_t)(uint32_t)(v >> 32);
+    st[i] = (int32_t)(sp ^ bias_s);
+    en[i] = e;
+    row[i] = (uint32_t)v;
+    long long prev = -1;
+    if (i > 0) {
+      prev = (long long)(keys[i - 1] >> pos_bits);
+      if (prev == contig) inv = e < (int32_t)(uint32_t)(vals[i - 1] >> 32);
+    }
+    for (long long c = prev + 1; c <= contig; ++c) seg[c] = (int32_t)i;
+    if (i == m - 1) for (long long c = contig + 1; c <= n_contigs; ++c) seg[c] = (int32_t)m;
   }
-  seg[c] = (int32_t)lo;
+  inv = __ballot_sync(0xffffffffu, inv) ? __popc(__ballot_sync(0xffffffffu, inv)) : 0;
+  if ((threadIdx.x & 31) == 0 && inv) atomicAdd(inversions, (unsigned long long)inv);
 }
 
-// unpack the start-sorted pairs; also emit the contig-tagged end keys for the running max
-// and the (contig | end) keys of the second sort.
-__global__ void __launch_bounds__(256) unpack_sorted_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ vals,
-                                                            int64_t m, int pos_bits, uint32_t bias_s, uint32_t bias_e,
-                                                            int32_t *__restrict__ st, int32_t *__restrict__ en,
-                                                            uint32_t *__restrict__ row, uint64_t *__restrict__ pm_keys,
+// nested case only: contig-tagged end keys for the running max and the (contig | end) keys of the second sort
+__global__ void __launch_bounds__(256) make_end_keys_kernel(const uint64_t *__restrict__ keys, const int32_t *__restrict__ en, int64_t m,
+                                                            int pos_bits, uint32_t bias_e, uint64_t *__restrict__ pm_keys,
                                                             uint64_t *__restrict__ ekeys, uint64_t *__restrict__ evals) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
-  const uint64_t k = keys[i], v = vals[i];
-  const uint64_t contig = k >> pos_bits;
-  const uint32_t sp = (uint32_t)(k & ((1ull << pos_bits) - 1ull));
-  const int32_t e = (int32_t)(uint32_t)(v >> 32);
-  st[i] = (int32_t)(sp ^ bias_s);
-  en[i] = e;
-  row[i] = (uint32_t)v;
+  const uint64_t contig = keys[i] >> pos_bits;
+  const int32_t e = en[i];
   pm_keys[i] = (contig << 32) | ((uint32_t)e ^ 0x80000000u);
   ekeys[i] = (contig << pos_bits) | ((uint32_t)e ^ bias_e);
   evals[i] = (uint64_t)i;
@@ -196,7 +210,7 @@ __global__ void __launch_bounds__(256) unpack_ends_kernel(const uint64_t *__rest
 // ---- fast-path construction ------------------------------------------------------------------
 // per contig: coordinate range of its indexed rows -> width of its slice on the global axis
 __global__ void __launch_bounds__(128) contig_span_kernel(const int32_t *__restrict__ seg, const int32_t *__restrict__ st,
-                                                          const int32_t *__restrict__ pmax, int32_t n_contigs,
+                                                          long long max_len, int32_t n_contigs,
                                                           ContigMap *__restrict__ cmap, unsigned long long *__restrict__ span) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_contigs) return;
@@ -205,8 +219,8 @@ __global__ void __launch_bounds__(128) contig_span_kernel(const int32_t *__restr
   m.off = 0;
   if (lo >= hi) { m.lo_m1 = 0; m.hi_p1 = 0; m.has = 0; span[c] = 0; }
   else {
-    m.lo_m1 = (long long)st[lo] - 1;          // rows are not inverted on this path: min coordinate = min start
-    m.hi_p1 = (long long)pmax[hi - 1] + 1;    // max coordinate = max end
+    m.lo_m1 = (long long)st[lo] - 1;                 // rows are not inverted on this path: min coordinate = min start
+    m.hi_p1 = (long long)st[hi - 1] + max_len + 1;   // upper bound of every end: largest start + longest interval
     m.has = 1;
     span[c] = (unsigned long long)(m.hi_p1 - m.lo_m1 + 1);
   }
@@ -216,20 +230,6 @@ __global__ void __launch_bounds__(128) contig_off_kernel(const unsigned long lon
                                                          ContigMap *__restrict__ cmap) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < n_contigs) cmap[c].off = (uint32_t)off[c];
-}
-// count positions where the running max differs from the end itself (0 <=> ends already sorted in start order)
-__global__ void __launch_bounds__(256) count_nested_kernel(const int32_t *__restrict__ en, const int32_t *__restrict__ pmax,
-                                                           int64_t m, unsigned long long *__restrict__ out) {
-  unsigned c = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) c += en[i] != pmax[i];
-#pragma unroll
-  for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
-}
-__global__ void __launch_bounds__(256) iota_ends_kernel(const int32_t *__restrict__ en, int64_t m, int32_t *__restrict__ en_sorted,
-                                                        uint32_t *__restrict__ en_pos) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < m) { en_sorted[i] = en[i]; en_pos[i] = (uint32_t)i; }
 }
 // global-axis coordinate of every sorted key (contig taken from the packed sort key)
 __global__ void __launch_bounds__(256) global_coord_kernel(const uint64_t *__restrict__ keys, int pos_bits, const int32_t *__restrict__ pos,

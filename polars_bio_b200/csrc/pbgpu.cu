@@ -112,6 +112,7 @@ void pbgpu_index_free(pbgpu_index *ix) {
   // users of non-blocking streams synchronise before freeing (pbgpu.h)
   if (ix->slab) cudaFreeAsync(ix->slab, 0);
   if (ix->slab2) cudaFreeAsync(ix->slab2, 0);
+  if (ix->slab_n) cudaFreeAsync(ix->slab_n, 0);
   if (cur != ix->device) cudaSetDevice(cur);
   delete ix;
 }
@@ -130,7 +131,7 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
   struct MarkEnd { cudaStream_t s; ~MarkEnd() { g_ev.mark(EV_BUILD1, s); } } mark_end{s};
   Scratch sc(s);
   // 1. domain of the coordinates (decides key width and whether the rank identity is safe)
-  BuildStats hs = {INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN, 0ull, 0ull};
+  BuildStats hs = {INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN, 0ull, 0ull, 0ull};
   if (m_in > 0) {
     BuildStats *d_stats = nullptr;
     PB_TRY(sc.get(&d_stats, 1));
@@ -145,18 +146,18 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
   const int64_t m = (int64_t)hs.valid;
   ix->m = m;
   ix->has_inverted = hs.inverted != 0;
-  // slab 1: seg + the six sorted arrays
+  // slab 1: seg + start-ordered rows
   const size_t seg_b = align_up(sizeof(int32_t) * ((size_t)n_contigs + 2)), arr_b = align_up(sizeof(int32_t) * (size_t)(m ? m : 1));
-  PB_TRY(dev_alloc(&ix->slab, seg_b + 6 * arr_b, s));
-  ix->bytes = seg_b + 6 * arr_b;
+  PB_TRY(dev_alloc(&ix->slab, seg_b + 3 * arr_b, s));
+  ix->bytes = seg_b + 3 * arr_b;
   char *base = (char *)ix->slab;
   ix->seg = (int32_t *)base;
   ix->st = (int32_t *)(base + seg_b);
   ix->en = (int32_t *)(base + seg_b + arr_b);
-  ix->pmax = (int32_t *)(base + seg_b + 2 * arr_b);
-  ix->en_sorted = (int32_t *)(base + seg_b + 3 * arr_b);
-  ix->row = (uint32_t *)(base + seg_b + 4 * arr_b);
-  ix->en_pos = (uint32_t *)(base + seg_b + 5 * arr_b);
+  ix->row = (uint32_t *)(base + seg_b + 2 * arr_b);
+  ix->pmax = ix->en;       // until nested intervals are detected: running max == end,
+  ix->en_sorted = ix->en;  // end order == start order,
+  ix->en_pos = nullptr;    // identity
   if (m == 0) {
     PB_CUDA(cudaMemsetAsync(ix->seg, 0, sizeof(int32_t) * ((size_t)n_contigs + 2), s));
     return PBGPU_OK;
@@ -176,56 +177,52 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
   PB_LAUNCH(make_start_keys_kernel, (unsigned)cdiv(m_in, 256), 256, 0, s, d_c, d_s, d_e, m_in, n_contigs, pos_bits, bias, keys, vals);
   PB_CHECK_LAUNCH();
   PB_TRY(radix_sort_pairs(keys, vals, m_in, pos_bits + contig_bits, s));
-  PB_LAUNCH(find_segments_kernel, (unsigned)cdiv(n_contigs + 1, 64), 64, 0, s, keys, m_in, pos_bits, n_contigs, ix->seg);
-  PB_CHECK_LAUNCH();
 
-  // 3. unpack + running max of the ends
-  uint64_t *pm_keys = nullptr, *ekeys = nullptr, *evals = nullptr;
-  PB_TRY(sc.get(&pm_keys, (size_t)m));
-  PB_TRY(sc.get(&ekeys, (size_t)m));
-  PB_TRY(sc.get(&evals, (size_t)m));
-  PB_LAUNCH(unpack_sorted_kernel, (unsigned)cdiv(m, 256), 256, 0, s, keys, vals, m, pos_bits, bias, bias, ix->st, ix->en, ix->row,
-            pm_keys, ekeys, evals);
-  PB_CHECK_LAUNCH();
-  PB_TRY((device_scan<MaxU64, true>((const unsigned long long *)pm_keys, (unsigned long long *)pm_keys, m, nullptr, s)));
-  PB_LAUNCH(unpack_pmax_kernel, (unsigned)cdiv(m, 256), 256, 0, s, pm_keys, m, ix->pmax);
-  PB_CHECK_LAUNCH();
-
-  // 4. one host round trip decides two things: are the ends already sorted in start order (no nested
-  //    intervals -> skip the second sort), and does the global axis fit 32 bits (fast path)?
+  // 3. unpack + segments + nested-interval detection; contig slices of the global axis.  One host round trip then
+  //    decides two things: second sort needed (nested intervals)?  global axis fits 32 bits (fast path)?
   const bool try_fast = !ix->has_inverted;
-  unsigned long long *d_meta = nullptr;  // [0] nested count, [1] total span
+  unsigned long long *d_meta = nullptr;  // [0] end inversions, [1] total span
   unsigned long long *d_span = nullptr;
   PB_TRY(sc.get(&d_meta, 2));
   PB_TRY(sc.get(&d_span, (size_t)n_contigs + 1));
   ContigMap *d_cmap_tmp = nullptr;
   PB_TRY(sc.get(&d_cmap_tmp, (size_t)n_contigs + 1));
   PB_CUDA(cudaMemsetAsync(d_meta, 0, 2 * sizeof(unsigned long long), s));
-  {
-    int64_t grid = cdiv(m, 256 * 8);
-    if (grid > kSMs * 8) grid = kSMs * 8;
-    PB_LAUNCH(count_nested_kernel, (unsigned)grid, 256, 0, s, ix->en, ix->pmax, m, d_meta);
-    if (try_fast) {
-      PB_LAUNCH(contig_span_kernel, (unsigned)cdiv(n_contigs, 128), 128, 0, s, ix->seg, ix->st, ix->pmax, n_contigs, d_cmap_tmp, d_span);
-      PB_TRY((device_scan<SumU64, false>(d_span, d_span, n_contigs, d_meta + 1, s)));
-    }
-    PB_CHECK_LAUNCH();
+  PB_LAUNCH(unpack_sorted_kernel, (unsigned)cdiv(m, 256), 256, 0, s, keys, vals, m, pos_bits, bias, n_contigs, ix->st, ix->en, ix->row,
+            ix->seg, d_meta);
+  if (try_fast) {
+    PB_LAUNCH(contig_span_kernel, (unsigned)cdiv(n_contigs, 128), 128, 0, s, ix->seg, ix->st, (long long)hs.max_len, n_contigs, d_cmap_tmp, d_span);
+    PB_TRY((device_scan<SumU64, false>(d_span, d_span, n_contigs, d_meta + 1, s)));
   }
+  PB_CHECK_LAUNCH();
   unsigned long long h_meta[2] = {0, 0};
   PB_CUDA(cudaMemcpyAsync(h_meta, d_meta, sizeof(h_meta), cudaMemcpyDeviceToHost, s));
   PB_CUDA(cudaStreamSynchronize(s));
   const bool nested = h_meta[0] != 0;
 
-  // 5. ends sorted per contig (stable over the start order -> ties keep (start,row) order)
+  // 4. nested intervals: running max of the ends, ends sorted per contig (stable over the start order, so ties keep
+  //    (start,row) order) and their positions.  Otherwise the three arrays alias `en` / identity.
+  uint64_t *ekeys = nullptr;
   if (nested) {
+    PB_TRY(dev_alloc(&ix->slab_n, 3 * arr_b, s));
+    ix->bytes += 3 * arr_b;
+    ix->pmax = (int32_t *)ix->slab_n;
+    ix->en_sorted = (int32_t *)((char *)ix->slab_n + arr_b);
+    ix->en_pos = (uint32_t *)((char *)ix->slab_n + 2 * arr_b);
+    uint64_t *pm_keys = nullptr, *evals = nullptr;
+    PB_TRY(sc.get(&pm_keys, (size_t)m));
+    PB_TRY(sc.get(&ekeys, (size_t)m));
+    PB_TRY(sc.get(&evals, (size_t)m));
+    PB_LAUNCH(make_end_keys_kernel, (unsigned)cdiv(m, 256), 256, 0, s, keys, ix->en, m, pos_bits, bias, pm_keys, ekeys, evals);
+    PB_CHECK_LAUNCH();
+    PB_TRY((device_scan<MaxU64, true>((const unsigned long long *)pm_keys, (unsigned long long *)pm_keys, m, nullptr, s)));
+    PB_LAUNCH(unpack_pmax_kernel, (unsigned)cdiv(m, 256), 256, 0, s, pm_keys, m, ix->pmax);
     PB_TRY(radix_sort_pairs(ekeys, evals, m, pos_bits + contig_bits, s));
     PB_LAUNCH(unpack_ends_kernel, (unsigned)cdiv(m, 256), 256, 0, s, ekeys, evals, m, pos_bits, bias, ix->en_sorted, ix->en_pos);
-  } else {
-    PB_LAUNCH(iota_ends_kernel, (unsigned)cdiv(m, 256), 256, 0, s, ix->en, m, ix->en_sorted, ix->en_pos);
+    PB_CHECK_LAUNCH();
   }
-  PB_CHECK_LAUNCH();
 
-  // 6. fast path: global axis + rank directories
+  // 5. fast path: global axis + rank directories
   const unsigned long long total_span = h_meta[1];
   if (try_fast && total_span > 0 && total_span < 0xFFFFFFF0ull) {
     int shift = 0;
@@ -245,8 +242,10 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
     ix->n_buckets = nb;
     PB_CUDA(cudaMemcpyAsync(ix->cmap, d_cmap_tmp, sizeof(ContigMap) * (size_t)n_contigs, cudaMemcpyDeviceToDevice, s));
     PB_LAUNCH(contig_off_kernel, (unsigned)cdiv(n_contigs, 128), 128, 0, s, d_span, n_contigs, ix->cmap);
+    // contig of position i: from the start-sorted keys (start order) or the end-sorted keys (end order; same order
+    // as the start keys when nothing is nested)
     PB_LAUNCH(global_coord_kernel, (unsigned)cdiv(m, 256), 256, 0, s, keys, pos_bits, ix->st, m, ix->cmap, ix->gs);
-    PB_LAUNCH(global_coord_kernel, (unsigned)cdiv(m, 256), 256, 0, s, ekeys, pos_bits, ix->en_sorted, m, ix->cmap, ix->ge);
+    PB_LAUNCH(global_coord_kernel, (unsigned)cdiv(m, 256), 256, 0, s, nested ? ekeys : keys, pos_bits, ix->en_sorted, m, ix->cmap, ix->ge);
     PB_LAUNCH(build_dir_kernel, (unsigned)cdiv((int64_t)nb + 1, 256), 256, 0, s, ix->gs, m, shift, nb, ix->dir_s);
     PB_LAUNCH(build_dir_kernel, (unsigned)cdiv((int64_t)nb + 1, 256), 256, 0, s, ix->ge, m, shift, nb, ix->dir_e);
     PB_CHECK_LAUNCH();
@@ -287,6 +286,11 @@ static int check_probe_args(const pbgpu_index *ix, const int32_t *c, const int32
 }  // extern "C"
 
 namespace pbgpu {
+// probes per thread in the fast count kernels (PBGPU_ITEMS=1|2; default 2)
+static int sweep_items() {
+  static int v = [] { const char *e = getenv("PBGPU_ITEMS"); return (e && e[0] == '1') ? 1 : 2; }();
+  return v;
+}
 template <typename OutT>
 int count_overlaps_impl(const pbgpu_index *ix, const int32_t *d_contig, const int32_t *d_start, const int32_t *d_end, int64_t n,
                         int filter_op, OutT *d_counts, cudaStream_t s) {
@@ -297,8 +301,15 @@ int count_overlaps_impl(const pbgpu_index *ix, const int32_t *d_contig, const in
   const unsigned grid = (unsigned)cdiv(n, kSweepThreads);
   const bool strict = filter_op == PBGPU_FILTER_STRICT;
   if (ix->fast) {
-    if (strict) PB_LAUNCH((count_overlaps_fast_kernel<true, OutT>), grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, d_counts);
-    else PB_LAUNCH((count_overlaps_fast_kernel<false, OutT>), grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, d_counts);
+    const int items = sweep_items();
+    const unsigned g2 = (unsigned)cdiv(n, kSweepThreads * 2);
+    if (items == 2) {
+      if (strict) PB_LAUNCH((count_overlaps_fast_kernel<true, OutT, 2>), g2, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, d_counts);
+      else PB_LAUNCH((count_overlaps_fast_kernel<false, OutT, 2>), g2, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, d_counts);
+    } else {
+      if (strict) PB_LAUNCH((count_overlaps_fast_kernel<true, OutT, 1>), grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, d_counts);
+      else PB_LAUNCH((count_overlaps_fast_kernel<false, OutT, 1>), grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, d_counts);
+    }
   } else {
     if (strict) PB_LAUNCH((count_overlaps_kernel<true, OutT>), grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, d_counts);
     else PB_LAUNCH((count_overlaps_kernel<false, OutT>), grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, d_counts);
@@ -390,10 +401,15 @@ int pbgpu_overlap_count(const pbgpu_index *ix, const int32_t *d_contig, const in
   g_ev.mark(EV_P1_0, s);
   const unsigned grid = (unsigned)p->nblk;
   if (ix->fast) {
-    if (filter_op == PBGPU_FILTER_STRICT)
-      PB_LAUNCH(overlap_count_fast_kernel<true>, grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->his, p->block_base);
-    else
-      PB_LAUNCH(overlap_count_fast_kernel<false>, grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->his, p->block_base);
+    const bool strict = filter_op == PBGPU_FILTER_STRICT;
+    const unsigned g2 = (unsigned)cdiv(n, kSweepThreads * 2);
+    if (sweep_items() == 2) {
+      if (strict) PB_LAUNCH((overlap_count_fast_kernel<true, 2>), g2, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->his, p->block_base);
+      else PB_LAUNCH((overlap_count_fast_kernel<false, 2>), g2, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->his, p->block_base);
+    } else {
+      if (strict) PB_LAUNCH((overlap_count_fast_kernel<true, 1>), grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->his, p->block_base);
+      else PB_LAUNCH((overlap_count_fast_kernel<false, 1>), grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->his, p->block_base);
+    }
   } else if (filter_op == PBGPU_FILTER_STRICT)
     PB_LAUNCH(overlap_count_kernel<true>, grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->block_base);
   else

@@ -160,7 +160,7 @@ __device__ __forceinline__ uint32_t dir_rank(const DirRec *__restrict__ dir, con
   // one 256-bit request per record (LDG.E.256): two 128-bit loads cost two L2 sector requests each time the
   // first is still in flight; no L1 allocation -- the directory is touched at random, nothing is reused
   uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
-  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+  asm("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
                : "l"(dir + b));
   if (!(r0 & 0x80000000u)) {
@@ -223,42 +223,66 @@ __device__ __forceinline__ bool fast_window(const IndexView &ix, int32_t c, int3
   return true;
 }
 
-template <bool STRICT, typename OutT>  // OutT: int64_t (the ABI's count column) or uint32_t (half the D2H for the Arrow bridge)
+// ITEMS probes per thread (strided by the block size, so loads stay coalesced): their directory lookups are
+// independent, which keeps more L2 requests in flight per warp.
+template <bool STRICT, typename OutT, int ITEMS>  // OutT: int64_t (the ABI's count column) or uint32_t (half the D2H for the Arrow bridge)
 __global__ void __launch_bounds__(kSweepThreads) count_overlaps_fast_kernel(IndexView ix, const int32_t *__restrict__ pc,
                                                                             const int32_t *__restrict__ ps,
                                                                             const int32_t *__restrict__ pe, int64_t n,
                                                                             OutT *__restrict__ counts) {
-  int64_t i = (int64_t)blockIdx.x * kSweepThreads + threadIdx.x;
-  if (i >= n) return;
-  uint32_t hi;
-  counts[i] = (OutT)fast_count<STRICT>(ix, pc[i], ps[i], pe[i], hi);
+  const int64_t base = (int64_t)blockIdx.x * (kSweepThreads * ITEMS) + threadIdx.x;
+  int32_t c[ITEMS], s[ITEMS], e[ITEMS];
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const int64_t i = base + (int64_t)j * kSweepThreads;
+    const bool ok = i < n;
+    c[j] = ok ? pc[i] : -1; s[j] = ok ? ps[i] : 0; e[j] = ok ? pe[i] : 0;
+  }
+  uint32_t cnt[ITEMS];
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) { uint32_t hi; cnt[j] = fast_count<STRICT>(ix, c[j], s[j], e[j], hi); }
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const int64_t i = base + (int64_t)j * kSweepThreads;
+    if (i < n) counts[i] = (OutT)cnt[j];
+  }
 }
 
-template <bool STRICT>
+template <bool STRICT, int ITEMS>
 __global__ void __launch_bounds__(kSweepThreads) overlap_count_fast_kernel(IndexView ix, const int32_t *__restrict__ pc,
                                                                            const int32_t *__restrict__ ps,
                                                                            const int32_t *__restrict__ pe, int64_t n,
                                                                            uint32_t *__restrict__ counts, uint32_t *__restrict__ his,
-                                                                           unsigned long long *__restrict__ block_totals) {
-  __shared__ unsigned long long wt[kSweepThreads / 32];
-  int64_t i = (int64_t)blockIdx.x * kSweepThreads + threadIdx.x;
-  uint32_t cnt = 0;
-  if (i < n) {
-    uint32_t hi;
-    cnt = fast_count<STRICT>(ix, pc[i], ps[i], pe[i], hi);
-    counts[i] = cnt;
-    his[i] = hi;
-  }
-  unsigned long long v = cnt;
+                                                                           unsigned long long *__restrict__ block_totals /*[ITEMS per block]*/) {
+  __shared__ unsigned long long wt[ITEMS][kSweepThreads / 32];
+  const int64_t base = (int64_t)blockIdx.x * (kSweepThreads * ITEMS) + threadIdx.x;
+  int32_t c[ITEMS], s[ITEMS], e[ITEMS];
 #pragma unroll
-  for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-  if ((threadIdx.x & 31) == 0) wt[threadIdx.x >> 5] = v;
+  for (int j = 0; j < ITEMS; ++j) {
+    const int64_t i = base + (int64_t)j * kSweepThreads;
+    const bool ok = i < n;
+    c[j] = ok ? pc[i] : -1; s[j] = ok ? ps[i] : 0; e[j] = ok ? pe[i] : 0;
+  }
+  uint32_t cnt[ITEMS], hi[ITEMS];
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) cnt[j] = fast_count<STRICT>(ix, c[j], s[j], e[j], hi[j]);
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const int64_t i = base + (int64_t)j * kSweepThreads;
+    if (i < n) { counts[i] = cnt[j]; his[i] = hi[j]; }
+    unsigned long long v = i < n ? cnt[j] : 0;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) == 0) wt[j][threadIdx.x >> 5] = v;
+  }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  // pass 2 works on 256-probe blocks: one total per 256 consecutive probes
+  if (threadIdx.x < ITEMS) {
     unsigned long long t = 0;
 #pragma unroll
-    for (int w = 0; w < kSweepThreads / 32; ++w) t += wt[w];
-    block_totals[blockIdx.x] = t;
+    for (int w = 0; w < kSweepThreads / 32; ++w) t += wt[threadIdx.x][w];
+    const int64_t blk = (int64_t)blockIdx.x * ITEMS + threadIdx.x;
+    if (blk * kSweepThreads < n) block_totals[blk] = t;
   }
 }
 
@@ -423,7 +447,7 @@ __global__ void __launch_bounds__(kSweepThreads) nearest_kernel(IndexView ix, co
         lg_lo = g;
         lcur = lg_lo;
       }
-      lpos = (int32_t)__ldg(ix.en_pos + lcur);
+      lpos = ix.en_pos ? (int32_t)__ldg(ix.en_pos + lcur) : lcur;  // NULL: end order == start order
       const int32_t bs = __ldg(ix.st + lpos), be = __ldg(ix.en + lpos);
       if (is_hit<STRICT>(qs, qe, bs, be)) { ++lcur; continue; }
       have_l = true;
