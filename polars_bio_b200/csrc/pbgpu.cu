@@ -288,7 +288,7 @@ static int check_probe_args(const pbgpu_index *ix, const int32_t *c, const int32
 namespace pbgpu {
 // probes per thread in the fast count kernels (PBGPU_ITEMS=1|2; default 2)
 static int sweep_items() {
-  static int v = [] { const char *e = getenv("PBGPU_ITEMS"); return (e && e[0] == '1') ? 1 : 2; }();
+  static int v = [] { const char *e = getenv("PBGPU_ITEMS"); return (e && e[0] == '1') ? 1 : ((e && e[0] == '4') ? 4 : 2); }();
   return v;
 }
 template <typename OutT>
@@ -302,8 +302,11 @@ int count_overlaps_impl(const pbgpu_index *ix, const int32_t *d_contig, const in
   const bool strict = filter_op == PBGPU_FILTER_STRICT;
   if (ix->fast) {
     const int items = sweep_items();
-    const unsigned g2 = (unsigned)cdiv(n, kSweepThreads * 2);
-    if (items == 2) {
+    const unsigned g2 = (unsigned)cdiv(n, kSweepThreads * 2), g4 = (unsigned)cdiv(n, kSweepThreads * 4);
+    if (items == 4) {
+      if (strict) PB_LAUNCH((count_overlaps_fast_kernel<true, OutT, 4>), g4, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, d_counts);
+      else PB_LAUNCH((count_overlaps_fast_kernel<false, OutT, 4>), g4, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, d_counts);
+    } else if (items == 2) {
       if (strict) PB_LAUNCH((count_overlaps_fast_kernel<true, OutT, 2>), g2, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, d_counts);
       else PB_LAUNCH((count_overlaps_fast_kernel<false, OutT, 2>), g2, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, d_counts);
     } else {
@@ -402,8 +405,11 @@ int pbgpu_overlap_count(const pbgpu_index *ix, const int32_t *d_contig, const in
   const unsigned grid = (unsigned)p->nblk;
   if (ix->fast) {
     const bool strict = filter_op == PBGPU_FILTER_STRICT;
-    const unsigned g2 = (unsigned)cdiv(n, kSweepThreads * 2);
-    if (sweep_items() == 2) {
+    const unsigned g2 = (unsigned)cdiv(n, kSweepThreads * 2), g4 = (unsigned)cdiv(n, kSweepThreads * 4);
+    if (sweep_items() == 4) {
+      if (strict) PB_LAUNCH((overlap_count_fast_kernel<true, 4>), g4, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->his, p->block_base);
+      else PB_LAUNCH((overlap_count_fast_kernel<false, 4>), g4, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->his, p->block_base);
+    } else if (sweep_items() == 2) {
       if (strict) PB_LAUNCH((overlap_count_fast_kernel<true, 2>), g2, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->his, p->block_base);
       else PB_LAUNCH((overlap_count_fast_kernel<false, 2>), g2, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->his, p->block_base);
     } else {

@@ -301,11 +301,11 @@ __global__ void __launch_bounds__(kSweepThreads) overlap_emit_fast_kernel(IndexV
                                                                           uint32_t *__restrict__ out_build) {
   __shared__ unsigned long long wt[kSweepThreads / 32 + 1];
   const int64_t i = (int64_t)blockIdx.x * kSweepThreads + threadIdx.x;
-  const uint32_t cnt = i < n ? counts[i] : 0u;
-  const unsigned long long pos = block_base[blockIdx.x] + block_exclusive<SumU64, kSweepThreads>((unsigned long long)cnt, wt);
-  uint32_t hi = 0;
+  // all three coalesced loads are issued before the block scan so their latency hides behind it
+  uint32_t cnt = 0, hi = 0;
   int32_t s = 0;
-  if (cnt) { hi = his[i]; s = ps[i]; }
+  if (i < n) { cnt = counts[i]; hi = his[i]; s = ps[i]; }
+  const unsigned long long pos = block_base[blockIdx.x] + block_exclusive<SumU64, kSweepThreads>((unsigned long long)cnt, wt);
   const bool generic = cnt && hi == kGenericProbe;
   const bool heavy = cnt >= kHeavyCount && !generic;
   if (generic) {  // rare: empty / inverted probe interval
@@ -318,10 +318,12 @@ __global__ void __launch_bounds__(kSweepThreads) overlap_emit_fast_kernel(IndexV
   } else if (cnt && !heavy) {
     uint32_t k = 0;
     for (int64_t j = (int64_t)hi - 1; k < cnt && j >= 0; --j) {
-      if (end_hits<STRICT>(__ldg(ix.en + j), s)) {
+      const int32_t ev = __ldg(ix.en + j);
+      const uint32_t rv = __ldg(ix.row + j);  // speculative: without nesting every candidate is a hit, and the two
+      if (end_hits<STRICT>(ev, s)) {          // loads then overlap instead of chaining
         const unsigned long long p = pos + (cnt - 1 - k);
         out_probe[p] = (uint32_t)i;
-        out_build[p] = __ldg(ix.row + j);
+        out_build[p] = rv;
         ++k;
       }
     }
