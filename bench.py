@@ -98,7 +98,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
         except Exception:
@@ -130,7 +130,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": "warm-up + timed steps (+ up to 0.4 s of the same step)"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -232,14 +232,16 @@ def run_sharded(args, world, rank, dev):
         ix.close()
         return cnt, a, b
 
+    # clocks are sampled from the warm-up on (same workload, same load): the timed region alone can be shorter than
+    # one nvidia-smi sampling period
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         cnt, a, b = step()
     pairs = a.numel()
     assert int(cnt.sum()) == pairs
     del cnt, a, b
-    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
     dist.barrier(); torch.cuda.synchronize()
-    sampler.start()
     launches0 = _native.launch_count()
     step_ms, xchg_ms = [], []
     for _ in range(args.steps):
@@ -254,6 +256,9 @@ def run_sharded(args, world, rank, dev):
     km = _native.stage_times()
     xtrace = []
     step(trace=xtrace)  # one extra, untimed step with host-side laps of the exchange
+    t_end = time.perf_counter() + 0.4
+    while len(sampler.lines) < 3 and time.perf_counter() < t_end:  # keep the GPU under the same load until sampled
+        step()
     dist.barrier(); torch.cuda.synchronize()
     clocks = sampler.stop()
     t = torch.tensor([float(np.sum(step_ms)), float(np.sum(xchg_ms))], device=dev, dtype=torch.float64)
@@ -338,6 +343,10 @@ def main():
         ix.close()
         return cnt, a, b
 
+    # clocks are sampled from the warm-up on (same workload, same load): the timed region alone can be shorter than
+    # one nvidia-smi sampling period
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         cnt, a, b = step_device()
     pairs = a.numel()
@@ -349,9 +358,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
     launches0 = _native.launch_count()
     step_ms, stage_ms, kern_ns = [], [], []
     for _ in range(args.steps):
@@ -366,6 +373,9 @@ def main():
         kern_ns.append(_native.stage_times())  # the library's own events around each kernel of this step
         del cnt, a, b
     launches = _native.launch_count() - launches0
+    t_end = time.perf_counter() + 0.4
+    while len(sampler.lines) < 3 and time.perf_counter() < t_end:  # keep the GPU under the same load until sampled
+        step_device()
     barrier()
     clocks = sampler.stop()
     total_ms = float(np.sum(step_ms))
