@@ -87,6 +87,6 @@ def test_sharded_join_two_gpus_matches_oracle():
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                        "--master-port", str(_free_port()), os.path.join(root, "scripts", "dist_check.py")], capture_output=True, text=True, timeout=600)
+                        "--master-port", str(_free_port()), os.path.join(root, "tests", "tools", "dist_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "DIST_CHECK_OK" in r.stdout
