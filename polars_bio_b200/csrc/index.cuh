@@ -247,16 +247,16 @@ __global__ void __launch_bounds__(256) build_dir_kernel(const uint32_t *__restri
   if (b > n_buckets) return;  // record n_buckets is the sentinel
   DirRec r;
   if (b == n_buckets) { r.base = (uint32_t)m; for (int k = 0; k < 7; ++k) r.key[k] = kDirPad; dir[b] = r; return; }
-  const uint64_t lo_key = (uint64_t)b << shift;
-  int64_t lo = 0, hi = m;
-  while (lo < hi) { int64_t mid = lo + ((hi - lo) >> 1); if ((uint64_t)g[mid] < lo_key) lo = mid + 1; else hi = mid; }
-  r.base = (uint32_t)lo;
+  const uint32_t lo_key = b << shift;  // < 2^32: the axis is shorter than 2^32 on this path; m < 2^31 -> 32-bit search
+  uint32_t lo = 0, hi = (uint32_t)m;
+  while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (__ldg(g + mid) < lo_key) lo = mid + 1; else hi = mid; }
+  r.base = lo;
 #pragma unroll
   for (int k = 0; k < 7; ++k) {
-    uint32_t v = (lo + k < m) ? g[lo + k] : kDirPad;
+    uint32_t v = (lo + k < (uint32_t)m) ? __ldg(g + lo + k) : kDirPad;
     r.key[k] = (v != kDirPad && (v >> shift) == b) ? v : kDirPad;
   }
-  if (lo + 7 < m && (g[lo + 7] >> shift) == b) r.base |= 0x80000000u;
+  if (lo + 7 < (uint32_t)m && (__ldg(g + lo + 7) >> shift) == b) r.base |= 0x80000000u;
   dir[b] = r;
 }
 

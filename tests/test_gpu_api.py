@@ -207,3 +207,57 @@ def test_errors_do_not_abort():
     bad = pa.table({"chrom": [1, 2], "start": [1, 2], "end": [3, 4]})
     with pytest.raises(pb._native.PbgpuError, match="unsupported type"):
         pb.overlap(pb.set_coordinate_system(bad, True), pb.set_coordinate_system(bad, True), output_type="pyarrow.Table")
+
+
+def test_string_view_and_binary_payload_and_nearest_pairs():
+    # utf8_view contig + payload come back as large_utf8; emit=1 for nearest yields (left_row, right_row?, distance?)
+    left = pa.table({"chrom": pa.array(["chr1", "chr1", "chr2", "chr9"]).cast(pa.string_view()),
+                     "start": pa.array([100, 500, 100, 5], pa.int32()), "end": pa.array([200, 600, 200, 9], pa.int32()),
+                     "tag": pa.array(["a-long-tag-beyond-12-bytes", "b", None, "d"]).cast(pa.string_view()),
+                     "blob": pa.array([b"\x00\x01", b"", b"xyz", None], pa.binary())})
+    right = pa.table({"chrom": ["chr1", "chr1", "chr2"], "start": pa.array([150, 900, 50], pa.int64()),
+                      "end": pa.array([160, 950, 120], pa.int64()), "w": pa.array([1.5, 2.5, None], pa.float32())})
+    left = pb.set_coordinate_system(left, True); right = pb.set_coordinate_system(right, True)
+    res = pb.overlap(left, right, output_type="pyarrow.Table")
+    assert res.schema.field("chrom_1").type == pa.large_string() and res.schema.field("tag_1").type == pa.large_string()
+    assert res.schema.field("blob_1").type == pa.binary() and res.schema.field("start_2").type == pa.int64()
+    got = sorted(zip(res["chrom_1"].to_pylist(), res["start_1"].to_pylist(), res["tag_1"].to_pylist(), res["blob_1"].to_pylist(),
+                     res["start_2"].to_pylist(), res["w_2"].to_pylist()), key=lambda r: (r[0], r[1]))
+    assert got == [("chr1", 100, "a-long-tag-beyond-12-bytes", b"\x00\x01", 150, 1.5), ("chr2", 100, None, b"xyz", 50, None)]
+    near = pb.nearest(left, right, output_type="pyarrow.Table")
+    assert near.num_rows == 4
+    d = dict(zip(near["start_1"].to_pylist(), near["distance"].to_pylist()))
+    assert d == {100: 0, 500: 300, 5: None}  # chr1/chr2 probes at start 100 both overlap; chr9 has no indexed rows -> null
+    from polars_bio_b200 import FilterOp, RangeOp, RangeOptions, range_operation_frame
+
+    ro = RangeOptions(range_op=RangeOp.Nearest, filter_op=FilterOp.Strict, nearest_k=2)
+    pairs = range_operation_frame(pb.ctx, left, right, ro, emit=1).to_arrow()
+    assert pairs.schema.names == ["left_row", "right_row", "distance"]
+    assert pairs["left_row"].to_pylist() == [0, 0, 1, 1, 2, 3]
+    assert pairs["right_row"].to_pylist() == [0, 1, 1, 0, 2, None]     # row 1: downstream variant (300) before upstream (340)
+    assert pairs["distance"].to_pylist() == [0, 700, 300, 340, 0, None]
+
+
+def test_count_overlaps_passthrough_multibatch_low_memory():
+    # the iterated table's columns are re-exported zero-copy: input batch boundaries and sliced views must line up
+    fx = FX["count_overlaps"]
+    d1 = pd.DataFrame(fx["df1"]); d1["payload"] = [f"row{i}" for i in range(len(d1))]
+    t1 = pa.concat_tables([pa.Table.from_pandas(d1.iloc[:4], preserve_index=False), pa.Table.from_pandas(d1.iloc[4:9], preserve_index=False),
+                           pa.Table.from_pandas(d1.iloc[9:], preserve_index=False)])
+    t2 = pa.Table.from_pandas(pd.DataFrame(fx["df2"]), preserve_index=False)
+    t1 = pb.set_coordinate_system(t1, False); t2 = pb.set_coordinate_system(t2, False)
+    from polars_bio_b200 import FilterOp, RangeOp, RangeOptions, range_operation_frame
+
+    ro = RangeOptions(range_op=RangeOp.CountOverlapsNaive, filter_op=FilterOp.Weak, columns_1=list(COLS), columns_2=list(COLS))
+    pb.set_option("datafusion.execution.batch_size", 3)
+    try:
+        ro.overlap_low_memory = True
+        batches = list(range_operation_frame(pb.ctx, t2, t1, ro).execute_stream())   # engine order: (indexed, iterated)
+    finally:
+        pb.set_option("datafusion.execution.batch_size", 8192)
+    assert [b.num_rows for b in batches] == [4, 5, 2]  # cap 3 is rounded up to 8 rows: slices follow the input batches
+    got = pa.Table.from_batches(batches).to_pandas()
+    assert got["payload"].tolist() == d1["payload"].tolist()
+    assert got["count"].tolist() == fx["expected"]["count"]
+    lim = range_operation_frame(pb.ctx, t2, t1, ro, limit=6).to_arrow()
+    assert lim.num_rows == 6 and lim["payload"].to_pylist() == d1["payload"].tolist()[:6]
