@@ -1,0 +1,112 @@
+"""CPU-only tests of the Arrow-level host code (polars_bio_b200/csrc/arrow_bridge.cpp): the product source is compiled
+with a stub CUDA header plus a small harness (tests/tools/bridge_harness/) so that stream draining, contig dictionary
+encoding, position narrowing and the materialisation code (two-phase gather of fixed-width / bool / utf8 / large_utf8 /
+binary / utf8_view / dictionary columns, nulls, NO_PARTNER rows, chunked inputs) run without a GPU."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pyarrow as pa
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HARNESS = os.path.join(ROOT, "tests", "tools", "bridge_harness")
+
+
+class _CS(ctypes.Structure):
+    _fields_ = [("get_schema", ctypes.c_void_p), ("get_next", ctypes.c_void_p), ("get_last_error", ctypes.c_void_p),
+                ("release", ctypes.c_void_p), ("private_data", ctypes.c_void_p)]
+
+
+@pytest.fixture(scope="module")
+def lib(tmp_path_factory):
+    d = tmp_path_factory.mktemp("bridge")
+    src = open(os.path.join(ROOT, "polars_bio_b200", "csrc", "arrow_bridge.cpp")).read()
+    assert "#include <cuda_runtime.h>" in src
+    src = src.replace("#include <cuda_runtime.h>", '#include "stub_cuda.h"') + open(os.path.join(HARNESS, "harness_tail.inc")).read()
+    cpp = d / "bridge_host.cpp"
+    cpp.write_text(src)
+    so = d / "libbridge_host.so"
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    r = subprocess.run([cxx, "-std=c++17", "-O1", "-fPIC", "-shared", "-I", HARNESS, "-I", os.path.join(ROOT, "include"),
+                        "-I", os.path.join(ROOT, "polars_bio_b200", "csrc"), "-o", str(so), str(cpp), "-lpthread"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    L = ctypes.CDLL(str(so))
+    L.dbg_roundtrip.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64,
+                                ctypes.c_void_p, ctypes.c_void_p]
+    return L
+
+
+def _roundtrip(lib, table, rows, cols=("chrom", "start", "end")):
+    s_in, s_out = _CS(), _CS()
+    table.to_reader()._export_to_c(ctypes.addressof(s_in))
+    rows = np.asarray(rows, dtype=np.uint32)
+    keys = np.zeros((table.num_rows, 3), dtype=np.int32)
+    rc = lib.dbg_roundtrip(ctypes.addressof(s_in), *(c.encode() for c in cols), rows.ctypes.data, len(rows), keys.ctypes.data,
+                           ctypes.addressof(s_out))
+    assert rc == 0, rc
+    return pa.RecordBatchReader._import_from_c(ctypes.addressof(s_out)).read_all(), keys
+
+
+def test_gather_all_supported_types_with_nulls_and_missing_partner(lib):
+    t = pa.table({
+        "chrom": pa.array(["chr1", "chr1", "chr2", None, "chr9"], type=pa.string_view()),
+        "start": pa.array([100, 500, 100, 7, 5], pa.int64()), "end": pa.array([200, 600, None, 9, 9], pa.uint32()),
+        "tag": pa.array(["a-long-tag-beyond-12-bytes", "b", None, "", "d"], type=pa.string_view()),
+        "blob": pa.array([b"\x00\x01", b"", b"xyz", None, b"q"], pa.binary()),
+        "big": pa.array(["L0", None, "L2", "L3", "L4"], pa.large_string()),
+        "f": pa.array([1.5, None, 3.5, 4.5, 5.5], pa.float64()), "b": pa.array([True, False, None, True, False]),
+        "i8": pa.array([1, 2, 3, None, 5], pa.int8()), "ts": pa.array([1, 2, 3, 4, None], pa.timestamp("us")),
+        "cat": pa.array(["x", "y", "x", None, "y"]).dictionary_encode(),
+    })
+    rows = [4, 0, 0xFFFFFFFF, 2, 3, 1]
+    out, keys = _roundtrip(lib, t, rows)
+    # keys: shared dictionary codes in order of first appearance; null contig / null position -> code -1
+    assert keys[:, 0].tolist() == [0, 0, -1, -1, 2] or keys[:, 0].tolist() == [0, 0, -1, -1, 1]
+    assert keys[0].tolist()[1:] == [100, 200] and keys[1].tolist()[1:] == [500, 600]
+    exp = t.to_pylist()
+    want = [exp[r] if r != 0xFFFFFFFF else {k: None for k in t.column_names} for r in rows]
+    assert out.to_pylist() == want
+    assert out.schema.field("chrom").type == pa.large_string() and out.schema.field("tag").type == pa.large_string()
+    assert out.schema.field("cat").type == pa.large_string()            # dictionary<string> is decoded
+    assert out.schema.field("blob").type == pa.binary() and out.schema.field("ts").type == pa.timestamp("us")
+    assert out.schema.field("start").type == pa.int64() and out.schema.field("end").type == pa.uint32()
+
+
+def test_chunked_input_and_many_rows(lib):
+    rng = np.random.default_rng(0)
+    n = 50_000
+    parts = []
+    for k in range(5):
+        m = n // 5
+        parts.append(pa.table({"chrom": pa.array(rng.choice(["chr1", "chr2", "chrX"], m)), "start": pa.array(rng.integers(0, 10**6, m), pa.int32()),
+                               "end": pa.array(rng.integers(0, 10**6, m), pa.int32()),
+                               "name": pa.array([f"r{k}_{i}" if i % 17 else None for i in range(m)])}))
+    t = pa.concat_tables(parts)
+    assert t.column("chrom").num_chunks == 5
+    rows = rng.integers(0, n, 200_000).astype(np.uint32)
+    rows[::1000] = 0xFFFFFFFF
+    out, keys = _roundtrip(lib, t, rows)
+    names = t.column("chrom").to_pylist()
+    codes = {}
+    for nm, c in zip(names, keys[:, 0]):
+        assert codes.setdefault(nm, int(c)) == int(c)                    # one code per contig string
+    assert len(set(codes.values())) == 3
+    assert np.array_equal(keys[:, 1], t.column("start").to_numpy()) and np.array_equal(keys[:, 2], t.column("end").to_numpy())
+    ref = t.to_pandas()
+    got = out.to_pandas()
+    ok = rows != 0xFFFFFFFF
+    assert got["name"][ok].tolist() == ref["name"].to_numpy()[rows[ok]].tolist()
+    assert got["start"][ok].astype("int64").tolist() == ref["start"].to_numpy()[rows[ok]].tolist()
+    assert got["start"][~ok].isna().all() and got["chrom"][~ok].isna().all()
+
+
+def test_int32_domain_check(lib):
+    t = pa.table({"chrom": ["chr1"], "start": pa.array([2**31], pa.int64()), "end": pa.array([2**31 + 5], pa.int64())})
+    s_in, s_out = _CS(), _CS()
+    t.to_reader()._export_to_c(ctypes.addressof(s_in))
+    rows = np.zeros(1, np.uint32)
+    rc = lib.dbg_roundtrip(ctypes.addressof(s_in), b"chrom", b"start", b"end", rows.ctypes.data, 1, None, ctypes.addressof(s_out))
+    assert rc == 4  # PBGPU_ERANGE

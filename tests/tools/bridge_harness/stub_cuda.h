@@ -1,0 +1,24 @@
+// host-only stand-ins for the few CUDA runtime calls arrow_bridge.cpp makes (TEST INFRASTRUCTURE)
+// host-only debug stubs
+#pragma once
+#include <stdlib.h>
+#include <stdint.h>
+typedef int cudaError_t; typedef void* cudaStream_t;
+#define cudaSuccess 0
+#define cudaHostAllocPortable 1
+#define cudaHostAllocWriteCombined 4
+#define cudaStreamNonBlocking 1
+#define cudaMemcpyHostToDevice 1
+#define cudaMemcpyDeviceToHost 2
+static inline cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { *p = malloc(n); return *p ? 0 : 1; }
+static inline cudaError_t cudaFreeHost(void* p) { free(p); return 0; }
+static inline cudaError_t cudaGetLastError() { return 0; }
+static inline const char* cudaGetErrorString(cudaError_t) { return "stub"; }
+static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }
+static inline cudaError_t cudaSetDevice(int) { return 0; }
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = 0; return 1; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
+static inline cudaError_t cudaMallocAsync(void** p, size_t n, cudaStream_t) { *p = malloc(n); return 0; }
+static inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { free(p); return 0; }
+static inline cudaError_t cudaMemcpyAsync(void*, const void*, size_t, int, cudaStream_t) { return 0; }
