@@ -103,6 +103,31 @@ def test_chunked_input_and_many_rows(lib):
     assert got["start"][~ok].isna().all() and got["chrom"][~ok].isna().all()
 
 
+def test_count_passthrough_views_follow_input_batches(lib):
+    # count_overlaps / coverage re-export the iterated table zero-copy: output batches = slices (<= 8 rows here) of the
+    # input batches, sliced offsets must address the right rows for every type, incl. nested ones the gather cannot do
+    parts = [pa.table({"chrom": pa.array([f"c{i % 3}" for i in range(lo, hi)]), "start": pa.array(range(lo, hi), pa.int32()),
+                       "end": pa.array(range(lo + 5, hi + 5), pa.int32()), "name": pa.array([None if i % 4 == 0 else f"n{i}" for i in range(lo, hi)]),
+                       "lst": pa.array([[i, i + 1] for i in range(lo, hi)], pa.list_(pa.int32()))})
+             for lo, hi in ((0, 5), (5, 25), (25, 31))]
+    t = pa.concat_tables(parts)
+    s_in, s_out = _CS(), _CS()
+    t.to_reader()._export_to_c(ctypes.addressof(s_in))
+    rc = lib.dbg_roundtrip(ctypes.addressof(s_in), b"chrom", b"start", b"end", None, -1, None, ctypes.addressof(s_out))
+    assert rc == 0
+    batches = list(pa.RecordBatchReader._import_from_c(ctypes.addressof(s_out)))
+    assert [b.num_rows for b in batches] == [5, 8, 8, 4, 6]
+    out = pa.Table.from_batches(batches)
+    assert out.column_names == t.column_names + ["count"]
+    assert out.drop(["count"]).to_pylist() == t.to_pylist()
+    assert out["count"].to_pylist() == [10 * i for i in range(31)]
+    s_in, s_out = _CS(), _CS()
+    t.to_reader()._export_to_c(ctypes.addressof(s_in))
+    assert lib.dbg_roundtrip(ctypes.addressof(s_in), b"chrom", b"start", b"end", None, 7, None, ctypes.addressof(s_out)) == 0   # limit = 7
+    lim = pa.RecordBatchReader._import_from_c(ctypes.addressof(s_out)).read_all()
+    assert lim.num_rows == 7 and lim["start"].to_pylist() == list(range(7))
+
+
 def test_int32_domain_check(lib):
     t = pa.table({"chrom": ["chr1"], "start": pa.array([2**31], pa.int64()), "end": pa.array([2**31 + 5], pa.int64())})
     s_in, s_out = _CS(), _CS()
