@@ -13,12 +13,17 @@
 //   en_pos            position in (st,en,row) order of every en_sorted entry (nearest upstream)
 // Fast path (no inverted rows, total coordinate span < 2^32): every contig is shifted to its own slice of
 // one global uint32 axis (G(c,p) = off[c] + clamp(p, lo_c-1, hi_c+1) - (lo_c-1)), which makes the two sorted
-// arrays globally monotone, and each gets a bucketed *rank directory*:
+// arrays globally monotone, and both share ONE bucketed *joint rank directory*:
 //   gs, ge            global-axis starts (start order) / ends (end order), uint32[m]
-//   dir_s, dir_e      one 32-byte record per 2^shift-wide bucket of the axis: {rank of the bucket's first
-//                     entry | overflow flag, the bucket's first 7 keys (0xFFFFFFFF padded)}
-//                     -> rank(x) = base + #{keys < x}: ONE 32-byte sector per query instead of a 20-step
-//                     binary search; buckets holding more than 7 keys fall back to a search inside the bucket.
+//   jdir              one 32-byte record per W = 2^shift wide bucket b of the axis (JRec below): the rank of the
+//                     bucket's first start and first end, then up to 12 in-bucket keys as 15-bit offsets: the starts
+//                     of [bW, bW+2W) -- the record OVERLAPS the next bucket -- and the ends of [bW, bW+W).
+//                     A probe needs rank_S(a.end) and rank_E(a.start); a.start picks the bucket, and whenever
+//                     a.end < bW+2W (always when the probe is no longer than W) the same record answers both:
+//                     ONE random 32-byte sector per probe (the L1TEX t-stage serves one divergent request per
+//                     clock per SM, so requests per probe is what bounds the count kernels), no search.  Longer
+//                     probes read the record of a.end's bucket too; crowded buckets (more than 12 keys) keep the
+//                     rank range instead of keys and are searched.
 #pragma once
 #include "common.cuh"
 #include "radix_sort.cuh"
@@ -31,11 +36,19 @@ struct ContigMap {   // per contig: position of its slice on the global axis
   uint32_t off;      // global coordinate of lo_m1
   int32_t has;       // contig has indexed rows
 };
-struct alignas(32) DirRec {
-  uint32_t base;     // rank of the first entry of the bucket; bit 31 = bucket holds more than 7 entries
-  uint32_t key[7];
+// Joint rank record of bucket b (W = 2^shift, lo = b*W):
+//   w[0]  rank of the first start >= lo (#{gs < lo}); bit 31 = crowded
+//   normal : w[1] = #{ge < lo} - nS   (nS = number of start keys stored, so that w[1] + #{fields < 0x4000+t} is
+//                                      the end rank: every start field is < 0x4000)
+//            w[2..7] = 12 x 16-bit fields, ascending: starts of [lo, lo+2W) as (g - lo) < 0x4000, then ends of
+//                      [lo, lo+W) as 0x4000 | (g - lo), padded with 0x7FFF.  Bit 15 of every field is clear: that
+//                      is the guard bit of the packed compare in jrec_nlt().
+//   crowded: w[1] = #{ge < lo}, w[2] = #{gs < lo+2W}, w[3] = #{ge < lo+W}: rank ranges to search inside
+struct alignas(32) JRec {
+  uint32_t w[8];
 };
-constexpr uint32_t kDirPad = 0xFFFFFFFFu;
+constexpr int kJKeys = 12;
+constexpr int kJMaxShift = 13;  // 2W <= 0x4000
 }  // namespace pbgpu
 
 struct pbgpu_index {
@@ -53,7 +66,8 @@ struct pbgpu_index {
   uint32_t n_buckets = 0;
   pbgpu::ContigMap *cmap = nullptr;
   uint32_t *gs = nullptr, *ge = nullptr;
-  pbgpu::DirRec *dir_s = nullptr, *dir_e = nullptr;
+  pbgpu::JRec *jdir = nullptr;
+  uint2 *er = nullptr;  // (end, row) interleaved in start order: one 8-byte load per emitted pair in pass 2
   void *slab = nullptr, *slab2 = nullptr, *slab_n = nullptr;  // stream-ordered allocations backing every array above
   // without nested intervals pmax and en_sorted alias `en` and en_pos is NULL (= identity)
   size_t bytes = 0;
@@ -65,8 +79,8 @@ struct IndexView {
   const ContigMap *__restrict__ cmap;
   const uint32_t *__restrict__ gs;
   const uint32_t *__restrict__ ge;
-  const DirRec *__restrict__ dir_s;
-  const DirRec *__restrict__ dir_e;
+  const JRec *__restrict__ jdir;
+  const uint2 *__restrict__ er;
   int shift;
   const int32_t *__restrict__ seg;
   const int32_t *__restrict__ st;
@@ -80,7 +94,7 @@ struct IndexView {
 };
 
 inline IndexView view_of(const pbgpu_index *ix) {
-  return IndexView{ix->cmap, ix->gs, ix->ge, ix->dir_s, ix->dir_e, ix->shift, ix->seg, ix->st, ix->en, ix->pmax, ix->en_sorted, ix->row, ix->en_pos, ix->n_contigs, ix->has_inverted};
+  return IndexView{ix->cmap, ix->gs, ix->ge, ix->jdir, ix->er, ix->shift, ix->seg, ix->st, ix->en, ix->pmax, ix->en_sorted, ix->row, ix->en_pos, ix->n_contigs, ix->has_inverted};
 }
 
 struct BuildStats {  // device-side reduction target
@@ -155,7 +169,8 @@ __global__ void __launch_bounds__(256) make_start_keys_kernel(const int32_t *__r
 __global__ void __launch_bounds__(256) unpack_sorted_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ vals,
                                                             int64_t m, int pos_bits, uint32_t bias_s, int32_t n_contigs,
                                                             int32_t *__restrict__ st, int32_t *__restrict__ en,
-                                                            uint32_t *__restrict__ row, int32_t *__restrict__ seg,
+                                                            uint32_t *__restrict__ row, uint2 *__restrict__ er,
+                                                            int32_t *__restrict__ seg,
                                                             unsigned long long *__restrict__ inversions) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned inv = 0;
@@ -167,6 +182,7 @@ __global__ void __launch_bounds__(256) unpack_sorted_kernel(const uint64_t *__re
     st[i] = (int32_t)(sp ^ bias_s);
     en[i] = e;
     row[i] = (uint32_t)v;
+    er[i] = make_uint2((uint32_t)e, (uint32_t)v);
     long long prev = -1;
     if (i > 0) {
       prev = (long long)(keys[i - 1] >> pos_bits);
@@ -239,24 +255,53 @@ __global__ void __launch_bounds__(256) global_coord_kernel(const uint64_t *__res
   const ContigMap cm = cmap[keys[i] >> pos_bits];
   g[i] = cm.off + (uint32_t)((long long)pos[i] - cm.lo_m1);
 }
-// one thread per bucket: rank of its first entry by binary search (neighbouring buckets share their search
-// path, so the loads coalesce), then its first 7 keys
-__global__ void __launch_bounds__(256) build_dir_kernel(const uint32_t *__restrict__ g, int64_t m, int shift, uint32_t n_buckets,
-                                                        DirRec *__restrict__ dir) {
+// first index in [lo,hi) with g[idx] >= x (x may be 2^32: 64-bit compare)
+__device__ __forceinline__ uint32_t lower_bound_g(const uint32_t *__restrict__ g, uint32_t lo, uint32_t hi, uint64_t x) {
+  while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if ((uint64_t)__ldg(g + mid) < x) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+// one thread per bucket: ranks of its first start / first end by binary search (neighbouring buckets share their
+// search paths, so the loads coalesce), then the keys of its window packed into the record (JRec above)
+__global__ void __launch_bounds__(256) build_jdir_kernel(const uint32_t *__restrict__ gs, const uint32_t *__restrict__ ge, int64_t m,
+                                                         int shift, uint32_t n_buckets, JRec *__restrict__ dir) {
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b > n_buckets) return;  // record n_buckets is the sentinel
-  DirRec r;
-  if (b == n_buckets) { r.base = (uint32_t)m; for (int k = 0; k < 7; ++k) r.key[k] = kDirPad; dir[b] = r; return; }
-  const uint32_t lo_key = b << shift;  // < 2^32: the axis is shorter than 2^32 on this path; m < 2^31 -> 32-bit search
-  uint32_t lo = 0, hi = (uint32_t)m;
-  while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (__ldg(g + mid) < lo_key) lo = mid + 1; else hi = mid; }
-  r.base = lo;
-#pragma unroll
-  for (int k = 0; k < 7; ++k) {
-    uint32_t v = (lo + k < (uint32_t)m) ? __ldg(g + lo + k) : kDirPad;
-    r.key[k] = (v != kDirPad && (v >> shift) == b) ? v : kDirPad;
+  if (b > n_buckets) return;  // record n_buckets: every key is below it (only reached by thresholds == its lo)
+  const uint64_t lo = (uint64_t)b << shift, W = 1ull << shift;  // the axis is shorter than 2^32 on this path
+  const uint32_t mm = (uint32_t)m;
+  uint32_t ls = 0, hs = mm, le = 0, he = mm;  // two interleaved searches: their loads overlap
+  while (ls < hs || le < he) {
+    if (ls < hs) { const uint32_t mid = ls + ((hs - ls) >> 1); if ((uint64_t)__ldg(gs + mid) < lo) ls = mid + 1; else hs = mid; }
+    if (le < he) { const uint32_t mid = le + ((he - le) >> 1); if ((uint64_t)__ldg(ge + mid) < lo) le = mid + 1; else he = mid; }
   }
-  if (lo + 7 < (uint32_t)m && (__ldg(g + lo + 7) >> shift) == b) r.base |= 0x80000000u;
+  const uint32_t base_s = ls, base_e = le;
+  uint32_t ns = 0, ne = 0;  // keys of the window, counted up to one past the capacity
+  while (ns <= (uint32_t)kJKeys && base_s + ns < mm && (uint64_t)__ldg(gs + base_s + ns) < lo + 2 * W) ++ns;
+  while (ns + ne <= (uint32_t)kJKeys && base_e + ne < mm && (uint64_t)__ldg(ge + base_e + ne) < lo + W) ++ne;
+  JRec r;
+  if (ns + ne > (uint32_t)kJKeys) {  // crowded: keep the rank ranges
+    r.w[0] = base_s | 0x80000000u;
+    r.w[1] = base_e;
+    r.w[2] = lower_bound_g(gs, base_s + ns, mm, lo + 2 * W);
+    r.w[3] = lower_bound_g(ge, base_e + ne, mm, lo + W);
+    r.w[4] = r.w[5] = r.w[6] = r.w[7] = 0x7FFF7FFFu;
+  } else {
+    r.w[0] = base_s;
+    r.w[1] = base_e - ns;
+    const uint32_t lo32 = (uint32_t)lo;
+#pragma unroll
+    for (int k = 0; k < kJKeys / 2; ++k) {
+      uint32_t f[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t slot = 2 * k + h;
+        uint32_t v = 0x7FFFu;
+        if (slot < ns) v = __ldg(gs + base_s + slot) - lo32;
+        else if (slot < ns + ne) v = 0x4000u | (__ldg(ge + base_e + (slot - ns)) - lo32);
+        f[h] = v;
+      }
+      r.w[2 + k] = f[0] | (f[1] << 16);
+    }
+  }
   dir[b] = r;
 }
 

@@ -148,13 +148,15 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
   ix->has_inverted = hs.inverted != 0;
   // slab 1: seg + start-ordered rows
   const size_t seg_b = align_up(sizeof(int32_t) * ((size_t)n_contigs + 2)), arr_b = align_up(sizeof(int32_t) * (size_t)(m ? m : 1));
-  PB_TRY(dev_alloc(&ix->slab, seg_b + 3 * arr_b, s));
-  ix->bytes = seg_b + 3 * arr_b;
+  const size_t er_b = align_up(sizeof(uint2) * (size_t)(m ? m : 1));
+  PB_TRY(dev_alloc(&ix->slab, seg_b + 3 * arr_b + er_b, s));
+  ix->bytes = seg_b + 3 * arr_b + er_b;
   char *base = (char *)ix->slab;
   ix->seg = (int32_t *)base;
   ix->st = (int32_t *)(base + seg_b);
   ix->en = (int32_t *)(base + seg_b + arr_b);
   ix->row = (uint32_t *)(base + seg_b + 2 * arr_b);
+  ix->er = (uint2 *)(base + seg_b + 3 * arr_b);
   ix->pmax = ix->en;       // until nested intervals are detected: running max == end,
   ix->en_sorted = ix->en;  // end order == start order,
   ix->en_pos = nullptr;    // identity
@@ -189,7 +191,7 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
   PB_TRY(sc.get(&d_cmap_tmp, (size_t)n_contigs + 1));
   PB_CUDA(cudaMemsetAsync(d_meta, 0, 2 * sizeof(unsigned long long), s));
   PB_LAUNCH(unpack_sorted_kernel, (unsigned)cdiv(m, 256), 256, 0, s, keys, vals, m, pos_bits, bias, n_contigs, ix->st, ix->en, ix->row,
-            ix->seg, d_meta);
+            ix->er, ix->seg, d_meta);
   if (try_fast) {
     PB_LAUNCH(contig_span_kernel, (unsigned)cdiv(n_contigs, 128), 128, 0, s, ix->seg, ix->st, (long long)hs.max_len, n_contigs, d_cmap_tmp, d_span);
     PB_TRY((device_scan<SumU64, false>(d_span, d_span, n_contigs, d_meta + 1, s)));
@@ -225,19 +227,20 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
   // 5. fast path: global axis + rank directories
   const unsigned long long total_span = h_meta[1];
   if (try_fast && total_span > 0 && total_span < 0xFFFFFFF0ull) {
+    // bucket width: the smallest power of two that leaves at most m/0.6 buckets (0.6-1.2 indexed rows per bucket:
+    // a record then holds ~3 keys on average of its 12 and crowded records stay below ~0.2 %), capped at 2^13
     int shift = 0;
-    while (shift < 31 && (total_span >> shift) > (unsigned long long)m) ++shift;  // about one indexed row per bucket
+    while (shift < kJMaxShift && (total_span >> shift) > ((unsigned long long)m * 5ull) / 3ull) ++shift;
     const uint32_t nb = (uint32_t)(total_span >> shift) + 1;
     const size_t cm_b = align_up(sizeof(ContigMap) * ((size_t)n_contigs + 1)), g_b = align_up(4 * (size_t)m);
-    const size_t d_b = align_up(sizeof(DirRec) * ((size_t)nb + 1));
-    PB_TRY(dev_alloc(&ix->slab2, cm_b + 2 * g_b + 2 * d_b, s));
-    ix->bytes += cm_b + 2 * g_b + 2 * d_b;
+    const size_t d_b = align_up(sizeof(JRec) * ((size_t)nb + 1));
+    PB_TRY(dev_alloc(&ix->slab2, cm_b + 2 * g_b + d_b, s));
+    ix->bytes += cm_b + 2 * g_b + d_b;
     char *b2 = (char *)ix->slab2;
     ix->cmap = (ContigMap *)b2;
     ix->gs = (uint32_t *)(b2 + cm_b);
     ix->ge = (uint32_t *)(b2 + cm_b + g_b);
-    ix->dir_s = (DirRec *)(b2 + cm_b + 2 * g_b);
-    ix->dir_e = (DirRec *)(b2 + cm_b + 2 * g_b + d_b);
+    ix->jdir = (JRec *)(b2 + cm_b + 2 * g_b);
     ix->shift = shift;
     ix->n_buckets = nb;
     PB_CUDA(cudaMemcpyAsync(ix->cmap, d_cmap_tmp, sizeof(ContigMap) * (size_t)n_contigs, cudaMemcpyDeviceToDevice, s));
@@ -246,8 +249,7 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
     // as the start keys when nothing is nested)
     PB_LAUNCH(global_coord_kernel, (unsigned)cdiv(m, 256), 256, 0, s, keys, pos_bits, ix->st, m, ix->cmap, ix->gs);
     PB_LAUNCH(global_coord_kernel, (unsigned)cdiv(m, 256), 256, 0, s, nested ? ekeys : keys, pos_bits, ix->en_sorted, m, ix->cmap, ix->ge);
-    PB_LAUNCH(build_dir_kernel, (unsigned)cdiv((int64_t)nb + 1, 256), 256, 0, s, ix->gs, m, shift, nb, ix->dir_s);
-    PB_LAUNCH(build_dir_kernel, (unsigned)cdiv((int64_t)nb + 1, 256), 256, 0, s, ix->ge, m, shift, nb, ix->dir_e);
+    PB_LAUNCH(build_jdir_kernel, (unsigned)cdiv((int64_t)nb + 1, 256), 256, 0, s, ix->gs, ix->ge, m, shift, nb, ix->jdir);
     PB_CHECK_LAUNCH();
     ix->fast = 1;
   }

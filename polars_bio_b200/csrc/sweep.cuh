@@ -150,32 +150,55 @@ __global__ void __launch_bounds__(kSweepThreads) overlap_emit_kernel(IndexView i
 
 
 // =============================================================================================
-// Fast path: rank directory over the global coordinate axis (index.cuh).  One 32-byte sector per
-// rank query; the count is the sweep-line identity  |{st < a.end}| - |{en <= a.start}|  (Strict)
+// Fast path: joint rank directory over the global coordinate axis (index.cuh).  One 32-byte sector per
+// probe (two for probes longer than a bucket); the count is the sweep-line identity  |{st < a.end}| - |{en <= a.start}|  (Strict)
 // /  |{st <= a.end}| - |{en < a.start}|  (Weak)  (polars_bio/range_op.py:548-594).
 // =============================================================================================
-template <bool LE>  // LE: number of keys <= x ; else number of keys < x
-__device__ __forceinline__ uint32_t dir_rank(const DirRec *__restrict__ dir, const uint32_t *__restrict__ g, int shift, uint32_t x) {
-  const uint32_t b = x >> shift;
-  // one 256-bit request per record (LDG.E.256): two 128-bit loads cost two L2 sector requests each time the
-  // first is still in flight; no L1 allocation -- the directory is touched at random, nothing is reused
-  uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+// one 256-bit request per record (LDG.E.256): two 128-bit loads cost two L2 sector requests each time the first is
+// still in flight; no L1 allocation -- the directory is touched at random, nothing is reused
+__device__ __forceinline__ void ld_jrec(const JRec *__restrict__ p, uint32_t (&w)[8]) {
   asm("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
-               : "l"(dir + b));
-  if (!(r0 & 0x80000000u)) {
-    uint32_t n;
-    if (LE) n = (r1 <= x) + (r2 <= x) + (r3 <= x) + (r4 <= x) + (r5 <= x) + (r6 <= x) + (r7 <= x);
-    else n = (r1 < x) + (r2 < x) + (r3 < x) + (r4 < x) + (r5 < x) + (r6 < x) + (r7 < x);
-    return r0 + n;
-  }
-  uint32_t a = r0 & 0x7fffffffu, e = __ldg(&dir[b + 1].base) & 0x7fffffffu;  // crowded bucket: search inside it
-  while (a < e) {
-    const uint32_t mid = a + ((e - a) >> 1);
-    const uint32_t v = __ldg(g + mid);
-    if (LE ? (v <= x) : (v < x)) a = mid + 1; else e = mid;
-  }
+      : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+      : "l"(p));
+}
+// number of the record's 12 fields below t (t <= 0x7FFF).  Packed compare: every field has bit 15 clear, so
+// field + (0x8000 - t) carries into bit 15 exactly when field >= t and never into the neighbouring field; the six
+// words' guard bits are moved to distinct positions and counted with one POPC.
+__device__ __forceinline__ uint32_t jrec_nlt(const uint32_t (&w)[8], uint32_t t) {
+  const uint32_t c = (0x8000u - t) * 0x00010001u;
+  uint32_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) acc |= ((w[2 + i] + c) & 0x80008000u) >> i;
+  return (uint32_t)kJKeys - (uint32_t)__popc(acc);
+}
+__device__ __forceinline__ uint32_t search_g(const uint32_t *__restrict__ g, uint32_t a, uint32_t e, uint32_t x) {
+  while (a < e) { const uint32_t mid = a + ((e - a) >> 1); if (__ldg(g + mid) < x) a = mid + 1; else e = mid; }
   return a;
+}
+// Both ranks of a proper probe with global-axis coordinates g_s <= g_e:
+//   hi = number of indexed starts before the probe end   (Strict: gs <  g_e ; Weak: gs <= g_e)
+//   re = number of indexed ends   before the probe start (Strict: ge <= g_s ; Weak: ge <  g_s)
+// written as "keys below xS / xE" so one packed compare serves both predicates.
+template <bool STRICT>
+__device__ __forceinline__ void jdir_ranks(const IndexView &ix, uint32_t g_s, uint32_t g_e, uint32_t &hi, uint32_t &re) {
+  const uint32_t xS = g_e + (STRICT ? 0u : 1u), xE = g_s + (STRICT ? 1u : 0u);  // the axis ends below 2^32-16: no wrap
+  const int sh = ix.shift;
+  const uint32_t b = g_s >> sh, lo = b << sh;
+  uint32_t w[8];
+  ld_jrec(ix.jdir + b, w);
+  const uint32_t dS = xS - lo;
+  const bool same = dS <= (2u << sh);  // the record covers the starts of [lo, lo+2W)
+  if (!(w[0] & 0x80000000u)) {
+    re = w[1] + jrec_nlt(w, 0x4000u + (xE - lo));
+    if (same) { hi = w[0] + jrec_nlt(w, dS); return; }
+  } else {  // crowded bucket: search inside its rank range
+    re = search_g(ix.ge, w[1], w[3], xE);
+    if (same) { hi = search_g(ix.gs, w[0] & 0x7fffffffu, w[2], xS); return; }
+  }
+  const uint32_t b2 = g_e >> sh, lo2 = b2 << sh;  // probe longer than the overlap: the record of its end bucket
+  ld_jrec(ix.jdir + b2, w);
+  if (!(w[0] & 0x80000000u)) hi = w[0] + jrec_nlt(w, xS - lo2);
+  else hi = search_g(ix.gs, w[0] & 0x7fffffffu, w[2], xS);
 }
 
 constexpr uint32_t kGenericProbe = 0xFFFFFFFFu;  // pass-1 marker: this probe must take the generic window path
@@ -195,8 +218,8 @@ __device__ __forceinline__ uint32_t fast_count(const IndexView &ix, int32_t c, i
   ls = ls < cm.lo_m1 ? cm.lo_m1 : (ls > cm.hi_p1 ? cm.hi_p1 : ls);
   le = le < cm.lo_m1 ? cm.lo_m1 : (le > cm.hi_p1 ? cm.hi_p1 : le);
   const uint32_t g_s = cm.off + (uint32_t)(ls - cm.lo_m1), g_e = cm.off + (uint32_t)(le - cm.lo_m1);
-  const uint32_t hi = STRICT ? dir_rank<false>(ix.dir_s, ix.gs, ix.shift, g_e) : dir_rank<true>(ix.dir_s, ix.gs, ix.shift, g_e);
-  const uint32_t re = STRICT ? dir_rank<true>(ix.dir_e, ix.ge, ix.shift, g_s) : dir_rank<false>(ix.dir_e, ix.ge, ix.shift, g_s);
+  uint32_t hi, re;
+  jdir_ranks<STRICT>(ix, g_s, g_e, hi, re);
   hi_out = hi;
   return hi - re;
 }
@@ -208,14 +231,16 @@ __device__ __forceinline__ uint32_t fast_count(const IndexView &ix, int32_t c, i
 template <bool STRICT>
 __device__ __forceinline__ bool fast_window(const IndexView &ix, int32_t c, int32_t s, int32_t e, int32_t seg_lo,
                                             int32_t &lo, int32_t &hi, int32_t &lend) {
-  if (!ix.dir_s || !(STRICT ? (s < e) : (s <= e))) return false;
+  if (!ix.jdir || !(STRICT ? (s < e) : (s <= e))) return false;
   const ContigMap cm = ix.cmap[c];
   long long ls = s, le = e;
   ls = ls < cm.lo_m1 ? cm.lo_m1 : (ls > cm.hi_p1 ? cm.hi_p1 : ls);
   le = le < cm.lo_m1 ? cm.lo_m1 : (le > cm.hi_p1 ? cm.hi_p1 : le);
   const uint32_t g_s = cm.off + (uint32_t)(ls - cm.lo_m1), g_e = cm.off + (uint32_t)(le - cm.lo_m1);
-  hi = (int32_t)(STRICT ? dir_rank<false>(ix.dir_s, ix.gs, ix.shift, g_e) : dir_rank<true>(ix.dir_s, ix.gs, ix.shift, g_e));
-  lend = (int32_t)(STRICT ? dir_rank<true>(ix.dir_e, ix.ge, ix.shift, g_s) : dir_rank<false>(ix.dir_e, ix.ge, ix.shift, g_s));
+  uint32_t uh, ur;
+  jdir_ranks<STRICT>(ix, g_s, g_e, uh, ur);
+  hi = (int32_t)uh;
+  lend = (int32_t)ur;
   const int32_t p = lend;  // = hi - cnt
   if (p >= hi) { lo = hi; return true; }
   if (p <= seg_lo || !end_hits<STRICT>(__ldg(ix.pmax + p - 1), s)) lo = p;
@@ -318,9 +343,10 @@ __global__ void __launch_bounds__(kSweepThreads) overlap_emit_fast_kernel(IndexV
   } else if (cnt && !heavy) {
     uint32_t k = 0;
     for (int64_t j = (int64_t)hi - 1; k < cnt && j >= 0; --j) {
-      const int32_t ev = __ldg(ix.en + j);
-      const uint32_t rv = __ldg(ix.row + j);  // speculative: without nesting every candidate is a hit, and the two
-      if (end_hits<STRICT>(ev, s)) {          // loads then overlap instead of chaining
+      const uint2 v = __ldg(ix.er + j);  // (end, row) interleaved: one 8-byte random load per candidate
+      const int32_t ev = (int32_t)v.x;
+      const uint32_t rv = v.y;
+      if (end_hits<STRICT>(ev, s)) {
         const unsigned long long p = pos + (cnt - 1 - k);
         out_probe[p] = (uint32_t)i;
         out_build[p] = rv;
