@@ -428,10 +428,18 @@ def main():
         reads_t, vars_t = table(probe), table(build)
         cols = ("contig", "pos_start", "pos_end")
 
+        split = []
+
         def step_api():
+            t_a = time.perf_counter()
             c = pb.count_overlaps(reads_t, vars_t, cols1=cols, cols2=cols, output_type="pyarrow.Table")
+            t_b = time.perf_counter()
             o = pb.overlap(reads_t, vars_t, cols1=cols, cols2=cols, output_type="pyarrow.Table")
-            return c.num_rows, o.num_rows
+            t_c = time.perf_counter()
+            rows = c.num_rows, o.num_rows
+            del c, o
+            split.append((t_b - t_a, t_c - t_b, time.perf_counter() - t_c))
+            return rows
 
         for _ in range(2):
             step_api()
@@ -447,9 +455,14 @@ def main():
             t = torch.tensor([e2e_sec], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_sec = float(t.item())
-        e2e = {"value": pairs_all / e2e_sec, "unit": "pairs/s", "h2d_bytes_per_step": 2 * 12 * (n + m),
-               "d2h_bytes_per_step": 8 * n + 8 * pairs, "ms_per_step": e2e_sec * 1e3,
-               "api": "pb.count_overlaps + pb.overlap on host pyarrow Tables (utf8 contig), materialised pyarrow.Table outputs"}
+        # bytes on the bus per step, counted from what the bridge copies: both calls upload the variants (3 x int32)
+        # and the reads (contig code as uint8 + 2 x int32); count_overlaps brings back uint32 counts, overlap the
+        # key columns of the result rows (contig code uint8 + 4 x int32 positions; no payload columns -> no row ids)
+        e2e = {"value": pairs_all / e2e_sec, "unit": "pairs/s", "h2d_bytes_per_step": 2 * (12 * m + 9 * n),
+               "d2h_bytes_per_step": 4 * n + 17 * pairs, "ms_per_step": e2e_sec * 1e3,
+               "api": "pb.count_overlaps + pb.overlap on host pyarrow Tables (utf8 contig), materialised pyarrow.Table outputs",
+               "split_ms": dict(zip(("count_overlaps", "overlap", "release_results"),
+                                    (float(x) * 1e3 for x in np.mean(np.array(split[-e2e_steps:]), axis=0))))}
 
     line = {
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,

@@ -110,6 +110,15 @@ PBGPU_API int pbgpu_overlap_emit(const pbgpu_overlap_plan *plan, uint32_t *d_pro
  * Left / LeftDistinct output modes (operation.rs:229-233) are filters over these.           */
 PBGPU_API const uint32_t *pbgpu_overlap_plan_counts(const pbgpu_overlap_plan *plan);
 PBGPU_API void pbgpu_overlap_plan_free(pbgpu_overlap_plan *plan);
+/* Streaming sink (BASELINE config 5: ~1e9 pairs through a bounded buffer).  Pass 1 leaves the
+ * exclusive pair offset of every 256-probe block; pass 2 can then be run over any block range [blk_lo, blk_hi)
+ * into a buffer of offsets[blk_hi] - offsets[blk_lo] pairs, so a consumer sizes each chunk to its ring slot
+ * (reference: the output stream of IntervalJoinExec yields bounded RecordBatches, range_op_io.py:148-161). */
+PBGPU_API int64_t pbgpu_overlap_plan_blocks(const pbgpu_overlap_plan *plan);
+PBGPU_API int pbgpu_overlap_plan_block_offsets(const pbgpu_overlap_plan *plan, uint64_t *h_offsets /* [blocks+1], host */,
+                                               void *stream);
+PBGPU_API int pbgpu_overlap_emit_blocks(const pbgpu_overlap_plan *plan, int64_t blk_lo, int64_t blk_hi,
+                                        uint32_t *d_probe_rows, uint32_t *d_build_rows, void *stream);
 
 /* NearestProvider (operation.rs:146-158): for every iterated row up to k indexed rows of the
  * same contig ordered by (overlapping first when include_overlaps, distance, start, row);
@@ -183,6 +192,9 @@ typedef struct {                 /* mirrors RangeOptions, src/option.rs:8-41    
   uint64_t limit;                /* 0 = none (src/lib.rs:120-131)                             */
   uint32_t max_batch_rows;       /* 0 -> 1<<20; low_memory / batch_size cap (range_op.py:168) */
   int32_t device;                /* CUDA device ordinal, -1 = current                         */
+  uint64_t sink_pairs;           /* overlap: pairs per ring slot of the streaming sink; a larger */
+                                 /* result is emitted chunk by chunk from out->get_next with the */
+                                 /* device state kept alive.  0 -> $PBGPU_SINK_PAIRS -> 1<<24    */
 } PbRangeOptions;
 
 /* `left` / `right` are df1 / df2 exactly as the Python facade passes them to

@@ -43,6 +43,7 @@ class PbRangeOptions(ctypes.Structure):
         ("limit", ctypes.c_uint64),
         ("max_batch_rows", ctypes.c_uint32),
         ("device", ctypes.c_int32),
+        ("sink_pairs", ctypes.c_uint64),
     ]
 
 
@@ -77,6 +78,10 @@ def lib() -> ctypes.CDLL:
     L.pbgpu_coverage.argtypes = [vp, vp, vp, vp, i64, ctypes.c_int, vp, vp]
     L.pbgpu_overlap_count.argtypes = [vp, vp, vp, vp, i64, ctypes.c_int, vp, ctypes.POINTER(vp), ctypes.POINTER(i64)]
     L.pbgpu_overlap_emit.argtypes = [vp, vp, vp, vp]
+    L.pbgpu_overlap_plan_blocks.argtypes = [vp]
+    L.pbgpu_overlap_plan_blocks.restype = i64
+    L.pbgpu_overlap_plan_block_offsets.argtypes = [vp, vp, vp]
+    L.pbgpu_overlap_emit_blocks.argtypes = [vp, i64, i64, vp, vp, vp]
     L.pbgpu_overlap_plan_counts.argtypes = [vp]
     L.pbgpu_overlap_plan_counts.restype = vp
     L.pbgpu_overlap_plan_free.argtypes = [vp]

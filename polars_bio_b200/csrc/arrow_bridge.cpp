@@ -38,6 +38,8 @@ struct pbgpu_index;
 namespace pbgpu {
 int set_error(int code, const char *fmt, ...);
 extern thread_local char g_err[512];
+int widen_codes_u8(const uint8_t *d_in, int64_t n, int32_t n_contigs, int32_t *d_out, void *stream);
+int gather_i32_u8(const int32_t *d_src, const uint32_t *d_rows, int64_t n, uint8_t *d_out, void *stream);
 int count_overlaps_u32(const pbgpu_index *ix, const int32_t *c, const int32_t *s, const int32_t *e, int64_t n, int filter_op,
                        uint32_t *d_counts, void *stream);  // pbgpu.cu (internal)
 }  // namespace pbgpu
@@ -232,17 +234,23 @@ struct HostCache {
     const char *e = getenv("PBGPU_HOST_CACHE_MB");
     if (e) limit = (size_t)atoll(e) << 20;
   }
+  // process exit: the CUDA context may already be gone, so page-locked blocks are left to the OS
   ~HostCache() {
-    for (auto &kv : free_) for (void *p : kv.second) free(p);
+    for (auto &kv : free_) for (void *p : kv.second) if (!((size_t *)p)[1]) free(p);
   }
 };
 HostCache &host_cache() { static HostCache c; return c; }
-constexpr size_t kHdr = 64;
+constexpr size_t kHdr = 64;  // block header: [0] capacity, [1] 1 = page-locked (cudaHostRegister'ed) for direct D2H landing
+constexpr size_t kDmaMin = (size_t)1 << 20;
 inline size_t size_class(size_t bytes) {
   size_t need = bytes + kHdr;
   if (need <= ((size_t)64 << 10)) return need;                                  // small: not cached
   if (need <= ((size_t)1 << 20)) { size_t c = (size_t)64 << 10; while (c < need) c <<= 1; return c; }
   return (need + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);           // multiples of 1 MiB
+}
+void free_block(void *base) {
+  if (((size_t *)base)[1]) { if (cudaHostUnregister(base) != cudaSuccess) cudaGetLastError(); }
+  free(base);
 }
 void *hmalloc(size_t bytes) {
   const size_t cap = size_class(bytes ? bytes : 1);
@@ -253,9 +261,30 @@ void *hmalloc(size_t bytes) {
     auto it = c.free_.find(cap);
     if (it != c.free_.end() && !it->second.empty()) { base = it->second.back(); it->second.pop_back(); c.cached -= cap; }
   }
-  if (!base && posix_memalign(&base, 64, cap) != 0) return nullptr;
+  if (!base) {
+    if (posix_memalign(&base, cap >= kDmaMin ? 4096 : 64, cap) != 0) return nullptr;
+    ((size_t *)base)[1] = 0;
+  }
   *(size_t *)base = cap;
   return (char *)base + kHdr;
+}
+// A result buffer the DMA engine can write directly: the block is page-locked once (cudaHostRegister is
+// milliseconds per 100 MB) and stays so while it cycles through the cache, so steady-state calls pay nothing and the
+// pinned-staging -> host copy of every result column disappears.  *dma = false when registration is not possible
+// (small block, PBGPU_DIRECT_D2H=0, or the driver refuses): the caller then stages through a pinned buffer.
+void *hmalloc_dma(size_t bytes, bool *dma) {
+  static const bool enabled = [] { const char *e = getenv("PBGPU_DIRECT_D2H"); return !(e && e[0] == '0'); }();
+  void *p = hmalloc(bytes);
+  *dma = false;
+  if (!p || !enabled) return p;
+  size_t *base = (size_t *)((char *)p - kHdr);
+  if (base[0] < kDmaMin) return p;
+  if (!base[1]) {
+    if (cudaHostRegister(base, base[0], cudaHostRegisterPortable) == cudaSuccess) base[1] = 1;
+    else cudaGetLastError();
+  }
+  *dma = base[1] != 0;
+  return p;
 }
 void *hcalloc(size_t bytes) {
   void *p = hmalloc(bytes);
@@ -271,29 +300,24 @@ void hfree(void *p) {
     std::lock_guard<std::mutex> lk(c.mu);
     if (c.cached + cap <= c.limit) { c.free_[cap].push_back(base); c.cached += cap; return; }
   }
-  free(base);
+  free_block(base);
 }
 
-// Result arrays handed to the consumer live in plain host memory (they may outlive the call by a long time, and
-// pinned memory is a scarce, slow-to-allocate resource): D2H lands in a cached pinned buffer, then the pool copies
-// it out in parallel and the pinned buffer goes straight back to the cache.
+// Result arrays handed to the consumer live in cached host blocks (they may outlive the call by a long time).
+// Large ones are page-locked in place (hmalloc_dma) and the D2H lands in them directly; otherwise the D2H lands in a
+// cached pinned staging buffer and the pool copies it out in parallel (copy_out).
 struct HostBufs {
   std::vector<void *> v;
   ~HostBufs() { for (void *p : v) hfree(p); }
 };
-void *copy_out(HostBufs &hb, const void *pinned, size_t bytes) {
-  void *dst = hmalloc(bytes);
-  if (!dst) return nullptr;
-  hb.v.push_back(dst);
+void copy_into(void *dst, const void *pinned, size_t bytes) {
   const size_t chunk = (size_t)4 << 20;
   const int64_t nt = (int64_t)((bytes + chunk - 1) / chunk);
   Pool::get().parallel_for(nt, [&](int64_t i) {
     const size_t off = (size_t)i * chunk;
     memcpy((char *)dst + off, (const char *)pinned + off, std::min(chunk, bytes - off));
   });
-  return dst;
 }
-
 // ---------------------------------------------------------------------------------------------
 inline bool bit_get(const uint8_t *bits, int64_t i) { return (bits[i >> 3] >> (i & 7)) & 1; }
 inline void bit_set(uint8_t *bits, int64_t i) { bits[i >> 3] |= (uint8_t)(1u << (i & 7)); }
@@ -438,8 +462,10 @@ inline int64_t int_at(const void *buf, char f, int64_t j) {
 inline bool is_int_format(const char *f) { return f && f[0] && !f[1] && strchr("cCsSiIlL", f[0]); }
 
 // Encode the three key columns of a table into int32 staging (code = -1 for null keys).
+// code8 != NULL: contig codes are written as one byte each instead (255 = null key or code >= 255): a quarter of the
+// H2D bytes of that column when the index holds at most 255 contigs (codes it does not know cannot match anyway).
 int encode_keys(const Table &t, const char *side, ContigDict &dict, int32_t *code, int32_t *st, int32_t *en,
-                int64_t row_lo = 0, int64_t row_hi = INT64_MAX) {
+                int64_t row_lo = 0, int64_t row_hi = INT64_MAX, uint8_t *code8 = nullptr) {
   const ArrowSchema *fc = t.schema.children[t.key[0]];
   const ArrowSchema *fs = t.schema.children[t.key[1]];
   const ArrowSchema *fe = t.schema.children[t.key[2]];
@@ -480,28 +506,72 @@ int encode_keys(const Table &t, const char *side, ContigDict &dict, int32_t *cod
       for (int64_t j = 0; j < d->length; ++j)
         dict_codes[j] = (vd && !bit_get(vd, j + d->offset)) ? -1 : dict.intern(str_at(d, sk, j + d->offset));
     }
-    for (int64_t i = tk.lo; i < tk.hi; ++i) {
-      int32_t c;
-      if (vc && !bit_get(vc, i + oc)) c = -1;
-      else if (is_dict) {
-        int64_t k = int_at(ac->buffers[1], fc->format[0], i + oc);
-        c = (k >= 0 && k < (int64_t)dict_codes.size()) ? dict_codes[k] : -1;
-      } else {
-        std::string_view sv = str_at(ac, sk, i + oc);
-        if (have_prev && sv.size() == prev.size() && memcmp(sv.data(), prev.data(), sv.size()) == 0) c = prev_code;
-        else {
-          auto it = local.find(sv);
-          if (it != local.end()) c = it->second;
-          else { c = dict.intern(sv); local.emplace(sv, c); }
-          prev = sv; prev_code = c; have_prev = true;
-        }
+    // ---- fast paths (the common shape: int32 positions and string contigs in long runs, no nulls) ----
+    // positions: a straight copy into the staging buffer
+    const bool fast_s = !vs && sf == 'i', fast_e = !ve && ef == 'i';
+    if (fast_s) memcpy(st + g0 + tk.lo, (const int32_t *)as->buffers[1] + os + tk.lo, 4 * (size_t)(tk.hi - tk.lo));
+    if (fast_e) memcpy(en + g0 + tk.lo, (const int32_t *)ae->buffers[1] + oe + tk.lo, 4 * (size_t)(tk.hi - tk.lo));
+    // contigs: genomic tables are (mostly) sorted by contig, so a block of rows usually repeats one string.  For
+    // utf8 / large_utf8 that is: equal lengths and a data region that is periodic with that length -- two
+    // vectorisable sweeps instead of a hash lookup or memcmp per row.
+    auto block_is_run = [&](int64_t a, int64_t b) -> bool {  // rows [a,b) of this batch (b - a >= 2), no nulls
+      if (sk == StrKind::Utf8) {
+        const int32_t *o = (const int32_t *)ac->buffers[1] + oc;
+        const int32_t L = o[a + 1] - o[a];
+        int bad = 0;
+        for (int64_t i = a + 1; i < b; ++i) bad |= (o[i + 1] - o[i]) ^ L;
+        if (bad) return false;
+        const char *d = (const char *)ac->buffers[2] + o[a];
+        return L == 0 || memcmp(d, d + L, (size_t)L * (size_t)(b - a - 1)) == 0;
       }
-      int64_t s = int_at(as->buffers[1], sf, i + os), e = int_at(ae->buffers[1], ef, i + oe);
-      if ((vs && !bit_get(vs, i + os)) || (ve && !bit_get(ve, i + oe))) { c = -1; s = 0; e = 0; }
-      if (s < INT32_MIN || s > INT32_MAX || e < INT32_MIN || e > INT32_MAX) { range_err.store(1); c = -1; s = 0; e = 0; }
-      code[g0 + i] = c;
-      st[g0 + i] = (int32_t)s;
-      en[g0 + i] = (int32_t)e;
+      if (sk == StrKind::LargeUtf8) {
+        const int64_t *o = (const int64_t *)ac->buffers[1] + oc;
+        const int64_t L = o[a + 1] - o[a];
+        int64_t bad = 0;
+        for (int64_t i = a + 1; i < b; ++i) bad |= (o[i + 1] - o[i]) ^ L;
+        if (bad) return false;
+        const char *d = (const char *)ac->buffers[2] + o[a];
+        return L == 0 || memcmp(d, d + L, (size_t)L * (size_t)(b - a - 1)) == 0;
+      }
+      return false;
+    };
+    auto lookup = [&](std::string_view sv) -> int32_t {
+      if (have_prev && sv.size() == prev.size() && memcmp(sv.data(), prev.data(), sv.size()) == 0) return prev_code;
+      int32_t c;
+      auto it = local.find(sv);
+      if (it != local.end()) c = it->second;
+      else { c = dict.intern(sv); local.emplace(sv, c); }
+      prev = sv; prev_code = c; have_prev = true;
+      return c;
+    };
+    const bool run_ok = !is_dict && !vc && fast_s && fast_e && (sk == StrKind::Utf8 || sk == StrKind::LargeUtf8);
+    constexpr int64_t kRun = 1024;
+    for (int64_t blk = tk.lo; blk < tk.hi; blk += kRun) {
+      const int64_t bhi = std::min(tk.hi, blk + kRun);
+      if (run_ok && bhi - blk >= 2 && block_is_run(blk, bhi)) {
+        const int32_t c = lookup(str_at(ac, sk, blk + oc));
+        if (code8) memset(code8 + g0 + blk, (c < 0 || c >= 255) ? 255 : c, (size_t)(bhi - blk));
+        else for (int64_t i = blk; i < bhi; ++i) code[g0 + i] = c;
+        continue;
+      }
+      for (int64_t i = blk; i < bhi; ++i) {
+        int32_t c;
+        if (vc && !bit_get(vc, i + oc)) c = -1;
+        else if (is_dict) {
+          int64_t k = int_at(ac->buffers[1], fc->format[0], i + oc);
+          c = (k >= 0 && k < (int64_t)dict_codes.size()) ? dict_codes[k] : -1;
+        } else c = lookup(str_at(ac, sk, i + oc));
+        if (!fast_s || !fast_e) {
+          int64_t s = fast_s ? 0 : int_at(as->buffers[1], sf, i + os), e = fast_e ? 0 : int_at(ae->buffers[1], ef, i + oe);
+          bool null_pos = (vs && !bit_get(vs, i + os)) || (ve && !bit_get(ve, i + oe));
+          if (s < INT32_MIN || s > INT32_MAX || e < INT32_MIN || e > INT32_MAX) { range_err.store(1); null_pos = true; }
+          if (null_pos) { c = -1; s = 0; e = 0; if (fast_s) st[g0 + i] = 0; if (fast_e) en[g0 + i] = 0; }
+          if (!fast_s) st[g0 + i] = (int32_t)s;
+          if (!fast_e) en[g0 + i] = (int32_t)e;
+        }
+        if (code8) code8[g0 + i] = (uint8_t)((c < 0 || c >= 255) ? 255 : c);
+        else code[g0 + i] = c;
+      }
     }
   });
   if (!pool_ok) return set_error(PBGPU_ENOMEM, "host allocation failed while encoding the %s table", side);
@@ -909,15 +979,21 @@ int pos_column(const std::shared_ptr<void> &keep, const int32_t *src, int64_t n,
 // contig column from dictionary codes: offsets + data filled sequentially (no random reads of the source table);
 // the buffers are shared by the left and right contig columns of a join batch (equal by the join condition)
 struct StrBufs { std::shared_ptr<HostBufs> keep; void *offs = nullptr; char *data = nullptr; bool large = false; };
-int contig_buffers(const int32_t *codes, int64_t n, const std::vector<std::string> &names, bool large, StrBufs *sb) {
+template <typename CodeT>  // int32 codes, or uint8 when they travelled as bytes (<= 255 indexed contigs)
+int contig_buffers(const CodeT *codes, int64_t n, const std::vector<std::string> &names, bool large, StrBufs *sb) {
   sb->keep = std::make_shared<HostBufs>();
   sb->large = large;
   const int64_t nch = (n + kGatherChunk - 1) / kGatherChunk;
   std::vector<int64_t> bytes((size_t)std::max<int64_t>(nch, 1), 0), off((size_t)std::max<int64_t>(nch, 1), 0);
+  std::vector<uint8_t> uniform((size_t)std::max<int64_t>(nch, 1), 0);  // chunk repeats one contig (sorted output: nearly always)
   std::vector<uint32_t> len(names.size());
   for (size_t k = 0; k < names.size(); ++k) len[k] = (uint32_t)names[k].size();
   Pool::get().parallel_for(nch, [&](int64_t ci) {
     const int64_t lo = ci * kGatherChunk, hi = std::min(n, lo + kGatherChunk);
+    const CodeT c0 = codes[lo];
+    int diff = 0;
+    for (int64_t i = lo; i < hi; ++i) diff |= (int)(codes[i] ^ c0);
+    if (!diff) { uniform[ci] = 1; bytes[ci] = (int64_t)len[c0] * (hi - lo); return; }
     int64_t b = 0;
     for (int64_t i = lo; i < hi; ++i) b += len[codes[i]];
     bytes[ci] = b;
@@ -933,6 +1009,19 @@ int contig_buffers(const int32_t *codes, int64_t n, const std::vector<std::strin
   Pool::get().parallel_for(nch, [&](int64_t ci) {
     const int64_t lo = ci * kGatherChunk, hi = std::min(n, lo + kGatherChunk);
     int64_t pos = off[ci];
+    if (uniform[ci]) {  // arithmetic offsets + one pattern replicated by doubling copies
+      const std::string &nm = names[codes[lo]];
+      const int64_t L = (int64_t)nm.size();
+      if (large) { int64_t *o = (int64_t *)sb->offs; for (int64_t i = lo; i < hi; ++i) o[i] = pos + (i - lo) * L; }
+      else { int32_t *o = (int32_t *)sb->offs; const int32_t p0 = (int32_t)pos, l32 = (int32_t)L; for (int64_t i = lo; i < hi; ++i) o[i] = p0 + (int32_t)(i - lo) * l32; }
+      const int64_t tot = L * (hi - lo);
+      if (tot > 0) {
+        char *d = sb->data + pos;
+        memcpy(d, nm.data(), (size_t)L);
+        for (int64_t done = L; done < tot; ) { const int64_t c = std::min(done, tot - done); memcpy(d + done, d, (size_t)c); done += c; }
+      }
+      return;
+    }
     for (int64_t i = lo; i < hi; ++i) {
       if (large) ((int64_t *)sb->offs)[i] = pos; else ((int32_t *)sb->offs)[i] = (int32_t)pos;
       const std::string &nm = names[codes[i]];
@@ -961,6 +1050,77 @@ ArrowArray str_view(const StrBufs &sb, int64_t n) {
   return v;
 }
 
+#define BR_CUDA(expr)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess) return set_error(PBGPU_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+#define BR_TRY(expr) do { int _rc = (expr); if (_rc != PBGPU_OK) return _rc; } while (0)
+
+struct DevBufs {  // device scratch of one call, freed stream-ordered
+  cudaStream_t s = nullptr;
+  std::vector<void *> v;
+  template <typename T>
+  T *get(size_t count) {
+    void *p = nullptr;
+    if (cudaMallocAsync(&p, sizeof(T) * (count ? count : 1), s) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    v.push_back(p);
+    return (T *)p;
+  }
+  void release() { for (void *p : v) cudaFreeAsync(p, s); v.clear(); }
+  ~DevBufs() { release(); }
+};
+
+// Everything one pbgpu_range_op call holds on the device.  It normally dies when the call returns; a streaming
+// overlap (result larger than one ring slot) hands it to the output stream, which keeps emitting from it.
+struct CallState {
+  int device = -1;      // device the state lives on
+  cudaStream_t s = nullptr;
+  cudaStream_t s2 = nullptr;  // count_overlaps / coverage: kernel + D2H of slice k while slice k+1 uploads on `s`
+  DevBufs dev;
+  PinnedHold stage;     // D2H landing buffers the host reads (returned to the cache when the state dies)
+  PinnedHold stage_wc;  // H2D staging: write-combined pinned memory, written once by the encoders, read by DMA
+  pbgpu_index *ix = nullptr;
+  pbgpu_overlap_plan *plan = nullptr;
+  CallState() { stage_wc.wc = true; }
+  CallState(const CallState &) = delete;
+  CallState &operator=(const CallState &) = delete;
+  ~CallState() {
+    int prev = -1;
+    if (device >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != device) cudaSetDevice(device); else prev = -1;
+    if (s2) { cudaStreamSynchronize(s2); cudaStreamDestroy(s2); }
+    if (s) cudaStreamSynchronize(s);  // the index / plan are freed on the legacy stream: nothing of ours may still read them
+    if (plan) pbgpu_overlap_plan_free(plan);
+    if (ix) pbgpu_index_free(ix);
+    dev.release();
+    if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// Streaming sink of a materialised / index-pair overlap (BASELINE config 5): pass 2 runs over
+// runs of 256-probe blocks whose pairs fit one ring slot; the slot's pairs (and the key columns gathered from them)
+// are copied to the host, and the next chunk is enqueued while the consumer materialises the current one.
+struct Sink {
+  std::vector<uint64_t> offs;  // exclusive pair offset of every block (+ total)
+  int64_t nblk = 0, next_blk = 0, cap = 0;
+  bool mat = false, join = false, need_l = false, need_r = false;
+  bool code8 = false;  // the contig code column of the result rows comes down as bytes (<= 255 indexed contigs)
+  const int32_t *dc_i = nullptr, *ds_i = nullptr, *de_i = nullptr, *ds_x = nullptr, *de_x = nullptr;
+  uint32_t *d_p = nullptr, *d_b = nullptr;  // the device slot
+  int32_t *d_k[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  void *h_stage[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // pinned landing (only when direct D2H is off)
+  struct Chunk {
+    bool valid = false;
+    int64_t base = 0, rows = 0;
+    std::shared_ptr<HostBufs> pins;
+    const uint32_t *lrow = nullptr, *rrow = nullptr;
+    const int32_t *k[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    struct Staged { void *fin; const void *landing; size_t bytes; };
+    std::vector<Staged> staged;  // pinned landing -> final copies still to do after the sync
+  } infl;  // the chunk in flight
+};
+
 // ---- the output stream ---------------------------------------------------------------------------
 struct OutStream {
   std::shared_ptr<Table> left, right;  // shared with zero-copy output views of their columns
@@ -974,14 +1134,104 @@ struct OutStream {
   std::vector<uint32_t> own_l, own_r;  // host-built row lists (nearest expansion, distinct)
   std::vector<int64_t> own_x;
   // overlap, materialised: key columns of the result rows gathered on the device (NULL = not available)
+  const uint8_t *k_code8 = nullptr;  // the same column as k_code when it travelled as bytes
   const int32_t *k_code = nullptr, *k_ls = nullptr, *k_le = nullptr, *k_rs = nullptr, *k_re = nullptr;
   std::vector<std::string> contig_names;  // dictionary: code -> contig string
   int64_t cursor = 0;
+  int64_t chunk_base = 0, chunk_rows = 0;  // result rows [chunk_base, chunk_base + chunk_rows) are behind lrow / rrow / k_*
+  std::unique_ptr<CallState> call;         // device state (kept past the call only by a streaming overlap)
+  std::unique_ptr<Sink> sink;
   int view_batch = 0;        // pass-through modes: input batch being re-exported
   int64_t view_off = 0;      //   and the offset inside it
   uint32_t batch_rows = 1 << 20;
   std::string last_error;
 };
+
+// enqueue pass 2 + key gathers + D2H of the next chunk on the call's stream (no sync)
+int sink_enqueue(OutStream *st) {
+  Sink &sk = *st->sink;
+  CallState &cs = *st->call;
+  Sink::Chunk &ch = sk.infl;
+  ch = Sink::Chunk();
+  int64_t lo = sk.next_blk, hi = lo, rows = 0;
+  while (lo < sk.nblk) {  // a run of whole blocks that fits the slot (at least one block), skipping empty runs
+    hi = (int64_t)(std::upper_bound(sk.offs.begin() + lo, sk.offs.end(), sk.offs[lo] + (uint64_t)sk.cap) - sk.offs.begin()) - 1;
+    if (hi <= lo) hi = lo + 1;
+    rows = (int64_t)(sk.offs[hi] - sk.offs[lo]);
+    if (rows > 0) break;
+    lo = hi;
+  }
+  sk.next_blk = hi;
+  if (lo >= sk.nblk || rows <= 0) return PBGPU_OK;  // nothing left
+  cudaStream_t s = cs.s;
+  BR_TRY(pbgpu_overlap_emit_blocks(cs.plan, lo, hi, sk.d_p, sk.d_b, s));
+  ch.pins = std::make_shared<HostBufs>();
+  int slot = 0;
+  auto fetch = [&](const void *d_src, const void **dst, size_t width) -> int {
+    bool dma = false;
+    void *fin = hmalloc_dma(width * (size_t)rows, &dma);
+    if (!fin) return set_error(PBGPU_ENOMEM, "host allocation failed");
+    ch.pins->v.push_back(fin);
+    *dst = fin;
+    void *h = fin;
+    if (!dma) {
+      if (!sk.h_stage[slot]) sk.h_stage[slot] = cs.stage.get<uint32_t>((size_t)sk.cap);
+      h = sk.h_stage[slot];
+      if (!h) return set_error(PBGPU_ENOMEM, "pinned allocation failed");
+      ch.staged.push_back({fin, h, width * (size_t)rows});
+    }
+    ++slot;
+    BR_CUDA(cudaMemcpyAsync(h, d_src, width * (size_t)rows, cudaMemcpyDeviceToHost, s));
+    return PBGPU_OK;
+  };
+  if (sk.mat) {  // key columns of the result rows: gathered where they already live
+    struct G { const int32_t *src; const uint32_t *rows; bool on; };
+    const G gs[5] = {{sk.dc_i, sk.d_p, true}, {sk.ds_i, sk.d_p, true}, {sk.de_i, sk.d_p, true}, {sk.ds_x, sk.d_b, sk.join}, {sk.de_x, sk.d_b, sk.join}};
+    for (int j = 0; j < 5; ++j) {
+      if (!gs[j].on) continue;
+      if (j == 0 && sk.code8) {
+        BR_TRY(pbgpu::gather_i32_u8(gs[j].src, gs[j].rows, rows, (uint8_t *)sk.d_k[j], s));
+        BR_TRY(fetch(sk.d_k[j], (const void **)&ch.k[j], 1));
+        continue;
+      }
+      BR_TRY(pbgpu_gather_i32(gs[j].src, gs[j].rows, rows, sk.d_k[j], s));
+      BR_TRY(fetch(sk.d_k[j], (const void **)&ch.k[j], 4));
+    }
+  }
+  if (sk.need_l) BR_TRY(fetch(sk.d_p, (const void **)&ch.lrow, 4));
+  if (sk.need_r) BR_TRY(fetch(sk.d_b, (const void **)&ch.rrow, 4));
+  ch.base = (int64_t)sk.offs[lo];
+  ch.rows = rows;
+  ch.valid = true;
+  return PBGPU_OK;
+}
+
+// make the chunk in flight the current one (sync), then start the next; the device state is dropped after the last
+int sink_advance(OutStream *st) {
+  Sink &sk = *st->sink;
+  if (!st->call) return set_error(PBGPU_EINVAL, "streaming overlap: device state already released");
+  CallState &cs = *st->call;
+  int prev = -1;
+  if (cudaGetDevice(&prev) == cudaSuccess && prev != cs.device) cudaSetDevice(cs.device); else prev = -1;
+  struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev};
+  if (!sk.infl.valid) BR_TRY(sink_enqueue(st));
+  if (!sk.infl.valid) return set_error(PBGPU_EINVAL, "streaming overlap: ran out of chunks before the last row");
+  BR_CUDA(cudaStreamSynchronize(cs.s));
+  Sink::Chunk &ch = sk.infl;
+  for (auto &c : ch.staged) copy_into(c.fin, c.landing, c.bytes);
+  st->pins = ch.pins;
+  st->lrow = ch.lrow;
+  st->rrow = ch.rrow ? ch.rrow : ch.lrow;  // never dereferenced when not needed; keeps emit=1 paths well defined
+  st->k_code = sk.code8 ? nullptr : ch.k[0];
+  st->k_code8 = sk.code8 ? (const uint8_t *)ch.k[0] : nullptr;
+  st->k_ls = ch.k[1]; st->k_le = ch.k[2]; st->k_rs = ch.k[3]; st->k_re = ch.k[4];
+  st->chunk_base = ch.base;
+  st->chunk_rows = ch.rows;
+  ch.valid = false;
+  if (st->chunk_base + st->chunk_rows < st->n_out) BR_TRY(sink_enqueue(st));  // prefetch while the consumer materialises
+  if (!sk.infl.valid) st->call.reset();  // last chunk is on the host: free the device side now
+  return PBGPU_OK;
+}
 
 bool want_distance(const PbRangeOptions &o) { return o.range_op == PBGPU_OP_NEAREST && o.compute_distance; }
 
@@ -1032,7 +1282,12 @@ int out_get_next(ArrowArrayStream *s, ArrowArray *out) {
   if (st->cursor >= st->n_out) return 0;  // end of stream: released (release == NULL) array
   Trace tr;
   struct LapEnd { Trace &t; ~LapEnd() { t.lap("get_next (materialise batch)"); } } lap_end{tr};
-  const int64_t lo = st->cursor, n = std::min<int64_t>(st->batch_rows, st->n_out - lo);
+  if (st->sink && st->cursor >= st->chunk_base + st->chunk_rows) {  // streaming overlap: next chunk of pairs
+    if (sink_advance(st) != PBGPU_OK) { st->last_error = pbgpu::g_err; return 5; }
+  }
+  const int64_t row0 = st->cursor;  // first result row of this batch; `lo` = its position inside the resident chunk
+  const int64_t lo = row0 - st->chunk_base;
+  const int64_t n = std::min<int64_t>(std::min<int64_t>(st->batch_rows, st->n_out - row0), st->chunk_rows - lo);
   std::unique_ptr<OwnedArray> top(new OwnedArray());
   int rc = PBGPU_OK;
   auto push = [&](ArrowArray &&a) { top->kids.push_back(a); };
@@ -1057,7 +1312,7 @@ int out_get_next(ArrowArrayStream *s, ArrowArray *out) {
       else { ArrowArray b{}; rc = plain_column<uint32_t>(st->rrow + lo, n, nullptr, &b); if (rc == PBGPU_OK) push(std::move(b)); }
     }
     if (rc == PBGPU_OK && want_distance(o)) { ArrowArray d{}; rc = nullable_i64_column(st->extra + lo, n, &d); if (rc == PBGPU_OK) push(std::move(d)); }
-  } else if (o.range_op == PBGPU_OP_OVERLAP && st->k_code) {
+  } else if (o.range_op == PBGPU_OP_OVERLAP && (st->k_code || st->k_code8)) {
     // key columns come from the device-gathered int32 arrays; only true payload columns are gathered on the host
     struct Slot { int kind; const Table *t; int col; const int32_t *pos; const uint32_t *rows; };  // 0 contig, 1 position, 2 payload
     std::vector<Slot> slots;
@@ -1083,7 +1338,8 @@ int out_get_next(ArrowArrayStream *s, ArrowArray *out) {
       bool ok;
       const bool large = out_format(f, &ok)[0] == 'U';
       StrBufs &sb = large ? sb_large : sb_small;
-      if (!sb.keep) rc = contig_buffers(st->k_code + lo, n, st->contig_names, large, &sb);
+      if (!sb.keep) rc = st->k_code8 ? contig_buffers(st->k_code8 + lo, n, st->contig_names, large, &sb)
+                                     : contig_buffers(st->k_code + lo, n, st->contig_names, large, &sb);
       if (rc == PBGPU_OK) push(str_view(sb, n));
     }
     for (; next_payload < payload.size(); ++next_payload) if (payload[next_payload].release) payload[next_payload].release(&payload[next_payload]);
@@ -1133,26 +1389,6 @@ void out_release(ArrowArrayStream *s) {
   s->release = nullptr;
 }
 
-struct DevBufs {  // device scratch of one call, freed stream-ordered
-  cudaStream_t s;
-  std::vector<void *> v;
-  template <typename T>
-  T *get(size_t count) {
-    void *p = nullptr;
-    if (cudaMallocAsync(&p, sizeof(T) * (count ? count : 1), s) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    v.push_back(p);
-    return (T *)p;
-  }
-  ~DevBufs() { for (void *p : v) cudaFreeAsync(p, s); }
-};
-
-#define BR_CUDA(expr)                                                                                   \
-  do {                                                                                                  \
-    cudaError_t _e = (expr);                                                                            \
-    if (_e != cudaSuccess) return set_error(PBGPU_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
-  } while (0)
-#define BR_TRY(expr) do { int _rc = (expr); if (_rc != PBGPU_OK) return _rc; } while (0)
-
 int run(Table *L, Table *R, OutStream *os) {
   const PbRangeOptions &o = os->opt;
   // roles: which table is indexed, which is iterated (see pbgpu.h)
@@ -1163,21 +1399,23 @@ int run(Table *L, Table *R, OutStream *os) {
   Table *IT = iter_is_left ? L : R, *IX = iter_is_left ? R : L;
   Trace tr;
   ContigDict dict;
-  PinnedHold stage;     // D2H landing buffers the host reads (returned to the cache when this call ends)
-  PinnedHold stage_wc;  // H2D staging: write-combined pinned memory, written once by the encoders, read by DMA
-  stage_wc.wc = true;
+  os->call.reset(new CallState());
+  CallState &cs = *os->call;  // dies with this call (end of run) unless a streaming overlap keeps it
+  PinnedHold &stage = cs.stage, &stage_wc = cs.stage_wc;
   const int64_t n = IT->rows, m = IX->rows;
-  int32_t *hc_i = stage_wc.get<int32_t>(n), *hs_i = stage_wc.get<int32_t>(n), *he_i = stage_wc.get<int32_t>(n);
+  int32_t *hs_i = stage_wc.get<int32_t>(n), *he_i = stage_wc.get<int32_t>(n);
   int32_t *hc_x = stage_wc.get<int32_t>(m), *hs_x = stage_wc.get<int32_t>(m), *he_x = stage_wc.get<int32_t>(m);
-  if (!hc_i || !hs_i || !he_i || !hc_x || !hs_x || !he_x) return set_error(PBGPU_ENOMEM, "pinned staging allocation failed");
+  if (!hs_i || !he_i || !hc_x || !hs_x || !he_x) return set_error(PBGPU_ENOMEM, "pinned staging allocation failed");
 
   int prev_dev = -1;
-  if (o.device >= 0) { BR_CUDA(cudaGetDevice(&prev_dev)); BR_CUDA(cudaSetDevice(o.device)); }
+  BR_CUDA(cudaGetDevice(&prev_dev));
+  if (o.device >= 0 && o.device != prev_dev) BR_CUDA(cudaSetDevice(o.device)); else prev_dev = -1;
   struct DevRestore { int d; ~DevRestore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev};
-  cudaStream_t s;
-  BR_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-  struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamSynchronize(s); cudaStreamDestroy(s); } } sg{s};
-  DevBufs dev{s, {}};
+  BR_CUDA(cudaGetDevice(&cs.device));
+  BR_CUDA(cudaStreamCreateWithFlags(&cs.s, cudaStreamNonBlocking));
+  cudaStream_t s = cs.s;
+  cs.dev.s = s;
+  DevBufs &dev = cs.dev;
   int32_t *dc_x = dev.get<int32_t>(m), *ds_x = dev.get<int32_t>(m), *de_x = dev.get<int32_t>(m);
   int32_t *dc_i = dev.get<int32_t>(n), *ds_i = dev.get<int32_t>(n), *de_i = dev.get<int32_t>(n);
   if (!dc_x || !ds_x || !de_x || !dc_i || !ds_i || !de_i) return set_error(PBGPU_ENOMEM, "device allocation failed");
@@ -1192,53 +1430,85 @@ int run(Table *L, Table *R, OutStream *os) {
   tr.lap("encode + H2D indexed side");
   pbgpu_index *ix = nullptr;
   BR_TRY(pbgpu_index_build(dc_x, ds_x, de_x, m, n_contigs, s, &ix));
+  cs.ix = ix;
   tr.lap("index build");
-  // iterated side in slices: the DMA of slice k runs while the host encodes slice k+1
+  // iterated side in slices: the DMA of slice k runs while the host encodes slice k+1.  With at most 255 indexed
+  // contigs the contig codes travel as bytes and are widened on the device.
+  // count_overlaps / coverage are row-local, so they join the pipeline: the kernel of slice k and the D2H of its
+  // result run on a second stream while slice k+1 is still on its way up (PCIe is full duplex), and the host widens
+  // slice k while slice k+1 comes down.
+  const bool row_local = o.range_op == PBGPU_OP_COUNT_OVERLAPS_NAIVE || o.range_op == PBGPU_OP_COVERAGE;
+  const bool is_cov = o.range_op == PBGPU_OP_COVERAGE;
+  struct SliceOut { int64_t lo, hi; cudaEvent_t up, down; };
+  std::vector<SliceOut> slices;
+  struct EvGuard { std::vector<SliceOut> &v; ~EvGuard() { for (auto &x : v) { if (x.up) cudaEventDestroy(x.up); if (x.down) cudaEventDestroy(x.down); } } } evg{slices};
+  uint32_t *d_cnt = nullptr, *h_cnt = nullptr;  // count: u32 on the wire (half the D2H bytes), widened on the host
+  int64_t *d_cov = nullptr, *h_cov = nullptr, *fin64 = nullptr;
+  bool cov_dma = false;
+  if (row_local) {
+    BR_CUDA(cudaStreamCreateWithFlags(&cs.s2, cudaStreamNonBlocking));
+    fin64 = (int64_t *)(is_cov ? hmalloc_dma(8 * (size_t)(n ? n : 1), &cov_dma) : hmalloc(8 * (size_t)(n ? n : 1)));
+    if (!fin64) return set_error(PBGPU_ENOMEM, "host allocation failed");
+    os->pins->v.push_back(fin64);
+    if (is_cov) { d_cov = dev.get<int64_t>(n); h_cov = cov_dma ? fin64 : stage.get<int64_t>(n); if (!d_cov || !h_cov) return set_error(PBGPU_ENOMEM, "allocation failed"); }
+    else { d_cnt = dev.get<uint32_t>(n); h_cnt = stage.get<uint32_t>(n); if (!d_cnt || !h_cnt) return set_error(PBGPU_ENOMEM, "allocation failed"); }
+  }
   {
+    const bool narrow = n_contigs <= 255;
+    int32_t *hc_i = narrow ? nullptr : stage_wc.get<int32_t>(n);
+    uint8_t *hc8 = narrow ? stage_wc.get<uint8_t>(n) : nullptr;
+    uint8_t *dc8 = narrow ? dev.get<uint8_t>(n) : nullptr;
+    if ((!narrow && !hc_i) || (narrow && (!hc8 || !dc8))) return set_error(PBGPU_ENOMEM, "staging allocation failed");
     const int64_t slice = std::max<int64_t>(1 << 20, (n + 7) / 8);
+    slices.reserve(8);
     for (int64_t lo = 0; lo < n; lo += slice) {
       const int64_t hi = std::min(n, lo + slice);
-      int rc = encode_keys(*IT, iter_is_left ? "left" : "right", dict, hc_i, hs_i, he_i, lo, hi);
-      if (rc != PBGPU_OK) { cudaStreamSynchronize(s); pbgpu_index_free(ix); return rc; }
-      cudaMemcpyAsync(dc_i + lo, hc_i + lo, 4 * (size_t)(hi - lo), cudaMemcpyHostToDevice, s);
+      int rc = encode_keys(*IT, iter_is_left ? "left" : "right", dict, hc_i, hs_i, he_i, lo, hi, hc8);
+      if (rc != PBGPU_OK) return rc;
+      if (narrow) {
+        cudaMemcpyAsync(dc8 + lo, hc8 + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, s);
+        rc = pbgpu::widen_codes_u8(dc8 + lo, hi - lo, n_contigs, dc_i + lo, s);
+        if (rc != PBGPU_OK) return rc;
+      } else
+        cudaMemcpyAsync(dc_i + lo, hc_i + lo, 4 * (size_t)(hi - lo), cudaMemcpyHostToDevice, s);
       cudaMemcpyAsync(ds_i + lo, hs_i + lo, 4 * (size_t)(hi - lo), cudaMemcpyHostToDevice, s);
       cudaMemcpyAsync(de_i + lo, he_i + lo, 4 * (size_t)(hi - lo), cudaMemcpyHostToDevice, s);
+      if (row_local) {
+        slices.push_back({lo, hi, nullptr, nullptr});
+        SliceOut &so = slices.back();
+        BR_CUDA(cudaEventCreateWithFlags(&so.up, cudaEventDisableTiming));
+        BR_CUDA(cudaEventCreateWithFlags(&so.down, cudaEventDisableTiming));
+        BR_CUDA(cudaEventRecord(so.up, s));  // also orders the index build (enqueued on s before) ahead of the kernel
+        BR_CUDA(cudaStreamWaitEvent(cs.s2, so.up, 0));
+        if (is_cov) {
+          BR_TRY(pbgpu_coverage(ix, dc_i + lo, ds_i + lo, de_i + lo, hi - lo, o.filter_op, d_cov + lo, cs.s2));
+          BR_CUDA(cudaMemcpyAsync(h_cov + lo, d_cov + lo, 8 * (size_t)(hi - lo), cudaMemcpyDeviceToHost, cs.s2));
+        } else {
+          BR_TRY(pbgpu::count_overlaps_u32(ix, dc_i + lo, ds_i + lo, de_i + lo, hi - lo, o.filter_op, d_cnt + lo, cs.s2));
+          BR_CUDA(cudaMemcpyAsync(h_cnt + lo, d_cnt + lo, 4 * (size_t)(hi - lo), cudaMemcpyDeviceToHost, cs.s2));
+        }
+        BR_CUDA(cudaEventRecord(so.down, cs.s2));
+      }
     }
-    if (cudaGetLastError() != cudaSuccess) { cudaStreamSynchronize(s); pbgpu_index_free(ix); return set_error(PBGPU_ECUDA, "H2D copy of the iterated table failed"); }
+    if (cudaGetLastError() != cudaSuccess) return set_error(PBGPU_ECUDA, "H2D copy of the iterated table failed");
   }
   tr.lap("encode + H2D iterated side");
-  // the index is freed on the legacy stream: make sure nothing on this call's (non-blocking) stream still reads it
-  struct IxGuard { pbgpu_index *p; cudaStream_t s; ~IxGuard() { cudaStreamSynchronize(s); pbgpu_index_free(p); } } ig{ix, s};
   const uint64_t limit = o.limit;
 
-  if (o.range_op == PBGPU_OP_COUNT_OVERLAPS_NAIVE || o.range_op == PBGPU_OP_COVERAGE) {
-    if (o.range_op == PBGPU_OP_COVERAGE) {
-      int64_t *d_out = dev.get<int64_t>(n);
-      int64_t *h_out = stage.get<int64_t>(n);
-      if (!d_out || !h_out) return set_error(PBGPU_ENOMEM, "allocation failed");
-      BR_TRY(pbgpu_coverage(ix, dc_i, ds_i, de_i, n, o.filter_op, d_out, s));
-      BR_CUDA(cudaMemcpyAsync(h_out, d_out, 8 * (size_t)n, cudaMemcpyDeviceToHost, s));
-      BR_CUDA(cudaStreamSynchronize(s));
-      os->extra = (const int64_t *)copy_out(*os->pins, h_out, 8 * (size_t)n);
-    } else {  // counts fit 32 bits (< 2^31 indexed rows): half the D2H bytes, widened to the Int64 column on the host
-      uint32_t *d_out = dev.get<uint32_t>(n);
-      uint32_t *h_out = stage.get<uint32_t>(n);
-      if (!d_out || !h_out) return set_error(PBGPU_ENOMEM, "allocation failed");
-      BR_TRY(pbgpu::count_overlaps_u32(ix, dc_i, ds_i, de_i, n, o.filter_op, d_out, s));
-      BR_CUDA(cudaMemcpyAsync(h_out, d_out, 4 * (size_t)n, cudaMemcpyDeviceToHost, s));
-      BR_CUDA(cudaStreamSynchronize(s));
-      int64_t *wide = (int64_t *)hmalloc(8 * (size_t)(n ? n : 1));
-      if (wide) {
-        os->pins->v.push_back(wide);
-        const int64_t nch = (n + kGatherChunk - 1) / kGatherChunk;
-        Pool::get().parallel_for(nch, [&](int64_t ci) {
-          const int64_t lo = ci * kGatherChunk, hi = std::min(n, lo + kGatherChunk);
-          for (int64_t i = lo; i < hi; ++i) wide[i] = (int64_t)h_out[i];
-        });
-      }
-      os->extra = wide;
+  if (row_local) {
+    for (const SliceOut &so : slices) {
+      BR_CUDA(cudaEventSynchronize(so.down));
+      if (is_cov && cov_dma) continue;  // landed in the result buffer directly
+      const int64_t lo = so.lo, hi = so.hi, nch = (hi - lo + kGatherChunk - 1) / kGatherChunk;
+      Pool::get().parallel_for(nch, [&](int64_t ci) {
+        const int64_t a = lo + ci * kGatherChunk, b = std::min(hi, a + kGatherChunk);
+        if (is_cov) memcpy(fin64 + a, h_cov + a, 8 * (size_t)(b - a));
+        else for (int64_t i = a; i < b; ++i) fin64[i] = (int64_t)h_cnt[i];
+      });
     }
-    if (!os->extra) return set_error(PBGPU_ENOMEM, "host allocation failed");
+    BR_CUDA(cudaStreamSynchronize(cs.s2));
+    BR_CUDA(cudaStreamSynchronize(s));
+    os->extra = fin64;
     os->n_out = n;
   } else if (o.range_op == PBGPU_OP_OVERLAP && o.output_mode == PBGPU_OUT_LEFT_DISTINCT) {
     int64_t *d_out = dev.get<int64_t>(n);
@@ -1255,48 +1525,47 @@ int run(Table *L, Table *R, OutStream *os) {
     pbgpu_overlap_plan *plan = nullptr;
     int64_t total = 0;
     BR_TRY(pbgpu_overlap_count(ix, dc_i, ds_i, de_i, n, o.filter_op, s, &plan, &total));
-    struct PlanGuard { pbgpu_overlap_plan *p; cudaStream_t s; ~PlanGuard() { cudaStreamSynchronize(s); pbgpu_overlap_plan_free(p); } } pg{plan, s};
-    uint32_t *d_p = dev.get<uint32_t>((size_t)total), *d_b = dev.get<uint32_t>((size_t)total);
-    if (!d_p || !d_b) return set_error(PBGPU_ENOMEM, "device allocation failed for %lld pairs", (long long)total);
-    BR_TRY(pbgpu_overlap_emit(plan, d_p, d_b, s));
-    const bool join = o.output_mode == PBGPU_OUT_JOIN;
-    auto has_payload = [](const Table &t) { for (int c = 0; c < (int)t.n_cols(); ++c) if (c != t.key[0] && c != t.key[1] && c != t.key[2]) return true; return false; };
-    const bool mat = o.emit == 0;
-    const bool need_l = !mat || has_payload(*L), need_r = !mat || (join && has_payload(*R));
-    // all result arrays: device gathers + D2H enqueued back to back, ONE stream sync, then parallel copies out of the
-    // pinned landing buffers into cached host memory
-    struct Fetch { const void *d_src; const void **dst; void *h; };
-    std::vector<Fetch> fetches;
-    auto enqueue = [&](const void *d_src, const void **dst) -> int {
-      void *h = stage.get<uint32_t>((size_t)total);
-      if (!h) return set_error(PBGPU_ENOMEM, "pinned allocation failed");
-      BR_CUDA(cudaMemcpyAsync(h, d_src, 4 * (size_t)total, cudaMemcpyDeviceToHost, s));
-      fetches.push_back({d_src, dst, h});
-      return PBGPU_OK;
-    };
-    if (mat) {  // key columns of the result rows: gathered where they already live
-      struct G { const int32_t *src; const uint32_t *rows; const int32_t **dst; bool on; };
-      const G gs[5] = {{dc_i, d_p, &os->k_code, true}, {ds_i, d_p, &os->k_ls, true}, {de_i, d_p, &os->k_le, true},
-                       {ds_x, d_b, &os->k_rs, join}, {de_x, d_b, &os->k_re, join}};
-      for (const G &g : gs) {
-        if (!g.on) continue;
-        int32_t *d_k = dev.get<int32_t>((size_t)total);
-        if (!d_k) return set_error(PBGPU_ENOMEM, "device allocation failed");
-        BR_TRY(pbgpu_gather_i32(g.src, g.rows, total, d_k, s));
-        BR_TRY(enqueue(d_k, (const void **)g.dst));
-      }
-      os->contig_names.resize(dict.map.size());
-      for (auto &kv : dict.map) os->contig_names[(size_t)kv.second] = kv.first;
-    }
-    if (need_l) BR_TRY(enqueue(d_p, (const void **)&os->lrow));
-    if (need_r) BR_TRY(enqueue(d_b, (const void **)&os->rrow));
-    BR_CUDA(cudaStreamSynchronize(s));
-    for (auto &f : fetches) {
-      *f.dst = copy_out(*os->pins, f.h, 4 * (size_t)total);
-      if (!*f.dst) return set_error(PBGPU_ENOMEM, "host allocation failed");
-    }
-    if (!os->rrow) os->rrow = os->lrow;  // never dereferenced in this case; keeps emit=1 paths well defined
+    cs.plan = plan;
     os->n_out = total;
+    if (total > 0) {
+      // pass 2 goes through the streaming sink: one chunk when the result fits a ring slot (the common case; the
+      // device state is then released before this call returns), else chunk by chunk from out->get_next
+      os->sink.reset(new Sink());
+      Sink &sk = *os->sink;
+      const bool join = o.output_mode == PBGPU_OUT_JOIN;
+      auto has_payload = [](const Table &t) { for (int c = 0; c < (int)t.n_cols(); ++c) if (c != t.key[0] && c != t.key[1] && c != t.key[2]) return true; return false; };
+      sk.mat = o.emit == 0;
+      sk.join = join;
+      sk.need_l = !sk.mat || has_payload(*L);
+      sk.need_r = !sk.mat || (join && has_payload(*R));
+      sk.code8 = n_contigs <= 255;
+      sk.dc_i = dc_i; sk.ds_i = ds_i; sk.de_i = de_i; sk.ds_x = ds_x; sk.de_x = de_x;
+      sk.nblk = pbgpu_overlap_plan_blocks(plan);
+      sk.offs.resize((size_t)sk.nblk + 1);
+      BR_TRY(pbgpu_overlap_plan_block_offsets(plan, sk.offs.data(), s));
+      uint64_t widest = 0;
+      for (int64_t b = 0; b < sk.nblk; ++b) widest = std::max(widest, sk.offs[b + 1] - sk.offs[b]);
+      uint64_t cap = o.sink_pairs;
+      if (!cap) { const char *e = getenv("PBGPU_SINK_PAIRS"); cap = e ? strtoull(e, nullptr, 10) : 0; }
+      if (!cap) cap = (uint64_t)1 << 24;
+      const uint64_t want = limit ? std::min<uint64_t>((uint64_t)total, limit + widest) : (uint64_t)total;  // rows ever read
+      sk.cap = (int64_t)std::max<uint64_t>(std::min<uint64_t>(cap, want), widest);
+      sk.d_p = dev.get<uint32_t>((size_t)sk.cap);
+      sk.d_b = dev.get<uint32_t>((size_t)sk.cap);
+      if (!sk.d_p || !sk.d_b) return set_error(PBGPU_ENOMEM, "device allocation failed for a ring slot of %lld pairs", (long long)sk.cap);
+      if (sk.mat) {
+        for (int j = 0; j < 5; ++j) {
+          if (j >= 3 && !join) continue;
+          sk.d_k[j] = dev.get<int32_t>((size_t)sk.cap);
+          if (!sk.d_k[j]) return set_error(PBGPU_ENOMEM, "device allocation failed");
+        }
+        os->contig_names.resize(dict.map.size());
+        for (auto &kv : dict.map) os->contig_names[(size_t)kv.second] = kv.first;
+      }
+      if (limit && (uint64_t)os->n_out > limit) os->n_out = (int64_t)limit;  // before the first prefetch decision
+      BR_TRY(sink_enqueue(os));
+      BR_TRY(sink_advance(os));  // first chunk resident; drops the device state when it was the only one
+    }
   } else if (o.range_op == PBGPU_OP_NEAREST) {
     const int64_t k = o.nearest_k ? (int64_t)o.nearest_k : 1;
     uint32_t *d_p = dev.get<uint32_t>((size_t)(n * k));
@@ -1323,6 +1592,11 @@ int run(Table *L, Table *R, OutStream *os) {
     os->n_out = (int64_t)os->own_l.size();
   } else {
     return set_error(PBGPU_EINVAL, "unsupported range_op %d", o.range_op);
+  }
+  if (!os->sink) {  // everything is on the host already
+    os->chunk_base = 0;
+    os->chunk_rows = os->n_out;
+    os->call.reset();
   }
   if (limit && (uint64_t)os->n_out > limit) os->n_out = (int64_t)limit;
   tr.lap("provider kernels + D2H");

@@ -323,6 +323,30 @@ int count_overlaps_impl(const pbgpu_index *ix, const int32_t *d_contig, const in
   g_ev.mark(EV_COUNT1, s);
   return PBGPU_OK;
 }
+// contig codes that travelled as bytes (Arrow bridge, <= 255 indexed contigs): widen, unknown codes -> null key
+__global__ void __launch_bounds__(256) widen_codes_u8_kernel(const uint8_t *__restrict__ in, int64_t n, int32_t n_contigs,
+                                                             int32_t *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) { const int32_t v = in[i]; out[i] = v < n_contigs ? v : -1; }
+}
+int widen_codes_u8(const uint8_t *d_in, int64_t n, int32_t n_contigs, int32_t *d_out, void *stream) {
+  if (n <= 0) return PBGPU_OK;
+  PB_LAUNCH(widen_codes_u8_kernel, (unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream, d_in, n, n_contigs, d_out);
+  PB_CHECK_LAUNCH();
+  return PBGPU_OK;
+}
+// result-row contig codes for the Arrow bridge, as bytes (matched rows only: 0 <= code < n_contigs <= 255)
+__global__ void __launch_bounds__(256) gather_i32_u8_kernel(const int32_t *__restrict__ src, const uint32_t *__restrict__ rows,
+                                                            int64_t n, uint8_t *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) out[i] = (uint8_t)__ldg(src + rows[i]);
+}
+int gather_i32_u8(const int32_t *d_src, const uint32_t *d_rows, int64_t n, uint8_t *d_out, void *stream) {
+  if (n <= 0) return PBGPU_OK;
+  PB_LAUNCH(gather_i32_u8_kernel, (unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream, d_src, d_rows, n, d_out);
+  PB_CHECK_LAUNCH();
+  return PBGPU_OK;
+}
 // internal (same .so, not part of the C ABI): 32-bit counts for the Arrow bridge, widened on the host
 int count_overlaps_u32(const pbgpu_index *ix, const int32_t *c, const int32_t *s_, const int32_t *e, int64_t n, int filter_op,
                        uint32_t *d_counts, void *stream) {
@@ -438,29 +462,53 @@ int pbgpu_overlap_count(const pbgpu_index *ix, const int32_t *d_contig, const in
   return PBGPU_OK;
 }
 
+static int emit_blocks_impl(const pbgpu_overlap_plan *p, int64_t blk_lo, int64_t blk_hi,
+                            uint32_t *d_probe_rows, uint32_t *d_build_rows, cudaStream_t s) {
+  g_ev.mark(EV_EMIT0, s);
+  const unsigned grid = (unsigned)(blk_hi - blk_lo);
+  if (p->ix->fast) {
+    if (p->filter_op == PBGPU_FILTER_STRICT)
+      PB_LAUNCH(overlap_emit_fast_kernel<true>, grid, kSweepThreads, 0, s, view_of(p->ix), p->pc, p->ps, p->pe, p->n, p->counts,
+                p->his, p->block_base, blk_lo, d_probe_rows, d_build_rows);
+    else
+      PB_LAUNCH(overlap_emit_fast_kernel<false>, grid, kSweepThreads, 0, s, view_of(p->ix), p->pc, p->ps, p->pe, p->n, p->counts,
+                p->his, p->block_base, blk_lo, d_probe_rows, d_build_rows);
+  } else if (p->filter_op == PBGPU_FILTER_STRICT)
+    PB_LAUNCH(overlap_emit_kernel<true>, grid, kSweepThreads, 0, s, view_of(p->ix), p->pc, p->ps, p->pe, p->n, p->counts,
+              p->block_base, blk_lo, d_probe_rows, d_build_rows);
+  else
+    PB_LAUNCH(overlap_emit_kernel<false>, grid, kSweepThreads, 0, s, view_of(p->ix), p->pc, p->ps, p->pe, p->n, p->counts,
+              p->block_base, blk_lo, d_probe_rows, d_build_rows);
+  PB_CHECK_LAUNCH();
+  g_ev.mark(EV_EMIT1, s);
+  return PBGPU_OK;
+}
+
 int pbgpu_overlap_emit(const pbgpu_overlap_plan *p, uint32_t *d_probe_rows, uint32_t *d_build_rows, void *stream) {
   if (!p) return set_error(PBGPU_EINVAL, "plan is NULL");
   if (p->n == 0 || p->total == 0) return PBGPU_OK;
   if (!d_probe_rows || !d_build_rows) return set_error(PBGPU_EINVAL, "output buffer is NULL");
+  return emit_blocks_impl(p, 0, p->nblk, d_probe_rows, d_build_rows, (cudaStream_t)stream);
+}
+
+int64_t pbgpu_overlap_plan_blocks(const pbgpu_overlap_plan *p) { return p ? p->nblk : 0; }
+
+int pbgpu_overlap_plan_block_offsets(const pbgpu_overlap_plan *p, uint64_t *h_offsets, void *stream) {
+  if (!p || !h_offsets) return set_error(PBGPU_EINVAL, "plan/h_offsets is NULL");
+  if (p->n == 0) { h_offsets[0] = 0; return PBGPU_OK; }
   cudaStream_t s = (cudaStream_t)stream;
-  g_ev.mark(EV_EMIT0, s);
-  const unsigned grid = (unsigned)p->nblk;
-  if (p->ix->fast) {
-    if (p->filter_op == PBGPU_FILTER_STRICT)
-      PB_LAUNCH(overlap_emit_fast_kernel<true>, grid, kSweepThreads, 0, s, view_of(p->ix), p->pc, p->ps, p->pe, p->n, p->counts,
-                p->his, p->block_base, d_probe_rows, d_build_rows);
-    else
-      PB_LAUNCH(overlap_emit_fast_kernel<false>, grid, kSweepThreads, 0, s, view_of(p->ix), p->pc, p->ps, p->pe, p->n, p->counts,
-                p->his, p->block_base, d_probe_rows, d_build_rows);
-  } else if (p->filter_op == PBGPU_FILTER_STRICT)
-    PB_LAUNCH(overlap_emit_kernel<true>, grid, kSweepThreads, 0, s, view_of(p->ix), p->pc, p->ps, p->pe, p->n, p->counts,
-              p->block_base, d_probe_rows, d_build_rows);
-  else
-    PB_LAUNCH(overlap_emit_kernel<false>, grid, kSweepThreads, 0, s, view_of(p->ix), p->pc, p->ps, p->pe, p->n, p->counts,
-              p->block_base, d_probe_rows, d_build_rows);
-  PB_CHECK_LAUNCH();
-  g_ev.mark(EV_EMIT1, s);
+  PB_CUDA(cudaMemcpyAsync(h_offsets, p->block_base, sizeof(uint64_t) * (size_t)(p->nblk + 1), cudaMemcpyDeviceToHost, s));
+  PB_CUDA(cudaStreamSynchronize(s));
   return PBGPU_OK;
+}
+
+int pbgpu_overlap_emit_blocks(const pbgpu_overlap_plan *p, int64_t blk_lo, int64_t blk_hi, uint32_t *d_probe_rows,
+                              uint32_t *d_build_rows, void *stream) {
+  if (!p) return set_error(PBGPU_EINVAL, "plan is NULL");
+  if (blk_lo < 0 || blk_hi > p->nblk || blk_lo > blk_hi) return set_error(PBGPU_EINVAL, "block range [%lld,%lld) outside [0,%lld)", (long long)blk_lo, (long long)blk_hi, (long long)p->nblk);
+  if (blk_lo == blk_hi || p->total == 0) return PBGPU_OK;
+  if (!d_probe_rows || !d_build_rows) return set_error(PBGPU_EINVAL, "output buffer is NULL");
+  return emit_blocks_impl(p, blk_lo, blk_hi, d_probe_rows, d_build_rows, (cudaStream_t)stream);
 }
 
 int pbgpu_nearest(const pbgpu_index *ix, const int32_t *d_contig, const int32_t *d_start, const int32_t *d_end, int64_t n,

@@ -100,13 +100,15 @@ __global__ void __launch_bounds__(kSweepThreads) overlap_emit_kernel(IndexView i
                                                                      const int32_t *__restrict__ pe, int64_t n,
                                                                      const uint32_t *__restrict__ counts,
                                                                      const unsigned long long *__restrict__ block_base,
+                                                                     int64_t blk0,
                                                                      uint32_t *__restrict__ out_probe,
                                                                      uint32_t *__restrict__ out_build) {
   __shared__ unsigned long long wt[kSweepThreads / 32 + 1];
-  const int64_t i = (int64_t)blockIdx.x * kSweepThreads + threadIdx.x;
+  const int64_t blk = blk0 + blockIdx.x;  // block range [blk0, blk0+grid): the output buffer starts at the first pair of block blk0
+  const int64_t i = blk * kSweepThreads + threadIdx.x;
   const bool in_range = i < n;
   const uint32_t cnt = in_range ? counts[i] : 0u;
-  unsigned long long pos = block_base[blockIdx.x] + block_exclusive<SumU64, kSweepThreads>((unsigned long long)cnt, wt);
+  unsigned long long pos = block_base[blk] - block_base[blk0] + block_exclusive<SumU64, kSweepThreads>((unsigned long long)cnt, wt);
 
   int32_t lo = 0, hi = 0, s = 0;
   if (cnt) {
@@ -322,15 +324,17 @@ __global__ void __launch_bounds__(kSweepThreads) overlap_emit_fast_kernel(IndexV
                                                                           const uint32_t *__restrict__ counts,
                                                                           const uint32_t *__restrict__ his,
                                                                           const unsigned long long *__restrict__ block_base,
+                                                                          int64_t blk0,
                                                                           uint32_t *__restrict__ out_probe,
                                                                           uint32_t *__restrict__ out_build) {
   __shared__ unsigned long long wt[kSweepThreads / 32 + 1];
-  const int64_t i = (int64_t)blockIdx.x * kSweepThreads + threadIdx.x;
+  const int64_t blk = blk0 + blockIdx.x;  // block range [blk0, blk0+grid): the output buffer starts at the first pair of block blk0
+  const int64_t i = blk * kSweepThreads + threadIdx.x;
   // all three coalesced loads are issued before the block scan so their latency hides behind it
   uint32_t cnt = 0, hi = 0;
   int32_t s = 0;
   if (i < n) { cnt = counts[i]; hi = his[i]; s = ps[i]; }
-  const unsigned long long pos = block_base[blockIdx.x] + block_exclusive<SumU64, kSweepThreads>((unsigned long long)cnt, wt);
+  const unsigned long long pos = block_base[blk] - block_base[blk0] + block_exclusive<SumU64, kSweepThreads>((unsigned long long)cnt, wt);
   const bool generic = cnt && hi == kGenericProbe;
   const bool heavy = cnt >= kHeavyCount && !generic;
   if (generic) {  // rare: empty / inverted probe interval

@@ -9,7 +9,7 @@ constructs (/root/reference/src/operation.rs:146-158, 253-263, 331-340): an inde
 from __future__ import annotations
 
 import ctypes
-from typing import Optional, Tuple
+from typing import Iterator, Optional, Tuple
 
 import torch
 
@@ -107,6 +107,47 @@ class DeviceIndex:
             finally:
                 self._L.pbgpu_overlap_plan_free(plan)
         return p, b
+
+    def overlap_pairs_stream(self, contig, start, end, filter_op: int, max_pairs: int = 1 << 24) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
+        """Streaming sink (SURVEY.md 7 step 6 / BASELINE config 5): the same pairs as :meth:`overlap_pairs`, in the
+        same order, yielded chunk by chunk from TWO device buffers of at most ``max_pairs`` pairs (a chunk is a run of
+        whole 256-probe blocks; one oversized block still gets its own chunk).  Pass 1 runs once over all probes;
+        pass 2 runs per chunk.  The yielded tensors are views of the ring slot: consume (or copy) them before
+        advancing the generator twice."""
+        import numpy as np
+
+        c, s, e = (_col(x, self.device) for x in (contig, start, end))
+        n = c.numel()
+        plan = ctypes.c_void_p()
+        total = ctypes.c_int64(0)
+        with torch.cuda.device(self.device):
+            sp = _stream_ptr(self.device)
+            check(self._L.pbgpu_overlap_count(self._h, c.data_ptr(), s.data_ptr(), e.data_ptr(), n, filter_op, sp,
+                                              ctypes.byref(plan), ctypes.byref(total)))
+            try:
+                nblk = int(self._L.pbgpu_overlap_plan_blocks(plan))
+                offs = np.zeros(nblk + 1, dtype=np.uint64)
+                check(self._L.pbgpu_overlap_plan_block_offsets(plan, offs.ctypes.data, sp))
+                offs = offs.astype(np.int64)
+                cap = int(max(max_pairs, int(np.diff(offs).max()) if nblk else 0, 1))
+                ring = [(torch.empty(cap, dtype=torch.int32, device=self.device),
+                         torch.empty(cap, dtype=torch.int32, device=self.device)) for _ in range(2)]
+                lo, k = 0, 0
+                while lo < nblk:
+                    # largest hi with offs[hi] - offs[lo] <= cap (at least one block)
+                    hi = int(np.searchsorted(offs, offs[lo] + cap, side="right")) - 1
+                    hi = max(hi, lo + 1)
+                    cnt = int(offs[hi] - offs[lo])
+                    if cnt:
+                        p, b = ring[k & 1]
+                        check(self._L.pbgpu_overlap_emit_blocks(plan, lo, hi, p.data_ptr(), b.data_ptr(), sp))
+                        k += 1
+                        yield p[:cnt], b[:cnt]
+                    lo = hi
+                torch.cuda.current_stream(self.device).synchronize()
+            finally:
+                torch.cuda.current_stream(self.device).synchronize()
+                self._L.pbgpu_overlap_plan_free(plan)
 
     # -- NearestProvider ---------------------------------------------------------------------
     def nearest(self, contig, start, end, filter_op: int, k: int = 1, include_overlaps: bool = True,

@@ -262,3 +262,36 @@ def test_count_overlaps_passthrough_multibatch_low_memory():
     assert got["count"].tolist() == fx["expected"]["count"]
     lim = range_operation_frame(pb.ctx, t2, t1, ro, limit=6).to_arrow()
     assert lim.num_rows == 6 and lim["payload"].to_pylist() == d1["payload"].tolist()[:6]
+
+
+@pytest.mark.parametrize("cap", ["1", "1000", "20000"])
+def test_streaming_sink_matches_single_shot(cap, monkeypatch):
+    # SURVEY.md 7 step 6 / BASELINE config 5: results larger than one ring slot are emitted chunk by chunk from
+    # get_next with the device state kept alive; rows, order, limit and every output flavour must not change.
+    ex, fb = exons_fbrain_frames()
+    ex.attrs["coordinate_system_zero_based"] = True; fb.attrs["coordinate_system_zero_based"] = True
+    ex = ex.assign(tag=np.arange(len(ex)).astype(str))  # a payload column: row ids must travel too
+    from polars_bio_b200 import RangeOp, RangeOptions, FilterOp, OverlapOutputMode, range_operation_frame
+
+    def run(**kw):
+        opts = RangeOptions(range_op=RangeOp.Overlap, filter_op=FilterOp.Strict, columns_1=list(COLS), columns_2=list(COLS), **kw)
+        return opts
+
+    monkeypatch.delenv("PBGPU_SINK_PAIRS", raising=False)
+    whole = range_operation_frame(pb.ctx, ex, fb, run()).to_arrow()
+    whole_pairs = range_operation_frame(pb.ctx, ex, fb, run(), emit=1).to_arrow()
+    whole_left = range_operation_frame(pb.ctx, ex, fb, run(overlap_output=OverlapOutputMode.Left)).to_arrow()
+    monkeypatch.setenv("PBGPU_SINK_PAIRS", cap)
+    chunked = range_operation_frame(pb.ctx, ex, fb, run()).to_arrow()
+    assert chunked.num_rows == 54246 and chunked.equals(whole)  # same rows in the same order
+    assert range_operation_frame(pb.ctx, ex, fb, run(), emit=1).to_arrow().equals(whole_pairs)
+    assert range_operation_frame(pb.ctx, ex, fb, run(overlap_output=OverlapOutputMode.Left)).to_arrow().equals(whole_left)
+    lim = range_operation_frame(pb.ctx, ex, fb, run(), limit=12345).to_arrow()
+    assert lim.equals(whole.slice(0, 12345))
+    # dropping a half-consumed stream must release the device state cleanly
+    it = range_operation_frame(pb.ctx, ex, fb, run(overlap_low_memory=True)).execute_stream()
+    first = next(iter(it))
+    assert first.num_rows > 0
+    del it, first
+    res = pb.overlap(ex, fb, cols1=COLS, cols2=COLS, output_type="pandas.DataFrame")
+    assert len(res) == 54246

@@ -41,6 +41,12 @@ def _run_all(pc, ps, pe, bc, bs, be, nc, strict, ks=((1, True), (3, True), (1, F
     oa, ob = oix.overlap_pairs(pc, ps, pe, strict)
     assert len(a) == len(oa)
     assert np.array_equal(_u32(a), oa) and np.array_equal(_u32(b), ob)  # same order too: (probe, start, row)
+    # streaming sink: the same pairs in the same order through a two-slot ring of small chunks
+    for cap in (1, 257, 1 << 14):
+        chunks = [(_u32(x).copy(), _u32(y).copy()) for x, y in ix.overlap_pairs_stream(dpc, dps, dpe, fo, max_pairs=cap)]
+        sa = np.concatenate([x for x, _ in chunks]) if chunks else np.zeros(0, np.uint32)
+        sb = np.concatenate([y for _, y in chunks]) if chunks else np.zeros(0, np.uint32)
+        assert np.array_equal(sa, oa) and np.array_equal(sb, ob), cap
     cov = ix.coverage(dpc, dps, dpe, fo).cpu().numpy()
     assert np.array_equal(cov, oix.coverage(pc, ps, pe, strict))
     for k, inc in ks:

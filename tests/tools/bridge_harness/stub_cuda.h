@@ -22,3 +22,13 @@ static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
 static inline cudaError_t cudaMallocAsync(void** p, size_t n, cudaStream_t) { *p = malloc(n); return 0; }
 static inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { free(p); return 0; }
 static inline cudaError_t cudaMemcpyAsync(void*, const void*, size_t, int, cudaStream_t) { return 0; }
+typedef void* cudaEvent_t;
+#define cudaEventDisableTiming 2
+#define cudaHostRegisterPortable 1
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = 0; return 0; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
+static inline cudaError_t cudaHostRegister(void*, size_t, unsigned) { return 0; }
+static inline cudaError_t cudaHostUnregister(void*) { return 0; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return 0; }
