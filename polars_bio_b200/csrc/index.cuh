@@ -57,6 +57,7 @@ struct pbgpu_index {
   int32_t n_contigs = 0;
   int device = 0;
   int has_inverted = 0;  // some indexed row has start > end: rank identity disabled
+  int nested = 0;        // some indexed interval contains a later-starting one (ends not ascending in start order)
   int32_t *seg = nullptr;
   int32_t *st = nullptr, *en = nullptr, *pmax = nullptr, *en_sorted = nullptr;
   uint32_t *row = nullptr, *en_pos = nullptr;
@@ -279,6 +280,98 @@ __global__ void __launch_bounds__(256) build_jdir_kernel(const uint32_t *__restr
   while (ns + ne <= (uint32_t)kJKeys && base_e + ne < mm && (uint64_t)__ldg(ge + base_e + ne) < lo + W) ++ne;
   JRec r;
   if (ns + ne > (uint32_t)kJKeys) {  // crowded: keep the rank ranges
+    r.w[0] = base_s | 0x80000000u;
+    r.w[1] = base_e;
+    r.w[2] = lower_bound_g(gs, base_s + ns, mm, lo + 2 * W);
+    r.w[3] = lower_bound_g(ge, base_e + ne, mm, lo + W);
+    r.w[4] = r.w[5] = r.w[6] = r.w[7] = 0x7FFF7FFFu;
+  } else {
+    r.w[0] = base_s;
+    r.w[1] = base_e - ns;
+    const uint32_t lo32 = (uint32_t)lo;
+#pragma unroll
+    for (int k = 0; k < kJKeys / 2; ++k) {
+      uint32_t f[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t slot = 2 * k + h;
+        uint32_t v = 0x7FFFu;
+        if (slot < ns) v = __ldg(gs + base_s + slot) - lo32;
+        else if (slot < ns + ne) v = 0x4000u | (__ldg(ge + base_e + (slot - ns)) - lo32);
+        f[h] = v;
+      }
+      r.w[2 + k] = f[0] | (f[1] << 16);
+    }
+  }
+  dir[b] = r;
+}
+
+// ---- streaming construction of the joint directory (default; PBGPU_JDIR=search keeps the kernel above) ---------
+// The sorted global-axis arrays already hold every rank: #{g < b*W} is the position of the first entry whose bucket is
+// >= b.  jdir_mark_kernel: one thread per sorted position i computes gs[i], ge[i] (what global_coord_kernel did) and,
+// where the bucket number steps up between i-1 and i, writes i into the rank word (w[0] for starts, w[1] for ends) of
+// every record in (bucket(i-1), bucket(i)]; position m-1 also closes the tail (bucket(m-1), n_buckets] with m.  Total
+// writes = number of records, O(m) loads -- no binary search (build_jdir_kernel: 2 x log2(m) dependent loads per
+// bucket).  Runs longer than 8 records are filled by the whole warp so one large gap cannot serialise a thread.
+__device__ __forceinline__ void jdir_fill_run(JRec *__restrict__ dir, int field, long long first, long long last_incl,
+                                              uint32_t val, bool active) {
+  const int lane = threadIdx.x & 31;
+  const long long len = active ? last_incl - first + 1 : 0;
+  const bool big = len > 8;
+  if (len > 0 && !big)
+    for (long long b = first; b <= last_incl; ++b) dir[b].w[field] = val;
+  unsigned mask = __ballot_sync(0xffffffffu, big);
+  while (mask) {
+    const int src = __ffs(mask) - 1;
+    mask &= mask - 1;
+    const long long f = __shfl_sync(0xffffffffu, first, src), l = __shfl_sync(0xffffffffu, last_incl, src);
+    const uint32_t v = __shfl_sync(0xffffffffu, val, src);
+    for (long long b = f + lane; b <= l; b += 32) dir[b].w[field] = v;
+  }
+}
+__device__ __forceinline__ uint32_t global_coord_of(const uint64_t *__restrict__ keys, int pos_bits, const int32_t *__restrict__ pos,
+                                                    int64_t i, const ContigMap *__restrict__ cmap) {
+  const ContigMap cm = cmap[keys[i] >> pos_bits];
+  return cm.off + (uint32_t)((long long)__ldg(pos + i) - cm.lo_m1);
+}
+__global__ void __launch_bounds__(256) jdir_mark_kernel(const uint64_t *__restrict__ skeys, const uint64_t *__restrict__ ekeys, int pos_bits,
+                                                        const int32_t *__restrict__ st, const int32_t *__restrict__ en_sorted, int64_t m,
+                                                        const ContigMap *__restrict__ cmap, int shift, uint32_t n_buckets,
+                                                        uint32_t *__restrict__ gs, uint32_t *__restrict__ ge, JRec *__restrict__ dir) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // no early return: the warp fills runs together
+  const bool ok = i < m;
+  long long s_prev = -1, s_cur = -1, e_prev = -1, e_cur = -1;
+  if (ok) {
+    const uint32_t g_s = global_coord_of(skeys, pos_bits, st, i, cmap), g_e = global_coord_of(ekeys, pos_bits, en_sorted, i, cmap);
+    gs[i] = g_s;
+    ge[i] = g_e;
+    s_cur = (long long)(g_s >> shift);
+    e_cur = (long long)(g_e >> shift);
+    if (i > 0) {
+      s_prev = (long long)(global_coord_of(skeys, pos_bits, st, i - 1, cmap) >> shift);
+      e_prev = (long long)(global_coord_of(ekeys, pos_bits, en_sorted, i - 1, cmap) >> shift);
+    }
+  }
+  jdir_fill_run(dir, 0, s_prev + 1, s_cur, (uint32_t)i, ok);
+  jdir_fill_run(dir, 1, e_prev + 1, e_cur, (uint32_t)i, ok);
+  const bool last = i == m - 1;
+  jdir_fill_run(dir, 0, s_cur + 1, (long long)n_buckets, (uint32_t)m, last);
+  jdir_fill_run(dir, 1, e_cur + 1, (long long)n_buckets, (uint32_t)m, last);
+}
+// one thread per record: ranks are in w[0] / w[1] (jdir_mark_kernel); pack the keys of its window (same record layout and
+// the same crowded rule as build_jdir_kernel).  Only this thread touches record b, so it rewrites w[0], w[1] in place.
+__global__ void __launch_bounds__(256) jdir_pack_kernel(const uint32_t *__restrict__ gs, const uint32_t *__restrict__ ge, int64_t m,
+                                                        int shift, uint32_t n_buckets, JRec *__restrict__ dir) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > n_buckets) return;
+  const uint64_t lo = (uint64_t)b << shift, W = 1ull << shift;
+  const uint32_t mm = (uint32_t)m;
+  const uint32_t base_s = dir[b].w[0], base_e = dir[b].w[1];
+  uint32_t ns = 0, ne = 0;
+  while (ns <= (uint32_t)kJKeys && base_s + ns < mm && (uint64_t)__ldg(gs + base_s + ns) < lo + 2 * W) ++ns;
+  while (ns + ne <= (uint32_t)kJKeys && base_e + ne < mm && (uint64_t)__ldg(ge + base_e + ne) < lo + W) ++ne;
+  JRec r;
+  if (ns + ne > (uint32_t)kJKeys) {
     r.w[0] = base_s | 0x80000000u;
     r.w[1] = base_e;
     r.w[2] = lower_bound_g(gs, base_s + ns, mm, lo + 2 * W);

@@ -122,6 +122,13 @@ size_t pbgpu_index_bytes(const pbgpu_index *ix) { return ix ? ix->bytes : 0; }
 
 static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// PBGPU_JDIR=search: build the joint directory with one binary search pair per bucket (the first implementation; kept
+// for A/B runs) instead of the streaming mark + pack kernels
+static bool jdir_by_search() {
+  static bool v = [] { const char *e = getenv("PBGPU_JDIR"); return e && !strcmp(e, "search"); }();
+  return v;
+}
+
 static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *d_s, const int32_t *d_e, int64_t m_in,
                             int32_t n_contigs, cudaStream_t s) {
   ix->m_in = m_in;
@@ -201,6 +208,7 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
   PB_CUDA(cudaMemcpyAsync(h_meta, d_meta, sizeof(h_meta), cudaMemcpyDeviceToHost, s));
   PB_CUDA(cudaStreamSynchronize(s));
   const bool nested = h_meta[0] != 0;
+  ix->nested = nested;
 
   // 4. nested intervals: running max of the ends, ends sorted per contig (stable over the start order, so ties keep
   //    (start,row) order) and their positions.  Otherwise the three arrays alias `en` / identity.
@@ -247,9 +255,15 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
     PB_LAUNCH(contig_off_kernel, (unsigned)cdiv(n_contigs, 128), 128, 0, s, d_span, n_contigs, ix->cmap);
     // contig of position i: from the start-sorted keys (start order) or the end-sorted keys (end order; same order
     // as the start keys when nothing is nested)
-    PB_LAUNCH(global_coord_kernel, (unsigned)cdiv(m, 256), 256, 0, s, keys, pos_bits, ix->st, m, ix->cmap, ix->gs);
-    PB_LAUNCH(global_coord_kernel, (unsigned)cdiv(m, 256), 256, 0, s, nested ? ekeys : keys, pos_bits, ix->en_sorted, m, ix->cmap, ix->ge);
-    PB_LAUNCH(build_jdir_kernel, (unsigned)cdiv((int64_t)nb + 1, 256), 256, 0, s, ix->gs, ix->ge, m, shift, nb, ix->jdir);
+    if (jdir_by_search()) {
+      PB_LAUNCH(global_coord_kernel, (unsigned)cdiv(m, 256), 256, 0, s, keys, pos_bits, ix->st, m, ix->cmap, ix->gs);
+      PB_LAUNCH(global_coord_kernel, (unsigned)cdiv(m, 256), 256, 0, s, nested ? ekeys : keys, pos_bits, ix->en_sorted, m, ix->cmap, ix->ge);
+      PB_LAUNCH(build_jdir_kernel, (unsigned)cdiv((int64_t)nb + 1, 256), 256, 0, s, ix->gs, ix->ge, m, shift, nb, ix->jdir);
+    } else {  // streaming: global coordinates + rank words in one pass over the sorted rows, then one pass over the records
+      PB_LAUNCH(jdir_mark_kernel, (unsigned)cdiv(m, 256), 256, 0, s, keys, nested ? ekeys : keys, pos_bits, ix->st, ix->en_sorted, m,
+                ix->cmap, shift, nb, ix->gs, ix->ge, ix->jdir);
+      PB_LAUNCH(jdir_pack_kernel, (unsigned)cdiv((int64_t)nb + 1, 256), 256, 0, s, ix->gs, ix->ge, m, shift, nb, ix->jdir);
+    }
     PB_CHECK_LAUNCH();
     ix->fast = 1;
   }
@@ -378,6 +392,13 @@ int pbgpu_coverage(const pbgpu_index *ix, const int32_t *d_contig, const int32_t
 
 }  // extern "C"
 
+// PBGPU_EMIT=walk: pass 2 always walks the candidate window (the first implementation; kept for A/B runs).  The flat
+// expansion needs the fast path, no nested intervals and 32 x indexed rows < 2^32 (32-bit warp scan of the counts).
+static bool emit_flat_ok(const pbgpu_index *ix) {
+  static bool walk = [] { const char *e = getenv("PBGPU_EMIT"); return e && !strcmp(e, "walk"); }();
+  return !walk && ix->fast && !ix->nested && ix->m < (1ll << 27);
+}
+
 struct pbgpu_overlap_plan {
   const pbgpu_index *ix;
   const int32_t *pc, *ps, *pe;
@@ -388,7 +409,8 @@ struct pbgpu_overlap_plan {
   uint32_t *counts;                 // [n]
   uint32_t *his;                    // [n] start-rank of every probe (fast path only)
   unsigned long long *block_base;   // [nblk] exclusive-scanned block totals
-  void *slab;                       // one stream-ordered allocation behind the three arrays
+  unsigned long long *warp_off;     // [n/32] offset of every 32-probe group inside its block (flat pass 2 only)
+  void *slab;                       // one stream-ordered allocation behind the arrays
   int64_t total;
 };
 
@@ -415,17 +437,20 @@ int pbgpu_overlap_count(const pbgpu_index *ix, const int32_t *d_contig, const in
   cudaStream_t s = (cudaStream_t)stream;
   pbgpu_overlap_plan *p = new (std::nothrow) pbgpu_overlap_plan();
   if (!p) return set_error(PBGPU_ENOMEM, "host allocation failed");
-  *p = pbgpu_overlap_plan{ix, d_contig, d_start, d_end, n, filter_op, 0, cdiv(n, kSweepThreads), nullptr, nullptr, nullptr, nullptr, 0};
+  *p = pbgpu_overlap_plan{ix, d_contig, d_start, d_end, n, filter_op, 0, cdiv(n, kSweepThreads), nullptr, nullptr, nullptr, nullptr, nullptr, 0};
   cudaGetDevice(&p->device);
   auto fail = [&](int rc) { pbgpu_overlap_plan_free(p); return rc; };
   if (n == 0) { *plan = p; return PBGPU_OK; }
   {
     const size_t cb = align_up(sizeof(uint32_t) * (size_t)n), bb = align_up(sizeof(unsigned long long) * (size_t)(p->nblk + 1));
-    int rc0 = dev_alloc(&p->slab, 2 * cb + bb, s);
+    const bool flat = emit_flat_ok(ix);
+    const size_t wb = flat ? align_up(sizeof(unsigned long long) * (size_t)(p->nblk * (kSweepThreads / 32))) : 0;
+    int rc0 = dev_alloc(&p->slab, 2 * cb + bb + wb, s);
     if (rc0 != PBGPU_OK) return fail(rc0);
     p->counts = (uint32_t *)p->slab;
     p->his = (uint32_t *)((char *)p->slab + cb);
     p->block_base = (unsigned long long *)((char *)p->slab + 2 * cb);
+    if (flat) p->warp_off = (unsigned long long *)((char *)p->slab + 2 * cb + bb);
   }
   g_ev.mark(EV_P1_0, s);
   const unsigned grid = (unsigned)p->nblk;
@@ -433,14 +458,14 @@ int pbgpu_overlap_count(const pbgpu_index *ix, const int32_t *d_contig, const in
     const bool strict = filter_op == PBGPU_FILTER_STRICT;
     const unsigned g2 = (unsigned)cdiv(n, kSweepThreads * 2), g4 = (unsigned)cdiv(n, kSweepThreads * 4);
     if (sweep_items() == 4) {
-      if (strict) PB_LAUNCH((overlap_count_fast_kernel<true, 4>), g4, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->his, p->block_base);
-      else PB_LAUNCH((overlap_count_fast_kernel<false, 4>), g4, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->his, p->block_base);
+      if (strict) PB_LAUNCH((overlap_count_fast_kernel<true, 4>), g4, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->his, p->block_base, p->warp_off);
+      else PB_LAUNCH((overlap_count_fast_kernel<false, 4>), g4, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->his, p->block_base, p->warp_off);
     } else if (sweep_items() == 2) {
-      if (strict) PB_LAUNCH((overlap_count_fast_kernel<true, 2>), g2, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->his, p->block_base);
-      else PB_LAUNCH((overlap_count_fast_kernel<false, 2>), g2, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->his, p->block_base);
+      if (strict) PB_LAUNCH((overlap_count_fast_kernel<true, 2>), g2, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->his, p->block_base, p->warp_off);
+      else PB_LAUNCH((overlap_count_fast_kernel<false, 2>), g2, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->his, p->block_base, p->warp_off);
     } else {
-      if (strict) PB_LAUNCH((overlap_count_fast_kernel<true, 1>), grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->his, p->block_base);
-      else PB_LAUNCH((overlap_count_fast_kernel<false, 1>), grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->his, p->block_base);
+      if (strict) PB_LAUNCH((overlap_count_fast_kernel<true, 1>), grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->his, p->block_base, p->warp_off);
+      else PB_LAUNCH((overlap_count_fast_kernel<false, 1>), grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->his, p->block_base, p->warp_off);
     }
   } else if (filter_op == PBGPU_FILTER_STRICT)
     PB_LAUNCH(overlap_count_kernel<true>, grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->block_base);
@@ -466,7 +491,15 @@ static int emit_blocks_impl(const pbgpu_overlap_plan *p, int64_t blk_lo, int64_t
                             uint32_t *d_probe_rows, uint32_t *d_build_rows, cudaStream_t s) {
   g_ev.mark(EV_EMIT0, s);
   const unsigned grid = (unsigned)(blk_hi - blk_lo);
-  if (p->ix->fast) {
+  if (p->warp_off) {  // fast path over an index without nested intervals: pure expansion of (count, start rank)
+    const unsigned g2 = (unsigned)cdiv(blk_hi - blk_lo, 2);
+    if (p->filter_op == PBGPU_FILTER_STRICT)
+      PB_LAUNCH((overlap_emit_flat_kernel<true, 2>), g2, kSweepThreads, 0, s, view_of(p->ix), p->pc, p->ps, p->pe, p->n, p->counts,
+                p->his, p->block_base, p->warp_off, blk_lo, blk_hi, d_probe_rows, d_build_rows);
+    else
+      PB_LAUNCH((overlap_emit_flat_kernel<false, 2>), g2, kSweepThreads, 0, s, view_of(p->ix), p->pc, p->ps, p->pe, p->n, p->counts,
+                p->his, p->block_base, p->warp_off, blk_lo, blk_hi, d_probe_rows, d_build_rows);
+  } else if (p->ix->fast) {
     if (p->filter_op == PBGPU_FILTER_STRICT)
       PB_LAUNCH(overlap_emit_fast_kernel<true>, grid, kSweepThreads, 0, s, view_of(p->ix), p->pc, p->ps, p->pe, p->n, p->counts,
                 p->his, p->block_base, blk_lo, d_probe_rows, d_build_rows);

@@ -127,10 +127,167 @@ __global__ void __launch_bounds__(kRsThreads) rs_scatter_kernel(const uint64_t *
   }
 }
 
+// ---- single-kernel pass: decoupled look-back ("onesweep") ------------------------------------------------------
+// The digit totals of EVERY pass are permutation-invariant, so one kernel histograms them all up front
+// (rs_hist_all_kernel).  A pass is then ONE kernel: a tile takes a ticket (tiles start in ticket order, so a tile only
+// ever waits on tiles that are already running), ranks its keys exactly like rs_scatter_kernel, publishes its per-digit
+// counts as  count | AGGREGATE  in status[tile][digit], walks back over its predecessors adding their words until it
+// meets an  inclusive-prefix | PREFIX  word, publishes its own inclusive prefix, and scatters.  Flag and count share
+// one 32-bit word (2 + 30 bits, hence n < 2^30 on this path), so no fence is needed between them.
+// HBM traffic per pass: 16 B read + 16 B write per element (+ 8 B once for the histogram) instead of 8 + 16 + 16.
+constexpr uint32_t kLbAgg = 1u << 30, kLbPre = 2u << 30, kLbMask = (1u << 30) - 1u;
+constexpr int kRsMaxPasses = 8;
+
+__global__ void __launch_bounds__(kRsThreads) rs_hist_all_kernel(const uint64_t *__restrict__ keys, int64_t n, int passes,
+                                                                 uint32_t *__restrict__ digit_totals /*[passes][256], zeroed*/) {
+  __shared__ uint32_t h[kRsMaxPasses][kRsRadix];
+  for (int i = threadIdx.x; i < passes * kRsRadix; i += kRsThreads) (&h[0][0])[i] = 0;
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * kRsThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kRsThreads) {
+    const uint64_t k = keys[i];
+    for (int p = 0; p < passes; ++p) atomicAdd(&h[p][(k >> (8 * p)) & 0xff], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < passes * kRsRadix; i += kRsThreads) {
+    const uint32_t v = (&h[0][0])[i];
+    if (v) atomicAdd(digit_totals + i, v);
+  }
+}
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v) {
+  asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(kRsThreads, 2) rs_onesweep_kernel(const uint64_t *__restrict__ keys_in,
+                                                                 const uint64_t *__restrict__ vals_in,
+                                                                 uint64_t *__restrict__ keys_out,
+                                                                 uint64_t *__restrict__ vals_out, int64_t n, int shift,
+                                                                 const uint32_t *__restrict__ digit_totals /*[256] of this pass*/,
+                                                                 uint32_t *status /*[nblk][256], zeroed*/,
+                                                                 uint32_t *ticket /*zeroed*/) {
+  __shared__ uint32_t wcnt[kRsWarps][kRsRadix];
+  __shared__ uint32_t dbase[kRsRadix];
+  __shared__ uint32_t wt[kRsThreads / 32 + 1];
+  __shared__ uint32_t tile_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) tile_s = atomicAdd(ticket, 1u);
+  for (int i = threadIdx.x; i < kRsWarps * kRsRadix; i += kRsThreads) (&wcnt[0][0])[i] = 0;
+  __syncthreads();
+  const uint32_t tile = tile_s;
+
+  const int64_t wbase = (int64_t)tile * kRsTile + (int64_t)warp * (32 * kRsItems);
+  uint64_t k[kRsItems], v[kRsItems];
+  uint32_t rank[kRsItems];
+  const unsigned lt = lanemask_lt();
+#pragma unroll
+  for (int r = 0; r < kRsItems; ++r) {
+    const int64_t i = wbase + r * 32 + lane;
+    const bool ok = i < n;
+    k[r] = ok ? keys_in[i] : 0;
+    v[r] = ok ? vals_in[i] : 0;
+  }
+#pragma unroll
+  for (int r = 0; r < kRsItems; ++r) {
+    const bool ok = wbase + r * 32 + lane < n;
+    const unsigned d = ok ? (unsigned)((k[r] >> shift) & 0xff) : 0x100u;
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const int leader = __ffs(peers) - 1;
+    uint32_t old = 0;
+    if (ok && lane == leader) {
+      old = wcnt[warp][d];
+      wcnt[warp][d] = old + __popc(peers);
+    }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    rank[r] = old + __popc(peers & lt);
+    __syncwarp();
+  }
+  __syncthreads();
+  // global base of every digit: exclusive scan of this pass's totals (all threads take part in the block scan)
+  const uint32_t gbase = block_exclusive<SumU32, kRsThreads>(threadIdx.x < kRsRadix ? digit_totals[threadIdx.x] : 0u, wt);
+  if (threadIdx.x < kRsRadix) {
+    const int d = threadIdx.x;
+    uint32_t run = 0;  // exclusive prefix over warps, per digit; run ends as the tile's count of digit d
+#pragma unroll
+    for (int w = 0; w < kRsWarps; ++w) {
+      const uint32_t t = wcnt[w][d];
+      wcnt[w][d] = run;
+      run += t;
+    }
+    uint32_t *mine = status + (size_t)tile * kRsRadix + d;
+    uint32_t excl = 0;
+    if (tile == 0) st_volatile_u32(mine, run | kLbPre);
+    else {
+      st_volatile_u32(mine, run | kLbAgg);
+      for (int64_t t = (int64_t)tile - 1;; --t) {  // tile 0 always ends the walk with a PREFIX word
+        const uint32_t *theirs = status + (size_t)t * kRsRadix + d;
+        uint32_t w;
+        do { w = ld_volatile_u32(theirs); } while ((w >> 30) == 0u);
+        excl += w & kLbMask;
+        if (w & kLbPre) break;
+      }
+      st_volatile_u32(mine, (excl + run) | kLbPre);
+    }
+    dbase[d] = gbase + excl;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kRsItems; ++r) {
+    const int64_t i = wbase + r * 32 + lane;
+    if (i < n) {
+      const unsigned d = (unsigned)((k[r] >> shift) & 0xff);
+      const uint32_t dst = dbase[d] + wcnt[warp][d] + rank[r];
+      keys_out[dst] = k[r];
+      vals_out[dst] = v[r];
+    }
+  }
+}
+
+// PBGPU_SORT=3k: the three-kernels-per-pass sort (the first implementation; kept for A/B runs and for n >= 2^30)
+static inline bool rs_three_kernel() {
+  static bool v = [] { const char *e = getenv("PBGPU_SORT"); return e && !strcmp(e, "3k"); }();
+  return v;
+}
+
+inline int radix_sort_pairs_onesweep(uint64_t *keys, uint64_t *vals, int64_t n, int bits, cudaStream_t s) {
+  const int64_t nblk = cdiv(n, kRsTile);
+  const int passes = (bits + 7) / 8;
+  Scratch sc(s);
+  uint64_t *k2 = nullptr, *v2 = nullptr;
+  uint32_t *work = nullptr;  // [passes][256] digit totals | [passes] tickets (padded to 256) | [passes][nblk][256] status
+  PB_TRY(sc.get(&k2, (size_t)n));
+  PB_TRY(sc.get(&v2, (size_t)n));
+  const size_t tot_w = (size_t)passes * kRsRadix, tick_w = kRsRadix, stat_w = (size_t)passes * (size_t)nblk * kRsRadix;
+  PB_TRY(sc.get(&work, tot_w + tick_w + stat_w));
+  PB_CUDA(cudaMemsetAsync(work, 0, sizeof(uint32_t) * (tot_w + tick_w + stat_w), s));
+  uint32_t *totals = work, *tickets = work + tot_w, *status = work + tot_w + tick_w;
+  int64_t hgrid = cdiv(n, (int64_t)kRsThreads * 16);
+  if (hgrid > kSMs * 2) hgrid = kSMs * 2;
+  PB_LAUNCH(rs_hist_all_kernel, (unsigned)hgrid, kRsThreads, 0, s, keys, n, passes, totals);
+  uint64_t *ki = keys, *vi = vals, *ko = k2, *vo = v2;
+  for (int pass = 0; pass < passes; ++pass) {
+    PB_LAUNCH(rs_onesweep_kernel, (unsigned)nblk, kRsThreads, 0, s, ki, vi, ko, vo, n, 8 * pass, totals + (size_t)pass * kRsRadix,
+              status + (size_t)pass * (size_t)nblk * kRsRadix, tickets + pass);
+    uint64_t *t = ki; ki = ko; ko = t;
+    t = vi; vi = vo; vo = t;
+  }
+  PB_CHECK_LAUNCH();
+  if (ki != keys) {
+    PB_CUDA(cudaMemcpyAsync(keys, ki, sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+    PB_CUDA(cudaMemcpyAsync(vals, vi, sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+  }
+  return PBGPU_OK;
+}
+
 // Sorts n pairs by the low `bits` bits of the key.  keys/vals are overwritten with the sorted
 // result (internally ping-pongs with scratch).  n < 2^32.
 inline int radix_sort_pairs(uint64_t *keys, uint64_t *vals, int64_t n, int bits, cudaStream_t s) {
   if (n <= 1 || bits <= 0) return PBGPU_OK;
+  if (n < (int64_t)kLbMask && bits <= 8 * kRsMaxPasses && !rs_three_kernel()) return radix_sort_pairs_onesweep(keys, vals, n, bits, s);
   const int64_t nblk = cdiv(n, kRsTile);
   Scratch sc(s);
   uint64_t *k2 = nullptr, *v2 = nullptr;

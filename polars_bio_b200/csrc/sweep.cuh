@@ -280,7 +280,8 @@ __global__ void __launch_bounds__(kSweepThreads) overlap_count_fast_kernel(Index
                                                                            const int32_t *__restrict__ ps,
                                                                            const int32_t *__restrict__ pe, int64_t n,
                                                                            uint32_t *__restrict__ counts, uint32_t *__restrict__ his,
-                                                                           unsigned long long *__restrict__ block_totals /*[ITEMS per block]*/) {
+                                                                           unsigned long long *__restrict__ block_totals /*[ITEMS per block]*/,
+                                                                           unsigned long long *__restrict__ warp_off /*[n/32] or NULL*/) {
   __shared__ unsigned long long wt[ITEMS][kSweepThreads / 32];
   const int64_t base = (int64_t)blockIdx.x * (kSweepThreads * ITEMS) + threadIdx.x;
   int32_t c[ITEMS], s[ITEMS], e[ITEMS];
@@ -310,6 +311,14 @@ __global__ void __launch_bounds__(kSweepThreads) overlap_count_fast_kernel(Index
     for (int w = 0; w < kSweepThreads / 32; ++w) t += wt[threadIdx.x][w];
     const int64_t blk = (int64_t)blockIdx.x * ITEMS + threadIdx.x;
     if (blk * kSweepThreads < n) block_totals[blk] = t;
+  }
+  // offset of every 32-probe group inside its 256-probe block: lets pass 2 run warp by warp with no block-wide barrier
+  if (warp_off && threadIdx.x < ITEMS * (kSweepThreads / 32)) {
+    const int j = threadIdx.x / (kSweepThreads / 32), w = threadIdx.x % (kSweepThreads / 32);
+    unsigned long long t = 0;
+    for (int k = 0; k < w; ++k) t += wt[j][k];
+    const int64_t g = ((int64_t)blockIdx.x * ITEMS + j) * (kSweepThreads / 32) + w;
+    if (g * 32 < n) warp_off[g] = t;
   }
 }
 
@@ -382,6 +391,86 @@ __global__ void __launch_bounds__(kSweepThreads) overlap_emit_fast_kernel(IndexV
         }
       }
       found += __popc(m);
+    }
+  }
+}
+
+// pass 2 when the indexed intervals do not nest (ends ascend with starts inside every contig -- SNVs, reads, exons of
+// one transcript): the hits of a proper probe are exactly the positions [hi-cnt, hi) of the start order, so pass 2 is
+// a pure expansion of (cnt, hi) into pairs and never looks at a coordinate.  Warp-granular: a warp owns 32
+// consecutive probes, output slot j of the warp belongs to the last probe whose exclusive offset is <= j (five-step
+// shuffle search), so the 32 lanes write 32 CONSECUTIVE pairs per step whatever the individual counts are -- stores
+// coalesce, the work is balanced across lanes and long hit lists need no separate path.  No block-wide barrier:
+// block base (scanned block totals) + the group's offset inside the block (pass 1) + the warp scan (32-bit: the
+// caller takes this kernel only when 32 x indexed rows < 2^32).
+template <bool STRICT, int ITEMS>
+__global__ void __launch_bounds__(kSweepThreads) overlap_emit_flat_kernel(IndexView ix, const int32_t *__restrict__ pc,
+                                                                          const int32_t *__restrict__ ps,
+                                                                          const int32_t *__restrict__ pe, int64_t n,
+                                                                          const uint32_t *__restrict__ counts,
+                                                                          const uint32_t *__restrict__ his,
+                                                                          const unsigned long long *__restrict__ block_base,
+                                                                          const unsigned long long *__restrict__ warp_off,
+                                                                          int64_t blk0, int64_t blk_hi,
+                                                                          uint32_t *__restrict__ out_probe,
+                                                                          uint32_t *__restrict__ out_build) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned long long base0 = block_base[blk0];
+  uint32_t cnt[ITEMS], hi[ITEMS];
+  unsigned long long bbase[ITEMS], woff[ITEMS];
+  int64_t idx[ITEMS];
+#pragma unroll
+  for (int t = 0; t < ITEMS; ++t) {  // every load of the warp's ITEMS groups is in flight before the first use
+    const int64_t blk = blk0 + (int64_t)blockIdx.x * ITEMS + t;
+    const int64_t i = blk * kSweepThreads + threadIdx.x;
+    idx[t] = i;
+    const bool ok = blk < blk_hi && i < n;
+    cnt[t] = ok ? counts[i] : 0u;
+    hi[t] = ok ? his[i] : 0u;
+    const bool gok = blk < blk_hi && (i - lane) < n;
+    woff[t] = gok ? warp_off[blk * (kSweepThreads / 32) + warp] : 0ull;
+    bbase[t] = gok ? block_base[blk] : base0;
+  }
+#pragma unroll
+  for (int t = 0; t < ITEMS; ++t) {
+    uint32_t incl = cnt[t];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) continue;  // warp-uniform
+    const uint32_t excl = incl - cnt[t];
+    const unsigned long long wpos = bbase[t] - base0 + woff[t];
+    const uint32_t first = hi[t] - cnt[t];  // first hit position (garbage for generic probes: never used)
+    const bool generic = cnt[t] && hi[t] == kGenericProbe;
+    if (generic) {  // rare: empty / inverted probe interval, bare predicate over its window
+      const int64_t i = idx[t];
+      int32_t lo, h2;
+      const int32_t c = pc[i], s = ps[i];
+      probe_window<STRICT>(ix, ix.seg[c], ix.seg[c + 1], s, pe[i], lo, h2);
+      unsigned long long p = wpos + excl;
+      for (int32_t j = lo; j < h2; ++j)
+        if (end_hits<STRICT>(__ldg(ix.en + j), s)) { out_probe[p] = (uint32_t)i; out_build[p] = __ldg(ix.row + j); ++p; }
+    }
+    const uint32_t i_first = (uint32_t)(idx[t] - lane);
+    for (uint32_t j0 = 0; j0 < total; j0 += 32) {
+      const uint32_t j = j0 + lane;
+      int p = 0;
+#pragma unroll
+      for (int step = 16; step; step >>= 1) {
+        const int cand = p + step;
+        const uint32_t e = __shfl_sync(0xffffffffu, excl, cand & 31);
+        if (e <= j) p = cand;  // cand <= 31 always: p < 32 - step before the step
+      }
+      const uint32_t e_p = __shfl_sync(0xffffffffu, excl, p);
+      const uint32_t f_p = __shfl_sync(0xffffffffu, first, p);
+      const bool g_p = __shfl_sync(0xffffffffu, (int)generic, p) != 0;
+      if (j < total && !g_p) {
+        out_probe[wpos + j] = i_first + (uint32_t)p;
+        out_build[wpos + j] = __ldg(ix.row + (f_p + (j - e_p)));
+      }
     }
   }
 }

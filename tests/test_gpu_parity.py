@@ -164,6 +164,45 @@ def test_rank_directory_crowded_buckets_and_contig_edges(strict):
     assert cnt.max() > 64
 
 
+@pytest.mark.parametrize("strict", [True, False])
+def test_flat_emit_on_index_without_nested_intervals(strict):
+    """Pass 2 as a pure expansion of (count, start rank) -- taken when no indexed interval contains a later-starting
+    one (fixed-length rows: ends ascend with starts): several contigs, duplicates, probes with 0 / few / >32 / >1000
+    hits in the same warp, empty + inverted + null-keyed probes, streaming block ranges (inside _run_all)."""
+    rng = np.random.default_rng(31)
+    m = 40_000
+    bc = rng.integers(0, 4, m).astype(np.int32)
+    bs = rng.integers(0, 200_000, m).astype(np.int32)
+    bs[:2000] = rng.choice([77, 5000, 5001], 2000)                            # duplicates / crowded buckets
+    be = (bs + 25).astype(np.int32)                                          # fixed length: nothing nests
+    n = 9000
+    pc = rng.integers(0, 5, n).astype(np.int32)                              # contig 4 has no indexed rows
+    ps = rng.integers(-50, 200_100, n).astype(np.int32)
+    ln = rng.choice([0, 1, 10, 150, 700, 30_000], n, p=[0.05, 0.2, 0.3, 0.3, 0.1, 0.05])
+    pe = (ps + ln).astype(np.int32)
+    pe[::17] = ps[::17] - 3                                                  # inverted probes (generic path)
+    pc[::41] = -1
+    cnt = _run_all(pc, ps, pe, bc, bs, be, 5, strict, ks=((1, True), (3, False)))
+    assert cnt.max() > 1000 and (cnt == 0).sum() > 100
+
+
+def test_sort_over_many_tiles_and_directory_gaps():
+    """Index build at a size where the radix sort spans many tiles (decoupled look-back across tiles), with equal
+    keys in different tiles (stability: row order among equal starts), 24 contigs and two far-apart clusters per
+    contig (long runs of empty directory buckets filled by whole warps)."""
+    rng = np.random.default_rng(41)
+    m = 300_000
+    bc = rng.integers(0, 24, m).astype(np.int32)
+    near = rng.random(m) < 0.5
+    bs = np.where(near, rng.integers(0, 4000, m), 90_000_000 + rng.integers(0, 4000, m)).astype(np.int32)
+    be = (bs + 1).astype(np.int32)
+    n = 50_000
+    pc = rng.integers(0, 24, n).astype(np.int32)
+    ps = np.where(rng.random(n) < 0.5, rng.integers(0, 4100, n), 90_000_000 + rng.integers(-100, 4100, n)).astype(np.int32)
+    pe = (ps + rng.integers(1, 6, n)).astype(np.int32)
+    _run_all(pc, ps, pe, bc, bs, be, 24, True, ks=((1, True),))
+
+
 def test_span_beyond_32_bits_takes_generic_path():
     # three contigs spanning ~2^31 each: the global axis does not fit uint32, the index must fall back
     rng = np.random.default_rng(3)
