@@ -110,6 +110,9 @@ PBGPU_API int pbgpu_overlap_emit(const pbgpu_overlap_plan *plan, uint32_t *d_pro
  * Left / LeftDistinct output modes (operation.rs:229-233) are filters over these.           */
 PBGPU_API const uint32_t *pbgpu_overlap_plan_counts(const pbgpu_overlap_plan *plan);
 PBGPU_API void pbgpu_overlap_plan_free(pbgpu_overlap_plan *plan);
+/* same, with the plan's device scratch released in stream order on `stream` (the stream pass 2 was enqueued on):
+ * no host synchronisation is needed between pbgpu_overlap_emit and the free                                     */
+PBGPU_API void pbgpu_overlap_plan_free_async(pbgpu_overlap_plan *plan, void *stream);
 /* Streaming sink (BASELINE config 5: ~1e9 pairs through a bounded buffer).  Pass 1 leaves the
  * exclusive pair offset of every 256-probe block; pass 2 can then be run over any block range [blk_lo, blk_hi)
  * into a buffer of offsets[blk_hi] - offsets[blk_lo] pairs, so a consumer sizes each chunk to its ring slot

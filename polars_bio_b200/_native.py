@@ -86,6 +86,8 @@ def lib() -> ctypes.CDLL:
     L.pbgpu_overlap_plan_counts.restype = vp
     L.pbgpu_overlap_plan_free.argtypes = [vp]
     L.pbgpu_overlap_plan_free.restype = None
+    L.pbgpu_overlap_plan_free_async.argtypes = [vp, vp]
+    L.pbgpu_overlap_plan_free_async.restype = None
     L.pbgpu_nearest.argtypes = [vp, vp, vp, vp, i64, ctypes.c_int, i64, ctypes.c_int, vp, vp, vp]
     L.pbgpu_pack_by_owner.argtypes = [vp, vp, vp, i64, vp, i32, i32, u32, vp, vp, vp]
     L.pbgpu_gather_i32.argtypes = [vp, vp, i64, vp, vp]

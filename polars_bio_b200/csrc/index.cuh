@@ -366,12 +366,35 @@ __global__ void __launch_bounds__(256) jdir_pack_kernel(const uint32_t *__restri
   if (b > n_buckets) return;
   const uint64_t lo = (uint64_t)b << shift, W = 1ull << shift;
   const uint32_t mm = (uint32_t)m;
-  const uint32_t base_s = dir[b].w[0], base_e = dir[b].w[1];
+  const uint2 base = *reinterpret_cast<const uint2 *>(&dir[b].w[0]);
+  const uint32_t base_s = base.x, base_e = base.y;
+  // the first keys of both windows are fetched at once (a record holds ~3 on average): one round trip instead of a
+  // dependent load per key; only fuller records go on one key at a time
+  constexpr int kAhead = 4;
+  uint32_t fs[kAhead], fe[kAhead];
+#pragma unroll
+  for (int k = 0; k < kAhead; ++k) {
+    fs[k] = base_s + k < mm ? __ldg(gs + base_s + k) : 0xFFFFFFFFu;
+    fe[k] = base_e + k < mm ? __ldg(ge + base_e + k) : 0xFFFFFFFFu;
+  }
+  const uint32_t lo32 = (uint32_t)lo;
   uint32_t ns = 0, ne = 0;
-  while (ns <= (uint32_t)kJKeys && base_s + ns < mm && (uint64_t)__ldg(gs + base_s + ns) < lo + 2 * W) ++ns;
-  while (ns + ne <= (uint32_t)kJKeys && base_e + ne < mm && (uint64_t)__ldg(ge + base_e + ne) < lo + W) ++ne;
+  bool more = true;
+#pragma unroll
+  for (int k = 0; k < kAhead; ++k) {
+    if (more && base_s + k < mm && (uint64_t)fs[k] < lo + 2 * W) ++ns; else more = false;
+  }
+  if (more)  // all prefetched starts are inside: continue one by one (counted up to one past the capacity)
+    while (ns <= (uint32_t)kJKeys && base_s + ns < mm && (uint64_t)__ldg(gs + base_s + ns) < lo + 2 * W) ++ns;
+  more = true;
+#pragma unroll
+  for (int k = 0; k < kAhead; ++k) {
+    if (more && base_e + k < mm && (uint64_t)fe[k] < lo + W) ++ne; else more = false;
+  }
+  if (more)
+    while (ns + ne <= (uint32_t)kJKeys && base_e + ne < mm && (uint64_t)__ldg(ge + base_e + ne) < lo + W) ++ne;
   JRec r;
-  if (ns + ne > (uint32_t)kJKeys) {
+  if (ns + ne > (uint32_t)kJKeys) {  // crowded: keep the rank ranges
     r.w[0] = base_s | 0x80000000u;
     r.w[1] = base_e;
     r.w[2] = lower_bound_g(gs, base_s + ns, mm, lo + 2 * W);
@@ -380,7 +403,6 @@ __global__ void __launch_bounds__(256) jdir_pack_kernel(const uint32_t *__restri
   } else {
     r.w[0] = base_s;
     r.w[1] = base_e - ns;
-    const uint32_t lo32 = (uint32_t)lo;
 #pragma unroll
     for (int k = 0; k < kJKeys / 2; ++k) {
       uint32_t f[2];
@@ -388,8 +410,16 @@ __global__ void __launch_bounds__(256) jdir_pack_kernel(const uint32_t *__restri
       for (int h = 0; h < 2; ++h) {
         const uint32_t slot = 2 * k + h;
         uint32_t v = 0x7FFFu;
-        if (slot < ns) v = __ldg(gs + base_s + slot) - lo32;
-        else if (slot < ns + ne) v = 0x4000u | (__ldg(ge + base_e + (slot - ns)) - lo32);
+        if (slot < ns) v = (slot < (uint32_t)kAhead ? fs[slot % kAhead] : __ldg(gs + base_s + slot)) - lo32;  // slot is a constant here
+        else if (slot < ns + ne) {
+          const uint32_t j = slot - ns;
+          uint32_t e = 0;
+          bool got = false;
+#pragma unroll
+          for (int a = 0; a < kAhead; ++a) if (j == (uint32_t)a) { e = fe[a]; got = true; }
+          if (!got) e = __ldg(ge + base_e + j);
+          v = 0x4000u | (e - lo32);
+        }
         f[h] = v;
       }
       r.w[2 + k] = f[0] | (f[1] << 16);

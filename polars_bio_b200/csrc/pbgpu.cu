@@ -76,6 +76,74 @@ struct StageEvents {
 };
 static thread_local StageEvents g_ev;
 
+// ---- host scalars without a copy engine round trip ------------------------------------------------------------
+// The build needs two small device results on the host (coordinate statistics; nested? + axis span) and pass 1 one
+// (the pair total).  cudaMemcpyAsync into pageable memory + cudaStreamSynchronize costs 10-20 us of idle GPU per
+// scalar; instead a one-thread kernel posts the words into a page-locked, device-mapped mailbox followed by a
+// sequence number and the host spins on that number (the write is visible ~1-2 us after it is issued).  If the
+// number does not show up within a bounded spin the stream is synchronised the ordinary way, which also surfaces
+// any kernel fault.  One mailbox per host thread.  PBGPU_SYNC=memcpy keeps the copy-engine path (A/B runs).
+constexpr int kMailboxWords = 16;  // word 15 = sequence number
+__global__ void mailbox_post_kernel(const unsigned long long *__restrict__ src, int n_words, volatile unsigned long long *mb,
+                                    unsigned long long seq) {
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < n_words; ++i) mb[i] = src[i];
+    __threadfence_system();
+    mb[kMailboxWords - 1] = seq;
+  }
+}
+struct Mailbox {
+  volatile unsigned long long *h = nullptr;
+  unsigned long long *d = nullptr;
+  unsigned long long seq = 0;
+  bool tried = false;
+  ~Mailbox() { if (h) cudaFreeHost((void *)h); }
+};
+static thread_local Mailbox g_mailbox;
+static bool sync_by_memcpy() {
+  static bool v = [] { const char *e = getenv("PBGPU_SYNC"); return e && !strcmp(e, "memcpy"); }();
+  return v;
+}
+// copies n_words (<= 15) 64-bit words from device memory to `out`; returns after they have arrived
+int fetch_words(const void *d_src, int n_words, unsigned long long *out, cudaStream_t s) {
+  Mailbox &mb = g_mailbox;
+  if (!mb.tried && !sync_by_memcpy()) {
+    mb.tried = true;
+    void *hp = nullptr, *dp = nullptr;
+    if (cudaHostAlloc(&hp, sizeof(unsigned long long) * kMailboxWords, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess &&
+        cudaHostGetDevicePointer(&dp, hp, 0) == cudaSuccess) {
+      memset(hp, 0, sizeof(unsigned long long) * kMailboxWords);
+      mb.h = (volatile unsigned long long *)hp;
+      mb.d = (unsigned long long *)dp;
+    } else {
+      cudaGetLastError();
+      if (hp) cudaFreeHost(hp);
+    }
+  }
+  if (!mb.h || n_words > kMailboxWords - 1) {
+    PB_CUDA(cudaMemcpyAsync(out, d_src, sizeof(unsigned long long) * (size_t)n_words, cudaMemcpyDeviceToHost, s));
+    PB_CUDA(cudaStreamSynchronize(s));
+    return PBGPU_OK;
+  }
+  const unsigned long long seq = ++mb.seq;
+  PB_LAUNCH(mailbox_post_kernel, 1, 32, 0, s, (const unsigned long long *)d_src, n_words, mb.d, seq);
+  PB_CHECK_LAUNCH();
+  bool arrived = false;
+  for (long spin = 0; spin < 20000000L; ++spin) {  // ~ tens of ms at most
+    if (mb.h[kMailboxWords - 1] == seq) { arrived = true; break; }
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+  if (!arrived) {
+    PB_CUDA(cudaStreamSynchronize(s));  // long-running predecessor or a fault: wait the ordinary way
+    if (mb.h[kMailboxWords - 1] != seq) return set_error(PBGPU_ECUDA, "device result did not arrive in the host mailbox");
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  for (int i = 0; i < n_words; ++i) out[i] = mb.h[i];
+  return PBGPU_OK;
+}
+
 }  // namespace pbgpu
 
 using namespace pbgpu;
@@ -147,8 +215,8 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
     if (grid > kSMs * 8) grid = kSMs * 8;
     PB_LAUNCH(build_stats_kernel, (unsigned)grid, 256, 0, s, d_c, d_s, d_e, m_in, n_contigs, d_stats);
     PB_CHECK_LAUNCH();
-    PB_CUDA(cudaMemcpyAsync(&hs, d_stats, sizeof(hs), cudaMemcpyDeviceToHost, s));
-    PB_CUDA(cudaStreamSynchronize(s));
+    static_assert(sizeof(BuildStats) % 8 == 0 && sizeof(BuildStats) / 8 <= kMailboxWords - 1, "BuildStats must fit the mailbox");
+    PB_TRY(fetch_words(d_stats, (int)(sizeof(BuildStats) / 8), reinterpret_cast<unsigned long long *>(&hs), s));
   }
   const int64_t m = (int64_t)hs.valid;
   ix->m = m;
@@ -205,8 +273,7 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
   }
   PB_CHECK_LAUNCH();
   unsigned long long h_meta[2] = {0, 0};
-  PB_CUDA(cudaMemcpyAsync(h_meta, d_meta, sizeof(h_meta), cudaMemcpyDeviceToHost, s));
-  PB_CUDA(cudaStreamSynchronize(s));
+  PB_TRY(fetch_words(d_meta, 2, h_meta, s));
   const bool nested = h_meta[0] != 0;
   ix->nested = nested;
 
@@ -426,6 +493,16 @@ void pbgpu_overlap_plan_free(pbgpu_overlap_plan *p) {
   delete p;
 }
 
+void pbgpu_overlap_plan_free_async(pbgpu_overlap_plan *p, void *stream) {
+  if (!p) return;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (cur != p->device) cudaSetDevice(p->device);
+  if (p->slab) cudaFreeAsync(p->slab, (cudaStream_t)stream);  // ordered after the pass-2 launches enqueued on `stream`
+  if (cur != p->device) cudaSetDevice(cur);
+  delete p;
+}
+
 const uint32_t *pbgpu_overlap_plan_counts(const pbgpu_overlap_plan *plan) { return plan ? plan->counts : nullptr; }
 
 int pbgpu_overlap_count(const pbgpu_index *ix, const int32_t *d_contig, const int32_t *d_start, const int32_t *d_end, int64_t n,
@@ -478,9 +555,8 @@ int pbgpu_overlap_count(const pbgpu_index *ix, const int32_t *d_contig, const in
   if (rc != PBGPU_OK) return fail(rc);
   g_ev.mark(EV_SCAN1, s);
   unsigned long long h_total = 0;
-  if (cudaMemcpyAsync(&h_total, d_total, sizeof(h_total), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-      cudaStreamSynchronize(s) != cudaSuccess)
-    return fail(set_error(PBGPU_ECUDA, "overlap pass 1 failed: %s", cudaGetErrorString(cudaGetLastError())));
+  rc = fetch_words(d_total, 1, &h_total, s);
+  if (rc != PBGPU_OK) return fail(rc);
   p->total = (int64_t)h_total;
   *total_pairs = p->total;
   *plan = p;

@@ -127,25 +127,42 @@ __global__ void __launch_bounds__(kRsThreads) rs_scatter_kernel(const uint64_t *
   }
 }
 
-// ---- single-kernel pass: decoupled look-back ("onesweep") ------------------------------------------------------
+// ---- single-kernel pass: decoupled look-back ("onesweep") with shared-memory staged stores -----------------------
 // The digit totals of EVERY pass are permutation-invariant, so one kernel histograms them all up front
 // (rs_hist_all_kernel).  A pass is then ONE kernel: a tile takes a ticket (tiles start in ticket order, so a tile only
 // ever waits on tiles that are already running), ranks its keys exactly like rs_scatter_kernel, publishes its per-digit
-// counts as  count | AGGREGATE  in status[tile][digit], walks back over its predecessors adding their words until it
-// meets an  inclusive-prefix | PREFIX  word, publishes its own inclusive prefix, and scatters.  Flag and count share
-// one 32-bit word (2 + 30 bits, hence n < 2^30 on this path), so no fence is needed between them.
-// HBM traffic per pass: 16 B read + 16 B write per element (+ 8 B once for the histogram) instead of 8 + 16 + 16.
+// counts as  count | AGGREGATE  in status[tile][digit], walks back over its predecessors -- a window of kLbWindow
+// status words in flight at a time -- adding their words until it meets an  inclusive-prefix | PREFIX  word, and
+// publishes its own inclusive prefix.  Flag and count share one 32-bit word (2 + 30 bits, hence n < 2^30 on this
+// path), so no fence is needed between them.
+// Stores: a thread-per-key scatter writes 8 bytes to 32 different lines per warp instruction, and the L1TEX t-stage
+// replays a divergent store once per line (~2 cycles each): 2 x n such stores per pass were the whole cost of a pass
+// (r01n: 30 us at 1M rows).  Here the tile is first sorted by digit INSIDE shared memory (key at its local rank), then
+// written out position by position: consecutive positions of one digit go to consecutive global addresses, so a warp
+// store covers a few runs instead of 32 lines.  Values follow through the same staging buffer.
+// HBM traffic per pass: 16 B read + 16 B write per element (+ 8 B once for the histogram).
 constexpr uint32_t kLbAgg = 1u << 30, kLbPre = 2u << 30, kLbMask = (1u << 30) - 1u;
 constexpr int kRsMaxPasses = 8;
+constexpr int kLbWindow = 8;
 
 __global__ void __launch_bounds__(kRsThreads) rs_hist_all_kernel(const uint64_t *__restrict__ keys, int64_t n, int passes,
                                                                  uint32_t *__restrict__ digit_totals /*[passes][256], zeroed*/) {
   __shared__ uint32_t h[kRsMaxPasses][kRsRadix];
   for (int i = threadIdx.x; i < passes * kRsRadix; i += kRsThreads) (&h[0][0])[i] = 0;
   __syncthreads();
-  for (int64_t i = (int64_t)blockIdx.x * kRsThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kRsThreads) {
-    const uint64_t k = keys[i];
-    for (int p = 0; p < passes; ++p) atomicAdd(&h[p][(k >> (8 * p)) & 0xff], 1u);
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * kRsThreads;
+  const int64_t rounds = (n + stride - 1) / stride;  // same trip count for every thread: the warp stays converged
+  for (int64_t r = 0; r < rounds; ++r) {
+    const int64_t i = r * stride + (int64_t)blockIdx.x * kRsThreads + threadIdx.x;
+    const bool ok = i < n;
+    const uint64_t k = ok ? keys[i] : 0;
+    for (int p = 0; p < passes - 1; ++p)
+      if (ok) atomicAdd(&h[p][(k >> (8 * p)) & 0xff], 1u);
+    // top digit: usually a few distinct values (partial digit / contig code) -> one atomic per group, not per key
+    const unsigned d = ok ? (unsigned)((k >> (8 * (passes - 1))) & 0xff) : 0x100u;
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    if (ok && lane == __ffs(peers) - 1) atomicAdd(&h[passes - 1][d], (uint32_t)__popc(peers));
   }
   __syncthreads();
   for (int i = threadIdx.x; i < passes * kRsRadix; i += kRsThreads) {
@@ -164,86 +181,127 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v) {
 }
 
 __global__ void __launch_bounds__(kRsThreads, 2) rs_onesweep_kernel(const uint64_t *__restrict__ keys_in,
-                                                                 const uint64_t *__restrict__ vals_in,
-                                                                 uint64_t *__restrict__ keys_out,
-                                                                 uint64_t *__restrict__ vals_out, int64_t n, int shift,
-                                                                 const uint32_t *__restrict__ digit_totals /*[256] of this pass*/,
-                                                                 uint32_t *status /*[nblk][256], zeroed*/,
-                                                                 uint32_t *ticket /*zeroed*/) {
-  __shared__ uint32_t wcnt[kRsWarps][kRsRadix];
-  __shared__ uint32_t dbase[kRsRadix];
+                                                                    const uint64_t *__restrict__ vals_in,
+                                                                    uint64_t *__restrict__ keys_out,
+                                                                    uint64_t *__restrict__ vals_out, int64_t n, int shift,
+                                                                    const uint32_t *__restrict__ digit_totals /*[256] of this pass*/,
+                                                                    uint32_t *status /*[nblk][256], zeroed*/,
+                                                                    uint32_t *ticket /*zeroed*/) {
+  __shared__ uint64_t stage[kRsTile];            // the tile in digit order: keys, then values
+  __shared__ uint16_t wcnt[kRsWarps][kRsRadix];  // per-warp digit counters (<= 256 keys per warp) -> exclusive warp offsets
+  __shared__ uint32_t dbase[kRsRadix];           // global position of local position 0 of digit d: dst = dbase[d] + local
+  __shared__ uint32_t toff[kRsRadix];            // first local position of digit d
   __shared__ uint32_t wt[kRsThreads / 32 + 1];
   __shared__ uint32_t tile_s;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) tile_s = atomicAdd(ticket, 1u);
-  for (int i = threadIdx.x; i < kRsWarps * kRsRadix; i += kRsThreads) (&wcnt[0][0])[i] = 0;
+  for (int i = threadIdx.x; i < kRsWarps * kRsRadix / 2; i += kRsThreads) ((uint32_t *)&wcnt[0][0])[i] = 0;
   __syncthreads();
   const uint32_t tile = tile_s;
+  const int64_t tbase = (int64_t)tile * kRsTile;
+  const int tile_n = (int)((n - tbase) < (int64_t)kRsTile ? (n - tbase) : (int64_t)kRsTile);
 
-  const int64_t wbase = (int64_t)tile * kRsTile + (int64_t)warp * (32 * kRsItems);
+  // warp w owns the contiguous slice [tbase + w*256, +256): round r covers 32 consecutive keys
+  const int wofs = warp * (32 * kRsItems);
   uint64_t k[kRsItems], v[kRsItems];
-  uint32_t rank[kRsItems];
+  uint32_t q[kRsItems];  // rank inside (warp, digit), later the local position in the tile
   const unsigned lt = lanemask_lt();
 #pragma unroll
   for (int r = 0; r < kRsItems; ++r) {
-    const int64_t i = wbase + r * 32 + lane;
-    const bool ok = i < n;
-    k[r] = ok ? keys_in[i] : 0;
-    v[r] = ok ? vals_in[i] : 0;
+    const int li = wofs + r * 32 + lane;
+    const bool ok = li < tile_n;
+    k[r] = ok ? keys_in[tbase + li] : 0;
+    v[r] = ok ? vals_in[tbase + li] : 0;
   }
 #pragma unroll
   for (int r = 0; r < kRsItems; ++r) {
-    const bool ok = wbase + r * 32 + lane < n;
-    const unsigned d = ok ? (unsigned)((k[r] >> shift) & 0xff) : 0x100u;
+    const bool ok = wofs + r * 32 + lane < tile_n;
+    const unsigned d = ok ? (unsigned)((k[r] >> shift) & 0xff) : 0x100u;  // 0x100: out-of-range lanes group together
     const unsigned peers = __match_any_sync(0xffffffffu, d);
     const int leader = __ffs(peers) - 1;
     uint32_t old = 0;
     if (ok && lane == leader) {
       old = wcnt[warp][d];
-      wcnt[warp][d] = old + __popc(peers);
+      wcnt[warp][d] = (uint16_t)(old + __popc(peers));
     }
     old = __shfl_sync(0xffffffffu, old, leader);
-    rank[r] = old + __popc(peers & lt);
+    q[r] = old + __popc(peers & lt);
     __syncwarp();
   }
   __syncthreads();
-  // global base of every digit: exclusive scan of this pass's totals (all threads take part in the block scan)
-  const uint32_t gbase = block_exclusive<SumU32, kRsThreads>(threadIdx.x < kRsRadix ? digit_totals[threadIdx.x] : 0u, wt);
+  // per digit: exclusive prefix over warps; run = the tile's count of digit d
+  uint32_t run = 0;
   if (threadIdx.x < kRsRadix) {
-    const int d = threadIdx.x;
-    uint32_t run = 0;  // exclusive prefix over warps, per digit; run ends as the tile's count of digit d
 #pragma unroll
     for (int w = 0; w < kRsWarps; ++w) {
-      const uint32_t t = wcnt[w][d];
-      wcnt[w][d] = run;
+      const uint32_t t = wcnt[w][threadIdx.x];
+      wcnt[w][threadIdx.x] = (uint16_t)run;
       run += t;
     }
+  }
+  // global base of every digit (exclusive scan of this pass's totals) and first local position of every digit
+  // (exclusive scan of the tile's counts); all threads take part in the block scans
+  const uint32_t gbase = block_exclusive<SumU32, kRsThreads>(threadIdx.x < kRsRadix ? digit_totals[threadIdx.x] : 0u, wt);
+  __syncthreads();  // wt is reused
+  const uint32_t lbase = block_exclusive<SumU32, kRsThreads>(run, wt);
+  if (threadIdx.x < kRsRadix) {
+    const int d = threadIdx.x;
     uint32_t *mine = status + (size_t)tile * kRsRadix + d;
     uint32_t excl = 0;
     if (tile == 0) st_volatile_u32(mine, run | kLbPre);
     else {
       st_volatile_u32(mine, run | kLbAgg);
-      for (int64_t t = (int64_t)tile - 1;; --t) {  // tile 0 always ends the walk with a PREFIX word
-        const uint32_t *theirs = status + (size_t)t * kRsRadix + d;
-        uint32_t w;
-        do { w = ld_volatile_u32(theirs); } while ((w >> 30) == 0u);
-        excl += w & kLbMask;
-        if (w & kLbPre) break;
+      int64_t t = (int64_t)tile - 1;
+      bool done = false;
+      while (!done) {  // tile 0 always ends the walk with a PREFIX word; positions below it read as an empty PREFIX
+        uint32_t w[kLbWindow];
+#pragma unroll
+        for (int j = 0; j < kLbWindow; ++j) w[j] = (t - j >= 0) ? ld_volatile_u32(status + (size_t)(t - j) * kRsRadix + d) : kLbPre;
+#pragma unroll
+        for (int j = 0; j < kLbWindow; ++j) {
+          if (!done) {
+            while ((w[j] >> 30) == 0u) w[j] = ld_volatile_u32(status + (size_t)(t - j) * kRsRadix + d);  // not published yet
+            excl += w[j] & kLbMask;
+            done = (w[j] & kLbPre) != 0u;
+          }
+        }
+        t -= kLbWindow;
       }
       st_volatile_u32(mine, (excl + run) | kLbPre);
     }
-    dbase[d] = gbase + excl;
+    toff[d] = lbase;
+    dbase[d] = gbase + excl - lbase;  // may wrap below zero: dbase[d] + local position is exact mod 2^32
+  }
+  __syncthreads();
+  // keys to their local rank
+#pragma unroll
+  for (int r = 0; r < kRsItems; ++r) {
+    if (wofs + r * 32 + lane < tile_n) {
+      const unsigned d = (unsigned)((k[r] >> shift) & 0xff);
+      q[r] = toff[d] + wcnt[warp][d] + q[r];
+      stage[q[r]] = k[r];
+    }
+  }
+  __syncthreads();
+  uint32_t dst[kRsItems];
+#pragma unroll
+  for (int r = 0; r < kRsItems; ++r) {
+    const int p = r * kRsThreads + threadIdx.x;
+    if (p < tile_n) {
+      const uint64_t kk = stage[p];
+      dst[r] = dbase[(unsigned)((kk >> shift) & 0xff)] + (uint32_t)p;
+      keys_out[dst[r]] = kk;
+    }
   }
   __syncthreads();
 #pragma unroll
+  for (int r = 0; r < kRsItems; ++r)
+    if (wofs + r * 32 + lane < tile_n) stage[q[r]] = v[r];
+  __syncthreads();
+#pragma unroll
   for (int r = 0; r < kRsItems; ++r) {
-    const int64_t i = wbase + r * 32 + lane;
-    if (i < n) {
-      const unsigned d = (unsigned)((k[r] >> shift) & 0xff);
-      const uint32_t dst = dbase[d] + wcnt[warp][d] + rank[r];
-      keys_out[dst] = k[r];
-      vals_out[dst] = v[r];
-    }
+    const int p = r * kRsThreads + threadIdx.x;
+    if (p < tile_n) vals_out[dst[r]] = stage[p];
   }
 }
 

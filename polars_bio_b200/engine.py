@@ -103,9 +103,9 @@ class DeviceIndex:
                 p = torch.empty(total.value, dtype=torch.int32, device=self.device)
                 b = torch.empty(total.value, dtype=torch.int32, device=self.device)
                 check(self._L.pbgpu_overlap_emit(plan, p.data_ptr(), b.data_ptr(), sp))
-                torch.cuda.current_stream(self.device).synchronize()  # plan scratch is read by the emit kernel
             finally:
-                self._L.pbgpu_overlap_plan_free(plan)
+                # the plan's scratch is read by the emit kernel: released in stream order behind it, no host sync
+                self._L.pbgpu_overlap_plan_free_async(plan, sp)
         return p, b
 
     def overlap_pairs_stream(self, contig, start, end, filter_op: int, max_pairs: int = 1 << 24) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:

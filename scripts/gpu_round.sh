@@ -21,7 +21,7 @@ if [ $RC -ne 0 ]; then
 fi
 
 echo "== A/B variants (device-resident bench, no e2e)"
-for v in "PBGPU_X=default" "PBGPU_JDIR=search" "PBGPU_SORT=3k" "PBGPU_EMIT=walk" "PBGPU_ITEMS=4" $EXTRA_VARIANTS; do
+for v in ${VARIANTS:-PBGPU_X=default PBGPU_JDIR=search PBGPU_SORT=3k PBGPU_EMIT=walk PBGPU_SYNC=memcpy}; do
   n=$(echo "$v" | tr ' =' '__')
   timeout 300 env $v python bench.py --steps 20 --warmup 3 --no-cpu-baseline --skip-e2e > $O/${TAG}_ab_${n}.json 2> $O/${TAG}_ab_${n}.err
   python - "$O/${TAG}_ab_${n}.json" "$v" <<'EOF'
@@ -36,17 +36,21 @@ except Exception as e:
 EOF
 done
 
+if [ -z "$SKIP_BENCH" ]; then
 echo "== bench (full line)"
 timeout 900 python bench.py > $O/${TAG}_bench_1gpu.json 2> $O/${TAG}_bench_1gpu.err
 tail -c 3000 $O/${TAG}_bench_1gpu.json
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $O/${TAG}_bench_ref.json 2> $O/${TAG}_bench_ref.err
 tail -c 600 $O/${TAG}_bench_ref.json
+fi
 
-if [ -z "$SKIP_NCU" ]; then
+if [ -z "$SKIP_NCU_LIST" ]; then
 echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --skip-e2e > $O/${TAG}_ncu_launches.log 2>&1
 echo "ncu launches rc=$?"
+fi
+if [ -z "$SKIP_NCU" ]; then
 echo "== ncu full capture"
 timeout 900 ncu --set full --clock-control none --import-source on \
     -k regex:'overlap_emit|count_overlaps_fast|overlap_count_fast|rs_onesweep|rs_hist_all|jdir_|unpack_sorted|make_start_keys|build_stats' \
@@ -58,5 +62,11 @@ if [ -n "$SCALE_CONFIGS" ]; then
 echo "== full-size configs $SCALE_CONFIGS"
 timeout 900 python tests/tools/scale_check.py $SCALE_CONFIGS > $O/${TAG}_scale.jsonl 2> $O/${TAG}_scale.err
 cat $O/${TAG}_scale.jsonl | cut -c1-1200
+fi
+if [ -n "$SCALE_NCU" ]; then
+echo "== ncu launch list of full-size config $SCALE_NCU"
+PB_REPS=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/${TAG}_scale${SCALE_NCU}_launches.csv \
+    python tests/tools/scale_check.py $SCALE_NCU > $O/${TAG}_scale${SCALE_NCU}_ncu.log 2>&1
+echo "rc=$?"
 fi
 echo "== done"

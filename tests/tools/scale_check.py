@@ -36,7 +36,7 @@ def t(a):
     return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 
 
-def timed(fn, reps=3):
+def timed(fn, reps=int(os.environ.get("PB_REPS", "3"))):
     out = fn(); torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     ms = []
