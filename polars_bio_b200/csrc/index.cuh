@@ -104,22 +104,49 @@ struct BuildStats {  // device-side reduction target
   unsigned long long max_len;  // longest (end - start) over the non-inverted rows
 };
 
-__global__ void __launch_bounds__(256) build_stats_kernel(const int32_t *__restrict__ c, const int32_t *__restrict__ s,
-                                                          const int32_t *__restrict__ e, int64_t n, int32_t n_contigs,
-                                                          BuildStats *st) {
-  __shared__ int sm[4][8];
-  __shared__ unsigned su[3][8];
+// ---- prep: the one pass over the raw input ----------------------------------------------------------------------
+// Per row: sort key  contig << 32 | (start ^ 0x80000000)  (null-keyed rows: contig = n_contigs, so the partition drops
+// them behind the last real contig) and value  end << 32 | row;  per block: coordinate statistics and the histogram of
+// every 8-bit key digit (the radix passes' totals), flushed with one atomic per non-empty bin.  Two rows per thread
+// and iteration so six independent loads are in flight.
+constexpr int kPrepThreads = 512;
+__global__ void __launch_bounds__(kPrepThreads) prep_kernel(const int32_t *__restrict__ c, const int32_t *__restrict__ s,
+                                                            const int32_t *__restrict__ e, int64_t n, int32_t n_contigs, int n_digits,
+                                                            BuildStats *st, uint64_t *__restrict__ keys, uint64_t *__restrict__ vals,
+                                                            uint32_t *__restrict__ digit_totals /*[kRsMaxPasses][256], zeroed*/) {
+  __shared__ uint32_t h[kRsMaxPasses][kRsRadix];
+  __shared__ int sm[4][kPrepThreads / 32];
+  __shared__ unsigned su[3][kPrepThreads / 32];
+  for (int i = threadIdx.x; i < n_digits * kRsRadix; i += kPrepThreads) (&h[0][0])[i] = 0;
+  __syncthreads();
   int mn_s = INT32_MAX, mx_s = INT32_MIN, mn_e = INT32_MAX, mx_e = INT32_MIN;
   unsigned inv = 0, val = 0, mlen = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    int32_t cc = c[i];
-    if (cc < 0 || cc >= n_contigs) continue;
-    int32_t ss = s[i], ee = e[i];
-    mn_s = min(mn_s, ss); mx_s = max(mx_s, ss);
-    mn_e = min(mn_e, ee); mx_e = max(mx_e, ee);
-    inv += ss > ee;
-    if (ee >= ss) mlen = max(mlen, (unsigned)((long long)ee - (long long)ss));
-    ++val;
+  const int64_t stride = (int64_t)gridDim.x * kPrepThreads;
+  for (int64_t i0 = (int64_t)blockIdx.x * kPrepThreads + threadIdx.x; i0 < n; i0 += 2 * stride) {
+    int32_t cc[2], ss[2], ee[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t i = i0 + u * stride;
+      const bool in = i < n;
+      cc[u] = in ? c[i] : -1; ss[u] = in ? s[i] : 0; ee[u] = in ? e[i] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i >= n) continue;
+      const bool ok = cc[u] >= 0 && cc[u] < n_contigs;
+      const uint64_t key = ((ok ? (uint64_t)cc[u] : (uint64_t)n_contigs) << 32) | (ok ? ((uint32_t)ss[u] ^ 0x80000000u) : 0u);
+      keys[i] = key;
+      vals[i] = ((uint64_t)(uint32_t)ee[u] << 32) | (uint32_t)i;
+      for (int p = 0; p < n_digits; ++p) atomicAdd(&h[p][(key >> (8 * p)) & 0xff], 1u);
+      if (ok) {
+        mn_s = min(mn_s, ss[u]); mx_s = max(mx_s, ss[u]);
+        mn_e = min(mn_e, ee[u]); mx_e = max(mx_e, ee[u]);
+        inv += ss[u] > ee[u];
+        if (ee[u] >= ss[u]) mlen = max(mlen, (unsigned)((long long)ee[u] - (long long)ss[u]));
+        ++val;
+      }
+    }
   }
 #pragma unroll
   for (int d = 16; d; d >>= 1) {
@@ -134,39 +161,29 @@ __global__ void __launch_bounds__(256) build_stats_kernel(const int32_t *__restr
   const int w = threadIdx.x >> 5;
   if ((threadIdx.x & 31) == 0) { sm[0][w] = mn_s; sm[1][w] = mx_s; sm[2][w] = mn_e; sm[3][w] = mx_e; su[0][w] = inv; su[1][w] = val; su[2][w] = mlen; }
   __syncthreads();
-  if (threadIdx.x == 0) {  // one set of atomics per block (per-warp atomics on six shared addresses cost 80 us at 1M rows)
-    for (int k = 1; k < 8; ++k) {
+  if (threadIdx.x == 0) {  // one set of atomics per block
+    for (int k = 1; k < kPrepThreads / 32; ++k) {
       sm[0][0] = min(sm[0][0], sm[0][k]); sm[1][0] = max(sm[1][0], sm[1][k]);
       sm[2][0] = min(sm[2][0], sm[2][k]); sm[3][0] = max(sm[3][0], sm[3][k]);
       su[0][0] += su[0][k]; su[1][0] += su[1][k]; su[2][0] = max(su[2][0], su[2][k]);
     }
-    atomicMin(&st->min_start, sm[0][0]); atomicMax(&st->max_start, sm[1][0]);
-    atomicMin(&st->min_end, sm[2][0]); atomicMax(&st->max_end, sm[3][0]);
-    if (su[0][0]) atomicAdd(&st->inverted, (unsigned long long)su[0][0]);
-    atomicAdd(&st->valid, (unsigned long long)su[1][0]);
-    atomicMax(&st->max_len, (unsigned long long)su[2][0]);
+    if (su[1][0]) {
+      atomicMin(&st->min_start, sm[0][0]); atomicMax(&st->max_start, sm[1][0]);
+      atomicMin(&st->min_end, sm[2][0]); atomicMax(&st->max_end, sm[3][0]);
+      if (su[0][0]) atomicAdd(&st->inverted, (unsigned long long)su[0][0]);
+      atomicAdd(&st->valid, (unsigned long long)su[1][0]);
+      atomicMax(&st->max_len, (unsigned long long)su[2][0]);
+    }
+  }
+  for (int i = threadIdx.x; i < n_digits * kRsRadix; i += kPrepThreads) {
+    const uint32_t v = (&h[0][0])[i];
+    if (v) atomicAdd(digit_totals + i, v);
   }
 }
 
-// key = contig << pos_bits | biased start ; value = end << 32 | row.  Null-keyed rows get
-// contig = n_contigs so the partition drops them behind the last real contig.
-__global__ void __launch_bounds__(256) make_start_keys_kernel(const int32_t *__restrict__ c, const int32_t *__restrict__ s,
-                                                              const int32_t *__restrict__ e, int64_t n, int32_t n_contigs,
-                                                              int pos_bits, uint32_t bias, uint64_t *__restrict__ keys,
-                                                              uint64_t *__restrict__ vals) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int32_t cc = c[i];
-  bool ok = cc >= 0 && cc < n_contigs;
-  uint64_t cpart = ok ? (uint64_t)cc : (uint64_t)n_contigs;
-  uint32_t sp = ok ? ((uint32_t)s[i] ^ bias) : 0u;
-  keys[i] = (cpart << pos_bits) | sp;
-  vals[i] = ((uint64_t)(uint32_t)e[i] << 32) | (uint32_t)i;
-}
-
 // unpack the start-sorted pairs into SoA, find the contig segments (boundary detection: the thread that sees a
-// contig change writes seg[] for every contig in between, empty ones included) and count end inversions
-// (en[i] < en[i-1] inside a contig; 0 <=> no nested intervals <=> ends are already sorted in start order).
+// contig change writes seg[] for every contig in between, empty ones included) and flag end inversions
+// (en[i] < en[i-1] inside a contig; none <=> no nested intervals <=> ends are already sorted in start order).
 __global__ void __launch_bounds__(256) unpack_sorted_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ vals,
                                                             int64_t m, int pos_bits, uint32_t bias_s, int32_t n_contigs,
                                                             int32_t *__restrict__ st, int32_t *__restrict__ en,
@@ -192,8 +209,9 @@ __global__ void __launch_bounds__(256) unpack_sorted_kernel(const uint64_t *__re
     for (long long c = prev + 1; c <= contig; ++c) seg[c] = (int32_t)i;
     if (i == m - 1) for (long long c = contig + 1; c <= n_contigs; ++c) seg[c] = (int32_t)m;
   }
-  inv = __ballot_sync(0xffffffffu, inv) ? __popc(__ballot_sync(0xffffffffu, inv)) : 0;
-  if ((threadIdx.x & 31) == 0 && inv) atomicAdd(inversions, (unsigned long long)inv);
+  // only "any inversion at all?" matters: one plain store per warp that saw one (every writer stores the same value;
+  // an atomic per warp on this single address serialised 2.8M updates = 1.2 ms at 90M nested rows)
+  if (__ballot_sync(0xffffffffu, inv) && (threadIdx.x & 31) == 0) *inversions = 1ull;
 }
 
 // nested case only: contig-tagged end keys for the running max and the (contig | end) keys of the second sort
@@ -242,6 +260,29 @@ __global__ void __launch_bounds__(128) contig_span_kernel(const int32_t *__restr
     span[c] = (unsigned long long)(m.hi_p1 - m.lo_m1 + 1);
   }
   cmap[c] = m;
+}
+// small contig tables (<= 1024): spans, their exclusive scan (= slice offsets), the total span and the finished
+// ContigMap in ONE single-block launch (instead of span kernel + scan + copy + offset kernel)
+__global__ void __launch_bounds__(1024) contig_layout_kernel(const int32_t *__restrict__ seg, const int32_t *__restrict__ st,
+                                                             long long max_len, int32_t n_contigs,
+                                                             ContigMap *__restrict__ cmap, unsigned long long *__restrict__ total_span) {
+  __shared__ unsigned long long wt[1024 / 32 + 1];
+  const int c = threadIdx.x;
+  ContigMap m;
+  m.off = 0; m.lo_m1 = 0; m.hi_p1 = 0; m.has = 0;
+  unsigned long long span = 0;
+  if (c < n_contigs) {
+    const int32_t lo = seg[c], hi = seg[c + 1];
+    if (lo < hi) {
+      m.lo_m1 = (long long)st[lo] - 1;
+      m.hi_p1 = (long long)st[hi - 1] + max_len + 1;
+      m.has = 1;
+      span = (unsigned long long)(m.hi_p1 - m.lo_m1 + 1);
+    }
+  }
+  const unsigned long long off = block_exclusive<SumU64, 1024>(span, wt);
+  if (c < n_contigs) { m.off = (uint32_t)off; cmap[c] = m; }  // off is only used when the total fits 32 bits
+  if (threadIdx.x == 0) *total_span = wt[1024 / 32];
 }
 __global__ void __launch_bounds__(128) contig_off_kernel(const unsigned long long *__restrict__ off, int32_t n_contigs,
                                                          ContigMap *__restrict__ cmap) {
@@ -309,24 +350,25 @@ __global__ void __launch_bounds__(256) build_jdir_kernel(const uint32_t *__restr
 // ---- streaming construction of the joint directory (default; PBGPU_JDIR=search keeps the kernel above) ---------
 // The sorted global-axis arrays already hold every rank: #{g < b*W} is the position of the first entry whose bucket is
 // >= b.  jdir_mark_kernel: one thread per sorted position i computes gs[i], ge[i] (what global_coord_kernel did) and,
-// where the bucket number steps up between i-1 and i, writes i into the rank word (w[0] for starts, w[1] for ends) of
-// every record in (bucket(i-1), bucket(i)]; position m-1 also closes the tail (bucket(m-1), n_buckets] with m.  Total
-// writes = number of records, O(m) loads -- no binary search (build_jdir_kernel: 2 x log2(m) dependent loads per
-// bucket).  Runs longer than 8 records are filled by the whole warp so one large gap cannot serialise a thread.
-__device__ __forceinline__ void jdir_fill_run(JRec *__restrict__ dir, int field, long long first, long long last_incl,
+// where the bucket number steps up between i-1 and i, writes i into rank_s[b] / rank_e[b] (compact scratch arrays:
+// neighbouring positions write neighbouring buckets) for every b in (bucket(i-1), bucket(i)]; position m-1 also closes
+// the tail (bucket(m-1), n_buckets] with m.  Total writes = number of records, O(m) loads -- no binary search
+// (build_jdir_kernel: 2 x log2(m) dependent loads per bucket).  Runs longer than 8 buckets are filled by the whole
+// warp so one large gap cannot serialise a thread.
+__device__ __forceinline__ void jdir_fill_run(uint32_t *__restrict__ rank, long long first, long long last_incl,
                                               uint32_t val, bool active) {
   const int lane = threadIdx.x & 31;
   const long long len = active ? last_incl - first + 1 : 0;
   const bool big = len > 8;
   if (len > 0 && !big)
-    for (long long b = first; b <= last_incl; ++b) dir[b].w[field] = val;
+    for (long long b = first; b <= last_incl; ++b) rank[b] = val;
   unsigned mask = __ballot_sync(0xffffffffu, big);
   while (mask) {
     const int src = __ffs(mask) - 1;
     mask &= mask - 1;
     const long long f = __shfl_sync(0xffffffffu, first, src), l = __shfl_sync(0xffffffffu, last_incl, src);
     const uint32_t v = __shfl_sync(0xffffffffu, val, src);
-    for (long long b = f + lane; b <= l; b += 32) dir[b].w[field] = v;
+    for (long long b = f + lane; b <= l; b += 32) rank[b] = v;
   }
 }
 __device__ __forceinline__ uint32_t global_coord_of(const uint64_t *__restrict__ keys, int pos_bits, const int32_t *__restrict__ pos,
@@ -337,7 +379,8 @@ __device__ __forceinline__ uint32_t global_coord_of(const uint64_t *__restrict__
 __global__ void __launch_bounds__(256) jdir_mark_kernel(const uint64_t *__restrict__ skeys, const uint64_t *__restrict__ ekeys, int pos_bits,
                                                         const int32_t *__restrict__ st, const int32_t *__restrict__ en_sorted, int64_t m,
                                                         const ContigMap *__restrict__ cmap, int shift, uint32_t n_buckets,
-                                                        uint32_t *__restrict__ gs, uint32_t *__restrict__ ge, JRec *__restrict__ dir) {
+                                                        uint32_t *__restrict__ gs, uint32_t *__restrict__ ge,
+                                                        uint32_t *__restrict__ rank_s, uint32_t *__restrict__ rank_e) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // no early return: the warp fills runs together
   const bool ok = i < m;
   long long s_prev = -1, s_cur = -1, e_prev = -1, e_cur = -1;
@@ -352,22 +395,22 @@ __global__ void __launch_bounds__(256) jdir_mark_kernel(const uint64_t *__restri
       e_prev = (long long)(global_coord_of(ekeys, pos_bits, en_sorted, i - 1, cmap) >> shift);
     }
   }
-  jdir_fill_run(dir, 0, s_prev + 1, s_cur, (uint32_t)i, ok);
-  jdir_fill_run(dir, 1, e_prev + 1, e_cur, (uint32_t)i, ok);
+  jdir_fill_run(rank_s, s_prev + 1, s_cur, (uint32_t)i, ok);
+  jdir_fill_run(rank_e, e_prev + 1, e_cur, (uint32_t)i, ok);
   const bool last = i == m - 1;
-  jdir_fill_run(dir, 0, s_cur + 1, (long long)n_buckets, (uint32_t)m, last);
-  jdir_fill_run(dir, 1, e_cur + 1, (long long)n_buckets, (uint32_t)m, last);
+  jdir_fill_run(rank_s, s_cur + 1, (long long)n_buckets, (uint32_t)m, last);
+  jdir_fill_run(rank_e, e_cur + 1, (long long)n_buckets, (uint32_t)m, last);
 }
-// one thread per record: ranks are in w[0] / w[1] (jdir_mark_kernel); pack the keys of its window (same record layout and
-// the same crowded rule as build_jdir_kernel).  Only this thread touches record b, so it rewrites w[0], w[1] in place.
+// one thread per record: ranks from jdir_mark_kernel; pack the keys of its window (same record layout and the same
+// crowded rule as build_jdir_kernel).
 __global__ void __launch_bounds__(256) jdir_pack_kernel(const uint32_t *__restrict__ gs, const uint32_t *__restrict__ ge, int64_t m,
-                                                        int shift, uint32_t n_buckets, JRec *__restrict__ dir) {
+                                                        int shift, uint32_t n_buckets, const uint32_t *__restrict__ rank_s,
+                                                        const uint32_t *__restrict__ rank_e, JRec *__restrict__ dir) {
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b > n_buckets) return;
   const uint64_t lo = (uint64_t)b << shift, W = 1ull << shift;
   const uint32_t mm = (uint32_t)m;
-  const uint2 base = *reinterpret_cast<const uint2 *>(&dir[b].w[0]);
-  const uint32_t base_s = base.x, base_e = base.y;
+  const uint32_t base_s = rank_s[b], base_e = rank_e[b];
   // the first keys of both windows are fetched at once (a record holds ~3 on average): one round trip instead of a
   // dependent load per key; only fuller records go on one key at a time
   constexpr int kAhead = 4;

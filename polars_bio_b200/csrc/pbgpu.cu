@@ -205,15 +205,31 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
   g_ev.mark(EV_BUILD0, s);
   struct MarkEnd { cudaStream_t s; ~MarkEnd() { g_ev.mark(EV_BUILD1, s); } } mark_end{s};
   Scratch sc(s);
-  // 1. domain of the coordinates (decides key width and whether the rank identity is safe)
+  // 1. ONE pass over the input: coordinate statistics (key width, fast-path eligibility), the sort keys
+  //    contig << 32 | biased start  with values  end << 32 | row, and the digit totals of every radix pass.
+  //    The key format does not depend on the statistics, so nothing waits for the host before it.
+  const int contig_bits = bit_length_u32((uint32_t)n_contigs);  // codes 0..n_contigs (sentinel included)
+  const int contig_digits = (contig_bits + 7) / 8;
+  constexpr int pos_bits = 32;
+  constexpr uint32_t bias = 0x80000000u;
   BuildStats hs = {INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN, 0ull, 0ull, 0ull};
+  uint64_t *keys = nullptr, *vals = nullptr, *keys2 = nullptr, *vals2 = nullptr;
+  uint32_t *d_totals = nullptr;
   if (m_in > 0) {
-    BuildStats *d_stats = nullptr;
-    PB_TRY(sc.get(&d_stats, 1));
+    PB_TRY(sc.get(&keys, (size_t)m_in));
+    PB_TRY(sc.get(&vals, (size_t)m_in));
+    PB_TRY(sc.get(&keys2, (size_t)m_in));
+    PB_TRY(sc.get(&vals2, (size_t)m_in));
+    char *d_prep = nullptr;  // BuildStats | digit totals [kRsMaxPasses][256]
+    const size_t stats_b = align_up(sizeof(BuildStats)), tot_b = sizeof(uint32_t) * kRsMaxPasses * kRsRadix;
+    PB_TRY(sc.get(&d_prep, stats_b + tot_b));
+    BuildStats *d_stats = (BuildStats *)d_prep;
+    d_totals = (uint32_t *)(d_prep + stats_b);
+    PB_CUDA(cudaMemsetAsync(d_prep, 0, stats_b + tot_b, s));
     PB_CUDA(cudaMemcpyAsync(d_stats, &hs, sizeof(hs), cudaMemcpyHostToDevice, s));
-    int64_t grid = cdiv(m_in, 256 * 8);
-    if (grid > kSMs * 8) grid = kSMs * 8;
-    PB_LAUNCH(build_stats_kernel, (unsigned)grid, 256, 0, s, d_c, d_s, d_e, m_in, n_contigs, d_stats);
+    int64_t grid = cdiv(m_in, kPrepThreads * 2);
+    if (grid > kSMs * 2) grid = kSMs * 2;
+    PB_LAUNCH(prep_kernel, (unsigned)grid, kPrepThreads, 0, s, d_c, d_s, d_e, m_in, n_contigs, 4 + contig_digits, d_stats, keys, vals, d_totals);
     PB_CHECK_LAUNCH();
     static_assert(sizeof(BuildStats) % 8 == 0 && sizeof(BuildStats) / 8 <= kMailboxWords - 1, "BuildStats must fit the mailbox");
     PB_TRY(fetch_words(d_stats, (int)(sizeof(BuildStats) / 8), reinterpret_cast<unsigned long long *>(&hs), s));
@@ -239,21 +255,24 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
     PB_CUDA(cudaMemsetAsync(ix->seg, 0, sizeof(int32_t) * ((size_t)n_contigs + 2), s));
     return PBGPU_OK;
   }
-  const int mn = hs.min_start < hs.min_end ? hs.min_start : hs.min_end;
-  const int mx = hs.max_start > hs.max_end ? hs.max_start : hs.max_end;
-  uint32_t bias = 0;
-  int pos_bits;
-  if (mn >= 0) { pos_bits = bit_length_u32((uint32_t)mx); if (pos_bits < 1) pos_bits = 1; }
-  else { bias = 0x80000000u; pos_bits = 32; }
-  const int contig_bits = bit_length_u32((uint32_t)n_contigs);  // codes 0..n_contigs (sentinel included)
 
-  // 2. radix partition by contig + sort by start: one stable LSD sort of (contig|start) keys
-  uint64_t *keys = nullptr, *vals = nullptr;
-  PB_TRY(sc.get(&keys, (size_t)m_in));
-  PB_TRY(sc.get(&vals, (size_t)m_in));
-  PB_LAUNCH(make_start_keys_kernel, (unsigned)cdiv(m_in, 256), 256, 0, s, d_c, d_s, d_e, m_in, n_contigs, pos_bits, bias, keys, vals);
-  PB_CHECK_LAUNCH();
-  PB_TRY(radix_sort_pairs(keys, vals, m_in, pos_bits + contig_bits, s));
+  // 2. radix partition by contig + sort by start: one stable LSD sort of the (contig | start) keys.  Only digits
+  //    that can differ are sorted: every biased start lies between the biased min and max, so they agree above the
+  //    highest bit of min ^ max; the contig digits are needed when there is more than one contig or a null key
+  //    (sentinel code n_contigs, which must end up behind every real contig).
+  auto varying_digits = [](int32_t lo, int32_t hi, int *pos, int np) {
+    const int vb = bit_length_u32((uint32_t)lo ^ (uint32_t)hi);
+    for (int p = 0; p * 8 < vb; ++p) pos[np++] = p;
+    return np;
+  };
+  int dpos[kRsMaxPasses], ndig = varying_digits(hs.min_start, hs.max_start, dpos, 0);
+  const bool contig_passes = n_contigs > 1 || m < m_in;
+  if (contig_passes) for (int q = 0; q < contig_digits; ++q) dpos[ndig++] = 4 + q;
+  SortedPairs sorted;
+  PB_TRY(radix_sort_digits(keys, vals, keys2, vals2, m_in, dpos, ndig, d_totals, s, &sorted));
+  uint64_t *keys_alt = sorted.keys == keys ? keys2 : keys, *vals_alt = sorted.vals == vals ? vals2 : vals;  // free for reuse
+  keys = sorted.keys;
+  vals = sorted.vals;
 
   // 3. unpack + segments + nested-interval detection; contig slices of the global axis.  One host round trip then
   //    decides two things: second sort needed (nested intervals)?  global axis fits 32 bits (fast path)?
@@ -267,9 +286,14 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
   PB_CUDA(cudaMemsetAsync(d_meta, 0, 2 * sizeof(unsigned long long), s));
   PB_LAUNCH(unpack_sorted_kernel, (unsigned)cdiv(m, 256), 256, 0, s, keys, vals, m, pos_bits, bias, n_contigs, ix->st, ix->en, ix->row,
             ix->er, ix->seg, d_meta);
+  const bool small_table = n_contigs <= 1024;
   if (try_fast) {
-    PB_LAUNCH(contig_span_kernel, (unsigned)cdiv(n_contigs, 128), 128, 0, s, ix->seg, ix->st, (long long)hs.max_len, n_contigs, d_cmap_tmp, d_span);
-    PB_TRY((device_scan<SumU64, false>(d_span, d_span, n_contigs, d_meta + 1, s)));
+    if (small_table)
+      PB_LAUNCH(contig_layout_kernel, 1, 1024, 0, s, ix->seg, ix->st, (long long)hs.max_len, n_contigs, d_cmap_tmp, d_meta + 1);
+    else {
+      PB_LAUNCH(contig_span_kernel, (unsigned)cdiv(n_contigs, 128), 128, 0, s, ix->seg, ix->st, (long long)hs.max_len, n_contigs, d_cmap_tmp, d_span);
+      PB_TRY((device_scan<SumU64, false>(d_span, d_span, n_contigs, d_meta + 1, s)));
+    }
   }
   PB_CHECK_LAUNCH();
   unsigned long long h_meta[2] = {0, 0};
@@ -286,16 +310,22 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
     ix->pmax = (int32_t *)ix->slab_n;
     ix->en_sorted = (int32_t *)((char *)ix->slab_n + arr_b);
     ix->en_pos = (uint32_t *)((char *)ix->slab_n + 2 * arr_b);
-    uint64_t *pm_keys = nullptr, *evals = nullptr;
-    PB_TRY(sc.get(&pm_keys, (size_t)m));
+    uint64_t *pm_keys = keys_alt, *evals = nullptr, *ekeys2 = vals_alt, *evals2 = nullptr;  // the sort's idle buffers are reused
     PB_TRY(sc.get(&ekeys, (size_t)m));
     PB_TRY(sc.get(&evals, (size_t)m));
+    PB_TRY(sc.get(&evals2, (size_t)m));
     PB_LAUNCH(make_end_keys_kernel, (unsigned)cdiv(m, 256), 256, 0, s, keys, ix->en, m, pos_bits, bias, pm_keys, ekeys, evals);
     PB_CHECK_LAUNCH();
     PB_TRY((device_scan<MaxU64, true>((const unsigned long long *)pm_keys, (unsigned long long *)pm_keys, m, nullptr, s)));
     PB_LAUNCH(unpack_pmax_kernel, (unsigned)cdiv(m, 256), 256, 0, s, pm_keys, m, ix->pmax);
-    PB_TRY(radix_sort_pairs(ekeys, evals, m, pos_bits + contig_bits, s));
-    PB_LAUNCH(unpack_ends_kernel, (unsigned)cdiv(m, 256), 256, 0, s, ekeys, evals, m, pos_bits, bias, ix->en_sorted, ix->en_pos);
+    // the rows are already grouped by contig: sorting the varying end digits stably, then the contig digits, gives
+    // (contig, end, start, row) order
+    int epos[kRsMaxPasses], ne = varying_digits(hs.min_end, hs.max_end, epos, 0);
+    if (n_contigs > 1) for (int q = 0; q < contig_digits; ++q) epos[ne++] = 4 + q;
+    SortedPairs es;
+    PB_TRY(radix_sort_digits(ekeys, evals, ekeys2, evals2, m, epos, ne, nullptr, s, &es));
+    ekeys = es.keys;
+    PB_LAUNCH(unpack_ends_kernel, (unsigned)cdiv(m, 256), 256, 0, s, es.keys, es.vals, m, pos_bits, bias, ix->en_sorted, ix->en_pos);
     PB_CHECK_LAUNCH();
   }
 
@@ -319,7 +349,7 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
     ix->shift = shift;
     ix->n_buckets = nb;
     PB_CUDA(cudaMemcpyAsync(ix->cmap, d_cmap_tmp, sizeof(ContigMap) * (size_t)n_contigs, cudaMemcpyDeviceToDevice, s));
-    PB_LAUNCH(contig_off_kernel, (unsigned)cdiv(n_contigs, 128), 128, 0, s, d_span, n_contigs, ix->cmap);
+    if (!small_table) PB_LAUNCH(contig_off_kernel, (unsigned)cdiv(n_contigs, 128), 128, 0, s, d_span, n_contigs, ix->cmap);
     // contig of position i: from the start-sorted keys (start order) or the end-sorted keys (end order; same order
     // as the start keys when nothing is nested)
     if (jdir_by_search()) {
@@ -327,9 +357,12 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
       PB_LAUNCH(global_coord_kernel, (unsigned)cdiv(m, 256), 256, 0, s, nested ? ekeys : keys, pos_bits, ix->en_sorted, m, ix->cmap, ix->ge);
       PB_LAUNCH(build_jdir_kernel, (unsigned)cdiv((int64_t)nb + 1, 256), 256, 0, s, ix->gs, ix->ge, m, shift, nb, ix->jdir);
     } else {  // streaming: global coordinates + rank words in one pass over the sorted rows, then one pass over the records
+      uint32_t *rank_s = nullptr, *rank_e = nullptr;
+      PB_TRY(sc.get(&rank_s, (size_t)nb + 1));
+      PB_TRY(sc.get(&rank_e, (size_t)nb + 1));
       PB_LAUNCH(jdir_mark_kernel, (unsigned)cdiv(m, 256), 256, 0, s, keys, nested ? ekeys : keys, pos_bits, ix->st, ix->en_sorted, m,
-                ix->cmap, shift, nb, ix->gs, ix->ge, ix->jdir);
-      PB_LAUNCH(jdir_pack_kernel, (unsigned)cdiv((int64_t)nb + 1, 256), 256, 0, s, ix->gs, ix->ge, m, shift, nb, ix->jdir);
+                ix->cmap, shift, nb, ix->gs, ix->ge, rank_s, rank_e);
+      PB_LAUNCH(jdir_pack_kernel, (unsigned)cdiv((int64_t)nb + 1, 256), 256, 0, s, ix->gs, ix->ge, m, shift, nb, rank_s, rank_e, ix->jdir);
     }
     PB_CHECK_LAUNCH();
     ix->fast = 1;

@@ -150,19 +150,16 @@ __global__ void __launch_bounds__(kRsThreads) rs_hist_all_kernel(const uint64_t 
   __shared__ uint32_t h[kRsMaxPasses][kRsRadix];
   for (int i = threadIdx.x; i < passes * kRsRadix; i += kRsThreads) (&h[0][0])[i] = 0;
   __syncthreads();
-  const int lane = threadIdx.x & 31;
+  constexpr int U = 4;  // loads in flight per thread (a one-load loop was latency-bound: 12 us at 1M keys)
   const int64_t stride = (int64_t)gridDim.x * kRsThreads;
-  const int64_t rounds = (n + stride - 1) / stride;  // same trip count for every thread: the warp stays converged
-  for (int64_t r = 0; r < rounds; ++r) {
-    const int64_t i = r * stride + (int64_t)blockIdx.x * kRsThreads + threadIdx.x;
-    const bool ok = i < n;
-    const uint64_t k = ok ? keys[i] : 0;
-    for (int p = 0; p < passes - 1; ++p)
-      if (ok) atomicAdd(&h[p][(k >> (8 * p)) & 0xff], 1u);
-    // top digit: usually a few distinct values (partial digit / contig code) -> one atomic per group, not per key
-    const unsigned d = ok ? (unsigned)((k >> (8 * (passes - 1))) & 0xff) : 0x100u;
-    const unsigned peers = __match_any_sync(0xffffffffu, d);
-    if (ok && lane == __ffs(peers) - 1) atomicAdd(&h[passes - 1][d], (uint32_t)__popc(peers));
+  for (int64_t i0 = (int64_t)blockIdx.x * kRsThreads + threadIdx.x; i0 < n; i0 += stride * U) {
+    uint64_t k[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { const int64_t i = i0 + u * stride; k[u] = i < n ? keys[i] : 0; }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (i0 + u * stride < n)
+        for (int p = 0; p < passes; ++p) atomicAdd(&h[p][(k[u] >> (8 * p)) & 0xff], 1u);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < passes * kRsRadix; i += kRsThreads) {
@@ -311,65 +308,81 @@ static inline bool rs_three_kernel() {
   return v;
 }
 
-inline int radix_sort_pairs_onesweep(uint64_t *keys, uint64_t *vals, int64_t n, int bits, cudaStream_t s) {
+struct SortedPairs { uint64_t *keys, *vals; };
+
+// Stable LSD sort of n pairs over the listed 8-bit digit positions (digit p = key bits [8p, 8p+8)), lowest first.
+// Ping-pongs between (keys, vals) and (k2, v2); *out says where the sorted pairs ended up (no copy back).
+// totals_by_pos: digit totals [kRsMaxPasses][256] indexed by digit position, when the caller already has them
+// (the build's prep kernel); NULL = histogram here.
+inline int radix_sort_digits(uint64_t *keys, uint64_t *vals, uint64_t *k2, uint64_t *v2, int64_t n, const int *digit_pos, int npass,
+                             const uint32_t *totals_by_pos, cudaStream_t s, SortedPairs *out) {
+  out->keys = keys;
+  out->vals = vals;
+  if (n <= 1 || npass <= 0) return PBGPU_OK;
   const int64_t nblk = cdiv(n, kRsTile);
-  const int passes = (bits + 7) / 8;
+  int max_pos = 0;
+  for (int p = 0; p < npass; ++p) {
+    if (digit_pos[p] < 0 || digit_pos[p] >= kRsMaxPasses) return set_error(PBGPU_EINVAL, "bad digit position %d", digit_pos[p]);
+    if (digit_pos[p] > max_pos) max_pos = digit_pos[p];
+  }
   Scratch sc(s);
-  uint64_t *k2 = nullptr, *v2 = nullptr;
-  uint32_t *work = nullptr;  // [passes][256] digit totals | [passes] tickets (padded to 256) | [passes][nblk][256] status
-  PB_TRY(sc.get(&k2, (size_t)n));
-  PB_TRY(sc.get(&v2, (size_t)n));
-  const size_t tot_w = (size_t)passes * kRsRadix, tick_w = kRsRadix, stat_w = (size_t)passes * (size_t)nblk * kRsRadix;
-  PB_TRY(sc.get(&work, tot_w + tick_w + stat_w));
-  PB_CUDA(cudaMemsetAsync(work, 0, sizeof(uint32_t) * (tot_w + tick_w + stat_w), s));
-  uint32_t *totals = work, *tickets = work + tot_w, *status = work + tot_w + tick_w;
-  int64_t hgrid = cdiv(n, (int64_t)kRsThreads * 16);
-  if (hgrid > kSMs * 2) hgrid = kSMs * 2;
-  PB_LAUNCH(rs_hist_all_kernel, (unsigned)hgrid, kRsThreads, 0, s, keys, n, passes, totals);
   uint64_t *ki = keys, *vi = vals, *ko = k2, *vo = v2;
-  for (int pass = 0; pass < passes; ++pass) {
-    PB_LAUNCH(rs_onesweep_kernel, (unsigned)nblk, kRsThreads, 0, s, ki, vi, ko, vo, n, 8 * pass, totals + (size_t)pass * kRsRadix,
-              status + (size_t)pass * (size_t)nblk * kRsRadix, tickets + pass);
-    uint64_t *t = ki; ki = ko; ko = t;
-    t = vi; vi = vo; vo = t;
+  if (n < (int64_t)kLbMask && !rs_three_kernel()) {
+    uint32_t *work = nullptr;  // [kRsMaxPasses][256] digit totals (when not supplied) | tickets (256) | [npass][nblk][256] status
+    const size_t tot_w = totals_by_pos ? 0 : (size_t)kRsMaxPasses * kRsRadix, tick_w = kRsRadix, stat_w = (size_t)npass * (size_t)nblk * kRsRadix;
+    PB_TRY(sc.get(&work, tot_w + tick_w + stat_w));
+    PB_CUDA(cudaMemsetAsync(work, 0, sizeof(uint32_t) * (tot_w + tick_w + stat_w), s));
+    uint32_t *tickets = work + tot_w, *status = work + tot_w + tick_w;
+    if (!totals_by_pos) {
+      int64_t hgrid = cdiv(n, (int64_t)kRsThreads * 4);
+      if (hgrid > kSMs * 4) hgrid = kSMs * 4;
+      PB_LAUNCH(rs_hist_all_kernel, (unsigned)hgrid, kRsThreads, 0, s, keys, n, max_pos + 1, work);
+      totals_by_pos = work;
+    }
+    for (int p = 0; p < npass; ++p) {
+      PB_LAUNCH(rs_onesweep_kernel, (unsigned)nblk, kRsThreads, 0, s, ki, vi, ko, vo, n, 8 * digit_pos[p],
+                totals_by_pos + (size_t)digit_pos[p] * kRsRadix, status + (size_t)p * (size_t)nblk * kRsRadix, tickets + p);
+      uint64_t *t = ki; ki = ko; ko = t;
+      t = vi; vi = vo; vo = t;
+    }
+    PB_CHECK_LAUNCH();
+  } else {
+    uint32_t *hist = nullptr, *totals = nullptr;
+    PB_TRY(sc.get(&hist, (size_t)(nblk * kRsRadix)));
+    PB_TRY(sc.get(&totals, (size_t)npass * kRsRadix));
+    PB_CUDA(cudaMemsetAsync(totals, 0, sizeof(uint32_t) * (size_t)npass * kRsRadix, s));
+    for (int p = 0; p < npass; ++p) {
+      uint32_t *tot = totals + p * kRsRadix;
+      const int shift = 8 * digit_pos[p];
+      PB_LAUNCH(rs_hist_kernel, (unsigned)nblk, kRsThreads, 0, s, ki, n, shift, hist, nblk, tot);
+      PB_LAUNCH(rs_offsets_kernel, kRsRadix / 8, 256, 0, s, hist, nblk, tot);
+      PB_LAUNCH(rs_scatter_kernel, (unsigned)nblk, kRsThreads, 0, s, ki, vi, ko, vo, n, shift, hist, nblk);
+      PB_CHECK_LAUNCH();
+      uint64_t *t = ki; ki = ko; ko = t;
+      t = vi; vi = vo; vo = t;
+    }
   }
-  PB_CHECK_LAUNCH();
-  if (ki != keys) {
-    PB_CUDA(cudaMemcpyAsync(keys, ki, sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToDevice, s));
-    PB_CUDA(cudaMemcpyAsync(vals, vi, sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToDevice, s));
-  }
+  out->keys = ki;
+  out->vals = vi;
   return PBGPU_OK;
 }
 
-// Sorts n pairs by the low `bits` bits of the key.  keys/vals are overwritten with the sorted
-// result (internally ping-pongs with scratch).  n < 2^32.
+// Sorts n pairs by the low `bits` bits of the key.  keys/vals are overwritten with the sorted result.  n < 2^32.
 inline int radix_sort_pairs(uint64_t *keys, uint64_t *vals, int64_t n, int bits, cudaStream_t s) {
   if (n <= 1 || bits <= 0) return PBGPU_OK;
-  if (n < (int64_t)kLbMask && bits <= 8 * kRsMaxPasses && !rs_three_kernel()) return radix_sort_pairs_onesweep(keys, vals, n, bits, s);
-  const int64_t nblk = cdiv(n, kRsTile);
+  if (bits > 8 * kRsMaxPasses) bits = 8 * kRsMaxPasses;
   Scratch sc(s);
   uint64_t *k2 = nullptr, *v2 = nullptr;
-  uint32_t *hist = nullptr;
   PB_TRY(sc.get(&k2, (size_t)n));
   PB_TRY(sc.get(&v2, (size_t)n));
-  PB_TRY(sc.get(&hist, (size_t)(nblk * kRsRadix)));
-  uint32_t *totals = nullptr;
-  const int passes = (bits + 7) / 8;
-  PB_TRY(sc.get(&totals, (size_t)passes * kRsRadix));
-  PB_CUDA(cudaMemsetAsync(totals, 0, sizeof(uint32_t) * (size_t)passes * kRsRadix, s));
-  uint64_t *ki = keys, *vi = vals, *ko = k2, *vo = v2;
-  for (int shift = 0, pass = 0; shift < bits; shift += 8, ++pass) {
-    uint32_t *tot = totals + pass * kRsRadix;
-    PB_LAUNCH(rs_hist_kernel, (unsigned)nblk, kRsThreads, 0, s, ki, n, shift, hist, nblk, tot);
-    PB_LAUNCH(rs_offsets_kernel, kRsRadix / 8, 256, 0, s, hist, nblk, tot);
-    PB_LAUNCH(rs_scatter_kernel, (unsigned)nblk, kRsThreads, 0, s, ki, vi, ko, vo, n, shift, hist, nblk);
-    PB_CHECK_LAUNCH();
-    uint64_t *t = ki; ki = ko; ko = t;
-    t = vi; vi = vo; vo = t;
-  }
-  if (ki != keys) {
-    PB_CUDA(cudaMemcpyAsync(keys, ki, sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToDevice, s));
-    PB_CUDA(cudaMemcpyAsync(vals, vi, sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+  int pos[kRsMaxPasses];
+  const int npass = (bits + 7) / 8;
+  for (int p = 0; p < npass; ++p) pos[p] = p;
+  SortedPairs r;
+  PB_TRY(radix_sort_digits(keys, vals, k2, v2, n, pos, npass, nullptr, s, &r));
+  if (r.keys != keys) {
+    PB_CUDA(cudaMemcpyAsync(keys, r.keys, sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+    PB_CUDA(cudaMemcpyAsync(vals, r.vals, sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToDevice, s));
   }
   return PBGPU_OK;
 }

@@ -69,4 +69,9 @@ PB_REPS=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none 
     python tests/tools/scale_check.py $SCALE_NCU > $O/${TAG}_scale${SCALE_NCU}_ncu.log 2>&1
 echo "rc=$?"
 fi
+if [ -n "$E2E_TRACE" ]; then
+echo "== e2e trace"
+timeout 300 python scripts/e2e_trace.py > $O/${TAG}_e2e_trace.log 2>&1
+tail -40 $O/${TAG}_e2e_trace.log
+fi
 echo "== done"
