@@ -209,9 +209,10 @@ __global__ void __launch_bounds__(256) unpack_sorted_kernel(const uint64_t *__re
     for (long long c = prev + 1; c <= contig; ++c) seg[c] = (int32_t)i;
     if (i == m - 1) for (long long c = contig + 1; c <= n_contigs; ++c) seg[c] = (int32_t)m;
   }
-  // only "any inversion at all?" matters: one plain store per warp that saw one (every writer stores the same value;
-  // an atomic per warp on this single address serialised 2.8M updates = 1.2 ms at 90M nested rows)
-  if (__ballot_sync(0xffffffffu, inv) && (threadIdx.x & 31) == 0) *inversions = 1ull;
+  // only "any inversion at all?" matters.  One update per BLOCK that saw one, and only while the flag still reads 0:
+  // an atomic per warp on this single address serialised 2.8M updates (1.2 ms at 90M nested rows)
+  const int any = __syncthreads_or((int)inv);
+  if (any && threadIdx.x == 0 && *(volatile unsigned long long *)inversions == 0ull) atomicMax(inversions, 1ull);
 }
 
 // nested case only: contig-tagged end keys for the running max and the (contig | end) keys of the second sort

@@ -104,8 +104,9 @@ static bool sync_by_memcpy() {
   static bool v = [] { const char *e = getenv("PBGPU_SYNC"); return e && !strcmp(e, "memcpy"); }();
   return v;
 }
-// copies n_words (<= 15) 64-bit words from device memory to `out`; returns after they have arrived
-int fetch_words(const void *d_src, int n_words, unsigned long long *out, cudaStream_t s) {
+struct MailboxSlot { unsigned long long *d; unsigned long long seq; };
+// next sequence number of the calling thread's mailbox; d == nullptr when there is none (allocation failed / disabled)
+MailboxSlot mailbox_open() {
   Mailbox &mb = g_mailbox;
   if (!mb.tried && !sync_by_memcpy()) {
     mb.tried = true;
@@ -120,14 +121,13 @@ int fetch_words(const void *d_src, int n_words, unsigned long long *out, cudaStr
       if (hp) cudaFreeHost(hp);
     }
   }
-  if (!mb.h || n_words > kMailboxWords - 1) {
-    PB_CUDA(cudaMemcpyAsync(out, d_src, sizeof(unsigned long long) * (size_t)n_words, cudaMemcpyDeviceToHost, s));
-    PB_CUDA(cudaStreamSynchronize(s));
-    return PBGPU_OK;
-  }
-  const unsigned long long seq = ++mb.seq;
-  PB_LAUNCH(mailbox_post_kernel, 1, 32, 0, s, (const unsigned long long *)d_src, n_words, mb.d, seq);
-  PB_CHECK_LAUNCH();
+  if (!mb.h) return MailboxSlot{nullptr, 0};
+  return MailboxSlot{mb.d, ++mb.seq};
+}
+// waits until the device has posted sequence number slot.seq (by a kernel enqueued on s), then copies n_words out
+int mailbox_wait(const MailboxSlot &slot, int n_words, unsigned long long *out, cudaStream_t s) {
+  Mailbox &mb = g_mailbox;
+  const unsigned long long seq = slot.seq;
   bool arrived = false;
   for (long spin = 0; spin < 20000000L; ++spin) {  // ~ tens of ms at most
     if (mb.h[kMailboxWords - 1] == seq) { arrived = true; break; }
@@ -142,6 +142,18 @@ int fetch_words(const void *d_src, int n_words, unsigned long long *out, cudaStr
   std::atomic_thread_fence(std::memory_order_acquire);
   for (int i = 0; i < n_words; ++i) out[i] = mb.h[i];
   return PBGPU_OK;
+}
+// copies n_words (<= 15) 64-bit words from device memory to `out`; returns after they have arrived
+int fetch_words(const void *d_src, int n_words, unsigned long long *out, cudaStream_t s) {
+  const MailboxSlot slot = n_words <= kMailboxWords - 1 ? mailbox_open() : MailboxSlot{nullptr, 0};
+  if (!slot.d) {
+    PB_CUDA(cudaMemcpyAsync(out, d_src, sizeof(unsigned long long) * (size_t)n_words, cudaMemcpyDeviceToHost, s));
+    PB_CUDA(cudaStreamSynchronize(s));
+    return PBGPU_OK;
+  }
+  PB_LAUNCH(mailbox_post_kernel, 1, 32, 0, s, (const unsigned long long *)d_src, n_words, slot.d, slot.seq);
+  PB_CHECK_LAUNCH();
+  return mailbox_wait(slot, n_words, out, s);
 }
 
 }  // namespace pbgpu
@@ -197,6 +209,28 @@ static bool jdir_by_search() {
   return v;
 }
 
+// PBGPU_TRACE_BUILD=1: host wall time of every build stage on stderr, with the stream drained at each lap (tuning aid;
+// changes the timing it reports on by serialising host and device)
+struct BuildTrace {
+  bool on;
+  cudaStream_t s;
+  double t0;
+  static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+  explicit BuildTrace(cudaStream_t st) : s(st) {
+    const char *e = getenv("PBGPU_TRACE_BUILD");
+    on = e && e[0] == '1';
+    t0 = now();
+  }
+  void lap(const char *what, bool drain = true) {
+    if (!on) return;
+    const double t1 = now();
+    double t2 = t1;
+    if (drain) { cudaStreamSynchronize(s); t2 = now(); }
+    fprintf(stderr, "[pbgpu build] %-34s host %8.3f ms  + drain %8.3f ms\n", what, t1 - t0, t2 - t1);
+    t0 = now();
+  }
+};
+
 static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *d_s, const int32_t *d_e, int64_t m_in,
                             int32_t n_contigs, cudaStream_t s) {
   ix->m_in = m_in;
@@ -205,6 +239,7 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
   g_ev.mark(EV_BUILD0, s);
   struct MarkEnd { cudaStream_t s; ~MarkEnd() { g_ev.mark(EV_BUILD1, s); } } mark_end{s};
   Scratch sc(s);
+  BuildTrace bt(s);
   // 1. ONE pass over the input: coordinate statistics (key width, fast-path eligibility), the sort keys
   //    contig << 32 | biased start  with values  end << 32 | row, and the digit totals of every radix pass.
   //    The key format does not depend on the statistics, so nothing waits for the host before it.
@@ -223,6 +258,7 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
     char *d_prep = nullptr;  // BuildStats | digit totals [kRsMaxPasses][256]
     const size_t stats_b = align_up(sizeof(BuildStats)), tot_b = sizeof(uint32_t) * kRsMaxPasses * kRsRadix;
     PB_TRY(sc.get(&d_prep, stats_b + tot_b));
+    bt.lap("scratch alloc (keys, vals x2)");
     BuildStats *d_stats = (BuildStats *)d_prep;
     d_totals = (uint32_t *)(d_prep + stats_b);
     PB_CUDA(cudaMemsetAsync(d_prep, 0, stats_b + tot_b, s));
@@ -233,6 +269,7 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
     PB_CHECK_LAUNCH();
     static_assert(sizeof(BuildStats) % 8 == 0 && sizeof(BuildStats) / 8 <= kMailboxWords - 1, "BuildStats must fit the mailbox");
     PB_TRY(fetch_words(d_stats, (int)(sizeof(BuildStats) / 8), reinterpret_cast<unsigned long long *>(&hs), s));
+    bt.lap("prep kernel + stats fetch");
   }
   const int64_t m = (int64_t)hs.valid;
   ix->m = m;
@@ -241,6 +278,7 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
   const size_t seg_b = align_up(sizeof(int32_t) * ((size_t)n_contigs + 2)), arr_b = align_up(sizeof(int32_t) * (size_t)(m ? m : 1));
   const size_t er_b = align_up(sizeof(uint2) * (size_t)(m ? m : 1));
   PB_TRY(dev_alloc(&ix->slab, seg_b + 3 * arr_b + er_b, s));
+  bt.lap("slab 1 alloc");
   ix->bytes = seg_b + 3 * arr_b + er_b;
   char *base = (char *)ix->slab;
   ix->seg = (int32_t *)base;
@@ -270,6 +308,7 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
   if (contig_passes) for (int q = 0; q < contig_digits; ++q) dpos[ndig++] = 4 + q;
   SortedPairs sorted;
   PB_TRY(radix_sort_digits(keys, vals, keys2, vals2, m_in, dpos, ndig, d_totals, s, &sorted));
+  bt.lap("start sort");
   uint64_t *keys_alt = sorted.keys == keys ? keys2 : keys, *vals_alt = sorted.vals == vals ? vals2 : vals;  // free for reuse
   keys = sorted.keys;
   vals = sorted.vals;
@@ -298,6 +337,7 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
   PB_CHECK_LAUNCH();
   unsigned long long h_meta[2] = {0, 0};
   PB_TRY(fetch_words(d_meta, 2, h_meta, s));
+  bt.lap("unpack + layout + meta fetch");
   const bool nested = h_meta[0] != 0;
   ix->nested = nested;
 
@@ -314,6 +354,7 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
     PB_TRY(sc.get(&ekeys, (size_t)m));
     PB_TRY(sc.get(&evals, (size_t)m));
     PB_TRY(sc.get(&evals2, (size_t)m));
+    bt.lap("nested: allocs");
     PB_LAUNCH(make_end_keys_kernel, (unsigned)cdiv(m, 256), 256, 0, s, keys, ix->en, m, pos_bits, bias, pm_keys, ekeys, evals);
     PB_CHECK_LAUNCH();
     PB_TRY((device_scan<MaxU64, true>((const unsigned long long *)pm_keys, (unsigned long long *)pm_keys, m, nullptr, s)));
@@ -327,6 +368,7 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
     ekeys = es.keys;
     PB_LAUNCH(unpack_ends_kernel, (unsigned)cdiv(m, 256), 256, 0, s, es.keys, es.vals, m, pos_bits, bias, ix->en_sorted, ix->en_pos);
     PB_CHECK_LAUNCH();
+    bt.lap("nested: pmax + end sort");
   }
 
   // 5. fast path: global axis + rank directories
@@ -340,6 +382,7 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
     const size_t cm_b = align_up(sizeof(ContigMap) * ((size_t)n_contigs + 1)), g_b = align_up(4 * (size_t)m);
     const size_t d_b = align_up(sizeof(JRec) * ((size_t)nb + 1));
     PB_TRY(dev_alloc(&ix->slab2, cm_b + 2 * g_b + d_b, s));
+    bt.lap("slab 2 alloc");
     ix->bytes += cm_b + 2 * g_b + d_b;
     char *b2 = (char *)ix->slab2;
     ix->cmap = (ContigMap *)b2;
@@ -365,6 +408,7 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
       PB_LAUNCH(jdir_pack_kernel, (unsigned)cdiv((int64_t)nb + 1, 256), 256, 0, s, ix->gs, ix->ge, m, shift, nb, rank_s, rank_e, ix->jdir);
     }
     PB_CHECK_LAUNCH();
+    bt.lap("directory");
     ix->fast = 1;
   }
   return PBGPU_OK;
@@ -499,6 +543,13 @@ static bool emit_flat_ok(const pbgpu_index *ix) {
   return !walk && ix->fast && !ix->nested && ix->m < (1ll << 27);
 }
 
+// PBGPU_P1SCAN=kernels: pass 1 leaves raw block totals and a separate device scan turns them into offsets (the first
+// implementation; kept for A/B runs) instead of the look-back inside pass 1
+static bool p1_scan_by_kernels() {
+  static bool v = [] { const char *e = getenv("PBGPU_P1SCAN"); return e && !strcmp(e, "kernels"); }();
+  return v;
+}
+
 struct pbgpu_overlap_plan {
   const pbgpu_index *ix;
   const int32_t *pc, *ps, *pe;
@@ -551,45 +602,66 @@ int pbgpu_overlap_count(const pbgpu_index *ix, const int32_t *d_contig, const in
   cudaGetDevice(&p->device);
   auto fail = [&](int rc) { pbgpu_overlap_plan_free(p); return rc; };
   if (n == 0) { *plan = p; return PBGPU_OK; }
+  const int items = sweep_items();
+  const unsigned grid = (unsigned)p->nblk, grid_fast = (unsigned)cdiv(n, (int64_t)kSweepThreads * items);
+  const bool lookback = ix->fast && !p1_scan_by_kernels();
+  unsigned long long *d_status = nullptr;
   {
     const size_t cb = align_up(sizeof(uint32_t) * (size_t)n), bb = align_up(sizeof(unsigned long long) * (size_t)(p->nblk + 1));
     const bool flat = emit_flat_ok(ix);
     const size_t wb = flat ? align_up(sizeof(unsigned long long) * (size_t)(p->nblk * (kSweepThreads / 32))) : 0;
-    int rc0 = dev_alloc(&p->slab, 2 * cb + bb + wb, s);
+    const size_t sb = lookback ? align_up(sizeof(unsigned long long) * ((size_t)grid_fast + 1)) : 0;  // status words + ticket
+    int rc0 = dev_alloc(&p->slab, 2 * cb + bb + wb + sb, s);
     if (rc0 != PBGPU_OK) return fail(rc0);
     p->counts = (uint32_t *)p->slab;
     p->his = (uint32_t *)((char *)p->slab + cb);
     p->block_base = (unsigned long long *)((char *)p->slab + 2 * cb);
     if (flat) p->warp_off = (unsigned long long *)((char *)p->slab + 2 * cb + bb);
+    if (lookback) {
+      d_status = (unsigned long long *)((char *)p->slab + 2 * cb + bb + wb);
+      if (cudaMemsetAsync(d_status, 0, sb, s) != cudaSuccess) return fail(set_error(PBGPU_ECUDA, "memset failed"));
+    }
   }
   g_ev.mark(EV_P1_0, s);
-  const unsigned grid = (unsigned)p->nblk;
+  unsigned long long *d_total = p->block_base + p->nblk;
+  unsigned long long h_total = 0;
+  int rc = PBGPU_OK;
   if (ix->fast) {
     const bool strict = filter_op == PBGPU_FILTER_STRICT;
-    const unsigned g2 = (unsigned)cdiv(n, kSweepThreads * 2), g4 = (unsigned)cdiv(n, kSweepThreads * 4);
-    if (sweep_items() == 4) {
-      if (strict) PB_LAUNCH((overlap_count_fast_kernel<true, 4>), g4, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->his, p->block_base, p->warp_off);
-      else PB_LAUNCH((overlap_count_fast_kernel<false, 4>), g4, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->his, p->block_base, p->warp_off);
-    } else if (sweep_items() == 2) {
-      if (strict) PB_LAUNCH((overlap_count_fast_kernel<true, 2>), g2, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->his, p->block_base, p->warp_off);
-      else PB_LAUNCH((overlap_count_fast_kernel<false, 2>), g2, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->his, p->block_base, p->warp_off);
-    } else {
-      if (strict) PB_LAUNCH((overlap_count_fast_kernel<true, 1>), grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->his, p->block_base, p->warp_off);
-      else PB_LAUNCH((overlap_count_fast_kernel<false, 1>), grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->his, p->block_base, p->warp_off);
+    const MailboxSlot slot = lookback ? mailbox_open() : MailboxSlot{nullptr, 0};
+    unsigned int *d_ticket = lookback ? (unsigned int *)(d_status + grid_fast) : nullptr;
+#define PB_P1(ST, IT, LB)                                                                                                   \
+  PB_LAUNCH((overlap_count_fast_kernel<ST, IT, LB>), grid_fast, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, \
+            p->counts, p->his, p->block_base, p->warp_off, d_status, d_ticket, slot.d, slot.seq)
+#define PB_P1_ITEMS(ST, LB) do { if (items == 4) PB_P1(ST, 4, LB); else if (items == 2) PB_P1(ST, 2, LB); else PB_P1(ST, 1, LB); } while (0)
+    if (lookback) { if (strict) PB_P1_ITEMS(true, true); else PB_P1_ITEMS(false, true); }
+    else { if (strict) PB_P1_ITEMS(true, false); else PB_P1_ITEMS(false, false); }
+#undef PB_P1_ITEMS
+#undef PB_P1
+    if (cudaGetLastError() != cudaSuccess) return fail(set_error(PBGPU_ECUDA, "overlap_count_fast_kernel launch failed"));
+    g_ev.mark(EV_P1_1, s);
+    if (lookback) {  // offsets and total came out of pass 1 itself; the total is already on its way to the mailbox
+      g_ev.mark(EV_SCAN1, s);
+      if (slot.d) rc = mailbox_wait(slot, 1, &h_total, s);
+      else if (cudaMemcpyAsync(&h_total, d_total, sizeof(h_total), cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess)
+        rc = set_error(PBGPU_ECUDA, "overlap pass 1 failed: %s", cudaGetErrorString(cudaGetLastError()));
+      if (rc != PBGPU_OK) return fail(rc);
     }
-  } else if (filter_op == PBGPU_FILTER_STRICT)
-    PB_LAUNCH(overlap_count_kernel<true>, grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->block_base);
-  else
-    PB_LAUNCH(overlap_count_kernel<false>, grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->block_base);
-  if (cudaGetLastError() != cudaSuccess) return fail(set_error(PBGPU_ECUDA, "overlap_count_kernel launch failed"));
-  g_ev.mark(EV_P1_1, s);
-  unsigned long long *d_total = p->block_base + p->nblk;
-  int rc = device_scan<SumU64, false>(p->block_base, p->block_base, p->nblk, d_total, s);
-  if (rc != PBGPU_OK) return fail(rc);
-  g_ev.mark(EV_SCAN1, s);
-  unsigned long long h_total = 0;
-  rc = fetch_words(d_total, 1, &h_total, s);
-  if (rc != PBGPU_OK) return fail(rc);
+  } else {
+    if (filter_op == PBGPU_FILTER_STRICT)
+      PB_LAUNCH(overlap_count_kernel<true>, grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->block_base);
+    else
+      PB_LAUNCH(overlap_count_kernel<false>, grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, p->counts, p->block_base);
+    if (cudaGetLastError() != cudaSuccess) return fail(set_error(PBGPU_ECUDA, "overlap_count_kernel launch failed"));
+    g_ev.mark(EV_P1_1, s);
+  }
+  if (!lookback) {
+    rc = device_scan<SumU64, false>(p->block_base, p->block_base, p->nblk, d_total, s);
+    if (rc != PBGPU_OK) return fail(rc);
+    g_ev.mark(EV_SCAN1, s);
+    rc = fetch_words(d_total, 1, &h_total, s);
+    if (rc != PBGPU_OK) return fail(rc);
+  }
   p->total = (int64_t)h_total;
   *total_pairs = p->total;
   *plan = p;

@@ -275,15 +275,47 @@ __global__ void __launch_bounds__(kSweepThreads) count_overlaps_fast_kernel(Inde
   }
 }
 
-template <bool STRICT, int ITEMS>
+// Exact 64-bit sum of one uint32 per lane with two REDUX instructions (16-bit halves cannot overflow in a warp):
+// ten SHFLs for a 64-bit butterfly would share the MIO/LSU path these L1TEX-bound kernels are limited by.
+__device__ __forceinline__ unsigned long long warp_sum_u32(uint32_t v) {
+  const uint32_t lo = __reduce_add_sync(0xffffffffu, v & 0xffffu), hi = __reduce_add_sync(0xffffffffu, v >> 16);
+  return (unsigned long long)lo + ((unsigned long long)hi << 16);
+}
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// Pass 1 on the fast path.  Besides the per-probe (count, start rank) it produces the pair offsets pass 2 needs, in
+// the same launch: the offset of every 32-probe group inside its 256-probe block (warp_off), and -- LOOKBACK -- the
+// exclusive pair offset of every 256-probe block plus the grand total by a decoupled look-back over the launch's
+// blocks (ticket order; status word = 2 flag bits | 62-bit pair count; warp 0 inspects 32 predecessors per step).
+// That replaces the three-kernel device scan + a host fetch: the block holding the last ticket posts the total
+// straight into the caller's host mailbox (pbgpu.cu) when one is given.  Without LOOKBACK the raw block totals are
+// left in block_base for a separate scan (A/B: PBGPU_P1SCAN=kernels).
+constexpr unsigned long long kP1Agg = 1ull << 62, kP1Pre = 2ull << 62, kP1Mask = (1ull << 62) - 1ull;
+template <bool STRICT, int ITEMS, bool LOOKBACK>
 __global__ void __launch_bounds__(kSweepThreads) overlap_count_fast_kernel(IndexView ix, const int32_t *__restrict__ pc,
                                                                            const int32_t *__restrict__ ps,
                                                                            const int32_t *__restrict__ pe, int64_t n,
                                                                            uint32_t *__restrict__ counts, uint32_t *__restrict__ his,
-                                                                           unsigned long long *__restrict__ block_totals /*[ITEMS per block]*/,
-                                                                           unsigned long long *__restrict__ warp_off /*[n/32] or NULL*/) {
+                                                                           unsigned long long *__restrict__ block_base /*[nblk+1]*/,
+                                                                           unsigned long long *__restrict__ warp_off /*[n/32] or NULL*/,
+                                                                           unsigned long long *status /*[grid], zeroed*/,
+                                                                           unsigned int *ticket /*zeroed*/,
+                                                                           volatile unsigned long long *mailbox, unsigned long long mailbox_seq) {
   __shared__ unsigned long long wt[ITEMS][kSweepThreads / 32];
-  const int64_t base = (int64_t)blockIdx.x * (kSweepThreads * ITEMS) + threadIdx.x;
+  __shared__ unsigned int tile_s;
+  unsigned int tile = blockIdx.x;
+  if (LOOKBACK) {
+    if (threadIdx.x == 0) tile_s = atomicAdd(ticket, 1u);
+    __syncthreads();
+    tile = tile_s;
+  }
+  const int64_t base = (int64_t)tile * (kSweepThreads * ITEMS) + threadIdx.x;
   int32_t c[ITEMS], s[ITEMS], e[ITEMS];
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
@@ -298,30 +330,69 @@ __global__ void __launch_bounds__(kSweepThreads) overlap_count_fast_kernel(Index
   for (int j = 0; j < ITEMS; ++j) {
     const int64_t i = base + (int64_t)j * kSweepThreads;
     if (i < n) { counts[i] = cnt[j]; his[i] = hi[j]; }
-    unsigned long long v = i < n ? cnt[j] : 0;
-#pragma unroll
-    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    const unsigned long long v = warp_sum_u32(i < n ? cnt[j] : 0u);
     if ((threadIdx.x & 31) == 0) wt[j][threadIdx.x >> 5] = v;
   }
   __syncthreads();
-  // pass 2 works on 256-probe blocks: one total per 256 consecutive probes
-  if (threadIdx.x < ITEMS) {
-    unsigned long long t = 0;
-#pragma unroll
-    for (int w = 0; w < kSweepThreads / 32; ++w) t += wt[threadIdx.x][w];
-    const int64_t blk = (int64_t)blockIdx.x * ITEMS + threadIdx.x;
-    if (blk * kSweepThreads < n) block_totals[blk] = t;
-  }
   // offset of every 32-probe group inside its 256-probe block: lets pass 2 run warp by warp with no block-wide barrier
-  if (warp_off && threadIdx.x < ITEMS * (kSweepThreads / 32)) {
-    const int j = threadIdx.x / (kSweepThreads / 32), w = threadIdx.x % (kSweepThreads / 32);
+  if (warp_off && threadIdx.x >= 32 && threadIdx.x < 32 + ITEMS * (kSweepThreads / 32)) {
+    const int q = threadIdx.x - 32;
+    const int j = q / (kSweepThreads / 32), w = q % (kSweepThreads / 32);
     unsigned long long t = 0;
     for (int k = 0; k < w; ++k) t += wt[j][k];
-    const int64_t g = ((int64_t)blockIdx.x * ITEMS + j) * (kSweepThreads / 32) + w;
+    const int64_t g = ((int64_t)tile * ITEMS + j) * (kSweepThreads / 32) + w;
     if (g * 32 < n) warp_off[g] = t;
   }
+  if (threadIdx.x >= 32) return;
+  // warp 0: one total per 256 consecutive probes (lane j < ITEMS holds the total of sub-block j)
+  const int lane = threadIdx.x;
+  unsigned long long t = 0;
+  if (lane < ITEMS) {
+#pragma unroll
+    for (int w = 0; w < kSweepThreads / 32; ++w) t += wt[lane][w];
+  }
+  const int64_t blk = (int64_t)tile * ITEMS + lane;
+  if (!LOOKBACK) {
+    if (lane < ITEMS && blk * kSweepThreads < n) block_base[blk] = t;
+    return;
+  }
+  unsigned long long total = 0, before = 0;  // pairs of the whole tile; pairs of the sub-blocks ahead of this lane's
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const unsigned long long tj = __shfl_sync(0xffffffffu, t, j);
+    total += tj;
+    if (j < lane) before += tj;
+  }
+  unsigned long long excl = 0;
+  if (tile == 0) {
+    if (lane == 0) st_volatile_u64(status, total | kP1Pre);
+  } else {
+    if (lane == 0) st_volatile_u64(status + tile, total | kP1Agg);
+    for (long long top = (long long)tile - 1;; top -= 32) {
+      const long long idx = top - lane;
+      unsigned long long w = kP1Pre;  // below tile 0: an empty prefix ends the walk
+      if (idx >= 0) { do { w = ld_volatile_u64(status + idx); } while ((w >> 62) == 0ull); }
+      const unsigned pre = __ballot_sync(0xffffffffu, (w >> 62) == 2ull);
+      const int first = pre ? __ffs(pre) - 1 : 31;
+      unsigned long long v = lane <= first ? (w & kP1Mask) : 0ull;
+#pragma unroll
+      for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+      excl += v;
+      if (pre) break;
+    }
+    if (lane == 0) st_volatile_u64(status + tile, (excl + total) | kP1Pre);
+  }
+  if (lane < ITEMS && blk * kSweepThreads < n) block_base[blk] = excl + before;
+  if (tile == gridDim.x - 1 && lane == 0) {
+    const int64_t nblk = (n + kSweepThreads - 1) / kSweepThreads;
+    block_base[nblk] = excl + total;
+    if (mailbox) {
+      mailbox[0] = excl + total;
+      __threadfence_system();
+      mailbox[15] = mailbox_seq;
+    }
+  }
 }
-
 // pass 2 on the fast path: the hits of a probe are the `cnt` entries below its start-rank `hi` whose end
 // reaches past the probe start, so walk down from hi-1 until cnt of them are found (exactly cnt steps when
 // the indexed intervals do not nest) and write them back to front: output stays ordered by (start,row).
