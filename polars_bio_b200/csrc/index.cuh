@@ -102,6 +102,7 @@ struct BuildStats {  // device-side reduction target
   int min_start, max_start, min_end, max_end;
   unsigned long long inverted, valid;
   unsigned long long max_len;  // longest (end - start) over the non-inverted rows
+  unsigned long long blocks_done;  // prep_kernel: blocks that have added their share (the last one posts to the host)
 };
 
 // ---- prep: the one pass over the raw input ----------------------------------------------------------------------
@@ -113,7 +114,8 @@ constexpr int kPrepThreads = 512;
 __global__ void __launch_bounds__(kPrepThreads) prep_kernel(const int32_t *__restrict__ c, const int32_t *__restrict__ s,
                                                             const int32_t *__restrict__ e, int64_t n, int32_t n_contigs, int n_digits,
                                                             BuildStats *st, uint64_t *__restrict__ keys, uint64_t *__restrict__ vals,
-                                                            uint32_t *__restrict__ digit_totals /*[kRsMaxPasses][256], zeroed*/) {
+                                                            uint32_t *__restrict__ digit_totals /*[kRsMaxPasses][256], zeroed*/,
+                                                            volatile unsigned long long *mailbox, unsigned long long mailbox_seq) {
   __shared__ uint32_t h[kRsMaxPasses][kRsRadix];
   __shared__ int sm[4][kPrepThreads / 32];
   __shared__ unsigned su[3][kPrepThreads / 32];
@@ -173,6 +175,16 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(const int32_t *__res
       if (su[0][0]) atomicAdd(&st->inverted, (unsigned long long)su[0][0]);
       atomicAdd(&st->valid, (unsigned long long)su[1][0]);
       atomicMax(&st->max_len, (unsigned long long)su[2][0]);
+    }
+    if (mailbox) {  // the block that finishes last posts the five statistics words to the host mailbox (pbgpu.cu)
+      __threadfence();
+      if (atomicAdd(&st->blocks_done, 1ull) == (unsigned long long)gridDim.x - 1ull) {
+        __threadfence();
+        const volatile unsigned long long *w = reinterpret_cast<const volatile unsigned long long *>(st);
+        for (int k = 0; k < 5; ++k) mailbox[k] = w[k];
+        __threadfence_system();
+        mailbox[15] = mailbox_seq;
+      }
     }
   }
   for (int i = threadIdx.x; i < n_digits * kRsRadix; i += kPrepThreads) {
@@ -266,7 +278,8 @@ __global__ void __launch_bounds__(128) contig_span_kernel(const int32_t *__restr
 // ContigMap in ONE single-block launch (instead of span kernel + scan + copy + offset kernel)
 __global__ void __launch_bounds__(1024) contig_layout_kernel(const int32_t *__restrict__ seg, const int32_t *__restrict__ st,
                                                              long long max_len, int32_t n_contigs,
-                                                             ContigMap *__restrict__ cmap, unsigned long long *__restrict__ total_span) {
+                                                             ContigMap *__restrict__ cmap, unsigned long long *meta /*[0] nested flag (in), [1] total span (out)*/,
+                                                             volatile unsigned long long *mailbox, unsigned long long mailbox_seq) {
   __shared__ unsigned long long wt[1024 / 32 + 1];
   const int c = threadIdx.x;
   ContigMap m;
@@ -283,7 +296,16 @@ __global__ void __launch_bounds__(1024) contig_layout_kernel(const int32_t *__re
   }
   const unsigned long long off = block_exclusive<SumU64, 1024>(span, wt);
   if (c < n_contigs) { m.off = (uint32_t)off; cmap[c] = m; }  // off is only used when the total fits 32 bits
-  if (threadIdx.x == 0) *total_span = wt[1024 / 32];
+  if (threadIdx.x == 0) {
+    const unsigned long long total = wt[1024 / 32];
+    meta[1] = total;
+    if (mailbox) {  // both meta words straight to the host mailbox (pbgpu.cu)
+      mailbox[0] = meta[0];
+      mailbox[1] = total;
+      __threadfence_system();
+      mailbox[15] = mailbox_seq;
+    }
+  }
 }
 __global__ void __launch_bounds__(128) contig_off_kernel(const unsigned long long *__restrict__ off, int32_t n_contigs,
                                                          ContigMap *__restrict__ cmap) {

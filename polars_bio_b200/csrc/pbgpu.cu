@@ -247,7 +247,7 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
   const int contig_digits = (contig_bits + 7) / 8;
   constexpr int pos_bits = 32;
   constexpr uint32_t bias = 0x80000000u;
-  BuildStats hs = {INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN, 0ull, 0ull, 0ull};
+  BuildStats hs = {INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN, 0ull, 0ull, 0ull, 0ull};
   uint64_t *keys = nullptr, *vals = nullptr, *keys2 = nullptr, *vals2 = nullptr;
   uint32_t *d_totals = nullptr;
   if (m_in > 0) {
@@ -265,10 +265,13 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
     PB_CUDA(cudaMemcpyAsync(d_stats, &hs, sizeof(hs), cudaMemcpyHostToDevice, s));
     int64_t grid = cdiv(m_in, kPrepThreads * 2);
     if (grid > kSMs * 2) grid = kSMs * 2;
-    PB_LAUNCH(prep_kernel, (unsigned)grid, kPrepThreads, 0, s, d_c, d_s, d_e, m_in, n_contigs, 4 + contig_digits, d_stats, keys, vals, d_totals);
+    static_assert(sizeof(BuildStats) == 48, "BuildStats: 5 payload words + the block counter word, posted by prep_kernel");
+    const MailboxSlot slot = mailbox_open();
+    PB_LAUNCH(prep_kernel, (unsigned)grid, kPrepThreads, 0, s, d_c, d_s, d_e, m_in, n_contigs, 4 + contig_digits, d_stats, keys, vals, d_totals,
+              slot.d, slot.seq);
     PB_CHECK_LAUNCH();
-    static_assert(sizeof(BuildStats) % 8 == 0 && sizeof(BuildStats) / 8 <= kMailboxWords - 1, "BuildStats must fit the mailbox");
-    PB_TRY(fetch_words(d_stats, (int)(sizeof(BuildStats) / 8), reinterpret_cast<unsigned long long *>(&hs), s));
+    if (slot.d) PB_TRY(mailbox_wait(slot, 5, reinterpret_cast<unsigned long long *>(&hs), s));
+    else PB_TRY(fetch_words(d_stats, 5, reinterpret_cast<unsigned long long *>(&hs), s));
     bt.lap("prep kernel + stats fetch");
   }
   const int64_t m = (int64_t)hs.valid;
@@ -326,9 +329,12 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
   PB_LAUNCH(unpack_sorted_kernel, (unsigned)cdiv(m, 256), 256, 0, s, keys, vals, m, pos_bits, bias, n_contigs, ix->st, ix->en, ix->row,
             ix->er, ix->seg, d_meta);
   const bool small_table = n_contigs <= 1024;
+  MailboxSlot meta_slot{nullptr, 0};  // set when the layout kernel posts d_meta to the host itself
   if (try_fast) {
-    if (small_table)
-      PB_LAUNCH(contig_layout_kernel, 1, 1024, 0, s, ix->seg, ix->st, (long long)hs.max_len, n_contigs, d_cmap_tmp, d_meta + 1);
+    if (small_table) {
+      meta_slot = mailbox_open();
+      PB_LAUNCH(contig_layout_kernel, 1, 1024, 0, s, ix->seg, ix->st, (long long)hs.max_len, n_contigs, d_cmap_tmp, d_meta, meta_slot.d, meta_slot.seq);
+    }
     else {
       PB_LAUNCH(contig_span_kernel, (unsigned)cdiv(n_contigs, 128), 128, 0, s, ix->seg, ix->st, (long long)hs.max_len, n_contigs, d_cmap_tmp, d_span);
       PB_TRY((device_scan<SumU64, false>(d_span, d_span, n_contigs, d_meta + 1, s)));
@@ -336,7 +342,8 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
   }
   PB_CHECK_LAUNCH();
   unsigned long long h_meta[2] = {0, 0};
-  PB_TRY(fetch_words(d_meta, 2, h_meta, s));
+  if (meta_slot.d) PB_TRY(mailbox_wait(meta_slot, 2, h_meta, s));
+  else PB_TRY(fetch_words(d_meta, 2, h_meta, s));
   bt.lap("unpack + layout + meta fetch");
   const bool nested = h_meta[0] != 0;
   ix->nested = nested;
@@ -543,10 +550,11 @@ static bool emit_flat_ok(const pbgpu_index *ix) {
   return !walk && ix->fast && !ix->nested && ix->m < (1ll << 27);
 }
 
-// PBGPU_P1SCAN=kernels: pass 1 leaves raw block totals and a separate device scan turns them into offsets (the first
-// implementation; kept for A/B runs) instead of the look-back inside pass 1
+// Pass 1 leaves raw block totals and a device scan turns them into offsets.  PBGPU_P1SCAN=lookback does the scan
+// inside pass 1 instead (decoupled look-back over its blocks): measured 2.5x SLOWER (r01s: 181 vs 72 us at 10M
+// probes -- a 512-probe tile lives ~5 us, the ticket + status round trips add ~3 us to every one), kept for A/B runs.
 static bool p1_scan_by_kernels() {
-  static bool v = [] { const char *e = getenv("PBGPU_P1SCAN"); return e && !strcmp(e, "kernels"); }();
+  static bool v = [] { const char *e = getenv("PBGPU_P1SCAN"); return !(e && !strcmp(e, "lookback")); }();
   return v;
 }
 
@@ -656,10 +664,12 @@ int pbgpu_overlap_count(const pbgpu_index *ix, const int32_t *d_contig, const in
     g_ev.mark(EV_P1_1, s);
   }
   if (!lookback) {
-    rc = device_scan<SumU64, false>(p->block_base, p->block_base, p->nblk, d_total, s);
+    const MailboxSlot slot = mailbox_open();
+    bool posted = false;
+    rc = device_scan<SumU64, false>(p->block_base, p->block_base, p->nblk, d_total, s, slot.d, slot.seq, &posted);
     if (rc != PBGPU_OK) return fail(rc);
     g_ev.mark(EV_SCAN1, s);
-    rc = fetch_words(d_total, 1, &h_total, s);
+    rc = posted ? mailbox_wait(slot, 1, &h_total, s) : fetch_words(d_total, 1, &h_total, s);
     if (rc != PBGPU_OK) return fail(rc);
   }
   p->total = (int64_t)h_total;

@@ -126,11 +126,14 @@ __global__ void __launch_bounds__(kScanThreads) scan_final_kernel(const typename
 
 // whole scan in one block (one launch instead of three) for small arrays (contig tables, a few thousand
 // block totals); its serial loop costs ~2 us per 4096 entries, so larger inputs take the three-kernel path
-template <typename Op, bool INCLUSIVE>
+// mailbox (optional; uint64 totals only): host-mapped words, see pbgpu.cu -- the total goes to word 0, then the
+// sequence number to word 15, so the host has it without a further launch or copy.
+template <typename Op, bool INCLUSIVE, int ITEMS = 4>
 __global__ void __launch_bounds__(1024) scan_single_block_kernel(const typename Op::T *__restrict__ in, typename Op::T *__restrict__ out,
-                                                                 int64_t n, typename Op::T *__restrict__ total_out) {
+                                                                 int64_t n, typename Op::T *__restrict__ total_out,
+                                                                 volatile unsigned long long *mailbox = nullptr,
+                                                                 unsigned long long mailbox_seq = 0) {
   using T = typename Op::T;
-  constexpr int ITEMS = 4;
   __shared__ T wt[1024 / 32 + 1];
   __shared__ T carry_s;
   if (threadIdx.x == 0) carry_s = Op::id();
@@ -156,20 +159,38 @@ __global__ void __launch_bounds__(1024) scan_single_block_kernel(const typename 
     if (threadIdx.x == 0) carry_s = Op::op(carry_s, wt[1024 / 32]);
     __syncthreads();
   }
-  if (total_out && threadIdx.x == 0) *total_out = carry_s;
+  if (threadIdx.x == 0) {
+    if (total_out) *total_out = carry_s;
+    if (mailbox) {
+      mailbox[0] = (unsigned long long)carry_s;
+      __threadfence_system();
+      mailbox[15] = mailbox_seq;
+    }
+  }
 }
 
 // out may alias in.  d_total (optional, device) receives the grand total.
+// mailbox/mailbox_seq: when given and the single-block path is taken, the total is also posted to the host mailbox and
+// *posted is set; otherwise the caller fetches d_total itself.
 template <typename Op, bool INCLUSIVE>
-int device_scan(const typename Op::T *in, typename Op::T *out, int64_t n, typename Op::T *d_total, cudaStream_t s) {
+int device_scan(const typename Op::T *in, typename Op::T *out, int64_t n, typename Op::T *d_total, cudaStream_t s,
+                unsigned long long *mailbox = nullptr, unsigned long long mailbox_seq = 0, bool *posted = nullptr) {
   using T = typename Op::T;
+  if (posted) *posted = false;
   if (n <= 0) {
     if (d_total) PB_CUDA(cudaMemsetAsync(d_total, 0, sizeof(T), s));
     return PBGPU_OK;
   }
   if (n <= 8192) {
-    PB_LAUNCH((scan_single_block_kernel<Op, INCLUSIVE>), 1, 1024, 0, s, in, out, n, d_total);
+    PB_LAUNCH((scan_single_block_kernel<Op, INCLUSIVE, 4>), 1, 1024, 0, s, in, out, n, d_total, mailbox, mailbox_seq);
     PB_CHECK_LAUNCH();
+    if (posted) *posted = mailbox != nullptr;
+    return PBGPU_OK;
+  }
+  if (n <= 65536) {  // one launch, 16K entries per round: cheaper than three dependent launches at this size
+    PB_LAUNCH((scan_single_block_kernel<Op, INCLUSIVE, 16>), 1, 1024, 0, s, in, out, n, d_total, mailbox, mailbox_seq);
+    PB_CHECK_LAUNCH();
+    if (posted) *posted = mailbox != nullptr;
     return PBGPU_OK;
   }
   const int64_t nblk = cdiv(n, kScanTile);
