@@ -67,7 +67,9 @@ __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const typenam
 // single block: exclusive scan of the partials in place (looping over chunks)
 template <typename Op>
 __global__ void __launch_bounds__(1024) scan_partials_kernel(typename Op::T *__restrict__ partial, int64_t nparts,
-                                                             typename Op::T *__restrict__ total_out) {
+                                                             typename Op::T *__restrict__ total_out,
+                                                             volatile unsigned long long *mailbox = nullptr,
+                                                             unsigned long long mailbox_seq = 0) {
   using T = typename Op::T;
   __shared__ T wt[1024 / 32 + 1];
   __shared__ T carry_s;
@@ -83,7 +85,14 @@ __global__ void __launch_bounds__(1024) scan_partials_kernel(typename Op::T *__r
     if (threadIdx.x == 0) carry_s = Op::op(carry, wt[1024 / 32]);
     __syncthreads();
   }
-  if (total_out && threadIdx.x == 0) *total_out = carry_s;
+  if (threadIdx.x == 0) {
+    if (total_out) *total_out = carry_s;
+    if (mailbox) {  // host-mapped words (pbgpu.cu): total, then the sequence number
+      mailbox[0] = (unsigned long long)carry_s;
+      __threadfence_system();
+      mailbox[15] = mailbox_seq;
+    }
+  }
 }
 
 template <typename Op, bool INCLUSIVE>
@@ -170,7 +179,7 @@ __global__ void __launch_bounds__(1024) scan_single_block_kernel(const typename 
 }
 
 // out may alias in.  d_total (optional, device) receives the grand total.
-// mailbox/mailbox_seq: when given and the single-block path is taken, the total is also posted to the host mailbox and
+// mailbox/mailbox_seq: when given, the kernel that computes the total also posts it to the host mailbox and
 // *posted is set; otherwise the caller fetches d_total itself.
 template <typename Op, bool INCLUSIVE>
 int device_scan(const typename Op::T *in, typename Op::T *out, int64_t n, typename Op::T *d_total, cudaStream_t s,
@@ -187,18 +196,16 @@ int device_scan(const typename Op::T *in, typename Op::T *out, int64_t n, typena
     if (posted) *posted = mailbox != nullptr;
     return PBGPU_OK;
   }
-  if (n <= 65536) {  // one launch, 16K entries per round: cheaper than three dependent launches at this size
-    PB_LAUNCH((scan_single_block_kernel<Op, INCLUSIVE, 16>), 1, 1024, 0, s, in, out, n, d_total, mailbox, mailbox_seq);
-    PB_CHECK_LAUNCH();
-    if (posted) *posted = mailbox != nullptr;
-    return PBGPU_OK;
-  }
+
   const int64_t nblk = cdiv(n, kScanTile);
   Scratch sc(s);
   T *partial = nullptr;
   PB_TRY(sc.get(&partial, (size_t)nblk));
   PB_LAUNCH(scan_reduce_kernel<Op>, (unsigned)nblk, kScanThreads, 0, s, in, n, partial);
-  PB_LAUNCH(scan_partials_kernel<Op>, 1, 1024, 0, s, partial, nblk, d_total);
+  // the total is known after the second launch: posted from there, the host has it while the third still runs
+  // (a single block over all n entries was tried for n <= 64K: 48 us at 39K entries against 13 us for these three)
+  PB_LAUNCH(scan_partials_kernel<Op>, 1, 1024, 0, s, partial, nblk, d_total, mailbox, mailbox_seq);
+  if (posted) *posted = mailbox != nullptr;
   PB_LAUNCH((scan_final_kernel<Op, INCLUSIVE>), (unsigned)nblk, kScanThreads, 0, s, in, out, n, partial);
   PB_CHECK_LAUNCH();
   return PBGPU_OK;
