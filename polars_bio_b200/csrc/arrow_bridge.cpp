@@ -53,8 +53,16 @@ struct Trace {
   std::chrono::steady_clock::time_point t0;
   Trace() {
     const char *e = getenv("PBGPU_TRACE");
-    on = e && e[0] == '1';
+    on = e && (e[0] == '1' || e[0] == '2');
     t0 = std::chrono::steady_clock::now();
+  }
+  // PBGPU_TRACE=2: additionally drain `s` first, so the lap holds the device work queued so far (serialises the pipeline)
+  void lap_drained(const char *what, cudaStream_t s) {
+    const char *e = getenv("PBGPU_TRACE");
+    if (!(e && e[0] == '2')) return;
+    on = true;
+    cudaStreamSynchronize(s);
+    lap(what);
   }
   void lap(const char *what) {
     if (!on) return;
@@ -464,6 +472,52 @@ inline bool is_int_format(const char *f) { return f && f[0] && !f[1] && strchr("
 // Encode the three key columns of a table into int32 staging (code = -1 for null keys).
 // code8 != NULL: contig codes are written as one byte each instead (255 = null key or code >= 255): a quarter of the
 // H2D bytes of that column when the index holds at most 255 contigs (codes it does not know cannot match anyway).
+// ---- streaming stores into the H2D staging buffers -------------------------------------------------------------
+// The staging buffers are written by pool threads and then read once by the copy engine.  Measured on the B200 boxes
+// (scripts/h2d_probe.cu): a 12 MB pinned buffer just written with ordinary stores by other threads is DMA-read at
+// 5 GB/s (the lines sit dirty in those cores' caches), the same buffer written with non-temporal stores at 51 GB/s --
+// 1.4 ms per call for the indexed side alone; 96 MB: 26 vs 50 GB/s.  (cudaHostAllocWriteCombined made no difference
+// there.)  So everything that lands in staging goes through these, and every task ends with an sfence.
+#if defined(__SSE2__)
+#include <emmintrin.h>
+inline void nt_copy(void *dst, const void *src, size_t bytes) {
+  char *d = (char *)dst;
+  const char *s = (const char *)src;
+  size_t head = (16 - ((uintptr_t)d & 15)) & 15;
+  if (head > bytes) head = bytes;
+  memcpy(d, s, head);
+  d += head; s += head; bytes -= head;
+  const size_t blocks = bytes / 16;
+  for (size_t i = 0; i < blocks; ++i) _mm_stream_si128((__m128i *)d + i, _mm_loadu_si128((const __m128i *)s + i));
+  memcpy(d + blocks * 16, s + blocks * 16, bytes - blocks * 16);
+}
+inline void nt_fill(void *dst, size_t bytes, __m128i pattern /*period divides 16; dst aligned to the period*/, const void *pat_bytes) {
+  char *d = (char *)dst;
+  size_t head = (16 - ((uintptr_t)d & 15)) & 15;
+  if (head > bytes) head = bytes;
+  memcpy(d, (const char *)pat_bytes + (16 - head) % 16, head);  // pattern is periodic with a divisor of 16: any 16-aligned phase
+  d += head; bytes -= head;
+  const size_t blocks = bytes / 16;
+  for (size_t i = 0; i < blocks; ++i) _mm_stream_si128((__m128i *)d + i, pattern);
+  memcpy(d + blocks * 16, pat_bytes, bytes - blocks * 16);
+}
+inline void nt_fill8(uint8_t *dst, uint8_t v, size_t n) {
+  alignas(16) uint8_t pat[16];
+  memset(pat, v, 16);
+  nt_fill(dst, n, _mm_set1_epi8((char)v), pat);
+}
+inline void nt_fill32(int32_t *dst, int32_t v, size_t n) {  // dst is 4-byte aligned: head/tail are whole elements
+  alignas(16) int32_t pat[4] = {v, v, v, v};
+  nt_fill(dst, 4 * n, _mm_set1_epi32(v), pat);
+}
+inline void nt_fence() { _mm_sfence(); }
+#else
+inline void nt_copy(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); }
+inline void nt_fill8(uint8_t *dst, uint8_t v, size_t n) { memset(dst, v, n); }
+inline void nt_fill32(int32_t *dst, int32_t v, size_t n) { for (size_t i = 0; i < n; ++i) dst[i] = v; }
+inline void nt_fence() {}
+#endif
+
 int encode_keys(const Table &t, const char *side, ContigDict &dict, int32_t *code, int32_t *st, int32_t *en,
                 int64_t row_lo = 0, int64_t row_hi = INT64_MAX, uint8_t *code8 = nullptr) {
   const ArrowSchema *fc = t.schema.children[t.key[0]];
@@ -509,8 +563,8 @@ int encode_keys(const Table &t, const char *side, ContigDict &dict, int32_t *cod
     // ---- fast paths (the common shape: int32 positions and string contigs in long runs, no nulls) ----
     // positions: a straight copy into the staging buffer
     const bool fast_s = !vs && sf == 'i', fast_e = !ve && ef == 'i';
-    if (fast_s) memcpy(st + g0 + tk.lo, (const int32_t *)as->buffers[1] + os + tk.lo, 4 * (size_t)(tk.hi - tk.lo));
-    if (fast_e) memcpy(en + g0 + tk.lo, (const int32_t *)ae->buffers[1] + oe + tk.lo, 4 * (size_t)(tk.hi - tk.lo));
+    if (fast_s) nt_copy(st + g0 + tk.lo, (const int32_t *)as->buffers[1] + os + tk.lo, 4 * (size_t)(tk.hi - tk.lo));
+    if (fast_e) nt_copy(en + g0 + tk.lo, (const int32_t *)ae->buffers[1] + oe + tk.lo, 4 * (size_t)(tk.hi - tk.lo));
     // contigs: genomic tables are (mostly) sorted by contig, so a block of rows usually repeats one string.  For
     // utf8 / large_utf8 that is: equal lengths and a data region that is periodic with that length -- two
     // vectorisable sweeps instead of a hash lookup or memcmp per row.
@@ -550,11 +604,15 @@ int encode_keys(const Table &t, const char *side, ContigDict &dict, int32_t *cod
       const int64_t bhi = std::min(tk.hi, blk + kRun);
       if (run_ok && bhi - blk >= 2 && block_is_run(blk, bhi)) {
         const int32_t c = lookup(str_at(ac, sk, blk + oc));
-        if (code8) memset(code8 + g0 + blk, (c < 0 || c >= 255) ? 255 : c, (size_t)(bhi - blk));
-        else for (int64_t i = blk; i < bhi; ++i) code[g0 + i] = c;
+        if (code8) nt_fill8(code8 + g0 + blk, (uint8_t)((c < 0 || c >= 255) ? 255 : c), (size_t)(bhi - blk));
+        else nt_fill32(code + g0 + blk, c, (size_t)(bhi - blk));
         continue;
       }
+      // row by row into block-local arrays (they stay in this core's cache), streamed out to staging afterwards
+      int32_t tc[kRun], ts[kRun], te[kRun];
+      uint8_t tc8[kRun];
       for (int64_t i = blk; i < bhi; ++i) {
+        const int64_t li = i - blk;
         int32_t c;
         if (vc && !bit_get(vc, i + oc)) c = -1;
         else if (is_dict) {
@@ -565,14 +623,20 @@ int encode_keys(const Table &t, const char *side, ContigDict &dict, int32_t *cod
           int64_t s = fast_s ? 0 : int_at(as->buffers[1], sf, i + os), e = fast_e ? 0 : int_at(ae->buffers[1], ef, i + oe);
           bool null_pos = (vs && !bit_get(vs, i + os)) || (ve && !bit_get(ve, i + oe));
           if (s < INT32_MIN || s > INT32_MAX || e < INT32_MIN || e > INT32_MAX) { range_err.store(1); null_pos = true; }
-          if (null_pos) { c = -1; s = 0; e = 0; if (fast_s) st[g0 + i] = 0; if (fast_e) en[g0 + i] = 0; }
-          if (!fast_s) st[g0 + i] = (int32_t)s;
-          if (!fast_e) en[g0 + i] = (int32_t)e;
+          if (null_pos) { c = -1; s = 0; e = 0; }  // null-keyed row: never matches; a fast-copied position may stay as it is
+          ts[li] = (int32_t)s;
+          te[li] = (int32_t)e;
         }
-        if (code8) code8[g0 + i] = (uint8_t)((c < 0 || c >= 255) ? 255 : c);
-        else code[g0 + i] = c;
+        if (code8) tc8[li] = (uint8_t)((c < 0 || c >= 255) ? 255 : c);
+        else tc[li] = c;
       }
+      const size_t nb = (size_t)(bhi - blk);
+      if (!fast_s) nt_copy(st + g0 + blk, ts, 4 * nb);
+      if (!fast_e) nt_copy(en + g0 + blk, te, 4 * nb);
+      if (code8) nt_copy(code8 + g0 + blk, tc8, nb);
+      else nt_copy(code + g0 + blk, tc, 4 * nb);
     }
+    nt_fence();
   });
   if (!pool_ok) return set_error(PBGPU_ENOMEM, "host allocation failed while encoding the %s table", side);
   if (range_err.load())
@@ -1419,14 +1483,17 @@ int run(Table *L, Table *R, OutStream *os) {
   int32_t *dc_x = dev.get<int32_t>(m), *ds_x = dev.get<int32_t>(m), *de_x = dev.get<int32_t>(m);
   int32_t *dc_i = dev.get<int32_t>(n), *ds_i = dev.get<int32_t>(n), *de_i = dev.get<int32_t>(n);
   if (!dc_x || !ds_x || !de_x || !dc_i || !ds_i || !de_i) return set_error(PBGPU_ENOMEM, "device allocation failed");
+  tr.lap_drained("  stream + device allocations", s);
 
   // indexed side first: encode -> H2D -> index build.  Contigs that only occur on the iterated side get codes
   // >= n_contigs of the index and are treated as null keys by the kernels (they cannot match anything anyway).
   BR_TRY(encode_keys(*IX, iter_is_left ? "right" : "left", dict, hc_x, hs_x, he_x));
   const int32_t n_contigs = (int32_t)dict.map.size();
+  tr.lap_drained("  encode indexed side", s);
   BR_CUDA(cudaMemcpyAsync(dc_x, hc_x, 4 * (size_t)m, cudaMemcpyHostToDevice, s));
   BR_CUDA(cudaMemcpyAsync(ds_x, hs_x, 4 * (size_t)m, cudaMemcpyHostToDevice, s));
   BR_CUDA(cudaMemcpyAsync(de_x, he_x, 4 * (size_t)m, cudaMemcpyHostToDevice, s));
+  tr.lap_drained("  H2D indexed side", s);
   tr.lap("encode + H2D indexed side");
   pbgpu_index *ix = nullptr;
   BR_TRY(pbgpu_index_build(dc_x, ds_x, de_x, m, n_contigs, s, &ix));

@@ -135,3 +135,26 @@ def test_int32_domain_check(lib):
     rows = np.zeros(1, np.uint32)
     rc = lib.dbg_roundtrip(ctypes.addressof(s_in), b"chrom", b"start", b"end", rows.ctypes.data, 1, None, ctypes.addressof(s_out))
     assert rc == 4  # PBGPU_ERANGE
+
+
+def test_key_encoding_streaming_stores_all_alignments(lib):
+    """encode_keys writes the staging buffers with non-temporal stores (aligned 16-byte body + plain head / tail):
+    long contig runs (fill path), ragged contigs (row-by-row blocks), int32 fast copies and narrowed int64 positions,
+    over batches cut at odd offsets so heads and tails of every length occur."""
+    rng = np.random.default_rng(7)
+    n = 20_011
+    contig = np.where(np.arange(n) < 9_000, "chr1", np.where(np.arange(n) < 15_000, "chrX", "chr7"))
+    ragged = rng.integers(0, 3, n)
+    contig = np.where((np.arange(n) > 12_000) & (np.arange(n) < 13_500), np.array(["chr1", "chrX", "chrUn_x"])[ragged], contig)
+    start = rng.integers(0, 2**31 - 1000, n).astype(np.int32)
+    end64 = (start.astype(np.int64) + rng.integers(0, 900, n))
+    full = pa.table({"chrom": pa.array(contig), "start": pa.array(start), "end": pa.array(end64, pa.int64())})
+    cuts = [0, 1, 4, 1031, 1033, 5000, 5003, 12_345, 16_384, 16_387, n]
+    batches = [b for lo, hi in zip(cuts[:-1], cuts[1:]) for b in full.slice(lo, hi - lo).to_batches()]
+    t = pa.Table.from_batches(batches)
+    _, keys = _roundtrip(lib, t, [0])
+    names = {}
+    for nm, c in zip(contig, keys[:, 0]):
+        assert names.setdefault(nm, c) == c
+    assert len(set(names.values())) == len(names) == 4
+    assert np.array_equal(keys[:, 1], start) and np.array_equal(keys[:, 2], end64.astype(np.int32))
