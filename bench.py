@@ -71,16 +71,19 @@ def measured_peak_gbs():
 
 
 def ncu_traffic(kernel_label: str):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel from the committed ncu capture."""
-    p = os.path.join(ROOT, "profiles", "r01c_traffic.json")
-    try:
-        t = json.load(open(p))
-        for name, v in t.items():
-            if name in kernel_label:
-                return v["traffic_bytes"]
-    except Exception:
-        pass
-    return None
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel from the newest committed
+    `ncu --set full` capture (profiles/<tag>_traffic.json, written by scripts/ncu_summary.py).  Returns (bytes, file)."""
+    import glob
+    for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")), reverse=True):
+        try:
+            t = json.load(open(p))
+            for name, v in t.items():
+                base = name.split("<")[0].rsplit("_", 2)[0]  # overlap_emit_flat_kernel<..> -> overlap_emit
+                if kernel_label.startswith(base + "_"):
+                    return v["traffic_bytes"], "profiles/" + os.path.basename(p)
+        except Exception:
+            continue
+    return None, None
 
 
 class ClockSampler:
@@ -404,8 +407,9 @@ def main():
     }
     dom = max(cands, key=lambda k: cands[k][1])
     ach = cands[dom][0] / (cands[dom][1] * 1e-3) / 1e9
+    traffic, traffic_file = ncu_traffic(dom)
     roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "traffic": ncu_traffic(dom), "traffic_source": "profiles/r01c_traffic.json (ncu --set full, cold-cache replay, per launch)",
+            "traffic": traffic, "traffic_source": f"{traffic_file} (ncu --set full, cold-cache replay, per launch)",
             "peak_source": peak_src, "algorithmic_bytes": cands[dom][0], "kernel_ms": cands[dom][1],
             "all_kernels": {k: {"ms": v[1], "algorithmic_bytes": v[0], "GBps": v[0] / (v[1] * 1e-3) / 1e9} for k, v in cands.items()},
             "index_build_ms": km["partition_sort_ns"], "offset_scan_ms": km["scan_ns"],
