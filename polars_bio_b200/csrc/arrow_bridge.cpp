@@ -42,6 +42,8 @@ int widen_codes_u8(const uint8_t *d_in, int64_t n, int32_t n_contigs, int32_t *d
 int gather_i32_u8(const int32_t *d_src, const uint32_t *d_rows, int64_t n, uint8_t *d_out, void *stream);
 int count_overlaps_u32(const pbgpu_index *ix, const int32_t *c, const int32_t *s, const int32_t *e, int64_t n, int filter_op,
                        uint32_t *d_counts, void *stream);  // pbgpu.cu (internal)
+int dev_alloc(void **p, size_t bytes, cudaStream_t s);  // stream-ordered device blocks through pbgpu.cu's block cache
+void dev_free(void *p, cudaStream_t s);
 }  // namespace pbgpu
 using pbgpu::set_error;
 
@@ -1127,11 +1129,11 @@ struct DevBufs {  // device scratch of one call, freed stream-ordered
   template <typename T>
   T *get(size_t count) {
     void *p = nullptr;
-    if (cudaMallocAsync(&p, sizeof(T) * (count ? count : 1), s) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (pbgpu::dev_alloc(&p, sizeof(T) * (count ? count : 1), s) != PBGPU_OK) return nullptr;  // block cache of pbgpu.cu
     v.push_back(p);
     return (T *)p;
   }
-  void release() { for (void *p : v) cudaFreeAsync(p, s); v.clear(); }
+  void release() { for (void *p : v) pbgpu::dev_free(p, s); v.clear(); }
   ~DevBufs() { release(); }
 };
 

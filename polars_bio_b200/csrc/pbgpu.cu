@@ -3,6 +3,8 @@
 #include <stdarg.h>
 
 #include <mutex>
+#include <utility>
+#include <vector>
 
 #include "common.cuh"
 #include "index.cuh"
@@ -32,20 +34,144 @@ static void tune_pool(int dev) {
   }
 }
 
+// ---- device block cache ---------------------------------------------------------------------------------------
+// cudaMallocAsync splits and re-merges the blocks of its pool.  A build over 90 M rows asks for a dozen blocks of
+// 0.3-3.6 GB in varying order; the pool then keeps mapping fresh physical memory (30-360 ms per block, measured:
+// profiles/r01x) although the same sizes were freed a moment ago.  Blocks of >= 64 KB are therefore never handed
+// back on free: they are parked, whole, with an event recorded on the freeing stream, and the next request of the
+// same size class gets one of them -- stream-ordered like cudaMallocAsync itself: reuse on the freeing stream
+// needs nothing, reuse on another stream first waits for the event.  Size classes are 1/16-octave steps, so the
+// sizes of one workload map onto themselves call after call and a steady state makes no allocator calls at all.
+// Parked bytes are capped (PBGPU_DEV_CACHE_MB, default 1/3 of the device); on overflow or on an allocation
+// failure the oldest parked blocks go back to the pool.  Smaller requests use the pool directly.
+struct ParkedBlock { void *p; size_t bytes; cudaStream_t stream; cudaEvent_t ev; int dev; uint64_t age; };
+struct BlockCache {
+  std::mutex mu;
+  std::vector<ParkedBlock> parked;
+  std::vector<std::pair<void *, size_t>> live;  // blocks of cacheable size handed out: pointer -> class size
+  std::vector<std::pair<int, cudaEvent_t>> spare_events;  // (device, event)
+  size_t parked_bytes = 0, cap = 0;
+  uint64_t clock = 0;
+  bool enabled = true;
+  BlockCache() {
+    const char *e = getenv("PBGPU_DEV_CACHE_MB");
+    if (e) { const long long mb = atoll(e); if (mb <= 0) enabled = false; else cap = (size_t)mb << 20; }
+  }
+};
+static BlockCache &block_cache() { static BlockCache *c = new BlockCache(); return *c; }  // never destroyed: no CUDA calls at exit
+constexpr size_t kCacheMinBytes = 64 << 10;
+static size_t size_class(size_t b) {
+  int hb = 63 - __builtin_clzll((unsigned long long)b);
+  const size_t step = (size_t)1 << (hb > 4 ? hb - 4 : 0);
+  return (b + step - 1) & ~(step - 1);
+}
+// give parked blocks back to the pool, oldest first, until at most `keep` bytes stay parked (mu held)
+static void cache_release_locked(BlockCache &c, int dev, size_t keep) {
+  while (c.parked_bytes > keep && !c.parked.empty()) {
+    size_t k = 0;
+    for (size_t i = 1; i < c.parked.size(); ++i) if (c.parked[i].age < c.parked[k].age) k = i;
+    ParkedBlock b = c.parked[k];
+    c.parked[k] = c.parked.back();
+    c.parked.pop_back();
+    c.parked_bytes -= b.bytes;
+    int cur = dev;
+    if (b.dev != cur) cudaSetDevice(b.dev);
+    if (b.ev) { cudaEventSynchronize(b.ev); c.spare_events.emplace_back(b.dev, b.ev); }
+    cudaFreeAsync(b.p, cudaStreamPerThread);  // its last use has completed: any stream will do
+    if (b.dev != cur) cudaSetDevice(cur);
+  }
+}
+
 int dev_alloc(void **p, size_t bytes, cudaStream_t s) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64) std::call_once(g_pool_once[dev], tune_pool, dev);
-  cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 1, s);
+  if (!bytes) bytes = 1;
+  BlockCache &c = block_cache();
+  const bool cacheable = c.enabled && bytes >= kCacheMinBytes;
+  if (cacheable) {
+    bytes = size_class(bytes);
+    std::lock_guard<std::mutex> lk(c.mu);
+    int hit = -1;
+    for (size_t i = 0; i < c.parked.size(); ++i) {
+      const ParkedBlock &b = c.parked[i];
+      if (b.dev != dev || b.bytes != bytes) continue;
+      if (b.stream == s) { hit = (int)i; break; }  // same stream: plain stream order, no wait
+      if (hit < 0) hit = (int)i;
+    }
+    if (hit >= 0) {
+      ParkedBlock b = c.parked[hit];
+      c.parked[hit] = c.parked.back();
+      c.parked.pop_back();
+      c.parked_bytes -= b.bytes;
+      if (b.ev) {
+        if (b.stream != s && cudaStreamWaitEvent(s, b.ev, 0) != cudaSuccess) { cudaGetLastError(); cudaEventSynchronize(b.ev); }
+        c.spare_events.emplace_back(b.dev, b.ev);
+      }
+      c.live.emplace_back(b.p, b.bytes);
+      *p = b.p;
+      return PBGPU_OK;
+    }
+  }
+  cudaError_t e = cudaMallocAsync(p, bytes, s);
+  if (e == cudaErrorMemoryAllocation && c.enabled) {  // hand every parked block back and try once more
+    cudaGetLastError();
+    {
+      std::lock_guard<std::mutex> lk(c.mu);
+      cache_release_locked(c, dev, 0);
+    }
+    cudaStreamSynchronize(cudaStreamPerThread);
+    e = cudaMallocAsync(p, bytes, s);
+  }
   if (e != cudaSuccess) {
     cudaGetLastError();
     return set_error(e == cudaErrorMemoryAllocation ? PBGPU_ENOMEM : PBGPU_ECUDA, "cudaMallocAsync(%zu) failed: %s", bytes,
                      cudaGetErrorString(e));
   }
+  if (cacheable) {
+    std::lock_guard<std::mutex> lk(c.mu);
+    c.live.emplace_back(*p, bytes);
+  }
   return PBGPU_OK;
 }
 void dev_free(void *p, cudaStream_t s) {
-  if (p) cudaFreeAsync(p, s);
+  if (!p) return;
+  BlockCache &c = block_cache();
+  if (c.enabled) {
+    std::lock_guard<std::mutex> lk(c.mu);
+    for (size_t i = c.live.size(); i-- > 0;) {
+      if (c.live[i].first != p) continue;
+      const size_t bytes = c.live[i].second;
+      c.live[i] = c.live.back();
+      c.live.pop_back();
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (!c.cap) {
+        size_t fr = 0, tot = 0;
+        c.cap = cudaMemGetInfo(&fr, &tot) == cudaSuccess ? tot / 3 : ((size_t)16 << 30);
+      }
+      cudaEvent_t ev = nullptr;
+      for (size_t k = c.spare_events.size(); k-- > 0;) {
+        if (c.spare_events[k].first != dev) continue;
+        ev = c.spare_events[k].second;
+        c.spare_events[k] = c.spare_events.back();
+        c.spare_events.pop_back();
+        break;
+      }
+      if (!ev && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); ev = nullptr; }
+      if (!ev || cudaEventRecord(ev, s) != cudaSuccess) {  // cannot order a later reuse: ordinary free
+        cudaGetLastError();
+        if (ev) c.spare_events.emplace_back(dev, ev);
+        cudaFreeAsync(p, s);
+        return;
+      }
+      c.parked.push_back(ParkedBlock{p, bytes, s, ev, dev, ++c.clock});
+      c.parked_bytes += bytes;
+      if (c.parked_bytes > c.cap) cache_release_locked(c, dev, c.cap - c.cap / 4);
+      return;
+    }
+  }
+  cudaFreeAsync(p, s);
 }
 
 // CUDA-event stage marks, always on (an event record is ~1 us of host time and no device sync): pairs of
@@ -190,9 +316,9 @@ void pbgpu_index_free(pbgpu_index *ix) {
   if (cur != ix->device) cudaSetDevice(ix->device);
   // stream-ordered free on the legacy default stream: ordered after everything blocking streams have queued;
   // users of non-blocking streams synchronise before freeing (pbgpu.h)
-  if (ix->slab) cudaFreeAsync(ix->slab, 0);
-  if (ix->slab2) cudaFreeAsync(ix->slab2, 0);
-  if (ix->slab_n) cudaFreeAsync(ix->slab_n, 0);
+  dev_free(ix->slab, 0);
+  dev_free(ix->slab2, 0);
+  dev_free(ix->slab_n, 0);
   if (cur != ix->device) cudaSetDevice(cur);
   delete ix;
 }
@@ -580,7 +706,7 @@ void pbgpu_overlap_plan_free(pbgpu_overlap_plan *p) {
   int cur = 0;
   cudaGetDevice(&cur);
   if (cur != p->device) cudaSetDevice(p->device);
-  if (p->slab) cudaFreeAsync(p->slab, 0);  // legacy stream: ordered after the emit kernel of blocking streams
+  dev_free(p->slab, 0);  // legacy stream: ordered after the emit kernel of blocking streams
   if (cur != p->device) cudaSetDevice(cur);
   delete p;
 }
@@ -590,7 +716,7 @@ void pbgpu_overlap_plan_free_async(pbgpu_overlap_plan *p, void *stream) {
   int cur = 0;
   cudaGetDevice(&cur);
   if (cur != p->device) cudaSetDevice(p->device);
-  if (p->slab) cudaFreeAsync(p->slab, (cudaStream_t)stream);  // ordered after the pass-2 launches enqueued on `stream`
+  dev_free(p->slab, (cudaStream_t)stream);  // ordered after the pass-2 launches enqueued on `stream`
   if (cur != p->device) cudaSetDevice(cur);
   delete p;
 }

@@ -280,3 +280,32 @@ def test_full_size_properties_config2():
     sl = slice(4_000_000, 4_200_000)
     oc = oracle.Index(bc, bs, be, nc).count_overlaps(pc[sl], ps[sl], pe[sl], True, threads=4)
     assert np.array_equal(cnt[sl].cpu().numpy(), oc)
+
+
+def test_block_cache_reuse_across_sizes_and_streams():
+    """The device block cache (pbgpu.cu) parks freed blocks and hands them to the next request of the same size
+    class -- in stream order on the freeing stream, behind an event on any other.  Alternate two table sizes on the
+    default stream and two side streams, freeing every index right after use: every result must still equal the
+    oracle's (a block handed out too early would be overwritten while the previous job still reads it)."""
+    eng = _engine()
+    rng = np.random.default_rng(77)
+    jobs = []
+    for m, n in ((120_000, 400_000), (40_000, 150_000)):
+        bc, bs, be = synth(m, 3, 5_000_000, 400, int(rng.integers(1 << 30)))
+        pc, ps, pe = synth(n, 3, 5_000_000, 200, int(rng.integers(1 << 30)))
+        oix = oracle.Index(bc, bs, be, 3)
+        jobs.append(((pc, ps, pe), (bc, bs, be), oix.count_overlaps(pc, ps, pe, True), oix.overlap_pairs(pc, ps, pe, True)))
+    streams = [torch.cuda.current_stream(), torch.cuda.Stream(), torch.cuda.Stream()]
+    for it in range(12):
+        (pc, ps, pe), (bc, bs, be), ocnt, (oa, ob) = jobs[it % 2]
+        st = streams[it % 3]
+        with torch.cuda.stream(st):
+            dp, db = [_dev(x) for x in (pc, ps, pe)], [_dev(x) for x in (bc, bs, be)]
+            st.wait_stream(torch.cuda.default_stream())  # the H2D copies above ran on `st` already; keep it explicit
+            ix = eng.DeviceIndex(*db, 3)
+            cnt = ix.count_overlaps(*dp, eng.FILTER_STRICT)
+            a, b = ix.overlap_pairs(*dp, eng.FILTER_STRICT)
+            st.synchronize()  # non-blocking stream: synchronise before the index goes back (pbgpu.h)
+            ix.close()
+        assert np.array_equal(cnt.cpu().numpy(), ocnt), it
+        assert np.array_equal(_u32(a), oa) and np.array_equal(_u32(b), ob), it
