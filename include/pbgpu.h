@@ -47,8 +47,9 @@ extern "C" {
 
 /* ---- option enums (src/option.rs) ------------------------------------------------------ */
 enum { PBGPU_FILTER_WEAK = 0, PBGPU_FILTER_STRICT = 1 };             /* option.rs:96-99   */
-enum { PBGPU_OP_OVERLAP = 0, PBGPU_OP_NEAREST = 3, PBGPU_OP_COVERAGE = 4,
-       PBGPU_OP_COUNT_OVERLAPS_NAIVE = 6 };                           /* option.rs:103-112 */
+enum { PBGPU_OP_OVERLAP = 0, PBGPU_OP_COMPLEMENT = 1, PBGPU_OP_CLUSTER = 2, PBGPU_OP_NEAREST = 3, PBGPU_OP_COVERAGE = 4,
+       PBGPU_OP_SUBTRACT = 5, PBGPU_OP_COUNT_OVERLAPS_NAIVE = 6, PBGPU_OP_MERGE = 7 };  /* option.rs:103-112; the unary
+       sweeps (1, 2, 5, 7) exist at the device level only (pbgpu_merge / _cluster / _subtract)                     */
 enum { PBGPU_OUT_JOIN = 0, PBGPU_OUT_LEFT = 1, PBGPU_OUT_LEFT_DISTINCT = 2 }; /* operation.rs:229-233 */
 
 #define PBGPU_NO_PARTNER 0xFFFFFFFFu
@@ -157,6 +158,39 @@ PBGPU_API int pbgpu_unpack_records(const int32_t *d_packed, int64_t n, int32_t *
  * d_out[i] = d_global_of_local[d_local[i]]  (PBGPU_NO_PARTNER passes through).  d_out may alias d_local. */
 PBGPU_API int pbgpu_translate_rows(const uint32_t *d_local, int64_t n, const uint32_t *d_global_of_local,
                                    uint32_t *d_out, void *stream);
+
+/* ---- unary sweeps: they reuse the contig partition + start sort of the index build.
+ * Reference: MergeProvider / ClusterProvider / ComplementProvider / SubtractProvider constructed at
+ * /root/reference/src/operation.rs:352-380, 382-430, 432-461, 463-510; behaviour pinned by tests/_expected.py:174-181,
+ * tests/test_coordinate_system_metadata.py:1032-1054, tests/test_partitioned_range_operation_regressions.py:24-59.
+ * A row joins the running interval iff  start < reach + min_dist  (Strict, 0-based half-open) /
+ * start <= reach + min_dist  (Weak, 1-based closed), reach = largest end so far; min_dist >= 0.
+ * Results are device tables owned by the library (exact-sized; the call synchronises `stream` once to size them). */
+typedef struct pbgpu_intervals pbgpu_intervals;
+PBGPU_API int64_t pbgpu_intervals_rows(const pbgpu_intervals *t);
+/* device columns of a result (any out pointer may be NULL): merge -> contig, start, end, count (n_intervals);
+ * subtract -> row (uint32 row of the left table), start, end; columns a result does not have read NULL          */
+PBGPU_API int pbgpu_intervals_columns(const pbgpu_intervals *t, const int32_t **d_contig, const uint32_t **d_row,
+                                      const int32_t **d_start, const int32_t **d_end, const int64_t **d_count);
+/* copy columns into caller-owned device buffers of pbgpu_intervals_rows() entries (NULL = skip), on `stream`     */
+PBGPU_API int pbgpu_intervals_copy(const pbgpu_intervals *t, int32_t *d_contig, uint32_t *d_row, int32_t *d_start,
+                                   int32_t *d_end, int64_t *d_count, void *stream);
+PBGPU_API void pbgpu_intervals_free(pbgpu_intervals *t, void *stream);   /* stream-ordered release on `stream` */
+/* merge: one row per merged interval, ordered by (contig code, start)                                            */
+PBGPU_API int pbgpu_merge(const int32_t *d_contig, const int32_t *d_start, const int32_t *d_end, int64_t m,
+                          int32_t n_contigs, int filter_op, int64_t min_dist, void *stream, pbgpu_intervals **out);
+/* cluster: for every input row the id of its merged interval (numbered from 0 in (contig code, start) order; -1 for
+ * null-keyed rows) and that interval's start / end.  d_cluster int64[m], d_cluster_start / d_cluster_end int32[m]. */
+PBGPU_API int pbgpu_cluster(const int32_t *d_contig, const int32_t *d_start, const int32_t *d_end, int64_t m,
+                            int32_t n_contigs, int filter_op, int64_t min_dist, int64_t *d_cluster,
+                            int32_t *d_cluster_start, int32_t *d_cluster_end, int64_t *n_clusters, void *stream);
+/* subtract: for every left row the pieces no right row of the same contig covers, ordered by (left row, start); an
+ * untouched row passes through whole, a covered one leaves nothing.  Right rows with start > end cover nothing, left
+ * rows with start > end pass through.  Weak (closed coordinates): [s,e] minus [s2,e2] leaves [s,s2-1] and [e2+1,e].
+ * complement (operation.rs:432-461) is this call with the view table on the left.                                 */
+PBGPU_API int pbgpu_subtract(const int32_t *l_contig, const int32_t *l_start, const int32_t *l_end, int64_t n,
+                             const int32_t *r_contig, const int32_t *r_start, const int32_t *r_end, int64_t m,
+                             int32_t n_contigs, int filter_op, void *stream, pbgpu_intervals **out);
 
 /* CUDA-event durations (ns) of the most recent index build / provider kernels issued by the calling
  * thread, measured on the stream they were launched on (events are recorded on every call; this function

@@ -94,6 +94,15 @@ def lib() -> ctypes.CDLL:
     L.pbgpu_contig_histogram.argtypes = [vp, i64, i32, vp, vp]
     L.pbgpu_unpack_records.argtypes = [vp, i64, vp, vp, vp, vp, vp]
     L.pbgpu_translate_rows.argtypes = [vp, i64, vp, vp, vp]
+    L.pbgpu_intervals_rows.argtypes = [vp]
+    L.pbgpu_intervals_rows.restype = i64
+    L.pbgpu_intervals_columns.argtypes = [vp] + [ctypes.POINTER(vp)] * 5
+    L.pbgpu_intervals_copy.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.pbgpu_intervals_free.argtypes = [vp, vp]
+    L.pbgpu_intervals_free.restype = None
+    L.pbgpu_merge.argtypes = [vp, vp, vp, i64, i32, ctypes.c_int, i64, vp, ctypes.POINTER(vp)]
+    L.pbgpu_cluster.argtypes = [vp, vp, vp, i64, i32, ctypes.c_int, i64, vp, vp, vp, ctypes.POINTER(i64), vp]
+    L.pbgpu_subtract.argtypes = [vp, vp, vp, i64, vp, vp, vp, i64, i32, ctypes.c_int, vp, ctypes.POINTER(vp)]
     L.pbgpu_last_stage_times.argtypes = [ctypes.POINTER(StageTimes)]
     L.pbgpu_range_op.argtypes = [vp, vp, ctypes.POINTER(PbRangeOptions), vp]
     _lib = L

@@ -323,6 +323,15 @@ void pbgpu_index_free(pbgpu_index *ix) {
   delete ix;
 }
 
+// internal: release an index in stream order on `s` (the stream its last reader was enqueued on)
+static void index_free_on(pbgpu_index *ix, cudaStream_t s) {
+  if (!ix) return;
+  dev_free(ix->slab, s);
+  dev_free(ix->slab2, s);
+  dev_free(ix->slab_n, s);
+  delete ix;
+}
+
 int64_t pbgpu_index_rows(const pbgpu_index *ix) { return ix ? ix->m : 0; }
 size_t pbgpu_index_bytes(const pbgpu_index *ix) { return ix ? ix->bytes : 0; }
 
@@ -357,8 +366,10 @@ struct BuildTrace {
   }
 };
 
+// sweep_only: the caller wants the (contig, start, row) order, the segments and the running max of the ends only (the
+// unary sweeps of unary.cuh): the end order and the rank directory are skipped
 static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *d_s, const int32_t *d_e, int64_t m_in,
-                            int32_t n_contigs, cudaStream_t s) {
+                            int32_t n_contigs, cudaStream_t s, bool sweep_only = false) {
   ix->m_in = m_in;
   ix->n_contigs = n_contigs;
   PB_CUDA(cudaGetDevice(&ix->device));
@@ -492,6 +503,12 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
     PB_CHECK_LAUNCH();
     PB_TRY((device_scan<MaxU64, true>((const unsigned long long *)pm_keys, (unsigned long long *)pm_keys, m, nullptr, s)));
     PB_LAUNCH(unpack_pmax_kernel, (unsigned)cdiv(m, 256), 256, 0, s, pm_keys, m, ix->pmax);
+    PB_CHECK_LAUNCH();
+    if (sweep_only) {
+      ix->en_sorted = nullptr;
+      ix->en_pos = nullptr;
+      return PBGPU_OK;
+    }
     // the rows are already grouped by contig: sorting the varying end digits stably, then the contig digits, gives
     // (contig, end, start, row) order
     int epos[kRsMaxPasses], ne = varying_digits(hs.min_end, hs.max_end, epos, 0);
@@ -504,6 +521,7 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
     bt.lap("nested: pmax + end sort");
   }
 
+  if (sweep_only) return PBGPU_OK;
   // 5. fast path: global axis + rank directories
   const unsigned long long total_span = h_meta[1];
   if (try_fast && total_span > 0 && total_span < 0xFFFFFFF0ull) {
@@ -1024,3 +1042,5 @@ extern "C" int pbgpu_pack_by_owner(const int32_t *d_contig, const int32_t *d_sta
   }
   return PBGPU_OK;
 }
+
+#include "unary.cuh"

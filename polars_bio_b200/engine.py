@@ -161,3 +161,59 @@ class DeviceIndex:
                                         int(include_overlaps), partner.data_ptr(),
                                         dist.data_ptr() if dist is not None else None, _stream_ptr(self.device)))
         return partner, dist
+
+
+# ---- unary sweeps (MergeProvider / ClusterProvider / SubtractProvider, operation.rs:352-510) ------------------
+def _intervals_out(L, handle, device, want):
+    """Copies the requested columns of a pbgpu_intervals result into torch tensors and releases it in stream order."""
+    sp = _stream_ptr(device)
+    try:
+        n = int(L.pbgpu_intervals_rows(handle))
+        out = {w: torch.empty(n, dtype=torch.int64 if w == "count" else torch.int32, device=device) for w in want}
+        args = [out[w].data_ptr() if w in out and n else None for w in ("contig", "row", "start", "end", "count")]
+        check(L.pbgpu_intervals_copy(handle, *args, sp))
+        return tuple(out[w] for w in want)
+    finally:
+        L.pbgpu_intervals_free(handle, sp)
+
+
+def merge_intervals(contig, start, end, n_contigs: int, filter_op: int, min_dist: int = 0):
+    """Merged intervals of one table, ordered by (contig code, start): (contig, start, end) int32, n_intervals int64."""
+    device = contig.device
+    c, s, e = (_col(x, device) for x in (contig, start, end))
+    L = _native.lib()
+    h = ctypes.c_void_p()
+    with torch.cuda.device(device):
+        check(L.pbgpu_merge(c.data_ptr(), s.data_ptr(), e.data_ptr(), c.numel(), int(n_contigs), filter_op, int(min_dist),
+                            _stream_ptr(device), ctypes.byref(h)))
+        return _intervals_out(L, h, device, ("contig", "start", "end", "count"))
+
+
+def cluster_intervals(contig, start, end, n_contigs: int, filter_op: int, min_dist: int = 0):
+    """Per input row: cluster id (int64; numbered in (contig code, start) order, -1 for null-keyed rows) and the
+    cluster's start / end (int32).  Returns (cluster, cluster_start, cluster_end, n_clusters)."""
+    device = contig.device
+    c, s, e = (_col(x, device) for x in (contig, start, end))
+    m = c.numel()
+    cid = torch.empty(m, dtype=torch.int64, device=device)
+    cs = torch.empty(m, dtype=torch.int32, device=device)
+    ce = torch.empty(m, dtype=torch.int32, device=device)
+    k = ctypes.c_int64(0)
+    with torch.cuda.device(device):
+        check(_native.lib().pbgpu_cluster(c.data_ptr(), s.data_ptr(), e.data_ptr(), m, int(n_contigs), filter_op, int(min_dist),
+                                          cid.data_ptr(), cs.data_ptr(), ce.data_ptr(), ctypes.byref(k), _stream_ptr(device)))
+    return cid, cs, ce, int(k.value)
+
+
+def subtract_intervals(l_contig, l_start, l_end, r_contig, r_start, r_end, n_contigs: int, filter_op: int):
+    """Pieces of every left row that no right row covers, ordered by (left row, start): (left_row, start, end) int32
+    tensors (left_row holds uint32 row ids).  complement = the view table on the left."""
+    device = l_contig.device
+    lc, ls, le = (_col(x, device) for x in (l_contig, l_start, l_end))
+    rc, rs, re = (_col(x, device) for x in (r_contig, r_start, r_end))
+    L = _native.lib()
+    h = ctypes.c_void_p()
+    with torch.cuda.device(device):
+        check(L.pbgpu_subtract(lc.data_ptr(), ls.data_ptr(), le.data_ptr(), lc.numel(), rc.data_ptr(), rs.data_ptr(), re.data_ptr(),
+                               rc.numel(), int(n_contigs), filter_op, _stream_ptr(device), ctypes.byref(h)))
+        return _intervals_out(L, h, device, ("row", "start", "end"))

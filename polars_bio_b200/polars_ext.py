@@ -37,6 +37,20 @@ class PolarsRangesOperations:
         return IntervalOperations.coverage(self._ldf, other_df, suffixes=suffixes, cols1=cols1, cols2=cols2,
                                            projection_pushdown=projection_pushdown)
 
+    def merge(self, min_dist=0, cols=["chrom", "start", "end"], projection_pushdown=True):
+        return IntervalOperations.merge(self._ldf, min_dist=min_dist, cols=cols, projection_pushdown=projection_pushdown)
+
+    def cluster(self, min_dist=0, cols=["chrom", "start", "end"], projection_pushdown=True):
+        return IntervalOperations.cluster(self._ldf, min_dist=min_dist, cols=cols, projection_pushdown=projection_pushdown)
+
+    def complement(self, view_df=None, cols=["chrom", "start", "end"], view_cols=None, projection_pushdown=True):
+        return IntervalOperations.complement(self._ldf, view_df=view_df, cols=cols, view_cols=view_cols,
+                                             projection_pushdown=projection_pushdown)
+
+    def subtract(self, other_df, cols1=["chrom", "start", "end"], cols2=["chrom", "start", "end"], projection_pushdown=True):
+        return IntervalOperations.subtract(self._ldf, other_df, cols1=cols1, cols2=cols2,
+                                           projection_pushdown=projection_pushdown)
+
 
 if pl is not None:  # pragma: no cover - exercised only where polars exists
     pl.api.register_lazyframe_namespace("pb")(PolarsRangesOperations)

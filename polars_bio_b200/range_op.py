@@ -11,14 +11,14 @@ from __future__ import annotations
 
 from typing import Literal, Union
 
-from ._metadata import validate_coordinate_systems
+from ._metadata import validate_coordinate_system_single, validate_coordinate_systems
 from .constants import DEFAULT_INTERVAL_COLUMNS
 from .context import ctx
 from .logging import logger
 from .options import FilterOp, OverlapOutputMode, RangeOp, RangeOptions
-from .range_op_helpers import _validate_overlap_input, range_operation
+from .range_op_helpers import _validate_overlap_input, range_operation, unary_operation
 
-__all__ = ["overlap", "nearest", "count_overlaps", "coverage"]
+__all__ = ["overlap", "nearest", "count_overlaps", "coverage", "merge", "cluster", "complement", "subtract"]
 
 DEFAULT_OUTPUT_TYPE = "polars.LazyFrame"
 
@@ -34,6 +34,10 @@ def _parse_overlap_output_mode(overlap_output: str) -> OverlapOutputMode:
 
 def _filter_op(df1, df2) -> FilterOp:
     return FilterOp.Strict if validate_coordinate_systems(df1, df2, ctx) else FilterOp.Weak
+
+
+def _filter_op_single(df) -> FilterOp:  # range_op.py:87-111
+    return FilterOp.Strict if validate_coordinate_system_single(df, ctx) else FilterOp.Weak
 
 
 class IntervalOperations:
@@ -106,8 +110,63 @@ class IntervalOperations:
                             columns_1=cols2, columns_2=cols1)
         return range_operation(df2, df1, opts, output_type, ctx)
 
+    # ---- unary sweeps (range_op.py:599-868) -------------------------------------------------
+    @staticmethod
+    def merge(df, min_dist: int = 0, cols=["chrom", "start", "end"], on_cols=None, output_type: str = DEFAULT_OUTPUT_TYPE,
+              projection_pushdown: bool = True):
+        """Merge overlapping intervals (range_op.py:600-655): (contig, start, end) as Int64 + ``n_intervals``.
+        0-based: adjacent intervals stay apart; 1-based: intervals sharing an end point merge
+        (tests/test_coordinate_system_metadata.py:1032-1054)."""
+        _validate_overlap_input(cols, cols, on_cols, ("_1", "_2"), output_type)
+        filter_op = _filter_op_single(df)
+        cols = DEFAULT_INTERVAL_COLUMNS if cols is None else list(cols)
+        opts = RangeOptions(range_op=RangeOp.Merge, filter_op=filter_op, columns_1=cols, columns_2=cols, min_dist=min_dist)
+        return unary_operation(df, df, opts, output_type, ctx)
+
+    @staticmethod
+    def cluster(df, min_dist: int = 0, cols=["chrom", "start", "end"], output_type: str = DEFAULT_OUTPUT_TYPE,
+                projection_pushdown: bool = True):
+        """Every input row + ``cluster`` (id), ``cluster_start``, ``cluster_end`` of the merged interval it belongs to
+        (range_op.py:657-712)."""
+        _validate_overlap_input(cols, cols, None, ("_1", "_2"), output_type)
+        filter_op = _filter_op_single(df)
+        cols = DEFAULT_INTERVAL_COLUMNS if cols is None else list(cols)
+        opts = RangeOptions(range_op=RangeOp.Cluster, filter_op=filter_op, columns_1=cols, columns_2=cols, min_dist=min_dist)
+        return unary_operation(df, df, opts, output_type, ctx)
+
+    @staticmethod
+    def complement(df, view_df=None, cols=["chrom", "start", "end"], view_cols=None, output_type: str = DEFAULT_OUTPUT_TYPE,
+                   projection_pushdown: bool = True):
+        """The gaps between the intervals, inside ``view_df``'s regions when given, else inside [0, i64::MAX) of every
+        contig present (range_op.py:714-789)."""
+        _validate_overlap_input(cols, cols, None, ("_1", "_2"), output_type)
+        filter_op = _filter_op_single(df)
+        cols = DEFAULT_INTERVAL_COLUMNS if cols is None else list(cols)
+        view_cols = cols if view_cols is None else list(view_cols)
+        if view_df is None:
+            logger.warning("No view_df provided — complement will span [0, i64::MAX) per contig. "
+                           "Pass a view_df with contig boundaries (e.g., chromosome sizes) for meaningful results.")
+        opts = RangeOptions(range_op=RangeOp.Complement, filter_op=filter_op, columns_1=cols, columns_2=cols,
+                            view_table=None if view_df is None else "_view", view_columns=view_cols)
+        return unary_operation(df, df, opts, output_type, ctx, view_df=view_df)
+
+    @staticmethod
+    def subtract(df1, df2, cols1=["chrom", "start", "end"], cols2=["chrom", "start", "end"],
+                 output_type: str = DEFAULT_OUTPUT_TYPE, projection_pushdown: bool = True):
+        """df1's intervals with every part covered by df2 removed; df1's other columns are kept (range_op.py:791-868)."""
+        _validate_overlap_input(cols1, cols2, None, ("_1", "_2"), output_type)
+        filter_op = _filter_op(df1, df2)
+        cols1 = DEFAULT_INTERVAL_COLUMNS if cols1 is None else list(cols1)
+        cols2 = DEFAULT_INTERVAL_COLUMNS if cols2 is None else list(cols2)
+        opts = RangeOptions(range_op=RangeOp.Subtract, filter_op=filter_op, columns_1=cols1, columns_2=cols2)
+        return unary_operation(df1, df2, opts, output_type, ctx)
+
 
 overlap = IntervalOperations.overlap
 nearest = IntervalOperations.nearest
 coverage = IntervalOperations.coverage
 count_overlaps = IntervalOperations.count_overlaps
+merge = IntervalOperations.merge
+cluster = IntervalOperations.cluster
+complement = IntervalOperations.complement
+subtract = IntervalOperations.subtract
