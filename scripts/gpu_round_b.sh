@@ -5,8 +5,9 @@ TAG=${1:-run}
 O=gpurun_out
 mkdir -p $O
 echo "== pytest -m gpu"
-timeout 600 python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest_gpu.log 2>&1
-echo "pytest rc=$?"; tail -3 $O/${TAG}_pytest_gpu.log
+timeout 900 python -m pytest tests -m gpu -q ${PYTEST_ARGS:--x} > $O/${TAG}_pytest_gpu.log 2>&1
+echo "pytest rc=$?"; grep -E "^(FAILED|ERROR)|passed|failed" $O/${TAG}_pytest_gpu.log | tail -40
+grep -n -E "^E  " $O/${TAG}_pytest_gpu.log | head -60
 echo "== bench"
 timeout 600 python bench.py > $O/${TAG}_bench_1gpu.json 2> $O/${TAG}_bench_1gpu.err
 echo "bench rc=$?"; tail -c 3500 $O/${TAG}_bench_1gpu.json; tail -5 $O/${TAG}_bench_1gpu.err
