@@ -270,9 +270,9 @@ def measure_e2e(args, probe, build, contig_name, expect_pairs, barrier, world, d
 def run_sharded(args, world, rank, dev):
     """N > 1: weak scaling over contigs WITH the exchange step.  The job is N copies of config 2 (contig k = copy k
     of chr1; N x 10M reads, N x 1M variants); every rank starts with an arbitrary 1/N slice of both tables (rows of
-    all contigs mixed), as when row-groups are read round-robin.  One step = per-contig histogram (all_reduce) +
-    owner table + K8 pack + NCCL all-to-all of 16-byte records + unpack, for both tables, then the same local pass
-    as at N = 1 (index build + count_overlaps + two-pass emit) + translation of pair ids to global row ids."""
+    all contigs mixed), as when row-groups are read round-robin.  One step = the contig exchange of both tables
+    (dist.shard_tables: per-contig histograms, owner table, then either the peer-memory scatter over NVLink or
+    K8 pack + NCCL all-to-all of 16-byte records + unpack), then the same local pass as at N = 1 (index build + count_overlaps + two-pass emit) + translation of pair ids to global row ids."""
     import torch
     import torch.distributed as dist
 
@@ -350,9 +350,12 @@ def run_sharded(args, world, rank, dev):
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": {"workload": f"{world} x config2 (contig k = copy k of chr1): {n} reads x {m} variants per GPU, rows start on arbitrary ranks; "
-                               "contig all-to-all + index build + count_overlaps + two-pass pair emit",
+                               "contig exchange + index build + count_overlaps + two-pass pair emit",
                    "pairs_per_step": pairs_all, "l2": "flushed between timed steps (256 MiB write)",
-                   "parallelism": f"contig-sharded x{world}, NCCL all-to-all of 16-byte records",
+                   "parallelism": (f"contig-sharded x{world}, rows stored straight into their owner's columns over NVLink peer memory "
+                                   "(CUDA IPC arenas; plan + scatter kernels, NCCL only for a histogram all_gather and the closing all_reduce)"
+                                   if pbd.exchange_kind() == "peer" else f"contig-sharded x{world}, NCCL all-to-all of 16-byte records"),
+                   "exchange": pbd.exchange_kind(),
                    "exchange_ms_per_step": float(t[1].item()) / args.steps,
                    "exchange_host_laps_ms": {k: round(v * 1e3, 3) for k, v in xtrace},
                    "exchange_bytes_per_gpu": 16 * (n + m)},
@@ -364,6 +367,7 @@ def run_sharded(args, world, rank, dev):
     }
     if rank == 0:
         print(json.dumps(line))
+    pbd.close_peer_exchanges()
     dist.destroy_process_group()
 
 

@@ -159,6 +159,36 @@ PBGPU_API int pbgpu_unpack_records(const int32_t *d_packed, int64_t n, int32_t *
 PBGPU_API int pbgpu_translate_rows(const uint32_t *d_local, int64_t n, const uint32_t *d_global_of_local,
                                    uint32_t *d_out, void *stream);
 
+/* The same exchange over NVLink peer memory, without NCCL on the data path (one process per GPU on one node; there is
+ * no reference counterpart -- the reference is single-process).  Every rank owns a receive arena
+ * (pbgpu_peer_alloc: cudaMalloc + CUDA IPC handle), maps the arenas of its peers (pbgpu_peer_open) and stores each
+ * row straight into the column arrays of the rank that owns its contig:
+ *   pbgpu_peer_histogram  d_hist int64[n_contigs+1], zeroed: rows per contig ADDED, [n_contigs] = n.  The caller
+ *                         all-gathers these rows into int64 [world][n_tables][n_contigs+1].
+ *   pbgpu_peer_plan       on the device, identically on every rank: contig -> owner (LPT bin packing), this rank's
+ *                         region in every destination's arena (regions in source-rank order, so received rows are
+ *                         ordered by global row id as after the stable NCCL exchange).  arena_base: HOST array, the
+ *                         address of every rank's arena in this process; cap_rows: HOST array, rows per column of
+ *                         table t (multiples of 64); arena layout: table t at byte 16*sum(cap_rows[<t]), columns
+ *                         contig | start | end | row, each cap_rows[t] x 4 bytes.  Outputs (device): d_owner
+ *                         int32[n_contigs], d_dst [n_tables][world] records of 4 pointers, d_result int64[3*n_tables+1]
+ *                         = received rows per table | global row id base per table | largest region any rank needs
+ *                         per table | overflow flag (some region exceeds cap_rows: nothing is scattered).
+ *   pbgpu_peer_scatter    one table: block destination counts, their scan, and the scatter itself.  d_row_id_base,
+ *                         d_dst (+ table * world records), d_flag (= d_result + 3*n_tables) are read on the device.
+ * The caller orders "all peers have written" before "I read" (a tiny all_reduce after the scatter).               */
+PBGPU_API int pbgpu_peer_alloc(size_t bytes, void **d_ptr, unsigned char *handle_out /* [64] */);
+PBGPU_API int pbgpu_peer_free(void *d_ptr);
+PBGPU_API int pbgpu_peer_open(const unsigned char *handle /* [64] */, void **d_ptr);
+PBGPU_API int pbgpu_peer_close(void *d_ptr);
+PBGPU_API int pbgpu_peer_histogram(const int32_t *d_contig, int64_t n, int32_t n_contigs, int64_t *d_hist, void *stream);
+PBGPU_API int pbgpu_peer_plan(const int64_t *d_gathered, int32_t world, int32_t rank, int32_t n_tables, int32_t n_contigs,
+                              const uint64_t *arena_base, const int64_t *cap_rows, int32_t *d_owner, void *d_dst,
+                              int64_t *d_result, void *stream);
+PBGPU_API int pbgpu_peer_scatter(const int32_t *d_contig, const int32_t *d_start, const int32_t *d_end, int64_t n,
+                                 const int32_t *d_owner, int32_t n_contigs, int32_t n_ranks, const int64_t *d_row_id_base,
+                                 const void *d_dst, const int64_t *d_flag, void *stream);
+
 /* ---- unary sweeps: they reuse the contig partition + start sort of the index build.
  * Reference: MergeProvider / ClusterProvider / ComplementProvider / SubtractProvider constructed at
  * /root/reference/src/operation.rs:352-380, 382-430, 432-461, 463-510; behaviour pinned by tests/_expected.py:174-181,

@@ -94,6 +94,13 @@ def lib() -> ctypes.CDLL:
     L.pbgpu_contig_histogram.argtypes = [vp, i64, i32, vp, vp]
     L.pbgpu_unpack_records.argtypes = [vp, i64, vp, vp, vp, vp, vp]
     L.pbgpu_translate_rows.argtypes = [vp, i64, vp, vp, vp]
+    L.pbgpu_peer_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp), vp]
+    L.pbgpu_peer_free.argtypes = [vp]
+    L.pbgpu_peer_open.argtypes = [vp, ctypes.POINTER(vp)]
+    L.pbgpu_peer_close.argtypes = [vp]
+    L.pbgpu_peer_histogram.argtypes = [vp, i64, i32, vp, vp]
+    L.pbgpu_peer_plan.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    L.pbgpu_peer_scatter.argtypes = [vp, vp, vp, i64, vp, i32, i32, vp, vp, vp, vp]
     L.pbgpu_intervals_rows.argtypes = [vp]
     L.pbgpu_intervals_rows.restype = i64
     L.pbgpu_intervals_columns.argtypes = [vp] + [ctypes.POINTER(vp)] * 5

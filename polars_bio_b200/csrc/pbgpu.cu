@@ -1044,3 +1044,4 @@ extern "C" int pbgpu_pack_by_owner(const int32_t *d_contig, const int32_t *d_sta
 }
 
 #include "unary.cuh"
+#include "peer.cuh"

@@ -9,6 +9,12 @@ its contigs with no further communication:
     -> NCCL all-to-all of the records over NVLink (counts first, then payload)
     -> unpack to columns -> local index build / count / emit -> pair row ids translated back to global ids.
 
+Default on one node: the exchange runs over NVLink peer memory instead (``PeerExchange``, csrc/peer.cuh): every rank
+maps every peer's receive arena (CUDA IPC) and one kernel per table stores each row straight into the columns of its
+owner -- pack + transfer + unpack fused, the owner table and region layout computed on the device, no host wait between
+the launches, NCCL only for a tiny all_gather of histograms and the closing all_reduce.  ``PBGPU_EXCHANGE=nccl`` (or a
+failed IPC mapping) selects the NCCL all-to-all path above; both deliver identical columns in identical order.
+
 ``torch.distributed`` is the plumbing (process group, all_to_all_single); packing, unpacking and id
 translation are kernels of libpbgpu.so.  The collectives run on the backend of the tensors' device, so
 the exchange logic is testable on CPU with gloo (tests/test_dist_gloo.py) given pre-packed records.
@@ -114,6 +120,9 @@ def shard_tables(tables, n_contigs: int, group=None, trace: Optional[list] = Non
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     T = len(tables)
+    ex = _peer_exchange_for(tables, n_contigs, group)
+    if ex is not None:
+        return ex.shard(tables, trace=trace)
     t0 = time.perf_counter()
     with torch.cuda.device(dev):
         sp = _stream_ptr(dev)
@@ -178,3 +187,312 @@ def translate(local_rows: torch.Tensor, global_of_local: torch.Tensor) -> torch.
         _native.check(_native.lib().pbgpu_translate_rows(local_rows.data_ptr(), local_rows.numel(), global_of_local.data_ptr(),
                                                          local_rows.data_ptr(), _stream_ptr(dev)))
     return local_rows
+
+
+# ------------------------------------------------------------------------------------------------
+# The exchange over NVLink peer memory (csrc/peer.cuh)
+# ------------------------------------------------------------------------------------------------
+PEER_MAX_RANKS = 16
+PEER_MAX_TABLES = 4
+
+
+class PeerUnavailable(RuntimeError):
+    """Peer arenas could not be set up on every rank (no CUDA IPC / no peer access): use the NCCL exchange."""
+
+
+class _DeviceSpan:
+    """Raw device memory as a ``__cuda_array_interface__`` object (zero-copy ``torch.as_tensor``)."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+
+
+def _i32_view(ptr: int, n: int, device) -> torch.Tensor:
+    if n == 0:
+        return torch.empty(0, dtype=torch.int32, device=device)
+    return torch.as_tensor(_DeviceSpan(ptr, n), device=device)
+
+
+def _round_cap(rows: int) -> int:
+    return max(64, (int(rows) + 63) // 64 * 64)
+
+
+def peer_layout(gathered, rank: int, cap_rows):
+    """Host restatement of ``peer_plan_kernel`` (tests and documentation; the product path plans on the device).
+    ``gathered``: int64 [world][T][n_contigs+1] (per-contig rows of every rank's slice, last entry = slice size).
+    Returns dict(owner int32[n_contigs], offset [T][world] = first row of ``rank``'s region at each destination,
+    rows [T][world] = rows ``rank`` sends there, received [T], base [T], need [T], overflow bool)."""
+    g = torch.as_tensor(gathered, dtype=torch.int64).cpu()
+    world, T, stride = g.shape
+    nc = stride - 1
+    owner = owner_table(g[:, :, :nc].sum(dim=(0, 1)), world)
+    cnt = torch.zeros((world, T, world), dtype=torch.int64)  # [source][table][destination]
+    for d in range(world):
+        sel = owner == d
+        if bool(sel.any()):
+            cnt[:, :, d] = g[:, :, :nc][:, :, sel].sum(dim=2)
+    before = cnt.cumsum(dim=0) - cnt  # rows of lower-ranked sources in the same (table, destination) region
+    region = cnt.sum(dim=0)  # [T][world]
+    need = region.max(dim=1).values
+    return {"owner": owner, "offset": before[rank], "rows": cnt[rank], "received": region[:, rank].clone(),
+            "base": g[:rank, :, nc].sum(dim=0), "need": need,
+            "overflow": bool((need > torch.as_tensor(list(cap_rows), dtype=torch.int64)).any())}
+
+
+class PeerExchange:
+    """Receive arenas of all ranks mapped into every rank + the plan / scatter kernels (include/pbgpu.h, peer section).
+
+    ``cap_rows[t]``: rows per column table ``t`` can receive on one rank; arenas grow (collectively) when a step needs
+    more.  Two arenas alternate between steps: a fast rank may already be writing step k+1 while a slow one still reads
+    step k.  The column tensors returned by ``shard`` are views into an arena and stay valid until the second-next
+    ``shard`` call (or ``close``).  ``arenas`` (tests): explicit base addresses [2][world] in this process -- several
+    simulated ranks on one device, no IPC."""
+
+    def __init__(self, n_contigs: int, cap_rows, device, group=None, arenas=None, world: Optional[int] = None,
+                 rank: Optional[int] = None):
+        import ctypes
+
+        from . import _native
+
+        self.L = _native.lib()
+        self.dev = torch.device(device)
+        self.group = group
+        self.nc = int(n_contigs)
+        self.T = len(cap_rows)
+        if arenas is not None:
+            self.world, self.rank, self.collective = int(world), int(rank), False
+        else:
+            self.collective = dist.is_initialized() and dist.get_world_size(group) > 1
+            self.world = dist.get_world_size(group) if self.collective else 1
+            self.rank = dist.get_rank(group) if self.collective else 0
+        if self.world > PEER_MAX_RANKS or not 1 <= self.T <= PEER_MAX_TABLES:
+            raise PeerUnavailable(f"peer exchange supports <= {PEER_MAX_RANKS} ranks and <= {PEER_MAX_TABLES} tables")
+        self.step = 0
+        self.own = [None, None]      # own arena per parity (owned allocations)
+        self.mapped = [[], []]       # peer mappings per parity (to close)
+        self.base = [None, None]     # ctypes uint64[world] per parity
+        self.external = arenas is not None
+        T, nc, w = self.T, self.nc, self.world
+        with torch.cuda.device(self.dev):
+            self.meta = torch.zeros((T, nc + 1), dtype=torch.int64, device=self.dev)
+            self.gathered = torch.zeros((w, T, nc + 1), dtype=torch.int64, device=self.dev)
+            self.owner = torch.zeros(max(nc, 1), dtype=torch.int32, device=self.dev)
+            self.dst = torch.zeros(T * w * 4, dtype=torch.int64, device=self.dev)
+            self.result = torch.zeros(3 * T + 1, dtype=torch.int64, device=self.dev)
+            self.result_h = torch.zeros(3 * T + 1, dtype=torch.int64).pin_memory()
+            self.token = torch.zeros(1, dtype=torch.int32, device=self.dev)
+            self.ready = torch.cuda.Event()
+        self._set_caps(cap_rows)
+        if self.external:
+            for par in (0, 1):
+                self.base[par] = (ctypes.c_uint64 * w)(*[int(a) for a in arenas[par]])
+        else:
+            self._allocate()
+
+    # -- arenas ------------------------------------------------------------------------------------
+    def _set_caps(self, cap_rows):
+        import ctypes
+
+        self.caps = [_round_cap(c) for c in cap_rows]
+        self.caps_c = (ctypes.c_int64 * self.T)(*self.caps)
+        self.tab_off = [16 * sum(self.caps[:t]) for t in range(self.T)]
+        self.arena_bytes = 16 * sum(self.caps)
+
+    def _allocate(self):
+        import ctypes
+
+        from . import _native
+
+        L, w = self.L, self.world
+        ok = True
+        err = ""
+        handles = torch.zeros(2 * 64, dtype=torch.uint8)
+        with torch.cuda.device(self.dev):
+            try:
+                for par in (0, 1):
+                    p = ctypes.c_void_p()
+                    h = (ctypes.c_ubyte * 64)()
+                    _native.check(L.pbgpu_peer_alloc(self.arena_bytes, ctypes.byref(p), h))
+                    self.own[par] = p.value
+                    handles[64 * par: 64 * par + 64] = torch.frombuffer(bytearray(h), dtype=torch.uint8)
+            except _native.PbgpuError as e:  # keep going: the agreement below must be reached by every rank
+                ok, err = False, str(e)
+            if self.collective:
+                mine = handles.to(self.dev)
+                everyone = torch.empty((w, 128), dtype=torch.uint8, device=self.dev)
+                dist.all_gather_into_tensor(everyone, mine, group=self.group)
+                everyone = everyone.cpu()
+                addrs = [[0] * w, [0] * w]
+                if ok:
+                    for par in (0, 1):
+                        for r in range(w):
+                            if r == self.rank:
+                                addrs[par][r] = self.own[par]
+                                continue
+                            hb = (ctypes.c_ubyte * 64)(*everyone[r, 64 * par: 64 * par + 64].tolist())
+                            p = ctypes.c_void_p()
+                            rc = L.pbgpu_peer_open(hb, ctypes.byref(p))
+                            if rc != 0:
+                                ok, err = False, L.pbgpu_last_error().decode("utf-8", "replace")
+                                break
+                            addrs[par][r] = p.value
+                            self.mapped[par].append(p.value)
+                        if not ok:
+                            break
+                flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.dev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+                if int(flag.item()) == 0:
+                    self._release()
+                    raise PeerUnavailable(err or "a peer could not map the arenas")
+            else:
+                if not ok:
+                    self._release()
+                    raise PeerUnavailable(err)
+                addrs = [[self.own[0]], [self.own[1]]]
+        for par in (0, 1):
+            self.base[par] = (ctypes.c_uint64 * w)(*addrs[par])
+
+    def _release(self):
+        """Unmap the peers' arenas and free our own.  Collective when the exchange is: nobody frees memory a peer may
+        still be writing to or has mapped."""
+        if self.external:
+            return
+        with torch.cuda.device(self.dev):
+            torch.cuda.synchronize(self.dev)
+            if self.collective:
+                dist.barrier(group=self.group)
+            for par in (0, 1):
+                for p in self.mapped[par]:
+                    self.L.pbgpu_peer_close(p)
+                self.mapped[par] = []
+            if self.collective:
+                dist.barrier(group=self.group)
+            for par in (0, 1):
+                if self.own[par]:
+                    self.L.pbgpu_peer_free(self.own[par])
+                self.own[par] = None
+
+    def close(self):
+        self._release()
+
+    def _grow(self, need):
+        self._release()
+        self._set_caps([max(c, int(n * 1.25) + 1024) for c, n in zip(self.caps, need)])
+        self._allocate()
+
+    # -- one exchange step -------------------------------------------------------------------------
+    def enqueue(self, tables, gathered: Optional[torch.Tensor] = None):
+        """Histograms, (all_gather,) plan and scatters of one step, without waiting for anything.  ``gathered``
+        (tests): pre-computed all-gathered histograms instead of the collective."""
+        from . import _native
+        from .engine import _stream_ptr
+
+        L, T, nc, w = self.L, self.T, self.nc, self.world
+        assert len(tables) == T
+        par = self.step & 1
+        self.step += 1
+        with torch.cuda.device(self.dev):
+            sp = _stream_ptr(self.dev)
+            if gathered is None:
+                self.meta.zero_()
+                for t, (c, _, _) in enumerate(tables):
+                    _native.check(L.pbgpu_peer_histogram(c.data_ptr(), c.numel(), nc, self.meta[t].data_ptr(), sp))
+                if self.collective:
+                    dist.all_gather_into_tensor(self.gathered, self.meta, group=self.group)
+                    gathered = self.gathered
+                else:
+                    gathered = self.meta
+            _native.check(L.pbgpu_peer_plan(gathered.data_ptr(), w, self.rank, T, nc, self.base[par], self.caps_c, self.owner.data_ptr(),
+                                            self.dst.data_ptr(), self.result.data_ptr(), sp))
+            self.result_h.copy_(self.result, non_blocking=True)
+            self.ready.record()
+            r0 = self.result.data_ptr()
+            for t, (c, s, e) in enumerate(tables):
+                _native.check(L.pbgpu_peer_scatter(c.data_ptr(), s.data_ptr(), e.data_ptr(), c.numel(), self.owner.data_ptr(), nc, w,
+                                                   r0 + 8 * (T + t), self.dst.data_ptr() + 32 * w * t, r0 + 8 * 3 * T, sp))
+            if self.collective:  # every rank's stores precede its contribution: after this, all regions here are complete
+                dist.all_reduce(self.token, group=self.group)
+        return par
+
+    def collect(self, par: int):
+        """Wait for the plan's host copy (it overlaps the scatter) and return the received columns of every table, or
+        None when an arena was too small (nothing was scattered)."""
+        self.ready.synchronize()
+        T = self.T
+        res = self.result_h.tolist()
+        if res[3 * T]:
+            return None, res[2 * T: 3 * T]
+        base = int(self.base[par][self.rank])
+        out = []
+        for t in range(T):
+            r, cap = int(res[t]), self.caps[t]
+            p = base + self.tab_off[t]
+            out.append(tuple(_i32_view(p + 4 * cap * k, r, self.dev) for k in range(4)))
+        return out, res[2 * T: 3 * T]
+
+    def shard(self, tables, trace: Optional[list] = None):
+        import time
+
+        t0 = time.perf_counter()
+        par = self.enqueue(tables)
+        if trace is not None: trace.append(("peer enqueue (hist+gather+plan+scatter+barrier)", time.perf_counter() - t0)); t0 = time.perf_counter()
+        out, need = self.collect(par)
+        if out is None:  # the same numbers on every rank, so every rank takes this branch together
+            self._grow(need)
+            par = self.enqueue(tables)
+            out, need = self.collect(par)
+            if out is None:
+                raise RuntimeError("peer exchange: arena still too small after growing")
+        if trace is not None:
+            torch.cuda.synchronize(self.dev)
+            trace.append(("peer wait", time.perf_counter() - t0))
+        return out, self.owner[: self.nc]
+
+
+_peer_cache: dict = {}
+
+
+def exchange_kind(group=None) -> str:
+    """'peer' or 'nccl': what ``shard_tables`` uses for this group right now."""
+    for (g, _, _), ex in _peer_cache.items():
+        if g == id(group) and ex is not None:
+            return "peer"
+    return "nccl"
+
+
+def _peer_exchange_for(tables, n_contigs: int, group=None):
+    """The cached PeerExchange of (group, n_contigs, #tables), created collectively on first use; None = NCCL path
+    (PBGPU_EXCHANGE=nccl, CPU tensors, too many ranks/tables, or the arenas could not be mapped on some rank)."""
+    import os
+    import sys
+
+    dev = tables[0][0].device
+    T = len(tables)
+    if dev.type != "cuda" or os.environ.get("PBGPU_EXCHANGE", "peer") == "nccl":
+        return None
+    key = (id(group), int(n_contigs), T)
+    if key in _peer_cache:
+        return _peer_cache[key]
+    collective = dist.is_initialized() and dist.get_world_size(group) > 1
+    world = dist.get_world_size(group) if collective else 1
+    ex = None
+    if world <= PEER_MAX_RANKS and T <= PEER_MAX_TABLES and all(c.numel() < (1 << 32) for c, _, _ in tables):
+        sizes = torch.tensor([c.numel() for c, _, _ in tables], dtype=torch.int64, device=dev)
+        if collective:
+            dist.all_reduce(sizes, group=group)
+        caps = [int(x) // world * 5 // 4 + 4096 for x in sizes.tolist()]
+        try:
+            ex = PeerExchange(n_contigs, caps, dev, group)
+        except PeerUnavailable as e:
+            if not collective or dist.get_rank(group) == 0:
+                sys.stderr.write(f"polars_bio_b200.dist: peer exchange unavailable ({e}); using the NCCL all-to-all\n")
+    _peer_cache[key] = ex
+    return ex
+
+
+def close_peer_exchanges():
+    """Free the cached arenas (collective).  Call before ``destroy_process_group``."""
+    for ex in _peer_cache.values():
+        if ex is not None:
+            ex.close()
+    _peer_cache.clear()

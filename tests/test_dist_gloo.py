@@ -90,3 +90,27 @@ def test_sharded_join_two_gpus_matches_oracle():
                         "--master-port", str(_free_port()), os.path.join(root, "tests", "tools", "dist_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "DIST_CHECK_OK" in r.stdout
+
+
+def test_peer_layout_matches_bruteforce():
+    """Host restatement of peer_plan_kernel (the GPU tests compare the kernel with it): regions in source order."""
+    import numpy as np
+
+    rng = np.random.default_rng(3)
+    for world, T, nc in ((1, 1, 3), (2, 2, 11), (4, 2, 25), (8, 3, 5)):
+        g = rng.integers(0, 1000, (world, T, nc + 1)).astype(np.int64)
+        g[:, :, nc] = g[:, :, :nc].sum(axis=2) + rng.integers(0, 50, (world, T))  # slice size incl. null-keyed rows
+        owner = pbd.owner_table(torch.from_numpy(g[:, :, :nc].sum(axis=(0, 1))), world).numpy()
+        for rank in range(world):
+            lay = pbd.peer_layout(g, rank, [10 ** 9] * T)
+            assert np.array_equal(lay["owner"].numpy(), owner)
+            for t in range(T):
+                assert int(lay["base"][t]) == int(g[:rank, t, nc].sum())
+                for d in range(world):
+                    cols = owner == d
+                    assert int(lay["rows"][t, d]) == int(g[rank, t, :nc][cols].sum())
+                    assert int(lay["offset"][t, d]) == int(g[:rank, t, :nc][:, cols].sum())
+                assert int(lay["received"][t]) == int(g[:, t, :nc][:, owner == rank].sum())
+                assert int(lay["need"][t]) == max(int(g[:, t, :nc][:, owner == d].sum()) for d in range(world))
+            assert not lay["overflow"]
+        assert pbd.peer_layout(g, 0, [1] * T)["overflow"]

@@ -38,11 +38,33 @@ def main():
     q1 = pbd.shard_table(*lp, n_contigs, owner, pbase)
     x1 = pbd.shard_table(*lb, n_contigs, owner, bbase)
     # path 2: the fused exchange (one all_reduce, one count all-to-all) must deliver the same rows
+    os.environ["PBGPU_EXCHANGE"] = "nccl"
     (q2, x2), owner2 = pbd.shard_tables([tuple(lp), tuple(lb)], n_contigs)
-    assert torch.equal(owner, owner2)
+    assert torch.equal(owner, owner2.cpu())
     for u, v in ((q1, q2), (x1, x2)):
         for col_u, col_v in zip(u, v):
             assert torch.equal(col_u, col_v)
+    # path 3: the exchange over NVLink peer memory (CUDA IPC arenas, plan + scatter kernels): same rows, same order,
+    # over several steps (both arena parities) and after the arenas had to grow
+    os.environ["PBGPU_EXCHANGE"] = "peer"
+    for it in range(4):
+        (q3, x3), owner3 = pbd.shard_tables([tuple(lp), tuple(lb)], n_contigs)
+        assert torch.equal(owner, owner3.cpu())
+        for u, v in ((q2, q3), (x2, x3)):
+            for col_u, col_v in zip(u, v):
+                assert torch.equal(col_u, col_v), ("peer exchange differs from the NCCL exchange", it)
+    kind = pbd.exchange_kind()
+    if kind == "peer":  # a second pair of tables, 3x larger on this group: forces a collective arena growth
+        big_p = [torch.cat([x, x, x]) for x in lp]
+        big_b = [torch.cat([x, x, x]) for x in lb]
+        os.environ["PBGPU_EXCHANGE"] = "nccl"
+        (qn, xn), _ = pbd.shard_tables([tuple(big_p), tuple(big_b)], n_contigs)
+        os.environ["PBGPU_EXCHANGE"] = "peer"
+        (qp, xp), _ = pbd.shard_tables([tuple(big_p), tuple(big_b)], n_contigs)
+        for u, v in ((qn, qp), (xn, xp)):
+            for col_u, col_v in zip(u, v):
+                assert torch.equal(col_u, col_v), "peer exchange differs after growing"
+        (q2, x2), _ = pbd.shard_tables([tuple(lp), tuple(lb)], n_contigs)
     qc, qs, qe, qrow = q2
     xc, xs, xe, xrow = x2
     ix = engine.DeviceIndex(xc, xs, xe, n_contigs)
@@ -59,8 +81,9 @@ def main():
         oa, ob = oracle.Index(bc, bs, be, n_contigs).overlap_pairs(pc, ps, pe, True)
         want = np.sort(oa.astype(np.int64) * M + ob.astype(np.int64))
         assert len(got) == len(want) and np.array_equal(got, want), (len(got), len(want))
-        print(f"DIST_CHECK_OK world={world} pairs={len(got)}")
+        print(f"DIST_CHECK_OK world={world} pairs={len(got)} exchange={kind}")
     dist.barrier()
+    pbd.close_peer_exchanges()
     dist.destroy_process_group()
 
 
