@@ -160,35 +160,78 @@ PBGPU_API int pbgpu_translate_rows(const uint32_t *d_local, int64_t n, const uin
                                    uint32_t *d_out, void *stream);
 
 /* The same exchange over NVLink peer memory, without NCCL on the data path (one process per GPU on one node; there is
- * no reference counterpart -- the reference is single-process).  Every rank owns a receive arena
- * (pbgpu_peer_alloc: cudaMalloc + CUDA IPC handle), maps the arenas of its peers (pbgpu_peer_open) and stores each
- * row straight into the column arrays of the rank that owns its contig:
- *   pbgpu_peer_histogram  d_hist int64[n_contigs+1], zeroed: rows per contig ADDED, [n_contigs] = n.  The caller
- *                         all-gathers these rows into int64 [world][n_tables][n_contigs+1].
- *   pbgpu_peer_plan       on the device, identically on every rank: contig -> owner (LPT bin packing), this rank's
- *                         region in every destination's arena (regions in source-rank order, so received rows are
- *                         ordered by global row id as after the stable NCCL exchange).  arena_base: HOST array, the
- *                         address of every rank's arena in this process; cap_rows: HOST array, rows per column of
- *                         table t (multiples of 64); arena layout: table t at byte 16*sum(cap_rows[<t]), columns
- *                         contig | start | end | row, each cap_rows[t] x 4 bytes.  Outputs (device): d_owner
- *                         int32[n_contigs], d_dst [n_tables][world] records of 4 pointers, d_result int64[3*n_tables+1]
- *                         = received rows per table | global row id base per table | largest region any rank needs
- *                         per table | overflow flag (some region exceeds cap_rows: nothing is scattered).
- *   pbgpu_peer_scatter    one table: block destination counts, their scan, and the scatter itself.  d_row_id_base,
- *                         d_dst (+ table * world records), d_flag (= d_result + 3*n_tables) are read on the device.
- * The caller orders "all peers have written" before "I read" (a tiny all_reduce after the scatter).               */
+ * no reference counterpart -- the reference is single-process).  Every rank owns two receive ARENAS
+ * (they alternate between steps) and one CONTROL block (pbgpu_peer_alloc: cudaMalloc + CUDA IPC handle), maps those of
+ * its peers (pbgpu_peer_open) and stores each row straight into the column arrays of the rank that owns its contig.
+ *
+ * Arena layout: table t at byte 16*sum(cap_rows[<t]); columns contig | start | end | row, each cap_rows[t] x 4 bytes
+ * (cap_rows: multiples of 64).  Control block (pbgpu_peer_ctl_bytes, zeroed before the handles are exchanged): flag
+ * words written remotely with st.release.sys and polled locally with a bounded spin ($PBGPU_PEER_TIMEOUT_MS, default
+ * 20 s: a dead peer becomes status 2 in d_result[3*n_tables] / *d_status, never a hung GPU) and one histogram slot per
+ * source rank.  `step` counts exchange steps from 1 and must be the same on every rank.
+ *
+ * One step = pbgpu_peer_begin + one pbgpu_peer_table per table:
+ *   histograms    rows per contig of this rank's slice of every table (+ the slice sizes), one launch; the block that
+ *                 finishes last publishes them into every control block and raises this rank's flag A there
+ *   plan          waits for flag A of every source; then, on the device and identically on every rank: contig -> owner
+ *                 (LPT bin packing), this rank's region in every destination's arena (regions in source-rank order, so
+ *                 received rows are ordered by global row id as after the stable NCCL exchange).  Outputs: d_owner
+ *                 int32[n_contigs], d_dst [n_tables][world] records of 4 pointers, d_result int64[3*n_tables+1] =
+ *                 received rows per table | global row id base per table | largest region any rank needs per table |
+ *                 flag (1 = some region exceeds cap_rows: nothing is scattered; 2 = a peer did not publish in time).
+ *                 h_result (page-locked host int64[3*n_tables+2], or NULL): the kernel stores the same words there and
+ *                 then the step number into the last one, so the host spins on that word instead of copying.
+ *   scatter       one table: block destination counts, their scan, and the scatter itself
+ *   signal, wait  flag B[table] raised at every destination after the scatter (same stream); wait until flag B[table]
+ *                 of every source shows `step`: the table is complete on this rank
+ * pbgpu_peer_table may run on a stream of its own ordered after pbgpu_peer_begin (work on one table overlaps the
+ * transfer of the next).  ctl_base == NULL: no control blocks -- begin stops after the histograms (all-gather d_hist into
+ * int64 [world][n_tables][n_contigs+1], call pbgpu_peer_plan with it), table only scatters, and the caller orders "all
+ * peers have written" before "I read" with a tiny all_reduce.                                                       */
 PBGPU_API int pbgpu_peer_alloc(size_t bytes, void **d_ptr, unsigned char *handle_out /* [64] */);
 PBGPU_API int pbgpu_peer_free(void *d_ptr);
 PBGPU_API int pbgpu_peer_open(const unsigned char *handle /* [64] */, void **d_ptr);
 PBGPU_API int pbgpu_peer_close(void *d_ptr);
-PBGPU_API int pbgpu_peer_histogram(const int32_t *d_contig, int64_t n, int32_t n_contigs, int64_t *d_hist, void *stream);
-PBGPU_API int pbgpu_peer_plan(const int64_t *d_gathered, int32_t world, int32_t rank, int32_t n_tables, int32_t n_contigs,
-                              const uint64_t *arena_base, const int64_t *cap_rows, int32_t *d_owner, void *d_dst,
-                              int64_t *d_result, void *stream);
+PBGPU_API size_t pbgpu_peer_ctl_bytes(int32_t world, int32_t n_tables, int32_t n_contigs);
+/* d_own_ctl != NULL: wait for flag A, histograms from the control block (d_gathered ignored); NULL: plain d_gathered.
+ * arena_base / cap_rows: HOST arrays [world] / [n_tables].                                                          */
+PBGPU_API int pbgpu_peer_plan(const int64_t *d_gathered, const void *d_own_ctl, uint64_t step, int32_t world, int32_t rank,
+                              int32_t n_tables, int32_t n_contigs, const uint64_t *arena_base, const int64_t *cap_rows,
+                              int32_t *d_owner, void *d_dst, int64_t *d_result, int64_t *h_result, void *stream);
+/* d_row_id_base, d_dst (+ table * world records) and d_flag (= d_result + 3*n_tables) are read on the device.      */
 PBGPU_API int pbgpu_peer_scatter(const int32_t *d_contig, const int32_t *d_start, const int32_t *d_end, int64_t n,
                                  const int32_t *d_owner, int32_t n_contigs, int32_t n_ranks, const int64_t *d_row_id_base,
                                  const void *d_dst, const int64_t *d_flag, void *stream);
-
+#define PBGPU_PEER_HIST 1     /* pbgpu_peer_begin: histograms (+ publication)                */
+#define PBGPU_PEER_PLAN 2     /* pbgpu_peer_begin: plan                                      */
+#define PBGPU_PEER_SCATTER 4  /* pbgpu_peer_table: scatter                                   */
+#define PBGPU_PEER_SIGNAL 8   /* pbgpu_peer_table: raise this rank's flag at every peer      */
+#define PBGPU_PEER_WAIT 16    /* pbgpu_peer_table: wait for every peer's flag                */
+typedef struct {
+  int32_t world, rank, n_tables, n_contigs;
+  int32_t phases;                /* 0 = everything the call does; else a PBGPU_PEER_* mask (tests drive the  */
+                                 /* phases of several simulated ranks one by one on a single stream)        */
+  int32_t reserved;
+  uint64_t step;                 /* counts from 1, the same on every rank                                   */
+  const int32_t *contig[4];      /* this rank's slice of every table (device)                               */
+  const int32_t *start[4];
+  const int32_t *end[4];
+  int64_t rows[4];
+  const uint64_t *arena_base;    /* HOST [world]: every rank's arena of this step, addresses in this process */
+  const uint64_t *ctl_base;      /* HOST [world]: control blocks, or NULL                                    */
+  const int64_t *cap_rows;       /* HOST [n_tables]                                                          */
+  int64_t *d_hist;               /* device int64 [n_tables*(n_contigs+1) + 1]                                */
+  int32_t *d_owner;              /* device int32 [n_contigs]                                                 */
+  void *d_dst;                   /* device, 32 bytes x n_tables x world                                      */
+  int64_t *d_result;             /* device int64 [3*n_tables+1]                                              */
+  int64_t *h_result;             /* page-locked host int64 [3*n_tables+2], or NULL                           */
+  int64_t *d_status;             /* device int64 [1]: set to 2 by a wait that timed out                      */
+  void *d_scratch;               /* device scratch of pbgpu_peer_scratch_bytes(step) bytes kept by the caller, */
+  uint64_t scratch_bytes;        /* or NULL / too small: the calls allocate stream-ordered scratch themselves */
+} pbgpu_peer_step;
+PBGPU_API size_t pbgpu_peer_scratch_bytes(const pbgpu_peer_step *step);
+PBGPU_API int pbgpu_peer_begin(const pbgpu_peer_step *step, void *stream);
+PBGPU_API int pbgpu_peer_table(const pbgpu_peer_step *step, int32_t table, void *stream);
 /* ---- unary sweeps: they reuse the contig partition + start sort of the index build.
  * Reference: MergeProvider / ClusterProvider / ComplementProvider / SubtractProvider constructed at
  * /root/reference/src/operation.rs:352-380, 382-430, 432-461, 463-510; behaviour pinned by tests/_expected.py:174-181,

@@ -47,6 +47,21 @@ class PbRangeOptions(ctypes.Structure):
     ]
 
 
+class PbPeerStep(ctypes.Structure):
+    """Mirror of ``pbgpu_peer_step`` (include/pbgpu.h)."""
+
+    _fields_ = [
+        ("world", ctypes.c_int32), ("rank", ctypes.c_int32), ("n_tables", ctypes.c_int32), ("n_contigs", ctypes.c_int32),
+        ("phases", ctypes.c_int32), ("reserved", ctypes.c_int32), ("step", ctypes.c_uint64),
+        ("contig", ctypes.c_void_p * 4), ("start", ctypes.c_void_p * 4), ("end", ctypes.c_void_p * 4),
+        ("rows", ctypes.c_int64 * 4),
+        ("arena_base", ctypes.c_void_p), ("ctl_base", ctypes.c_void_p), ("cap_rows", ctypes.c_void_p),
+        ("d_hist", ctypes.c_void_p), ("d_owner", ctypes.c_void_p), ("d_dst", ctypes.c_void_p),
+        ("d_result", ctypes.c_void_p), ("h_result", ctypes.c_void_p), ("d_status", ctypes.c_void_p),
+        ("d_scratch", ctypes.c_void_p), ("scratch_bytes", ctypes.c_uint64),
+    ]
+
+
 class StageTimes(ctypes.Structure):
     _fields_ = [("partition_sort_ns", ctypes.c_uint64), ("count_ns", ctypes.c_uint64),
                 ("scan_ns", ctypes.c_uint64), ("emit_ns", ctypes.c_uint64), ("count_overlaps_ns", ctypes.c_uint64)]
@@ -98,8 +113,13 @@ def lib() -> ctypes.CDLL:
     L.pbgpu_peer_free.argtypes = [vp]
     L.pbgpu_peer_open.argtypes = [vp, ctypes.POINTER(vp)]
     L.pbgpu_peer_close.argtypes = [vp]
-    L.pbgpu_peer_histogram.argtypes = [vp, i64, i32, vp, vp]
-    L.pbgpu_peer_plan.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    L.pbgpu_peer_plan.argtypes = [vp, vp, u64, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.pbgpu_peer_begin.argtypes = [ctypes.POINTER(PbPeerStep), vp]
+    L.pbgpu_peer_scratch_bytes.argtypes = [ctypes.POINTER(PbPeerStep)]
+    L.pbgpu_peer_scratch_bytes.restype = ctypes.c_size_t
+    L.pbgpu_peer_table.argtypes = [ctypes.POINTER(PbPeerStep), i32, vp]
+    L.pbgpu_peer_ctl_bytes.argtypes = [i32, i32, i32]
+    L.pbgpu_peer_ctl_bytes.restype = ctypes.c_size_t
     L.pbgpu_peer_scatter.argtypes = [vp, vp, vp, i64, vp, i32, i32, vp, vp, vp, vp]
     L.pbgpu_intervals_rows.argtypes = [vp]
     L.pbgpu_intervals_rows.restype = i64

@@ -7,7 +7,7 @@
 // stores each row straight into the column arrays of its owner: pack + transfer + unpack fused, no staging copy of
 // the records, no collective on the data path.
 //
-//   peer_hist_kernel     per-contig row counts of this rank's slice (+ the slice size)         -> all_gather (tiny)
+//   peer_hist_publish_kernel  per-contig row counts of this rank's slices (+ the slice sizes), all tables in one launch
 //   peer_plan_kernel     ON THE DEVICE, identically on every rank: contig -> owner by LPT bin packing (same table as
 //                        dist.owner_table), rows(source, table, destination), this source's region in every
 //                        destination's arena (regions are laid out in source order, so the received rows are ordered
@@ -19,7 +19,19 @@
 //                        4-byte elements of one column (NVLink packets carry whole sectors), not 32 scattered rows.
 //
 // The host never waits between these launches: the only host read (received rows per table, needed to size the join)
-// overlaps the scatter.  One tiny all_reduce afterwards orders "all peers have written" before "I read".
+// overlaps the scatter.
+//
+// Synchronisation is also done through peer memory: every rank owns a small CONTROL block that all peers map --
+// flag words written remotely with st.release.sys and polled locally with ld.acquire.sys (bounded spin: a dead peer
+// turns into an error code after the timeout, never into a hung GPU) plus a slot per source for the histograms:
+//   peer_hist_publish_kernel  the block that finishes last stores this rank's histograms into every peer's control
+//                             block, then raises flag A[rank] there
+//   peer_plan_kernel          first waits until flag A of every source shows this step
+//   peer_signal_wait_kernel   (after the scatter of table t, same stream) raises flag B[t][rank] at every destination,
+//                             then waits until flag B[t] of every source shows this step: table t is complete here
+// so a step needs no NCCL call at all, and each table can run its scatter / signal / wait on its own stream (the index
+// build over the small table overlaps the scatter of the big one).  Without control blocks (PBGPU_PEER_SYNC=nccl) the
+// caller all-gathers the histograms and closes the step with a tiny all_reduce.
 #pragma once
 #include "common.cuh"
 
@@ -45,10 +57,56 @@ struct PeerPlanArgs {
   long long tab_off[kPeerMaxTables];        // byte offset of table t inside an arena: columns contig|start|end|row
 };
 
-// rows per contig (null keys ignored) of one slice, added onto hist[0..n_contigs); hist[n_contigs] = slice size
-__global__ void __launch_bounds__(256) peer_hist_kernel(const int32_t *__restrict__ c, int64_t n, int32_t n_contigs,
-                                                        unsigned long long *__restrict__ hist) {
+// control block: flag A [kPeerMaxRanks] u64 | flag B [kPeerMaxTables][kPeerMaxRanks] u64 | pad to 1024 B | histograms
+// int64 [world][T][n_contigs+1] (slot s written by source s)
+constexpr size_t kPeerCtlFlagB = sizeof(unsigned long long) * kPeerMaxRanks;
+constexpr size_t kPeerCtlHist = 1024;
+static_assert(kPeerCtlFlagB + sizeof(unsigned long long) * kPeerMaxTables * kPeerMaxRanks <= kPeerCtlHist, "control block header");
+
+struct PeerCtlArgs {
+  unsigned long long ctl[kPeerMaxRanks];  // base address of every rank's control block in THIS process
+};
+
+__device__ __forceinline__ unsigned long long peer_ld_flag(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void peer_st_flag(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long peer_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// wait until *p >= want; false after timeout_ns
+__device__ __forceinline__ bool peer_spin(const unsigned long long *p, unsigned long long want, unsigned long long timeout_ns) {
+  if (peer_ld_flag(p) >= want) return true;
+  const unsigned long long t0 = peer_now_ns();
+  while (peer_ld_flag(p) < want) {
+    if (peer_now_ns() - t0 > timeout_ns) return false;
+    __nanosleep(64);
+  }
+  return true;
+}
+
+struct PeerTablesArgs {
+  const int32_t *c[kPeerMaxTables];
+  long long n[kPeerMaxTables];
+};
+
+// The histograms of all tables in one launch (blockIdx.y = table) into hist[T][n_contigs+1] (+ one counter word behind
+// it, zeroed with the rest); the block that finishes last publishes them (publish != 0): slot `rank` of every control
+// block, then flag A[rank] = step there.
+__global__ void __launch_bounds__(256) peer_hist_publish_kernel(PeerTablesArgs tb, int T, int32_t n_contigs, unsigned long long *__restrict__ hist_all,
+                                                                PeerCtlArgs a, int world, int rank, unsigned long long step, int publish) {
   extern __shared__ unsigned int bins[];
+  __shared__ bool last;
+  const int t = blockIdx.y;
+  const int32_t *__restrict__ c = tb.c[t];
+  const int64_t n = tb.n[t];
+  unsigned long long *hist = hist_all + (size_t)t * (n_contigs + 1);
   const bool use_smem = n_contigs <= 4096;
   if (blockIdx.x == 0 && threadIdx.x == 0) hist[n_contigs] = (unsigned long long)n;
   if (use_smem) { for (int i = threadIdx.x; i < n_contigs; i += blockDim.x) bins[i] = 0; __syncthreads(); }
@@ -61,18 +119,76 @@ __global__ void __launch_bounds__(256) peer_hist_kernel(const int32_t *__restric
     __syncthreads();
     for (int i = threadIdx.x; i < n_contigs; i += blockDim.x) if (bins[i]) atomicAdd(hist + i, (unsigned long long)bins[i]);
   }
+  if (!publish) return;
+  __threadfence();
+  __syncthreads();
+  const int len = T * (n_contigs + 1);
+  if (threadIdx.x == 0) last = atomicAdd((unsigned int *)(hist_all + len), 1u) == gridDim.x * gridDim.y - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  for (int d = 0; d < world; ++d) {
+    long long *slot = (long long *)((char *)a.ctl[d] + kPeerCtlHist) + (size_t)rank * len;
+    for (int i = threadIdx.x; i < len; i += blockDim.x) slot[i] = (long long)__ldcg(hist_all + i);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < world) {
+    __threadfence_system();
+    peer_st_flag((unsigned long long *)a.ctl[threadIdx.x] + rank, step);
+  }
+}
+
+// mode & 1: flag B[table][rank] = step at every destination (runs after the scatter of `table` on the same stream: the
+// kernel boundary orders the scatter's remote stores before these); mode & 2: wait until every source's flag B[table]
+// shows `step` here -- the table is complete on this rank; a timeout is reported through *status (= 2)
+__global__ void __launch_bounds__(32) peer_signal_wait_kernel(PeerCtlArgs a, int world, int rank, int table, unsigned long long step,
+                                                              unsigned long long timeout_ns, long long *__restrict__ status, int mode) {
+  if (threadIdx.x < world) {
+    const size_t off = (size_t)table * kPeerMaxRanks;
+    if (mode & 1) {
+      __threadfence_system();
+      peer_st_flag((unsigned long long *)((char *)a.ctl[threadIdx.x] + kPeerCtlFlagB) + off + rank, step);
+    }
+    if (mode & 2) {
+      const unsigned long long *f = (const unsigned long long *)((const char *)a.ctl[rank] + kPeerCtlFlagB) + off + threadIdx.x;
+      if (!peer_spin(f, step, timeout_ns)) *status = 2;
+    }
+  }
 }
 
 // g: [world][T][n_contigs+1] all-gathered histograms.  result: int64 [3T+1] = received rows[T] | global row id base[T] |
 // largest region any destination needs[T] | overflow flag.
-__global__ void __launch_bounds__(1024) peer_plan_kernel(const long long *__restrict__ g, int world, int rank, int T, int nc,
+// wait_flags != NULL: g is the histogram area of this rank's control block; wait until flag A of every source shows
+// `step` before reading it (timeout -> result[3T] = 2 and nothing else is written).
+__global__ void __launch_bounds__(1024) peer_plan_kernel(const long long *g /* peers write it: coherent loads only */, int world, int rank, int T, int nc,
                                                          PeerPlanArgs a, unsigned long long *__restrict__ w, int32_t *__restrict__ order,
-                                                         int32_t *__restrict__ owner, PeerDst *__restrict__ dst, long long *__restrict__ result) {
+                                                         int32_t *__restrict__ owner, PeerDst *__restrict__ dst, long long *__restrict__ result,
+                                                         const unsigned long long *__restrict__ wait_flags, unsigned long long step,
+                                                         unsigned long long timeout_ns, long long *host_result) {
   __shared__ unsigned long long cnt[kPeerMaxRanks * kPeerMaxTables * kPeerMaxRanks];
   __shared__ unsigned long long load[kPeerMaxRanks];
   __shared__ unsigned long long need[kPeerMaxTables];
   __shared__ int overflow;
+  __shared__ int timed_out;
   const int tid = threadIdx.x, stride = nc + 1;
+  if (wait_flags) {
+    if (tid == 0) timed_out = 0;
+    __syncthreads();
+    if (tid < world && !peer_spin(wait_flags + tid, step, timeout_ns)) timed_out = 1;
+    __syncthreads();
+    if (timed_out) {
+      if (tid == 0) {
+        result[3 * T] = 2;
+        if (host_result) {
+          host_result[3 * T] = 2;
+          __threadfence_system();
+          *(volatile long long *)(host_result + 3 * T + 1) = (long long)step;
+        }
+      }
+      return;
+    }
+  }
   for (int i = tid; i < world * T * world; i += blockDim.x) cnt[i] = 0;
   if (tid < kPeerMaxTables) need[tid] = 0;
   if (tid == 0) overflow = 0;
@@ -135,6 +251,16 @@ __global__ void __launch_bounds__(1024) peer_plan_kernel(const long long *__rest
   __syncthreads();
   if (tid < T) result[2 * T + tid] = (long long)need[tid];
   if (tid == 0) result[3 * T] = overflow;
+  // the same numbers straight into page-locked host memory, sequence word last: the host spins on it instead of
+  // paying a copy-engine round trip (it needs the received rows to size the join)
+  if (host_result) {
+    __syncthreads();
+    if (tid == 0) {
+      for (int i = 0; i <= 3 * T; ++i) host_result[i] = result[i];
+      __threadfence_system();
+      *(volatile long long *)(host_result + 3 * T + 1) = (long long)step;
+    }
+  }
 }
 
 __device__ __forceinline__ int peer_dest(int32_t cc, const int32_t *__restrict__ owner, int32_t n_contigs, int32_t n_ranks) {
@@ -196,6 +322,9 @@ __global__ void __launch_bounds__(1024) peer_block_scan_kernel(unsigned int *__r
   }
 }
 
+// One 1024-row tile per loop turn; the grid is either one block per tile or a few blocks per SM striding over the tiles
+// (the kernel is bound by the NVLink stores, not by occupancy: a small resident grid leaves room for the kernels of the
+// stream that overlaps it).  Tile t of the table always lands at bc[d][t], whichever block handles it.
 __global__ void __launch_bounds__(kPeerThreads) peer_scatter_kernel(const int32_t *__restrict__ c, const int32_t *__restrict__ s,
                                                                     const int32_t *__restrict__ e, int64_t n, const int32_t *__restrict__ owner,
                                                                     int32_t n_contigs, int32_t n_ranks, const long long *__restrict__ row_id_base,
@@ -210,63 +339,64 @@ __global__ void __launch_bounds__(kPeerThreads) peer_scatter_kernel(const int32_
   if (*flag) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt = lanemask_lt();
-  for (int i = threadIdx.x; i < kPeerItems * kPeerWarps * kPeerMaxRanks; i += kPeerThreads) (&wcnt[0][0])[i] = 0;
-  if (threadIdx.x < n_ranks) {
-    dst[threadIdx.x] = dst_table[threadIdx.x];
-    gbase[threadIdx.x] = bc[(int64_t)threadIdx.x * nblk + blockIdx.x];
-  }
-  __syncthreads();
-  const int64_t base = (int64_t)blockIdx.x * kPeerTile;
+  if (threadIdx.x < n_ranks) dst[threadIdx.x] = dst_table[threadIdx.x];
   const uint32_t id0 = (uint32_t)*row_id_base;
-  int32_t rc[kPeerItems], rs[kPeerItems], re[kPeerItems];
-  int rd[kPeerItems];
-  unsigned int slot[kPeerItems];
+  for (int64_t tile = blockIdx.x; tile < nblk; tile += gridDim.x) {
+    for (int i = threadIdx.x; i < kPeerItems * kPeerWarps * kPeerMaxRanks; i += kPeerThreads) (&wcnt[0][0])[i] = 0;
+    if (threadIdx.x < n_ranks) gbase[threadIdx.x] = bc[(int64_t)threadIdx.x * nblk + tile];
+    __syncthreads();
+    const int64_t base = tile * kPeerTile;
+    int32_t rc[kPeerItems], rs[kPeerItems], re[kPeerItems];
+    int rd[kPeerItems];
+    unsigned int slot[kPeerItems];
 #pragma unroll
-  for (int j = 0; j < kPeerItems; ++j) {
-    const int64_t i = base + (int64_t)j * kPeerThreads + threadIdx.x;
-    rd[j] = -1;
-    if (i < n) {
-      rc[j] = c[i]; rs[j] = s[i]; re[j] = e[i];
-      rd[j] = peer_dest(rc[j], owner, n_contigs, n_ranks);
+    for (int j = 0; j < kPeerItems; ++j) {
+      const int64_t i = base + (int64_t)j * kPeerThreads + threadIdx.x;
+      rd[j] = -1;
+      if (i < n) {
+        rc[j] = c[i]; rs[j] = s[i]; re[j] = e[i];
+        rd[j] = peer_dest(rc[j], owner, n_contigs, n_ranks);
+      }
     }
-  }
-  // rank of every row among the rows of its (item, warp) with the same destination; (item, warp, lane) order = row order
+    // rank of every row among the rows of its (item, warp) with the same destination; (item, warp, lane) order = row order
 #pragma unroll
-  for (int j = 0; j < kPeerItems; ++j) {
-    const unsigned peers = __match_any_sync(0xffffffffu, rd[j]);
-    if (rd[j] >= 0 && lane == __ffs(peers) - 1) wcnt[j * kPeerWarps + warp][rd[j]] = (unsigned)__popc(peers);
-    slot[j] = (unsigned)__popc(peers & lt);
-  }
-  __syncthreads();
-  if (threadIdx.x < n_ranks) {  // exclusive prefix over the 32 (item, warp) groups of this destination
-    unsigned int run = 0;
-    for (int k = 0; k < kPeerItems * kPeerWarps; ++k) { const unsigned int v = wcnt[k][threadIdx.x]; wcnt[k][threadIdx.x] = run; run += v; }
-    boff[threadIdx.x + 1] = run;  // block total, turned into offsets below
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned int run = 0;
-    for (int r = 0; r < n_ranks; ++r) { const unsigned int v = boff[r + 1]; boff[r] = run; run += v; }
-    boff[n_ranks] = run;
-  }
-  __syncthreads();
-  // stage in (destination, slot) order
+    for (int j = 0; j < kPeerItems; ++j) {
+      const unsigned peers = __match_any_sync(0xffffffffu, rd[j]);
+      if (rd[j] >= 0 && lane == __ffs(peers) - 1) wcnt[j * kPeerWarps + warp][rd[j]] = (unsigned)__popc(peers);
+      slot[j] = (unsigned)__popc(peers & lt);
+    }
+    __syncthreads();
+    if (threadIdx.x < n_ranks) {  // exclusive prefix over the 32 (item, warp) groups of this destination
+      unsigned int run = 0;
+      for (int k = 0; k < kPeerItems * kPeerWarps; ++k) { const unsigned int v = wcnt[k][threadIdx.x]; wcnt[k][threadIdx.x] = run; run += v; }
+      boff[threadIdx.x + 1] = run;  // block total, turned into offsets below
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int run = 0;
+      for (int r = 0; r < n_ranks; ++r) { const unsigned int v = boff[r + 1]; boff[r] = run; run += v; }
+      boff[n_ranks] = run;
+    }
+    __syncthreads();
+    // stage in (destination, slot) order
 #pragma unroll
-  for (int j = 0; j < kPeerItems; ++j) {
-    if (rd[j] < 0) continue;
-    const unsigned int p = boff[rd[j]] + wcnt[j * kPeerWarps + warp][rd[j]] + slot[j];
-    const int64_t i = base + (int64_t)j * kPeerThreads + threadIdx.x;
-    sc[p] = rc[j]; ss[p] = rs[j]; se[p] = re[j]; sr[p] = id0 + (uint32_t)i;
-  }
-  __syncthreads();
-  // write out: consecutive positions of one destination are consecutive elements of its region
-  const unsigned int total = boff[n_ranks];
-  for (unsigned int p = threadIdx.x; p < total; p += kPeerThreads) {
-    int r = 0;
-    while (p >= boff[r + 1]) ++r;
-    const unsigned long long k = (unsigned long long)gbase[r] + (p - boff[r]);
-    const PeerDst d = dst[r];
-    d.contig[k] = sc[p]; d.start[k] = ss[p]; d.end[k] = se[p]; d.row[k] = sr[p];
+    for (int j = 0; j < kPeerItems; ++j) {
+      if (rd[j] < 0) continue;
+      const unsigned int p = boff[rd[j]] + wcnt[j * kPeerWarps + warp][rd[j]] + slot[j];
+      const int64_t i = base + (int64_t)j * kPeerThreads + threadIdx.x;
+      sc[p] = rc[j]; ss[p] = rs[j]; se[p] = re[j]; sr[p] = id0 + (uint32_t)i;
+    }
+    __syncthreads();
+    // write out: consecutive positions of one destination are consecutive elements of its region
+    const unsigned int total = boff[n_ranks];
+    for (unsigned int p = threadIdx.x; p < total; p += kPeerThreads) {
+      int r = 0;
+      while (p >= boff[r + 1]) ++r;
+      const unsigned long long k = (unsigned long long)gbase[r] + (p - boff[r]);
+      const PeerDst d = dst[r];
+      d.contig[k] = sc[p]; d.start[k] = ss[p]; d.end[k] = se[p]; d.row[k] = sr[p];
+    }
+    __syncthreads();  // the staging arrays and counters are rewritten by the next tile
   }
 }
 
@@ -279,8 +409,11 @@ int pbgpu_peer_alloc(size_t bytes, void **d_ptr, unsigned char *handle_out /*[64
   if (!d_ptr || !handle_out) return set_error(PBGPU_EINVAL, "NULL argument");
   *d_ptr = nullptr;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
+  // whole 2 MiB pages: a small cudaMalloc block shares its page (and its IPC mapping) with other allocations
+  bytes = (bytes + ((size_t)2 << 20) - 1) / ((size_t)2 << 20) * ((size_t)2 << 20);
+  if (!bytes) bytes = (size_t)2 << 20;
   void *p = nullptr;
-  cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+  cudaError_t e = cudaMalloc(&p, bytes);
   if (e != cudaSuccess) {
     cudaGetLastError();
     return set_error(e == cudaErrorMemoryAllocation ? PBGPU_ENOMEM : PBGPU_ECUDA, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
@@ -319,25 +452,42 @@ int pbgpu_peer_close(void *d_ptr) {
   return PBGPU_OK;
 }
 
-int pbgpu_peer_histogram(const int32_t *d_contig, int64_t n, int32_t n_contigs, int64_t *d_hist, void *stream) {
-  if (n < 0 || n_contigs < 0) return set_error(PBGPU_EINVAL, "negative size");
-  if (!d_hist) return set_error(PBGPU_EINVAL, "NULL argument");
-  if (n > 0 && !d_contig) return set_error(PBGPU_EINVAL, "NULL column");
-  int64_t grid = cdiv(n, 256 * 16);
-  if (grid > kSMs * 8) grid = kSMs * 8;
-  if (grid < 1) grid = 1;
-  const size_t smem = n_contigs <= 4096 ? sizeof(unsigned int) * (size_t)n_contigs : 0;
-  PB_LAUNCH(peer_hist_kernel, (unsigned)grid, 256, smem, (cudaStream_t)stream, d_contig, n, n_contigs, (unsigned long long *)d_hist);
-  PB_CHECK_LAUNCH();
+static unsigned long long peer_timeout_ns() {
+  static unsigned long long v = [] {
+    const char *e = getenv("PBGPU_PEER_TIMEOUT_MS");
+    const long long ms = e ? atoll(e) : 20000;
+    return (unsigned long long)(ms > 0 ? ms : 20000) * 1000000ull;
+  }();
+  return v;
+}
+static int peer_ctl_args(const uint64_t *ctl_base, int32_t world, PeerCtlArgs *a) {
+  if (world < 1 || world > kPeerMaxRanks) return set_error(PBGPU_EINVAL, "bad world (at most %d ranks)", kPeerMaxRanks);
+  if (!ctl_base) return set_error(PBGPU_EINVAL, "NULL argument");
+  memset(a, 0, sizeof(*a));
+  for (int d = 0; d < world; ++d) {
+    if (!ctl_base[d]) return set_error(PBGPU_EINVAL, "NULL control block");
+    a->ctl[d] = ctl_base[d];
+  }
   return PBGPU_OK;
 }
 
-int pbgpu_peer_plan(const int64_t *d_gathered, int32_t world, int32_t rank, int32_t n_tables, int32_t n_contigs,
-                    const uint64_t *arena_base, const int64_t *cap_rows, int32_t *d_owner, void *d_dst, int64_t *d_result, void *stream) {
+size_t pbgpu_peer_ctl_bytes(int32_t world, int32_t n_tables, int32_t n_contigs) {
+  if (world < 1 || n_tables < 1 || n_contigs < 0) return 0;
+  return kPeerCtlHist + sizeof(long long) * (size_t)world * (size_t)n_tables * ((size_t)n_contigs + 1);
+}
+
+static int peer_plan_impl(const int64_t *d_gathered, const void *d_own_ctl, uint64_t step, int32_t world, int32_t rank, int32_t n_tables,
+                          int32_t n_contigs, const uint64_t *arena_base, const int64_t *cap_rows, int32_t *d_owner, void *d_dst,
+                          int64_t *d_result, int64_t *h_result, void *stream, void *scratch_w, void *scratch_order) {
   if (world < 1 || world > kPeerMaxRanks) return set_error(PBGPU_EINVAL, "bad world (at most %d ranks)", kPeerMaxRanks);
   if (n_tables < 1 || n_tables > kPeerMaxTables) return set_error(PBGPU_EINVAL, "bad n_tables (at most %d)", kPeerMaxTables);
   if (rank < 0 || rank >= world || n_contigs < 0) return set_error(PBGPU_EINVAL, "bad rank / n_contigs");
-  if (!d_gathered || !arena_base || !cap_rows || !d_owner || !d_dst || !d_result) return set_error(PBGPU_EINVAL, "NULL argument");
+  if ((!d_gathered && !d_own_ctl) || !arena_base || !cap_rows || !d_owner || !d_dst || !d_result) return set_error(PBGPU_EINVAL, "NULL argument");
+  const unsigned long long *wait_flags = nullptr;
+  if (d_own_ctl) {  // histograms were published into the control block: wait for flag A, read them from there
+    wait_flags = (const unsigned long long *)d_own_ctl;
+    d_gathered = (const int64_t *)((const char *)d_own_ctl + kPeerCtlHist);
+  }
   cudaStream_t s = (cudaStream_t)stream;
   PeerPlanArgs a;
   memset(&a, 0, sizeof(a));
@@ -350,23 +500,38 @@ int pbgpu_peer_plan(const int64_t *d_gathered, int32_t world, int32_t rank, int3
     off += 16ll * cap_rows[t];
   }
   Scratch sc(s);
-  unsigned long long *w = nullptr;
-  int32_t *order = nullptr;
-  PB_TRY(sc.get(&w, (size_t)n_contigs + 1));
-  PB_TRY(sc.get(&order, (size_t)n_contigs + 1));
+  unsigned long long *w = (unsigned long long *)scratch_w;
+  int32_t *order = (int32_t *)scratch_order;
+  if (!w || !order) {
+    PB_TRY(sc.get(&w, (size_t)n_contigs + 1));
+    PB_TRY(sc.get(&order, (size_t)n_contigs + 1));
+  }
   PB_LAUNCH(peer_plan_kernel, 1, 1024, 0, s, (const long long *)d_gathered, world, rank, n_tables, n_contigs, a, w, order, d_owner,
-            (PeerDst *)d_dst, (long long *)d_result);
+            (PeerDst *)d_dst, (long long *)d_result, wait_flags, (unsigned long long)step, peer_timeout_ns(), (long long *)h_result);
   PB_CHECK_LAUNCH();
   return PBGPU_OK;
+}
+int pbgpu_peer_plan(const int64_t *d_gathered, const void *d_own_ctl, uint64_t step, int32_t world, int32_t rank, int32_t n_tables,
+                    int32_t n_contigs, const uint64_t *arena_base, const int64_t *cap_rows, int32_t *d_owner, void *d_dst, int64_t *d_result,
+                    int64_t *h_result, void *stream) {
+  return peer_plan_impl(d_gathered, d_own_ctl, step, world, rank, n_tables, n_contigs, arena_base, cap_rows, d_owner, d_dst, d_result, h_result,
+                        stream, nullptr, nullptr);
 }
 
 // Every valid row of this rank's slice goes to the column arrays of its owner.  d_dst: n_ranks records of four device
 // pointers (contig, start, end, row) = the start of THIS source's region at each destination (own arena or mapped peer
 // memory), d_row_id_base: the global id of row 0, d_flag: non-zero = do nothing (arena overflow) -- all three are
 // outputs of pbgpu_peer_plan and are read on the device, so the host enqueues plan and scatter back to back.
-int pbgpu_peer_scatter(const int32_t *d_contig, const int32_t *d_start, const int32_t *d_end, int64_t n, const int32_t *d_owner,
-                       int32_t n_contigs, int32_t n_ranks, const int64_t *d_row_id_base, const void *d_dst, const int64_t *d_flag,
-                       void *stream) {
+// $PBGPU_PEER_GRID = blocks per SM of the scatter kernel (persistent grid striding over the tiles); 0 / unset = one
+// block per tile
+static int peer_grid_per_sm() {
+  static int v = [] { const char *e = getenv("PBGPU_PEER_GRID"); const int x = e ? atoi(e) : 0; return x > 0 && x <= 8 ? x : 0; }();
+  return v;
+}
+
+static int peer_scatter_impl(const int32_t *d_contig, const int32_t *d_start, const int32_t *d_end, int64_t n, const int32_t *d_owner,
+                             int32_t n_contigs, int32_t n_ranks, const int64_t *d_row_id_base, const void *d_dst, const int64_t *d_flag,
+                             void *stream, unsigned int *bc_scratch) {
   if (n < 0 || n >= (1ll << 32) || n_ranks < 1 || n_ranks > kPeerMaxRanks) return set_error(PBGPU_EINVAL, "bad n / n_ranks (at most %d ranks)", kPeerMaxRanks);
   if (!d_owner || !d_dst || !d_row_id_base || !d_flag) return set_error(PBGPU_EINVAL, "NULL argument");
   if (n == 0) return PBGPU_OK;
@@ -374,12 +539,111 @@ int pbgpu_peer_scatter(const int32_t *d_contig, const int32_t *d_start, const in
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t nblk = cdiv(n, kPeerTile);
   Scratch sc(s);
-  unsigned int *bc = nullptr;
-  PB_TRY(sc.get(&bc, (size_t)nblk * n_ranks));
+  unsigned int *bc = bc_scratch;
+  if (!bc) PB_TRY(sc.get(&bc, (size_t)nblk * n_ranks));
+  int64_t grid = nblk;
+  if (peer_grid_per_sm() && grid > (int64_t)kSMs * peer_grid_per_sm()) grid = (int64_t)kSMs * peer_grid_per_sm();
   PB_LAUNCH(peer_block_count_kernel, (unsigned)nblk, kPeerThreads, 0, s, d_contig, n, d_owner, n_contigs, n_ranks, (const long long *)d_flag, bc, nblk);
   PB_LAUNCH(peer_block_scan_kernel, (unsigned)n_ranks, 1024, 0, s, bc, nblk, (const long long *)d_flag);
-  PB_LAUNCH(peer_scatter_kernel, (unsigned)nblk, kPeerThreads, 0, s, d_contig, d_start, d_end, n, d_owner, n_contigs, n_ranks,
+  PB_LAUNCH(peer_scatter_kernel, (unsigned)grid, kPeerThreads, 0, s, d_contig, d_start, d_end, n, d_owner, n_contigs, n_ranks,
             (const long long *)d_row_id_base, (const PeerDst *)d_dst, bc, nblk, (const long long *)d_flag);
+  PB_CHECK_LAUNCH();
+  return PBGPU_OK;
+}
+int pbgpu_peer_scatter(const int32_t *d_contig, const int32_t *d_start, const int32_t *d_end, int64_t n, const int32_t *d_owner,
+                       int32_t n_contigs, int32_t n_ranks, const int64_t *d_row_id_base, const void *d_dst, const int64_t *d_flag,
+                       void *stream) {
+  return peer_scatter_impl(d_contig, d_start, d_end, n, d_owner, n_contigs, n_ranks, d_row_id_base, d_dst, d_flag, stream, nullptr);
+}
+
+// layout of the caller-provided scratch of a step: w u64[nc+1] | order i32[nc+1] (padded) | per table bc u32[world * tiles]
+struct PeerScratchLayout { size_t w, order, bc[kPeerMaxTables], total; };
+static PeerScratchLayout peer_scratch_layout(const pbgpu_peer_step *d) {
+  PeerScratchLayout l;
+  size_t off = 0;
+  auto take = [&off](size_t bytes) { const size_t at = off; off += (bytes + 255) / 256 * 256; return at; };
+  l.w = take(sizeof(unsigned long long) * ((size_t)d->n_contigs + 1));
+  l.order = take(sizeof(int32_t) * ((size_t)d->n_contigs + 1));
+  for (int t = 0; t < kPeerMaxTables; ++t)
+    l.bc[t] = t < d->n_tables ? take(sizeof(unsigned int) * (size_t)d->world * (size_t)cdiv(d->rows[t] > 0 ? d->rows[t] : 0, kPeerTile)) : 0;
+  l.total = off;
+  return l;
+}
+size_t pbgpu_peer_scratch_bytes(const pbgpu_peer_step *d) {
+  if (!d || d->world < 1 || d->n_tables < 1 || d->n_tables > kPeerMaxTables || d->n_contigs < 0) return 0;
+  return peer_scratch_layout(d).total;
+}
+
+
+static int peer_step_check(const pbgpu_peer_step *d) {
+  if (!d) return set_error(PBGPU_EINVAL, "NULL descriptor");
+  if (d->world < 1 || d->world > kPeerMaxRanks || d->rank < 0 || d->rank >= d->world) return set_error(PBGPU_EINVAL, "bad world / rank");
+  if (d->n_tables < 1 || d->n_tables > kPeerMaxTables || d->n_contigs < 0) return set_error(PBGPU_EINVAL, "bad n_tables / n_contigs");
+  if (!d->arena_base || !d->cap_rows || !d->d_hist || !d->d_owner || !d->d_dst || !d->d_result || !d->d_status)
+    return set_error(PBGPU_EINVAL, "NULL argument");
+  for (int t = 0; t < d->n_tables; ++t) {
+    if (d->rows[t] < 0 || d->rows[t] >= (1ll << 32)) return set_error(PBGPU_EINVAL, "bad row count");
+    if (d->rows[t] > 0 && (!d->contig[t] || !d->start[t] || !d->end[t])) return set_error(PBGPU_EINVAL, "NULL column");
+  }
+  return PBGPU_OK;
+}
+
+// First half of an exchange step on `stream`: histograms of all tables (one launch) and, with control blocks, their
+// publication and the plan (which posts its result to h_result).  Without control blocks the caller all-gathers d_hist
+// and calls pbgpu_peer_plan itself.
+int pbgpu_peer_begin(const pbgpu_peer_step *d, void *stream) {
+  PB_TRY(peer_step_check(d));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int ph = d->phases ? d->phases : (PBGPU_PEER_HIST | PBGPU_PEER_PLAN);
+  if (ph & PBGPU_PEER_HIST) {
+    const int len = d->n_tables * (d->n_contigs + 1);
+    PB_CUDA(cudaMemsetAsync(d->d_hist, 0, sizeof(int64_t) * ((size_t)len + 1), s));
+    PeerTablesArgs tb;
+    memset(&tb, 0, sizeof(tb));
+    int64_t gx = 1;
+    for (int t = 0; t < d->n_tables; ++t) {
+      tb.c[t] = d->contig[t];
+      tb.n[t] = d->rows[t];
+      int64_t g = cdiv(d->rows[t], 256 * 16);
+      if (g > gx) gx = g;
+    }
+    if (gx > kSMs * 8) gx = kSMs * 8;
+    PeerCtlArgs ca;
+    memset(&ca, 0, sizeof(ca));
+    if (d->ctl_base) PB_TRY(peer_ctl_args(d->ctl_base, d->world, &ca));
+    const size_t smem = d->n_contigs <= 4096 ? sizeof(unsigned int) * (size_t)d->n_contigs : 0;
+    PB_LAUNCH(peer_hist_publish_kernel, dim3((unsigned)gx, (unsigned)d->n_tables), 256, smem, s, tb, d->n_tables, d->n_contigs,
+              (unsigned long long *)d->d_hist, ca, d->world, d->rank, (unsigned long long)d->step, d->ctl_base ? 1 : 0);
+    PB_CHECK_LAUNCH();
+  }
+  if (!d->ctl_base || !(ph & PBGPU_PEER_PLAN)) return PBGPU_OK;
+  const PeerScratchLayout l = peer_scratch_layout(d);
+  const bool own = d->d_scratch && d->scratch_bytes >= l.total;
+  return peer_plan_impl(nullptr, (const void *)d->ctl_base[d->rank], d->step, d->world, d->rank, d->n_tables, d->n_contigs, d->arena_base,
+                        d->cap_rows, d->d_owner, d->d_dst, d->d_result, d->h_result, stream, own ? (char *)d->d_scratch + l.w : nullptr,
+                        own ? (char *)d->d_scratch + l.order : nullptr);
+}
+
+// Second half, once per table, on any stream ordered after pbgpu_peer_begin: the scatter of the table and, with control
+// blocks, its signal + wait (after which the table is complete on this rank).
+int pbgpu_peer_table(const pbgpu_peer_step *d, int32_t table, void *stream) {
+  PB_TRY(peer_step_check(d));
+  if (table < 0 || table >= d->n_tables) return set_error(PBGPU_EINVAL, "bad table");
+  const int T = d->n_tables;
+  const int ph = d->phases ? d->phases : (PBGPU_PEER_SCATTER | PBGPU_PEER_SIGNAL | PBGPU_PEER_WAIT);
+  if (ph & PBGPU_PEER_SCATTER) {
+    const PeerScratchLayout l = peer_scratch_layout(d);
+    const bool own = d->d_scratch && d->scratch_bytes >= l.total;
+    PB_TRY(peer_scatter_impl(d->contig[table], d->start[table], d->end[table], d->rows[table], d->d_owner, d->n_contigs, d->world,
+                             d->d_result + T + table, (const char *)d->d_dst + sizeof(PeerDst) * (size_t)d->world * table,
+                             d->d_result + 3 * T, stream, own ? (unsigned int *)((char *)d->d_scratch + l.bc[table]) : nullptr));
+  }
+  const int mode = ((ph & PBGPU_PEER_SIGNAL) ? 1 : 0) | ((ph & PBGPU_PEER_WAIT) ? 2 : 0);
+  if (!d->ctl_base || !mode) return PBGPU_OK;
+  PeerCtlArgs ca;
+  PB_TRY(peer_ctl_args(d->ctl_base, d->world, &ca));
+  PB_LAUNCH(peer_signal_wait_kernel, 1, 32, 0, (cudaStream_t)stream, ca, d->world, d->rank, table, (unsigned long long)d->step,
+            peer_timeout_ns(), (long long *)d->d_status, mode);
   PB_CHECK_LAUNCH();
   return PBGPU_OK;
 }

@@ -104,11 +104,17 @@ def shard_table(contig: torch.Tensor, start: torch.Tensor, end: torch.Tensor, n_
     return c2, s2, e2, row2
 
 
-def shard_tables(tables, n_contigs: int, group=None, trace: Optional[list] = None):
-    """Exchange several tables at once (typically the probe and the build side) with as few host round trips as
-    possible: ONE all_reduce (per-contig histogram of all tables + slice sizes), ONE count all-to-all, one payload
-    all-to-all per table.  ``tables``: list of (contig, start, end) int32 CUDA columns (this rank's slices).
-    Returns (list of (contig, start, end, global_row) owned columns, owner table)."""
+def shard_tables(tables, n_contigs: int, group=None, trace: Optional[list] = None, ready: Optional[list] = None):
+    """Exchange several tables at once (typically the probe and the build side).  ``tables``: list of (contig, start,
+    end) int32 CUDA columns (this rank's slices).  Returns (list of (contig, start, end, global_row) owned columns,
+    owner table).
+
+    On one node the rows travel over NVLink peer memory (``PeerExchange``; the returned columns are views into its
+    receive arena, valid until the second-next call).  ``ready`` (an empty list): overlapped mode -- the tables are
+    exchanged concurrently, in list order, on their own streams; the list receives one event per table and the
+    caller's stream must wait for event t before touching table t, so work on the first table (the index build)
+    overlaps the transfer of the next.  Fallback: ONE all_reduce (per-contig histogram of all tables + slice sizes),
+    ONE count all-to-all, one NCCL payload all-to-all per table."""
     import ctypes
     import time
 
@@ -122,7 +128,7 @@ def shard_tables(tables, n_contigs: int, group=None, trace: Optional[list] = Non
     T = len(tables)
     ex = _peer_exchange_for(tables, n_contigs, group)
     if ex is not None:
-        return ex.shard(tables, trace=trace)
+        return ex.shard(tables, trace=trace, ready=ready)
     t0 = time.perf_counter()
     with torch.cuda.device(dev):
         sp = _stream_ptr(dev)
@@ -171,10 +177,62 @@ def shard_tables(tables, n_contigs: int, group=None, trace: Optional[list] = Non
             row2 = torch.empty_like(c2)
             _native.check(L.pbgpu_unpack_records(recv.data_ptr(), r, c2.data_ptr(), s2.data_ptr(), e2.data_ptr(), row2.data_ptr(), sp))
             out.append((c2, s2, e2, row2))
+        if ready is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            ready.extend([ev] * T)
         if trace is not None:
             torch.cuda.synchronize(dev)
             trace.append(("all-to-all+unpack", time.perf_counter() - t0))
     return out, owner
+
+
+def replicate_table(contig: torch.Tensor, start: torch.Tensor, end: torch.Tensor, group=None):
+    """All ranks end up with the WHOLE table, rows in global order (rank 0's slice, rank 1's, ...): the other way to
+    distribute a join (degenerate case).  When the indexed table is small, or when there are fewer
+    contigs than ranks (BASELINE config 2: one contig), moving it everywhere costs less than moving the probes to
+    their contig's owner: every rank builds the same index and probes only the rows it already holds, so the big
+    table never crosses a link and a single contig still spreads over all GPUs.
+    Returns ((contig, start, end) whole table, first global row id of this rank's slice, rows per rank)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return (contig, start, end), 0, [contig.numel()]
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = contig.device
+    n = contig.numel()
+    sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+    sizes[rank] = n
+    dist.all_reduce(sizes, group=group)
+    sizes_l = [int(x) for x in sizes.tolist()]
+    cap = max(max(sizes_l), 1)
+    mine = torch.zeros((3, cap), dtype=torch.int32, device=dev)  # one collective for the three columns
+    mine[0, :n], mine[1, :n], mine[2, :n] = contig, start, end
+    everyone = torch.empty((world, 3, cap), dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(everyone.view(-1), mine.view(-1), group=group)
+    if all(x == cap for x in sizes_l):
+        cols = tuple(everyone[:, k, :].reshape(-1) for k in range(3))
+    else:
+        cols = tuple(torch.cat([everyone[r, k, : sizes_l[r]] for r in range(world)]) for k in range(3))
+    return cols, sum(sizes_l[:rank]), sizes_l
+
+
+def join_strategy(hist_probe: torch.Tensor, hist_build: torch.Tensor, world: int) -> str:
+    """'replicate' (``replicate_table`` of the indexed table, probes stay where they are) or 'shard' (``shard_tables``
+    by contig owner), from the global per-contig histograms: replicate when the contigs cannot keep every rank busy
+    (fewer non-empty contigs than ranks, or the largest one outweighs an even share by 2x), or when copying the indexed
+    table to every rank moves fewer rows than sending both tables to their owners."""
+    if world <= 1:
+        return "shard"
+    hp, hb = hist_probe.to("cpu", torch.float64), hist_build.to("cpu", torch.float64)
+    w = hp + hb
+    total = float(w.sum())
+    if total == 0:
+        return "shard"
+    busy = int((w > 0).sum())
+    if busy < world or float(w.max()) > 2.0 * total / world:
+        return "replicate"
+    moved_shard = total * (world - 1) / world            # rows crossing links, all ranks together
+    moved_replicate = float(hb.sum()) * (world - 1)
+    return "replicate" if moved_replicate < moved_shard else "shard"
 
 
 def translate(local_rows: torch.Tensor, global_of_local: torch.Tensor) -> torch.Tensor:
@@ -245,12 +303,18 @@ class PeerExchange:
     ``cap_rows[t]``: rows per column table ``t`` can receive on one rank; arenas grow (collectively) when a step needs
     more.  Two arenas alternate between steps: a fast rank may already be writing step k+1 while a slow one still reads
     step k.  The column tensors returned by ``shard`` are views into an arena and stay valid until the second-next
-    ``shard`` call (or ``close``).  ``arenas`` (tests): explicit base addresses [2][world] in this process -- several
-    simulated ranks on one device, no IPC."""
+    ``shard`` call (or ``close``).
 
-    def __init__(self, n_contigs: int, cap_rows, device, group=None, arenas=None, world: Optional[int] = None,
+    Synchronisation (``sync``): "flags" -- a control block per rank, mapped by all peers: histograms and completion
+    flags travel through peer memory, a step makes no NCCL call, and with ``ready=[]`` every table runs its scatter /
+    signal / wait on its own stream; "nccl" ($PBGPU_PEER_SYNC=nccl) -- all_gather of the histograms and a closing
+    all_reduce.  ``arenas`` / ``ctls`` (tests): explicit base addresses ([2][world] / [world]) in this process --
+    several simulated ranks on one device, no IPC, phases driven by the test."""
+
+    def __init__(self, n_contigs: int, cap_rows, device, group=None, arenas=None, ctls=None, world: Optional[int] = None,
                  rank: Optional[int] = None):
         import ctypes
+        import os
 
         from . import _native
 
@@ -259,7 +323,8 @@ class PeerExchange:
         self.group = group
         self.nc = int(n_contigs)
         self.T = len(cap_rows)
-        if arenas is not None:
+        self.external = arenas is not None
+        if self.external:
             self.world, self.rank, self.collective = int(world), int(rank), False
         else:
             self.collective = dist.is_initialized() and dist.get_world_size(group) > 1
@@ -267,27 +332,46 @@ class PeerExchange:
             self.rank = dist.get_rank(group) if self.collective else 0
         if self.world > PEER_MAX_RANKS or not 1 <= self.T <= PEER_MAX_TABLES:
             raise PeerUnavailable(f"peer exchange supports <= {PEER_MAX_RANKS} ranks and <= {PEER_MAX_TABLES} tables")
+        if self.external:
+            self.sync = "flags" if ctls is not None else "none"
+        else:
+            self.sync = "nccl" if os.environ.get("PBGPU_PEER_SYNC", "flags") == "nccl" else "flags"
         self.step = 0
         self.own = [None, None]      # own arena per parity (owned allocations)
-        self.mapped = [[], []]       # peer mappings per parity (to close)
-        self.base = [None, None]     # ctypes uint64[world] per parity
-        self.external = arenas is not None
+        self.own_ctl = None          # own control block
+        self.mapped = [[], []]       # peer arena mappings per parity (to close)
+        self.mapped_ctl = []         # peer control-block mappings
+        self.base = [None, None]     # ctypes uint64[world] per parity: arena addresses in this process
+        self.ctl = None              # ctypes uint64[world]: control-block addresses in this process
         T, nc, w = self.T, self.nc, self.world
+        self.ctl_bytes = int(self.L.pbgpu_peer_ctl_bytes(w, T, nc))
         with torch.cuda.device(self.dev):
-            self.meta = torch.zeros((T, nc + 1), dtype=torch.int64, device=self.dev)
-            self.gathered = torch.zeros((w, T, nc + 1), dtype=torch.int64, device=self.dev)
+            self.meta_all = torch.zeros(T * (nc + 1) + 1, dtype=torch.int64, device=self.dev)  # + the publish counter
+            self.meta = self.meta_all[: T * (nc + 1)].view(T, nc + 1)
+            self.gathered = torch.zeros((w, T, nc + 1), dtype=torch.int64, device=self.dev) if self.sync == "nccl" else None
             self.owner = torch.zeros(max(nc, 1), dtype=torch.int32, device=self.dev)
             self.dst = torch.zeros(T * w * 4, dtype=torch.int64, device=self.dev)
             self.result = torch.zeros(3 * T + 1, dtype=torch.int64, device=self.dev)
-            self.result_h = torch.zeros(3 * T + 1, dtype=torch.int64).pin_memory()
+            self.result_h = torch.zeros(3 * T + 2, dtype=torch.int64).pin_memory()  # posted by the plan kernel, sequence word last
+            self.result_np = self.result_h.numpy()
+            self.status = torch.zeros(1, dtype=torch.int64, device=self.dev)  # raised by a wait kernel that timed out
+            self.status_h = torch.zeros(1, dtype=torch.int64).pin_memory()
             self.token = torch.zeros(1, dtype=torch.int32, device=self.dev)
-            self.ready = torch.cuda.Event()
+            self.planned = torch.cuda.Event()
+            self.side = [torch.cuda.Stream(self.dev) for _ in range(T)] if not self.external else []
+            self.table_done = [None] * T  # events of the previous step's per-table tails
+        self.desc = _native.PbPeerStep()
+        self.views = {}
+        self.scratch = None
+        self._laps = None
         self._set_caps(cap_rows)
         if self.external:
             for par in (0, 1):
                 self.base[par] = (ctypes.c_uint64 * w)(*[int(a) for a in arenas[par]])
+            if ctls is not None:
+                self.ctl = (ctypes.c_uint64 * w)(*[int(a) for a in ctls])
         else:
-            self._allocate()
+            self._allocate(first=True)
 
     # -- arenas ------------------------------------------------------------------------------------
     def _set_caps(self, cap_rows):
@@ -297,64 +381,68 @@ class PeerExchange:
         self.caps_c = (ctypes.c_int64 * self.T)(*self.caps)
         self.tab_off = [16 * sum(self.caps[:t]) for t in range(self.T)]
         self.arena_bytes = 16 * sum(self.caps)
+        self.views = {}
 
-    def _allocate(self):
+    def _allocate(self, first: bool = False):
+        """Allocate the two arenas (and, the first time, the control block), exchange the IPC handles, map the peers'.
+        Collective; every rank reaches the agreement at the end whatever happened locally."""
         import ctypes
 
         from . import _native
 
         L, w = self.L, self.world
-        ok = True
-        err = ""
-        handles = torch.zeros(2 * 64, dtype=torch.uint8)
+        with_ctl = first and self.sync == "flags"
+        ok, err = True, ""
+        nh = 3 if with_ctl else 2
+        handles = torch.zeros(nh * 64, dtype=torch.uint8)
         with torch.cuda.device(self.dev):
             try:
-                for par in (0, 1):
+                for k in range(nh):
                     p = ctypes.c_void_p()
                     h = (ctypes.c_ubyte * 64)()
-                    _native.check(L.pbgpu_peer_alloc(self.arena_bytes, ctypes.byref(p), h))
-                    self.own[par] = p.value
-                    handles[64 * par: 64 * par + 64] = torch.frombuffer(bytearray(h), dtype=torch.uint8)
+                    _native.check(L.pbgpu_peer_alloc(self.arena_bytes if k < 2 else self.ctl_bytes, ctypes.byref(p), h))
+                    if k < 2:
+                        self.own[k] = p.value
+                    else:
+                        self.own_ctl = p.value
+                        _i32_view(p.value, self.ctl_bytes // 4, self.dev).zero_()
+                        torch.cuda.synchronize(self.dev)
+                    handles[64 * k: 64 * k + 64] = torch.frombuffer(bytearray(h), dtype=torch.uint8)
             except _native.PbgpuError as e:  # keep going: the agreement below must be reached by every rank
                 ok, err = False, str(e)
+            addrs = [[self.own[0]] * w, [self.own[1]] * w, [self.own_ctl] * w]
             if self.collective:
-                mine = handles.to(self.dev)
-                everyone = torch.empty((w, 128), dtype=torch.uint8, device=self.dev)
-                dist.all_gather_into_tensor(everyone, mine, group=self.group)
+                everyone = torch.empty((w, nh * 64), dtype=torch.uint8, device=self.dev)
+                dist.all_gather_into_tensor(everyone, handles.to(self.dev), group=self.group)
                 everyone = everyone.cpu()
-                addrs = [[0] * w, [0] * w]
                 if ok:
-                    for par in (0, 1):
+                    for k in range(nh):
                         for r in range(w):
                             if r == self.rank:
-                                addrs[par][r] = self.own[par]
                                 continue
-                            hb = (ctypes.c_ubyte * 64)(*everyone[r, 64 * par: 64 * par + 64].tolist())
+                            hb = (ctypes.c_ubyte * 64)(*everyone[r, 64 * k: 64 * k + 64].tolist())
                             p = ctypes.c_void_p()
-                            rc = L.pbgpu_peer_open(hb, ctypes.byref(p))
-                            if rc != 0:
+                            if L.pbgpu_peer_open(hb, ctypes.byref(p)) != 0:
                                 ok, err = False, L.pbgpu_last_error().decode("utf-8", "replace")
                                 break
-                            addrs[par][r] = p.value
-                            self.mapped[par].append(p.value)
+                            addrs[k][r] = p.value
+                            (self.mapped[k] if k < 2 else self.mapped_ctl).append(p.value)
                         if not ok:
                             break
                 flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.dev)
                 dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
-                if int(flag.item()) == 0:
-                    self._release()
-                    raise PeerUnavailable(err or "a peer could not map the arenas")
-            else:
-                if not ok:
-                    self._release()
-                    raise PeerUnavailable(err)
-                addrs = [[self.own[0]], [self.own[1]]]
+                ok = int(flag.item()) == 1
+            if not ok:
+                self._release(everything=True)
+                raise PeerUnavailable(err or "a peer could not map the arenas")
         for par in (0, 1):
             self.base[par] = (ctypes.c_uint64 * w)(*addrs[par])
+        if with_ctl:
+            self.ctl = (ctypes.c_uint64 * w)(*addrs[2])
 
-    def _release(self):
-        """Unmap the peers' arenas and free our own.  Collective when the exchange is: nobody frees memory a peer may
-        still be writing to or has mapped."""
+    def _release(self, everything: bool = False):
+        """Unmap the peers' arenas and free our own (``everything``: the control block too).  Collective when the
+        exchange is: nobody frees memory a peer may still be writing to or has mapped."""
         if self.external:
             return
         with torch.cuda.device(self.dev):
@@ -365,87 +453,223 @@ class PeerExchange:
                 for p in self.mapped[par]:
                     self.L.pbgpu_peer_close(p)
                 self.mapped[par] = []
+            if everything:
+                for p in self.mapped_ctl:
+                    self.L.pbgpu_peer_close(p)
+                self.mapped_ctl = []
             if self.collective:
                 dist.barrier(group=self.group)
             for par in (0, 1):
                 if self.own[par]:
                     self.L.pbgpu_peer_free(self.own[par])
                 self.own[par] = None
+            if everything and self.own_ctl:
+                self.L.pbgpu_peer_free(self.own_ctl)
+                self.own_ctl = None
 
     def close(self):
-        self._release()
+        try:
+            if not self.external:
+                self.check()
+        finally:
+            self._release(everything=True)
+
+    def check(self):
+        """Raise if a wait kernel of an earlier step timed out (a peer did not arrive)."""
+        with torch.cuda.device(self.dev):
+            torch.cuda.synchronize(self.dev)
+            if int(self.status.item()) != 0:
+                raise RuntimeError("peer exchange: a peer did not signal within the timeout; received tables are incomplete")
 
     def _grow(self, need):
         self._release()
         self._set_caps([max(c, int(n * 1.25) + 1024) for c, n in zip(self.caps, need)])
         self._allocate()
 
-    # -- one exchange step -------------------------------------------------------------------------
-    def enqueue(self, tables, gathered: Optional[torch.Tensor] = None):
-        """Histograms, (all_gather,) plan and scatters of one step, without waiting for anything.  ``gathered``
-        (tests): pre-computed all-gathered histograms instead of the collective."""
+    # -- phases of one exchange step, one by one (tests; enqueued on the current stream) ------------------
+    PH_HIST, PH_PLAN, PH_SCATTER, PH_SIGNAL, PH_WAIT = 1, 2, 4, 8, 16
+
+    def begin_step(self, tables=None) -> int:
+        par = self.step & 1
+        self.step += 1
+        if tables is not None:
+            self._fill_desc(tables, par)
+        return par
+
+    def phase(self, mask: int, table: Optional[int] = None):
+        """Run only the phases in ``mask`` of pbgpu_peer_begin (``table`` None) or pbgpu_peer_table."""
+        import ctypes
+
         from . import _native
         from .engine import _stream_ptr
 
-        L, T, nc, w = self.L, self.T, self.nc, self.world
-        assert len(tables) == T
-        par = self.step & 1
-        self.step += 1
+        self.desc.phases = mask
+        try:
+            with torch.cuda.device(self.dev):
+                if table is None:
+                    _native.check(self.L.pbgpu_peer_begin(ctypes.byref(self.desc), _stream_ptr(self.dev)))
+                else:
+                    _native.check(self.L.pbgpu_peer_table(ctypes.byref(self.desc), table, _stream_ptr(self.dev)))
+        finally:
+            self.desc.phases = 0
+
+    def phase_plan(self, par: int, gathered: torch.Tensor):
+        """Plan from explicit all-gathered histograms (no control blocks)."""
+        from . import _native
+        from .engine import _stream_ptr
+
         with torch.cuda.device(self.dev):
+            _native.check(self.L.pbgpu_peer_plan(gathered.data_ptr(), None, self.step, self.world, self.rank, self.T, self.nc,
+                                                 self.base[par], self.caps_c, self.owner.data_ptr(), self.dst.data_ptr(),
+                                                 self.result.data_ptr(), self.result_h.data_ptr(), _stream_ptr(self.dev)))
+
+    # -- one exchange step -------------------------------------------------------------------------
+    def _fill_desc(self, tables, par: int):
+        import ctypes
+
+        d = self.desc
+        d.world, d.rank, d.n_tables, d.n_contigs, d.step = self.world, self.rank, self.T, self.nc, self.step
+        for t, (c, s, e) in enumerate(tables):
+            d.contig[t], d.start[t], d.end[t], d.rows[t] = c.data_ptr() or None, s.data_ptr() or None, e.data_ptr() or None, c.numel()
+        d.arena_base = ctypes.cast(self.base[par], ctypes.c_void_p)
+        d.ctl_base = ctypes.cast(self.ctl, ctypes.c_void_p) if self.sync == "flags" else None
+        d.cap_rows = ctypes.cast(self.caps_c, ctypes.c_void_p)
+        d.d_hist, d.d_owner, d.d_dst = self.meta_all.data_ptr(), self.owner.data_ptr(), self.dst.data_ptr()
+        d.d_result, d.h_result, d.d_status = self.result.data_ptr(), self.result_h.data_ptr(), self.status.data_ptr()
+        need = int(self.L.pbgpu_peer_scratch_bytes(ctypes.byref(d)))
+        if self.scratch is None or self.scratch.numel() < need:  # kept across steps: no allocator call in a steady state
+            with torch.cuda.device(self.dev):
+                self.scratch = torch.empty(need * 3 // 2 + 4096, dtype=torch.uint8, device=self.dev)
+        d.d_scratch, d.scratch_bytes = self.scratch.data_ptr(), self.scratch.numel()
+        return ctypes.byref(d)
+
+    def enqueue(self, tables, overlap: bool = False):
+        """All launches of one step, without waiting for anything.  Returns (arena parity, per-table events or None).
+        ``overlap`` (flags only): table t's scatter / signal / wait run on side stream t; the caller makes its stream
+        wait for event t before touching table t."""
+        from . import _native
+        from .engine import _stream_ptr
+
+        assert len(tables) == self.T
+        L = self.L
+        par = self.begin_step()
+        self.desc.phases = 0
+        main = torch.cuda.current_stream(self.dev)
+        with torch.cuda.device(self.dev):
+            for ev in self.table_done:  # side streams of the previous step still read dst / owner / result
+                if ev is not None:
+                    main.wait_event(ev)
+            self.table_done = [None] * self.T
+            d = self._fill_desc(tables, par)
             sp = _stream_ptr(self.dev)
-            if gathered is None:
-                self.meta.zero_()
-                for t, (c, _, _) in enumerate(tables):
-                    _native.check(L.pbgpu_peer_histogram(c.data_ptr(), c.numel(), nc, self.meta[t].data_ptr(), sp))
+            laps = self._laps
+            if laps is not None:
+                laps.append(torch.cuda.Event(enable_timing=True)); laps[-1].record(main)
+            _native.check(L.pbgpu_peer_begin(d, sp))  # histograms (+ publish + plan with control blocks)
+            if self.sync != "flags":
                 if self.collective:
                     dist.all_gather_into_tensor(self.gathered, self.meta, group=self.group)
-                    gathered = self.gathered
-                else:
-                    gathered = self.meta
-            _native.check(L.pbgpu_peer_plan(gathered.data_ptr(), w, self.rank, T, nc, self.base[par], self.caps_c, self.owner.data_ptr(),
-                                            self.dst.data_ptr(), self.result.data_ptr(), sp))
-            self.result_h.copy_(self.result, non_blocking=True)
-            self.ready.record()
-            r0 = self.result.data_ptr()
-            for t, (c, s, e) in enumerate(tables):
-                _native.check(L.pbgpu_peer_scatter(c.data_ptr(), s.data_ptr(), e.data_ptr(), c.numel(), self.owner.data_ptr(), nc, w,
-                                                   r0 + 8 * (T + t), self.dst.data_ptr() + 32 * w * t, r0 + 8 * 3 * T, sp))
-            if self.collective:  # every rank's stores precede its contribution: after this, all regions here are complete
+                self.phase_plan(par, self.gathered if self.collective else self.meta)
+            if laps is not None:
+                laps.append(torch.cuda.Event(enable_timing=True)); laps[-1].record(main)
+            if overlap and self.sync == "flags":
+                self.planned.record(main)
+                events = []
+                for t in range(self.T):
+                    st = self.side[t]
+                    st.wait_event(self.planned)
+                    for col in tables[t]:
+                        col.record_stream(st)
+                    _native.check(L.pbgpu_peer_table(d, t, st.cuda_stream))
+                    ev = torch.cuda.Event(enable_timing=laps is not None)
+                    ev.record(st)
+                    events.append(ev)
+                    if laps is not None:
+                        laps.append(ev)
+                self.table_done = list(events)
+                return par, events
+            for t in range(self.T):
+                _native.check(L.pbgpu_peer_table(d, t, sp))
+                if laps is not None:
+                    laps.append(torch.cuda.Event(enable_timing=True)); laps[-1].record(main)
+            if self.sync != "flags" and self.collective:
+                # every rank's stores precede its contribution: after this, all regions here are complete
                 dist.all_reduce(self.token, group=self.group)
-        return par
+        return par, None
 
     def collect(self, par: int):
-        """Wait for the plan's host copy (it overlaps the scatter) and return the received columns of every table, or
-        None when an arena was too small (nothing was scattered)."""
-        self.ready.synchronize()
+        """Wait for the plan's host copy (it overlaps the scatter) and return (received columns of every table,
+        rows needed per table); columns = None when an arena was too small (nothing was scattered)."""
+        import time
+
         T = self.T
-        res = self.result_h.tolist()
+        seq, want = self.result_np[3 * T + 1: 3 * T + 2], self.step
+        if seq[0] != want:
+            t_end = time.perf_counter() + 120.0
+            while seq[0] != want:
+                if time.perf_counter() > t_end:
+                    raise RuntimeError("peer exchange: the plan kernel did not report within 120 s")
+        res = self.result_np[: 3 * T + 1].tolist()
+        if res[3 * T] == 2:
+            raise RuntimeError("peer exchange: a peer did not publish its histograms within the timeout")
         if res[3 * T]:
             return None, res[2 * T: 3 * T]
-        base = int(self.base[par][self.rank])
-        out = []
-        for t in range(T):
-            r, cap = int(res[t]), self.caps[t]
-            p = base + self.tab_off[t]
-            out.append(tuple(_i32_view(p + 4 * cap * k, r, self.dev) for k in range(4)))
-        return out, res[2 * T: 3 * T]
+        full = self.views.get(par)
+        if full is None:  # whole-capacity views of every column, made once per arena
+            base = int(self.base[par][self.rank])
+            full = [tuple(_i32_view(base + self.tab_off[t] + 4 * self.caps[t] * k, self.caps[t], self.dev) for k in range(4))
+                    for t in range(T)]
+            self.views[par] = full
+        return [tuple(v[: int(res[t])] for v in full[t]) for t in range(T)], res[2 * T: 3 * T]
 
-    def shard(self, tables, trace: Optional[list] = None):
+    def shard(self, tables, trace: Optional[list] = None, ready: Optional[list] = None):
+        """One exchange step.  ``ready`` (a list): overlapped mode -- it receives one event per table and the caller's
+        stream must wait for event t before using table t (``torch.cuda.current_stream().wait_event(ready[t])``)."""
         import time
 
         t0 = time.perf_counter()
-        par = self.enqueue(tables)
-        if trace is not None: trace.append(("peer enqueue (hist+gather+plan+scatter+barrier)", time.perf_counter() - t0)); t0 = time.perf_counter()
+        if self.step and self.status_h[0] != 0:
+            raise RuntimeError("peer exchange: a peer did not signal within the timeout in an earlier step")
+        self._laps = [] if trace is not None else None
+        par, events = self.enqueue(tables, overlap=ready is not None)
+        laps, self._laps = self._laps, None
+        if trace is not None: trace.append(("peer enqueue (hist+publish+plan+scatter+signal+wait)", time.perf_counter() - t0)); t0 = time.perf_counter()
         out, need = self.collect(par)
         if out is None:  # the same numbers on every rank, so every rank takes this branch together
+            if events is not None:
+                for ev in events:
+                    ev.synchronize()
             self._grow(need)
-            par = self.enqueue(tables)
+            par, events = self.enqueue(tables, overlap=ready is not None)
             out, need = self.collect(par)
             if out is None:
                 raise RuntimeError("peer exchange: arena still too small after growing")
+        main = torch.cuda.current_stream(self.dev)
+        if ready is not None:
+            if events is None:  # nccl sync: everything ran on the caller's stream
+                ev = torch.cuda.Event()
+                ev.record(main)
+                events = [ev] * self.T
+            ready.extend(events)
+        if self.sync == "flags":  # surfaced by the next step / check() / close(): no host wait here
+            with torch.cuda.device(self.dev):
+                if events is not None:
+                    s0 = self.side[0]
+                    for ev in events:
+                        s0.wait_event(ev)
+                    with torch.cuda.stream(s0):
+                        self.status_h.copy_(self.status, non_blocking=True)
+                else:
+                    self.status_h.copy_(self.status, non_blocking=True)
         if trace is not None:
             torch.cuda.synchronize(self.dev)
             trace.append(("peer wait", time.perf_counter() - t0))
+            if laps and len(laps) >= 2 + self.T:  # device laps (CUDA events), in seconds like the host laps
+                trace.append(("device: histograms+publish+plan (incl. waiting for the peers' histograms)", laps[0].elapsed_time(laps[1]) * 1e-3))
+                for t in range(self.T):
+                    since = laps[1] if (ready is not None or t == 0) else laps[1 + t]
+                    trace.append((f"device: table {t} count+scan+scatter+signal+wait" + (" (own stream, since the plan)" if ready is not None else ""),
+                                  since.elapsed_time(laps[2 + t]) * 1e-3))
         return out, self.owner[: self.nc]
 
 

@@ -114,3 +114,52 @@ def test_peer_layout_matches_bruteforce():
                 assert int(lay["need"][t]) == max(int(g[:, t, :nc][:, owner == d].sum()) for d in range(world))
             assert not lay["overflow"]
         assert pbd.peer_layout(g, 0, [1] * T)["overflow"]
+
+
+def _replicate_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        out = []
+        for even in (False, True):
+            n = 1000 if even else 700 + 300 * rank
+            rng = np.random.default_rng(50 + rank)
+            c = torch.from_numpy(rng.integers(0, 5, n).astype(np.int32))
+            s = torch.from_numpy(rng.integers(0, 10_000, n).astype(np.int32))
+            e = s + 7
+            (ac, as_, ae), base, sizes = pbd.replicate_table(c, s, e)
+            out.append((ac.tolist(), as_.tolist(), ae.tolist(), base, sizes, c.tolist(), s.tolist()))
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_replicate_table():
+    """Every rank gets the whole table in global row order (the replicate-the-indexed-side strategy of SURVEY 8e)."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_replicate_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for k in range(2):
+        r0, r1 = results[0][k], results[1][k]
+        assert r0[:3] == r1[:3]                                   # identical whole table on both ranks
+        assert r0[0] == r0[5] + r1[5] and r0[1] == r0[6] + r1[6]  # = rank 0's slice followed by rank 1's
+        assert r0[3] == 0 and r1[3] == len(r0[5]) and r0[4] == r1[4] == [len(r0[5]), len(r1[5])]
+        assert r0[2] == [x + 7 for x in r0[1]]
+
+
+def test_join_strategy():
+    one = torch.tensor([10_000_000.0]); onev = torch.tensor([1_000_000.0])
+    assert pbd.join_strategy(one, onev, 1) == "shard"
+    assert pbd.join_strategy(one, onev, 8) == "replicate"                      # a single contig cannot be sharded by contig
+    even_p, even_b = torch.full((24,), 4e6), torch.full((24,), 3.75e6)
+    assert pbd.join_strategy(even_p, even_b, 8) == "shard"                     # config 3: 100M x 90M over 24 contigs
+    assert pbd.join_strategy(torch.full((24,), 2e6), torch.full((24,), 2e5), 2) == "replicate"  # tiny indexed side
+    skew = torch.tensor([9e6] + [1e5] * 10)
+    assert pbd.join_strategy(skew, skew / 10, 4) == "replicate"                 # one contig dominates

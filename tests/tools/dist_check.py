@@ -53,6 +53,14 @@ def main():
         for u, v in ((q2, q3), (x2, x3)):
             for col_u, col_v in zip(u, v):
                 assert torch.equal(col_u, col_v), ("peer exchange differs from the NCCL exchange", it)
+    for it in range(3):  # overlapped mode: every table on its own stream, an event per table
+        ready = []
+        (x4, q4), _ = pbd.shard_tables([tuple(lb), tuple(lp)], n_contigs, ready=ready)
+        assert len(ready) == 2
+        for u, v, ev in ((x2, x4, ready[0]), (q2, q4, ready[1])):
+            torch.cuda.current_stream().wait_event(ev)
+            for col_u, col_v in zip(u, v):
+                assert torch.equal(col_u, col_v), ("overlapped peer exchange differs from the NCCL exchange", it)
     kind = pbd.exchange_kind()
     if kind == "peer":  # a second pair of tables, 3x larger on this group: forces a collective arena growth
         big_p = [torch.cat([x, x, x]) for x in lp]
@@ -82,6 +90,20 @@ def main():
         want = np.sort(oa.astype(np.int64) * M + ob.astype(np.int64))
         assert len(got) == len(want) and np.array_equal(got, want), (len(got), len(want))
         print(f"DIST_CHECK_OK world={world} pairs={len(got)} exchange={kind}")
+    # the other strategy (single-contig case): replicate the indexed table, probes stay where they are
+    assert pbd.join_strategy(torch.tensor([1e7]), torch.tensor([1e6]), world) == "replicate"
+    (ac, as_, ae), bbase2, bsizes = pbd.replicate_table(*lb)
+    assert bbase2 == bbase and sum(bsizes) == M and ac.numel() == M
+    assert np.array_equal(ac.cpu().numpy(), bc) and np.array_equal(as_.cpu().numpy(), bs) and np.array_equal(ae.cpu().numpy(), be)
+    ixr = engine.DeviceIndex(ac, as_, ae, n_contigs)
+    ra, rb = ixr.overlap_pairs(*lp, engine.FILTER_STRICT)
+    mine_r = (ra.cpu().numpy().view(np.uint32).astype(np.int64) + pbase) * M + rb.cpu().numpy().view(np.uint32).astype(np.int64)
+    parts = [None] * world
+    dist.all_gather_object(parts, mine_r)
+    if rank == 0:
+        got_r = np.sort(np.concatenate(parts))
+        assert np.array_equal(got_r, want), "replicated-build join differs from the oracle"
+        print(f"DIST_CHECK_REPLICATE_OK world={world} pairs={len(got_r)}")
     dist.barrier()
     pbd.close_peer_exchanges()
     dist.destroy_process_group()
