@@ -286,7 +286,7 @@ def run_sharded(args, world, rank, dev):
     FO = engine.FILTER_STRICT
     nc = world
 
-    overlap = os.environ.get("PBGPU_BENCH_OVERLAP", "0") != "0"
+    overlap = os.environ.get("PBGPU_BENCH_OVERLAP", "1") != "0"
 
     def step(ev=None, trace=None):
         # the indexed table first: its index build overlaps the transfer of the reads (one stream per table)
@@ -331,7 +331,11 @@ def run_sharded(args, world, rank, dev):
     xtrace = []
     step(trace=xtrace)  # one extra, untimed step with host-side laps of the exchange
     t_end = time.perf_counter() + 0.4
-    while len(sampler.lines) < 3 and time.perf_counter() < t_end:  # keep the GPU under the same load until sampled
+    while True:  # keep the GPUs under the same load until sampled; the step is collective, so the ranks decide together
+        more = torch.tensor([1.0 if (len(sampler.lines) < 3 and time.perf_counter() < t_end) else 0.0], device=dev)
+        dist.all_reduce(more, op=dist.ReduceOp.MAX)
+        if float(more.item()) == 0.0:
+            break
         step()
     dist.barrier(); torch.cuda.synchronize()
     clocks = sampler.stop()
@@ -361,9 +365,11 @@ def run_sharded(args, world, rank, dev):
                                "contig exchange + index build + count_overlaps + two-pass pair emit",
                    "pairs_per_step": pairs_all, "l2": "flushed between timed steps (256 MiB write)",
                    "parallelism": (f"contig-sharded x{world}, rows stored straight into their owner's columns over NVLink peer memory "
-                                   "(CUDA IPC arenas; plan + scatter kernels, NCCL only for a histogram all_gather and the closing all_reduce)"
+                                   "(CUDA IPC arenas; owner table + region layout planned on the device; "
+                                   + ("histograms and completion flags also travel through peer memory: no NCCL call in a step)"
+                                      if pbd.exchange_sync() == "flags" else "NCCL for a histogram all_gather and the closing all_reduce)")
                                    if pbd.exchange_kind() == "peer" else f"contig-sharded x{world}, NCCL all-to-all of 16-byte records"),
-                   "exchange": pbd.exchange_kind(),
+                   "exchange": pbd.exchange_kind(), "exchange_sync": pbd.exchange_sync(),
                    "exchange_overlap": ("index build overlaps the reads' transfer (one stream per table; exchange_ms_per_step then "
                                         "includes the index build)" if overlap and pbd.exchange_kind() == "peer" else "none"),
                    "exchange_ms_per_step": float(t[1].item()) / args.steps,

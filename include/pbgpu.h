@@ -167,7 +167,7 @@ PBGPU_API int pbgpu_translate_rows(const uint32_t *d_local, int64_t n, const uin
  * Arena layout: table t at byte 16*sum(cap_rows[<t]); columns contig | start | end | row, each cap_rows[t] x 4 bytes
  * (cap_rows: multiples of 64).  Control block (pbgpu_peer_ctl_bytes, zeroed before the handles are exchanged): flag
  * words written remotely with st.release.sys and polled locally with a bounded spin ($PBGPU_PEER_TIMEOUT_MS, default
- * 20 s: a dead peer becomes status 2 in d_result[3*n_tables] / *d_status, never a hung GPU) and one histogram slot per
+ * 60 s: a dead peer becomes status 2 in d_result[3*n_tables] / *d_status, never a hung GPU) and one histogram slot per
  * source rank.  `step` counts exchange steps from 1 and must be the same on every rank.
  *
  * One step = pbgpu_peer_begin + one pbgpu_peer_table per table:

@@ -684,6 +684,15 @@ def exchange_kind(group=None) -> str:
     return "nccl"
 
 
+def exchange_sync(group=None) -> str:
+    """How the peer exchange of this group synchronises: 'flags' (peer memory), 'nccl' (all_gather + all_reduce), or
+    'n/a' when the rows travel through the NCCL all-to-all."""
+    for (g, _, _), ex in _peer_cache.items():
+        if g == id(group) and ex is not None:
+            return ex.sync
+    return "n/a"
+
+
 def _peer_exchange_for(tables, n_contigs: int, group=None):
     """The cached PeerExchange of (group, n_contigs, #tables), created collectively on first use; None = NCCL path
     (PBGPU_EXCHANGE=nccl, CPU tensors, too many ranks/tables, or the arenas could not be mapped on some rank)."""
