@@ -247,6 +247,41 @@ def translate(local_rows: torch.Tensor, global_of_local: torch.Tensor) -> torch.
     return local_rows
 
 
+def overlap(probe, build, n_contigs: int, filter_op: int, group=None, strategy: Optional[str] = None):
+    """Distributed ``overlap`` in one call: every rank passes its slices of both tables ((contig, start, end) int32 CUDA
+    columns; global row id = position in the concatenation of the slices in rank order) and receives its share of the
+    pair set as (probe_row, build_row) GLOBAL ids (int32 storage of uint32 values, like ``DeviceIndex.overlap_pairs``);
+    the union over ranks is the pair set of the single-GPU join.  ``strategy``: 'shard' (contig owners, ``shard_tables``),
+    'replicate' (``replicate_table`` of the indexed side) or None = ``join_strategy`` on the global histograms.
+    Returns (probe_rows, build_rows, strategy used)."""
+    from . import engine
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if strategy is None:
+        h = torch.stack([contig_histogram(probe[0], n_contigs, group), contig_histogram(build[0], n_contigs, group)])
+        strategy = join_strategy(h[0], h[1], world)
+    if strategy == "replicate":
+        (bc, bs, be), _, _ = replicate_table(*build, group=group)
+        pbase, _ = row_id_base(probe[0].numel(), probe[0].device, group)
+        ix = engine.DeviceIndex(bc, bs, be, n_contigs)
+        a, b = ix.overlap_pairs(*probe, filter_op)
+        ix.close()
+        if pbase:  # int32 storage of uint32 ids: two's-complement addition is the uint32 addition
+            a += pbase - (1 << 32) if pbase >= (1 << 31) else pbase
+        return a, b, strategy
+    if strategy != "shard":
+        raise ValueError(f"unknown strategy {strategy!r}")
+    ready: list = []
+    (x, q), _ = shard_tables([tuple(build), tuple(probe)], n_contigs, group=group, ready=ready)
+    main = torch.cuda.current_stream(probe[0].device)
+    main.wait_event(ready[0])
+    ix = engine.DeviceIndex(x[0], x[1], x[2], n_contigs)
+    main.wait_event(ready[1])
+    a, b = ix.overlap_pairs(q[0], q[1], q[2], filter_op)
+    ix.close()
+    return translate(a, q[3]), translate(b, x[3]), strategy
+
+
 # ------------------------------------------------------------------------------------------------
 # The exchange over NVLink peer memory (csrc/peer.cuh)
 # ------------------------------------------------------------------------------------------------

@@ -104,6 +104,15 @@ def main():
         got_r = np.sort(np.concatenate(parts))
         assert np.array_equal(got_r, want), "replicated-build join differs from the oracle"
         print(f"DIST_CHECK_REPLICATE_OK world={world} pairs={len(got_r)}")
+    # the one-call form, both strategies and the automatic choice
+    for strat in ("shard", "replicate", None):
+        oa_, ob_, used = pbd.overlap(tuple(lp), tuple(lb), n_contigs, engine.FILTER_STRICT, strategy=strat)
+        mine_o = oa_.cpu().numpy().view(np.uint32).astype(np.int64) * M + ob_.cpu().numpy().view(np.uint32).astype(np.int64)
+        parts = [None] * world
+        dist.all_gather_object(parts, mine_o)
+        if rank == 0:
+            assert np.array_equal(np.sort(np.concatenate(parts)), want), ("dist.overlap differs from the oracle", strat, used)
+            print(f"DIST_CHECK_ONE_CALL_OK strategy={strat} used={used}")
     dist.barrier()
     pbd.close_peer_exchanges()
     dist.destroy_process_group()
