@@ -39,6 +39,7 @@
 
 #define PBO_API __attribute__((visibility("default")))
 
+struct pbo_node { int32_t st, en, left_max, right_max; };  /* max end over the left / right subtree of this slot */
 typedef struct {
   int64_t m;          /* indexed (build) rows kept: contig code >= 0                          */
   int32_t n_contigs;  /* contig codes are 0 .. n_contigs-1                                   */
@@ -47,6 +48,8 @@ typedef struct {
   int32_t *en;        /* ends in the same order                                               */
   uint32_t *row;      /* original row ids in the same order                                   */
   int32_t *sub_max;   /* augmented key: max end over the implicit subtree rooted at this slot */
+  struct pbo_node *node; /* (start, end, max end of the left subtree, of the right subtree) of every slot side by side:
+                          * one cache line per visited node, and a child that cannot hit is never loaded */
   int32_t *en_sorted; /* ends sorted by (contig, end, start, row)                             */
   uint32_t *en_pos;   /* position in st/en/row order of each en_sorted entry                  */
 } pbo_index;
@@ -91,7 +94,19 @@ static int32_t build_aug(const int32_t *en, int32_t *sub_max, int64_t lo, int64_
 PBO_API void pbo_index_free(pbo_index *ix) {
   if (!ix) return;
   free(ix->seg); free(ix->st); free(ix->en); free(ix->row);
-  free(ix->sub_max); free(ix->en_sorted); free(ix->en_pos); free(ix);
+  free(ix->sub_max); free(ix->node); free(ix->en_sorted); free(ix->en_pos); free(ix);
+}
+
+/* node[mid] of the implicit tree over [lo,hi): the children are the midpoints of [lo,mid) and [mid+1,hi) */
+static void fill_nodes(pbo_index *ix, int64_t lo, int64_t hi) {
+  if (lo >= hi) return;
+  const int64_t mid = lo + ((hi - lo) >> 1);
+  struct pbo_node *nd = &ix->node[mid];
+  nd->st = ix->st[mid]; nd->en = ix->en[mid];
+  nd->left_max = lo < mid ? ix->sub_max[lo + ((mid - lo) >> 1)] : INT32_MIN;
+  nd->right_max = mid + 1 < hi ? ix->sub_max[mid + 1 + ((hi - mid - 1) >> 1)] : INT32_MIN;
+  fill_nodes(ix, lo, mid);
+  fill_nodes(ix, mid + 1, hi);
 }
 
 PBO_API pbo_index *pbo_index_build(const int32_t *c, const int32_t *s, const int32_t *e,
@@ -117,6 +132,8 @@ PBO_API pbo_index *pbo_index_build(const int32_t *c, const int32_t *s, const int
   }
   for (int32_t k = 0; k < n_contigs; ++k) ix->seg[k + 1] += ix->seg[k];
   for (int32_t k = 0; k < n_contigs; ++k) build_aug(ix->en, ix->sub_max, ix->seg[k], ix->seg[k + 1]);
+  ix->node = (struct pbo_node *)malloc(sizeof(struct pbo_node) * mm);
+  for (int32_t k = 0; k < n_contigs; ++k) fill_nodes(ix, ix->seg[k], ix->seg[k + 1]);
   /* end order: stable sort of the start-ordered records by (contig, end) => ties keep (start,row) order */
   for (int64_t i = 0; i < m; ++i) {
     rec[i].key = (rec[i].key & 0xffffffff00000000ull) | (rec[i].b ^ 0x80000000u);
@@ -134,31 +151,47 @@ static inline int hit(int strict, int32_t as, int32_t ae, int32_t bs, int32_t be
 
 /* Tree query: visit every indexed interval of the contig slice that satisfies the predicate,
  * in (start,row) order.  cb_pos receives positions in sorted order; returns count.          */
+#define PBO_LEAF 16
 typedef struct { int64_t lo, hi; } pbo_span;
 static int64_t tree_query(const pbo_index *ix, int64_t lo0, int64_t hi0, int strict,
                           int32_t qs, int32_t qe, uint32_t *out_pos, int64_t cap) {
-  /* explicit stack; depth <= 64.  In-order traversal so results come out start-sorted. */
+  /* explicit stack; depth <= 64.  In-order traversal so results come out start-sorted.  A node carries the max end of
+   * each child's subtree, so a child that cannot hit is pruned without being loaded; and, like COITrees, the bottom of
+   * the tree is not descended node by node: a subtree of at most PBO_LEAF slots is a contiguous, start-sorted run of
+   * the node array and is scanned linearly. */
+  const struct pbo_node *nd = ix->node;
   struct { int64_t lo, hi; int stage; } stk[70];
   int sp = 0; int64_t n = 0;
+  if (lo0 >= hi0) return 0;
+  {
+    const int32_t mx = ix->sub_max[lo0 + ((hi0 - lo0) >> 1)];
+    if (strict ? (mx <= qs) : (mx < qs)) return 0;
+  }
   stk[sp].lo = lo0; stk[sp].hi = hi0; stk[sp].stage = 0; ++sp;
   while (sp > 0) {
-    int64_t lo = stk[sp - 1].lo, hi = stk[sp - 1].hi; int stage = stk[sp - 1].stage;
-    if (lo >= hi) { --sp; continue; }
-    int64_t mid = lo + ((hi - lo) >> 1);
+    const int64_t lo = stk[sp - 1].lo, hi = stk[sp - 1].hi; const int stage = stk[sp - 1].stage;
+    if (hi - lo <= PBO_LEAF) {   /* whole subtree (already known to reach past the query start): linear scan */
+      --sp;
+      for (int64_t j = lo; j < hi; ++j) {
+        const int32_t bs = nd[j].st;
+        if (strict ? (bs >= qe) : (bs > qe)) break;   /* sorted by start: nothing further can hit */
+        if (hit(strict, qs, qe, bs, nd[j].en)) { if (out_pos && n < cap) out_pos[n] = (uint32_t)j; ++n; }
+      }
+      continue;
+    }
+    const int64_t mid = lo + ((hi - lo) >> 1);
+    const struct pbo_node x = nd[mid];
     if (stage == 0) {
-      /* prune: nothing in this subtree ends after (at) the query start */
-      int32_t mx = ix->sub_max[mid];
-      if (strict ? (mx <= qs) : (mx < qs)) { --sp; continue; }
       stk[sp - 1].stage = 1;
-      stk[sp].lo = lo; stk[sp].hi = mid; stk[sp].stage = 0; ++sp;   /* left subtree first */
+      /* left subtree first, unless nothing in it ends after (at) the query start */
+      if (strict ? (x.left_max > qs) : (x.left_max >= qs)) { stk[sp].lo = lo; stk[sp].hi = mid; stk[sp].stage = 0; ++sp; }
       continue;
     }
     --sp;
     /* node itself, then right subtree, only if node start is still before the query end */
-    int32_t bs = ix->st[mid];
-    if (strict ? (bs < qe) : (bs <= qe)) {
-      if (hit(strict, qs, qe, bs, ix->en[mid])) { if (out_pos && n < cap) out_pos[n] = (uint32_t)mid; ++n; }
-      stk[sp].lo = mid + 1; stk[sp].hi = hi; stk[sp].stage = 0; ++sp;
+    if (strict ? (x.st < qe) : (x.st <= qe)) {
+      if (hit(strict, qs, qe, x.st, x.en)) { if (out_pos && n < cap) out_pos[n] = (uint32_t)mid; ++n; }
+      if (strict ? (x.right_max > qs) : (x.right_max >= qs)) { stk[sp].lo = mid + 1; stk[sp].hi = hi; stk[sp].stage = 0; ++sp; }
     }
   }
   return n;
