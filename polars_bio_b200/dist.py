@@ -219,7 +219,7 @@ def join_strategy(hist_probe: torch.Tensor, hist_build: torch.Tensor, world: int
     """'replicate' (``replicate_table`` of the indexed table, probes stay where they are) or 'shard' (``shard_tables``
     by contig owner), from the global per-contig histograms: replicate when the contigs cannot keep every rank busy
     (fewer non-empty contigs than ranks, or the largest one outweighs an even share by 2x), or when copying the indexed
-    table to every rank moves fewer rows than sending both tables to their owners."""
+    table to every rank moves fewer rows than sending both tables to their owners and the whole index stays L2-sized."""
     if world <= 1:
         return "shard"
     hp, hb = hist_probe.to("cpu", torch.float64), hist_build.to("cpu", torch.float64)
@@ -232,7 +232,9 @@ def join_strategy(hist_probe: torch.Tensor, hist_build: torch.Tensor, world: int
         return "replicate"
     moved_shard = total * (world - 1) / world            # rows crossing links, all ranks together
     moved_replicate = float(hb.sum()) * (world - 1)
-    return "replicate" if moved_replicate < moved_shard else "shard"
+    # a replicated index is world x larger than a shard's: only while its 32-byte-per-row rank directory still fits the
+    # 126 MB L2 (beyond that every probe costs a DRAM sector: DESIGN.md section 6, config 3)
+    return "replicate" if moved_replicate < moved_shard and float(hb.sum()) <= 3.0e6 else "shard"
 
 
 def translate(local_rows: torch.Tensor, global_of_local: torch.Tensor) -> torch.Tensor:

@@ -160,6 +160,7 @@ def test_join_strategy():
     assert pbd.join_strategy(one, onev, 8) == "replicate"                      # a single contig cannot be sharded by contig
     even_p, even_b = torch.full((24,), 4e6), torch.full((24,), 3.75e6)
     assert pbd.join_strategy(even_p, even_b, 8) == "shard"                     # config 3: 100M x 90M over 24 contigs
-    assert pbd.join_strategy(torch.full((24,), 2e6), torch.full((24,), 2e5), 2) == "replicate"  # tiny indexed side
+    assert pbd.join_strategy(torch.full((24,), 2e6), torch.full((24,), 1e5), 2) == "replicate"  # tiny indexed side
+    assert pbd.join_strategy(torch.full((24,), 2e6), torch.full((24,), 2e5), 2) == "shard"      # ... but not beyond L2
     skew = torch.tensor([9e6] + [1e5] * 10)
     assert pbd.join_strategy(skew, skew / 10, 4) == "replicate"                 # one contig dominates
