@@ -48,3 +48,33 @@ def test_product_path_does_not_import_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", txt, re.M), f
                 assert "liboracle" not in txt, f
+
+
+def test_ctypes_mirrors_match_the_header_layout(tmp_path):
+    """sizeof / offsetof of every struct that crosses the ABI, as gcc lays it out from include/pbgpu.h, against the
+    ctypes mirrors in polars_bio_b200/_native.py (a drifted mirror would corrupt arguments silently)."""
+    import subprocess
+
+    from polars_bio_b200 import _native
+
+    structs = {"PbRangeOptions": _native.PbRangeOptions, "pbgpu_peer_step": _native.PbPeerStep, "pbgpu_stage_times": _native.StageTimes}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "pbgpu.h"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} sizeof %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.run([cc, "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    seen = 0
+    for line in out.splitlines():
+        cname, field, value = line.split()
+        cls = structs[cname]
+        want = ctypes.sizeof(cls) if field == "sizeof" else getattr(cls, field).offset
+        assert int(value) == want, (cname, field, int(value), want)
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in structs.values())
