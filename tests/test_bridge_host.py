@@ -29,7 +29,8 @@ def lib(tmp_path_factory):
     cpp.write_text(src)
     so = d / "libbridge_host.so"
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    r = subprocess.run([cxx, "-std=c++17", "-O1", "-fPIC", "-shared", "-I", HARNESS, "-I", os.path.join(ROOT, "include"),
+    extra = os.environ.get("PB_BRIDGE_CXXFLAGS", "").split()  # e.g. -fsanitize=address,undefined (scripts/bridge_sanitize.sh)
+    r = subprocess.run([cxx, "-std=c++17", "-O1", *extra, "-fPIC", "-shared", "-I", HARNESS, "-I", os.path.join(ROOT, "include"),
                         "-I", os.path.join(ROOT, "polars_bio_b200", "csrc"), "-o", str(so), str(cpp), "-lpthread"],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
@@ -158,3 +159,71 @@ def test_key_encoding_streaming_stores_all_alignments(lib):
         assert names.setdefault(nm, c) == c
     assert len(set(names.values())) == len(names) == 4
     assert np.array_equal(keys[:, 1], start) and np.array_equal(keys[:, 2], end64.astype(np.int32))
+
+
+def _random_column(rng, n, kind):
+    null = rng.random(n) < rng.choice([0.0, 0.1, 0.6])
+    def mask(vals):
+        return [None if z else v for v, z in zip(vals, null)]
+    if kind == "i8":
+        return pa.array(mask(rng.integers(-128, 127, n).tolist()), pa.int8())
+    if kind == "u16":
+        return pa.array(mask(rng.integers(0, 65535, n).tolist()), pa.uint16())
+    if kind == "i64":
+        return pa.array(mask(rng.integers(-2**62, 2**62, n).tolist()), pa.int64())
+    if kind == "f32":
+        return pa.array(mask(rng.random(n).astype(np.float32).tolist()), pa.float32())
+    if kind == "bool":
+        return pa.array(mask((rng.random(n) < 0.5).tolist()), pa.bool_())
+    if kind == "date":
+        return pa.array(mask(rng.integers(0, 20000, n).tolist()), pa.date32())
+    words = ["", "a", "chrUn_KI270742v1", "x" * 40, "naïve-ütf8", "t\t\n", "0123456789ab", "0123456789abc"]
+    vals = mask([words[i] for i in rng.integers(0, len(words), n)])
+    if kind == "utf8":
+        return pa.array(vals, pa.string())
+    if kind == "large_utf8":
+        return pa.array(vals, pa.large_string())
+    if kind == "view":
+        return pa.array(vals, pa.string_view())
+    if kind == "binary":
+        return pa.array([None if v is None else v.encode() for v in vals], pa.binary())
+    if kind == "dict":
+        return pa.array(vals, pa.string()).dictionary_encode()
+    raise AssertionError(kind)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_gather_random_tables_equal_pyarrow_take(lib, seed):
+    """Materialisation of arbitrary result rows (any supported payload type, any null density, chunked and sliced
+    inputs, empty tables, missing partners) == pyarrow's own take; utf8_view and dictionary columns come back as large_utf8."""
+    rng = np.random.default_rng(1000 + seed)
+    kinds = ["i8", "u16", "i64", "f32", "bool", "date", "utf8", "large_utf8", "view", "binary", "dict"]
+    n = int(rng.choice([0, 1, 7, 8, 9, 63, 64, 65, 1000, 20_000]))
+    chosen = list(rng.choice(kinds, size=int(rng.integers(1, 6)), replace=False))
+    cols = {"chrom": pa.array([None if z else f"chr{c}" for c, z in zip(rng.integers(0, 4, n), rng.random(n) < 0.05)], pa.string()),
+            "start": pa.array(rng.integers(0, 10**6, n), pa.int32()), "end": pa.array(rng.integers(0, 10**6, n), pa.int64())}
+    for j, k in enumerate(chosen):
+        cols[f"p{j}_{k}"] = _random_column(rng, n, k)
+    t = pa.table(cols)
+    if n > 4:  # uneven chunks, the first one sliced off a larger array (non-zero offsets)
+        cuts = sorted(set([0, n] + rng.integers(1, n, 3).tolist()))
+        pad = pa.concat_tables([t.slice(0, 3), t])
+        t = pa.concat_tables([pad.slice(3 + lo, hi - lo) for lo, hi in zip(cuts[:-1], cuts[1:])])
+    m = int(rng.choice([0, 1, 5, 4097, 40_000]))
+    rows = rng.integers(0, max(n, 1), m).astype(np.uint32) if n else np.full(m, 0xFFFFFFFF, np.uint32)
+    if m:
+        rows[rng.random(m) < 0.1] = 0xFFFFFFFF
+    out, _ = _roundtrip(lib, t, rows)
+    assert out.num_rows == m and out.column_names == t.column_names
+    idx = pa.array([None if r == 0xFFFFFFFF else int(r) for r in rows], pa.int64())
+    want = t.combine_chunks().take(idx) if n else pa.table({c: pa.nulls(m, t.schema.field(c).type) for c in t.column_names})
+    for name in t.column_names:
+        got_c, want_c = out[name].combine_chunks(), want[name].combine_chunks()
+        if pa.types.is_dictionary(want_c.type) or pa.types.is_string_view(want_c.type):  # decoded / flattened to large_utf8
+            if pa.types.is_dictionary(want_c.type):
+                want_c = want_c.dictionary_decode()
+            assert got_c.type == pa.large_string(), (name, got_c.type)
+            assert got_c.to_pylist() == want_c.to_pylist(), name
+        else:
+            assert got_c.type == want_c.type, (name, got_c.type, want_c.type)
+            assert got_c.to_pylist() == want_c.to_pylist(), name
