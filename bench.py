@@ -310,6 +310,24 @@ def run_sharded(args, world, rank, dev):
     # one nvidia-smi sampling period
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
     sampler.start()
+    # The first step decides, on all ranks together, whether the peer-memory exchange works on this box (a rank that
+    # cannot reach a peer's flags gets an error after the bounded spin, not a hang); if it fails anywhere, every rank
+    # switches to the NCCL all-to-all and the line below says so ("exchange": "nccl").
+    err = None
+    try:
+        cnt, a, b = step()
+        torch.cuda.synchronize()
+    except Exception as e:  # noqa: BLE001 -- re-raised below unless the NCCL exchange can take over
+        err = e
+    ok = torch.tensor([0.0 if err is not None else 1.0], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if float(ok.item()) == 0.0:
+        if pbd.exchange_kind() != "peer":
+            raise err if err is not None else RuntimeError("the first step failed on another rank")
+        if rank == 0:
+            sys.stderr.write(f"bench: peer-memory exchange failed in the first step ({err!r}); falling back to the NCCL all-to-all\n")
+        os.environ["PBGPU_EXCHANGE"] = "nccl"
+        pbd.abandon_peer_exchanges()
     for _ in range(max(args.warmup, 3)):
         cnt, a, b = step()
     pairs = a.numel()

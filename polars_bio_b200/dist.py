@@ -760,6 +760,13 @@ def _peer_exchange_for(tables, n_contigs: int, group=None):
     return ex
 
 
+def abandon_peer_exchanges():
+    """Forget the cached exchanges WITHOUT the collective tear-down (their arenas stay allocated until the process
+    ends) and never try again: for a caller that saw the peer path fail and continues with PBGPU_EXCHANGE=nccl."""
+    for key in list(_peer_cache):
+        _peer_cache[key] = None
+
+
 def close_peer_exchanges():
     """Free the cached arenas (collective).  Call before ``destroy_process_group``."""
     for ex in _peer_cache.values():
