@@ -78,6 +78,9 @@ typedef struct pbgpu_index pbgpu_index;
 PBGPU_API int pbgpu_index_build(const int32_t *d_contig, const int32_t *d_start, const int32_t *d_end,
                                 int64_t m, int32_t n_contigs, void *stream, pbgpu_index **out);
 PBGPU_API void pbgpu_index_free(pbgpu_index *ix);
+/* Stream-ordered release: the index memory becomes reusable only after everything enqueued on `stream` so far (the
+ * kernels that read the index) has run.  The right call for users of non-blocking streams. */
+PBGPU_API void pbgpu_index_free_async(pbgpu_index *ix, void *stream);
 PBGPU_API int64_t pbgpu_index_rows(const pbgpu_index *ix);     /* rows kept (non-null keys)   */
 PBGPU_API size_t pbgpu_index_bytes(const pbgpu_index *ix);     /* HBM held by the index       */
 

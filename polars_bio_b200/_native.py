@@ -85,6 +85,8 @@ def lib() -> ctypes.CDLL:
     L.pbgpu_index_build.argtypes = [vp, vp, vp, i64, i32, vp, ctypes.POINTER(vp)]
     L.pbgpu_index_free.argtypes = [vp]
     L.pbgpu_index_free.restype = None
+    L.pbgpu_index_free_async.argtypes = [vp, vp]
+    L.pbgpu_index_free_async.restype = None
     L.pbgpu_index_rows.argtypes = [vp]
     L.pbgpu_index_rows.restype = i64
     L.pbgpu_index_bytes.argtypes = [vp]

@@ -323,14 +323,19 @@ void pbgpu_index_free(pbgpu_index *ix) {
   delete ix;
 }
 
-// internal: release an index in stream order on `s` (the stream its last reader was enqueued on)
+// release an index in stream order on `s` (the stream its last reader was enqueued on)
 static void index_free_on(pbgpu_index *ix, cudaStream_t s) {
   if (!ix) return;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (cur != ix->device) cudaSetDevice(ix->device);
   dev_free(ix->slab, s);
   dev_free(ix->slab2, s);
   dev_free(ix->slab_n, s);
+  if (cur != ix->device) cudaSetDevice(cur);
   delete ix;
 }
+void pbgpu_index_free_async(pbgpu_index *ix, void *stream) { index_free_on(ix, (cudaStream_t)stream); }
 
 int64_t pbgpu_index_rows(const pbgpu_index *ix) { return ix ? ix->m : 0; }
 size_t pbgpu_index_bytes(const pbgpu_index *ix) { return ix ? ix->bytes : 0; }

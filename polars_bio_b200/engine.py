@@ -53,8 +53,17 @@ class DeviceIndex:
                                             _stream_ptr(self.device), ctypes.byref(self._h)))
 
     def close(self):
+        """Stream-ordered release on the CURRENT stream of the index's device: the memory is reused only after the
+        kernels enqueued there so far (the ones reading this index) have run -- also on non-blocking side streams."""
         if getattr(self, "_h", None) is not None and self._h.value:
-            self._L.pbgpu_index_free(self._h)
+            try:
+                sp = _stream_ptr(self.device)
+            except Exception:  # interpreter shutdown: torch may be gone
+                sp = None
+            if sp is None:
+                self._L.pbgpu_index_free(self._h)
+            else:
+                self._L.pbgpu_index_free_async(self._h, sp)
             self._h = ctypes.c_void_p()
 
     __del__ = close
