@@ -25,6 +25,8 @@
 //                     probes read the record of a.end's bucket too; crowded buckets (more than 12 keys) keep the
 //                     rank range instead of keys and are searched.
 #pragma once
+#include <mutex>
+
 #include "common.cuh"
 #include "radix_sort.cuh"
 #include "scan.cuh"
@@ -70,6 +72,15 @@ struct pbgpu_index {
   pbgpu::JRec *jdir = nullptr;
   uint2 *er = nullptr;  // (end, row) interleaved in start order: one 8-byte load per emitted pair in pass 2
   void *slab = nullptr, *slab2 = nullptr, *slab_n = nullptr;  // stream-ordered allocations backing every array above
+  // Round 2: with nested intervals the ends are no longer sorted at build time.  `ge` then holds the global-axis ends
+  // grouped by directory bucket (ge_sorted = 0: unordered inside a bucket) and en_sorted / en_pos stay NULL until a
+  // caller needs the end order (nearest): built once, on that call's stream, into slab_e (ensure_end_order, pbgpu.cu).
+  int ge_sorted = 1;
+  int32_t min_end = 0, max_end = 0;
+  void *slab_e = nullptr;
+  cudaEvent_t end_ready = nullptr;
+  cudaStream_t end_stream = nullptr;
+  std::mutex mu;
   // without nested intervals pmax and en_sorted alias `en` and en_pos is NULL (= identity)
   size_t bytes = 0;
 };
@@ -92,10 +103,11 @@ struct IndexView {
   const uint32_t *__restrict__ en_pos;
   int32_t n_contigs;
   int has_inverted;
+  int ge_sorted;  // 0: the ends of a crowded directory record are counted one by one
 };
 
 inline IndexView view_of(const pbgpu_index *ix) {
-  return IndexView{ix->cmap, ix->gs, ix->ge, ix->jdir, ix->er, ix->shift, ix->seg, ix->st, ix->en, ix->pmax, ix->en_sorted, ix->row, ix->en_pos, ix->n_contigs, ix->has_inverted};
+  return IndexView{ix->cmap, ix->gs, ix->ge, ix->jdir, ix->er, ix->shift, ix->seg, ix->st, ix->en, ix->pmax, ix->en_sorted, ix->row, ix->en_pos, ix->n_contigs, ix->has_inverted, ix->ge_sorted};
 }
 
 struct BuildStats {  // device-side reduction target
@@ -492,6 +504,192 @@ __global__ void __launch_bounds__(256) jdir_pack_kernel(const uint32_t *__restri
     }
   }
   dir[b] = r;
+}
+
+// ---- round 2: no end sort on the fast path -----------------------------------------------------------------------
+// contig of sorted position i: the largest c with seg[c] <= i < seg[c+1] (empty contigs have seg[c] == seg[c+1])
+__device__ __forceinline__ int32_t contig_of_pos(const int32_t *__restrict__ seg, int32_t n_contigs, int64_t i) {
+  int32_t lo = 0, hi = n_contigs;  // first c with seg[c+1] > i
+  while (lo < hi) { const int32_t mid = lo + ((hi - lo) >> 1); if ((int64_t)__ldg(seg + mid + 1) <= i) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+
+// Running maximum of `en` inside every contig in ONE pass (decoupled look-back over 2048-row tiles; replaces key
+// construction + three-kernel scan + unpack: 56 -> 8 bytes per row).  The scanned value is contig << 32 | biased end:
+// the contig never decreases along the sorted rows, so the running maximum of that word restarts by itself at every
+// contig boundary.  Status word: 2 flag bits | 62-bit value (contig codes are below 2^30).
+constexpr int kPmThreads = 256, kPmItems = 8, kPmTile = kPmThreads * kPmItems;
+__global__ void __launch_bounds__(kPmThreads) pmax_lookback_kernel(const int32_t *__restrict__ seg, int32_t n_contigs,
+                                                                   const int32_t *__restrict__ en, int64_t m, int32_t *__restrict__ pmax,
+                                                                   unsigned long long *status /*[tiles], zeroed*/, unsigned int *ticket /*zeroed*/) {
+  constexpr unsigned long long kAgg = 1ull << 62, kPre = 2ull << 62, kMask = (1ull << 62) - 1ull;
+  __shared__ unsigned long long wt[kPmThreads / 32 + 1];
+  __shared__ unsigned long long prefix_s;
+  __shared__ unsigned int tile_s;
+  if (threadIdx.x == 0) tile_s = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const unsigned int tile = tile_s;
+  const int64_t i0 = (int64_t)tile * kPmTile + (int64_t)threadIdx.x * kPmItems;
+  unsigned long long v[kPmItems];
+  unsigned long long acc = 0ull;
+  if (i0 < m) {
+    int32_t c = contig_of_pos(seg, n_contigs, i0);
+    int64_t next = __ldg(seg + c + 1);
+    int32_t e[kPmItems];
+    if (i0 + kPmItems <= m) {
+      const int4 a = *reinterpret_cast<const int4 *>(en + i0), b = *reinterpret_cast<const int4 *>(en + i0 + 4);
+      e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w; e[4] = b.x; e[5] = b.y; e[6] = b.z; e[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < kPmItems; ++j) e[j] = i0 + j < m ? en[i0 + j] : INT32_MIN;
+    }
+#pragma unroll
+    for (int j = 0; j < kPmItems; ++j) {
+      const int64_t i = i0 + j;
+      while (i >= next && c + 1 < n_contigs) { ++c; next = __ldg(seg + c + 1); }
+      const unsigned long long w = i < m ? (((unsigned long long)(uint32_t)c << 32) | ((uint32_t)e[j] ^ 0x80000000u)) : 0ull;
+      acc = acc > w ? acc : w;
+      v[j] = acc;  // inclusive running max inside the thread
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < kPmItems; ++j) v[j] = 0ull;
+  }
+  const unsigned long long excl_thread = block_exclusive<MaxU64, kPmThreads>(acc, wt);
+  const unsigned long long total = wt[kPmThreads / 32];
+  if (threadIdx.x < 32) {  // warp 0: publish, look back
+    const int lane = threadIdx.x;
+    unsigned long long excl = 0ull;
+    if (tile == 0) {
+      if (lane == 0) st_volatile_u64(status, total | kPre);
+    } else {
+      if (lane == 0) st_volatile_u64(status + tile, total | kAgg);
+      for (long long top = (long long)tile - 1;; top -= 32) {
+        const long long idx = top - lane;
+        unsigned long long w = kPre;  // below tile 0: an empty prefix ends the walk
+        if (idx >= 0) { do { w = ld_volatile_u64(status + idx); } while ((w >> 62) == 0ull); }
+        const unsigned pre = __ballot_sync(0xffffffffu, (w >> 62) == 2ull);
+        const int first = pre ? __ffs(pre) - 1 : 31;
+        unsigned long long x = lane <= first ? (w & kMask) : 0ull;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, x, d); x = x > o ? x : o; }
+        excl = excl > x ? excl : x;
+        if (pre) break;
+      }
+      if (lane == 0) st_volatile_u64(status + tile, (excl > total ? excl : total) | kPre);
+    }
+    if (lane == 0) prefix_s = excl;
+  }
+  __syncthreads();
+  if (i0 >= m) return;
+  unsigned long long before = prefix_s;
+  before = before > excl_thread ? before : excl_thread;
+  int32_t o[kPmItems];
+#pragma unroll
+  for (int j = 0; j < kPmItems; ++j) {
+    const unsigned long long w = v[j] > before ? v[j] : before;
+    o[j] = (int32_t)((uint32_t)w ^ 0x80000000u);
+  }
+  if (i0 + kPmItems <= m) {
+    *reinterpret_cast<int4 *>(pmax + i0) = make_int4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<int4 *>(pmax + i0 + 4) = make_int4(o[4], o[5], o[6], o[7]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < kPmItems; ++j) if (i0 + j < m) pmax[i0 + j] = o[j];
+  }
+}
+
+// Directory over an index with nested intervals WITHOUT sorting the ends: the record of bucket b needs (1) the number
+// of ends below the bucket (rank), (2) the ends inside it -- as a SET: the packed compare counts fields below a
+// threshold whatever their order.  So the ends only have to be grouped by bucket: counting sort with the buckets as
+// bins.  jdir_mark_nested_kernel: global coordinates of both ends of every row (gs in start order, the end's coordinate
+// into a scratch column), start ranks of the buckets by run filling (as jdir_mark_kernel), and one atomic per row on
+// the bucket counter of its end (rows arrive in start order, so the counters touched by a warp are neighbours);
+// an exclusive scan turns the counters into cursors; jdir_place_ends_kernel drops every end at its bucket's cursor.
+// Afterwards cursor[b] = number of ends below bucket b+1.
+__global__ void __launch_bounds__(256) jdir_mark_nested_kernel(const uint64_t *__restrict__ skeys, int pos_bits, const int32_t *__restrict__ st,
+                                                               const int32_t *__restrict__ en, int64_t m, const ContigMap *__restrict__ cmap,
+                                                               int shift, uint32_t n_buckets, uint32_t *__restrict__ gs,
+                                                               uint32_t *__restrict__ ge_tmp, uint32_t *__restrict__ rank_s,
+                                                               uint32_t *__restrict__ ecnt) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // no early return: the warp fills runs together
+  const bool ok = i < m;
+  long long s_prev = -1, s_cur = -1;
+  if (ok) {
+    const ContigMap cm = cmap[skeys[i] >> pos_bits];
+    const uint32_t g_s = cm.off + (uint32_t)((long long)__ldg(st + i) - cm.lo_m1);
+    const uint32_t g_e = cm.off + (uint32_t)((long long)__ldg(en + i) - cm.lo_m1);
+    gs[i] = g_s;
+    ge_tmp[i] = g_e;
+    atomicAdd(ecnt + (g_e >> shift), 1u);
+    s_cur = (long long)(g_s >> shift);
+    if (i > 0) s_prev = (long long)(global_coord_of(skeys, pos_bits, st, i - 1, cmap) >> shift);
+  }
+  jdir_fill_run(rank_s, s_prev + 1, s_cur, (uint32_t)i, ok);
+  jdir_fill_run(rank_s, s_cur + 1, (long long)n_buckets, (uint32_t)m, i == m - 1);
+}
+__global__ void __launch_bounds__(256) jdir_place_ends_kernel(const uint32_t *__restrict__ ge_tmp, int64_t m, int shift,
+                                                              uint32_t *__restrict__ cursor, uint32_t *__restrict__ ge) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const uint32_t g = ge_tmp[i];
+  ge[atomicAdd(cursor + (g >> shift), 1u)] = g;
+}
+// One thread per record, both kinds of index.  rank_s[b] = starts below bucket b; the ends of bucket b are
+// ge[e_lo, e_hi) with  e_lo = ENDS_BY_CURSOR ? cursor[b-1] : rank_e[b],  e_hi = ENDS_BY_CURSOR ? cursor[b] : rank_e[b+1]
+// (rank arrays have n_buckets + 1 entries; the window of the last records is clamped).  No counting loops: the window
+// sizes are rank differences.  max_crowded_ends: largest number of ends in a crowded record (the nested build sorts
+// nothing inside a bucket; probes count linearly there, so the host wants to know how bad it can get).
+template <bool ENDS_BY_CURSOR>
+__global__ void __launch_bounds__(256) jdir_pack2_kernel(const uint32_t *__restrict__ gs, const uint32_t *__restrict__ ge, int64_t m,
+                                                         int shift, uint32_t n_buckets, const uint32_t *__restrict__ rank_s,
+                                                         const uint32_t *__restrict__ rank_e, JRec *__restrict__ dir,
+                                                         unsigned int *__restrict__ max_crowded_ends) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > n_buckets) return;
+  const uint32_t mm = (uint32_t)m;
+  const uint32_t base_s = rank_s[b];
+  const uint32_t top_s = b + 2 <= n_buckets ? rank_s[b + 2] : mm;
+  uint32_t base_e, top_e;
+  if (ENDS_BY_CURSOR) { base_e = b ? rank_e[b - 1] : 0u; top_e = rank_e[b]; }
+  else { base_e = rank_e[b]; top_e = b + 1 <= n_buckets ? rank_e[b + 1] : mm; }
+  const uint32_t ns = top_s - base_s, ne = top_e - base_e;
+  const uint32_t lo32 = b << shift;
+  JRec r;
+  if (ns + ne > (uint32_t)kJKeys) {  // crowded: keep the rank ranges
+    r.w[0] = base_s | 0x80000000u;
+    r.w[1] = base_e;
+    r.w[2] = top_s;
+    r.w[3] = top_e;
+    r.w[4] = r.w[5] = r.w[6] = r.w[7] = 0x7FFF7FFFu;
+    if (max_crowded_ends && ne > 1) atomicMax(max_crowded_ends, ne);
+  } else {
+    r.w[0] = base_s;
+    r.w[1] = base_e - ns;
+    uint32_t f[kJKeys];
+#pragma unroll
+    for (int k = 0; k < kJKeys; ++k) {
+      uint32_t v = 0x7FFFu;
+      if ((uint32_t)k < ns) v = __ldg(gs + base_s + k) - lo32;
+      else if ((uint32_t)k < ns + ne) v = 0x4000u | (__ldg(ge + base_e + ((uint32_t)k - ns)) - lo32);
+      f[k] = v;
+    }
+#pragma unroll
+    for (int k = 0; k < kJKeys / 2; ++k) r.w[2 + k] = f[2 * k] | (f[2 * k + 1] << 16);
+  }
+  dir[b] = r;
+}
+
+// (contig | end) sort keys + start-order positions for the LAZY end order (nearest, generic kernels); the contig comes
+// from the segment table
+__global__ void __launch_bounds__(256) make_end_keys_seg_kernel(const int32_t *__restrict__ seg, int32_t n_contigs, const int32_t *__restrict__ en,
+                                                                int64_t m, int pos_bits, uint32_t bias_e, uint64_t *__restrict__ ekeys,
+                                                                uint64_t *__restrict__ evals) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const uint64_t contig = (uint64_t)contig_of_pos(seg, n_contigs, i);
+  ekeys[i] = (contig << pos_bits) | ((uint32_t)en[i] ^ bias_e);
+  evals[i] = (uint64_t)i;
 }
 
 static inline int bit_length_u32(uint32_t x) {

@@ -319,6 +319,8 @@ void pbgpu_index_free(pbgpu_index *ix) {
   dev_free(ix->slab, 0);
   dev_free(ix->slab2, 0);
   dev_free(ix->slab_n, 0);
+  dev_free(ix->slab_e, 0);
+  if (ix->end_ready) cudaEventDestroy(ix->end_ready);
   if (cur != ix->device) cudaSetDevice(cur);
   delete ix;
 }
@@ -332,6 +334,8 @@ static void index_free_on(pbgpu_index *ix, cudaStream_t s) {
   dev_free(ix->slab, s);
   dev_free(ix->slab2, s);
   dev_free(ix->slab_n, s);
+  dev_free(ix->slab_e, s);
+  if (ix->end_ready) cudaEventDestroy(ix->end_ready);
   if (cur != ix->device) cudaSetDevice(cur);
   delete ix;
 }
@@ -341,13 +345,6 @@ int64_t pbgpu_index_rows(const pbgpu_index *ix) { return ix ? ix->m : 0; }
 size_t pbgpu_index_bytes(const pbgpu_index *ix) { return ix ? ix->bytes : 0; }
 
 static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
-
-// PBGPU_JDIR=search: build the joint directory with one binary search pair per bucket (the first implementation; kept
-// for A/B runs) instead of the streaming mark + pack kernels
-static bool jdir_by_search() {
-  static bool v = [] { const char *e = getenv("PBGPU_JDIR"); return e && !strcmp(e, "search"); }();
-  return v;
-}
 
 // PBGPU_TRACE_BUILD=1: host wall time of every build stage on stderr, with the stream drained at each lap (tuning aid;
 // changes the timing it reports on by serialising host and device)
@@ -370,6 +367,79 @@ struct BuildTrace {
     t0 = now();
   }
 };
+
+// PBGPU_JDIR_SHIFT=k: k more bits per directory bucket than the default rule picks (tuning: fewer, fuller records)
+static int jdir_extra_shift() {
+  static int v = [] { const char *e = getenv("PBGPU_JDIR_SHIFT"); return e ? atoi(e) : 0; }();
+  return v < 0 ? 0 : v;
+}
+constexpr int kCrowdedLinearMax = 64;  // crowded records of an unsorted-ends index are counted linearly up to this many ends
+
+namespace pbgpu {
+__global__ void widen_word_kernel(const unsigned int *__restrict__ in, unsigned long long *__restrict__ out) {
+  if (threadIdx.x == 0) *out = *in;
+}
+__global__ void __launch_bounds__(256) widen_u32_keys_kernel(const uint32_t *__restrict__ in, int64_t n, uint64_t *__restrict__ k, uint64_t *__restrict__ v) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) { k[i] = in[i]; v[i] = 0; }
+}
+__global__ void __launch_bounds__(256) narrow_u32_keys_kernel(const uint64_t *__restrict__ k, int64_t n, uint32_t *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) out[i] = (uint32_t)k[i];
+}
+}  // namespace pbgpu
+
+// End order of an index with nested intervals: ends sorted by (contig, end, start, row) and their positions in start
+// order (nearest's upstream walk, the generic kernels' rank identity).  Stable sort over the start order, so ties keep
+// (start, row) order.  Enqueued on `s`; the arrays live in their own slab.
+static int build_end_order(pbgpu_index *ix, cudaStream_t s) {
+  const int64_t m = ix->m;
+  if (!ix->nested || ix->en_sorted || m == 0) return PBGPU_OK;
+  const size_t arr_b = (sizeof(int32_t) * (size_t)m + 255) & ~(size_t)255;
+  PB_TRY(dev_alloc(&ix->slab_e, 2 * arr_b, s));
+  ix->bytes += 2 * arr_b;
+  int32_t *en_sorted = (int32_t *)ix->slab_e;
+  uint32_t *en_pos = (uint32_t *)((char *)ix->slab_e + arr_b);
+  Scratch sc(s);
+  uint64_t *ek = nullptr, *ev = nullptr, *ek2 = nullptr, *ev2 = nullptr;
+  PB_TRY(sc.get(&ek, (size_t)m));
+  PB_TRY(sc.get(&ev, (size_t)m));
+  PB_TRY(sc.get(&ek2, (size_t)m));
+  PB_TRY(sc.get(&ev2, (size_t)m));
+  constexpr int pos_bits = 32;
+  constexpr uint32_t bias = 0x80000000u;
+  PB_LAUNCH(make_end_keys_seg_kernel, (unsigned)cdiv(m, 256), 256, 0, s, ix->seg, ix->n_contigs, ix->en, m, pos_bits, bias, ek, ev);
+  PB_CHECK_LAUNCH();
+  int epos[kRsMaxPasses], ne = 0;
+  const int vb = bit_length_u32((uint32_t)ix->min_end ^ (uint32_t)ix->max_end);
+  for (int p = 0; p * 8 < vb; ++p) epos[ne++] = p;
+  const int contig_digits = (bit_length_u32((uint32_t)ix->n_contigs) + 7) / 8;
+  if (ix->n_contigs > 1) for (int q = 0; q < contig_digits; ++q) epos[ne++] = 4 + q;
+  SortedPairs es;
+  PB_TRY(radix_sort_digits(ek, ev, ek2, ev2, m, epos, ne, nullptr, s, &es));
+  PB_LAUNCH(unpack_ends_kernel, (unsigned)cdiv(m, 256), 256, 0, s, es.keys, es.vals, m, pos_bits, bias, en_sorted, en_pos);
+  PB_CHECK_LAUNCH();
+  ix->en_sorted = en_sorted;
+  ix->en_pos = en_pos;
+  return PBGPU_OK;
+}
+// nearest on a fast-path index: the end order is built by the first call that needs it (on that call's stream); later
+// calls on other streams wait for the event
+static int ensure_end_order(const pbgpu_index *cix, cudaStream_t s) {
+  pbgpu_index *ix = const_cast<pbgpu_index *>(cix);
+  if (!ix->nested) return PBGPU_OK;
+  std::lock_guard<std::mutex> lk(ix->mu);
+  if (!ix->en_sorted) {
+    PB_TRY(build_end_order(ix, s));
+    if (!ix->end_ready && cudaEventCreateWithFlags(&ix->end_ready, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); ix->end_ready = nullptr; }
+    if (ix->end_ready) PB_CUDA(cudaEventRecord(ix->end_ready, s));
+    else PB_CUDA(cudaStreamSynchronize(s));
+    ix->end_stream = s;
+  } else if (ix->end_ready && s != ix->end_stream) {
+    PB_CUDA(cudaStreamWaitEvent(s, ix->end_ready, 0));
+  }
+  return PBGPU_OK;
+}
 
 // sweep_only: the caller wants the (contig, start, row) order, the segments and the running max of the ends only (the
 // unary sweeps of unary.cuh): the end order and the rank directory are skipped
@@ -490,50 +560,38 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
   const bool nested = h_meta[0] != 0;
   ix->nested = nested;
 
-  // 4. nested intervals: running max of the ends, ends sorted per contig (stable over the start order, so ties keep
-  //    (start,row) order) and their positions.  Otherwise the three arrays alias `en` / identity.
-  uint64_t *ekeys = nullptr;
+  // 4. nested intervals: running maximum of the ends inside every contig, one look-back pass.  The ends are NOT sorted
+  //    here any more (round 1: a second five-pass radix sort, 7 of the 15.8 ms of a 90 M-row build): the fast path's
+  //    directory only needs them grouped by bucket (step 5), and the end order proper (en_sorted / en_pos: nearest and
+  //    the generic kernels) is built on first use (ensure_end_order) or right away when the fast path is not available.
+  ix->min_end = hs.min_end;
+  ix->max_end = hs.max_end;
   if (nested) {
-    PB_TRY(dev_alloc(&ix->slab_n, 3 * arr_b, s));
-    ix->bytes += 3 * arr_b;
+    PB_TRY(dev_alloc(&ix->slab_n, arr_b, s));
+    ix->bytes += arr_b;
     ix->pmax = (int32_t *)ix->slab_n;
-    ix->en_sorted = (int32_t *)((char *)ix->slab_n + arr_b);
-    ix->en_pos = (uint32_t *)((char *)ix->slab_n + 2 * arr_b);
-    uint64_t *pm_keys = keys_alt, *evals = nullptr, *ekeys2 = vals_alt, *evals2 = nullptr;  // the sort's idle buffers are reused
-    PB_TRY(sc.get(&ekeys, (size_t)m));
-    PB_TRY(sc.get(&evals, (size_t)m));
-    PB_TRY(sc.get(&evals2, (size_t)m));
-    bt.lap("nested: allocs");
-    PB_LAUNCH(make_end_keys_kernel, (unsigned)cdiv(m, 256), 256, 0, s, keys, ix->en, m, pos_bits, bias, pm_keys, ekeys, evals);
+    ix->en_sorted = nullptr;  // lazy
+    ix->en_pos = nullptr;
+    const int64_t tiles = cdiv(m, kPmTile);
+    unsigned long long *pm_status = nullptr;
+    PB_TRY(sc.get(&pm_status, (size_t)tiles + 1));
+    PB_CUDA(cudaMemsetAsync(pm_status, 0, sizeof(unsigned long long) * ((size_t)tiles + 1), s));
+    PB_LAUNCH(pmax_lookback_kernel, (unsigned)tiles, kPmThreads, 0, s, ix->seg, n_contigs, ix->en, m, ix->pmax, pm_status,
+              (unsigned int *)(pm_status + tiles));
     PB_CHECK_LAUNCH();
-    PB_TRY((device_scan<MaxU64, true>((const unsigned long long *)pm_keys, (unsigned long long *)pm_keys, m, nullptr, s)));
-    PB_LAUNCH(unpack_pmax_kernel, (unsigned)cdiv(m, 256), 256, 0, s, pm_keys, m, ix->pmax);
-    PB_CHECK_LAUNCH();
-    if (sweep_only) {
-      ix->en_sorted = nullptr;
-      ix->en_pos = nullptr;
-      return PBGPU_OK;
-    }
-    // the rows are already grouped by contig: sorting the varying end digits stably, then the contig digits, gives
-    // (contig, end, start, row) order
-    int epos[kRsMaxPasses], ne = varying_digits(hs.min_end, hs.max_end, epos, 0);
-    if (n_contigs > 1) for (int q = 0; q < contig_digits; ++q) epos[ne++] = 4 + q;
-    SortedPairs es;
-    PB_TRY(radix_sort_digits(ekeys, evals, ekeys2, evals2, m, epos, ne, nullptr, s, &es));
-    ekeys = es.keys;
-    PB_LAUNCH(unpack_ends_kernel, (unsigned)cdiv(m, 256), 256, 0, s, es.keys, es.vals, m, pos_bits, bias, ix->en_sorted, ix->en_pos);
-    PB_CHECK_LAUNCH();
-    bt.lap("nested: pmax + end sort");
+    bt.lap("nested: running max");
   }
-
   if (sweep_only) return PBGPU_OK;
-  // 5. fast path: global axis + rank directories
+
+  // 5. fast path: global axis + rank directory
   const unsigned long long total_span = h_meta[1];
   if (try_fast && total_span > 0 && total_span < 0xFFFFFFF0ull) {
     // bucket width: the smallest power of two that leaves at most m/0.6 buckets (0.6-1.2 indexed rows per bucket:
     // a record then holds ~3 keys on average of its 12 and crowded records stay below ~0.2 %), capped at 2^13
     int shift = 0;
     while (shift < kJMaxShift && (total_span >> shift) > ((unsigned long long)m * 5ull) / 3ull) ++shift;
+    shift += jdir_extra_shift();
+    if (shift > kJMaxShift) shift = kJMaxShift;
     const uint32_t nb = (uint32_t)(total_span >> shift) + 1;
     const size_t cm_b = align_up(sizeof(ContigMap) * ((size_t)n_contigs + 1)), g_b = align_up(4 * (size_t)m);
     const size_t d_b = align_up(sizeof(JRec) * ((size_t)nb + 1));
@@ -549,24 +607,55 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
     ix->n_buckets = nb;
     PB_CUDA(cudaMemcpyAsync(ix->cmap, d_cmap_tmp, sizeof(ContigMap) * (size_t)n_contigs, cudaMemcpyDeviceToDevice, s));
     if (!small_table) PB_LAUNCH(contig_off_kernel, (unsigned)cdiv(n_contigs, 128), 128, 0, s, d_span, n_contigs, ix->cmap);
-    // contig of position i: from the start-sorted keys (start order) or the end-sorted keys (end order; same order
-    // as the start keys when nothing is nested)
-    if (jdir_by_search()) {
-      PB_LAUNCH(global_coord_kernel, (unsigned)cdiv(m, 256), 256, 0, s, keys, pos_bits, ix->st, m, ix->cmap, ix->gs);
-      PB_LAUNCH(global_coord_kernel, (unsigned)cdiv(m, 256), 256, 0, s, nested ? ekeys : keys, pos_bits, ix->en_sorted, m, ix->cmap, ix->ge);
-      PB_LAUNCH(build_jdir_kernel, (unsigned)cdiv((int64_t)nb + 1, 256), 256, 0, s, ix->gs, ix->ge, m, shift, nb, ix->jdir);
-    } else {  // streaming: global coordinates + rank words in one pass over the sorted rows, then one pass over the records
-      uint32_t *rank_s = nullptr, *rank_e = nullptr;
-      PB_TRY(sc.get(&rank_s, (size_t)nb + 1));
-      PB_TRY(sc.get(&rank_e, (size_t)nb + 1));
-      PB_LAUNCH(jdir_mark_kernel, (unsigned)cdiv(m, 256), 256, 0, s, keys, nested ? ekeys : keys, pos_bits, ix->st, ix->en_sorted, m,
+    uint32_t *rank_s = nullptr, *rank_e = nullptr;
+    PB_TRY(sc.get(&rank_s, (size_t)nb + 1));
+    PB_TRY(sc.get(&rank_e, (size_t)nb + 2));  // + the crowded-ends word of the nested variant
+    if (!nested) {  // end order == start order: both rank arrays by run filling, one pass over the sorted rows
+      PB_LAUNCH(jdir_mark_kernel, (unsigned)cdiv(m, 256), 256, 0, s, keys, keys, pos_bits, ix->st, ix->en, m,
                 ix->cmap, shift, nb, ix->gs, ix->ge, rank_s, rank_e);
-      PB_LAUNCH(jdir_pack_kernel, (unsigned)cdiv((int64_t)nb + 1, 256), 256, 0, s, ix->gs, ix->ge, m, shift, nb, rank_s, rank_e, ix->jdir);
+      PB_LAUNCH(jdir_pack2_kernel<false>, (unsigned)cdiv((int64_t)nb + 1, 256), 256, 0, s, ix->gs, ix->ge, m, shift, nb, rank_s, rank_e, ix->jdir,
+                (unsigned int *)nullptr);
+      PB_CHECK_LAUNCH();
+      ix->ge_sorted = 1;
+    } else {  // ends grouped by bucket (counting sort with the buckets as bins), unordered inside a bucket
+      uint32_t *ge_tmp = (uint32_t *)keys_alt;  // the sort's idle buffer
+      unsigned int *d_crowded = rank_e + nb + 1;
+      PB_CUDA(cudaMemsetAsync(rank_e, 0, sizeof(uint32_t) * ((size_t)nb + 2), s));
+      PB_LAUNCH(jdir_mark_nested_kernel, (unsigned)cdiv(m, 256), 256, 0, s, keys, pos_bits, ix->st, ix->en, m, ix->cmap, shift, nb, ix->gs,
+                ge_tmp, rank_s, rank_e);
+      PB_CHECK_LAUNCH();
+      PB_TRY((device_scan<SumU32, false>(rank_e, rank_e, (int64_t)nb + 1, nullptr, s)));
+      PB_LAUNCH(jdir_place_ends_kernel, (unsigned)cdiv(m, 256), 256, 0, s, ge_tmp, m, shift, rank_e, ix->ge);
+      PB_LAUNCH(jdir_pack2_kernel<true>, (unsigned)cdiv((int64_t)nb + 1, 256), 256, 0, s, ix->gs, ix->ge, m, shift, nb, rank_s, rank_e, ix->jdir,
+                d_crowded);
+      PB_CHECK_LAUNCH();
+      // probes that land in a crowded record count its ends one by one (they are not sorted): fine for a few dozen,
+      // not for thousands of equal ends -- then the ends are sorted after all (one pass per varying digit)
+      unsigned long long crowded = 0;
+      {
+        unsigned long long *d_word = nullptr;
+        PB_TRY(sc.get(&d_word, 1));
+        PB_LAUNCH(widen_word_kernel, 1, 32, 0, s, d_crowded, d_word);
+        PB_TRY(fetch_words(d_word, 1, &crowded, s));
+      }
+      ix->ge_sorted = 0;
+      if (crowded > (unsigned long long)kCrowdedLinearMax) {
+        uint64_t *gk = keys_alt, *gv = vals_alt, *gk2 = nullptr, *gv2 = nullptr;  // keys_alt's first half still holds ge_tmp: not needed any more
+        PB_TRY(sc.get(&gk2, (size_t)m));
+        PB_TRY(sc.get(&gv2, (size_t)m));
+        PB_LAUNCH(widen_u32_keys_kernel, (unsigned)cdiv(m, 256), 256, 0, s, ix->ge, m, gk, gv);
+        int gpos[4] = {0, 1, 2, 3};
+        SortedPairs gsrt;
+        PB_TRY(radix_sort_digits(gk, gv, gk2, gv2, m, gpos, 4, nullptr, s, &gsrt));
+        PB_LAUNCH(narrow_u32_keys_kernel, (unsigned)cdiv(m, 256), 256, 0, s, gsrt.keys, m, ix->ge);
+        PB_CHECK_LAUNCH();
+        ix->ge_sorted = 1;
+      }
     }
-    PB_CHECK_LAUNCH();
     bt.lap("directory");
     ix->fast = 1;
   }
+  if (nested && !ix->fast) PB_TRY(build_end_order(ix, s));  // the generic kernels search the end order
   return PBGPU_OK;
 }
 
@@ -891,6 +980,7 @@ int pbgpu_nearest(const pbgpu_index *ix, const int32_t *d_contig, const int32_t 
   if (n == 0) return PBGPU_OK;
   if (!d_partner) return set_error(PBGPU_EINVAL, "d_partner is NULL");
   cudaStream_t s = (cudaStream_t)stream;
+  PB_TRY(ensure_end_order(ix, s));
   const unsigned grid = (unsigned)cdiv(n, kSweepThreads);
   if (filter_op == PBGPU_FILTER_STRICT)
     PB_LAUNCH(nearest_kernel<true>, grid, kSweepThreads, 0, s, view_of(ix), d_contig, d_start, d_end, n, k, include_overlaps,

@@ -39,7 +39,7 @@ __device__ __forceinline__ uint32_t probe_count(const IndexView &ix, int32_t c, 
   const int32_t seg_lo = ix.seg[c], seg_hi = ix.seg[c + 1];
   if (seg_lo >= seg_hi) return 0;
   const bool proper = STRICT ? (s < e) : (s <= e);
-  if (proper && !ix.has_inverted) {
+  if (proper && !ix.has_inverted && ix.en_sorted) {
     // rank identity: every indexed row ending before the probe starts also starts before it ends
     const int32_t hi = STRICT ? lower_bound_i32(ix.st, seg_lo, seg_hi, e) : upper_bound_i32(ix.st, seg_lo, seg_hi, e);
     const int32_t re = STRICT ? upper_bound_i32(ix.en_sorted, seg_lo, seg_hi, s) : lower_bound_i32(ix.en_sorted, seg_lo, seg_hi, s);
@@ -193,8 +193,9 @@ __device__ __forceinline__ void jdir_ranks(const IndexView &ix, uint32_t g_s, ui
   if (!(w[0] & 0x80000000u)) {
     re = w[1] + jrec_nlt(w, 0x4000u + (xE - lo));
     if (same) { hi = w[0] + jrec_nlt(w, dS); return; }
-  } else {  // crowded bucket: search inside its rank range
-    re = search_g(ix.ge, w[1], w[3], xE);
+  } else {  // crowded bucket: search inside its rank range (or count, when the bucket's ends are not sorted)
+    if (ix.ge_sorted) re = search_g(ix.ge, w[1], w[3], xE);
+    else { re = w[1]; for (uint32_t j = w[1]; j < w[3]; ++j) re += __ldg(ix.ge + j) < xE; }
     if (same) { hi = search_g(ix.gs, w[0] & 0x7fffffffu, w[2], xS); return; }
   }
   const uint32_t b2 = g_e >> sh, lo2 = b2 << sh;  // probe longer than the overlap: the record of its end bucket
@@ -280,14 +281,6 @@ __global__ void __launch_bounds__(kSweepThreads) count_overlaps_fast_kernel(Inde
 __device__ __forceinline__ unsigned long long warp_sum_u32(uint32_t v) {
   const uint32_t lo = __reduce_add_sync(0xffffffffu, v & 0xffffu), hi = __reduce_add_sync(0xffffffffu, v >> 16);
   return (unsigned long long)lo + ((unsigned long long)hi << 16);
-}
-__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
-  unsigned long long v;
-  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned long long v) {
-  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 // Pass 1 on the fast path.  Besides the per-probe (count, start rank) it produces the pair offsets pass 2 needs, in
 // the same launch: the offset of every 32-probe group inside its 256-probe block (warp_off), and -- LOOKBACK -- the

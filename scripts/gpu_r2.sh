@@ -1,0 +1,26 @@
+#!/bin/bash
+# round 2: one gpurun call = [pytest -m gpu] + [bench N=1] + optional extras, everything under gpurun_out/<tag>_*
+#   gpurun --timeout 2400 -- 'bash scripts/gpu_r2.sh r2c pytest bench trace'
+TAG=${1:-r2}; shift
+O=gpurun_out; mkdir -p $O
+for what in "$@"; do
+case $what in
+pytest)
+  echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest_gpu.log 2>&1; echo rc=$?; tail -12 $O/${TAG}_pytest_gpu.log;;
+pytest_scale)
+  echo "== pytest scale"; timeout 900 python -m pytest tests/test_gpu_scale.py -m gpu -x -q > $O/${TAG}_pytest_scale.log 2>&1; echo rc=$?; tail -12 $O/${TAG}_pytest_scale.log;;
+pytest_parity)
+  echo "== pytest parity"; timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_api.py tests/test_gpu_unary.py -m gpu -x -q > $O/${TAG}_pytest_parity.log 2>&1; echo rc=$?; tail -12 $O/${TAG}_pytest_parity.log;;
+bench)
+  echo "== bench N=1"; timeout 1200 python bench.py --steps 10 --warmup 3 > $O/${TAG}_bench_1gpu.json 2> $O/${TAG}_bench_1gpu.err; echo rc=$?; tail -c 7000 $O/${TAG}_bench_1gpu.json; tail -5 $O/${TAG}_bench_1gpu.err;;
+bench_dev)
+  echo "== bench N=1 (device only)"; timeout 600 python bench.py --steps 10 --warmup 3 --skip-e2e --no-cpu-baseline --skip-secondary > $O/${TAG}_bench_dev.json 2> $O/${TAG}_bench_dev.err; echo rc=$?; tail -c 5000 $O/${TAG}_bench_dev.json; tail -5 $O/${TAG}_bench_dev.err;;
+trace)
+  echo "== build trace (config 3)"; PBGPU_TRACE_BUILD=1 PB_REPS=2 timeout 600 python tests/tools/scale_check.py 3 > $O/${TAG}_scale3.jsonl 2> $O/${TAG}_build_trace.txt; echo rc=$?; tail -14 $O/${TAG}_build_trace.txt; cat $O/${TAG}_scale3.jsonl;;
+ref)
+  echo "== reference arm"; timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > $O/${TAG}_bench_ref.json 2> $O/${TAG}_bench_ref.err; echo rc=$?; cat $O/${TAG}_bench_ref.json;;
+launches)
+  echo "== ncu launch list (config 3, device only)"
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches.csv python bench.py --steps 1 --warmup 1 --skip-e2e --no-cpu-baseline --skip-secondary --skip-parity > $O/${TAG}_launches.log 2>&1; echo rc=$?; tail -3 $O/${TAG}_launches.log;;
+esac
+done

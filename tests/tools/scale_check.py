@@ -15,6 +15,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import oracle  # noqa: E402 (checker only)
+import workloads as wl  # noqa: E402
 from polars_bio_b200 import _native, engine  # noqa: E402
 
 GRCH38 = np.array([248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636, 138394717,
@@ -78,12 +79,9 @@ def sample_parity(name, pc, ps, pe, bc, bs, be, strict, counts=None, pairs=None,
 
 
 def config3():
-    rng_r, rng_v = np.random.default_rng(3), np.random.default_rng(4)
     n, m = int(100e6 * SCALE), int(90e6 * SCALE)
-    pc = contigs_by_length(rng_r, n); ps = uniform_on(rng_r, pc, 150); pe = (ps + 150).astype(np.int32)
-    bc = contigs_by_length(rng_v, m); bs = uniform_on(rng_v, bc, 200)
-    ln = np.where(rng_v.random(m) < 0.9, 1, rng_v.geometric(0.2, m) + 1).astype(np.int32)
-    be = (bs + ln).astype(np.int32)
+    pc, ps, pe = wl.config3_reads(0, n, n)
+    bc, bs, be = wl.config3_variants(0, m, m)
     dp, db = [t(x) for x in (pc, ps, pe)], [t(x) for x in (bc, bs, be)]
     ix, build_ms = timed(lambda: engine.DeviceIndex(*db, 24))
     cnt, count_ms = timed(lambda: ix.count_overlaps(*dp, engine.FILTER_STRICT))
