@@ -273,10 +273,13 @@ PBGPU_API int pbgpu_subtract(const int32_t *l_contig, const int32_t *l_start, co
  * waits for the last one).  A stage that has not run yet reads 0.                              */
 typedef struct {
   uint64_t partition_sort_ns;  /* pbgpu_index_build: contig partition + start sort + aux arrays + directories */
-  uint64_t count_ns;           /* overlap pass 1 kernel                                        */
+  uint64_t count_ns;           /* overlap pass 1 (incl. the probe partition when the index is beyond the L2) */
   uint64_t scan_ns;            /* pair-offset scan of pass 1                                   */
   uint64_t emit_ns;            /* overlap pass 2 kernel                                        */
-  uint64_t count_overlaps_ns;  /* pbgpu_count_overlaps kernel                                  */
+  uint64_t count_overlaps_ns;  /* pbgpu_count_overlaps: every kernel of the call (partition + count + un-binning when used) */
+  uint64_t bin_ns;             /* most recent probe partition (histogram + one radix pass; csrc/bins.cuh), 0 if none;    */
+                               /* it is INSIDE count_ns / count_overlaps_ns of the call that ran it                      */
+  uint64_t unbin_ns;           /* pbgpu_count_overlaps: counts back from bin order to row order                          */
 } pbgpu_stage_times;
 PBGPU_API int pbgpu_last_stage_times(pbgpu_stage_times *out);
 

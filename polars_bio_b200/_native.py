@@ -64,7 +64,8 @@ class PbPeerStep(ctypes.Structure):
 
 class StageTimes(ctypes.Structure):
     _fields_ = [("partition_sort_ns", ctypes.c_uint64), ("count_ns", ctypes.c_uint64),
-                ("scan_ns", ctypes.c_uint64), ("emit_ns", ctypes.c_uint64), ("count_overlaps_ns", ctypes.c_uint64)]
+                ("scan_ns", ctypes.c_uint64), ("emit_ns", ctypes.c_uint64), ("count_overlaps_ns", ctypes.c_uint64),
+                ("bin_ns", ctypes.c_uint64), ("unbin_ns", ctypes.c_uint64)]
 
 
 def lib() -> ctypes.CDLL:

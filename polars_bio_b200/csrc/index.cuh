@@ -67,6 +67,7 @@ struct pbgpu_index {
   int fast = 0;
   int shift = 0;
   uint32_t n_buckets = 0;
+  uint32_t axis_span = 0;  // length of the global axis (fast path)
   pbgpu::ContigMap *cmap = nullptr;
   uint32_t *gs = nullptr, *ge = nullptr;
   pbgpu::JRec *jdir = nullptr;

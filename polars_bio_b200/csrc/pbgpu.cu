@@ -11,6 +11,7 @@
 #include "radix_sort.cuh"
 #include "scan.cuh"
 #include "sweep.cuh"
+#include "bins.cuh"
 
 namespace pbgpu {
 
@@ -177,7 +178,7 @@ void dev_free(void *p, cudaStream_t s) {
 // CUDA-event stage marks, always on (an event record is ~1 us of host time and no device sync): pairs of
 // events bracket the index build and each provider kernel on the launching stream; pbgpu_last_stage_times()
 // turns them into durations after the fact.  One set per host thread and device.
-enum { EV_BUILD0, EV_BUILD1, EV_COUNT0, EV_COUNT1, EV_P1_0, EV_P1_1, EV_SCAN1, EV_EMIT0, EV_EMIT1, EV_N };
+enum { EV_BUILD0, EV_BUILD1, EV_COUNT0, EV_COUNT1, EV_P1_0, EV_P1_1, EV_SCAN1, EV_EMIT0, EV_EMIT1, EV_BIN0, EV_BIN1, EV_UNBIN0, EV_UNBIN1, EV_N };
 struct StageEvents {
   cudaEvent_t ev[EV_N] = {};
   bool set[EV_N] = {};
@@ -305,6 +306,8 @@ int pbgpu_last_stage_times(pbgpu_stage_times *out) {
   out->scan_ns = g_ev.span_ns(EV_P1_1, EV_SCAN1);
   out->emit_ns = g_ev.span_ns(EV_EMIT0, EV_EMIT1);
   out->count_overlaps_ns = g_ev.span_ns(EV_COUNT0, EV_COUNT1);
+  out->bin_ns = g_ev.span_ns(EV_BIN0, EV_BIN1);
+  out->unbin_ns = g_ev.span_ns(EV_UNBIN0, EV_UNBIN1);
   return PBGPU_OK;
 }
 
@@ -605,6 +608,7 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
     ix->jdir = (JRec *)(b2 + cm_b + 2 * g_b);
     ix->shift = shift;
     ix->n_buckets = nb;
+    ix->axis_span = (uint32_t)total_span;
     PB_CUDA(cudaMemcpyAsync(ix->cmap, d_cmap_tmp, sizeof(ContigMap) * (size_t)n_contigs, cudaMemcpyDeviceToDevice, s));
     if (!small_table) PB_LAUNCH(contig_off_kernel, (unsigned)cdiv(n_contigs, 128), 128, 0, s, d_span, n_contigs, ix->cmap);
     uint32_t *rank_s = nullptr, *rank_e = nullptr;
@@ -691,6 +695,61 @@ static int check_probe_args(const pbgpu_index *ix, const int32_t *c, const int32
 }  // extern "C"
 
 namespace pbgpu {
+// ---- probe partition (bins.cuh) ---------------------------------------------------------------------------------------
+// When: fast-path index whose rank directory is well beyond the L2 and enough probes to pay for the extra pass.
+// PBGPU_BIN=0 never, PBGPU_BIN=1 whenever the fast path is available (tests force it on small inputs).
+static int bin_mode() {
+  static int v = [] { const char *e = getenv("PBGPU_BIN"); return e ? (e[0] == '0' ? 0 : 2) : 1; }();
+  return v;
+}
+static bool want_bins(const pbgpu_index *ix, int64_t n) {
+  if (!ix->fast || n <= 0 || n >= (int64_t)kLbMask || bin_mode() == 0) return false;
+  if (bin_mode() == 2) return true;
+  return n >= (1 << 22) && (size_t)ix->n_buckets * sizeof(JRec) > ((size_t)96 << 20);
+}
+struct BinnedProbes {
+  int4 *recs = nullptr;
+  uint32_t *pos = nullptr;
+  void *slab = nullptr;
+  int bin_shift = 0;
+};
+// hist + one stable partition pass, enqueued on s.  The slab (records | pos | partition scratch) is the caller's to free.
+static int bin_probes(const pbgpu_index *ix, const int32_t *pc, const int32_t *ps, const int32_t *pe, int64_t n, int filter_op,
+                      bool write_pos, cudaStream_t s, BinnedProbes *out) {
+  const int64_t tiles = cdiv(n, kBinTile);
+  const size_t rec_b = align_up(sizeof(int4) * (size_t)n), pos_b = write_pos ? align_up(sizeof(uint32_t) * (size_t)n) : 0;
+  const size_t work_w = (size_t)kBinRadix + 64 + (size_t)tiles * kBinRadix;  // totals | ticket | status
+  PB_TRY(dev_alloc(&out->slab, rec_b + pos_b + sizeof(uint32_t) * work_w, s));
+  out->recs = (int4 *)out->slab;
+  out->pos = write_pos ? (uint32_t *)((char *)out->slab + rec_b) : nullptr;
+  uint32_t *work = (uint32_t *)((char *)out->slab + rec_b + pos_b);
+  uint32_t *totals = work, *ticket = work + kBinRadix, *status = work + kBinRadix + 64;
+  int span_bits = 0;
+  for (uint32_t v = ix->axis_span; v; v >>= 1) ++span_bits;
+  out->bin_shift = span_bits > 8 ? span_bits - 8 : 0;
+  g_ev.mark(EV_BIN0, s);
+  PB_CUDA(cudaMemsetAsync(work, 0, sizeof(uint32_t) * work_w, s));
+  int64_t hgrid = cdiv(n, 512 * 4);
+  if (hgrid > kSMs * 4) hgrid = kSMs * 4;
+  PB_LAUNCH(bin_hist_kernel, (unsigned)hgrid, 512, 0, s, view_of(ix), pc, ps, n, out->bin_shift, totals);
+  constexpr size_t stage_b = sizeof(int4) * kBinTile;
+  static std::once_flag attr_once;
+  std::call_once(attr_once, [] {
+    cudaFuncSetAttribute(bin_partition_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_b);
+    cudaFuncSetAttribute(bin_partition_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_b);
+  });
+  const int strict = filter_op == PBGPU_FILTER_STRICT;
+  if (write_pos)
+    PB_LAUNCH(bin_partition_kernel<true>, (unsigned)tiles, kBinThreads, stage_b, s, view_of(ix), pc, ps, pe, n, out->bin_shift, strict, totals, status,
+              ticket, out->recs, out->pos);
+  else
+    PB_LAUNCH(bin_partition_kernel<false>, (unsigned)tiles, kBinThreads, stage_b, s, view_of(ix), pc, ps, pe, n, out->bin_shift, strict, totals, status,
+              ticket, out->recs, out->pos);
+  PB_CHECK_LAUNCH();
+  g_ev.mark(EV_BIN1, s);
+  return PBGPU_OK;
+}
+
 // probes per thread in the fast count kernels (PBGPU_ITEMS=1|2; default 2)
 static int sweep_items() {
   static int v = [] { const char *e = getenv("PBGPU_ITEMS"); return (e && e[0] == '1') ? 1 : ((e && e[0] == '4') ? 4 : 2); }();
@@ -705,7 +764,24 @@ int count_overlaps_impl(const pbgpu_index *ix, const int32_t *d_contig, const in
   g_ev.mark(EV_COUNT0, s);
   const unsigned grid = (unsigned)cdiv(n, kSweepThreads);
   const bool strict = filter_op == PBGPU_FILTER_STRICT;
-  if (ix->fast) {
+  if (want_bins(ix, n)) {  // index beyond the L2: partition the probes by coordinate, count in bin order, counts back to row order
+    BinnedProbes bp;
+    int rc = bin_probes(ix, d_contig, d_start, d_end, n, filter_op, true, s, &bp);
+    uint32_t *cnt_b = nullptr;
+    if (rc == PBGPU_OK) rc = dev_alloc_t(&cnt_b, (size_t)n, s);
+    if (rc == PBGPU_OK) {
+      const unsigned g2 = (unsigned)cdiv(n, kSweepThreads * 2);
+      if (strict) PB_LAUNCH((binned_count_kernel<true, 2>), g2, kSweepThreads, 0, s, view_of(ix), bp.recs, d_start, d_end, n, cnt_b);
+      else PB_LAUNCH((binned_count_kernel<false, 2>), g2, kSweepThreads, 0, s, view_of(ix), bp.recs, d_start, d_end, n, cnt_b);
+      g_ev.mark(EV_UNBIN0, s);
+      PB_LAUNCH(unbin_counts_kernel<OutT>, (unsigned)cdiv(n, 256 * 4), 256, 0, s, cnt_b, bp.pos, n, d_counts);
+      g_ev.mark(EV_UNBIN1, s);
+      if (cudaGetLastError() != cudaSuccess) rc = set_error(PBGPU_ECUDA, "binned count launch failed");
+    }
+    dev_free(cnt_b, s);
+    dev_free(bp.slab, s);
+    if (rc != PBGPU_OK) return rc;
+  } else if (ix->fast) {
     const int items = sweep_items();
     const unsigned g2 = (unsigned)cdiv(n, kSweepThreads * 2), g4 = (unsigned)cdiv(n, kSweepThreads * 4);
     if (items == 4) {
@@ -783,10 +859,11 @@ int pbgpu_coverage(const pbgpu_index *ix, const int32_t *d_contig, const int32_t
 
 // PBGPU_EMIT=walk: pass 2 always walks the candidate window (the first implementation; kept for A/B runs).  The flat
 // expansion needs the fast path, no nested intervals and 32 x indexed rows < 2^32 (32-bit warp scan of the counts).
-static bool emit_flat_ok(const pbgpu_index *ix) {
+static bool emit_by_walk() {
   static bool walk = [] { const char *e = getenv("PBGPU_EMIT"); return e && !strcmp(e, "walk"); }();
-  return !walk && ix->fast && !ix->nested && ix->m < (1ll << 27);
+  return walk;
 }
+static bool emit_flat_ok(const pbgpu_index *ix) { return !emit_by_walk() && ix->fast && !ix->nested && ix->m < (1ll << 27); }
 
 // Pass 1 leaves raw block totals and a device scan turns them into offsets.  PBGPU_P1SCAN=lookback does the scan
 // inside pass 1 instead (decoupled look-back over its blocks): measured 2.5x SLOWER (r01s: 181 vs 72 us at 10M
@@ -809,6 +886,8 @@ struct pbgpu_overlap_plan {
   unsigned long long *warp_off;     // [n/32] offset of every 32-probe group inside its block (flat pass 2 only)
   void *slab;                       // one stream-ordered allocation behind the arrays
   int64_t total;
+  const int4 *recs;                 // probes partitioned by coordinate (bins.cuh) when the index is beyond the L2, else NULL
+  void *bin_slab;
 };
 
 extern "C" {
@@ -819,6 +898,7 @@ void pbgpu_overlap_plan_free(pbgpu_overlap_plan *p) {
   cudaGetDevice(&cur);
   if (cur != p->device) cudaSetDevice(p->device);
   dev_free(p->slab, 0);  // legacy stream: ordered after the emit kernel of blocking streams
+  dev_free(p->bin_slab, 0);
   if (cur != p->device) cudaSetDevice(cur);
   delete p;
 }
@@ -829,6 +909,7 @@ void pbgpu_overlap_plan_free_async(pbgpu_overlap_plan *p, void *stream) {
   cudaGetDevice(&cur);
   if (cur != p->device) cudaSetDevice(p->device);
   dev_free(p->slab, (cudaStream_t)stream);  // ordered after the pass-2 launches enqueued on `stream`
+  dev_free(p->bin_slab, (cudaStream_t)stream);
   if (cur != p->device) cudaSetDevice(cur);
   delete p;
 }
@@ -844,17 +925,18 @@ int pbgpu_overlap_count(const pbgpu_index *ix, const int32_t *d_contig, const in
   cudaStream_t s = (cudaStream_t)stream;
   pbgpu_overlap_plan *p = new (std::nothrow) pbgpu_overlap_plan();
   if (!p) return set_error(PBGPU_ENOMEM, "host allocation failed");
-  *p = pbgpu_overlap_plan{ix, d_contig, d_start, d_end, n, filter_op, 0, cdiv(n, kSweepThreads), nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+  *p = pbgpu_overlap_plan{ix, d_contig, d_start, d_end, n, filter_op, 0, cdiv(n, kSweepThreads), nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr};
   cudaGetDevice(&p->device);
   auto fail = [&](int rc) { pbgpu_overlap_plan_free(p); return rc; };
   if (n == 0) { *plan = p; return PBGPU_OK; }
   const int items = sweep_items();
   const unsigned grid = (unsigned)p->nblk, grid_fast = (unsigned)cdiv(n, (int64_t)kSweepThreads * items);
-  const bool lookback = ix->fast && !p1_scan_by_kernels();
+  const bool binned = want_bins(ix, n);
+  const bool lookback = ix->fast && !binned && !p1_scan_by_kernels();
   unsigned long long *d_status = nullptr;
   {
     const size_t cb = align_up(sizeof(uint32_t) * (size_t)n), bb = align_up(sizeof(unsigned long long) * (size_t)(p->nblk + 1));
-    const bool flat = emit_flat_ok(ix);
+    const bool flat = emit_flat_ok(ix) && !binned;
     const size_t wb = flat ? align_up(sizeof(unsigned long long) * (size_t)(p->nblk * (kSweepThreads / 32))) : 0;
     const size_t sb = lookback ? align_up(sizeof(unsigned long long) * ((size_t)grid_fast + 1)) : 0;  // status words + ticket
     int rc0 = dev_alloc(&p->slab, 2 * cb + bb + wb + sb, s);
@@ -872,7 +954,20 @@ int pbgpu_overlap_count(const pbgpu_index *ix, const int32_t *d_contig, const in
   unsigned long long *d_total = p->block_base + p->nblk;
   unsigned long long h_total = 0;
   int rc = PBGPU_OK;
-  if (ix->fast) {
+  if (binned) {  // index beyond the L2: pass 1 and pass 2 run over the probes partitioned by coordinate
+    BinnedProbes bp;
+    rc = bin_probes(ix, d_contig, d_start, d_end, n, filter_op, false, s, &bp);
+    p->recs = bp.recs;
+    p->bin_slab = bp.slab;
+    if (rc != PBGPU_OK) return fail(rc);
+    const unsigned g2 = (unsigned)cdiv(n, kSweepThreads * 2);
+    if (filter_op == PBGPU_FILTER_STRICT)
+      PB_LAUNCH((binned_p1_kernel<true, 2>), g2, kSweepThreads, 0, s, view_of(ix), p->recs, d_start, d_end, n, p->counts, p->his, p->block_base, p->warp_off);
+    else
+      PB_LAUNCH((binned_p1_kernel<false, 2>), g2, kSweepThreads, 0, s, view_of(ix), p->recs, d_start, d_end, n, p->counts, p->his, p->block_base, p->warp_off);
+    if (cudaGetLastError() != cudaSuccess) return fail(set_error(PBGPU_ECUDA, "binned_p1_kernel launch failed"));
+    g_ev.mark(EV_P1_1, s);
+  } else if (ix->fast) {
     const bool strict = filter_op == PBGPU_FILTER_STRICT;
     const MailboxSlot slot = lookback ? mailbox_open() : MailboxSlot{nullptr, 0};
     unsigned int *d_ticket = lookback ? (unsigned int *)(d_status + grid_fast) : nullptr;
@@ -928,6 +1023,20 @@ static int emit_blocks_impl(const pbgpu_overlap_plan *p, int64_t blk_lo, int64_t
     else
       PB_LAUNCH((overlap_emit_flat_kernel<false, 2>), g2, kSweepThreads, 0, s, view_of(p->ix), p->pc, p->ps, p->pe, p->n, p->counts,
                 p->his, p->block_base, p->warp_off, blk_lo, blk_hi, d_probe_rows, d_build_rows);
+  } else if (p->recs) {  // partitioned probes: pairs leave in bin order
+    if (p->filter_op == PBGPU_FILTER_STRICT)
+      PB_LAUNCH((overlap_emit_staged_kernel<true, true>), grid, kSweepThreads, 0, s, view_of(p->ix), p->recs, p->pc, p->ps, p->pe, p->n, p->counts,
+                p->his, p->block_base, blk_lo, d_probe_rows, d_build_rows);
+    else
+      PB_LAUNCH((overlap_emit_staged_kernel<false, true>), grid, kSweepThreads, 0, s, view_of(p->ix), p->recs, p->pc, p->ps, p->pe, p->n, p->counts,
+                p->his, p->block_base, blk_lo, d_probe_rows, d_build_rows);
+  } else if (p->ix->fast && !emit_by_walk()) {
+    if (p->filter_op == PBGPU_FILTER_STRICT)
+      PB_LAUNCH((overlap_emit_staged_kernel<true, false>), grid, kSweepThreads, 0, s, view_of(p->ix), (const int4 *)nullptr, p->pc, p->ps, p->pe, p->n,
+                p->counts, p->his, p->block_base, blk_lo, d_probe_rows, d_build_rows);
+    else
+      PB_LAUNCH((overlap_emit_staged_kernel<false, false>), grid, kSweepThreads, 0, s, view_of(p->ix), (const int4 *)nullptr, p->pc, p->ps, p->pe, p->n,
+                p->counts, p->his, p->block_base, blk_lo, d_probe_rows, d_build_rows);
   } else if (p->ix->fast) {
     if (p->filter_op == PBGPU_FILTER_STRICT)
       PB_LAUNCH(overlap_emit_fast_kernel<true>, grid, kSweepThreads, 0, s, view_of(p->ix), p->pc, p->ps, p->pe, p->n, p->counts,

@@ -9,6 +9,8 @@ pytest)
   echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest_gpu.log 2>&1; echo rc=$?; tail -12 $O/${TAG}_pytest_gpu.log;;
 pytest_scale)
   echo "== pytest scale"; timeout 900 python -m pytest tests/test_gpu_scale.py -m gpu -x -q > $O/${TAG}_pytest_scale.log 2>&1; echo rc=$?; tail -12 $O/${TAG}_pytest_scale.log;;
+bins)
+  echo "== bins check"; PBGPU_BIN=1 timeout 900 python tests/tools/bins_check.py > $O/${TAG}_bins_check.log 2>&1; echo rc=$?; tail -8 $O/${TAG}_bins_check.log;;
 pytest_parity)
   echo "== pytest parity"; timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_api.py tests/test_gpu_unary.py -m gpu -x -q > $O/${TAG}_pytest_parity.log 2>&1; echo rc=$?; tail -12 $O/${TAG}_pytest_parity.log;;
 bench)
@@ -20,7 +22,10 @@ trace)
 ref)
   echo "== reference arm"; timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > $O/${TAG}_bench_ref.json 2> $O/${TAG}_bench_ref.err; echo rc=$?; cat $O/${TAG}_bench_ref.json;;
 launches)
-  echo "== ncu launch list (config 3, device only)"
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches.csv python bench.py --steps 1 --warmup 1 --skip-e2e --no-cpu-baseline --skip-secondary --skip-parity > $O/${TAG}_launches.log 2>&1; echo rc=$?; tail -3 $O/${TAG}_launches.log;;
+  echo "== ncu launch list (config 3: one build + count_overlaps + overlap, cold)"
+  PB_REPS=2 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_config3_launches.csv python tests/tools/profile_config3.py > $O/${TAG}_launches.log 2>&1; echo rc=$?; tail -3 $O/${TAG}_launches.log;;
+prof)
+  echo "== ncu --set full (config 3, one launch of every hot kernel)"
+  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"${PROF_REGEX:-prep_kernel|rs_onesweep|unpack_sorted|pmax_lookback|jdir_|bin_hist|bin_partition|binned_|unbin_|emit_staged|count_overlaps_fast|overlap_count_fast|overlap_emit}" -c ${PROF_COUNT:-24} -o $O/${TAG}_config3_prof -f python tests/tools/profile_config3.py > $O/${TAG}_prof.log 2>&1; echo rc=$?; tail -3 $O/${TAG}_prof.log; ls -la $O/${TAG}_config3_prof.ncu-rep;;
 esac
 done
