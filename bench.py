@@ -369,7 +369,9 @@ def stage_roofline(n, m, pairs, km, peak, peak_src):
                                "frac": v[0] / (v[1] * 1e-3) / 1e9 / peak} for k, v in cands.items()},
             "overlap_two_pass": {"ms": two_pass_ms, "algorithmic_bytes": b_overlap,
                                  "frac": b_overlap / (two_pass_ms * 1e-3) / 1e9 / peak if two_pass_ms else None},
-            "index_build_ms": km["partition_sort_ns"], "offset_scan_ms": km["scan_ns"]}
+            "index_build_ms": km["partition_sort_ns"], "offset_scan_ms": km["scan_ns"],
+            "bin_ms": km.get("bin_ns", 0.0), "unbin_ms": km.get("unbin_ns", 0.0),
+            "bin_note": "probe partition (histogram + one radix pass) of the step's LAST partitioned call; it is inside that call's stage time"}
 
 
 def run_single(args, dev, local):

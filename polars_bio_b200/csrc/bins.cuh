@@ -73,8 +73,8 @@ __global__ void __launch_bounds__(512) bin_hist_kernel(IndexView ix, const int32
 
 // One stable radix pass over the probes (see radix_sort.cuh: rs_onesweep_kernel for the scheme).  Dynamic shared memory:
 // the tile's records in bin order (64 KB).  WRITE_POS: also pos[row] = destination of the row (count_overlaps un-binning).
-template <bool WRITE_POS>
-__global__ void __launch_bounds__(kBinThreads, 2) bin_partition_kernel(IndexView ix, const int32_t *__restrict__ pc,
+template <bool WRITE_POS, int OCC>
+__global__ void __launch_bounds__(kBinThreads, OCC) bin_partition_kernel(IndexView ix, const int32_t *__restrict__ pc,
                                                                        const int32_t *__restrict__ ps, const int32_t *__restrict__ pe,
                                                                        int64_t n, int bin_shift, int strict,
                                                                        const uint32_t *__restrict__ totals /*[256]*/,
@@ -109,20 +109,29 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_partition_kernel(IndexView
 #pragma unroll
     for (int r = 0; r < kBinItems; ++r) rec[r] = make_probe_rec(ix, c[r], s[r], e[r], (uint32_t)(tbase + wofs + r * 32 + lane), strict != 0);
   }
+  // bins + the eight MATCH instructions first, then the serial counter chain that consumes them (radix_sort.cuh)
+  unsigned dg[kBinItems];
+  {
+    unsigned peers[kBinItems];
 #pragma unroll
-  for (int r = 0; r < kBinItems; ++r) {
-    const bool ok = wofs + r * 32 + lane < tile_n;
-    const unsigned d = ok ? (rec[r].w == -1 ? 0u : ((uint32_t)rec[r].x >> bin_shift)) : 0x100u;
-    const unsigned peers = __match_any_sync(0xffffffffu, d);
-    const int leader = __ffs(peers) - 1;
-    uint32_t old = 0;
-    if (ok && lane == leader) {
-      old = wcnt[warp][d];
-      wcnt[warp][d] = (uint16_t)(old + __popc(peers));
+    for (int r = 0; r < kBinItems; ++r) {
+      const bool ok = wofs + r * 32 + lane < tile_n;
+      dg[r] = ok ? (rec[r].w == -1 ? 0u : ((uint32_t)rec[r].x >> bin_shift)) : 0x100u;
+      peers[r] = __match_any_sync(0xffffffffu, dg[r]);
     }
-    old = __shfl_sync(0xffffffffu, old, leader);
-    q[r] = old + __popc(peers & lt);
-    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < kBinItems; ++r) {
+      const bool ok = dg[r] != 0x100u;
+      const int leader = __ffs(peers[r]) - 1;
+      uint32_t old = 0;
+      if (ok && lane == leader) {
+        old = wcnt[warp][dg[r]];
+        wcnt[warp][dg[r]] = (uint16_t)(old + __popc(peers[r]));
+      }
+      old = __shfl_sync(0xffffffffu, old, leader);
+      q[r] = old + __popc(peers[r] & lt);
+      __syncwarp();
+    }
   }
   __syncthreads();
   uint32_t run = 0;
@@ -134,9 +143,18 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_partition_kernel(IndexView
       run += t;
     }
   }
-  const uint32_t gbase = block_exclusive<SumU32, kBinThreads>(threadIdx.x < kBinRadix ? totals[threadIdx.x] : 0u, wt);
-  __syncthreads();
+  // local bin offsets are all the staging needs: the records leave the registers before the look-back starts
   const uint32_t lbase = block_exclusive<SumU32, kBinThreads>(run, wt);
+  if (threadIdx.x < kBinRadix) toff[threadIdx.x] = lbase;
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kBinItems; ++r) {
+    if (dg[r] != 0x100u) {
+      q[r] = toff[dg[r]] + wcnt[warp][dg[r]] + q[r];
+      stage[q[r]] = rec[r];
+    }
+  }
+  const uint32_t gbase = block_exclusive<SumU32, kBinThreads>(threadIdx.x < kBinRadix ? totals[threadIdx.x] : 0u, wt);
   if (threadIdx.x < kBinRadix) {
     const int d = threadIdx.x;
     uint32_t *mine = status + (size_t)tile * kBinRadix + d;
@@ -162,21 +180,14 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_partition_kernel(IndexView
       }
       st_volatile_u32(mine, (excl + run) | kLbPre);
     }
-    toff[d] = lbase;
     dbase[d] = gbase + excl - lbase;  // may wrap below zero: dbase[d] + local position is exact mod 2^32
   }
   __syncthreads();
+  if (WRITE_POS) {
 #pragma unroll
-  for (int r = 0; r < kBinItems; ++r) {
-    const int li = wofs + r * 32 + lane;
-    if (li < tile_n) {
-      const unsigned d = rec[r].w == -1 ? 0u : ((uint32_t)rec[r].x >> bin_shift);
-      q[r] = toff[d] + wcnt[warp][d] + q[r];
-      stage[q[r]] = rec[r];
-      if (WRITE_POS) pos[tbase + li] = dbase[d] + q[r];
-    }
+    for (int r = 0; r < kBinItems; ++r)
+      if (dg[r] != 0x100u) pos[tbase + wofs + r * 32 + lane] = dbase[dg[r]] + q[r];
   }
-  __syncthreads();
 #pragma unroll
   for (int r = 0; r < kBinItems; ++r) {
     const int p = r * kBinThreads + threadIdx.x;
@@ -186,6 +197,13 @@ __global__ void __launch_bounds__(kBinThreads, 2) bin_partition_kernel(IndexView
       recs[dbase[d] + (uint32_t)p] = v;
     }
   }
+}
+
+// four consecutive (end, row) entries, 32-byte aligned, in one request
+__device__ __forceinline__ void ld_er4(const uint2 *__restrict__ p, uint32_t (&w)[8]) {
+  asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+      : "l"(p));
 }
 
 // count of one partitioned probe; hi_out as fast_count()
@@ -347,13 +365,32 @@ __global__ void __launch_bounds__(kSweepThreads) overlap_emit_staged_kernel(Inde
       const uint32_t hi_slot = lo_slot + kEmitStagePairs < wtotal ? lo_slot + kEmitStagePairs : wtotal;
       if (mine && excl < hi_slot && excl + mine > lo_slot) {
         while (k < cnt && j >= jlo) {
-          const uint32_t slot = excl + (cnt - 1 - k);  // slot of the next hit to be found
-          if (slot < lo_slot) break;                  // belongs to a later round
-          int32_t ev; uint32_t rv;
-          if (generic) { ev = __ldg(ix.en + j); rv = __ldg(ix.row + j); }
-          else { const uint2 v = __ldg(ix.er + j); ev = (int32_t)v.x; rv = v.y; }  // (end, row) interleaved: one 8-byte load per candidate
-          --j;
-          if ((long long)ev > thr) { stage[warp][slot - lo_slot] = make_uint2(pid, rv); ++k; }
+          uint32_t slot = excl + (cnt - 1 - k);  // slot of the next hit to be found
+          if (slot < lo_slot) break;            // belongs to a later round
+          if (generic) {
+            const int32_t ev = __ldg(ix.en + j);
+            const uint32_t rv = __ldg(ix.row + j);
+            --j;
+            if ((long long)ev > thr) { stage[warp][slot - lo_slot] = make_uint2(pid, rv); ++k; }
+            continue;
+          }
+          // four (end, row) candidates per request: the L1TEX serves one line per lane and request whatever its width,
+          // and that request rate -- not bytes -- bounds this kernel (438 M single-entry loads = 3.1 ms on config 3)
+          const int64_t g0 = j & ~(int64_t)3;
+          uint32_t w[8];
+          ld_er4(ix.er + g0, w);
+          bool paused = false;
+#pragma unroll
+          for (int t = 3; t >= 0; --t) {
+            const int64_t jj = g0 + t;
+            if (jj <= j && jj >= jlo && k < cnt && !paused) {
+              slot = excl + (cnt - 1 - k);
+              if (slot < lo_slot) { paused = true; j = jj; }
+              else if ((long long)(int32_t)w[2 * t] > thr) { stage[warp][slot - lo_slot] = make_uint2(pid, w[2 * t + 1]); ++k; }
+            }
+          }
+          if (paused) break;
+          j = g0 - 1;
         }
       }
       __syncwarp();

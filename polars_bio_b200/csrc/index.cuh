@@ -693,6 +693,291 @@ __global__ void __launch_bounds__(256) make_end_keys_seg_kernel(const int32_t *_
   evals[i] = (uint64_t)i;
 }
 
+// ---- round 2: global-key build (fast path; <= 1024 contigs, no inverted rows, axis < 2^32) ----------------------------
+// The generic build sorts 16-byte (contig | start, end | row) pairs over every varying digit of the 37..64-bit key:
+// five passes for the human genome (four start bytes + the contig byte).  When the contig slices of the global axis are
+// known BEFORE the sort, the key is the 32-bit global start: four passes whatever the number of contigs, the row id
+// rides in the low half of the 64-bit key and the end travels as a 4-byte value -- 12 bytes per row and pass instead
+// of 16, and the sorted keys ARE the gs column.  Price: one extra streaming pass over the input for the per-contig
+// coordinate range (the slices), before the keys can be formed.
+struct GStats {
+  unsigned long long valid, inverted, max_len;
+  long long min_end, max_end;   // as 64-bit so that atomics on them are plain 64-bit min / max
+  unsigned long long blocks_done;
+};
+__global__ void __launch_bounds__(256) gstats_init_kernel(int32_t *__restrict__ cmin, int32_t *__restrict__ cmax, int32_t n_contigs, GStats *st) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < n_contigs) { cmin[c] = INT32_MAX; cmax[c] = INT32_MIN; }
+  if (c == 0) { st->valid = 0; st->inverted = 0; st->max_len = 0; st->min_end = INT32_MAX; st->max_end = INT32_MIN; st->blocks_done = 0; }
+}
+// per contig: smallest and largest start; overall: valid / inverted rows, longest interval, range of the ends.
+// Warp-aggregated: the lanes of a warp that share a contig reduce among themselves (MATCH + REDUX) and their leader
+// touches the block's shared-memory slot once.
+__global__ void __launch_bounds__(512) contig_stats_kernel(const int32_t *__restrict__ c, const int32_t *__restrict__ s,
+                                                           const int32_t *__restrict__ e, int64_t n, int32_t n_contigs,
+                                                           int32_t *__restrict__ cmin, int32_t *__restrict__ cmax, GStats *st) {
+  __shared__ int32_t smin[1024], smax[1024];
+  __shared__ unsigned long long sred[3][512 / 32];
+  __shared__ int sred_e[2][512 / 32];
+  for (int i = threadIdx.x; i < n_contigs; i += 512) { smin[i] = INT32_MAX; smax[i] = INT32_MIN; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  unsigned inv = 0, val = 0, mlen = 0;
+  int mn_e = INT32_MAX, mx_e = INT32_MIN;
+  const int64_t stride = (int64_t)gridDim.x * 512;
+  for (int64_t i0 = (int64_t)blockIdx.x * 512 + threadIdx.x; i0 - threadIdx.x + (threadIdx.x & ~31) < n; i0 += 2 * stride) {  // whole warps iterate together
+    int32_t cc[2], ss[2], ee[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t i = i0 + u * stride;
+      const bool in = i < n;
+      cc[u] = in ? c[i] : -1; ss[u] = in ? s[i] : 0; ee[u] = in ? e[i] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const bool ok = cc[u] >= 0 && cc[u] < n_contigs;
+      const unsigned peers = __match_any_sync(0xffffffffu, ok ? cc[u] : -1);
+      if (ok) {
+        const int lo = __reduce_min_sync(peers, ss[u]), hi = __reduce_max_sync(peers, ss[u]);
+        if (lane == __ffs(peers) - 1) { atomicMin(&smin[cc[u]], lo); atomicMax(&smax[cc[u]], hi); }
+        mn_e = min(mn_e, ee[u]); mx_e = max(mx_e, ee[u]);
+        inv += ss[u] > ee[u];
+        if (ee[u] >= ss[u]) mlen = max(mlen, (unsigned)((long long)ee[u] - (long long)ss[u]));
+        ++val;
+      }
+    }
+  }
+  inv = __reduce_add_sync(0xffffffffu, inv); val = __reduce_add_sync(0xffffffffu, val); mlen = __reduce_max_sync(0xffffffffu, mlen);
+  mn_e = __reduce_min_sync(0xffffffffu, mn_e); mx_e = __reduce_max_sync(0xffffffffu, mx_e);
+  const int w = threadIdx.x >> 5;
+  if (lane == 0) { sred[0][w] = inv; sred[1][w] = val; sred[2][w] = mlen; sred_e[0][w] = mn_e; sred_e[1][w] = mx_e; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_contigs; i += 512) {
+    if (smin[i] != INT32_MAX) atomicMin(cmin + i, smin[i]);
+    if (smax[i] != INT32_MIN) atomicMax(cmax + i, smax[i]);
+  }
+  if (threadIdx.x == 0) {
+    unsigned long long a = 0, b = 0, m2 = 0;
+    int e0 = INT32_MAX, e1 = INT32_MIN;
+    for (int k = 0; k < 512 / 32; ++k) { a += sred[0][k]; b += sred[1][k]; m2 = max(m2, sred[2][k]); e0 = min(e0, sred_e[0][k]); e1 = max(e1, sred_e[1][k]); }
+    if (b) {
+      if (a) atomicAdd(&st->inverted, a);
+      atomicAdd(&st->valid, b);
+      atomicMax(&st->max_len, m2);
+      atomicMin(&st->min_end, (long long)e0);
+      atomicMax(&st->max_end, (long long)e1);
+    }
+  }
+}
+// slices of the global axis from the per-contig start ranges (one block, <= 1024 contigs): ContigMap, total span, and
+// the six statistics words straight to the host mailbox (valid, inverted, max_len, min_end, max_end, total span)
+__global__ void __launch_bounds__(1024) contig_layout_mm_kernel(const int32_t *__restrict__ cmin, const int32_t *__restrict__ cmax,
+                                                                const GStats *__restrict__ st, int32_t n_contigs,
+                                                                ContigMap *__restrict__ cmap, unsigned long long *__restrict__ d_out /*[6]*/,
+                                                                volatile unsigned long long *mailbox, unsigned long long mailbox_seq) {
+  __shared__ unsigned long long wt[1024 / 32 + 1];
+  const int c = threadIdx.x;
+  const long long max_len = (long long)st->max_len;
+  ContigMap m;
+  m.off = 0; m.lo_m1 = 0; m.hi_p1 = 0; m.has = 0;
+  unsigned long long span = 0;
+  if (c < n_contigs && cmin[c] != INT32_MAX) {
+    m.lo_m1 = (long long)cmin[c] - 1;
+    m.hi_p1 = (long long)cmax[c] + max_len + 1;
+    m.has = 1;
+    span = (unsigned long long)(m.hi_p1 - m.lo_m1 + 1);
+  }
+  const unsigned long long off = block_exclusive<SumU64, 1024>(span, wt);
+  if (c < n_contigs) { m.off = (uint32_t)off; cmap[c] = m; }  // off is only used when the total fits 32 bits
+  if (threadIdx.x == 0) {
+    const unsigned long long w[6] = {st->valid, st->inverted, st->max_len, (unsigned long long)st->min_end, (unsigned long long)st->max_end,
+                                     wt[1024 / 32]};
+    for (int k = 0; k < 6; ++k) d_out[k] = w[k];
+    if (mailbox) {
+      for (int k = 0; k < 6; ++k) mailbox[k] = w[k];
+      __threadfence_system();
+      mailbox[15] = mailbox_seq;
+    }
+  }
+}
+// key = global start << 32 | row, value = end; digit totals of key bytes 4..7.  Null-keyed rows (and rows of contigs
+// beyond the table) get global start 0xFFFFFFFF: they sort behind every valid row and are cut off.
+__global__ void __launch_bounds__(kPrepThreads) gkeys_kernel(const int32_t *__restrict__ c, const int32_t *__restrict__ s,
+                                                             const int32_t *__restrict__ e, int64_t n, int32_t n_contigs,
+                                                             const ContigMap *__restrict__ cmap, uint64_t *__restrict__ keys,
+                                                             uint32_t *__restrict__ vals, uint32_t *__restrict__ digit_totals /*[kRsMaxPasses][256], zeroed*/) {
+  __shared__ uint32_t h[4][kRsRadix];
+  for (int i = threadIdx.x; i < 4 * kRsRadix; i += kPrepThreads) (&h[0][0])[i] = 0;
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * kPrepThreads;
+  for (int64_t i0 = (int64_t)blockIdx.x * kPrepThreads + threadIdx.x; i0 < n; i0 += 2 * stride) {
+    int32_t cc[2], ss[2], ee[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t i = i0 + u * stride;
+      const bool in = i < n;
+      cc[u] = in ? c[i] : -1; ss[u] = in ? s[i] : 0; ee[u] = in ? e[i] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i >= n) continue;
+      uint32_t g = 0xFFFFFFFFu;
+      if (cc[u] >= 0 && cc[u] < n_contigs) {
+        const ContigMap cm = cmap[cc[u]];
+        g = cm.off + (uint32_t)((long long)ss[u] - cm.lo_m1);
+      }
+      keys[i] = ((uint64_t)g << 32) | (uint32_t)i;
+      vals[i] = (uint32_t)ee[u];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) atomicAdd(&h[p][(g >> (8 * p)) & 0xff], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * kRsRadix; i += kPrepThreads) {
+    const uint32_t v = (&h[0][0])[i];
+    if (v) atomicAdd(digit_totals + 4 * kRsRadix + i, v);  // digit positions 4..7 of the 64-bit key
+  }
+}
+// contig of a global coordinate: the last contig whose slice starts at or below it (empty contigs have empty slices)
+__device__ __forceinline__ int32_t contig_of_g(const ContigMap *__restrict__ cmap, int32_t n_contigs, uint32_t g) {
+  int32_t lo = 0, hi = n_contigs;  // first c with off[c] > g
+  while (lo < hi) { const int32_t mid = lo + ((hi - lo) >> 1); if (cmap[mid].off <= g) lo = mid + 1; else hi = mid; }
+  return lo - 1;
+}
+// unpack of the global-key sort: SoA columns, gs, contig segments by boundary detection, "any end inversion?"
+__global__ void __launch_bounds__(256) unpack_gsorted_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, int64_t m,
+                                                             const ContigMap *__restrict__ cmap, int32_t n_contigs,
+                                                             int32_t *__restrict__ st, int32_t *__restrict__ en, uint32_t *__restrict__ row,
+                                                             uint2 *__restrict__ er, uint32_t *__restrict__ gs, int32_t *__restrict__ seg,
+                                                             unsigned long long *__restrict__ inversions) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned inv = 0;
+  if (i < m) {
+    const uint64_t k = keys[i];
+    const uint32_t g = (uint32_t)(k >> 32), e = vals[i];
+    const int32_t contig = contig_of_g(cmap, n_contigs, g);
+    const ContigMap cm = cmap[contig];
+    st[i] = (int32_t)((long long)(g - cm.off) + cm.lo_m1);
+    en[i] = (int32_t)e;
+    row[i] = (uint32_t)k;
+    er[i] = make_uint2(e, (uint32_t)k);
+    gs[i] = g;
+    int32_t prev = -1;
+    if (i > 0) {
+      prev = contig_of_g(cmap, n_contigs, (uint32_t)(keys[i - 1] >> 32));
+      if (prev == contig) inv = (int32_t)e < (int32_t)vals[i - 1];
+    }
+    for (int32_t c = prev + 1; c <= contig; ++c) seg[c] = (int32_t)i;
+    if (i == m - 1) for (int32_t c = contig + 1; c <= n_contigs; ++c) seg[c] = (int32_t)m;
+  }
+  const int any = __syncthreads_or((int)inv);
+  if (any && threadIdx.x == 0 && *(volatile unsigned long long *)inversions == 0ull) atomicMax(inversions, 1ull);
+}
+// gs of the generic build's sorted rows (contig from the packed sort key)
+__global__ void __launch_bounds__(256) gs_from_keys_kernel(const uint64_t *__restrict__ keys, int pos_bits, const int32_t *__restrict__ st, int64_t m,
+                                                           const ContigMap *__restrict__ cmap, uint32_t *__restrict__ gs) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) gs[i] = global_coord_of(keys, pos_bits, st, i, cmap);
+}
+// Directory marks from the gs column: no contig lookups -- a row's end sits (en - st) past its start on the global axis.
+// NESTED = false: ends ascend in start order; ge and both rank arrays by run filling.
+// NESTED = true : ge_tmp + one atomic per row on the bucket counter of its end (see jdir_mark_nested_kernel).
+template <bool NESTED>
+__global__ void __launch_bounds__(256) jdir_mark_g_kernel(const uint32_t *__restrict__ gs, const int32_t *__restrict__ st,
+                                                          const int32_t *__restrict__ en, int64_t m, int shift, uint32_t n_buckets,
+                                                          uint32_t *__restrict__ ge_out, uint32_t *__restrict__ rank_s,
+                                                          uint32_t *__restrict__ rank_e_or_cnt) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // no early return: the warp fills runs together
+  const bool ok = i < m;
+  long long s_prev = -1, s_cur = -1, e_prev = -1, e_cur = -1;
+  if (ok) {
+    const uint32_t g_s = gs[i];
+    const uint32_t g_e = g_s + (uint32_t)(en[i] - st[i]);
+    ge_out[i] = g_e;
+    s_cur = (long long)(g_s >> shift);
+    e_cur = (long long)(g_e >> shift);
+    if (NESTED) atomicAdd(rank_e_or_cnt + (g_e >> shift), 1u);
+    if (i > 0) {
+      const uint32_t p_s = gs[i - 1];
+      s_prev = (long long)(p_s >> shift);
+      if (!NESTED) e_prev = (long long)((p_s + (uint32_t)(en[i - 1] - st[i - 1])) >> shift);
+    }
+  }
+  const bool last = i == m - 1;
+  jdir_fill_run(rank_s, s_prev + 1, s_cur, (uint32_t)i, ok);
+  jdir_fill_run(rank_s, s_cur + 1, (long long)n_buckets, (uint32_t)m, last);
+  if (!NESTED) {
+    jdir_fill_run(rank_e_or_cnt, e_prev + 1, e_cur, (uint32_t)i, ok);
+    jdir_fill_run(rank_e_or_cnt, e_cur + 1, (long long)n_buckets, (uint32_t)m, last);
+  }
+}
+
+// Running maximum of `en` inside every contig, two levels (the single look-back pass of the first round-2 version spent
+// 68 % of its time in barriers: with 2048-row tiles a tile's walk over its ~1000 resident predecessors costs ten times
+// its own work).  Level 1: maximum of every tile; a scan of the 44 K tile maxima; level 2: the tile's own running maximum
+// on top of its prefix.  The scanned word is contig << 32 | biased end: it restarts by itself at contig boundaries.
+__device__ __forceinline__ void pmax_tile_words(const int32_t *__restrict__ seg, int32_t n_contigs, const int32_t *__restrict__ en,
+                                                int64_t m, int64_t i0, unsigned long long (&v)[kPmItems], unsigned long long &acc) {
+  acc = 0ull;
+  if (i0 < m) {
+    int32_t c = contig_of_pos(seg, n_contigs, i0);
+    int64_t next = __ldg(seg + c + 1);
+    int32_t e[kPmItems];
+    if (i0 + kPmItems <= m) {
+      const int4 a = *reinterpret_cast<const int4 *>(en + i0), b = *reinterpret_cast<const int4 *>(en + i0 + 4);
+      e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w; e[4] = b.x; e[5] = b.y; e[6] = b.z; e[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < kPmItems; ++j) e[j] = i0 + j < m ? en[i0 + j] : INT32_MIN;
+    }
+#pragma unroll
+    for (int j = 0; j < kPmItems; ++j) {
+      const int64_t i = i0 + j;
+      while (i >= next && c + 1 < n_contigs) { ++c; next = __ldg(seg + c + 1); }
+      const unsigned long long w = i < m ? (((unsigned long long)(uint32_t)c << 32) | ((uint32_t)e[j] ^ 0x80000000u)) : 0ull;
+      acc = acc > w ? acc : w;
+      v[j] = acc;  // inclusive running max inside the thread
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < kPmItems; ++j) v[j] = 0ull;
+  }
+}
+__global__ void __launch_bounds__(kPmThreads) pmax_tile_max_kernel(const int32_t *__restrict__ seg, int32_t n_contigs, const int32_t *__restrict__ en,
+                                                                   int64_t m, unsigned long long *__restrict__ tile_max) {
+  __shared__ unsigned long long wt[kPmThreads / 32 + 1];
+  unsigned long long v[kPmItems], acc;
+  pmax_tile_words(seg, n_contigs, en, m, (int64_t)blockIdx.x * kPmTile + (int64_t)threadIdx.x * kPmItems, v, acc);
+  (void)block_exclusive<MaxU64, kPmThreads>(acc, wt);
+  if (threadIdx.x == 0) tile_max[blockIdx.x] = wt[kPmThreads / 32];
+}
+__global__ void __launch_bounds__(kPmThreads) pmax_tile_final_kernel(const int32_t *__restrict__ seg, int32_t n_contigs, const int32_t *__restrict__ en,
+                                                                     int64_t m, const unsigned long long *__restrict__ tile_prefix /*exclusive*/,
+                                                                     int32_t *__restrict__ pmax) {
+  __shared__ unsigned long long wt[kPmThreads / 32 + 1];
+  unsigned long long v[kPmItems], acc;
+  const int64_t i0 = (int64_t)blockIdx.x * kPmTile + (int64_t)threadIdx.x * kPmItems;
+  pmax_tile_words(seg, n_contigs, en, m, i0, v, acc);
+  unsigned long long before = block_exclusive<MaxU64, kPmThreads>(acc, wt);
+  const unsigned long long pre = tile_prefix[blockIdx.x];
+  before = before > pre ? before : pre;
+  if (i0 >= m) return;
+  int32_t o[kPmItems];
+#pragma unroll
+  for (int j = 0; j < kPmItems; ++j) {
+    const unsigned long long w = v[j] > before ? v[j] : before;
+    o[j] = (int32_t)((uint32_t)w ^ 0x80000000u);
+  }
+  if (i0 + kPmItems <= m) {
+    *reinterpret_cast<int4 *>(pmax + i0) = make_int4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<int4 *>(pmax + i0 + 4) = make_int4(o[4], o[5], o[6], o[7]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < kPmItems; ++j) if (i0 + j < m) pmax[i0 + j] = o[j];
+  }
+}
+
 static inline int bit_length_u32(uint32_t x) {
   int b = 0;
   while (x) { ++b; x >>= 1; }

@@ -444,17 +444,148 @@ static int ensure_end_order(const pbgpu_index *cix, cudaStream_t s) {
   return PBGPU_OK;
 }
 
-// sweep_only: the caller wants the (contig, start, row) order, the segments and the running max of the ends only (the
-// unary sweeps of unary.cuh): the end order and the rank directory are skipped
-static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *d_s, const int32_t *d_e, int64_t m_in,
-                            int32_t n_contigs, cudaStream_t s, bool sweep_only = false) {
-  ix->m_in = m_in;
-  ix->n_contigs = n_contigs;
-  PB_CUDA(cudaGetDevice(&ix->device));
-  g_ev.mark(EV_BUILD0, s);
-  struct MarkEnd { cudaStream_t s; ~MarkEnd() { g_ev.mark(EV_BUILD1, s); } } mark_end{s};
-  Scratch sc(s);
-  BuildTrace bt(s);
+// PBGPU_BUILD=generic: always the generic front half (16-byte pairs, one pass per varying key byte); default: the
+// global-key front half whenever it applies (A/B runs; the parity tests run both)
+static bool build_generic_only() {
+  static bool v = [] { const char *e = getenv("PBGPU_BUILD"); return e && !strcmp(e, "generic"); }();
+  return v;
+}
+
+// what the two front halves of the build hand to the common back half
+struct BuildFront {
+  bool nested = false;
+  unsigned long long total_span = 0;   // 0: no fast path (not computed / does not apply)
+  long long max_len = 0;
+  ContigMap *d_cmap = nullptr;         // device, n_contigs entries (scratch), offsets final
+  const uint64_t *keys = nullptr;      // generic: the sorted (contig | start) keys (contig of position i); gkey: NULL (gs is ready)
+  void *idle = nullptr;                // scratch of at least 8 bytes per input row, free for reuse
+  uint64_t *idle2 = nullptr;           // a second such buffer (generic) or NULL
+  bool gs_ready = false;
+};
+
+static void set_slab1(pbgpu_index *ix, int32_t n_contigs, int64_t m, size_t *arr_b_out) {
+  const size_t seg_b = align_up(sizeof(int32_t) * ((size_t)n_contigs + 2)), arr_b = align_up(sizeof(int32_t) * (size_t)(m ? m : 1));
+  char *base = (char *)ix->slab;
+  ix->seg = (int32_t *)base;
+  ix->st = (int32_t *)(base + seg_b);
+  ix->en = (int32_t *)(base + seg_b + arr_b);
+  ix->row = (uint32_t *)(base + seg_b + 2 * arr_b);
+  ix->er = (uint2 *)(base + seg_b + 3 * arr_b);
+  ix->pmax = ix->en;       // until nested intervals are detected: running max == end,
+  ix->en_sorted = ix->en;  // end order == start order,
+  ix->en_pos = nullptr;    // identity
+  *arr_b_out = arr_b;
+}
+static size_t slab1_bytes(int32_t n_contigs, int64_t m) {
+  return align_up(sizeof(int32_t) * ((size_t)n_contigs + 2)) + 3 * align_up(sizeof(int32_t) * (size_t)(m ? m : 1)) +
+         align_up(sizeof(uint2) * (size_t)(m ? m : 1));
+}
+// bucket width of the rank directory: the smallest power of two that leaves at most m/0.6 buckets (0.6-1.2 indexed rows
+// per bucket: a record then holds ~3 keys on average of its 12 and crowded records stay below ~0.2 %), capped at 2^13
+static int jdir_shift_for(unsigned long long total_span, int64_t m) {
+  int shift = 0;
+  while (shift < kJMaxShift && (total_span >> shift) > ((unsigned long long)m * 5ull) / 3ull) ++shift;
+  shift += jdir_extra_shift();
+  return shift > kJMaxShift ? kJMaxShift : shift;
+}
+static int alloc_slab2(pbgpu_index *ix, unsigned long long total_span, int64_t m, int32_t n_contigs, cudaStream_t s) {
+  const int shift = jdir_shift_for(total_span, m);
+  const uint32_t nb = (uint32_t)(total_span >> shift) + 1;
+  const size_t cm_b = align_up(sizeof(ContigMap) * ((size_t)n_contigs + 1)), g_b = align_up(4 * (size_t)m);
+  const size_t d_b = align_up(sizeof(JRec) * ((size_t)nb + 1));
+  PB_TRY(dev_alloc(&ix->slab2, cm_b + 2 * g_b + d_b, s));
+  ix->bytes += cm_b + 2 * g_b + d_b;
+  char *b2 = (char *)ix->slab2;
+  ix->cmap = (ContigMap *)b2;
+  ix->gs = (uint32_t *)(b2 + cm_b);
+  ix->ge = (uint32_t *)(b2 + cm_b + g_b);
+  ix->jdir = (JRec *)(b2 + cm_b + 2 * g_b);
+  ix->shift = shift;
+  ix->n_buckets = nb;
+  ix->axis_span = (uint32_t)total_span;
+  return PBGPU_OK;
+}
+
+// ---- front half, global-key variant (index.cuh): returns *applies = false when the table needs the generic one ------
+static int build_front_gkey(pbgpu_index *ix, const int32_t *d_c, const int32_t *d_s, const int32_t *d_e, int64_t m_in, int32_t n_contigs,
+                            cudaStream_t s, Scratch &sc, BuildTrace &bt, BuildFront *fr, bool *applies) {
+  *applies = false;
+  int32_t *cmin = nullptr, *cmax = nullptr;
+  GStats *d_st = nullptr;
+  unsigned long long *d_words = nullptr;
+  ContigMap *d_cmap = nullptr;
+  PB_TRY(sc.get(&cmin, (size_t)n_contigs + 1));
+  PB_TRY(sc.get(&cmax, (size_t)n_contigs + 1));
+  PB_TRY(sc.get(&d_st, 1));
+  PB_TRY(sc.get(&d_words, 8));
+  PB_TRY(sc.get(&d_cmap, (size_t)n_contigs + 1));
+  PB_LAUNCH(gstats_init_kernel, (unsigned)cdiv(n_contigs > 0 ? n_contigs : 1, 256), 256, 0, s, cmin, cmax, n_contigs, d_st);
+  int64_t grid = cdiv(m_in, 512 * 2);
+  if (grid > kSMs * 4) grid = kSMs * 4;
+  PB_LAUNCH(contig_stats_kernel, (unsigned)grid, 512, 0, s, d_c, d_s, d_e, m_in, n_contigs, cmin, cmax, d_st);
+  const MailboxSlot slot = mailbox_open();
+  PB_LAUNCH(contig_layout_mm_kernel, 1, 1024, 0, s, cmin, cmax, d_st, n_contigs, d_cmap, d_words, slot.d, slot.seq);
+  PB_CHECK_LAUNCH();
+  unsigned long long w[6] = {0, 0, 0, 0, 0, 0};
+  if (slot.d) PB_TRY(mailbox_wait(slot, 6, w, s));
+  else PB_TRY(fetch_words(d_words, 6, w, s));
+  bt.lap("contig ranges + layout + stats fetch");
+  const int64_t m = (int64_t)w[0];
+  const unsigned long long total_span = w[5];
+  if (w[1] != 0 || m == 0 || total_span == 0 || total_span >= 0xFFFFFFF0ull) return PBGPU_OK;  // inverted rows / empty / axis too long
+  *applies = true;
+  ix->m = m;
+  ix->has_inverted = 0;
+  ix->min_end = (int32_t)(long long)w[3];
+  ix->max_end = (int32_t)(long long)w[4];
+  fr->max_len = (long long)w[2];
+  fr->total_span = total_span;
+  fr->d_cmap = d_cmap;
+  size_t arr_b = 0;
+  PB_TRY(dev_alloc(&ix->slab, slab1_bytes(n_contigs, m), s));
+  ix->bytes = slab1_bytes(n_contigs, m);
+  set_slab1(ix, n_contigs, m, &arr_b);
+  PB_TRY(alloc_slab2(ix, total_span, m, n_contigs, s));
+  PB_CUDA(cudaMemcpyAsync(ix->cmap, d_cmap, sizeof(ContigMap) * (size_t)n_contigs, cudaMemcpyDeviceToDevice, s));
+  bt.lap("slab allocs");
+  uint64_t *k1 = nullptr, *k2 = nullptr;
+  uint32_t *v1 = nullptr, *v2 = nullptr, *d_totals = nullptr;
+  PB_TRY(sc.get(&k1, (size_t)m_in));
+  PB_TRY(sc.get(&k2, (size_t)m_in));
+  PB_TRY(sc.get(&v1, (size_t)m_in));
+  PB_TRY(sc.get(&v2, (size_t)m_in));
+  PB_TRY(sc.get(&d_totals, (size_t)kRsMaxPasses * kRsRadix));
+  PB_CUDA(cudaMemsetAsync(d_totals, 0, sizeof(uint32_t) * kRsMaxPasses * kRsRadix, s));
+  grid = cdiv(m_in, kPrepThreads * 2);
+  if (grid > kSMs * 2) grid = kSMs * 2;
+  PB_LAUNCH(gkeys_kernel, (unsigned)grid, kPrepThreads, 0, s, d_c, d_s, d_e, m_in, n_contigs, d_cmap, k1, v1, d_totals);
+  PB_CHECK_LAUNCH();
+  // key bytes 4..7 hold the global start; without null-keyed rows (their sentinel sets every bit) only the bytes below
+  // the top bit of the axis length vary
+  int dpos[4], ndig = 0;
+  const int vbits = m < m_in ? 32 : bit_length_u32((uint32_t)(total_span - 1));
+  for (int p = 0; p * 8 < vbits; ++p) dpos[ndig++] = 4 + p;
+  SortedKV<uint32_t> sorted;
+  PB_TRY(radix_sort_digits<uint32_t>(k1, v1, k2, v2, m_in, dpos, ndig, d_totals, s, &sorted));
+  bt.lap("global keys + start sort");
+  fr->idle = sorted.keys == k1 ? (void *)k2 : (void *)k1;
+  unsigned long long *d_inv = nullptr;
+  PB_TRY(sc.get(&d_inv, 1));
+  PB_CUDA(cudaMemsetAsync(d_inv, 0, sizeof(unsigned long long), s));
+  PB_LAUNCH(unpack_gsorted_kernel, (unsigned)cdiv(m, 256), 256, 0, s, sorted.keys, sorted.vals, m, d_cmap, n_contigs, ix->st, ix->en, ix->row,
+            ix->er, ix->gs, ix->seg, d_inv);
+  PB_CHECK_LAUNCH();
+  unsigned long long inv = 0;
+  PB_TRY(fetch_words(d_inv, 1, &inv, s));
+  bt.lap("unpack + nesting fetch");
+  fr->nested = inv != 0;
+  fr->gs_ready = true;
+  return PBGPU_OK;
+}
+
+// ---- front half, generic variant: any contig count, inverted rows, axes beyond 2^32 --------------------------------------
+static int build_front_generic(pbgpu_index *ix, const int32_t *d_c, const int32_t *d_s, const int32_t *d_e, int64_t m_in, int32_t n_contigs,
+                               cudaStream_t s, Scratch &sc, BuildTrace &bt, BuildFront *fr) {
   // 1. ONE pass over the input: coordinate statistics (key width, fast-path eligibility), the sort keys
   //    contig << 32 | biased start  with values  end << 32 | row, and the digit totals of every radix pass.
   //    The key format does not depend on the statistics, so nothing waits for the host before it.
@@ -492,47 +623,39 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
   const int64_t m = (int64_t)hs.valid;
   ix->m = m;
   ix->has_inverted = hs.inverted != 0;
-  // slab 1: seg + start-ordered rows
-  const size_t seg_b = align_up(sizeof(int32_t) * ((size_t)n_contigs + 2)), arr_b = align_up(sizeof(int32_t) * (size_t)(m ? m : 1));
-  const size_t er_b = align_up(sizeof(uint2) * (size_t)(m ? m : 1));
-  PB_TRY(dev_alloc(&ix->slab, seg_b + 3 * arr_b + er_b, s));
+  ix->min_end = hs.min_end;
+  ix->max_end = hs.max_end;
+  fr->max_len = (long long)hs.max_len;
+  size_t arr_b = 0;
+  PB_TRY(dev_alloc(&ix->slab, slab1_bytes(n_contigs, m), s));
   bt.lap("slab 1 alloc");
-  ix->bytes = seg_b + 3 * arr_b + er_b;
-  char *base = (char *)ix->slab;
-  ix->seg = (int32_t *)base;
-  ix->st = (int32_t *)(base + seg_b);
-  ix->en = (int32_t *)(base + seg_b + arr_b);
-  ix->row = (uint32_t *)(base + seg_b + 2 * arr_b);
-  ix->er = (uint2 *)(base + seg_b + 3 * arr_b);
-  ix->pmax = ix->en;       // until nested intervals are detected: running max == end,
-  ix->en_sorted = ix->en;  // end order == start order,
-  ix->en_pos = nullptr;    // identity
+  ix->bytes = slab1_bytes(n_contigs, m);
+  set_slab1(ix, n_contigs, m, &arr_b);
   if (m == 0) {
     PB_CUDA(cudaMemsetAsync(ix->seg, 0, sizeof(int32_t) * ((size_t)n_contigs + 2), s));
     return PBGPU_OK;
   }
-
   // 2. radix partition by contig + sort by start: one stable LSD sort of the (contig | start) keys.  Only digits
   //    that can differ are sorted: every biased start lies between the biased min and max, so they agree above the
   //    highest bit of min ^ max; the contig digits are needed when there is more than one contig or a null key
   //    (sentinel code n_contigs, which must end up behind every real contig).
-  auto varying_digits = [](int32_t lo, int32_t hi, int *pos, int np) {
-    const int vb = bit_length_u32((uint32_t)lo ^ (uint32_t)hi);
-    for (int p = 0; p * 8 < vb; ++p) pos[np++] = p;
-    return np;
-  };
-  int dpos[kRsMaxPasses], ndig = varying_digits(hs.min_start, hs.max_start, dpos, 0);
+  int dpos[kRsMaxPasses], ndig = 0;
+  {
+    const int vb = bit_length_u32((uint32_t)hs.min_start ^ (uint32_t)hs.max_start);
+    for (int p = 0; p * 8 < vb; ++p) dpos[ndig++] = p;
+  }
   const bool contig_passes = n_contigs > 1 || m < m_in;
   if (contig_passes) for (int q = 0; q < contig_digits; ++q) dpos[ndig++] = 4 + q;
   SortedPairs sorted;
-  PB_TRY(radix_sort_digits(keys, vals, keys2, vals2, m_in, dpos, ndig, d_totals, s, &sorted));
+  PB_TRY(radix_sort_digits<uint64_t>(keys, vals, keys2, vals2, m_in, dpos, ndig, d_totals, s, &sorted));
   bt.lap("start sort");
-  uint64_t *keys_alt = sorted.keys == keys ? keys2 : keys, *vals_alt = sorted.vals == vals ? vals2 : vals;  // free for reuse
+  fr->idle = sorted.keys == keys ? (void *)keys2 : (void *)keys;
+  fr->idle2 = sorted.vals == vals ? vals2 : vals;
   keys = sorted.keys;
   vals = sorted.vals;
-
+  fr->keys = keys;
   // 3. unpack + segments + nested-interval detection; contig slices of the global axis.  One host round trip then
-  //    decides two things: second sort needed (nested intervals)?  global axis fits 32 bits (fast path)?
+  //    decides two things: nested intervals?  global axis fits 32 bits (fast path)?
   const bool try_fast = !ix->has_inverted;
   unsigned long long *d_meta = nullptr;  // [0] end inversions, [1] total span
   unsigned long long *d_span = nullptr;
@@ -549,10 +672,10 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
     if (small_table) {
       meta_slot = mailbox_open();
       PB_LAUNCH(contig_layout_kernel, 1, 1024, 0, s, ix->seg, ix->st, (long long)hs.max_len, n_contigs, d_cmap_tmp, d_meta, meta_slot.d, meta_slot.seq);
-    }
-    else {
+    } else {
       PB_LAUNCH(contig_span_kernel, (unsigned)cdiv(n_contigs, 128), 128, 0, s, ix->seg, ix->st, (long long)hs.max_len, n_contigs, d_cmap_tmp, d_span);
       PB_TRY((device_scan<SumU64, false>(d_span, d_span, n_contigs, d_meta + 1, s)));
+      PB_LAUNCH(contig_off_kernel, (unsigned)cdiv(n_contigs, 128), 128, 0, s, d_span, n_contigs, d_cmap_tmp);
     }
   }
   PB_CHECK_LAUNCH();
@@ -560,15 +683,39 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
   if (meta_slot.d) PB_TRY(mailbox_wait(meta_slot, 2, h_meta, s));
   else PB_TRY(fetch_words(d_meta, 2, h_meta, s));
   bt.lap("unpack + layout + meta fetch");
-  const bool nested = h_meta[0] != 0;
-  ix->nested = nested;
+  fr->nested = h_meta[0] != 0;
+  fr->total_span = try_fast ? h_meta[1] : 0;
+  fr->d_cmap = d_cmap_tmp;
+  return PBGPU_OK;
+}
 
-  // 4. nested intervals: running maximum of the ends inside every contig, one look-back pass.  The ends are NOT sorted
-  //    here any more (round 1: a second five-pass radix sort, 7 of the 15.8 ms of a 90 M-row build): the fast path's
-  //    directory only needs them grouped by bucket (step 5), and the end order proper (en_sorted / en_pos: nearest and
-  //    the generic kernels) is built on first use (ensure_end_order) or right away when the fast path is not available.
-  ix->min_end = hs.min_end;
-  ix->max_end = hs.max_end;
+// sweep_only: the caller wants the (contig, start, row) order, the segments and the running max of the ends only (the
+// unary sweeps of unary.cuh): the end order and the rank directory are skipped
+static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *d_s, const int32_t *d_e, int64_t m_in,
+                            int32_t n_contigs, cudaStream_t s, bool sweep_only = false) {
+  ix->m_in = m_in;
+  ix->n_contigs = n_contigs;
+  PB_CUDA(cudaGetDevice(&ix->device));
+  g_ev.mark(EV_BUILD0, s);
+  struct MarkEnd { cudaStream_t s; ~MarkEnd() { g_ev.mark(EV_BUILD1, s); } } mark_end{s};
+  Scratch sc(s);
+  BuildTrace bt(s);
+  BuildFront fr;
+  bool gkey = false;
+  if (!build_generic_only() && m_in > 0 && n_contigs >= 1 && n_contigs <= 1024)
+    PB_TRY(build_front_gkey(ix, d_c, d_s, d_e, m_in, n_contigs, s, sc, bt, &fr, &gkey));
+  if (!gkey) PB_TRY(build_front_generic(ix, d_c, d_s, d_e, m_in, n_contigs, s, sc, bt, &fr));
+  const int64_t m = ix->m;
+  if (m == 0) return PBGPU_OK;
+  const bool nested = fr.nested;
+  ix->nested = nested;
+  const size_t arr_b = align_up(sizeof(int32_t) * (size_t)m);
+
+  // 4. nested intervals: running maximum of the ends inside every contig (two levels: tile maxima, their scan, tiles).
+  //    The ends are NOT sorted here any more (round 1: a second five-pass radix sort, 7 of the 15.8 ms of a 90 M-row
+  //    build): the fast path's directory only needs them grouped by bucket (step 5), and the end order proper
+  //    (en_sorted / en_pos: nearest and the generic kernels) is built on first use (ensure_end_order) or right away
+  //    when the fast path is not available.
   if (nested) {
     PB_TRY(dev_alloc(&ix->slab_n, arr_b, s));
     ix->bytes += arr_b;
@@ -576,57 +723,43 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
     ix->en_sorted = nullptr;  // lazy
     ix->en_pos = nullptr;
     const int64_t tiles = cdiv(m, kPmTile);
-    unsigned long long *pm_status = nullptr;
-    PB_TRY(sc.get(&pm_status, (size_t)tiles + 1));
-    PB_CUDA(cudaMemsetAsync(pm_status, 0, sizeof(unsigned long long) * ((size_t)tiles + 1), s));
-    PB_LAUNCH(pmax_lookback_kernel, (unsigned)tiles, kPmThreads, 0, s, ix->seg, n_contigs, ix->en, m, ix->pmax, pm_status,
-              (unsigned int *)(pm_status + tiles));
+    unsigned long long *tile_max = nullptr;
+    PB_TRY(sc.get(&tile_max, (size_t)tiles + 1));
+    PB_LAUNCH(pmax_tile_max_kernel, (unsigned)tiles, kPmThreads, 0, s, ix->seg, n_contigs, ix->en, m, tile_max);
+    PB_CHECK_LAUNCH();
+    PB_TRY((device_scan<MaxU64, false>(tile_max, tile_max, tiles, nullptr, s)));
+    PB_LAUNCH(pmax_tile_final_kernel, (unsigned)tiles, kPmThreads, 0, s, ix->seg, n_contigs, ix->en, m, tile_max, ix->pmax);
     PB_CHECK_LAUNCH();
     bt.lap("nested: running max");
   }
   if (sweep_only) return PBGPU_OK;
 
   // 5. fast path: global axis + rank directory
-  const unsigned long long total_span = h_meta[1];
-  if (try_fast && total_span > 0 && total_span < 0xFFFFFFF0ull) {
-    // bucket width: the smallest power of two that leaves at most m/0.6 buckets (0.6-1.2 indexed rows per bucket:
-    // a record then holds ~3 keys on average of its 12 and crowded records stay below ~0.2 %), capped at 2^13
-    int shift = 0;
-    while (shift < kJMaxShift && (total_span >> shift) > ((unsigned long long)m * 5ull) / 3ull) ++shift;
-    shift += jdir_extra_shift();
-    if (shift > kJMaxShift) shift = kJMaxShift;
-    const uint32_t nb = (uint32_t)(total_span >> shift) + 1;
-    const size_t cm_b = align_up(sizeof(ContigMap) * ((size_t)n_contigs + 1)), g_b = align_up(4 * (size_t)m);
-    const size_t d_b = align_up(sizeof(JRec) * ((size_t)nb + 1));
-    PB_TRY(dev_alloc(&ix->slab2, cm_b + 2 * g_b + d_b, s));
-    bt.lap("slab 2 alloc");
-    ix->bytes += cm_b + 2 * g_b + d_b;
-    char *b2 = (char *)ix->slab2;
-    ix->cmap = (ContigMap *)b2;
-    ix->gs = (uint32_t *)(b2 + cm_b);
-    ix->ge = (uint32_t *)(b2 + cm_b + g_b);
-    ix->jdir = (JRec *)(b2 + cm_b + 2 * g_b);
-    ix->shift = shift;
-    ix->n_buckets = nb;
-    ix->axis_span = (uint32_t)total_span;
-    PB_CUDA(cudaMemcpyAsync(ix->cmap, d_cmap_tmp, sizeof(ContigMap) * (size_t)n_contigs, cudaMemcpyDeviceToDevice, s));
-    if (!small_table) PB_LAUNCH(contig_off_kernel, (unsigned)cdiv(n_contigs, 128), 128, 0, s, d_span, n_contigs, ix->cmap);
+  const unsigned long long total_span = fr.total_span;
+  if (!ix->has_inverted && total_span > 0 && total_span < 0xFFFFFFF0ull) {
+    if (!ix->slab2) {  // generic front half: the directory slab and the gs column are still to come
+      PB_TRY(alloc_slab2(ix, total_span, m, n_contigs, s));
+      bt.lap("slab 2 alloc");
+      PB_CUDA(cudaMemcpyAsync(ix->cmap, fr.d_cmap, sizeof(ContigMap) * (size_t)n_contigs, cudaMemcpyDeviceToDevice, s));
+      PB_LAUNCH(gs_from_keys_kernel, (unsigned)cdiv(m, 256), 256, 0, s, fr.keys, 32, ix->st, m, ix->cmap, ix->gs);
+      PB_CHECK_LAUNCH();
+    }
+    const int shift = ix->shift;
+    const uint32_t nb = ix->n_buckets;
     uint32_t *rank_s = nullptr, *rank_e = nullptr;
     PB_TRY(sc.get(&rank_s, (size_t)nb + 1));
     PB_TRY(sc.get(&rank_e, (size_t)nb + 2));  // + the crowded-ends word of the nested variant
-    if (!nested) {  // end order == start order: both rank arrays by run filling, one pass over the sorted rows
-      PB_LAUNCH(jdir_mark_kernel, (unsigned)cdiv(m, 256), 256, 0, s, keys, keys, pos_bits, ix->st, ix->en, m,
-                ix->cmap, shift, nb, ix->gs, ix->ge, rank_s, rank_e);
+    if (!nested) {  // end order == start order: ge and both rank arrays by run filling, one pass over the sorted rows
+      PB_LAUNCH(jdir_mark_g_kernel<false>, (unsigned)cdiv(m, 256), 256, 0, s, ix->gs, ix->st, ix->en, m, shift, nb, ix->ge, rank_s, rank_e);
       PB_LAUNCH(jdir_pack2_kernel<false>, (unsigned)cdiv((int64_t)nb + 1, 256), 256, 0, s, ix->gs, ix->ge, m, shift, nb, rank_s, rank_e, ix->jdir,
                 (unsigned int *)nullptr);
       PB_CHECK_LAUNCH();
       ix->ge_sorted = 1;
     } else {  // ends grouped by bucket (counting sort with the buckets as bins), unordered inside a bucket
-      uint32_t *ge_tmp = (uint32_t *)keys_alt;  // the sort's idle buffer
+      uint32_t *ge_tmp = (uint32_t *)fr.idle;  // the sort's idle buffer
       unsigned int *d_crowded = rank_e + nb + 1;
       PB_CUDA(cudaMemsetAsync(rank_e, 0, sizeof(uint32_t) * ((size_t)nb + 2), s));
-      PB_LAUNCH(jdir_mark_nested_kernel, (unsigned)cdiv(m, 256), 256, 0, s, keys, pos_bits, ix->st, ix->en, m, ix->cmap, shift, nb, ix->gs,
-                ge_tmp, rank_s, rank_e);
+      PB_LAUNCH(jdir_mark_g_kernel<true>, (unsigned)cdiv(m, 256), 256, 0, s, ix->gs, ix->st, ix->en, m, shift, nb, ge_tmp, rank_s, rank_e);
       PB_CHECK_LAUNCH();
       PB_TRY((device_scan<SumU32, false>(rank_e, rank_e, (int64_t)nb + 1, nullptr, s)));
       PB_LAUNCH(jdir_place_ends_kernel, (unsigned)cdiv(m, 256), 256, 0, s, ge_tmp, m, shift, rank_e, ix->ge);
@@ -644,13 +777,15 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
       }
       ix->ge_sorted = 0;
       if (crowded > (unsigned long long)kCrowdedLinearMax) {
-        uint64_t *gk = keys_alt, *gv = vals_alt, *gk2 = nullptr, *gv2 = nullptr;  // keys_alt's first half still holds ge_tmp: not needed any more
+        uint64_t *gk = nullptr, *gv = nullptr, *gk2 = nullptr, *gv2 = nullptr;
+        PB_TRY(sc.get(&gk, (size_t)m));
+        PB_TRY(sc.get(&gv, (size_t)m));
         PB_TRY(sc.get(&gk2, (size_t)m));
         PB_TRY(sc.get(&gv2, (size_t)m));
         PB_LAUNCH(widen_u32_keys_kernel, (unsigned)cdiv(m, 256), 256, 0, s, ix->ge, m, gk, gv);
         int gpos[4] = {0, 1, 2, 3};
         SortedPairs gsrt;
-        PB_TRY(radix_sort_digits(gk, gv, gk2, gv2, m, gpos, 4, nullptr, s, &gsrt));
+        PB_TRY(radix_sort_digits<uint64_t>(gk, gv, gk2, gv2, m, gpos, 4, nullptr, s, &gsrt));
         PB_LAUNCH(narrow_u32_keys_kernel, (unsigned)cdiv(m, 256), 256, 0, s, gsrt.keys, m, ix->ge);
         PB_CHECK_LAUNCH();
         ix->ge_sorted = 1;
@@ -735,16 +870,18 @@ static int bin_probes(const pbgpu_index *ix, const int32_t *pc, const int32_t *p
   constexpr size_t stage_b = sizeof(int4) * kBinTile;
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(bin_partition_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_b);
-    cudaFuncSetAttribute(bin_partition_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_b);
+    cudaFuncSetAttribute(bin_partition_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_b);
+    cudaFuncSetAttribute(bin_partition_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_b);
+    cudaFuncSetAttribute(bin_partition_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_b);
+    cudaFuncSetAttribute(bin_partition_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_b);
   });
   const int strict = filter_op == PBGPU_FILTER_STRICT;
-  if (write_pos)
-    PB_LAUNCH(bin_partition_kernel<true>, (unsigned)tiles, kBinThreads, stage_b, s, view_of(ix), pc, ps, pe, n, out->bin_shift, strict, totals, status,
-              ticket, out->recs, out->pos);
-  else
-    PB_LAUNCH(bin_partition_kernel<false>, (unsigned)tiles, kBinThreads, stage_b, s, view_of(ix), pc, ps, pe, n, out->bin_shift, strict, totals, status,
-              ticket, out->recs, out->pos);
+#define PB_BINPART(WP, OCC)                                                                                                         \
+  PB_LAUNCH((bin_partition_kernel<WP, OCC>), (unsigned)tiles, kBinThreads, stage_b, s, view_of(ix), pc, ps, pe, n, out->bin_shift, strict, \
+            totals, status, ticket, out->recs, out->pos)
+  if (rs_occ() == 3) { if (write_pos) PB_BINPART(true, 3); else PB_BINPART(false, 3); }
+  else { if (write_pos) PB_BINPART(true, 2); else PB_BINPART(false, 2); }
+#undef PB_BINPART
   PB_CHECK_LAUNCH();
   g_ev.mark(EV_BIN1, s);
   return PBGPU_OK;

@@ -144,6 +144,12 @@ __global__ void __launch_bounds__(kRsThreads) rs_scatter_kernel(const uint64_t *
 constexpr uint32_t kLbAgg = 1u << 30, kLbPre = 2u << 30, kLbMask = (1u << 30) - 1u;
 constexpr int kRsMaxPasses = 8;
 constexpr int kLbWindow = 8;
+// resident blocks per SM the single-kernel passes are compiled for (register cap = 65536 / (512 * OCC)): both variants
+// are built, PBGPU_RS_OCC=2|3 picks at run time (A/B; default below)
+static inline int rs_occ() {
+  static int v = [] { const char *e = getenv("PBGPU_RS_OCC"); return (e && e[0] == '2') ? 2 : 3; }();
+  return v;
+}
 
 __global__ void __launch_bounds__(kRsThreads) rs_hist_all_kernel(const uint64_t *__restrict__ keys, int64_t n, int passes,
                                                                  uint32_t *__restrict__ digit_totals /*[passes][256], zeroed*/) {
@@ -177,10 +183,17 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v) {
   asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(kRsThreads, 2) rs_onesweep_kernel(const uint64_t *__restrict__ keys_in,
-                                                                    const uint64_t *__restrict__ vals_in,
+// V: value type moved along with the 64-bit key (uint64_t: end | row of the generic build; uint32_t: the end column of the
+// global-key build, where the row id rides in the low half of the key).
+// Register diet (round 2; ncu r2e: 64 registers -> 2 blocks of 512 per SM, warps 49 % active, short-scoreboard + barrier
+// stalls, DRAM 35 % busy): the eight MATCH instructions of a thread are issued back to back before the serial counter
+// chain that consumes them, and the values are loaded only after the keys have left for global memory, so keys and
+// values are never live together.
+template <typename V, int OCC>
+__global__ void __launch_bounds__(kRsThreads, OCC) rs_onesweep_kernel(const uint64_t *__restrict__ keys_in,
+                                                                    const V *__restrict__ vals_in,
                                                                     uint64_t *__restrict__ keys_out,
-                                                                    uint64_t *__restrict__ vals_out, int64_t n, int shift,
+                                                                    V *__restrict__ vals_out, int64_t n, int shift,
                                                                     const uint32_t *__restrict__ digit_totals /*[256] of this pass*/,
                                                                     uint32_t *status /*[nblk][256], zeroed*/,
                                                                     uint32_t *ticket /*zeroed*/) {
@@ -200,30 +213,36 @@ __global__ void __launch_bounds__(kRsThreads, 2) rs_onesweep_kernel(const uint64
 
   // warp w owns the contiguous slice [tbase + w*256, +256): round r covers 32 consecutive keys
   const int wofs = warp * (32 * kRsItems);
-  uint64_t k[kRsItems], v[kRsItems];
+  uint64_t k[kRsItems];
   uint32_t q[kRsItems];  // rank inside (warp, digit), later the local position in the tile
   const unsigned lt = lanemask_lt();
 #pragma unroll
   for (int r = 0; r < kRsItems; ++r) {
     const int li = wofs + r * 32 + lane;
-    const bool ok = li < tile_n;
-    k[r] = ok ? keys_in[tbase + li] : 0;
-    v[r] = ok ? vals_in[tbase + li] : 0;
+    k[r] = li < tile_n ? keys_in[tbase + li] : 0;
   }
+  {
+    unsigned peers[kRsItems];
 #pragma unroll
-  for (int r = 0; r < kRsItems; ++r) {
-    const bool ok = wofs + r * 32 + lane < tile_n;
-    const unsigned d = ok ? (unsigned)((k[r] >> shift) & 0xff) : 0x100u;  // 0x100: out-of-range lanes group together
-    const unsigned peers = __match_any_sync(0xffffffffu, d);
-    const int leader = __ffs(peers) - 1;
-    uint32_t old = 0;
-    if (ok && lane == leader) {
-      old = wcnt[warp][d];
-      wcnt[warp][d] = (uint16_t)(old + __popc(peers));
+    for (int r = 0; r < kRsItems; ++r) {
+      const bool ok = wofs + r * 32 + lane < tile_n;
+      const unsigned d = ok ? (unsigned)((k[r] >> shift) & 0xff) : 0x100u;  // 0x100: out-of-range lanes group together
+      peers[r] = __match_any_sync(0xffffffffu, d);
     }
-    old = __shfl_sync(0xffffffffu, old, leader);
-    q[r] = old + __popc(peers & lt);
-    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < kRsItems; ++r) {
+      const bool ok = wofs + r * 32 + lane < tile_n;
+      const unsigned d = (unsigned)((k[r] >> shift) & 0xff);
+      const int leader = __ffs(peers[r]) - 1;
+      uint32_t old = 0;
+      if (ok && lane == leader) {
+        old = wcnt[warp][d];
+        wcnt[warp][d] = (uint16_t)(old + __popc(peers[r]));
+      }
+      old = __shfl_sync(0xffffffffu, old, leader);
+      q[r] = old + __popc(peers[r] & lt);
+      __syncwarp();
+    }
   }
   __syncthreads();
   // per digit: exclusive prefix over warps; run = the tile's count of digit d
@@ -236,11 +255,20 @@ __global__ void __launch_bounds__(kRsThreads, 2) rs_onesweep_kernel(const uint64
       run += t;
     }
   }
-  // global base of every digit (exclusive scan of this pass's totals) and first local position of every digit
-  // (exclusive scan of the tile's counts); all threads take part in the block scans
-  const uint32_t gbase = block_exclusive<SumU32, kRsThreads>(threadIdx.x < kRsRadix ? digit_totals[threadIdx.x] : 0u, wt);
-  __syncthreads();  // wt is reused
+  // first local position of every digit (exclusive scan of the tile's counts): everything the staging needs.  The global
+  // bases (which wait for the predecessors) are only needed by the copy-out, so the keys go to shared memory first.
   const uint32_t lbase = block_exclusive<SumU32, kRsThreads>(run, wt);
+  if (threadIdx.x < kRsRadix) toff[threadIdx.x] = lbase;
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kRsItems; ++r) {
+    if (wofs + r * 32 + lane < tile_n) {
+      const unsigned d = (unsigned)((k[r] >> shift) & 0xff);
+      q[r] = toff[d] + wcnt[warp][d] + q[r];
+      stage[q[r]] = k[r];
+    }
+  }
+  const uint32_t gbase = block_exclusive<SumU32, kRsThreads>(threadIdx.x < kRsRadix ? digit_totals[threadIdx.x] : 0u, wt);  // (barriers inside)
   if (threadIdx.x < kRsRadix) {
     const int d = threadIdx.x;
     uint32_t *mine = status + (size_t)tile * kRsRadix + d;
@@ -266,18 +294,14 @@ __global__ void __launch_bounds__(kRsThreads, 2) rs_onesweep_kernel(const uint64
       }
       st_volatile_u32(mine, (excl + run) | kLbPre);
     }
-    toff[d] = lbase;
     dbase[d] = gbase + excl - lbase;  // may wrap below zero: dbase[d] + local position is exact mod 2^32
   }
-  __syncthreads();
-  // keys to their local rank
+  // values: loaded while the look-back is under way (the warps without a digit have nothing else to do)
+  V v[kRsItems];
 #pragma unroll
   for (int r = 0; r < kRsItems; ++r) {
-    if (wofs + r * 32 + lane < tile_n) {
-      const unsigned d = (unsigned)((k[r] >> shift) & 0xff);
-      q[r] = toff[d] + wcnt[warp][d] + q[r];
-      stage[q[r]] = k[r];
-    }
+    const int li = wofs + r * 32 + lane;
+    v[r] = li < tile_n ? vals_in[tbase + li] : V(0);
   }
   __syncthreads();
   uint32_t dst[kRsItems];
@@ -291,14 +315,15 @@ __global__ void __launch_bounds__(kRsThreads, 2) rs_onesweep_kernel(const uint64
     }
   }
   __syncthreads();
+  V *vstage = reinterpret_cast<V *>(stage);
 #pragma unroll
   for (int r = 0; r < kRsItems; ++r)
-    if (wofs + r * 32 + lane < tile_n) stage[q[r]] = v[r];
+    if (wofs + r * 32 + lane < tile_n) vstage[q[r]] = v[r];
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < kRsItems; ++r) {
     const int p = r * kRsThreads + threadIdx.x;
-    if (p < tile_n) vals_out[dst[r]] = stage[p];
+    if (p < tile_n) vals_out[dst[r]] = vstage[p];
   }
 }
 
@@ -308,14 +333,17 @@ static inline bool rs_three_kernel() {
   return v;
 }
 
-struct SortedPairs { uint64_t *keys, *vals; };
+template <typename V>
+struct SortedKV { uint64_t *keys; V *vals; };
+using SortedPairs = SortedKV<uint64_t>;
 
-// Stable LSD sort of n pairs over the listed 8-bit digit positions (digit p = key bits [8p, 8p+8)), lowest first.
-// Ping-pongs between (keys, vals) and (k2, v2); *out says where the sorted pairs ended up (no copy back).
+// Stable LSD sort of n (key, value) pairs over the listed 8-bit digit positions (digit p = key bits [8p, 8p+8)), lowest
+// first.  Ping-pongs between (keys, vals) and (k2, v2); *out says where the sorted pairs ended up (no copy back).
 // totals_by_pos: digit totals [kRsMaxPasses][256] indexed by digit position, when the caller already has them
 // (the build's prep kernel); NULL = histogram here.
-inline int radix_sort_digits(uint64_t *keys, uint64_t *vals, uint64_t *k2, uint64_t *v2, int64_t n, const int *digit_pos, int npass,
-                             const uint32_t *totals_by_pos, cudaStream_t s, SortedPairs *out) {
+template <typename V>
+inline int radix_sort_digits(uint64_t *keys, V *vals, uint64_t *k2, V *v2, int64_t n, const int *digit_pos, int npass,
+                             const uint32_t *totals_by_pos, cudaStream_t s, SortedKV<V> *out) {
   out->keys = keys;
   out->vals = vals;
   if (n <= 1 || npass <= 0) return PBGPU_OK;
@@ -326,8 +354,9 @@ inline int radix_sort_digits(uint64_t *keys, uint64_t *vals, uint64_t *k2, uint6
     if (digit_pos[p] > max_pos) max_pos = digit_pos[p];
   }
   Scratch sc(s);
-  uint64_t *ki = keys, *vi = vals, *ko = k2, *vo = v2;
-  if (n < (int64_t)kLbMask && !rs_three_kernel()) {
+  uint64_t *ki = keys, *ko = k2;
+  V *vi = vals, *vo = v2;
+  if (n < (int64_t)kLbMask && (!rs_three_kernel() || sizeof(V) != 8)) {
     uint32_t *work = nullptr;  // [kRsMaxPasses][256] digit totals (when not supplied) | tickets (256) | [npass][nblk][256] status
     const size_t tot_w = totals_by_pos ? 0 : (size_t)kRsMaxPasses * kRsRadix, tick_w = kRsRadix, stat_w = (size_t)npass * (size_t)nblk * kRsRadix;
     PB_TRY(sc.get(&work, tot_w + tick_w + stat_w));
@@ -340,13 +369,18 @@ inline int radix_sort_digits(uint64_t *keys, uint64_t *vals, uint64_t *k2, uint6
       totals_by_pos = work;
     }
     for (int p = 0; p < npass; ++p) {
-      PB_LAUNCH(rs_onesweep_kernel, (unsigned)nblk, kRsThreads, 0, s, ki, vi, ko, vo, n, 8 * digit_pos[p],
-                totals_by_pos + (size_t)digit_pos[p] * kRsRadix, status + (size_t)p * (size_t)nblk * kRsRadix, tickets + p);
+      if (rs_occ() == 3)
+        PB_LAUNCH((rs_onesweep_kernel<V, 3>), (unsigned)nblk, kRsThreads, 0, s, ki, vi, ko, vo, n, 8 * digit_pos[p],
+                  totals_by_pos + (size_t)digit_pos[p] * kRsRadix, status + (size_t)p * (size_t)nblk * kRsRadix, tickets + p);
+      else
+        PB_LAUNCH((rs_onesweep_kernel<V, 2>), (unsigned)nblk, kRsThreads, 0, s, ki, vi, ko, vo, n, 8 * digit_pos[p],
+                  totals_by_pos + (size_t)digit_pos[p] * kRsRadix, status + (size_t)p * (size_t)nblk * kRsRadix, tickets + p);
       uint64_t *t = ki; ki = ko; ko = t;
-      t = vi; vi = vo; vo = t;
+      V *u = vi; vi = vo; vo = u;
     }
     PB_CHECK_LAUNCH();
   } else {
+    if (sizeof(V) != 8) return set_error(PBGPU_ERANGE, "table too large for the single-kernel radix pass");
     uint32_t *hist = nullptr, *totals = nullptr;
     PB_TRY(sc.get(&hist, (size_t)(nblk * kRsRadix)));
     PB_TRY(sc.get(&totals, (size_t)npass * kRsRadix));
@@ -356,10 +390,10 @@ inline int radix_sort_digits(uint64_t *keys, uint64_t *vals, uint64_t *k2, uint6
       const int shift = 8 * digit_pos[p];
       PB_LAUNCH(rs_hist_kernel, (unsigned)nblk, kRsThreads, 0, s, ki, n, shift, hist, nblk, tot);
       PB_LAUNCH(rs_offsets_kernel, kRsRadix / 8, 256, 0, s, hist, nblk, tot);
-      PB_LAUNCH(rs_scatter_kernel, (unsigned)nblk, kRsThreads, 0, s, ki, vi, ko, vo, n, shift, hist, nblk);
+      PB_LAUNCH(rs_scatter_kernel, (unsigned)nblk, kRsThreads, 0, s, ki, (const uint64_t *)vi, ko, (uint64_t *)vo, n, shift, hist, nblk);
       PB_CHECK_LAUNCH();
       uint64_t *t = ki; ki = ko; ko = t;
-      t = vi; vi = vo; vo = t;
+      V *u = vi; vi = vo; vo = u;
     }
   }
   out->keys = ki;

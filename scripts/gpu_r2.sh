@@ -17,6 +17,24 @@ bench)
   echo "== bench N=1"; timeout 1200 python bench.py --steps 10 --warmup 3 > $O/${TAG}_bench_1gpu.json 2> $O/${TAG}_bench_1gpu.err; echo rc=$?; tail -c 7000 $O/${TAG}_bench_1gpu.json; tail -5 $O/${TAG}_bench_1gpu.err;;
 bench_dev)
   echo "== bench N=1 (device only)"; timeout 600 python bench.py --steps 10 --warmup 3 --skip-e2e --no-cpu-baseline --skip-secondary > $O/${TAG}_bench_dev.json 2> $O/${TAG}_bench_dev.err; echo rc=$?; tail -c 5000 $O/${TAG}_bench_dev.json; tail -5 $O/${TAG}_bench_dev.err;;
+ab)
+  echo "== A/B variants (device-resident bench, no e2e)"
+  for v in ${AB_VARIANTS:-PBGPU_X=default}; do
+    n=$(echo "$v" | tr ' =,' '___'); vv=$(echo "$v" | tr ',' ' ')
+    timeout 600 env $vv python bench.py --steps 8 --warmup 3 --skip-e2e --no-cpu-baseline --skip-secondary --skip-parity > $O/${TAG}_ab_${n}.json 2> $O/${TAG}_ab_${n}.err
+    python - "$O/${TAG}_ab_${n}.json" "$v" <<'PYEOF'
+import json, sys
+try:
+    d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    r = d["roofline"]
+    print(sys.argv[2], "ms/step %.3f" % d["ms_per_step"], "build %.3f" % r["index_build_ms"],
+          {k.split("(")[0].strip(): round(v["ms"], 3) for k, v in r["all_stages"].items()}, "bin %.3f unbin %.3f" % (r.get("bin_ms", 0), r.get("unbin_ms", 0)))
+except Exception as e:
+    print(sys.argv[2], "FAILED", e, open(sys.argv[1].replace(".json", ".err")).read()[-600:])
+PYEOF
+  done;;
+generic)
+  echo "== parity with the generic build front half"; PBGPU_BUILD=generic timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_scale.py -m gpu -x -q > $O/${TAG}_pytest_generic.log 2>&1; echo rc=$?; tail -4 $O/${TAG}_pytest_generic.log;;
 trace)
   echo "== build trace (config 3)"; PBGPU_TRACE_BUILD=1 PB_REPS=2 timeout 600 python tests/tools/scale_check.py 3 > $O/${TAG}_scale3.jsonl 2> $O/${TAG}_build_trace.txt; echo rc=$?; tail -14 $O/${TAG}_build_trace.txt; cat $O/${TAG}_scale3.jsonl;;
 ref)

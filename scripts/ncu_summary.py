@@ -95,6 +95,8 @@ def full_capture(rep):
 def main():
     tag = sys.argv[1]
     title = sys.argv[2] if len(sys.argv) > 2 else ""
+    if os.path.exists(os.path.join(OUT, f"{tag}_config3_launches.csv")) or os.path.exists(os.path.join(OUT, f"{tag}_config3_prof.ncu-rep")):
+        return main_config3(tag, title)
     os.makedirs(PROF, exist_ok=True)
     lines = [f"# {tag}: {title}".rstrip(": "), ""]
     lcsv = os.path.join(OUT, f"{tag}_launches.csv")
@@ -144,6 +146,44 @@ def main():
     if os.path.exists(rj):
         shutil.copy(rj, os.path.join(PROF, f"{tag}_bench_ref.json"))
     open(os.path.join(PROF, f"{tag}_summary.md"), "w").write("\n".join(lines))
+    print("\n".join(lines))
+
+
+def main_config3(tag, title):
+    """Round 2: captures of tests/tools/profile_config3.py (one index build + count_overlaps + two-pass overlap on
+    BASELINE config 3) -> profiles/<tag>_config3_{launches.csv,traffic.json,summary.md}."""
+    os.makedirs(PROF, exist_ok=True)
+    lines = [f"# {tag} (config 3: 100 M reads x 90 M variants, one B200): {title}".rstrip(": "), ""]
+    lcsv = os.path.join(OUT, f"{tag}_config3_launches.csv")
+    if os.path.exists(lcsv):
+        shutil.copy(lcsv, os.path.join(PROF, f"{tag}_config3_launches.csv"))
+        lines += ["Command: `PB_REPS=2 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python "
+                  "tests/tools/profile_config3.py` (two repetitions of: index build, count_overlaps, overlap pass 1 + 2). Per-launch "
+                  "times are cold-cache and serialised: compare SHARES, not absolutes.", "",
+                  "| share | launches | avg us | kernel |", "|---:|---:|---:|---|"]
+        for k, sh, n, a in launch_shares(lcsv):
+            lines.append(f"| {sh:.2f}% | {n} | {a:.2f} | `{k}` |")
+        lines.append("")
+    rep = os.path.join(OUT, f"{tag}_config3_prof.ncu-rep")
+    if os.path.exists(rep):
+        cap = full_capture(rep)
+        json.dump(cap, open(os.path.join(PROF, f"{tag}_config3_traffic.json"), "w"), indent=1)
+        lines += [f"## `ncu --set full --clock-control none --import-source on` ({tag}_config3_prof.ncu-rep; averages over the captured "
+                  "launches; ncu flushes caches between replays, so DRAM traffic is the cold-cache worst case)", "",
+                  "| kernel | n | time us | dram rd MB | dram wr MB | dram % | L2 hit % | lts % | l1tex % | l1tex->xbar req % | sm % | warps act % | regs | grid x block |",
+                  "|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---|"]
+        f = lambda v, d=1: "-" if v is None else f"{v:.{d}f}"
+        for k, o in cap.items():
+            lines.append(f"| `{k[:70]}` | {o['launches_captured']} | {f(o['time_us'])} | {f((o['dram_read_bytes'] or 0)/1e6)} | "
+                         f"{f((o['dram_write_bytes'] or 0)/1e6)} | {f(o['dram_pct'])} | {f(o['l2_hit_pct'])} | {f(o['lts_pct'])} | "
+                         f"{f(o['l1tex_pct'])} | {f(o['l1tex2xbar_req_pct'])} | {f(o['sm_pct'])} | {f(o['warps_active_pct'])} | "
+                         f"{f(o['regs'],0)} | {f(o['grid'],0)} x {f(o['block'],0)} |")
+        lines.append("")
+    for extra in ("bench_1gpu", "bench_dev"):
+        bj = os.path.join(OUT, f"{tag}_{extra}.json")
+        if os.path.exists(bj) and open(bj).read().strip():
+            shutil.copy(bj, os.path.join(PROF, f"{tag}_{extra}.json"))
+    open(os.path.join(PROF, f"{tag}_config3_summary.md"), "w").write("\n".join(lines))
     print("\n".join(lines))
 
 
