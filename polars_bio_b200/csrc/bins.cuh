@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(kBinThreads, OCC) bin_partition_kernel(IndexVi
                                                                        int64_t n, int bin_shift, int strict,
                                                                        const uint32_t *__restrict__ totals /*[256]*/,
                                                                        uint32_t *status /*[tiles][256], zeroed*/, uint32_t *ticket /*zeroed*/,
-                                                                       int4 *__restrict__ recs, uint32_t *__restrict__ pos) {
+                                                                       int4 *__restrict__ recs, uint32_t *__restrict__ pos, int bulk_store) {
   extern __shared__ __align__(16) unsigned char bin_smem[];
   int4 *stage = reinterpret_cast<int4 *>(bin_smem);
   __shared__ uint16_t wcnt[kBinWarps][kBinRadix];
@@ -154,6 +154,9 @@ __global__ void __launch_bounds__(kBinThreads, OCC) bin_partition_kernel(IndexVi
       stage[q[r]] = rec[r];
     }
   }
+  // the staged records are read by the bulk-copy (async proxy) engine below: order this thread's shared-memory writes
+  // before it; the barriers inside the next block scan make them visible to the issuing threads
+  if (bulk_store) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   const uint32_t gbase = block_exclusive<SumU32, kBinThreads>(threadIdx.x < kBinRadix ? totals[threadIdx.x] : 0u, wt);
   if (threadIdx.x < kBinRadix) {
     const int d = threadIdx.x;
@@ -187,6 +190,22 @@ __global__ void __launch_bounds__(kBinThreads, OCC) bin_partition_kernel(IndexVi
 #pragma unroll
     for (int r = 0; r < kBinItems; ++r)
       if (dg[r] != 0x100u) pos[tbase + wofs + r * 32 + lane] = dbase[dg[r]] + q[r];
+  }
+  if (bulk_store) {
+    // TMA bulk stores (cp.async.bulk shared -> global; SASS: UBLKCP): the records of (tile, bin d) are ONE run in shared
+    // memory and ONE run in global memory, both 16-byte aligned (16-byte records): thread d hands its bin's run to the
+    // copy engine as a whole instead of the block copying record by record through registers.
+    if (threadIdx.x < kBinRadix && run) {
+      const uint32_t first = toff[threadIdx.x];
+      const uint64_t gdst = (uint64_t)(uintptr_t)(recs + (dbase[threadIdx.x] + first));
+      const uint32_t ssrc = (uint32_t)__cvta_generic_to_shared(stage + first);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(run * 16u) : "memory");
+    }
+    if (threadIdx.x < kBinRadix) {
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the block's shared memory goes away when it exits
+    }
+    return;
   }
 #pragma unroll
   for (int r = 0; r < kBinItems; ++r) {

@@ -711,8 +711,9 @@ __global__ void __launch_bounds__(256) gstats_init_kernel(int32_t *__restrict__ 
   if (c == 0) { st->valid = 0; st->inverted = 0; st->max_len = 0; st->min_end = INT32_MAX; st->max_end = INT32_MIN; st->blocks_done = 0; }
 }
 // per contig: smallest and largest start; overall: valid / inverted rows, longest interval, range of the ends.
-// Warp-aggregated: the lanes of a warp that share a contig reduce among themselves (MATCH + REDUX) and their leader
-// touches the block's shared-memory slot once.
+// A row touches its contig's shared-memory slots with an atomic only when it would improve them (a plain load decides):
+// after the first few hundred rows of a block almost none does.  (First version: MATCH + REDUX per row, 1.3 ms per
+// 90 M rows; the loads are conflict-free broadcasts.)
 __global__ void __launch_bounds__(512) contig_stats_kernel(const int32_t *__restrict__ c, const int32_t *__restrict__ s,
                                                            const int32_t *__restrict__ e, int64_t n, int32_t n_contigs,
                                                            int32_t *__restrict__ cmin, int32_t *__restrict__ cmax, GStats *st) {
@@ -725,21 +726,20 @@ __global__ void __launch_bounds__(512) contig_stats_kernel(const int32_t *__rest
   unsigned inv = 0, val = 0, mlen = 0;
   int mn_e = INT32_MAX, mx_e = INT32_MIN;
   const int64_t stride = (int64_t)gridDim.x * 512;
-  for (int64_t i0 = (int64_t)blockIdx.x * 512 + threadIdx.x; i0 - threadIdx.x + (threadIdx.x & ~31) < n; i0 += 2 * stride) {  // whole warps iterate together
-    int32_t cc[2], ss[2], ee[2];
+  constexpr int U = 4;
+  for (int64_t i0 = (int64_t)blockIdx.x * 512 + threadIdx.x; i0 < n; i0 += U * stride) {
+    int32_t cc[U], ss[U], ee[U];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int64_t i = i0 + u * stride;
       const bool in = i < n;
       cc[u] = in ? c[i] : -1; ss[u] = in ? s[i] : 0; ee[u] = in ? e[i] : 0;
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const bool ok = cc[u] >= 0 && cc[u] < n_contigs;
-      const unsigned peers = __match_any_sync(0xffffffffu, ok ? cc[u] : -1);
-      if (ok) {
-        const int lo = __reduce_min_sync(peers, ss[u]), hi = __reduce_max_sync(peers, ss[u]);
-        if (lane == __ffs(peers) - 1) { atomicMin(&smin[cc[u]], lo); atomicMax(&smax[cc[u]], hi); }
+    for (int u = 0; u < U; ++u) {
+      if (cc[u] >= 0 && cc[u] < n_contigs) {
+        if (ss[u] < *(volatile int32_t *)&smin[cc[u]]) atomicMin(&smin[cc[u]], ss[u]);
+        if (ss[u] > *(volatile int32_t *)&smax[cc[u]]) atomicMax(&smax[cc[u]], ss[u]);
         mn_e = min(mn_e, ee[u]); mx_e = max(mx_e, ee[u]);
         inv += ss[u] > ee[u];
         if (ee[u] >= ss[u]) mlen = max(mlen, (unsigned)((long long)ee[u] - (long long)ss[u]));
@@ -845,29 +845,51 @@ __device__ __forceinline__ int32_t contig_of_g(const ContigMap *__restrict__ cma
   while (lo < hi) { const int32_t mid = lo + ((hi - lo) >> 1); if (cmap[mid].off <= g) lo = mid + 1; else hi = mid; }
   return lo - 1;
 }
-// unpack of the global-key sort: SoA columns, gs, contig segments by boundary detection, "any end inversion?"
+// unpack of the global-key sort: SoA columns, gs, contig segments by boundary detection, "any end inversion?".
+// The contig of a row: one search per block (its first row), then a walk forward -- rows are sorted, a block of 256
+// almost never spans more than two contigs; the predecessor's contig comes from the neighbouring lane.
 __global__ void __launch_bounds__(256) unpack_gsorted_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, int64_t m,
                                                              const ContigMap *__restrict__ cmap, int32_t n_contigs,
                                                              int32_t *__restrict__ st, int32_t *__restrict__ en, uint32_t *__restrict__ row,
                                                              uint2 *__restrict__ er, uint32_t *__restrict__ gs, int32_t *__restrict__ seg,
                                                              unsigned long long *__restrict__ inversions) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ int32_t c_first;
+  const int64_t b0 = (int64_t)blockIdx.x * blockDim.x;
+  const int64_t i = b0 + threadIdx.x;
+  if (threadIdx.x == 0) c_first = contig_of_g(cmap, n_contigs, (uint32_t)(keys[b0 > 0 ? b0 - 1 : 0] >> 32));  // contig of the row before the block
+  __syncthreads();
   unsigned inv = 0;
-  if (i < m) {
-    const uint64_t k = keys[i];
-    const uint32_t g = (uint32_t)(k >> 32), e = vals[i];
-    const int32_t contig = contig_of_g(cmap, n_contigs, g);
+  const bool ok = i < m;
+  uint64_t k = 0;
+  uint32_t e = 0;
+  int32_t contig = c_first;
+  if (ok) {
+    k = keys[i];
+    e = vals[i];
+    const uint32_t g = (uint32_t)(k >> 32);
+    while (contig + 1 < n_contigs && cmap[contig + 1].off <= g) ++contig;
+  }
+  // predecessor: the lane below; lane 0 reads it (the row before the block has contig c_first by construction)
+  int32_t prev = __shfl_up_sync(0xffffffffu, contig, 1);
+  uint32_t prev_e = __shfl_up_sync(0xffffffffu, e, 1);
+  if ((threadIdx.x & 31) == 0 && ok) {
+    if (i == 0) prev = -1;
+    else {
+      prev_e = vals[i - 1];
+      prev = c_first;
+      const uint32_t pg = (uint32_t)(keys[i - 1] >> 32);
+      while (prev + 1 < n_contigs && cmap[prev + 1].off <= pg) ++prev;
+    }
+  }
+  if (ok) {
+    const uint32_t g = (uint32_t)(k >> 32);
     const ContigMap cm = cmap[contig];
     st[i] = (int32_t)((long long)(g - cm.off) + cm.lo_m1);
     en[i] = (int32_t)e;
     row[i] = (uint32_t)k;
     er[i] = make_uint2(e, (uint32_t)k);
     gs[i] = g;
-    int32_t prev = -1;
-    if (i > 0) {
-      prev = contig_of_g(cmap, n_contigs, (uint32_t)(keys[i - 1] >> 32));
-      if (prev == contig) inv = (int32_t)e < (int32_t)vals[i - 1];
-    }
+    if (prev == contig) inv = (int32_t)e < (int32_t)prev_e;
     for (int32_t c = prev + 1; c <= contig; ++c) seg[c] = (int32_t)i;
     if (i == m - 1) for (int32_t c = contig + 1; c <= n_contigs; ++c) seg[c] = (int32_t)m;
   }

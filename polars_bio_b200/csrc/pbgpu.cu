@@ -371,9 +371,11 @@ struct BuildTrace {
   }
 };
 
-// PBGPU_JDIR_SHIFT=k: k more bits per directory bucket than the default rule picks (tuning: fewer, fuller records)
+// PBGPU_JDIR_SHIFT=k: k more bits per directory bucket than the 0.6-1.2-rows-per-bucket rule picks.  Default 1 (1.2-2.4 rows
+// per bucket, ~6 of a record's 12 key slots used): half the directory bytes to build and to stream through the L2 for the
+// same count-kernel time (r2f: build -0.75 ms on 90 M rows, count / pass 1 unchanged)
 static int jdir_extra_shift() {
-  static int v = [] { const char *e = getenv("PBGPU_JDIR_SHIFT"); return e ? atoi(e) : 0; }();
+  static int v = [] { const char *e = getenv("PBGPU_JDIR_SHIFT"); return e ? atoi(e) : 1; }();
   return v < 0 ? 0 : v;
 }
 constexpr int kCrowdedLinearMax = 64;  // crowded records of an unsorted-ends index are counted linearly up to this many ends
@@ -876,10 +878,14 @@ static int bin_probes(const pbgpu_index *ix, const int32_t *pc, const int32_t *p
     cudaFuncSetAttribute(bin_partition_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_b);
   });
   const int strict = filter_op == PBGPU_FILTER_STRICT;
+  // PBGPU_BIN_STORE=ldst: copy the staged runs out through registers instead of TMA bulk stores (A/B)
+  static const int bulk = [] { const char *e = getenv("PBGPU_BIN_STORE"); return (e && !strcmp(e, "ldst")) ? 0 : 1; }();
 #define PB_BINPART(WP, OCC)                                                                                                         \
   PB_LAUNCH((bin_partition_kernel<WP, OCC>), (unsigned)tiles, kBinThreads, stage_b, s, view_of(ix), pc, ps, pe, n, out->bin_shift, strict, \
-            totals, status, ticket, out->recs, out->pos)
-  if (rs_occ() == 3) { if (write_pos) PB_BINPART(true, 3); else PB_BINPART(false, 3); }
+            totals, status, ticket, out->recs, out->pos, bulk)
+  // r2f: the 40-register cap of the 3-blocks-per-SM build spills the 16-byte records (1.74 vs 1.55 ms per 100 M probes)
+  static const int bin_occ = [] { const char *e = getenv("PBGPU_BIN_OCC"); return (e && e[0] == '3') ? 3 : 2; }();
+  if (bin_occ == 3) { if (write_pos) PB_BINPART(true, 3); else PB_BINPART(false, 3); }
   else { if (write_pos) PB_BINPART(true, 2); else PB_BINPART(false, 2); }
 #undef PB_BINPART
   PB_CHECK_LAUNCH();

@@ -59,7 +59,10 @@ def sample_parity(name, pc, ps, pe, bc, bs, be, strict, counts=None, pairs=None,
         oc = oix.count_overlaps(pc[idx], ps[idx], pe[idx], strict, threads=thr)
         res["count_sample_equal"] = bool(np.array_equal(counts[idx], oc))
     if pairs is not None:  # pairs of the sampled probes (selected on the device: the pair buffers are GBs), compared as sets
-        a, b = pairs  # device int32 tensors, sorted by probe row
+        a, b = pairs  # device int32 tensors; pairs of one probe are contiguous, probes in bin order when the index is beyond the L2
+        order = torch.argsort(a, stable=True)
+        a, b = a[order], b[order]
+        del order
         idx_d = torch.from_numpy(idx.astype(np.int32)).to(a.device)
         lo_ = torch.searchsorted(a, idx_d, right=False); hi_ = torch.searchsorted(a, idx_d, right=True)
         w = hi_ - lo_
