@@ -323,6 +323,23 @@ typedef struct {                 /* mirrors RangeOptions, src/option.rs:8-41    
 PBGPU_API int pbgpu_range_op(struct ArrowArrayStream *left, struct ArrowArrayStream *right,
                              const PbRangeOptions *opts, struct ArrowArrayStream *out);
 
+/* Build once, probe many: the streamed counterpart of pbgpu_range_op -- what range_operation_lazy / _scan
+ * (src/lib.rs:154-166, 216-228) and the probe-side batch streams of src/scan.rs:103-139, 320-357 do in the reference:
+ * the indexed side is collected and indexed ONCE, the iterated side arrives in chunks (one pbgpu_range_probe call per
+ * chunk of record batches; concurrent calls from several partitions / threads are allowed), and every call returns the
+ * result rows of its chunk with the same column contract as pbgpu_range_op.  Host staging is sized by the chunk, not by
+ * the table.  Which input is the indexed one follows the operation (see pbgpu_range_op): overlap / nearest index
+ * `right` (df2, cols2) and iterate `left`; count_overlaps / coverage index `left` (cols1) and iterate `right`.
+ * With emit = 1 the iterated-side row ids of a probe are relative to its chunk.  opts->limit applies per probe call.
+ * Ownership: both calls MOVE their input stream (released before returning); the caller owns `out` and the session. */
+typedef struct pbgpu_range_session pbgpu_range_session;
+PBGPU_API int pbgpu_range_open(struct ArrowArrayStream *indexed, const PbRangeOptions *opts, pbgpu_range_session **out);
+PBGPU_API int pbgpu_range_probe(pbgpu_range_session *session, struct ArrowArrayStream *iterated, struct ArrowArrayStream *out);
+PBGPU_API void pbgpu_range_close(pbgpu_range_session *session);
+/* Page-locked host staging the Arrow level holds right now and its high-water mark since the last reset (bytes): what a
+ * streamed join keeps bounded by its chunk size.  Diagnostics; any pointer may be NULL. */
+PBGPU_API void pbgpu_pinned_stats(uint64_t *busy_bytes, uint64_t *peak_bytes, int reset_peak);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,7 +16,8 @@ from .logging import set_loglevel  # noqa: F401
 from .options import FilterOp, OverlapOutputMode, RangeOp, RangeOptions  # noqa: F401
 from .range_op import (IntervalOperations, cluster, complement, count_overlaps, coverage, merge, nearest,  # noqa: F401
                        overlap, subtract)
-from .range_op_io import RangeResult, range_operation_frame  # noqa: F401
+from .range_op_io import (LazyRangeSource, RangeResult, RangeSession, range_lazy_scan, range_operation_frame,  # noqa: F401
+                          range_operation_lazy, range_operation_scan)
 from . import polars_ext  # noqa: F401,E402  (registers LazyFrame.pb when polars is present)
 
 POLARS_BIO_MAX_THREADS = "datafusion.execution.target_partitions"  # /root/reference/polars_bio/__init__.py:142

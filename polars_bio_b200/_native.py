@@ -135,6 +135,12 @@ def lib() -> ctypes.CDLL:
     L.pbgpu_subtract.argtypes = [vp, vp, vp, i64, vp, vp, vp, i64, i32, ctypes.c_int, vp, ctypes.POINTER(vp)]
     L.pbgpu_last_stage_times.argtypes = [ctypes.POINTER(StageTimes)]
     L.pbgpu_range_op.argtypes = [vp, vp, ctypes.POINTER(PbRangeOptions), vp]
+    L.pbgpu_range_open.argtypes = [vp, ctypes.POINTER(PbRangeOptions), ctypes.POINTER(vp)]
+    L.pbgpu_range_probe.argtypes = [vp, vp, vp]
+    L.pbgpu_range_close.argtypes = [vp]
+    L.pbgpu_range_close.restype = None
+    L.pbgpu_pinned_stats.argtypes = [ctypes.POINTER(u64), ctypes.POINTER(u64), ctypes.c_int]
+    L.pbgpu_pinned_stats.restype = None
     _lib = L
     return L
 
@@ -142,6 +148,13 @@ def lib() -> ctypes.CDLL:
 def check(rc: int) -> None:
     if rc != 0:
         raise PbgpuError(rc, lib().pbgpu_last_error().decode("utf-8", "replace"))
+
+
+def pinned_stats(reset_peak: bool = False):
+    """(bytes of page-locked staging in use, high-water mark since the last reset) of the Arrow level."""
+    busy, peak = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    lib().pbgpu_pinned_stats(ctypes.byref(busy), ctypes.byref(peak), 1 if reset_peak else 0)
+    return int(busy.value), int(peak.value)
 
 
 def launch_count() -> int:

@@ -174,6 +174,7 @@ struct PinnedBuf {
 };
 std::mutex g_pin_mu;
 std::vector<PinnedBuf> g_pin;
+size_t g_pin_busy = 0, g_pin_peak = 0;  // page-locked staging bytes in use right now / high-water mark (pbgpu_pinned_stats)
 
 void *pinned_get(size_t bytes, bool wc = false) {
   if (bytes == 0) bytes = 1;
@@ -183,6 +184,8 @@ void *pinned_get(size_t bytes, bool wc = false) {
     if (!g_pin[i].busy && g_pin[i].wc == wc && g_pin[i].cap >= bytes && (best < 0 || g_pin[i].cap < g_pin[best].cap)) best = i;
   if (best >= 0) {
     g_pin[best].busy = true;
+    g_pin_busy += g_pin[best].cap;
+    if (g_pin_busy > g_pin_peak) g_pin_peak = g_pin_busy;
     return g_pin[best].p;
   }
   PinnedBuf b;
@@ -195,6 +198,8 @@ void *pinned_get(size_t bytes, bool wc = false) {
   b.busy = true;
   b.wc = wc;
   g_pin.push_back(b);
+  g_pin_busy += cap;
+  if (g_pin_busy > g_pin_peak) g_pin_peak = g_pin_busy;
   return b.p;
 }
 size_t pinned_cap_bytes() {
@@ -205,7 +210,7 @@ void pinned_put(void *p) {
   if (!p) return;
   std::lock_guard<std::mutex> lk(g_pin_mu);
   size_t total = 0;
-  for (auto &b : g_pin) { if (b.p == p) b.busy = false; total += b.cap; }
+  for (auto &b : g_pin) { if (b.p == p && b.busy) { b.busy = false; g_pin_busy -= b.cap; } total += b.cap; }
   // keep the cache bounded (PBGPU_PINNED_CACHE_MB, default 8 GiB): release idle buffers, largest first
   while (total > pinned_cap_bytes()) {
     int victim = -1;
@@ -1139,6 +1144,39 @@ struct DevBufs {  // device scratch of one call, freed stream-ordered
 
 // Everything one pbgpu_range_op call holds on the device.  It normally dies when the call returns; a streaming
 // overlap (result larger than one ring slot) hands it to the output stream, which keeps emitting from it.
+// The indexed ("build") side of a join, resident on the device: encoded key columns + the search structure.  One
+// pbgpu_range_op call owns one; a pbgpu_range_open session shares it between all its pbgpu_range_probe calls (the
+// build-once / probe-many shape of the reference's IntervalJoinExec: src/scan.rs:103-139 streams the probe side batch
+// by batch against the collected build side).
+struct IndexSide {
+  int device = -1;
+  cudaStream_t s = nullptr;        // the stream the columns were uploaded and the index was built on
+  cudaEvent_t ready = nullptr;     // recorded behind the build: probing streams wait for it
+  DevBufs dev;
+  PinnedHold stage_wc;             // H2D staging of the key columns
+  std::shared_ptr<Table> tab;
+  ContigDict dict;                 // contig name -> code, as the index knows them
+  int32_t n_contigs = 0;
+  int64_t m = 0;
+  int32_t *dc_x = nullptr, *ds_x = nullptr, *de_x = nullptr;
+  pbgpu_index *ix = nullptr;
+  IndexSide() { stage_wc.wc = true; }
+  IndexSide(const IndexSide &) = delete;
+  IndexSide &operator=(const IndexSide &) = delete;
+  ~IndexSide() {
+    int prev = -1;
+    if (device >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != device) cudaSetDevice(device); else prev = -1;
+    if (s) cudaStreamSynchronize(s);
+    if (ix) pbgpu_index_free(ix);  // probing calls have synchronised their own streams before dropping their reference
+    dev.release();
+    if (ready) cudaEventDestroy(ready);
+    if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// Everything one probing call (pbgpu_range_op / pbgpu_range_probe) holds on the device.  It normally dies when the call
+// returns; a streaming overlap (result larger than one ring slot) hands it to the output stream, which keeps emitting from it.
 struct CallState {
   int device = -1;      // device the state lives on
   cudaStream_t s = nullptr;
@@ -1146,7 +1184,8 @@ struct CallState {
   DevBufs dev;
   PinnedHold stage;     // D2H landing buffers the host reads (returned to the cache when the state dies)
   PinnedHold stage_wc;  // H2D staging: write-combined pinned memory, written once by the encoders, read by DMA
-  pbgpu_index *ix = nullptr;
+  std::shared_ptr<IndexSide> xs;  // the indexed side (shared with the session, if any)
+  pbgpu_index *ix = nullptr;      // = xs->ix
   pbgpu_overlap_plan *plan = nullptr;
   CallState() { stage_wc.wc = true; }
   CallState(const CallState &) = delete;
@@ -1155,11 +1194,11 @@ struct CallState {
     int prev = -1;
     if (device >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != device) cudaSetDevice(device); else prev = -1;
     if (s2) { cudaStreamSynchronize(s2); cudaStreamDestroy(s2); }
-    if (s) cudaStreamSynchronize(s);  // the index / plan are freed on the legacy stream: nothing of ours may still read them
+    if (s) cudaStreamSynchronize(s);  // the plan is freed on the legacy stream: nothing of ours may still read it
     if (plan) pbgpu_overlap_plan_free(plan);
-    if (ix) pbgpu_index_free(ix);
     dev.release();
     if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+    xs.reset();  // after our streams have drained: the last reference frees the index
     if (prev >= 0) cudaSetDevice(prev);
   }
 };
@@ -1455,6 +1494,46 @@ void out_release(ArrowArrayStream *s) {
   s->release = nullptr;
 }
 
+// Upload + index the indexed side.  `side`: what to call it in error messages.
+int prepare_index(const PbRangeOptions &o, std::shared_ptr<Table> IXt, const char *side, std::shared_ptr<IndexSide> *out) {
+  auto xs = std::make_shared<IndexSide>();
+  xs->tab = IXt;
+  Table *IX = IXt.get();
+  Trace tr;
+  const int64_t m = IX->rows;
+  xs->m = m;
+  int prev_dev = -1;
+  BR_CUDA(cudaGetDevice(&prev_dev));
+  if (o.device >= 0 && o.device != prev_dev) BR_CUDA(cudaSetDevice(o.device)); else prev_dev = -1;
+  struct DevRestore { int d; ~DevRestore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev};
+  BR_CUDA(cudaGetDevice(&xs->device));
+  BR_CUDA(cudaStreamCreateWithFlags(&xs->s, cudaStreamNonBlocking));
+  BR_CUDA(cudaEventCreateWithFlags(&xs->ready, cudaEventDisableTiming));
+  cudaStream_t s = xs->s;
+  xs->dev.s = s;
+  int32_t *hc_x = xs->stage_wc.get<int32_t>(m), *hs_x = xs->stage_wc.get<int32_t>(m), *he_x = xs->stage_wc.get<int32_t>(m);
+  if (!hc_x || !hs_x || !he_x) return set_error(PBGPU_ENOMEM, "pinned staging allocation failed");
+  xs->dc_x = xs->dev.get<int32_t>(m); xs->ds_x = xs->dev.get<int32_t>(m); xs->de_x = xs->dev.get<int32_t>(m);
+  if (!xs->dc_x || !xs->ds_x || !xs->de_x) return set_error(PBGPU_ENOMEM, "device allocation failed");
+  // Contigs that only occur on the iterated side get codes >= n_contigs of the index and are treated as null keys by
+  // the kernels (they cannot match anything anyway).
+  BR_TRY(encode_keys(*IX, side, xs->dict, hc_x, hs_x, he_x));
+  xs->n_contigs = (int32_t)xs->dict.map.size();
+  tr.lap_drained("  encode indexed side", s);
+  BR_CUDA(cudaMemcpyAsync(xs->dc_x, hc_x, 4 * (size_t)m, cudaMemcpyHostToDevice, s));
+  BR_CUDA(cudaMemcpyAsync(xs->ds_x, hs_x, 4 * (size_t)m, cudaMemcpyHostToDevice, s));
+  BR_CUDA(cudaMemcpyAsync(xs->de_x, he_x, 4 * (size_t)m, cudaMemcpyHostToDevice, s));
+  tr.lap_drained("  H2D indexed side", s);
+  tr.lap("encode + H2D indexed side");
+  BR_TRY(pbgpu_index_build(xs->dc_x, xs->ds_x, xs->de_x, m, xs->n_contigs, s, &xs->ix));
+  BR_CUDA(cudaEventRecord(xs->ready, s));
+  tr.lap("index build");
+  *out = xs;
+  return PBGPU_OK;
+}
+
+int run_iter(Table *L, Table *R, OutStream *os, std::shared_ptr<IndexSide> xs);
+
 int run(Table *L, Table *R, OutStream *os) {
   const PbRangeOptions &o = os->opt;
   // roles: which table is indexed, which is iterated (see pbgpu.h)
@@ -1462,45 +1541,45 @@ int run(Table *L, Table *R, OutStream *os) {
   //   nearest: iterate = left (df1), index = right (df2)                   operation.rs:143-158
   //   count/coverage: index = left (s1), iterate = right (s2), rows of right returned   operation.rs:316-340
   const bool iter_is_left = (o.range_op == PBGPU_OP_OVERLAP || o.range_op == PBGPU_OP_NEAREST);
+  std::shared_ptr<IndexSide> xs;
+  BR_TRY(prepare_index(o, iter_is_left ? os->right : os->left, iter_is_left ? "right" : "left", &xs));
+  return run_iter(L, R, os, xs);
+}
+
+// One iterated ("probe") table against a resident indexed side.
+int run_iter(Table *L, Table *R, OutStream *os, std::shared_ptr<IndexSide> xs) {
+  const PbRangeOptions &o = os->opt;
+  const bool iter_is_left = (o.range_op == PBGPU_OP_OVERLAP || o.range_op == PBGPU_OP_NEAREST);
   Table *IT = iter_is_left ? L : R, *IX = iter_is_left ? R : L;
   Trace tr;
-  ContigDict dict;
+  ContigDict dict;  // a private copy: encoding the iterated side adds the contigs only it has
+  { std::lock_guard<std::mutex> lk(xs->dict.mu); dict.map = xs->dict.map; }
   os->call.reset(new CallState());
   CallState &cs = *os->call;  // dies with this call (end of run) unless a streaming overlap keeps it
+  cs.xs = xs;
   PinnedHold &stage = cs.stage, &stage_wc = cs.stage_wc;
   const int64_t n = IT->rows, m = IX->rows;
   int32_t *hs_i = stage_wc.get<int32_t>(n), *he_i = stage_wc.get<int32_t>(n);
-  int32_t *hc_x = stage_wc.get<int32_t>(m), *hs_x = stage_wc.get<int32_t>(m), *he_x = stage_wc.get<int32_t>(m);
-  if (!hs_i || !he_i || !hc_x || !hs_x || !he_x) return set_error(PBGPU_ENOMEM, "pinned staging allocation failed");
+  if (!hs_i || !he_i) return set_error(PBGPU_ENOMEM, "pinned staging allocation failed");
 
   int prev_dev = -1;
   BR_CUDA(cudaGetDevice(&prev_dev));
-  if (o.device >= 0 && o.device != prev_dev) BR_CUDA(cudaSetDevice(o.device)); else prev_dev = -1;
+  if (xs->device != prev_dev) BR_CUDA(cudaSetDevice(xs->device)); else prev_dev = -1;
   struct DevRestore { int d; ~DevRestore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev};
-  BR_CUDA(cudaGetDevice(&cs.device));
+  cs.device = xs->device;
   BR_CUDA(cudaStreamCreateWithFlags(&cs.s, cudaStreamNonBlocking));
   cudaStream_t s = cs.s;
+  BR_CUDA(cudaStreamWaitEvent(s, xs->ready, 0));  // uploads and the index build ran on the indexed side's stream
   cs.dev.s = s;
   DevBufs &dev = cs.dev;
-  int32_t *dc_x = dev.get<int32_t>(m), *ds_x = dev.get<int32_t>(m), *de_x = dev.get<int32_t>(m);
+  int32_t *dc_x = xs->dc_x, *ds_x = xs->ds_x, *de_x = xs->de_x;
+  (void)dc_x; (void)m;
   int32_t *dc_i = dev.get<int32_t>(n), *ds_i = dev.get<int32_t>(n), *de_i = dev.get<int32_t>(n);
-  if (!dc_x || !ds_x || !de_x || !dc_i || !ds_i || !de_i) return set_error(PBGPU_ENOMEM, "device allocation failed");
+  if (!dc_i || !ds_i || !de_i) return set_error(PBGPU_ENOMEM, "device allocation failed");
   tr.lap_drained("  stream + device allocations", s);
-
-  // indexed side first: encode -> H2D -> index build.  Contigs that only occur on the iterated side get codes
-  // >= n_contigs of the index and are treated as null keys by the kernels (they cannot match anything anyway).
-  BR_TRY(encode_keys(*IX, iter_is_left ? "right" : "left", dict, hc_x, hs_x, he_x));
-  const int32_t n_contigs = (int32_t)dict.map.size();
-  tr.lap_drained("  encode indexed side", s);
-  BR_CUDA(cudaMemcpyAsync(dc_x, hc_x, 4 * (size_t)m, cudaMemcpyHostToDevice, s));
-  BR_CUDA(cudaMemcpyAsync(ds_x, hs_x, 4 * (size_t)m, cudaMemcpyHostToDevice, s));
-  BR_CUDA(cudaMemcpyAsync(de_x, he_x, 4 * (size_t)m, cudaMemcpyHostToDevice, s));
-  tr.lap_drained("  H2D indexed side", s);
-  tr.lap("encode + H2D indexed side");
-  pbgpu_index *ix = nullptr;
-  BR_TRY(pbgpu_index_build(dc_x, ds_x, de_x, m, n_contigs, s, &ix));
+  const int32_t n_contigs = xs->n_contigs;
+  pbgpu_index *ix = xs->ix;
   cs.ix = ix;
-  tr.lap("index build");
   // iterated side in slices: the DMA of slice k runs while the host encodes slice k+1.  With at most 255 indexed
   // contigs the contig codes travel as bytes and are widened on the device.
   // count_overlaps / coverage are row-local, so they join the pipeline: the kernel of slice k and the D2H of its
@@ -1674,24 +1753,122 @@ int run(Table *L, Table *R, OutStream *os) {
 
 }  // namespace
 
-extern "C" int pbgpu_range_op(struct ArrowArrayStream *left, struct ArrowArrayStream *right, const PbRangeOptions *opts,
-                              struct ArrowArrayStream *out) {
-  // The inputs are moved: whatever happens below, both are released exactly once before returning.
-  struct Releaser { ArrowArrayStream *s; ~Releaser() { if (s && s->release) s->release(s); } } rl{left}, rr{right};
-  if (!opts || !out) return set_error(PBGPU_EINVAL, "opts/out is NULL");
+namespace {
+int check_opts(const PbRangeOptions *opts) {
+  if (!opts) return set_error(PBGPU_EINVAL, "opts is NULL");
   if (opts->filter_op != PBGPU_FILTER_WEAK && opts->filter_op != PBGPU_FILTER_STRICT) return set_error(PBGPU_EINVAL, "bad filter_op %d", opts->filter_op);
   if (opts->range_op != PBGPU_OP_OVERLAP && opts->range_op != PBGPU_OP_NEAREST && opts->range_op != PBGPU_OP_COVERAGE &&
       opts->range_op != PBGPU_OP_COUNT_OVERLAPS_NAIVE)
     return set_error(PBGPU_EINVAL, "range_op %d is not on the GPU hot path (overlap=0, nearest=3, coverage=4, count_overlaps=6)", opts->range_op);
   if (opts->output_mode < PBGPU_OUT_JOIN || opts->output_mode > PBGPU_OUT_LEFT_DISTINCT) return set_error(PBGPU_EINVAL, "bad output_mode %d", opts->output_mode);
+  return PBGPU_OK;
+}
+std::unique_ptr<OutStream> new_outstream(const PbRangeOptions &opts, const std::string *sfx1, const std::string *sfx2) {
+  std::unique_ptr<OutStream> os(new OutStream());
+  os->opt = opts;
+  if (sfx1) os->suffix1 = *sfx1;
+  if (sfx2) os->suffix2 = *sfx2;
+  os->opt.suffixes[0] = os->opt.suffixes[1] = nullptr;
+  os->opt.cols1[0] = os->opt.cols1[1] = os->opt.cols1[2] = nullptr;  // caller strings are not retained
+  os->opt.cols2[0] = os->opt.cols2[1] = os->opt.cols2[2] = nullptr;
+  if (opts.max_batch_rows) os->batch_rows = opts.max_batch_rows;
+  os->batch_rows = (os->batch_rows + 7u) & ~7u;  // keep bitmap bytes chunk-private
+  return os;
+}
+void publish(ArrowArrayStream *out, std::unique_ptr<OutStream> os) {
+  out->get_schema = out_get_schema;
+  out->get_next = out_get_next;
+  out->get_last_error = out_last_error;
+  out->release = out_release;
+  out->private_data = os.release();
+}
+}  // namespace
+
+// ---- build once, probe many (include/pbgpu.h: pbgpu_range_open / _probe / _close) ----------------------------------------
+struct pbgpu_range_session {
+  PbRangeOptions opt{};
+  std::string cols1[3], cols2[3], suffix1 = "_1", suffix2 = "_2";
+  bool iter_is_left = true;
+  std::shared_ptr<Table> indexed;
+  std::shared_ptr<IndexSide> xs;
+};
+
+extern "C" int pbgpu_range_open(struct ArrowArrayStream *indexed, const PbRangeOptions *opts, pbgpu_range_session **out) {
+  struct Releaser { ArrowArrayStream *s; ~Releaser() { if (s && s->release) s->release(s); } } rl{indexed};
+  if (!out) return set_error(PBGPU_EINVAL, "out is NULL");
+  *out = nullptr;
+  int rc = check_opts(opts);
+  if (rc != PBGPU_OK) return rc;
   try {
-    std::unique_ptr<OutStream> os(new OutStream());
-    os->opt = *opts;
-    if (opts->suffixes[0]) os->suffix1 = opts->suffixes[0];
-    if (opts->suffixes[1]) os->suffix2 = opts->suffixes[1];
-    os->opt.suffixes[0] = os->opt.suffixes[1] = nullptr;
-    if (opts->max_batch_rows) os->batch_rows = opts->max_batch_rows;
-    os->batch_rows = (os->batch_rows + 7u) & ~7u;  // keep bitmap bytes chunk-private
+    std::unique_ptr<pbgpu_range_session> ss(new pbgpu_range_session());
+    ss->opt = *opts;
+    for (int i = 0; i < 3; ++i) {
+      if (!opts->cols1[i] || !opts->cols2[i]) return set_error(PBGPU_EINVAL, "NULL column name");
+      ss->cols1[i] = opts->cols1[i];
+      ss->cols2[i] = opts->cols2[i];
+    }
+    if (opts->suffixes[0]) ss->suffix1 = opts->suffixes[0];
+    if (opts->suffixes[1]) ss->suffix2 = opts->suffixes[1];
+    ss->iter_is_left = (opts->range_op == PBGPU_OP_OVERLAP || opts->range_op == PBGPU_OP_NEAREST);
+    ss->indexed = std::make_shared<Table>();
+    const char *side = ss->iter_is_left ? "right" : "left";
+    rc = drain(indexed, *ss->indexed, side);
+    for (int i = 0; i < 3 && rc == PBGPU_OK; ++i)
+      rc = find_col(*ss->indexed, (ss->iter_is_left ? ss->cols2[i] : ss->cols1[i]).c_str(), side, &ss->indexed->key[i]);
+    if (rc == PBGPU_OK) rc = prepare_index(ss->opt, ss->indexed, side, &ss->xs);
+    if (rc != PBGPU_OK) return rc;
+    *out = ss.release();
+    return PBGPU_OK;
+  } catch (const std::bad_alloc &) {
+    return set_error(PBGPU_ENOMEM, "host allocation failed");
+  } catch (const std::exception &e) {
+    return set_error(PBGPU_EINVAL, "internal error: %s", e.what());
+  }
+}
+
+extern "C" int pbgpu_range_probe(pbgpu_range_session *ss, struct ArrowArrayStream *iterated, struct ArrowArrayStream *out) {
+  struct Releaser { ArrowArrayStream *s; ~Releaser() { if (s && s->release) s->release(s); } } rl{iterated};
+  if (!ss || !out) return set_error(PBGPU_EINVAL, "session/out is NULL");
+  try {
+    std::unique_ptr<OutStream> os = new_outstream(ss->opt, &ss->suffix1, &ss->suffix2);
+    auto it = std::make_shared<Table>();
+    const char *side = ss->iter_is_left ? "left" : "right";
+    int rc = drain(iterated, *it, side);
+    for (int i = 0; i < 3 && rc == PBGPU_OK; ++i)
+      rc = find_col(*it, (ss->iter_is_left ? ss->cols1[i] : ss->cols2[i]).c_str(), side, &it->key[i]);
+    if (rc != PBGPU_OK) return rc;
+    os->left = ss->iter_is_left ? it : ss->indexed;
+    os->right = ss->iter_is_left ? ss->indexed : it;
+    rc = run_iter(os->left.get(), os->right.get(), os.get(), ss->xs);
+    if (rc != PBGPU_OK) return rc;
+    publish(out, std::move(os));
+    return PBGPU_OK;
+  } catch (const std::bad_alloc &) {
+    return set_error(PBGPU_ENOMEM, "host allocation failed");
+  } catch (const std::exception &e) {
+    return set_error(PBGPU_EINVAL, "internal error: %s", e.what());
+  }
+}
+
+extern "C" void pbgpu_range_close(pbgpu_range_session *ss) { delete ss; }
+
+extern "C" void pbgpu_pinned_stats(uint64_t *busy_bytes, uint64_t *peak_bytes, int reset_peak) {
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  if (busy_bytes) *busy_bytes = g_pin_busy;
+  if (peak_bytes) *peak_bytes = g_pin_peak;
+  if (reset_peak) g_pin_peak = g_pin_busy;
+}
+
+extern "C" int pbgpu_range_op(struct ArrowArrayStream *left, struct ArrowArrayStream *right, const PbRangeOptions *opts,
+                              struct ArrowArrayStream *out) {
+  // The inputs are moved: whatever happens below, both are released exactly once before returning.
+  struct Releaser { ArrowArrayStream *s; ~Releaser() { if (s && s->release) s->release(s); } } rl{left}, rr{right};
+  if (!out) return set_error(PBGPU_EINVAL, "opts/out is NULL");
+  int rc0 = check_opts(opts);
+  if (rc0 != PBGPU_OK) return rc0;
+  try {
+    std::string sfx1 = opts->suffixes[0] ? opts->suffixes[0] : "_1", sfx2 = opts->suffixes[1] ? opts->suffixes[1] : "_2";
+    std::unique_ptr<OutStream> os = new_outstream(*opts, &sfx1, &sfx2);
     os->left = std::make_shared<Table>();
     os->right = std::make_shared<Table>();
     Trace tr;
@@ -1701,15 +1878,9 @@ extern "C" int pbgpu_range_op(struct ArrowArrayStream *left, struct ArrowArraySt
     for (int i = 0; i < 3 && rc == PBGPU_OK; ++i) rc = find_col(*os->left, opts->cols1[i], "left", &os->left->key[i]);
     for (int i = 0; i < 3 && rc == PBGPU_OK; ++i) rc = find_col(*os->right, opts->cols2[i], "right", &os->right->key[i]);
     if (rc != PBGPU_OK) return rc;
-    os->opt.cols1[0] = os->opt.cols1[1] = os->opt.cols1[2] = nullptr;  // caller strings are not retained
-    os->opt.cols2[0] = os->opt.cols2[1] = os->opt.cols2[2] = nullptr;
     rc = run(os->left.get(), os->right.get(), os.get());
     if (rc != PBGPU_OK) return rc;
-    out->get_schema = out_get_schema;
-    out->get_next = out_get_next;
-    out->get_last_error = out_last_error;
-    out->release = out_release;
-    out->private_data = os.release();
+    publish(out, std::move(os));
     return PBGPU_OK;
   } catch (const std::bad_alloc &) {
     return set_error(PBGPU_ENOMEM, "host allocation failed");

@@ -32,6 +32,23 @@ def _parse_overlap_output_mode(overlap_output: str) -> OverlapOutputMode:
     raise ValueError("overlap_output must be either 'join' or 'left'")  # tests/test_overlap_output_mode.py:190-197
 
 
+# `algorithm=` of pb.overlap (range_op.py:124,167; src/operation.rs:39-50 stores it in bio.interval_join_algorithm): the
+# reference's CPU search structures plus "gpu".  Every accepted name runs on the B200 engine -- they all produce the same
+# rows (tests/test_overlap_algorithms.py) -- and the name is recorded in the session like the reference does.
+KNOWN_ALGORITHMS = ("gpu", "coitrees", "intervaltree", "arrayintervaltree", "lapper", "superintervals", "coitreesnearest")
+
+
+def _select_algorithm(algorithm) -> str:
+    name = "gpu" if algorithm is None else str(algorithm)
+    if name.lower() not in KNOWN_ALGORITHMS:
+        raise ValueError(f"unknown interval join algorithm {algorithm!r}; available: gpu, Coitrees, IntervalTree, "
+                         "ArrayIntervalTree, Lapper, SuperIntervals")
+    from .constants import INTERVAL_JOIN_ALGORITHM
+
+    ctx.set_option(INTERVAL_JOIN_ALGORITHM, name)
+    return name
+
+
 def _filter_op(df1, df2) -> FilterOp:
     return FilterOp.Strict if validate_coordinate_systems(df1, df2, ctx) else FilterOp.Weak
 
@@ -58,6 +75,7 @@ class IntervalOperations:
         filter_op = _filter_op(df1, df2)
         cols1 = DEFAULT_INTERVAL_COLUMNS if cols1 is None else list(cols1)
         cols2 = DEFAULT_INTERVAL_COLUMNS if cols2 is None else list(cols2)
+        algorithm = _select_algorithm(algorithm)
         logger.info("Optimizing into IntervalJoinExec using %s algorithm (B200 engine)", algorithm)
         opts = RangeOptions(range_op=RangeOp.Overlap, filter_op=filter_op, suffixes=tuple(suffixes), columns_1=cols1,
                             columns_2=cols2, overlap_alg=algorithm, overlap_low_memory=low_memory,

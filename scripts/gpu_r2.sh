@@ -9,6 +9,8 @@ pytest)
   echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest_gpu.log 2>&1; echo rc=$?; tail -12 $O/${TAG}_pytest_gpu.log;;
 pytest_scale)
   echo "== pytest scale"; timeout 900 python -m pytest tests/test_gpu_scale.py -m gpu -x -q > $O/${TAG}_pytest_scale.log 2>&1; echo rc=$?; tail -12 $O/${TAG}_pytest_scale.log;;
+stream)
+  echo "== pytest stream"; timeout 900 python -m pytest tests/test_gpu_stream.py tests/test_gpu_api.py -m gpu -x -q > $O/${TAG}_pytest_stream.log 2>&1; echo rc=$?; tail -25 $O/${TAG}_pytest_stream.log;;
 bins)
   echo "== bins check"; PBGPU_BIN=1 timeout 900 python tests/tools/bins_check.py > $O/${TAG}_bins_check.log 2>&1; echo rc=$?; tail -8 $O/${TAG}_bins_check.log;;
 pytest_parity)
