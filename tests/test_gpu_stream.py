@@ -157,7 +157,7 @@ def test_scan_paths_parquet_csv_bed(tables, tmp_path):
                 f.write(f"chr1,{i * 200 + 20},{i * 200 + 60},{i}\n")
         out = pb.overlap(str(csv), str(bed), cols1=COLS, cols2=COLS, output_type="pandas.DataFrame")
         assert list(out.columns) == ["chrom_1", "start_1", "end_1", "score_1", "chrom_2", "start_2", "end_2", "name_2", "score_2", "strand_2"]
-        assert len(out) == 500 and (out["start_1"] < out["end_2"]).all() and (out["end_1"] > out["start_2"]).all()
+        assert len(out) == 999 and (out["start_1"] < out["end_2"]).all() and (out["end_1"] > out["start_2"]).all()
     finally:
         pb.set_option("datafusion.bio.coordinate_system_zero_based", False)
 
