@@ -408,6 +408,112 @@ __global__ void __launch_bounds__(kPeerThreads) peer_scatter_kernel(const int32_
   }
 }
 
+
+// ---- round 2: the same scatter with TMA bulk stores over NVLink --------------------------------------------------------
+// peer_scatter_kernel leaves every (tile, destination) run as 4-byte-per-lane stores: a warp instruction covers 128 bytes
+// that start anywhere, so most of them straddle two 128-byte lines of the remote arena and travel as two NVLink packets;
+// measured ~400 GB/s of egress per GPU at N = 8 (770 GB/s peer copies).  Here a tile is 4096 rows (runs of ~512 rows per
+// destination and column at N = 8), and the rows of every destination are staged in shared memory at an offset with the
+// SAME residue mod 4 rows as their destination index (arenas are 2 MiB aligned, table offsets multiples of 1 KiB, column
+// capacities multiples of 64 rows: the four columns of a run share that residue).  The 16-byte-aligned body of every
+// column run then leaves as ONE cp.async.bulk shared -> global (SASS UBLKCP) straight into the owner's column on the
+// peer GPU; the <= 3 head and <= 3 tail rows are stored by the issuing thread.  One thread per (destination, column).
+constexpr int kPbThreads = 512, kPbItems = 8, kPbTile = kPbThreads * kPbItems, kPbWarps = kPbThreads / 32;
+constexpr int kPbSub = kPbTile / kPeerTile;           // count-kernel blocks (1024 rows) per bulk tile
+constexpr int kPbStageRows = kPbTile + 8 * kPeerMaxRanks;  // + alignment gaps between the destinations' segments
+__global__ void __launch_bounds__(kPbThreads) peer_scatter_bulk_kernel(const int32_t *__restrict__ c, const int32_t *__restrict__ s,
+                                                                       const int32_t *__restrict__ e, int64_t n, const int32_t *__restrict__ owner,
+                                                                       int32_t n_contigs, int32_t n_ranks, const long long *__restrict__ row_id_base,
+                                                                       const PeerDst *__restrict__ dst_table, const unsigned int *__restrict__ bc,
+                                                                       int64_t nblk /*1024-row blocks*/, const long long *__restrict__ flag) {
+  extern __shared__ __align__(16) unsigned char pb_smem[];
+  int32_t *col[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) col[k] = reinterpret_cast<int32_t *>(pb_smem) + (size_t)k * kPbStageRows;
+  __shared__ unsigned short wcnt[kPbItems * kPbWarps][kPeerMaxRanks];  // rows of (item, warp) per destination -> exclusive prefix
+  __shared__ unsigned int seg[kPeerMaxRanks], cnt[kPeerMaxRanks];      // first staged row / rows of every destination
+  __shared__ unsigned int gbase[kPeerMaxRanks];
+  __shared__ PeerDst dst[kPeerMaxRanks];
+  if (*flag) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt = lanemask_lt();
+  if (threadIdx.x < n_ranks) dst[threadIdx.x] = dst_table[threadIdx.x];
+  const uint32_t id0 = (uint32_t)*row_id_base;
+  const int64_t ntile = (nblk + kPbSub - 1) / kPbSub;
+  for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+    for (int i = threadIdx.x; i < kPbItems * kPbWarps * kPeerMaxRanks; i += kPbThreads) (&wcnt[0][0])[i] = 0;
+    if (threadIdx.x < n_ranks) gbase[threadIdx.x] = bc[(int64_t)threadIdx.x * nblk + tile * kPbSub];
+    __syncthreads();
+    const int64_t base = tile * kPbTile;
+    int32_t rc[kPbItems], rs[kPbItems], re[kPbItems];
+    int rd[kPbItems];
+    unsigned int slot[kPbItems];
+#pragma unroll
+    for (int j = 0; j < kPbItems; ++j) {
+      const int64_t i = base + (int64_t)j * kPbThreads + threadIdx.x;
+      rd[j] = -1;
+      if (i < n) {
+        rc[j] = c[i]; rs[j] = s[i]; re[j] = e[i];
+        rd[j] = peer_dest(rc[j], owner, n_contigs, n_ranks);
+      }
+    }
+    // rank of every row among the rows of its (item, warp) with the same destination; (item, warp, lane) order = row order
+#pragma unroll
+    for (int j = 0; j < kPbItems; ++j) {
+      const unsigned peers = __match_any_sync(0xffffffffu, rd[j]);
+      if (rd[j] >= 0 && lane == __ffs(peers) - 1) wcnt[j * kPbWarps + warp][rd[j]] = (unsigned short)__popc(peers);
+      slot[j] = (unsigned)__popc(peers & lt);
+    }
+    __syncthreads();
+    if (threadIdx.x < n_ranks) {  // exclusive prefix over the (item, warp) groups of this destination
+      unsigned int run = 0;
+      for (int k = 0; k < kPbItems * kPbWarps; ++k) { const unsigned int v = wcnt[k][threadIdx.x]; wcnt[k][threadIdx.x] = (unsigned short)run; run += v; }
+      cnt[threadIdx.x] = run;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {  // segments: destination r starts at the next multiple of 4 rows + the residue of its first remote row
+      unsigned int end = 0;
+      for (int r = 0; r < n_ranks; ++r) {
+        const unsigned int a = (unsigned int)((reinterpret_cast<uintptr_t>(dst[r].contig + gbase[r]) >> 2) & 3u);
+        seg[r] = ((end + 3u) & ~3u) + a;
+        end = seg[r] + cnt[r];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kPbItems; ++j) {
+      if (rd[j] < 0) continue;
+      const unsigned int p = seg[rd[j]] + wcnt[j * kPbWarps + warp][rd[j]] + slot[j];
+      const int64_t i = base + (int64_t)j * kPbThreads + threadIdx.x;
+      col[0][p] = rc[j]; col[1][p] = rs[j]; col[2][p] = re[j]; col[3][p] = (int32_t)(id0 + (uint32_t)i);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // staged rows are read by the bulk-copy engine
+    __syncthreads();
+    if (threadIdx.x < 4 * n_ranks) {
+      const int r = threadIdx.x >> 2, k = threadIdx.x & 3;
+      const unsigned int rows = cnt[r];
+      if (rows) {
+        int32_t *g = (k == 0 ? dst[r].contig : k == 1 ? dst[r].start : k == 2 ? dst[r].end : reinterpret_cast<int32_t *>(dst[r].row)) + gbase[r];
+        const int32_t *src = col[k] + seg[r];
+        const unsigned int head = min(rows, (4u - (seg[r] & 3u)) & 3u);  // rows before the first 16-byte boundary
+        const unsigned int body = (rows - head) & ~3u;
+        for (unsigned int q = 0; q < head; ++q) g[q] = src[q];
+        if (body) {
+          const uint64_t gdst = (uint64_t)reinterpret_cast<uintptr_t>(g + head);
+          const uint32_t ssrc = (uint32_t)__cvta_generic_to_shared(src + head);
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(body * 4u) : "memory");
+        }
+        for (unsigned int q = head + body; q < rows; ++q) g[q] = src[q];
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the staging arrays are rewritten by the next tile
+    }
+    __syncthreads();
+  }
+  // the block's shared memory goes away at exit and the signal kernel that follows promises delivery: wait for the writes
+  if (threadIdx.x < 4 * n_ranks) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 }  // namespace pbgpu
 
 extern "C" {
@@ -533,6 +639,11 @@ int pbgpu_peer_plan(const int64_t *d_gathered, const void *d_own_ctl, uint64_t s
 // $PBGPU_PEER_GRID = blocks per SM of the scatter kernel (persistent grid striding over the tiles), default 2: the
 // kernel is bound by the NVLink stores, and a small resident grid lets the index build of the other table run beside it
 // (r02d, N=2: 0.78 ms/step against 0.81 with one block per tile); 0 = one block per tile
+// PBGPU_PEER_STORE=ldst: the first scatter kernel (4-byte stores through registers); default: TMA bulk stores
+static bool peer_bulk_store() {
+  static bool v = [] { const char *e = getenv("PBGPU_PEER_STORE"); return !(e && !strcmp(e, "ldst")); }();
+  return v;
+}
 static int peer_grid_per_sm() {
   static int v = [] { const char *e = getenv("PBGPU_PEER_GRID"); const int x = e ? atoi(e) : 2; return x > 0 && x <= 8 ? x : 0; }();
   return v;
@@ -554,8 +665,18 @@ static int peer_scatter_impl(const int32_t *d_contig, const int32_t *d_start, co
   if (peer_grid_per_sm() && grid > (int64_t)kSMs * peer_grid_per_sm()) grid = (int64_t)kSMs * peer_grid_per_sm();
   PB_LAUNCH(peer_block_count_kernel, (unsigned)nblk, kPeerThreads, 0, s, d_contig, n, d_owner, n_contigs, n_ranks, (const long long *)d_flag, bc, nblk);
   PB_LAUNCH(peer_block_scan_kernel, (unsigned)n_ranks, 1024, 0, s, bc, nblk, (const long long *)d_flag);
-  PB_LAUNCH(peer_scatter_kernel, (unsigned)grid, kPeerThreads, 0, s, d_contig, d_start, d_end, n, d_owner, n_contigs, n_ranks,
-            (const long long *)d_row_id_base, (const PeerDst *)d_dst, bc, nblk, (const long long *)d_flag);
+  if (peer_bulk_store()) {
+    constexpr size_t smem = sizeof(int32_t) * 4 * (size_t)kPbStageRows;
+    static std::once_flag once;
+    std::call_once(once, [] { cudaFuncSetAttribute(peer_scatter_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+    int64_t bgrid = cdiv(nblk, kPbSub);
+    if (peer_grid_per_sm() && bgrid > (int64_t)kSMs * peer_grid_per_sm()) bgrid = (int64_t)kSMs * peer_grid_per_sm();
+    PB_LAUNCH(peer_scatter_bulk_kernel, (unsigned)bgrid, kPbThreads, smem, s, d_contig, d_start, d_end, n, d_owner, n_contigs, n_ranks,
+              (const long long *)d_row_id_base, (const PeerDst *)d_dst, bc, nblk, (const long long *)d_flag);
+  } else {
+    PB_LAUNCH(peer_scatter_kernel, (unsigned)grid, kPeerThreads, 0, s, d_contig, d_start, d_end, n, d_owner, n_contigs, n_ranks,
+              (const long long *)d_row_id_base, (const PeerDst *)d_dst, bc, nblk, (const long long *)d_flag);
+  }
   PB_CHECK_LAUNCH();
   return PBGPU_OK;
 }

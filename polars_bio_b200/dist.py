@@ -215,6 +215,9 @@ def replicate_table(contig: torch.Tensor, start: torch.Tensor, end: torch.Tensor
     return cols, sum(sizes_l[:rank]), sizes_l
 
 
+REPLICATE_MAX_ROWS = 400_000_000  # indexed rows a rank may hold as a full replica (28 GB of index + scratch)
+
+
 def join_strategy(hist_probe: torch.Tensor, hist_build: torch.Tensor, world: int) -> str:
     """'replicate' (``replicate_table`` of the indexed table, probes stay where they are) or 'shard' (``shard_tables``
     by contig owner), from the global per-contig histograms: replicate when the contigs cannot keep every rank busy
@@ -228,7 +231,10 @@ def join_strategy(hist_probe: torch.Tensor, hist_build: torch.Tensor, world: int
     if total == 0:
         return "shard"
     busy = int((w > 0).sum())
-    if busy < world or float(w.max()) > 2.0 * total / world:
+    # replicating costs every rank a FULL index (about 70 bytes per indexed row, transient sort scratch included) and
+    # world x the build time: only while that stays a small part of a 180 GB device (REPLICATE_MAX_ROWS); a larger
+    # single-contig table is sharded (or joined on one GPU) instead
+    if (busy < world or float(w.max()) > 2.0 * total / world) and float(hb.sum()) <= REPLICATE_MAX_ROWS:
         return "replicate"
     moved_shard = total * (world - 1) / world            # rows crossing links, all ranks together
     moved_replicate = float(hb.sum()) * (world - 1)
@@ -584,6 +590,8 @@ class PeerExchange:
         """All launches of one step, without waiting for anything.  Returns (arena parity, per-table events or None).
         ``overlap`` (flags only): table t's scatter / signal / wait run on side stream t; the caller makes its stream
         wait for event t before touching table t."""
+        import os
+
         from . import _native
         from .engine import _stream_ptr
 
@@ -612,12 +620,29 @@ class PeerExchange:
             if overlap and self.sync == "flags":
                 self.planned.record(main)
                 events = []
+                # The scatters take turns on the link, in list order (PBGPU_PEER_SERIAL=0: all at once, the first
+                # version): the first table -- the indexed one -- gets the whole NVLink egress and is complete after
+                # its own bytes instead of after everybody's, so its index build starts (and overlaps the scatter of the
+                # next table) that much earlier.  Only the scatter is serialised; signal + wait follow on each stream.
+                serial = os.environ.get("PBGPU_PEER_SERIAL", "1") != "0"
+                prev_scatter = None
                 for t in range(self.T):
                     st = self.side[t]
                     st.wait_event(self.planned)
                     for col in tables[t]:
                         col.record_stream(st)
-                    _native.check(L.pbgpu_peer_table(d, t, st.cuda_stream))
+                    if serial:
+                        if prev_scatter is not None:
+                            st.wait_event(prev_scatter)
+                        self.desc.phases = self.PH_SCATTER
+                        _native.check(L.pbgpu_peer_table(d, t, st.cuda_stream))
+                        prev_scatter = torch.cuda.Event()
+                        prev_scatter.record(st)
+                        self.desc.phases = self.PH_SIGNAL | self.PH_WAIT
+                        _native.check(L.pbgpu_peer_table(d, t, st.cuda_stream))
+                        self.desc.phases = 0
+                    else:
+                        _native.check(L.pbgpu_peer_table(d, t, st.cuda_stream))
                     ev = torch.cuda.Event(enable_timing=laps is not None)
                     ev.record(st)
                     events.append(ev)
@@ -715,8 +740,8 @@ _peer_cache: dict = {}
 
 def exchange_kind(group=None) -> str:
     """'peer' or 'nccl': what ``shard_tables`` uses for this group right now."""
-    for (g, _, _), ex in _peer_cache.items():
-        if g == id(group) and ex is not None:
+    for k, ex in _peer_cache.items():
+        if k[0] == id(group) and ex is not None:
             return "peer"
     return "nccl"
 
@@ -724,8 +749,8 @@ def exchange_kind(group=None) -> str:
 def exchange_sync(group=None) -> str:
     """How the peer exchange of this group synchronises: 'flags' (peer memory), 'nccl' (all_gather + all_reduce), or
     'n/a' when the rows travel through the NCCL all-to-all."""
-    for (g, _, _), ex in _peer_cache.items():
-        if g == id(group) and ex is not None:
+    for k, ex in _peer_cache.items():
+        if k[0] == id(group) and ex is not None:
             return ex.sync
     return "n/a"
 
@@ -738,19 +763,23 @@ def _peer_exchange_for(tables, n_contigs: int, group=None):
 
     dev = tables[0][0].device
     T = len(tables)
-    if dev.type != "cuda" or os.environ.get("PBGPU_EXCHANGE", "peer") == "nccl":
+    if dev.type != "cuda":
         return None
-    key = (id(group), int(n_contigs), T)
+    key = (id(group), int(n_contigs), T, dev.index)
     if key in _peer_cache:
         return _peer_cache[key]
     collective = dist.is_initialized() and dist.get_world_size(group) > 1
     world = dist.get_world_size(group) if collective else 1
     ex = None
-    if world <= PEER_MAX_RANKS and T <= PEER_MAX_TABLES and all(c.numel() < (1 << 32) for c, _, _ in tables):
-        sizes = torch.tensor([c.numel() for c, _, _ in tables], dtype=torch.int64, device=dev)
-        if collective:
-            dist.all_reduce(sizes, group=group)
-        caps = [int(x) // world * 5 // 4 + 4096 for x in sizes.tolist()]
+    # every rank must take the same branch below (the constructor runs collectives): the local verdict -- slice sizes,
+    # rank / table limits -- is agreed on with ONE unconditional MIN all_reduce, together with the SUM of the slice sizes
+    local_ok = (os.environ.get("PBGPU_EXCHANGE", "peer") != "nccl" and world <= PEER_MAX_RANKS and T <= PEER_MAX_TABLES
+                and all(c.numel() < (1 << 32) for c, _, _ in tables))
+    sizes = torch.tensor([c.numel() for c, _, _ in tables] + [0 if local_ok else 1], dtype=torch.int64, device=dev)
+    if collective:
+        dist.all_reduce(sizes, group=group)
+    if int(sizes[-1].item()) == 0:
+        caps = [int(x) // world * 5 // 4 + 4096 for x in sizes[:-1].tolist()]
         try:
             ex = PeerExchange(n_contigs, caps, dev, group)
         except PeerUnavailable as e:
