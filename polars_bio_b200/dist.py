@@ -773,13 +773,15 @@ def _peer_exchange_for(tables, n_contigs: int, group=None):
     ex = None
     # every rank must take the same branch below (the constructor runs collectives): the local verdict -- slice sizes,
     # rank / table limits -- is agreed on with ONE unconditional MIN all_reduce, together with the SUM of the slice sizes
-    local_ok = (os.environ.get("PBGPU_EXCHANGE", "peer") != "nccl" and world <= PEER_MAX_RANKS and T <= PEER_MAX_TABLES
-                and all(c.numel() < (1 << 32) for c, _, _ in tables))
-    sizes = torch.tensor([c.numel() for c, _, _ in tables] + [0 if local_ok else 1], dtype=torch.int64, device=dev)
+    local_ok = world <= PEER_MAX_RANKS and T <= PEER_MAX_TABLES and all(c.numel() < (1 << 32) for c, _, _ in tables)
+    env_nccl = os.environ.get("PBGPU_EXCHANGE", "peer") == "nccl"
+    sizes = torch.tensor([c.numel() for c, _, _ in tables] + [0 if local_ok else 1, 1 if env_nccl else 0], dtype=torch.int64, device=dev)
     if collective:
         dist.all_reduce(sizes, group=group)
-    if int(sizes[-1].item()) == 0:
-        caps = [int(x) // world * 5 // 4 + 4096 for x in sizes[:-1].tolist()]
+    if int(sizes[-1].item()) > 0:  # PBGPU_EXCHANGE=nccl on some rank: everybody takes the NCCL path, nothing is cached
+        return None
+    if int(sizes[-2].item()) == 0:
+        caps = [int(x) // world * 5 // 4 + 4096 for x in sizes[:-2].tolist()]
         try:
             ex = PeerExchange(n_contigs, caps, dev, group)
         except PeerUnavailable as e:
