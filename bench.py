@@ -11,7 +11,7 @@ every rank starts with a contiguous 1/N block of the rows of both tables (arbitr
 every row to the rank that owns its contig (LPT over the 24 skewed contigs), then every rank joins its contigs.
 One step = one pass of the whole hot path over that batch:
     [N > 1: contig exchange]  ->  index build  ->  count_overlaps (int64 per read)
-    ->  overlap pass 1 (count + offsets)  ->  overlap pass 2 (exact-sized (read, variant) pair buffer)  [-> global ids]
+    ->  overlap pass 1 (count + offsets)  ->  overlap pass 2 (exact-sized (read, variant) pair buffer of GLOBAL row ids)
 `value`   : pairs emitted per second, int32 columns already resident in HBM (CUDA events; inputs are 2.3 GB >> L2).
 `e2e`     : the same job through the public host-facing call with HOST buffers: N = 1 pb.count_overlaps + pb.overlap on
             host Arrow tables (utf8 contig) with the output frames materialised batch by batch; N > 1 pinned host
@@ -517,12 +517,11 @@ def run_sharded(args, world, rank, dev, local):
         main = torch.cuda.current_stream()
         if ready: main.wait_event(ready[0])
         if ev and not ready: ev[1].record()
-        ix = engine.DeviceIndex(xc, xs, xe, NC)
+        ix = engine.DeviceIndex(xc, xs, xe, NC, row_ids=xrow)  # global row ids travel with the rows: pairs come out global
         if ready: main.wait_event(ready[1])
         if ev and ready: ev[1].record()
         cnt = ix.count_overlaps(qc, qs, qe, FO)
-        a, b = ix.overlap_pairs(qc, qs, qe, FO)
-        pbd.translate(a, qrow); pbd.translate(b, xrow)
+        a, b = ix.overlap_pairs(qc, qs, qe, FO, probe_ids=qrow)
         ix.close()
         return cnt, a, b, qrow, qc, xc.numel()
 

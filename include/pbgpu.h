@@ -77,6 +77,11 @@ typedef struct pbgpu_index pbgpu_index;
 
 PBGPU_API int pbgpu_index_build(const int32_t *d_contig, const int32_t *d_start, const int32_t *d_end,
                                 int64_t m, int32_t n_contigs, void *stream, pbgpu_index **out);
+/* The same with an explicit id column: indexed row i is reported as d_row_ids[i] (uint32) wherever the plain build
+ * reports i -- pair buffers, nearest partners.  Multi-GPU: the global row ids that travelled with the rows, so results
+ * need no translation pass.  d_row_ids == NULL: pbgpu_index_build. */
+PBGPU_API int pbgpu_index_build_ids(const int32_t *d_contig, const int32_t *d_start, const int32_t *d_end,
+                                    const uint32_t *d_row_ids, int64_t m, int32_t n_contigs, void *stream, pbgpu_index **out);
 PBGPU_API void pbgpu_index_free(pbgpu_index *ix);
 /* Stream-ordered release: the index memory becomes reusable only after everything enqueued on `stream` so far (the
  * kernels that read the index) has run.  The right call for users of non-blocking streams. */
@@ -108,6 +113,10 @@ typedef struct pbgpu_overlap_plan pbgpu_overlap_plan;
 PBGPU_API int pbgpu_overlap_count(const pbgpu_index *ix, const int32_t *d_contig, const int32_t *d_start,
                                   const int32_t *d_end, int64_t n, int filter_op, void *stream,
                                   pbgpu_overlap_plan **plan, int64_t *total_pairs);
+/* pbgpu_overlap_count with an id column for the probes: probe row i is reported as d_probe_ids[i] (NULL: i). */
+PBGPU_API int pbgpu_overlap_count_ids(const pbgpu_index *ix, const int32_t *d_contig, const int32_t *d_start,
+                                      const int32_t *d_end, const uint32_t *d_probe_ids, int64_t n, int filter_op,
+                                      void *stream, pbgpu_overlap_plan **plan, int64_t *total_pairs);
 PBGPU_API int pbgpu_overlap_emit(const pbgpu_overlap_plan *plan, uint32_t *d_probe_rows,
                                  uint32_t *d_build_rows, void *stream);
 /* per-probe pair counts of pass 1 (uint32[n], device; valid until the plan is freed) -- the

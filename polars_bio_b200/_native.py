@@ -84,6 +84,7 @@ def lib() -> ctypes.CDLL:
     L.pbgpu_device_count.argtypes = [ctypes.POINTER(ctypes.c_int)]
     L.pbgpu_launch_count.restype = u64
     L.pbgpu_index_build.argtypes = [vp, vp, vp, i64, i32, vp, ctypes.POINTER(vp)]
+    L.pbgpu_index_build_ids.argtypes = [vp, vp, vp, vp, i64, i32, vp, ctypes.POINTER(vp)]
     L.pbgpu_index_free.argtypes = [vp]
     L.pbgpu_index_free.restype = None
     L.pbgpu_index_free_async.argtypes = [vp, vp]
@@ -95,6 +96,7 @@ def lib() -> ctypes.CDLL:
     L.pbgpu_count_overlaps.argtypes = [vp, vp, vp, vp, i64, ctypes.c_int, vp, vp]
     L.pbgpu_coverage.argtypes = [vp, vp, vp, vp, i64, ctypes.c_int, vp, vp]
     L.pbgpu_overlap_count.argtypes = [vp, vp, vp, vp, i64, ctypes.c_int, vp, ctypes.POINTER(vp), ctypes.POINTER(i64)]
+    L.pbgpu_overlap_count_ids.argtypes = [vp, vp, vp, vp, vp, i64, ctypes.c_int, vp, ctypes.POINTER(vp), ctypes.POINTER(i64)]
     L.pbgpu_overlap_emit.argtypes = [vp, vp, vp, vp]
     L.pbgpu_overlap_plan_blocks.argtypes = [vp]
     L.pbgpu_overlap_plan_blocks.restype = i64

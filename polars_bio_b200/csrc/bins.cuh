@@ -13,9 +13,12 @@
 // saved destination of every row (a gather whose sources are the same runs, so it reads whole sectors).
 //
 // Record (16 bytes, one LDG.128 per probe in every later kernel):
-//   x = global-axis start (clamped into the contig's slice), y = global-axis end, z = original row id,
-//   w = contig code of a proper probe | -1: no indexed rows on its contig / null key (count 0, nothing to look up)
-//       | -2 - contig: empty or inverted probe interval (bare predicate over the candidate window; s / e re-read by row)
+//   proper probe      : x = global-axis start (clamped into the contig's slice), y = global-axis end, w = contig code
+//   w = -1            : no indexed rows on its contig / null key (count 0, nothing to look up); bin 0
+//   w = -2 - contig   : empty or inverted probe interval: x = RAW start, y = RAW end (bare predicate over the candidate
+//                       window of the generic kernels); bin 0 (rare; their lookups are not worth a bin)
+//   z = the id reported for the probe: its row, or the caller's id column (multi-GPU: global row ids, so no translation
+//       pass over the pair buffer is needed)
 #pragma once
 #include "common.cuh"
 #include "index.cuh"
@@ -36,8 +39,10 @@ __device__ __forceinline__ int4 make_probe_rec(const IndexView &ix, int32_t c, i
   le = le < cm.lo_m1 ? cm.lo_m1 : (le > cm.hi_p1 ? cm.hi_p1 : le);
   const uint32_t g_s = cm.off + (uint32_t)(ls - cm.lo_m1), g_e = cm.off + (uint32_t)(le - cm.lo_m1);
   const bool proper = strict ? (s < e) : (s <= e);
-  return make_int4((int)g_s, (int)g_e, (int)row, proper ? c : -2 - c);
+  if (!proper) return make_int4(s, e, (int)row, -2 - c);
+  return make_int4((int)g_s, (int)g_e, (int)row, c);
 }
+__device__ __forceinline__ unsigned rec_bin(const int4 r, int bin_shift) { return r.w >= 0 ? ((uint32_t)r.x >> bin_shift) : 0u; }
 // bin of a probe: top bits of its global start; probes that look nothing up go to bin 0
 __device__ __forceinline__ uint32_t probe_bin(const IndexView &ix, int32_t c, int32_t s, int bin_shift) {
   if (c < 0 || c >= ix.n_contigs) return 0u;
@@ -48,21 +53,23 @@ __device__ __forceinline__ uint32_t probe_bin(const IndexView &ix, int32_t c, in
   return (cm.off + (uint32_t)(ls - cm.lo_m1)) >> bin_shift;
 }
 
-__global__ void __launch_bounds__(512) bin_hist_kernel(IndexView ix, const int32_t *__restrict__ pc, const int32_t *__restrict__ ps, int64_t n,
-                                                       int bin_shift, uint32_t *__restrict__ totals /*[256], zeroed*/) {
+__global__ void __launch_bounds__(512) bin_hist_kernel(IndexView ix, const int32_t *__restrict__ pc, const int32_t *__restrict__ ps,
+                                                       const int32_t *__restrict__ pe, int64_t n, int bin_shift, int strict,
+                                                       uint32_t *__restrict__ totals /*[256], zeroed*/) {
   __shared__ uint32_t h[kBinRadix];
   for (int i = threadIdx.x; i < kBinRadix; i += 512) h[i] = 0;
   __syncthreads();
   constexpr int U = 4;
   const int64_t stride = (int64_t)gridDim.x * 512;
   for (int64_t i0 = (int64_t)blockIdx.x * 512 + threadIdx.x; i0 < n; i0 += stride * U) {
-    int32_t c[U], s[U];
+    int32_t c[U], s[U], e[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) { const int64_t i = i0 + u * stride; const bool ok = i < n; c[u] = ok ? pc[i] : -1; s[u] = ok ? ps[i] : 0; }
+    for (int u = 0; u < U; ++u) { const int64_t i = i0 + u * stride; const bool ok = i < n; c[u] = ok ? pc[i] : -1; s[u] = ok ? ps[i] : 0; e[u] = ok ? pe[i] : 0; }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (i0 + u * stride >= n) continue;
-      const uint32_t d = probe_bin(ix, c[u], s[u], bin_shift);
+      const bool proper = strict ? (s[u] < e[u]) : (s[u] <= e[u]);
+      const uint32_t d = proper ? probe_bin(ix, c[u], s[u], bin_shift) : 0u;
       // neighbouring lanes often share a bin only by chance (random probes): plain shared-memory atomics
       atomicAdd(&h[d], 1u);
     }
@@ -76,6 +83,7 @@ __global__ void __launch_bounds__(512) bin_hist_kernel(IndexView ix, const int32
 template <bool WRITE_POS, int OCC>
 __global__ void __launch_bounds__(kBinThreads, OCC) bin_partition_kernel(IndexView ix, const int32_t *__restrict__ pc,
                                                                        const int32_t *__restrict__ ps, const int32_t *__restrict__ pe,
+                                                                       const uint32_t *__restrict__ ids /*NULL: the row*/,
                                                                        int64_t n, int bin_shift, int strict,
                                                                        const uint32_t *__restrict__ totals /*[256]*/,
                                                                        uint32_t *status /*[tiles][256], zeroed*/, uint32_t *ticket /*zeroed*/,
@@ -107,7 +115,11 @@ __global__ void __launch_bounds__(kBinThreads, OCC) bin_partition_kernel(IndexVi
       c[r] = ok ? pc[tbase + li] : -1; s[r] = ok ? ps[tbase + li] : 0; e[r] = ok ? pe[tbase + li] : 0;
     }
 #pragma unroll
-    for (int r = 0; r < kBinItems; ++r) rec[r] = make_probe_rec(ix, c[r], s[r], e[r], (uint32_t)(tbase + wofs + r * 32 + lane), strict != 0);
+    for (int r = 0; r < kBinItems; ++r) {
+      const int li = wofs + r * 32 + lane;
+      const uint32_t id = (ids && li < tile_n) ? ids[tbase + li] : (uint32_t)(tbase + li);
+      rec[r] = make_probe_rec(ix, c[r], s[r], e[r], id, strict != 0);
+    }
   }
   // bins + the eight MATCH instructions first, then the serial counter chain that consumes them (radix_sort.cuh)
   unsigned dg[kBinItems];
@@ -116,7 +128,7 @@ __global__ void __launch_bounds__(kBinThreads, OCC) bin_partition_kernel(IndexVi
 #pragma unroll
     for (int r = 0; r < kBinItems; ++r) {
       const bool ok = wofs + r * 32 + lane < tile_n;
-      dg[r] = ok ? (rec[r].w == -1 ? 0u : ((uint32_t)rec[r].x >> bin_shift)) : 0x100u;
+      dg[r] = ok ? rec_bin(rec[r], bin_shift) : 0x100u;
       peers[r] = __match_any_sync(0xffffffffu, dg[r]);
     }
 #pragma unroll
@@ -212,8 +224,7 @@ __global__ void __launch_bounds__(kBinThreads, OCC) bin_partition_kernel(IndexVi
     const int p = r * kBinThreads + threadIdx.x;
     if (p < tile_n) {
       const int4 v = stage[p];
-      const unsigned d = v.w == -1 ? 0u : ((uint32_t)v.x >> bin_shift);
-      recs[dbase[d] + (uint32_t)p] = v;
+      recs[dbase[rec_bin(v, bin_shift)] + (uint32_t)p] = v;
     }
   }
 }
@@ -227,8 +238,7 @@ __device__ __forceinline__ void ld_er4(const uint2 *__restrict__ p, uint32_t (&w
 
 // count of one partitioned probe; hi_out as fast_count()
 template <bool STRICT>
-__device__ __forceinline__ uint32_t binned_count(const IndexView &ix, const int4 r, const int32_t *__restrict__ ps,
-                                                 const int32_t *__restrict__ pe, uint32_t &hi_out) {
+__device__ __forceinline__ uint32_t binned_count(const IndexView &ix, const int4 r, uint32_t &hi_out) {
   hi_out = 0;
   if (r.w >= 0) {
     uint32_t hi, re;
@@ -237,13 +247,12 @@ __device__ __forceinline__ uint32_t binned_count(const IndexView &ix, const int4
     return hi - re;
   }
   if (r.w == -1) return 0;
-  hi_out = kGenericProbe;  // empty / inverted probe: bare predicate, raw coordinates re-read by row
-  return probe_count<STRICT>(ix, -2 - r.w, __ldg(ps + (uint32_t)r.z), __ldg(pe + (uint32_t)r.z));
+  hi_out = kGenericProbe;  // empty / inverted probe: bare predicate over its raw coordinates
+  return probe_count<STRICT>(ix, -2 - r.w, r.x, r.y);
 }
 
 template <bool STRICT, int ITEMS>
-__global__ void __launch_bounds__(kSweepThreads) binned_count_kernel(IndexView ix, const int4 *__restrict__ recs, const int32_t *__restrict__ ps,
-                                                                     const int32_t *__restrict__ pe, int64_t n, uint32_t *__restrict__ cnt_b) {
+__global__ void __launch_bounds__(kSweepThreads) binned_count_kernel(IndexView ix, const int4 *__restrict__ recs, int64_t n, uint32_t *__restrict__ cnt_b) {
   const int64_t base = (int64_t)blockIdx.x * (kSweepThreads * ITEMS) + threadIdx.x;
   int4 r[ITEMS];
 #pragma unroll
@@ -253,7 +262,7 @@ __global__ void __launch_bounds__(kSweepThreads) binned_count_kernel(IndexView i
   }
   uint32_t cnt[ITEMS];
 #pragma unroll
-  for (int j = 0; j < ITEMS; ++j) { uint32_t hi; cnt[j] = binned_count<STRICT>(ix, r[j], ps, pe, hi); }
+  for (int j = 0; j < ITEMS; ++j) { uint32_t hi; cnt[j] = binned_count<STRICT>(ix, r[j], hi); }
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     const int64_t i = base + (int64_t)j * kSweepThreads;
@@ -279,8 +288,7 @@ __global__ void __launch_bounds__(256) unbin_counts_kernel(const uint32_t *__res
 // pass 1 over partitioned probes: (count, start rank) per position + the raw total of every 256 positions (scanned by the
 // caller) + the offset of every 32-position group inside its block (flat pass 2)
 template <bool STRICT, int ITEMS>
-__global__ void __launch_bounds__(kSweepThreads) binned_p1_kernel(IndexView ix, const int4 *__restrict__ recs, const int32_t *__restrict__ ps,
-                                                                  const int32_t *__restrict__ pe, int64_t n, uint32_t *__restrict__ counts,
+__global__ void __launch_bounds__(kSweepThreads) binned_p1_kernel(IndexView ix, const int4 *__restrict__ recs, int64_t n, uint32_t *__restrict__ counts,
                                                                   uint32_t *__restrict__ his, unsigned long long *__restrict__ block_base,
                                                                   unsigned long long *__restrict__ warp_off) {
   __shared__ unsigned long long wt[ITEMS][kSweepThreads / 32];
@@ -293,7 +301,7 @@ __global__ void __launch_bounds__(kSweepThreads) binned_p1_kernel(IndexView ix, 
   }
   uint32_t cnt[ITEMS], hi[ITEMS];
 #pragma unroll
-  for (int j = 0; j < ITEMS; ++j) cnt[j] = binned_count<STRICT>(ix, r[j], ps, pe, hi[j]);
+  for (int j = 0; j < ITEMS; ++j) cnt[j] = binned_count<STRICT>(ix, r[j], hi[j]);
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     const int64_t i = base + (int64_t)j * kSweepThreads;
@@ -333,7 +341,7 @@ constexpr uint32_t kEmitHeavy = 192;   // hits of ONE probe from which the whole
 template <bool STRICT, bool BINNED>
 __global__ void __launch_bounds__(kSweepThreads) overlap_emit_staged_kernel(IndexView ix, const int4 *__restrict__ recs,
                                                                             const int32_t *__restrict__ pc, const int32_t *__restrict__ ps,
-                                                                            const int32_t *__restrict__ pe, int64_t n,
+                                                                            const int32_t *__restrict__ pe, const uint32_t *__restrict__ ids, int64_t n,
                                                                             const uint32_t *__restrict__ counts, const uint32_t *__restrict__ his,
                                                                             const unsigned long long *__restrict__ block_base, int64_t blk0,
                                                                             uint32_t *__restrict__ out_probe, uint32_t *__restrict__ out_build) {
@@ -344,16 +352,17 @@ __global__ void __launch_bounds__(kSweepThreads) overlap_emit_staged_kernel(Inde
   const int64_t i = blk * kSweepThreads + threadIdx.x;
   uint32_t cnt = 0, hi = 0, pid = (uint32_t)i;
   long long s = 0;  // probe start in the index's own coordinates (raw, or a stand-in with the same order against every indexed end)
-  int32_t c = -1;
+  int32_t c = -1, e_raw = 0;
   if (i < n) {
     cnt = counts[i]; hi = his[i];
     if (BINNED) {
       const int4 r = recs[i];
-      pid = (uint32_t)r.z;
+      pid = (uint32_t)r.z;  // already the caller's id when an id column was given
       if (r.w >= 0) { c = r.w; const ContigMap cm = ix.cmap[c]; s = (long long)(uint32_t)r.x - (long long)cm.off + cm.lo_m1; }
-      else if (r.w < -1) { c = -2 - r.w; s = __ldg(ps + pid); }
+      else if (r.w < -1) { c = -2 - r.w; s = r.x; e_raw = r.y; }
     } else {
       s = ps[i];
+      if (ids) pid = ids[i];
     }
   }
   const unsigned long long pos = block_base[blk] - block_base[blk0] + block_exclusive<SumU64, kSweepThreads>((unsigned long long)cnt, wt);
@@ -372,7 +381,7 @@ __global__ void __launch_bounds__(kSweepThreads) overlap_emit_staged_kernel(Inde
   int64_t j = (int64_t)hi - 1, jlo = 0;
   if (generic) {
     const int32_t cc = BINNED ? c : pc[i];
-    const int32_t ee = BINNED ? __ldg(pe + pid) : pe[i];
+    const int32_t ee = BINNED ? e_raw : pe[i];
     int32_t glo, ghi;
     probe_window<STRICT>(ix, ix.seg[cc], ix.seg[cc + 1], (int32_t)s, ee, glo, ghi);
     j = (int64_t)ghi - 1; jlo = glo;

@@ -128,7 +128,8 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(const int32_t *__res
                                                             const int32_t *__restrict__ e, int64_t n, int32_t n_contigs, int n_digits,
                                                             BuildStats *st, uint64_t *__restrict__ keys, uint64_t *__restrict__ vals,
                                                             uint32_t *__restrict__ digit_totals /*[kRsMaxPasses][256], zeroed*/,
-                                                            volatile unsigned long long *mailbox, unsigned long long mailbox_seq) {
+                                                            volatile unsigned long long *mailbox, unsigned long long mailbox_seq,
+                                                            const uint32_t *__restrict__ row_ids /*NULL: the row's position*/) {
   __shared__ uint32_t h[kRsMaxPasses][kRsRadix];
   __shared__ int sm[4][kPrepThreads / 32];
   __shared__ unsigned su[3][kPrepThreads / 32];
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(const int32_t *__res
       const bool ok = cc[u] >= 0 && cc[u] < n_contigs;
       const uint64_t key = ((ok ? (uint64_t)cc[u] : (uint64_t)n_contigs) << 32) | (ok ? ((uint32_t)ss[u] ^ 0x80000000u) : 0u);
       keys[i] = key;
-      vals[i] = ((uint64_t)(uint32_t)ee[u] << 32) | (uint32_t)i;
+      vals[i] = ((uint64_t)(uint32_t)ee[u] << 32) | (row_ids ? row_ids[i] : (uint32_t)i);
       for (int p = 0; p < n_digits; ++p) atomicAdd(&h[p][(key >> (8 * p)) & 0xff], 1u);
       if (ok) {
         mn_s = min(mn_s, ss[u]); mx_s = max(mx_s, ss[u]);
@@ -805,7 +806,8 @@ __global__ void __launch_bounds__(1024) contig_layout_mm_kernel(const int32_t *_
 __global__ void __launch_bounds__(kPrepThreads) gkeys_kernel(const int32_t *__restrict__ c, const int32_t *__restrict__ s,
                                                              const int32_t *__restrict__ e, int64_t n, int32_t n_contigs,
                                                              const ContigMap *__restrict__ cmap, uint64_t *__restrict__ keys,
-                                                             uint32_t *__restrict__ vals, uint32_t *__restrict__ digit_totals /*[kRsMaxPasses][256], zeroed*/) {
+                                                             uint32_t *__restrict__ vals, uint32_t *__restrict__ digit_totals /*[kRsMaxPasses][256], zeroed*/,
+                                                             const uint32_t *__restrict__ row_ids /*NULL: the row's position*/) {
   __shared__ uint32_t h[4][kRsRadix];
   for (int i = threadIdx.x; i < 4 * kRsRadix; i += kPrepThreads) (&h[0][0])[i] = 0;
   __syncthreads();
@@ -827,7 +829,7 @@ __global__ void __launch_bounds__(kPrepThreads) gkeys_kernel(const int32_t *__re
         const ContigMap cm = cmap[cc[u]];
         g = cm.off + (uint32_t)((long long)ss[u] - cm.lo_m1);
       }
-      keys[i] = ((uint64_t)g << 32) | (uint32_t)i;
+      keys[i] = ((uint64_t)g << 32) | (row_ids ? row_ids[i] : (uint32_t)i);
       vals[i] = (uint32_t)ee[u];
 #pragma unroll
       for (int p = 0; p < 4; ++p) atomicAdd(&h[p][(g >> (8 * p)) & 0xff], 1u);

@@ -509,8 +509,8 @@ static int alloc_slab2(pbgpu_index *ix, unsigned long long total_span, int64_t m
 }
 
 // ---- front half, global-key variant (index.cuh): returns *applies = false when the table needs the generic one ------
-static int build_front_gkey(pbgpu_index *ix, const int32_t *d_c, const int32_t *d_s, const int32_t *d_e, int64_t m_in, int32_t n_contigs,
-                            cudaStream_t s, Scratch &sc, BuildTrace &bt, BuildFront *fr, bool *applies) {
+static int build_front_gkey(pbgpu_index *ix, const int32_t *d_c, const int32_t *d_s, const int32_t *d_e, const uint32_t *d_ids, int64_t m_in,
+                            int32_t n_contigs, cudaStream_t s, Scratch &sc, BuildTrace &bt, BuildFront *fr, bool *applies) {
   *applies = false;
   int32_t *cmin = nullptr, *cmax = nullptr;
   GStats *d_st = nullptr;
@@ -560,7 +560,7 @@ static int build_front_gkey(pbgpu_index *ix, const int32_t *d_c, const int32_t *
   PB_CUDA(cudaMemsetAsync(d_totals, 0, sizeof(uint32_t) * kRsMaxPasses * kRsRadix, s));
   grid = cdiv(m_in, kPrepThreads * 2);
   if (grid > kSMs * 2) grid = kSMs * 2;
-  PB_LAUNCH(gkeys_kernel, (unsigned)grid, kPrepThreads, 0, s, d_c, d_s, d_e, m_in, n_contigs, d_cmap, k1, v1, d_totals);
+  PB_LAUNCH(gkeys_kernel, (unsigned)grid, kPrepThreads, 0, s, d_c, d_s, d_e, m_in, n_contigs, d_cmap, k1, v1, d_totals, d_ids);
   PB_CHECK_LAUNCH();
   // key bytes 4..7 hold the global start; without null-keyed rows (their sentinel sets every bit) only the bytes below
   // the top bit of the axis length vary
@@ -586,8 +586,8 @@ static int build_front_gkey(pbgpu_index *ix, const int32_t *d_c, const int32_t *
 }
 
 // ---- front half, generic variant: any contig count, inverted rows, axes beyond 2^32 --------------------------------------
-static int build_front_generic(pbgpu_index *ix, const int32_t *d_c, const int32_t *d_s, const int32_t *d_e, int64_t m_in, int32_t n_contigs,
-                               cudaStream_t s, Scratch &sc, BuildTrace &bt, BuildFront *fr) {
+static int build_front_generic(pbgpu_index *ix, const int32_t *d_c, const int32_t *d_s, const int32_t *d_e, const uint32_t *d_ids, int64_t m_in,
+                               int32_t n_contigs, cudaStream_t s, Scratch &sc, BuildTrace &bt, BuildFront *fr) {
   // 1. ONE pass over the input: coordinate statistics (key width, fast-path eligibility), the sort keys
   //    contig << 32 | biased start  with values  end << 32 | row, and the digit totals of every radix pass.
   //    The key format does not depend on the statistics, so nothing waits for the host before it.
@@ -616,7 +616,7 @@ static int build_front_generic(pbgpu_index *ix, const int32_t *d_c, const int32_
     static_assert(sizeof(BuildStats) == 48, "BuildStats: 5 payload words + the block counter word, posted by prep_kernel");
     const MailboxSlot slot = mailbox_open();
     PB_LAUNCH(prep_kernel, (unsigned)grid, kPrepThreads, 0, s, d_c, d_s, d_e, m_in, n_contigs, 4 + contig_digits, d_stats, keys, vals, d_totals,
-              slot.d, slot.seq);
+              slot.d, slot.seq, d_ids);
     PB_CHECK_LAUNCH();
     if (slot.d) PB_TRY(mailbox_wait(slot, 5, reinterpret_cast<unsigned long long *>(&hs), s));
     else PB_TRY(fetch_words(d_stats, 5, reinterpret_cast<unsigned long long *>(&hs), s));
@@ -694,7 +694,7 @@ static int build_front_generic(pbgpu_index *ix, const int32_t *d_c, const int32_
 // sweep_only: the caller wants the (contig, start, row) order, the segments and the running max of the ends only (the
 // unary sweeps of unary.cuh): the end order and the rank directory are skipped
 static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *d_s, const int32_t *d_e, int64_t m_in,
-                            int32_t n_contigs, cudaStream_t s, bool sweep_only = false) {
+                            int32_t n_contigs, cudaStream_t s, bool sweep_only = false, const uint32_t *d_ids = nullptr) {
   ix->m_in = m_in;
   ix->n_contigs = n_contigs;
   PB_CUDA(cudaGetDevice(&ix->device));
@@ -705,8 +705,8 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
   BuildFront fr;
   bool gkey = false;
   if (!build_generic_only() && m_in > 0 && n_contigs >= 1 && n_contigs <= 1024)
-    PB_TRY(build_front_gkey(ix, d_c, d_s, d_e, m_in, n_contigs, s, sc, bt, &fr, &gkey));
-  if (!gkey) PB_TRY(build_front_generic(ix, d_c, d_s, d_e, m_in, n_contigs, s, sc, bt, &fr));
+    PB_TRY(build_front_gkey(ix, d_c, d_s, d_e, d_ids, m_in, n_contigs, s, sc, bt, &fr, &gkey));
+  if (!gkey) PB_TRY(build_front_generic(ix, d_c, d_s, d_e, d_ids, m_in, n_contigs, s, sc, bt, &fr));
   const int64_t m = ix->m;
   if (m == 0) return PBGPU_OK;
   const bool nested = fr.nested;
@@ -802,6 +802,11 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
 
 int pbgpu_index_build(const int32_t *d_contig, const int32_t *d_start, const int32_t *d_end, int64_t m, int32_t n_contigs,
                       void *stream, pbgpu_index **out) {
+  return pbgpu_index_build_ids(d_contig, d_start, d_end, nullptr, m, n_contigs, stream, out);
+}
+
+int pbgpu_index_build_ids(const int32_t *d_contig, const int32_t *d_start, const int32_t *d_end, const uint32_t *d_row_ids, int64_t m,
+                          int32_t n_contigs, void *stream, pbgpu_index **out) {
   if (!out) return set_error(PBGPU_EINVAL, "out is NULL");
   *out = nullptr;
   if (m < 0 || n_contigs < 0) return set_error(PBGPU_EINVAL, "negative size");
@@ -810,7 +815,7 @@ int pbgpu_index_build(const int32_t *d_contig, const int32_t *d_start, const int
   if (n_contigs >= (1 << 30)) return set_error(PBGPU_ERANGE, "too many contigs");
   pbgpu_index *ix = new (std::nothrow) pbgpu_index();
   if (!ix) return set_error(PBGPU_ENOMEM, "host allocation failed");
-  int rc = index_build_impl(ix, d_contig, d_start, d_end, m, n_contigs, (cudaStream_t)stream);
+  int rc = index_build_impl(ix, d_contig, d_start, d_end, m, n_contigs, (cudaStream_t)stream, false, d_row_ids);
   if (rc != PBGPU_OK) {
     pbgpu_index_free(ix);
     return rc;
@@ -851,8 +856,8 @@ struct BinnedProbes {
   int bin_shift = 0;
 };
 // hist + one stable partition pass, enqueued on s.  The slab (records | pos | partition scratch) is the caller's to free.
-static int bin_probes(const pbgpu_index *ix, const int32_t *pc, const int32_t *ps, const int32_t *pe, int64_t n, int filter_op,
-                      bool write_pos, cudaStream_t s, BinnedProbes *out) {
+static int bin_probes(const pbgpu_index *ix, const int32_t *pc, const int32_t *ps, const int32_t *pe, const uint32_t *ids, int64_t n,
+                      int filter_op, bool write_pos, cudaStream_t s, BinnedProbes *out) {
   const int64_t tiles = cdiv(n, kBinTile);
   const size_t rec_b = align_up(sizeof(int4) * (size_t)n), pos_b = write_pos ? align_up(sizeof(uint32_t) * (size_t)n) : 0;
   const size_t work_w = (size_t)kBinRadix + 64 + (size_t)tiles * kBinRadix;  // totals | ticket | status
@@ -868,7 +873,7 @@ static int bin_probes(const pbgpu_index *ix, const int32_t *pc, const int32_t *p
   PB_CUDA(cudaMemsetAsync(work, 0, sizeof(uint32_t) * work_w, s));
   int64_t hgrid = cdiv(n, 512 * 4);
   if (hgrid > kSMs * 4) hgrid = kSMs * 4;
-  PB_LAUNCH(bin_hist_kernel, (unsigned)hgrid, 512, 0, s, view_of(ix), pc, ps, n, out->bin_shift, totals);
+  PB_LAUNCH(bin_hist_kernel, (unsigned)hgrid, 512, 0, s, view_of(ix), pc, ps, pe, n, out->bin_shift, filter_op == PBGPU_FILTER_STRICT, totals);
   constexpr size_t stage_b = sizeof(int4) * kBinTile;
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {
@@ -881,7 +886,7 @@ static int bin_probes(const pbgpu_index *ix, const int32_t *pc, const int32_t *p
   // PBGPU_BIN_STORE=ldst: copy the staged runs out through registers instead of TMA bulk stores (A/B)
   static const int bulk = [] { const char *e = getenv("PBGPU_BIN_STORE"); return (e && !strcmp(e, "ldst")) ? 0 : 1; }();
 #define PB_BINPART(WP, OCC)                                                                                                         \
-  PB_LAUNCH((bin_partition_kernel<WP, OCC>), (unsigned)tiles, kBinThreads, stage_b, s, view_of(ix), pc, ps, pe, n, out->bin_shift, strict, \
+  PB_LAUNCH((bin_partition_kernel<WP, OCC>), (unsigned)tiles, kBinThreads, stage_b, s, view_of(ix), pc, ps, pe, ids, n, out->bin_shift, strict, \
             totals, status, ticket, out->recs, out->pos, bulk)
   // r2f: the 40-register cap of the 3-blocks-per-SM build spills the 16-byte records (1.74 vs 1.55 ms per 100 M probes)
   static const int bin_occ = [] { const char *e = getenv("PBGPU_BIN_OCC"); return (e && e[0] == '3') ? 3 : 2; }();
@@ -909,13 +914,13 @@ int count_overlaps_impl(const pbgpu_index *ix, const int32_t *d_contig, const in
   const bool strict = filter_op == PBGPU_FILTER_STRICT;
   if (want_bins(ix, n)) {  // index beyond the L2: partition the probes by coordinate, count in bin order, counts back to row order
     BinnedProbes bp;
-    int rc = bin_probes(ix, d_contig, d_start, d_end, n, filter_op, true, s, &bp);
+    int rc = bin_probes(ix, d_contig, d_start, d_end, nullptr, n, filter_op, true, s, &bp);
     uint32_t *cnt_b = nullptr;
     if (rc == PBGPU_OK) rc = dev_alloc_t(&cnt_b, (size_t)n, s);
     if (rc == PBGPU_OK) {
       const unsigned g2 = (unsigned)cdiv(n, kSweepThreads * 2);
-      if (strict) PB_LAUNCH((binned_count_kernel<true, 2>), g2, kSweepThreads, 0, s, view_of(ix), bp.recs, d_start, d_end, n, cnt_b);
-      else PB_LAUNCH((binned_count_kernel<false, 2>), g2, kSweepThreads, 0, s, view_of(ix), bp.recs, d_start, d_end, n, cnt_b);
+      if (strict) PB_LAUNCH((binned_count_kernel<true, 2>), g2, kSweepThreads, 0, s, view_of(ix), bp.recs, n, cnt_b);
+      else PB_LAUNCH((binned_count_kernel<false, 2>), g2, kSweepThreads, 0, s, view_of(ix), bp.recs, n, cnt_b);
       g_ev.mark(EV_UNBIN0, s);
       PB_LAUNCH(unbin_counts_kernel<OutT>, (unsigned)cdiv(n, 256 * 4), 256, 0, s, cnt_b, bp.pos, n, d_counts);
       g_ev.mark(EV_UNBIN1, s);
@@ -1031,6 +1036,7 @@ struct pbgpu_overlap_plan {
   int64_t total;
   const int4 *recs;                 // probes partitioned by coordinate (bins.cuh) when the index is beyond the L2, else NULL
   void *bin_slab;
+  const uint32_t *probe_ids;        // id reported for probe row i (NULL: i itself)
 };
 
 extern "C" {
@@ -1061,6 +1067,12 @@ const uint32_t *pbgpu_overlap_plan_counts(const pbgpu_overlap_plan *plan) { retu
 
 int pbgpu_overlap_count(const pbgpu_index *ix, const int32_t *d_contig, const int32_t *d_start, const int32_t *d_end, int64_t n,
                         int filter_op, void *stream, pbgpu_overlap_plan **plan, int64_t *total_pairs) {
+  return pbgpu_overlap_count_ids(ix, d_contig, d_start, d_end, nullptr, n, filter_op, stream, plan, total_pairs);
+}
+
+int pbgpu_overlap_count_ids(const pbgpu_index *ix, const int32_t *d_contig, const int32_t *d_start, const int32_t *d_end,
+                            const uint32_t *d_probe_ids, int64_t n, int filter_op, void *stream, pbgpu_overlap_plan **plan,
+                            int64_t *total_pairs) {
   PB_TRY(check_probe_args(ix, d_contig, d_start, d_end, n, filter_op));
   if (!plan || !total_pairs) return set_error(PBGPU_EINVAL, "plan/total_pairs is NULL");
   *plan = nullptr;
@@ -1068,7 +1080,7 @@ int pbgpu_overlap_count(const pbgpu_index *ix, const int32_t *d_contig, const in
   cudaStream_t s = (cudaStream_t)stream;
   pbgpu_overlap_plan *p = new (std::nothrow) pbgpu_overlap_plan();
   if (!p) return set_error(PBGPU_ENOMEM, "host allocation failed");
-  *p = pbgpu_overlap_plan{ix, d_contig, d_start, d_end, n, filter_op, 0, cdiv(n, kSweepThreads), nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr};
+  *p = pbgpu_overlap_plan{ix, d_contig, d_start, d_end, n, filter_op, 0, cdiv(n, kSweepThreads), nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, d_probe_ids};
   cudaGetDevice(&p->device);
   auto fail = [&](int rc) { pbgpu_overlap_plan_free(p); return rc; };
   if (n == 0) { *plan = p; return PBGPU_OK; }
@@ -1099,15 +1111,15 @@ int pbgpu_overlap_count(const pbgpu_index *ix, const int32_t *d_contig, const in
   int rc = PBGPU_OK;
   if (binned) {  // index beyond the L2: pass 1 and pass 2 run over the probes partitioned by coordinate
     BinnedProbes bp;
-    rc = bin_probes(ix, d_contig, d_start, d_end, n, filter_op, false, s, &bp);
+    rc = bin_probes(ix, d_contig, d_start, d_end, d_probe_ids, n, filter_op, false, s, &bp);
     p->recs = bp.recs;
     p->bin_slab = bp.slab;
     if (rc != PBGPU_OK) return fail(rc);
     const unsigned g2 = (unsigned)cdiv(n, kSweepThreads * 2);
     if (filter_op == PBGPU_FILTER_STRICT)
-      PB_LAUNCH((binned_p1_kernel<true, 2>), g2, kSweepThreads, 0, s, view_of(ix), p->recs, d_start, d_end, n, p->counts, p->his, p->block_base, p->warp_off);
+      PB_LAUNCH((binned_p1_kernel<true, 2>), g2, kSweepThreads, 0, s, view_of(ix), p->recs, n, p->counts, p->his, p->block_base, p->warp_off);
     else
-      PB_LAUNCH((binned_p1_kernel<false, 2>), g2, kSweepThreads, 0, s, view_of(ix), p->recs, d_start, d_end, n, p->counts, p->his, p->block_base, p->warp_off);
+      PB_LAUNCH((binned_p1_kernel<false, 2>), g2, kSweepThreads, 0, s, view_of(ix), p->recs, n, p->counts, p->his, p->block_base, p->warp_off);
     if (cudaGetLastError() != cudaSuccess) return fail(set_error(PBGPU_ECUDA, "binned_p1_kernel launch failed"));
     g_ev.mark(EV_P1_1, s);
   } else if (ix->fast) {
@@ -1154,6 +1166,14 @@ int pbgpu_overlap_count(const pbgpu_index *ix, const int32_t *d_contig, const in
   return PBGPU_OK;
 }
 
+namespace pbgpu {
+__global__ void __launch_bounds__(256) probe_ids_in_place_kernel(uint32_t *__restrict__ rows, const unsigned long long *__restrict__ block_base,
+                                                                 int64_t blk_lo, int64_t blk_hi, const uint32_t *__restrict__ ids) {
+  const unsigned long long cnt = block_base[blk_hi] - block_base[blk_lo];
+  for (unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x; i < cnt; i += (unsigned long long)gridDim.x * 256) rows[i] = ids[rows[i]];
+}
+}  // namespace pbgpu
+
 static int emit_blocks_impl(const pbgpu_overlap_plan *p, int64_t blk_lo, int64_t blk_hi,
                             uint32_t *d_probe_rows, uint32_t *d_build_rows, cudaStream_t s) {
   g_ev.mark(EV_EMIT0, s);
@@ -1162,23 +1182,23 @@ static int emit_blocks_impl(const pbgpu_overlap_plan *p, int64_t blk_lo, int64_t
     const unsigned g2 = (unsigned)cdiv(blk_hi - blk_lo, 2);
     if (p->filter_op == PBGPU_FILTER_STRICT)
       PB_LAUNCH((overlap_emit_flat_kernel<true, 2>), g2, kSweepThreads, 0, s, view_of(p->ix), p->pc, p->ps, p->pe, p->n, p->counts,
-                p->his, p->block_base, p->warp_off, blk_lo, blk_hi, d_probe_rows, d_build_rows);
+                p->his, p->block_base, p->warp_off, blk_lo, blk_hi, d_probe_rows, d_build_rows, p->probe_ids);
     else
       PB_LAUNCH((overlap_emit_flat_kernel<false, 2>), g2, kSweepThreads, 0, s, view_of(p->ix), p->pc, p->ps, p->pe, p->n, p->counts,
-                p->his, p->block_base, p->warp_off, blk_lo, blk_hi, d_probe_rows, d_build_rows);
+                p->his, p->block_base, p->warp_off, blk_lo, blk_hi, d_probe_rows, d_build_rows, p->probe_ids);
   } else if (p->recs) {  // partitioned probes: pairs leave in bin order
     if (p->filter_op == PBGPU_FILTER_STRICT)
-      PB_LAUNCH((overlap_emit_staged_kernel<true, true>), grid, kSweepThreads, 0, s, view_of(p->ix), p->recs, p->pc, p->ps, p->pe, p->n, p->counts,
+      PB_LAUNCH((overlap_emit_staged_kernel<true, true>), grid, kSweepThreads, 0, s, view_of(p->ix), p->recs, p->pc, p->ps, p->pe, (const uint32_t *)nullptr, p->n, p->counts,
                 p->his, p->block_base, blk_lo, d_probe_rows, d_build_rows);
     else
-      PB_LAUNCH((overlap_emit_staged_kernel<false, true>), grid, kSweepThreads, 0, s, view_of(p->ix), p->recs, p->pc, p->ps, p->pe, p->n, p->counts,
+      PB_LAUNCH((overlap_emit_staged_kernel<false, true>), grid, kSweepThreads, 0, s, view_of(p->ix), p->recs, p->pc, p->ps, p->pe, (const uint32_t *)nullptr, p->n, p->counts,
                 p->his, p->block_base, blk_lo, d_probe_rows, d_build_rows);
   } else if (p->ix->fast && !emit_by_walk()) {
     if (p->filter_op == PBGPU_FILTER_STRICT)
-      PB_LAUNCH((overlap_emit_staged_kernel<true, false>), grid, kSweepThreads, 0, s, view_of(p->ix), (const int4 *)nullptr, p->pc, p->ps, p->pe, p->n,
+      PB_LAUNCH((overlap_emit_staged_kernel<true, false>), grid, kSweepThreads, 0, s, view_of(p->ix), (const int4 *)nullptr, p->pc, p->ps, p->pe, p->probe_ids, p->n,
                 p->counts, p->his, p->block_base, blk_lo, d_probe_rows, d_build_rows);
     else
-      PB_LAUNCH((overlap_emit_staged_kernel<false, false>), grid, kSweepThreads, 0, s, view_of(p->ix), (const int4 *)nullptr, p->pc, p->ps, p->pe, p->n,
+      PB_LAUNCH((overlap_emit_staged_kernel<false, false>), grid, kSweepThreads, 0, s, view_of(p->ix), (const int4 *)nullptr, p->pc, p->ps, p->pe, p->probe_ids, p->n,
                 p->counts, p->his, p->block_base, blk_lo, d_probe_rows, d_build_rows);
   } else if (p->ix->fast) {
     if (p->filter_op == PBGPU_FILTER_STRICT)
@@ -1193,6 +1213,9 @@ static int emit_blocks_impl(const pbgpu_overlap_plan *p, int64_t blk_lo, int64_t
   else
     PB_LAUNCH(overlap_emit_kernel<false>, grid, kSweepThreads, 0, s, view_of(p->ix), p->pc, p->ps, p->pe, p->n, p->counts,
               p->block_base, blk_lo, d_probe_rows, d_build_rows);
+  // the window-walking kernels of the generic path report probe rows: map them to the caller's ids in place
+  if (p->probe_ids && !p->recs && !p->warp_off && !(p->ix->fast && !emit_by_walk()))
+    PB_LAUNCH(probe_ids_in_place_kernel, kSMs * 8, 256, 0, s, d_probe_rows, p->block_base, blk_lo, blk_hi, p->probe_ids);
   PB_CHECK_LAUNCH();
   g_ev.mark(EV_EMIT1, s);
   return PBGPU_OK;

@@ -477,12 +477,14 @@ __global__ void __launch_bounds__(kSweepThreads) overlap_emit_flat_kernel(IndexV
                                                                           const unsigned long long *__restrict__ warp_off,
                                                                           int64_t blk0, int64_t blk_hi,
                                                                           uint32_t *__restrict__ out_probe,
-                                                                          uint32_t *__restrict__ out_build) {
+                                                                          uint32_t *__restrict__ out_build,
+                                                                          const uint32_t *__restrict__ ids /*NULL: probe row*/) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned long long base0 = block_base[blk0];
   uint32_t cnt[ITEMS], hi[ITEMS];
   unsigned long long bbase[ITEMS], woff[ITEMS];
   int64_t idx[ITEMS];
+  uint32_t pid[ITEMS];
 #pragma unroll
   for (int t = 0; t < ITEMS; ++t) {  // every load of the warp's ITEMS groups is in flight before the first use
     const int64_t blk = blk0 + (int64_t)blockIdx.x * ITEMS + t;
@@ -491,6 +493,7 @@ __global__ void __launch_bounds__(kSweepThreads) overlap_emit_flat_kernel(IndexV
     const bool ok = blk < blk_hi && i < n;
     cnt[t] = ok ? counts[i] : 0u;
     hi[t] = ok ? his[i] : 0u;
+    pid[t] = (ok && ids) ? ids[i] : (uint32_t)i;
     const bool gok = blk < blk_hi && (i - lane) < n;
     woff[t] = gok ? warp_off[blk * (kSweepThreads / 32) + warp] : 0ull;
     bbase[t] = gok ? block_base[blk] : base0;
@@ -516,9 +519,8 @@ __global__ void __launch_bounds__(kSweepThreads) overlap_emit_flat_kernel(IndexV
       probe_window<STRICT>(ix, ix.seg[c], ix.seg[c + 1], s, pe[i], lo, h2);
       unsigned long long p = wpos + excl;
       for (int32_t j = lo; j < h2; ++j)
-        if (end_hits<STRICT>(__ldg(ix.en + j), s)) { out_probe[p] = (uint32_t)i; out_build[p] = __ldg(ix.row + j); ++p; }
+        if (end_hits<STRICT>(__ldg(ix.en + j), s)) { out_probe[p] = pid[t]; out_build[p] = __ldg(ix.row + j); ++p; }
     }
-    const uint32_t i_first = (uint32_t)(idx[t] - lane);
     for (uint32_t j0 = 0; j0 < total; j0 += 32) {
       const uint32_t j = j0 + lane;
       int p = 0;
@@ -531,8 +533,9 @@ __global__ void __launch_bounds__(kSweepThreads) overlap_emit_flat_kernel(IndexV
       const uint32_t e_p = __shfl_sync(0xffffffffu, excl, p);
       const uint32_t f_p = __shfl_sync(0xffffffffu, first, p);
       const bool g_p = __shfl_sync(0xffffffffu, (int)generic, p) != 0;
+      const uint32_t id_p = __shfl_sync(0xffffffffu, pid[t], p);
       if (j < total && !g_p) {
-        out_probe[wpos + j] = i_first + (uint32_t)p;
+        out_probe[wpos + j] = id_p;
         out_build[wpos + j] = __ldg(ix.row + (f_p + (j - e_p)));
       }
     }

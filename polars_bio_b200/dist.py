@@ -283,11 +283,11 @@ def overlap(probe, build, n_contigs: int, filter_op: int, group=None, strategy: 
     (x, q), _ = shard_tables([tuple(build), tuple(probe)], n_contigs, group=group, ready=ready)
     main = torch.cuda.current_stream(probe[0].device)
     main.wait_event(ready[0])
-    ix = engine.DeviceIndex(x[0], x[1], x[2], n_contigs)
+    ix = engine.DeviceIndex(x[0], x[1], x[2], n_contigs, row_ids=x[3])  # global ids travel with the rows: nothing to translate
     main.wait_event(ready[1])
-    a, b = ix.overlap_pairs(q[0], q[1], q[2], filter_op)
+    a, b = ix.overlap_pairs(q[0], q[1], q[2], filter_op, probe_ids=q[3])
     ix.close()
-    return translate(a, q[3]), translate(b, x[3]), strategy
+    return a, b, strategy
 
 
 # ------------------------------------------------------------------------------------------------

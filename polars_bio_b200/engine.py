@@ -40,7 +40,10 @@ class DeviceIndex:
     is a null key that never matches); ``start``/``end`` are int32 coordinates.
     """
 
-    def __init__(self, contig: torch.Tensor, start: torch.Tensor, end: torch.Tensor, n_contigs: int):
+    def __init__(self, contig: torch.Tensor, start: torch.Tensor, end: torch.Tensor, n_contigs: int,
+                 row_ids: Optional[torch.Tensor] = None):
+        """``row_ids`` (int32 storage of uint32 ids, one per row): what indexed row i is called in pair buffers and
+        nearest partners instead of i -- the global row ids of a sharded table, so results need no translation."""
         if not torch.cuda.is_available():
             raise RuntimeError("polars_bio_b200 needs a CUDA device (no CPU fallback)")
         self.device = contig.device
@@ -48,9 +51,12 @@ class DeviceIndex:
         self._h = ctypes.c_void_p()
         self.n_contigs = int(n_contigs)
         c, s, e = (_col(x, self.device) for x in (contig, start, end))
+        ids = None if row_ids is None else _col(row_ids, self.device)
+        if ids is not None and ids.numel() != c.numel():
+            raise ValueError("row_ids must have one entry per row")
         with torch.cuda.device(self.device):
-            check(self._L.pbgpu_index_build(c.data_ptr(), s.data_ptr(), e.data_ptr(), c.numel(), self.n_contigs,
-                                            _stream_ptr(self.device), ctypes.byref(self._h)))
+            check(self._L.pbgpu_index_build_ids(c.data_ptr(), s.data_ptr(), e.data_ptr(), ids.data_ptr() if ids is not None else None,
+                                                c.numel(), self.n_contigs, _stream_ptr(self.device), ctypes.byref(self._h)))
 
     def close(self):
         """Stream-ordered release on the CURRENT stream of the index's device: the memory is reused only after the
@@ -97,17 +103,23 @@ class DeviceIndex:
         return out
 
     # -- OverlapProvider ---------------------------------------------------------------------
-    def overlap_pairs(self, contig, start, end, filter_op: int) -> Tuple[torch.Tensor, torch.Tensor]:
-        """Two-pass count-then-emit.  Returns (probe_rows, build_rows): int32 tensors holding
-        uint32 row ids, ordered by probe row then (start,row) of the indexed partner."""
+    def overlap_pairs(self, contig, start, end, filter_op: int, probe_ids: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Two-pass count-then-emit.  Returns (probe_rows, build_rows): int32 tensors holding uint32 row ids (or the
+        ids given by ``probe_ids`` / the index's ``row_ids``).  The pairs of one probe are contiguous and ordered by
+        (start, row) of the indexed partner; probes come in row order, or grouped by coordinate bin when the index is far
+        beyond the L2 (csrc/bins.cuh) -- pair order is not part of the contract (the reference's tests sort)."""
         c, s, e = (_col(x, self.device) for x in (contig, start, end))
         n = c.numel()
+        ids = None if probe_ids is None else _col(probe_ids, self.device)
+        if ids is not None and ids.numel() != n:
+            raise ValueError("probe_ids must have one entry per probe row")
         plan = ctypes.c_void_p()
         total = ctypes.c_int64(0)
         with torch.cuda.device(self.device):
             sp = _stream_ptr(self.device)
-            check(self._L.pbgpu_overlap_count(self._h, c.data_ptr(), s.data_ptr(), e.data_ptr(), n, filter_op, sp,
-                                              ctypes.byref(plan), ctypes.byref(total)))
+            check(self._L.pbgpu_overlap_count_ids(self._h, c.data_ptr(), s.data_ptr(), e.data_ptr(),
+                                                  ids.data_ptr() if ids is not None else None, n, filter_op, sp,
+                                                  ctypes.byref(plan), ctypes.byref(total)))
             try:
                 p = torch.empty(total.value, dtype=torch.int32, device=self.device)
                 b = torch.empty(total.value, dtype=torch.int32, device=self.device)
