@@ -94,7 +94,13 @@ def _to_device(*cols: np.ndarray):
     if not torch.cuda.is_available():
         raise RuntimeError("polars_bio_b200 needs a CUDA device (no CPU fallback)")
     dev = torch.device("cuda", torch.cuda.current_device())
-    return [torch.from_numpy(np.ascontiguousarray(c, dtype=np.int32)).pin_memory().to(dev, non_blocking=True) for c in cols]
+    out = []
+    for c in cols:
+        a = np.ascontiguousarray(c, dtype=np.int32)
+        if not a.flags.writeable:  # zero-copy views of Arrow buffers are read-only; torch wants to own a writable array
+            a = a.copy()
+        out.append(torch.from_numpy(a).pin_memory().to(dev, non_blocking=True))
+    return out
 
 
 def _contig_column(names: List[str], codes: np.ndarray, like: pa.DataType) -> pa.Array:
