@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kBinThreads, OCC) bin_partition_kernel(IndexVi
     for (int r = 0; r < kBinItems; ++r) {
       const bool ok = wofs + r * 32 + lane < tile_n;
       dg[r] = ok ? rec_bin(rec[r], bin_shift) : 0x100u;
-      peers[r] = __match_any_sync(0xffffffffu, dg[r]);
+      peers[r] = rs_match(dg[r]);
     }
 #pragma unroll
     for (int r = 0; r < kBinItems; ++r) {

@@ -95,6 +95,21 @@ __device__ __forceinline__ unsigned lanemask_lt() {
   return m;
 }
 
+// Lanes of the warp holding the same 9-bit value (bit 8 = "no element"): the ballot form of __match_any_sync.  The MATCH
+// instruction walks the distinct values of the warp one by one -- with random 8-bit digits that is ~28 rounds, and ncu
+// (r2h) showed the radix passes stalled on its result (short scoreboard 32 %, DRAM 27 % busy).  Nine VOTE + LOP3 pairs
+// cost the same whatever the values are.
+__device__ __forceinline__ unsigned match9(unsigned d) {
+  unsigned peers = 0xffffffffu;
+#pragma unroll
+  for (int b = 0; b < 9; ++b) {
+    const bool bit = (d >> b) & 1u;
+    const unsigned v = __ballot_sync(0xffffffffu, bit);
+    peers &= bit ? v : ~v;
+  }
+  return peers;
+}
+
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
   unsigned long long v;
   asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");

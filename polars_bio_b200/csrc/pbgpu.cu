@@ -371,12 +371,15 @@ struct BuildTrace {
   }
 };
 
-// PBGPU_JDIR_SHIFT=k: k more bits per directory bucket than the 0.6-1.2-rows-per-bucket rule picks.  Default 1 (1.2-2.4 rows
-// per bucket, ~6 of a record's 12 key slots used): half the directory bytes to build and to stream through the L2 for the
-// same count-kernel time (r2f: build -0.75 ms on 90 M rows, count / pass 1 unchanged)
-static int jdir_extra_shift() {
-  static int v = [] { const char *e = getenv("PBGPU_JDIR_SHIFT"); return e ? atoi(e) : 1; }();
-  return v < 0 ? 0 : v;
+// PBGPU_JDIR_SHIFT=k: k more bits per directory bucket than the 0.6-1.2-rows-per-bucket rule picks.  Default: 1 when the
+// directory would otherwise exceed the L2 by far (1.2-2.4 rows per bucket, ~6 of a record's 12 key slots used: half the
+// directory bytes to build and to stream through the L2 for the same count-kernel time; r2f: build -0.75 ms on 90 M rows),
+// 0 for directories that stay L2-resident (r2h: config 2's count kernels lose 30 % with the fuller records: more of them
+// are crowded and take the search path).
+static int jdir_extra_shift(unsigned long long n_buckets) {
+  static int v = [] { const char *e = getenv("PBGPU_JDIR_SHIFT"); return e ? atoi(e) : -1; }();
+  if (v >= 0) return v;
+  return n_buckets * sizeof(JRec) > ((unsigned long long)192 << 20) ? 1 : 0;
 }
 constexpr int kCrowdedLinearMax = 64;  // crowded records of an unsorted-ends index are counted linearly up to this many ends
 
@@ -487,7 +490,7 @@ static size_t slab1_bytes(int32_t n_contigs, int64_t m) {
 static int jdir_shift_for(unsigned long long total_span, int64_t m) {
   int shift = 0;
   while (shift < kJMaxShift && (total_span >> shift) > ((unsigned long long)m * 5ull) / 3ull) ++shift;
-  shift += jdir_extra_shift();
+  shift += jdir_extra_shift(total_span >> shift);
   return shift > kJMaxShift ? kJMaxShift : shift;
 }
 static int alloc_slab2(pbgpu_index *ix, unsigned long long total_span, int64_t m, int32_t n_contigs, cudaStream_t s) {

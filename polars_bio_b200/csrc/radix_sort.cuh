@@ -146,6 +146,14 @@ constexpr int kRsMaxPasses = 8;
 constexpr int kLbWindow = 8;
 // resident blocks per SM the single-kernel passes are compiled for (register cap = 65536 / (512 * OCC)): both variants
 // are built, PBGPU_RS_OCC=2|3 picks at run time (A/B; default below)
+// PBGPU_MATCH=hw at compile time (-DPBGPU_MATCH_HW) keeps the MATCH instruction (A/B builds)
+__device__ __forceinline__ unsigned rs_match(unsigned d) {
+#ifdef PBGPU_MATCH_HW
+  return __match_any_sync(0xffffffffu, d);
+#else
+  return match9(d);
+#endif
+}
 static inline int rs_occ() {
   static int v = [] { const char *e = getenv("PBGPU_RS_OCC"); return (e && e[0] == '2') ? 2 : 3; }();
   return v;
@@ -227,7 +235,7 @@ __global__ void __launch_bounds__(kRsThreads, OCC) rs_onesweep_kernel(const uint
     for (int r = 0; r < kRsItems; ++r) {
       const bool ok = wofs + r * 32 + lane < tile_n;
       const unsigned d = ok ? (unsigned)((k[r] >> shift) & 0xff) : 0x100u;  // 0x100: out-of-range lanes group together
-      peers[r] = __match_any_sync(0xffffffffu, d);
+      peers[r] = rs_match(d);
     }
 #pragma unroll
     for (int r = 0; r < kRsItems; ++r) {
