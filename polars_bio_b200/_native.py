@@ -13,7 +13,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpbgpu.so")
+LIB_PATH = os.environ.get("PBGPU_LIB") or os.path.join(_HERE, "libpbgpu.so")  # PBGPU_LIB: an experimental build (A/B of compile-time parameters)
 
 _i32p = ctypes.c_void_p  # device pointers travel as integers
 _lib = None

@@ -596,7 +596,7 @@ int encode_keys(const Table &t, const char *side, ContigDict &dict, int32_t *cod
       }
       return false;
     };
-    auto lookup = [&](std::string_view sv) -> int32_t {
+    auto lookup_slow = [&](std::string_view sv) -> int32_t {
       if (have_prev && sv.size() == prev.size() && memcmp(sv.data(), prev.data(), sv.size()) == 0) return prev_code;
       int32_t c;
       auto it = local.find(sv);
@@ -604,6 +604,33 @@ int encode_keys(const Table &t, const char *side, ContigDict &dict, int32_t *cod
       else { c = dict.intern(sv); local.emplace(sv, c); }
       prev = sv; prev_code = c; have_prev = true;
       return c;
+    };
+    // Short names (<= 7 bytes: "chr1" .. "chrUn", "1" .. "MT") in arbitrary order -- rows of all contigs mixed, the shape
+    // of BASELINE config 3 -- would pay a std::hash + compare per row (~40 ns); instead the string is read as ONE 64-bit
+    // word (length in the top byte) and looked up in a 128-entry direct-mapped table: ~3 ns per row.  The 8-byte read must
+    // stay inside the data buffer, so the last few bytes of it take the ordinary path.
+    struct SmallEnt { uint64_t key; int32_t code; };
+    SmallEnt small[128];
+    for (auto &e : small) { e.key = ~0ull; e.code = -1; }
+    const char *data_end = nullptr;
+    if (!is_dict && (sk == StrKind::Utf8 || sk == StrKind::LargeUtf8) && ac->buffers[2]) {
+      const int64_t last = ac->offset + ac->length;  // offsets[last] = end of the data this array can reference
+      data_end = (const char *)ac->buffers[2] +
+                 (sk == StrKind::Utf8 ? (int64_t)((const int32_t *)ac->buffers[1])[last] : ((const int64_t *)ac->buffers[1])[last]);
+    }
+    auto lookup = [&](std::string_view sv) -> int32_t {
+      const size_t L = sv.size();
+      if (L <= 7 && data_end && sv.data() + 8 <= data_end) {
+        uint64_t w;
+        memcpy(&w, sv.data(), 8);
+        const uint64_t key = (w & ((1ull << (8 * L)) - 1ull)) | ((uint64_t)L << 56);
+        SmallEnt &e = small[(key * 0x9E3779B97F4A7C15ull) >> 57];
+        if (e.key == key) return e.code;
+        const int32_t c = lookup_slow(sv);
+        e.key = key; e.code = c;
+        return c;
+      }
+      return lookup_slow(sv);
     };
     const bool run_ok = !is_dict && !vc && fast_s && fast_e && (sk == StrKind::Utf8 || sk == StrKind::LargeUtf8);
     constexpr int64_t kRun = 1024;

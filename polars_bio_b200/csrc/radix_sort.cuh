@@ -143,7 +143,10 @@ __global__ void __launch_bounds__(kRsThreads) rs_scatter_kernel(const uint64_t *
 // HBM traffic per pass: 16 B read + 16 B write per element (+ 8 B once for the histogram).
 constexpr uint32_t kLbAgg = 1u << 30, kLbPre = 2u << 30, kLbMask = (1u << 30) - 1u;
 constexpr int kRsMaxPasses = 8;
-constexpr int kLbWindow = 8;
+#ifndef PBGPU_LB_WINDOW
+#define PBGPU_LB_WINDOW 8
+#endif
+constexpr int kLbWindow = PBGPU_LB_WINDOW;  // predecessor status words a look-back step keeps in flight per digit (r2r A/B on config 3: 8 -> build 7.07 ms, 16 -> 7.29, 32 -> 8.03: the walk is not what bounds a pass)
 // resident blocks per SM the single-kernel passes are compiled for (register cap = 65536 / (512 * OCC)): both variants
 // are built, PBGPU_RS_OCC=2|3 picks at run time (A/B; default below)
 // PBGPU_MATCH=hw at compile time (-DPBGPU_MATCH_HW) keeps the MATCH instruction (A/B builds)

@@ -24,7 +24,7 @@ bench_dev)
 ab)
   echo "== A/B variants (device-resident bench, no e2e)"
   for v in ${AB_VARIANTS:-PBGPU_X=default}; do
-    n=$(echo "$v" | tr ' =,' '___'); vv=$(echo "$v" | tr ',' ' ')
+    n=$(echo "$v" | tr ' =,/' '____'); vv=$(echo "$v" | tr ',' ' ')
     timeout 600 env $vv python bench.py --steps 8 --warmup 3 --skip-e2e --no-cpu-baseline --skip-secondary --skip-parity > $O/${TAG}_ab_${n}.json 2> $O/${TAG}_ab_${n}.err
     python - "$O/${TAG}_ab_${n}.json" "$v" <<'PYEOF'
 import json, sys
