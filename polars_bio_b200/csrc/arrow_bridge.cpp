@@ -42,6 +42,13 @@ int widen_codes_u8(const uint8_t *d_in, int64_t n, int32_t n_contigs, int32_t *d
 int gather_i32_u8(const int32_t *d_src, const uint32_t *d_rows, int64_t n, uint8_t *d_out, void *stream);
 int count_overlaps_u32(const pbgpu_index *ix, const int32_t *c, const int32_t *s, const int32_t *e, int64_t n, int filter_op,
                        uint32_t *d_counts, void *stream);  // pbgpu.cu (internal)
+int gather_fixed(const void *d_src, int width, const uint32_t *d_rows, int64_t n, void *d_out, void *stream);
+int gather_valid_bits(const uint8_t *d_valid, const uint32_t *d_rows, int64_t n, uint32_t *d_bits, unsigned long long *d_null_count, void *stream);
+int gather_str_plan(const long long *d_off, const uint8_t *d_valid, const uint32_t *d_rows, int64_t n, unsigned long long *d_pos,
+                    unsigned long long *d_total, void *stream);
+int gather_str_bytes(const long long *d_off, const char *d_chars, const uint32_t *d_rows, int64_t n, const unsigned long long *d_pos,
+                     const unsigned long long *d_total, void *d_out_off, int large, char *d_out_chars, void *stream);
+int rebase_offsets(const void *d_in, int large, int64_t len, long long base, long long *d_out, void *stream);
 int dev_alloc(void **p, size_t bytes, cudaStream_t s);  // stream-ordered device blocks through pbgpu.cu's block cache
 void dev_free(void *p, cudaStream_t s);
 }  // namespace pbgpu
@@ -1242,10 +1249,30 @@ struct Sink {
   uint32_t *d_p = nullptr, *d_b = nullptr;  // the device slot
   int32_t *d_k[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   void *h_stage[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // pinned landing (only when direct D2H is off)
+  // Payload columns gathered ON THE DEVICE (the reference materialises the joined rows itself,
+  // operation.rs:272-303): fixed-width values of 1..16 bytes and utf8 / large_utf8 / binary, nulls included.  The column
+  // is uploaded once per call; every chunk of pairs gathers from it and brings down ready-made Arrow buffers.  Other
+  // types (bool, string views, dictionaries, nested) stay on the host gather path.
+  struct DevCol {
+    int table = 0, col = 0;    // 0 = left, 1 = right
+    int width = 0;             // > 0: fixed width
+    bool is_str = false, large = false;
+    const void *d_data = nullptr;       // values / characters
+    const uint8_t *d_valid = nullptr;   // one byte per source row, NULL = no nulls
+    const long long *d_off = nullptr;   // strings: rows + 1 offsets into d_data
+    void *d_out = nullptr;              // per chunk: cap values, or cap + 1 offsets
+    uint32_t *d_bits = nullptr;
+    unsigned long long *d_pos = nullptr, *d_meta = nullptr;  // strings: scanned lengths; [0] total bytes, [1] null count
+    void *h_stage[3] = {nullptr, nullptr, nullptr};          // pinned landing buffers (bits / values or offsets / characters),
+    size_t h_cap[3] = {0, 0, 0};                             // used when the final buffer is not page-locked; reused by every chunk
+  };
+  std::vector<DevCol> dcols;
+  struct ColOut { const void *data = nullptr, *bits = nullptr, *offs = nullptr; };
   struct Chunk {
     bool valid = false;
     int64_t base = 0, rows = 0;
     std::shared_ptr<HostBufs> pins;
+    std::vector<ColOut> cols;  // one per dcols entry
     const uint32_t *lrow = nullptr, *rrow = nullptr;
     const int32_t *k[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     struct Staged { void *fin; const void *landing; size_t bytes; };
@@ -1268,6 +1295,7 @@ struct OutStream {
   // overlap, materialised: key columns of the result rows gathered on the device (NULL = not available)
   const uint8_t *k_code8 = nullptr;  // the same column as k_code when it travelled as bytes
   const int32_t *k_code = nullptr, *k_ls = nullptr, *k_le = nullptr, *k_rs = nullptr, *k_re = nullptr;
+  std::vector<Sink::ColOut> dev_cols;     // payload columns of the resident chunk that were gathered on the device
   std::vector<std::string> contig_names;  // dictionary: code -> contig string
   int64_t cursor = 0;
   int64_t chunk_base = 0, chunk_rows = 0;  // result rows [chunk_base, chunk_base + chunk_rows) are behind lrow / rrow / k_*
@@ -1278,6 +1306,27 @@ struct OutStream {
   uint32_t batch_rows = 1 << 20;
   std::string last_error;
 };
+
+// a batch-sized window [lo, lo + n) of a device-gathered payload column of the resident chunk: zero-copy, the chunk's
+// buffers (validity bits, values or offsets + characters) with the Arrow `offset` field doing the slicing
+struct DevColPriv { std::shared_ptr<void> keep; const void *bufs[3]; };
+void release_dev_col(ArrowArray *a) {
+  if (!a || !a->release) return;
+  delete (DevColPriv *)a->private_data;
+  a->release = nullptr;
+}
+ArrowArray dev_col_view(const std::shared_ptr<void> &keep, const Sink::DevCol &dc, const Sink::ColOut &co, int64_t lo, int64_t n) {
+  DevColPriv *p = new DevColPriv{keep, {co.bits, dc.is_str ? co.offs : co.data, dc.is_str ? co.data : nullptr}};
+  ArrowArray v{};
+  v.length = n;
+  v.offset = lo;
+  v.null_count = co.bits ? -1 : 0;
+  v.n_buffers = dc.is_str ? 3 : 2;
+  v.buffers = p->bufs;
+  v.release = release_dev_col;
+  v.private_data = p;
+  return v;
+}
 
 // enqueue pass 2 + key gathers + D2H of the next chunk on the call's stream (no sync)
 int sink_enqueue(OutStream *st) {
@@ -1332,6 +1381,56 @@ int sink_enqueue(OutStream *st) {
   }
   if (sk.need_l) BR_TRY(fetch(sk.d_p, (const void **)&ch.lrow, 4));
   if (sk.need_r) BR_TRY(fetch(sk.d_b, (const void **)&ch.rrow, 4));
+  // payload columns that live on the device: gather by the chunk's row ids, bring down ready-made Arrow buffers
+  auto fetch_bytes = [&](Sink::DevCol &dc, int which, const void *d_src, size_t bytes, const void **dst) -> int {
+    bool dma = false;
+    void *fin = hmalloc_dma(bytes ? bytes : 1, &dma);
+    if (!fin) return set_error(PBGPU_ENOMEM, "host allocation failed");
+    ch.pins->v.push_back(fin);
+    *dst = fin;
+    if (!bytes) return PBGPU_OK;
+    void *h = fin;
+    if (!dma) {  // small buffers are not page-locked: land in the column's pinned slot (free again once sink_advance has copied it out)
+      if (dc.h_cap[which] < bytes) {
+        const size_t cap = std::max(bytes, 2 * dc.h_cap[which]);
+        dc.h_stage[which] = cs.stage.get<char>(cap);
+        dc.h_cap[which] = dc.h_stage[which] ? cap : 0;
+      }
+      h = dc.h_stage[which];
+      if (!h) return set_error(PBGPU_ENOMEM, "pinned allocation failed");
+      ch.staged.push_back({fin, h, bytes});
+    }
+    BR_CUDA(cudaMemcpyAsync(h, d_src, bytes, cudaMemcpyDeviceToHost, s));
+    return PBGPU_OK;
+  };
+  ch.cols.assign(sk.dcols.size(), Sink::ColOut());
+  for (size_t k = 0; k < sk.dcols.size(); ++k) {
+    Sink::DevCol &dc = sk.dcols[k];
+    const uint32_t *d_rows = dc.table == 0 ? sk.d_p : sk.d_b;
+    if (dc.d_valid) {
+      BR_TRY(pbgpu::gather_valid_bits(dc.d_valid, d_rows, rows, dc.d_bits, nullptr, s));
+      BR_TRY(fetch_bytes(dc, 0, dc.d_bits, 4 * (size_t)((rows + 31) / 32), &ch.cols[k].bits));
+    }
+    if (!dc.is_str) {
+      BR_TRY(pbgpu::gather_fixed(dc.d_data, dc.width, d_rows, rows, dc.d_out, s));
+      BR_TRY(fetch_bytes(dc, 1, dc.d_out, (size_t)dc.width * (size_t)rows, &ch.cols[k].data));
+      continue;
+    }
+    BR_TRY(pbgpu::gather_str_plan(dc.d_off, dc.d_valid, d_rows, rows, dc.d_pos, dc.d_meta, s));
+    unsigned long long total = 0;  // bytes of this chunk's strings: sizes the host and device buffers (one sync per string column)
+    BR_CUDA(cudaMemcpyAsync(&total, dc.d_meta, 8, cudaMemcpyDeviceToHost, s));
+    BR_CUDA(cudaStreamSynchronize(s));
+    if (!dc.large && total > (unsigned long long)INT32_MAX)
+      return set_error(PBGPU_ERANGE, "utf8 column would exceed 2 GiB in one chunk of the result; lower sink_pairs or use large_utf8");
+    void *d_chars_v = nullptr;
+    BR_TRY(pbgpu::dev_alloc(&d_chars_v, (size_t)total + 16, s));
+    char *d_chars = (char *)d_chars_v;
+    int rc_s = pbgpu::gather_str_bytes(dc.d_off, (const char *)dc.d_data, d_rows, rows, dc.d_pos, dc.d_meta, dc.d_out, dc.large ? 1 : 0, d_chars, s);
+    if (rc_s == PBGPU_OK) rc_s = fetch_bytes(dc, 1, dc.d_out, (size_t)(dc.large ? 8 : 4) * (size_t)(rows + 1), &ch.cols[k].offs);
+    if (rc_s == PBGPU_OK) rc_s = fetch_bytes(dc, 2, d_chars, (size_t)total, &ch.cols[k].data);
+    pbgpu::dev_free(d_chars_v, s);  // stream-ordered: behind the copy that reads it
+    if (rc_s != PBGPU_OK) return rc_s;
+  }
   ch.base = (int64_t)sk.offs[lo];
   ch.rows = rows;
   ch.valid = true;
@@ -1357,6 +1456,7 @@ int sink_advance(OutStream *st) {
   st->k_code = sk.code8 ? nullptr : ch.k[0];
   st->k_code8 = sk.code8 ? (const uint8_t *)ch.k[0] : nullptr;
   st->k_ls = ch.k[1]; st->k_le = ch.k[2]; st->k_rs = ch.k[3]; st->k_re = ch.k[4];
+  st->dev_cols = ch.cols;
   st->chunk_base = ch.base;
   st->chunk_rows = ch.rows;
   ch.valid = false;
@@ -1446,18 +1546,25 @@ int out_get_next(ArrowArrayStream *s, ArrowArray *out) {
     if (rc == PBGPU_OK && want_distance(o)) { ArrowArray d{}; rc = nullable_i64_column(st->extra + lo, n, &d); if (rc == PBGPU_OK) push(std::move(d)); }
   } else if (o.range_op == PBGPU_OP_OVERLAP && (st->k_code || st->k_code8)) {
     // key columns come from the device-gathered int32 arrays; only true payload columns are gathered on the host
-    struct Slot { int kind; const Table *t; int col; const int32_t *pos; const uint32_t *rows; };  // 0 contig, 1 position, 2 payload
+    struct Slot { int kind; const Table *t; int col; const int32_t *pos; const uint32_t *rows; int dev; };  // 0 contig, 1 position, 2 payload (host gather), 3 payload (device-gathered buffers)
     std::vector<Slot> slots;
-    auto plan_table = [&](const Table &t, const uint32_t *rows, const int32_t *ks, const int32_t *ke) {
+    auto plan_table = [&](const Table &t, int which, const uint32_t *rows, const int32_t *ks, const int32_t *ke) {
       for (int c = 0; c < (int)t.n_cols(); ++c) {
-        if (c == t.key[0]) slots.push_back({0, &t, c, nullptr, nullptr});
-        else if (c == t.key[1]) slots.push_back({1, &t, c, ks + lo, nullptr});
-        else if (c == t.key[2]) slots.push_back({1, &t, c, ke + lo, nullptr});
-        else { slots.push_back({2, &t, c, nullptr, rows + lo}); jobs.push_back(GatherJob{&t, c, rows + lo}); }
+        if (c == t.key[0]) slots.push_back({0, &t, c, nullptr, nullptr, -1});
+        else if (c == t.key[1]) slots.push_back({1, &t, c, ks + lo, nullptr, -1});
+        else if (c == t.key[2]) slots.push_back({1, &t, c, ke + lo, nullptr, -1});
+        else {
+          int dev = -1;
+          if (st->sink)
+            for (size_t k = 0; k < st->sink->dcols.size() && k < st->dev_cols.size(); ++k)
+              if (st->sink->dcols[k].table == which && st->sink->dcols[k].col == c) dev = (int)k;
+          if (dev >= 0) slots.push_back({3, &t, c, nullptr, nullptr, dev});
+          else { slots.push_back({2, &t, c, nullptr, rows + lo, -1}); jobs.push_back(GatherJob{&t, c, rows + lo}); }
+        }
       }
     };
-    plan_table(*st->left, st->lrow, st->k_ls, st->k_le);
-    if (o.output_mode == PBGPU_OUT_JOIN) plan_table(*st->right, st->rrow, st->k_rs, st->k_re);
+    plan_table(*st->left, 0, st->lrow, st->k_ls, st->k_le);
+    if (o.output_mode == PBGPU_OUT_JOIN) plan_table(*st->right, 1, st->rrow, st->k_rs, st->k_re);
     std::vector<ArrowArray> payload;
     if (!jobs.empty()) rc = gather_columns(jobs, n, &payload);
     StrBufs sb_small, sb_large;
@@ -1466,6 +1573,7 @@ int out_get_next(ArrowArrayStream *s, ArrowArray *out) {
       const Slot &sl = slots[k];
       const ArrowSchema *f = sl.t->schema.children[sl.col];
       if (sl.kind == 2) { push(std::move(payload[next_payload++])); continue; }
+      if (sl.kind == 3) { push(dev_col_view(keep, st->sink->dcols[(size_t)sl.dev], st->dev_cols[(size_t)sl.dev], lo, n)); continue; }
       if (sl.kind == 1) { ArrowArray a{}; rc = pos_column(keep, sl.pos, n, f->format, &a); if (rc == PBGPU_OK) push(std::move(a)); continue; }
       bool ok;
       const bool large = out_format(f, &ok)[0] == 'U';
@@ -1519,6 +1627,100 @@ void out_release(ArrowArrayStream *s) {
   if (!s || !s->release) return;
   delete (OutStream *)s->private_data;
   s->release = nullptr;
+}
+
+// Payload columns of one input table to the device (Sink::DevCol): fixed-width values and utf8 / binary columns, each as
+// ONE contiguous device column whatever the batch structure of the input, plus a byte-per-row validity column when any
+// batch has nulls.  PBGPU_DEV_GATHER=0 keeps every payload column on the host gather path.
+int upload_payload(const Table &t, int which, Sink &sk, CallState &cs) {
+  static const bool enabled = [] { const char *e = getenv("PBGPU_DEV_GATHER"); return !(e && e[0] == '0'); }();
+  if (!enabled || t.rows == 0) return PBGPU_OK;
+  cudaStream_t s = cs.s;
+  const int64_t rows = t.rows;
+  for (int c = 0; c < (int)t.n_cols(); ++c) {
+    if (c == t.key[0] || c == t.key[1] || c == t.key[2]) continue;
+    const ArrowSchema *f = t.schema.children[c];
+    if (f->dictionary) continue;
+    const int w = fixed_width(f->format);
+    const StrKind k = str_kind(f->format);
+    const bool fixed = (w == 1 || w == 2 || w == 4 || w == 8 || w == 16);
+    const bool str = k == StrKind::Utf8 || k == StrKind::LargeUtf8;
+    if (!fixed && !str) continue;
+    Sink::DevCol dc;
+    dc.table = which; dc.col = c; dc.width = fixed ? w : 0; dc.is_str = str; dc.large = k == StrKind::LargeUtf8;
+    bool any_null = false;
+    for (const ArrowArray &ba : t.batches) { const ArrowArray *a = ba.children[c]; if (a->null_count != 0 && a->buffers[0]) any_null = true; }
+    if (any_null) {
+      uint8_t *hv = cs.stage_wc.get<uint8_t>((size_t)rows);
+      uint8_t *dv = cs.dev.get<uint8_t>((size_t)rows);
+      if (!hv || !dv) return set_error(PBGPU_ENOMEM, "allocation failed");
+      for (size_t b = 0; b < t.batches.size(); ++b) {
+        const ArrowArray &ba = t.batches[b];
+        const ArrowArray *a = ba.children[c];
+        const uint8_t *bits = (a->null_count != 0) ? (const uint8_t *)a->buffers[0] : nullptr;
+        const int64_t off = a->offset + ba.offset, len = ba.length, g0 = t.start[b];
+        const int64_t nch = (len + kGatherChunk - 1) / kGatherChunk;
+        Pool::get().parallel_for(nch, [&](int64_t ci) {
+          const int64_t lo = ci * kGatherChunk, hi = std::min(len, lo + kGatherChunk);
+          if (!bits) memset(hv + g0 + lo, 1, (size_t)(hi - lo));
+          else for (int64_t i = lo; i < hi; ++i) hv[g0 + i] = bit_get(bits, off + i) ? 1 : 0;
+        });
+      }
+      BR_CUDA(cudaMemcpyAsync(dv, hv, (size_t)rows, cudaMemcpyHostToDevice, s));
+      dc.d_valid = dv;
+      dc.d_bits = cs.dev.get<uint32_t>((size_t)(sk.cap + 31) / 32 + 1);
+      if (!dc.d_bits) return set_error(PBGPU_ENOMEM, "device allocation failed");
+    }
+    if (fixed) {
+      char *dd = cs.dev.get<char>((size_t)rows * w);
+      dc.d_out = cs.dev.get<char>((size_t)sk.cap * w);
+      if (!dd || !dc.d_out) return set_error(PBGPU_ENOMEM, "device allocation failed");
+      for (size_t b = 0; b < t.batches.size(); ++b) {
+        const ArrowArray &ba = t.batches[b];
+        const ArrowArray *a = ba.children[c];
+        const size_t bytes = (size_t)ba.length * w;
+        if (a->buffers[1]) BR_CUDA(cudaMemcpyAsync(dd + (size_t)t.start[b] * w, (const char *)a->buffers[1] + (size_t)(a->offset + ba.offset) * w, bytes, cudaMemcpyHostToDevice, s));
+        else BR_CUDA(cudaMemsetAsync(dd + (size_t)t.start[b] * w, 0, bytes, s));
+      }
+      dc.d_data = dd;
+    } else {
+      const bool large = dc.large;
+      auto off_at = [&](const ArrowArray *a, int64_t i) -> int64_t {
+        return large ? ((const int64_t *)a->buffers[1])[i] : (int64_t)((const int32_t *)a->buffers[1])[i];
+      };
+      int64_t total = 0;
+      std::vector<int64_t> base(t.batches.size());
+      for (size_t b = 0; b < t.batches.size(); ++b) {
+        const ArrowArray &ba = t.batches[b];
+        const ArrowArray *a = ba.children[c];
+        const int64_t o0 = a->offset + ba.offset;
+        base[b] = total;
+        total += off_at(a, o0 + ba.length) - off_at(a, o0);
+      }
+      char *dd = cs.dev.get<char>((size_t)total + 16);
+      long long *doff = cs.dev.get<long long>((size_t)rows + 1);
+      dc.d_out = cs.dev.get<char>((size_t)(sk.cap + 1) * (large ? 8 : 4));
+      dc.d_pos = cs.dev.get<unsigned long long>((size_t)sk.cap + 1);
+      dc.d_meta = cs.dev.get<unsigned long long>(2);
+      if (!dd || !doff || !dc.d_out || !dc.d_pos || !dc.d_meta) return set_error(PBGPU_ENOMEM, "device allocation failed");
+      for (size_t b = 0; b < t.batches.size(); ++b) {
+        const ArrowArray &ba = t.batches[b];
+        const ArrowArray *a = ba.children[c];
+        const int64_t o0 = a->offset + ba.offset, len = ba.length;
+        const size_t ow = large ? 8 : 4;
+        char *d_raw = cs.dev.get<char>((size_t)(len + 1) * ow);
+        if (!d_raw) return set_error(PBGPU_ENOMEM, "device allocation failed");
+        BR_CUDA(cudaMemcpyAsync(d_raw, (const char *)a->buffers[1] + (size_t)o0 * ow, (size_t)(len + 1) * ow, cudaMemcpyHostToDevice, s));
+        BR_TRY(pbgpu::rebase_offsets(d_raw, large ? 1 : 0, len, (long long)base[b], doff + t.start[b], s));
+        const int64_t c0 = off_at(a, o0), c1 = off_at(a, o0 + len);
+        if (c1 > c0) BR_CUDA(cudaMemcpyAsync(dd + base[b], (const char *)a->buffers[2] + c0, (size_t)(c1 - c0), cudaMemcpyHostToDevice, s));
+      }
+      dc.d_data = dd;
+      dc.d_off = doff;
+    }
+    sk.dcols.push_back(dc);
+  }
+  return PBGPU_OK;
 }
 
 // Upload + index the indexed side.  `side`: what to call it in error messages.
@@ -1736,6 +1938,8 @@ int run_iter(Table *L, Table *R, OutStream *os, std::shared_ptr<IndexSide> xs) {
         }
         os->contig_names.resize(dict.map.size());
         for (auto &kv : dict.map) os->contig_names[(size_t)kv.second] = kv.first;
+        BR_TRY(upload_payload(*L, 0, sk, cs));
+        if (join) BR_TRY(upload_payload(*R, 1, sk, cs));
       }
       if (limit && (uint64_t)os->n_out > limit) os->n_out = (int64_t)limit;  // before the first prefetch decision
       BR_TRY(sink_enqueue(os));

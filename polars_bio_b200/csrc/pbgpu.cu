@@ -1346,6 +1346,121 @@ __global__ void __launch_bounds__(256) gather_i32_kernel(const int32_t *__restri
 }
 }  // namespace pbgpu
 
+// ---- payload gather on the device (the reference's output IS the joined rows, operation.rs:272-303) -----
+// Result row j takes column value src[rows[j]] (rows[j] == PBGPU_NO_PARTNER: null).  Fixed-width values of 1..16 bytes,
+// validity as one byte per source row in, one BIT per result row out (Arrow layout, packed by warp ballot), and
+// utf8 / binary columns as (lengths -> exclusive scan -> byte copy).
+namespace pbgpu {
+template <typename T>
+__global__ void __launch_bounds__(256) gather_fixed_kernel(const T *__restrict__ src, const uint32_t *__restrict__ rows, int64_t n, T *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t r = rows[i];
+  T z{};
+  out[i] = r == PBGPU_NO_PARTNER ? z : src[r];
+}
+// bit j of out = row present and (valid == NULL or valid[rows[j]]); out has ceil(n / 32) words, n may end inside a word
+__global__ void __launch_bounds__(256) gather_valid_bits_kernel(const uint8_t *__restrict__ valid, const uint32_t *__restrict__ rows, int64_t n,
+                                                                uint32_t *__restrict__ out, unsigned long long *__restrict__ null_count) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  bool ok = false;
+  if (i < n) {
+    const uint32_t r = rows[i];
+    ok = r != PBGPU_NO_PARTNER && (!valid || valid[r] != 0);
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, ok);
+  if ((threadIdx.x & 31) == 0 && i < n) {
+    out[i >> 5] = m;
+    const int64_t in_word = n - i < 32 ? n - i : 32;
+    const unsigned nulls = (unsigned)in_word - (unsigned)__popc(m);
+    if (nulls && null_count) atomicAdd(null_count, (unsigned long long)nulls);
+  }
+}
+// lengths of the gathered strings (0 for nulls / missing partners), as 64-bit for the scan
+__global__ void __launch_bounds__(256) gather_str_len_kernel(const long long *__restrict__ off, const uint8_t *__restrict__ valid,
+                                                             const uint32_t *__restrict__ rows, int64_t n, unsigned long long *__restrict__ len) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t r = rows[i];
+  len[i] = (r == PBGPU_NO_PARTNER || (valid && !valid[r])) ? 0ull : (unsigned long long)(off[r + 1] - off[r]);
+}
+// one warp per result row: copies its bytes; OffT = the output offset type (int32 utf8 / int64 large_utf8); also writes the
+// Arrow offsets (n + 1 entries) from the scanned lengths
+template <typename OffT>
+__global__ void __launch_bounds__(256) gather_str_bytes_kernel(const long long *__restrict__ off, const char *__restrict__ chars,
+                                                               const uint32_t *__restrict__ rows, int64_t n,
+                                                               const unsigned long long *__restrict__ out_pos /*exclusive scan of len, n entries*/,
+                                                               const unsigned long long *__restrict__ total, OffT *__restrict__ out_off,
+                                                               char *__restrict__ out_chars) {
+  const int64_t w = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w > n) return;
+  if (w == n) { if (lane == 0) out_off[n] = (OffT)*total; return; }
+  const unsigned long long p = out_pos[w];
+  if (lane == 0) out_off[w] = (OffT)p;
+  const uint32_t r = rows[w];
+  if (r == PBGPU_NO_PARTNER) return;
+  const long long a = off[r], b = off[r + 1];
+  const unsigned long long next = w + 1 < n ? out_pos[w + 1] : *total;
+  const long long L = (long long)(next - p);  // 0 for nulls even when the source slot holds bytes
+  for (long long k = lane; k < L && a + k < b; k += 32) out_chars[p + k] = chars[a + k];
+}
+// per-batch Arrow offsets (int32 or int64, first entry anywhere) -> one global int64 offset column
+template <typename OffT>
+__global__ void __launch_bounds__(256) rebase_offsets_kernel(const OffT *__restrict__ in /*len + 1 entries*/, int64_t len, long long base,
+                                                             long long *__restrict__ out /*written at [0, len] */) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i <= len) out[i] = (long long)in[i] - (long long)in[0] + base;
+}
+
+int gather_fixed(const void *d_src, int width, const uint32_t *d_rows, int64_t n, void *d_out, void *stream) {
+  if (n <= 0) return PBGPU_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)cdiv(n, 256);
+  switch (width) {
+    case 1: PB_LAUNCH(gather_fixed_kernel<uint8_t>, grid, 256, 0, s, (const uint8_t *)d_src, d_rows, n, (uint8_t *)d_out); break;
+    case 2: PB_LAUNCH(gather_fixed_kernel<uint16_t>, grid, 256, 0, s, (const uint16_t *)d_src, d_rows, n, (uint16_t *)d_out); break;
+    case 4: PB_LAUNCH(gather_fixed_kernel<uint32_t>, grid, 256, 0, s, (const uint32_t *)d_src, d_rows, n, (uint32_t *)d_out); break;
+    case 8: PB_LAUNCH(gather_fixed_kernel<uint2>, grid, 256, 0, s, (const uint2 *)d_src, d_rows, n, (uint2 *)d_out); break;
+    case 16: PB_LAUNCH(gather_fixed_kernel<uint4>, grid, 256, 0, s, (const uint4 *)d_src, d_rows, n, (uint4 *)d_out); break;
+    default: return set_error(PBGPU_EINVAL, "gather_fixed: unsupported width %d", width);
+  }
+  PB_CHECK_LAUNCH();
+  return PBGPU_OK;
+}
+int gather_valid_bits(const uint8_t *d_valid, const uint32_t *d_rows, int64_t n, uint32_t *d_bits, unsigned long long *d_null_count, void *stream) {
+  if (n <= 0) return PBGPU_OK;
+  PB_LAUNCH(gather_valid_bits_kernel, (unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream, d_valid, d_rows, n, d_bits, d_null_count);
+  PB_CHECK_LAUNCH();
+  return PBGPU_OK;
+}
+// lengths + exclusive scan: d_pos[n] (scratch, 8 bytes per row) and *d_total = bytes of the gathered column
+int gather_str_plan(const long long *d_off, const uint8_t *d_valid, const uint32_t *d_rows, int64_t n, unsigned long long *d_pos,
+                    unsigned long long *d_total, void *stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n <= 0) { PB_CUDA(cudaMemsetAsync(d_total, 0, 8, s)); return PBGPU_OK; }
+  PB_LAUNCH(gather_str_len_kernel, (unsigned)cdiv(n, 256), 256, 0, s, d_off, d_valid, d_rows, n, d_pos);
+  PB_CHECK_LAUNCH();
+  return device_scan<SumU64, false>(d_pos, d_pos, n, d_total, s);
+}
+int gather_str_bytes(const long long *d_off, const char *d_chars, const uint32_t *d_rows, int64_t n, const unsigned long long *d_pos,
+                     const unsigned long long *d_total, void *d_out_off, int large, char *d_out_chars, void *stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)cdiv((n + 1) * 32, 256);
+  if (large) PB_LAUNCH(gather_str_bytes_kernel<long long>, grid, 256, 0, s, d_off, d_chars, d_rows, n, d_pos, d_total, (long long *)d_out_off, d_out_chars);
+  else PB_LAUNCH(gather_str_bytes_kernel<int>, grid, 256, 0, s, d_off, d_chars, d_rows, n, d_pos, d_total, (int *)d_out_off, d_out_chars);
+  PB_CHECK_LAUNCH();
+  return PBGPU_OK;
+}
+int rebase_offsets(const void *d_in, int large, int64_t len, long long base, long long *d_out, void *stream) {
+  const unsigned grid = (unsigned)cdiv(len + 1, 256);
+  if (large) PB_LAUNCH(rebase_offsets_kernel<long long>, grid, 256, 0, (cudaStream_t)stream, (const long long *)d_in, len, base, d_out);
+  else PB_LAUNCH(rebase_offsets_kernel<int>, grid, 256, 0, (cudaStream_t)stream, (const int *)d_in, len, base, d_out);
+  PB_CHECK_LAUNCH();
+  return PBGPU_OK;
+}
+}  // namespace pbgpu
+
 extern "C" int pbgpu_gather_i32(const int32_t *d_src, const uint32_t *d_rows, int64_t n, int32_t *d_out, void *stream) {
   if (n < 0) return set_error(PBGPU_EINVAL, "negative n");
   if (n == 0) return PBGPU_OK;

@@ -11,6 +11,8 @@ pytest_scale)
   echo "== pytest scale"; timeout 900 python -m pytest tests/test_gpu_scale.py -m gpu -x -q > $O/${TAG}_pytest_scale.log 2>&1; echo rc=$?; tail -12 $O/${TAG}_pytest_scale.log;;
 ids)
   echo "== ids check"; timeout 600 python tests/tools/ids_check.py > $O/${TAG}_ids_check.log 2>&1; echo rc=$?; tail -6 $O/${TAG}_ids_check.log; PBGPU_BIN=1 timeout 600 python tests/tools/ids_check.py > $O/${TAG}_ids_check_bins.log 2>&1; echo rc=$?; tail -3 $O/${TAG}_ids_check_bins.log;;
+payload)
+  echo "== pytest payload"; timeout 900 python -m pytest tests/test_gpu_payload.py tests/test_gpu_api.py -m gpu -x -q > $O/${TAG}_pytest_payload.log 2>&1; echo rc=$?; tail -25 $O/${TAG}_pytest_payload.log;;
 stream)
   echo "== pytest stream"; timeout 900 python -m pytest tests/test_gpu_stream.py tests/test_gpu_api.py -m gpu -x -q > $O/${TAG}_pytest_stream.log 2>&1; echo rc=$?; tail -25 $O/${TAG}_pytest_stream.log;;
 bins)

@@ -32,3 +32,4 @@ static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
 static inline cudaError_t cudaHostRegister(void*, size_t, unsigned) { return 0; }
 static inline cudaError_t cudaHostUnregister(void*) { return 0; }
 static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return 0; }
+static inline cudaError_t cudaMemsetAsync(void*, int, size_t, cudaStream_t) { return 0; }
