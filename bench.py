@@ -293,6 +293,26 @@ def measure_e2e_api(args, probe, build, expect_pairs, dev):
     torch.cuda.synchronize()
     e2e_sec = (time.perf_counter() - t0) / e2e_steps
     assert rows_c == n and rows_o == expect_pairs, (rows_c, rows_o, expect_pairs)
+    # the same overlap with two payload columns on each side (materialised on the device: fixed-width + utf8)
+    with_payload = None
+    if not args.skip_payload_e2e:
+        reads_p = reads_t.append_column("read_id", pa.array(np.arange(n, dtype=np.int64))).append_column(
+            "mapq", pa.array((probe[1] % 60).astype(np.uint8)))
+        vars_p = vars_t.append_column("variant_id", pa.array(np.arange(m, dtype=np.int64))).append_column(
+            "ref", pc.take(pa.array(["A", "C", "G", "T"]), pa.array((build[1] & 3).astype(np.int32))))
+        reads_p, vars_p = pb.set_coordinate_system(reads_p, True), pb.set_coordinate_system(vars_p, True)
+        tp = []
+        for it in range(3):
+            t_a = time.perf_counter()
+            ro = consume(pb.overlap(reads_p, vars_p, cols1=cols, cols2=cols, output_type="datafusion.DataFrame"))
+            tp.append(time.perf_counter() - t_a)
+            assert ro == expect_pairs
+        sec = float(np.mean(tp[1:]))
+        with_payload = {"ms_per_call": sec * 1e3, "pairs_per_s": expect_pairs / sec,
+                        "columns": "reads: read_id int64, mapq uint8; variants: variant_id int64, ref utf8 -> 10 output columns",
+                        "h2d_bytes": int(12 * m + 9 * n + 9 * n + 8 * m + 5 * m + 1), "d2h_bytes": int((17 + 8 + 1 + 8 + 4 + 1) * expect_pairs),
+                        "note": "pb.overlap only, 2 timed calls after 1 warm-up; payload columns gathered on the device"}
+        del reads_p, vars_p
     # bytes on the bus per step, counted from what the bridge copies: both calls upload the variants (3 x int32) and
     # the reads (contig code as uint8 + 2 x int32); count_overlaps brings back uint32 counts, overlap the key columns of
     # the result rows (contig code uint8 + 4 x int32 positions; no payload columns -> no row ids)
@@ -301,7 +321,8 @@ def measure_e2e_api(args, probe, build, expect_pairs, dev):
             "api": "pb.count_overlaps + pb.overlap on host pyarrow Tables (utf8 contig); output frames materialised per batch "
                    "and consumed as a stream",
             "split_ms": dict(zip(("count_overlaps", "overlap"),
-                                 (float(x) * 1e3 for x in np.mean(np.array(split[-e2e_steps:]), axis=0))))}
+                                 (float(x) * 1e3 for x in np.mean(np.array(split[-e2e_steps:]), axis=0)))),
+            "overlap_with_payload": with_payload}
 
 
 def secondary_config2(dev, steps: int = 10):
@@ -732,6 +753,7 @@ def main():
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-parity", action="store_true")
     ap.add_argument("--skip-secondary", action="store_true")
+    ap.add_argument("--skip-payload-e2e", action="store_true", help="N = 1: skip the e2e overlap variant with payload columns")
     ap.add_argument("--skip-replicate", action="store_true", help="N > 1 parity: skip the replicate-strategy leg")
     args = ap.parse_args()
     if args.impl == "reference":
