@@ -110,6 +110,18 @@ __device__ __forceinline__ unsigned match9(unsigned d) {
   return peers;
 }
 
+// the same over 8-bit values (every lane holds an element)
+__device__ __forceinline__ unsigned match8(unsigned d) {
+  unsigned peers = 0xffffffffu;
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const bool bit = (d >> b) & 1u;
+    const unsigned v = __ballot_sync(0xffffffffu, bit);
+    peers &= bit ? v : ~v;
+  }
+  return peers;
+}
+
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
   unsigned long long v;
   asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");

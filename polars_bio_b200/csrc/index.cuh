@@ -38,6 +38,15 @@ struct ContigMap {   // per contig: position of its slice on the global axis
   uint32_t off;      // global coordinate of lo_m1
   int32_t has;       // contig has indexed rows
 };
+// The same slice in 32-bit form, one 16-byte load per probe (round 2; the 64-bit clamp against lo_m1 / hi_p1 and the three
+// 8-byte loads of a ContigMap were a tenth of the instructions of a count-kernel probe):
+//   G(c, p) = clamp(p, lo, hi) + delta  (mod 2^32),  lo = max(lo_m1, INT32_MIN), hi = min(hi_p1, INT32_MAX) -- an int32
+//   coordinate cannot lie beyond those anyway -- and delta = off - lo_m1 (mod 2^32).
+struct alignas(16) ContigMap32 {
+  int32_t lo, hi;
+  uint32_t delta;
+  int32_t has;
+};
 // Joint rank record of bucket b (W = 2^shift, lo = b*W):
 //   w[0]  rank of the first start >= lo (#{gs < lo}); bit 31 = crowded
 //   normal : w[1] = #{ge < lo} - nS   (nS = number of start keys stored, so that w[1] + #{fields < 0x4000+t} is
@@ -69,6 +78,7 @@ struct pbgpu_index {
   uint32_t n_buckets = 0;
   uint32_t axis_span = 0;  // length of the global axis (fast path)
   pbgpu::ContigMap *cmap = nullptr;
+  pbgpu::ContigMap32 *cmap32 = nullptr;
   uint32_t *gs = nullptr, *ge = nullptr;
   pbgpu::JRec *jdir = nullptr;
   uint2 *er = nullptr;  // (end, row) interleaved in start order: one 8-byte load per emitted pair in pass 2
@@ -90,6 +100,7 @@ namespace pbgpu {
 
 struct IndexView {
   const ContigMap *__restrict__ cmap;
+  const ContigMap32 *__restrict__ cmap32;
   const uint32_t *__restrict__ gs;
   const uint32_t *__restrict__ ge;
   const JRec *__restrict__ jdir;
@@ -108,7 +119,7 @@ struct IndexView {
 };
 
 inline IndexView view_of(const pbgpu_index *ix) {
-  return IndexView{ix->cmap, ix->gs, ix->ge, ix->jdir, ix->er, ix->shift, ix->seg, ix->st, ix->en, ix->pmax, ix->en_sorted, ix->row, ix->en_pos, ix->n_contigs, ix->has_inverted, ix->ge_sorted};
+  return IndexView{ix->cmap, ix->cmap32, ix->gs, ix->ge, ix->jdir, ix->er, ix->shift, ix->seg, ix->st, ix->en, ix->pmax, ix->en_sorted, ix->row, ix->en_pos, ix->n_contigs, ix->has_inverted, ix->ge_sorted};
 }
 
 struct BuildStats {  // device-side reduction target
@@ -117,6 +128,28 @@ struct BuildStats {  // device-side reduction target
   unsigned long long max_len;  // longest (end - start) over the non-inverted rows
   unsigned long long blocks_done;  // prep_kernel: blocks that have added their share (the last one posts to the host)
 };
+
+__device__ __forceinline__ ContigMap32 ld_cmap32(const ContigMap32 *__restrict__ p) {
+  const int4 v = __ldg(reinterpret_cast<const int4 *>(p));
+  return ContigMap32{v.x, v.y, (uint32_t)v.z, v.w};
+}
+// global-axis coordinate of an int32 position on a contig that has indexed rows
+__device__ __forceinline__ uint32_t global_of(const ContigMap32 &cm, int32_t p) {
+  return (uint32_t)min(max(p, cm.lo), cm.hi) + cm.delta;
+}
+__global__ void __launch_bounds__(256) cmap32_kernel(const ContigMap *__restrict__ cmap, int32_t n_contigs, ContigMap32 *__restrict__ out) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= n_contigs) return;
+  const ContigMap m = cmap[c];
+  ContigMap32 r{0, 0, 0u, 0};
+  if (m.has) {
+    r.lo = (int32_t)(m.lo_m1 < (long long)INT32_MIN ? (long long)INT32_MIN : m.lo_m1);
+    r.hi = (int32_t)(m.hi_p1 > (long long)INT32_MAX ? (long long)INT32_MAX : m.hi_p1);
+    r.delta = m.off - (uint32_t)(unsigned long long)m.lo_m1;
+    r.has = 1;
+  }
+  out[c] = r;
+}
 
 // ---- prep: the one pass over the raw input ----------------------------------------------------------------------
 // Per row: sort key  contig << 32 | (start ^ 0x80000000)  (null-keyed rows: contig = n_contigs, so the partition drops

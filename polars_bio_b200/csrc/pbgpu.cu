@@ -498,13 +498,15 @@ static int alloc_slab2(pbgpu_index *ix, unsigned long long total_span, int64_t m
   const uint32_t nb = (uint32_t)(total_span >> shift) + 1;
   const size_t cm_b = align_up(sizeof(ContigMap) * ((size_t)n_contigs + 1)), g_b = align_up(4 * (size_t)m);
   const size_t d_b = align_up(sizeof(JRec) * ((size_t)nb + 1));
-  PB_TRY(dev_alloc(&ix->slab2, cm_b + 2 * g_b + d_b, s));
-  ix->bytes += cm_b + 2 * g_b + d_b;
+  const size_t cm32_b = align_up(sizeof(ContigMap32) * ((size_t)n_contigs + 1));
+  PB_TRY(dev_alloc(&ix->slab2, cm_b + 2 * g_b + d_b + cm32_b, s));
+  ix->bytes += cm_b + 2 * g_b + d_b + cm32_b;
   char *b2 = (char *)ix->slab2;
   ix->cmap = (ContigMap *)b2;
   ix->gs = (uint32_t *)(b2 + cm_b);
   ix->ge = (uint32_t *)(b2 + cm_b + g_b);
   ix->jdir = (JRec *)(b2 + cm_b + 2 * g_b);
+  ix->cmap32 = (ContigMap32 *)(b2 + cm_b + 2 * g_b + d_b);
   ix->shift = shift;
   ix->n_buckets = nb;
   ix->axis_span = (uint32_t)total_span;
@@ -552,6 +554,7 @@ static int build_front_gkey(pbgpu_index *ix, const int32_t *d_c, const int32_t *
   set_slab1(ix, n_contigs, m, &arr_b);
   PB_TRY(alloc_slab2(ix, total_span, m, n_contigs, s));
   PB_CUDA(cudaMemcpyAsync(ix->cmap, d_cmap, sizeof(ContigMap) * (size_t)n_contigs, cudaMemcpyDeviceToDevice, s));
+  PB_LAUNCH(cmap32_kernel, (unsigned)cdiv(n_contigs, 256), 256, 0, s, d_cmap, n_contigs, ix->cmap32);
   bt.lap("slab allocs");
   uint64_t *k1 = nullptr, *k2 = nullptr;
   uint32_t *v1 = nullptr, *v2 = nullptr, *d_totals = nullptr;
@@ -746,6 +749,7 @@ static int index_build_impl(pbgpu_index *ix, const int32_t *d_c, const int32_t *
       PB_TRY(alloc_slab2(ix, total_span, m, n_contigs, s));
       bt.lap("slab 2 alloc");
       PB_CUDA(cudaMemcpyAsync(ix->cmap, fr.d_cmap, sizeof(ContigMap) * (size_t)n_contigs, cudaMemcpyDeviceToDevice, s));
+      PB_LAUNCH(cmap32_kernel, (unsigned)cdiv(n_contigs, 256), 256, 0, s, fr.d_cmap, n_contigs, ix->cmap32);
       PB_LAUNCH(gs_from_keys_kernel, (unsigned)cdiv(m, 256), 256, 0, s, fr.keys, 32, ix->st, m, ix->cmap, ix->gs);
       PB_CHECK_LAUNCH();
     }

@@ -157,6 +157,13 @@ __device__ __forceinline__ unsigned rs_match(unsigned d) {
   return match9(d);
 #endif
 }
+__device__ __forceinline__ unsigned rs_match8(unsigned d) {
+#ifdef PBGPU_MATCH_HW
+  return __match_any_sync(0xffffffffu, d);
+#else
+  return match8(d);
+#endif
+}
 static inline int rs_occ() {
   static int v = [] { const char *e = getenv("PBGPU_RS_OCC"); return (e && e[0] == '2') ? 2 : 3; }();
   return v;
@@ -200,28 +207,27 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v) {
 // stalls, DRAM 35 % busy): the eight MATCH instructions of a thread are issued back to back before the serial counter
 // chain that consumes them, and the values are loaded only after the keys have left for global memory, so keys and
 // values are never live together.
-template <typename V, int OCC>
-__global__ void __launch_bounds__(kRsThreads, OCC) rs_onesweep_kernel(const uint64_t *__restrict__ keys_in,
-                                                                    const V *__restrict__ vals_in,
-                                                                    uint64_t *__restrict__ keys_out,
-                                                                    V *__restrict__ vals_out, int64_t n, int shift,
-                                                                    const uint32_t *__restrict__ digit_totals /*[256] of this pass*/,
-                                                                    uint32_t *status /*[nblk][256], zeroed*/,
-                                                                    uint32_t *ticket /*zeroed*/) {
-  __shared__ uint64_t stage[kRsTile];            // the tile in digit order: keys, then values
-  __shared__ uint16_t wcnt[kRsWarps][kRsRadix];  // per-warp digit counters (<= 256 keys per warp) -> exclusive warp offsets
-  __shared__ uint32_t dbase[kRsRadix];           // global position of local position 0 of digit d: dst = dbase[d] + local
-  __shared__ uint32_t toff[kRsRadix];            // first local position of digit d
-  __shared__ uint32_t wt[kRsThreads / 32 + 1];
-  __shared__ uint32_t tile_s;
+// Shared memory of one pass (declared once in the kernel; the tile body below is instantiated twice)
+struct RsShared {
+  uint64_t stage[kRsTile];            // the tile in digit order: keys, then values
+  uint16_t wcnt[kRsWarps][kRsRadix];  // per-warp digit counters (<= 256 keys per warp) -> exclusive warp offsets
+  uint32_t dbase[kRsRadix];           // global position of local position 0 of digit d: dst = dbase[d] + local
+  uint32_t toff[kRsRadix];            // first local position of digit d
+  uint32_t wt[kRsThreads / 32 + 1];
+  uint32_t tile_s;
+};
+// FULL: the tile holds kRsTile keys -- every bounds test and the "no element" bit of the digit match fold away (all tiles
+// but the last one; the kernel branches once per block; r2x A/B: build 6.78 -> 6.74 ms on config 3).  W: predecessor status
+// words a look-back step keeps in flight per digit (r2r A/B on config 3: 8 -> build 7.07 ms, 16 -> 7.29, 32 -> 8.03; r2x:
+// W = 32 for sorts whose tiles are all resident at once does not help either -- 1 M rows: 0.180 vs 0.186 ms per build --
+// a pass there is bound by the per-block instruction chain, not by the walk).
+template <typename V, bool FULL, int W>
+__device__ __forceinline__ void rs_onesweep_tile(RsShared &sm, const uint64_t *__restrict__ keys_in, const V *__restrict__ vals_in,
+                                                 uint64_t *__restrict__ keys_out, V *__restrict__ vals_out, int shift,
+                                                 const uint32_t *__restrict__ digit_totals, uint32_t *status, uint32_t tile,
+                                                 int64_t tbase, int tile_n_rt) {
+  const int tile_n = FULL ? kRsTile : tile_n_rt;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) tile_s = atomicAdd(ticket, 1u);
-  for (int i = threadIdx.x; i < kRsWarps * kRsRadix / 2; i += kRsThreads) ((uint32_t *)&wcnt[0][0])[i] = 0;
-  __syncthreads();
-  const uint32_t tile = tile_s;
-  const int64_t tbase = (int64_t)tile * kRsTile;
-  const int tile_n = (int)((n - tbase) < (int64_t)kRsTile ? (n - tbase) : (int64_t)kRsTile);
-
   // warp w owns the contiguous slice [tbase + w*256, +256): round r covers 32 consecutive keys
   const int wofs = warp * (32 * kRsItems);
   uint64_t k[kRsItems];
@@ -230,25 +236,28 @@ __global__ void __launch_bounds__(kRsThreads, OCC) rs_onesweep_kernel(const uint
 #pragma unroll
   for (int r = 0; r < kRsItems; ++r) {
     const int li = wofs + r * 32 + lane;
-    k[r] = li < tile_n ? keys_in[tbase + li] : 0;
+    k[r] = (FULL || li < tile_n) ? keys_in[tbase + li] : 0;
   }
   {
     unsigned peers[kRsItems];
 #pragma unroll
     for (int r = 0; r < kRsItems; ++r) {
-      const bool ok = wofs + r * 32 + lane < tile_n;
-      const unsigned d = ok ? (unsigned)((k[r] >> shift) & 0xff) : 0x100u;  // 0x100: out-of-range lanes group together
-      peers[r] = rs_match(d);
+      if (FULL) peers[r] = rs_match8((unsigned)((k[r] >> shift) & 0xff));
+      else {
+        const bool ok = wofs + r * 32 + lane < tile_n;
+        const unsigned d = ok ? (unsigned)((k[r] >> shift) & 0xff) : 0x100u;  // 0x100: out-of-range lanes group together
+        peers[r] = rs_match(d);
+      }
     }
 #pragma unroll
     for (int r = 0; r < kRsItems; ++r) {
-      const bool ok = wofs + r * 32 + lane < tile_n;
+      const bool ok = FULL || wofs + r * 32 + lane < tile_n;
       const unsigned d = (unsigned)((k[r] >> shift) & 0xff);
       const int leader = __ffs(peers[r]) - 1;
       uint32_t old = 0;
       if (ok && lane == leader) {
-        old = wcnt[warp][d];
-        wcnt[warp][d] = (uint16_t)(old + __popc(peers[r]));
+        old = sm.wcnt[warp][d];
+        sm.wcnt[warp][d] = (uint16_t)(old + __popc(peers[r]));
       }
       old = __shfl_sync(0xffffffffu, old, leader);
       q[r] = old + __popc(peers[r] & lt);
@@ -261,25 +270,25 @@ __global__ void __launch_bounds__(kRsThreads, OCC) rs_onesweep_kernel(const uint
   if (threadIdx.x < kRsRadix) {
 #pragma unroll
     for (int w = 0; w < kRsWarps; ++w) {
-      const uint32_t t = wcnt[w][threadIdx.x];
-      wcnt[w][threadIdx.x] = (uint16_t)run;
+      const uint32_t t = sm.wcnt[w][threadIdx.x];
+      sm.wcnt[w][threadIdx.x] = (uint16_t)run;
       run += t;
     }
   }
   // first local position of every digit (exclusive scan of the tile's counts): everything the staging needs.  The global
   // bases (which wait for the predecessors) are only needed by the copy-out, so the keys go to shared memory first.
-  const uint32_t lbase = block_exclusive<SumU32, kRsThreads>(run, wt);
-  if (threadIdx.x < kRsRadix) toff[threadIdx.x] = lbase;
+  const uint32_t lbase = block_exclusive<SumU32, kRsThreads>(run, sm.wt);
+  if (threadIdx.x < kRsRadix) sm.toff[threadIdx.x] = lbase;
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < kRsItems; ++r) {
-    if (wofs + r * 32 + lane < tile_n) {
+    if (FULL || wofs + r * 32 + lane < tile_n) {
       const unsigned d = (unsigned)((k[r] >> shift) & 0xff);
-      q[r] = toff[d] + wcnt[warp][d] + q[r];
-      stage[q[r]] = k[r];
+      q[r] = sm.toff[d] + sm.wcnt[warp][d] + q[r];
+      sm.stage[q[r]] = k[r];
     }
   }
-  const uint32_t gbase = block_exclusive<SumU32, kRsThreads>(threadIdx.x < kRsRadix ? digit_totals[threadIdx.x] : 0u, wt);  // (barriers inside)
+  const uint32_t gbase = block_exclusive<SumU32, kRsThreads>(threadIdx.x < kRsRadix ? digit_totals[threadIdx.x] : 0u, sm.wt);  // (barriers inside)
   if (threadIdx.x < kRsRadix) {
     const int d = threadIdx.x;
     uint32_t *mine = status + (size_t)tile * kRsRadix + d;
@@ -290,52 +299,75 @@ __global__ void __launch_bounds__(kRsThreads, OCC) rs_onesweep_kernel(const uint
       int64_t t = (int64_t)tile - 1;
       bool done = false;
       while (!done) {  // tile 0 always ends the walk with a PREFIX word; positions below it read as an empty PREFIX
-        uint32_t w[kLbWindow];
+        uint32_t w[W];
 #pragma unroll
-        for (int j = 0; j < kLbWindow; ++j) w[j] = (t - j >= 0) ? ld_volatile_u32(status + (size_t)(t - j) * kRsRadix + d) : kLbPre;
+        for (int j = 0; j < W; ++j) w[j] = (t - j >= 0) ? ld_volatile_u32(status + (size_t)(t - j) * kRsRadix + d) : kLbPre;
 #pragma unroll
-        for (int j = 0; j < kLbWindow; ++j) {
+        for (int j = 0; j < W; ++j) {
           if (!done) {
             while ((w[j] >> 30) == 0u) w[j] = ld_volatile_u32(status + (size_t)(t - j) * kRsRadix + d);  // not published yet
             excl += w[j] & kLbMask;
             done = (w[j] & kLbPre) != 0u;
           }
         }
-        t -= kLbWindow;
+        t -= W;
       }
       st_volatile_u32(mine, (excl + run) | kLbPre);
     }
-    dbase[d] = gbase + excl - lbase;  // may wrap below zero: dbase[d] + local position is exact mod 2^32
+    sm.dbase[d] = gbase + excl - lbase;  // may wrap below zero: dbase[d] + local position is exact mod 2^32
   }
   // values: loaded while the look-back is under way (the warps without a digit have nothing else to do)
   V v[kRsItems];
 #pragma unroll
   for (int r = 0; r < kRsItems; ++r) {
     const int li = wofs + r * 32 + lane;
-    v[r] = li < tile_n ? vals_in[tbase + li] : V(0);
+    v[r] = (FULL || li < tile_n) ? vals_in[tbase + li] : V(0);
   }
   __syncthreads();
   uint32_t dst[kRsItems];
 #pragma unroll
   for (int r = 0; r < kRsItems; ++r) {
     const int p = r * kRsThreads + threadIdx.x;
-    if (p < tile_n) {
-      const uint64_t kk = stage[p];
-      dst[r] = dbase[(unsigned)((kk >> shift) & 0xff)] + (uint32_t)p;
+    if (FULL || p < tile_n) {
+      const uint64_t kk = sm.stage[p];
+      dst[r] = sm.dbase[(unsigned)((kk >> shift) & 0xff)] + (uint32_t)p;
       keys_out[dst[r]] = kk;
     }
   }
   __syncthreads();
-  V *vstage = reinterpret_cast<V *>(stage);
+  V *vstage = reinterpret_cast<V *>(sm.stage);
 #pragma unroll
   for (int r = 0; r < kRsItems; ++r)
-    if (wofs + r * 32 + lane < tile_n) vstage[q[r]] = v[r];
+    if (FULL || wofs + r * 32 + lane < tile_n) vstage[q[r]] = v[r];
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < kRsItems; ++r) {
     const int p = r * kRsThreads + threadIdx.x;
-    if (p < tile_n) vals_out[dst[r]] = vstage[p];
+    if (FULL || p < tile_n) vals_out[dst[r]] = vstage[p];
   }
+}
+
+template <typename V, int OCC, int W>
+__global__ void __launch_bounds__(kRsThreads, OCC) rs_onesweep_kernel(const uint64_t *__restrict__ keys_in,
+                                                                    const V *__restrict__ vals_in,
+                                                                    uint64_t *__restrict__ keys_out,
+                                                                    V *__restrict__ vals_out, int64_t n, int shift,
+                                                                    const uint32_t *__restrict__ digit_totals /*[256] of this pass*/,
+                                                                    uint32_t *status /*[nblk][256], zeroed*/,
+                                                                    uint32_t *ticket /*zeroed*/) {
+  __shared__ RsShared sm;
+  if (threadIdx.x == 0) sm.tile_s = atomicAdd(ticket, 1u);
+  for (int i = threadIdx.x; i < kRsWarps * kRsRadix / 2; i += kRsThreads) ((uint32_t *)&sm.wcnt[0][0])[i] = 0;
+  __syncthreads();
+  const uint32_t tile = sm.tile_s;
+  const int64_t tbase = (int64_t)tile * kRsTile;
+  const int tile_n = (int)((n - tbase) < (int64_t)kRsTile ? (n - tbase) : (int64_t)kRsTile);
+#ifdef PBGPU_RS_NOFULL
+  if (false) {}
+#else
+  if (tile_n == kRsTile) rs_onesweep_tile<V, true, W>(sm, keys_in, vals_in, keys_out, vals_out, shift, digit_totals, status, tile, tbase, tile_n);
+#endif
+  else rs_onesweep_tile<V, false, W>(sm, keys_in, vals_in, keys_out, vals_out, shift, digit_totals, status, tile, tbase, tile_n);
 }
 
 // PBGPU_SORT=3k: the three-kernels-per-pass sort (the first implementation; kept for A/B runs and for n >= 2^30)
@@ -380,12 +412,12 @@ inline int radix_sort_digits(uint64_t *keys, V *vals, uint64_t *k2, V *v2, int64
       totals_by_pos = work;
     }
     for (int p = 0; p < npass; ++p) {
+      const uint32_t *tot = totals_by_pos + (size_t)digit_pos[p] * kRsRadix;
+      uint32_t *stat = status + (size_t)p * (size_t)nblk * kRsRadix;
       if (rs_occ() == 3)
-        PB_LAUNCH((rs_onesweep_kernel<V, 3>), (unsigned)nblk, kRsThreads, 0, s, ki, vi, ko, vo, n, 8 * digit_pos[p],
-                  totals_by_pos + (size_t)digit_pos[p] * kRsRadix, status + (size_t)p * (size_t)nblk * kRsRadix, tickets + p);
+        PB_LAUNCH((rs_onesweep_kernel<V, 3, kLbWindow>), (unsigned)nblk, kRsThreads, 0, s, ki, vi, ko, vo, n, 8 * digit_pos[p], tot, stat, tickets + p);
       else
-        PB_LAUNCH((rs_onesweep_kernel<V, 2>), (unsigned)nblk, kRsThreads, 0, s, ki, vi, ko, vo, n, 8 * digit_pos[p],
-                  totals_by_pos + (size_t)digit_pos[p] * kRsRadix, status + (size_t)p * (size_t)nblk * kRsRadix, tickets + p);
+        PB_LAUNCH((rs_onesweep_kernel<V, 2, kLbWindow>), (unsigned)nblk, kRsThreads, 0, s, ki, vi, ko, vo, n, 8 * digit_pos[p], tot, stat, tickets + p);
       uint64_t *t = ki; ki = ko; ko = t;
       V *u = vi; vi = vo; vo = u;
     }

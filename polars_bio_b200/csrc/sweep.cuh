@@ -211,16 +211,14 @@ template <bool STRICT>
 __device__ __forceinline__ uint32_t fast_count(const IndexView &ix, int32_t c, int32_t s, int32_t e, uint32_t &hi_out) {
   hi_out = 0;
   if (c < 0 || c >= ix.n_contigs) return 0;
-  const ContigMap cm = ix.cmap[c];
+  const ContigMap32 cm = ld_cmap32(ix.cmap32 + c);
   if (!cm.has) return 0;
   if (!(STRICT ? (s < e) : (s <= e))) {  // empty / inverted probe: identity not valid, bare predicate instead
     hi_out = kGenericProbe;
     return probe_count<STRICT>(ix, c, s, e);
   }
-  long long ls = s, le = e;  // clamp into the contig's slice: order against every indexed coordinate is preserved
-  ls = ls < cm.lo_m1 ? cm.lo_m1 : (ls > cm.hi_p1 ? cm.hi_p1 : ls);
-  le = le < cm.lo_m1 ? cm.lo_m1 : (le > cm.hi_p1 ? cm.hi_p1 : le);
-  const uint32_t g_s = cm.off + (uint32_t)(ls - cm.lo_m1), g_e = cm.off + (uint32_t)(le - cm.lo_m1);
+  // clamped into the contig's slice: order against every indexed coordinate is preserved
+  const uint32_t g_s = global_of(cm, s), g_e = global_of(cm, e);
   uint32_t hi, re;
   jdir_ranks<STRICT>(ix, g_s, g_e, hi, re);
   hi_out = hi;
@@ -235,11 +233,8 @@ template <bool STRICT>
 __device__ __forceinline__ bool fast_window(const IndexView &ix, int32_t c, int32_t s, int32_t e, int32_t seg_lo,
                                             int32_t &lo, int32_t &hi, int32_t &lend) {
   if (!ix.jdir || !(STRICT ? (s < e) : (s <= e))) return false;
-  const ContigMap cm = ix.cmap[c];
-  long long ls = s, le = e;
-  ls = ls < cm.lo_m1 ? cm.lo_m1 : (ls > cm.hi_p1 ? cm.hi_p1 : ls);
-  le = le < cm.lo_m1 ? cm.lo_m1 : (le > cm.hi_p1 ? cm.hi_p1 : le);
-  const uint32_t g_s = cm.off + (uint32_t)(ls - cm.lo_m1), g_e = cm.off + (uint32_t)(le - cm.lo_m1);
+  const ContigMap32 cm = ld_cmap32(ix.cmap32 + c);
+  const uint32_t g_s = global_of(cm, s), g_e = global_of(cm, e);
   uint32_t uh, ur;
   jdir_ranks<STRICT>(ix, g_s, g_e, uh, ur);
   hi = (int32_t)uh;

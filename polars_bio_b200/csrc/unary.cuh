@@ -125,12 +125,9 @@ __device__ __forceinline__ void run_ranks(const IndexView &ix, int32_t c, int32_
   const int32_t seg_lo = ix.seg[c], seg_hi = ix.seg[c + 1];
   if (seg_lo >= seg_hi) { p = q = seg_lo; return; }
   if (ix.jdir && (STRICT ? (s < e) : (s <= e))) {
-    const ContigMap cm = ix.cmap[c];
-    long long ls = s, le = e;
-    ls = ls < cm.lo_m1 ? cm.lo_m1 : (ls > cm.hi_p1 ? cm.hi_p1 : ls);
-    le = le < cm.lo_m1 ? cm.lo_m1 : (le > cm.hi_p1 ? cm.hi_p1 : le);
+    const ContigMap32 cm = ld_cmap32(ix.cmap32 + c);
     uint32_t hi, re;
-    jdir_ranks<STRICT>(ix, cm.off + (uint32_t)(ls - cm.lo_m1), cm.off + (uint32_t)(le - cm.lo_m1), hi, re);
+    jdir_ranks<STRICT>(ix, global_of(cm, s), global_of(cm, e), hi, re);
     q = (int32_t)hi;
     p = (int32_t)re;
     return;

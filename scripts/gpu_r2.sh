@@ -23,6 +23,17 @@ bench)
   echo "== bench N=1"; timeout 1200 python bench.py --steps 10 --warmup 3 > $O/${TAG}_bench_1gpu.json 2> $O/${TAG}_bench_1gpu.err; echo rc=$?; tail -c 7000 $O/${TAG}_bench_1gpu.json; tail -5 $O/${TAG}_bench_1gpu.err;;
 bench_dev)
   echo "== bench N=1 (device only)"; timeout 600 python bench.py --steps 10 --warmup 3 --skip-e2e --no-cpu-baseline --skip-secondary > $O/${TAG}_bench_dev.json 2> $O/${TAG}_bench_dev.err; echo rc=$?; tail -c 5000 $O/${TAG}_bench_dev.json; tail -5 $O/${TAG}_bench_dev.err;;
+bench_dev2)
+  echo "== bench N=1 (device only, with the config-2 secondary and the parity check)"; timeout 900 python bench.py --steps 10 --warmup 3 --skip-e2e --no-cpu-baseline > $O/${TAG}_bench_dev2.json 2> $O/${TAG}_bench_dev2.err; echo rc=$?; python scripts/bench_brief.py $O/${TAG}_bench_dev2.json; tail -5 $O/${TAG}_bench_dev2.err;;
+ab2)
+  echo "== A/B variants (device-resident bench with the config-2 secondary, no e2e)"
+  for v in ${AB_VARIANTS:-PBGPU_X=default}; do
+    n=$(echo "$v" | tr ' =,/' '____'); vv=$(echo "$v" | tr ',' ' ')
+    timeout 600 env $vv python bench.py --steps 8 --warmup 3 --skip-e2e --no-cpu-baseline --skip-parity > $O/${TAG}_ab_${n}.json 2> $O/${TAG}_ab_${n}.err
+    echo "-- $v"; python scripts/bench_brief.py $O/${TAG}_ab_${n}.json || tail -5 $O/${TAG}_ab_${n}.err
+  done;;
+share8)
+  PB_WORLD=8 PB_RANK=0 timeout 300 python tests/tools/rank_share.py > $O/${TAG}_rank_share_w8.json 2> $O/${TAG}_rank_share_w8.err; echo rc=$?; cat $O/${TAG}_rank_share_w8.json; tail -3 $O/${TAG}_rank_share_w8.err;;
 ab)
   echo "== A/B variants (device-resident bench, no e2e)"
   for v in ${AB_VARIANTS:-PBGPU_X=default}; do
