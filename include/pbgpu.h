@@ -49,7 +49,8 @@ extern "C" {
 enum { PBGPU_FILTER_WEAK = 0, PBGPU_FILTER_STRICT = 1 };             /* option.rs:96-99   */
 enum { PBGPU_OP_OVERLAP = 0, PBGPU_OP_COMPLEMENT = 1, PBGPU_OP_CLUSTER = 2, PBGPU_OP_NEAREST = 3, PBGPU_OP_COVERAGE = 4,
        PBGPU_OP_SUBTRACT = 5, PBGPU_OP_COUNT_OVERLAPS_NAIVE = 6, PBGPU_OP_MERGE = 7 };  /* option.rs:103-112; the unary
-       sweeps (1, 2, 5, 7) exist at the device level only (pbgpu_merge / _cluster / _subtract)                     */
+       sweeps (1, 2, 5, 7) run through pbgpu_range_op like the binary operations (and pbgpu_merge / _cluster /
+       _subtract at the device level)                                                                              */
 enum { PBGPU_OUT_JOIN = 0, PBGPU_OUT_LEFT = 1, PBGPU_OUT_LEFT_DISTINCT = 2 }; /* operation.rs:229-233 */
 
 #define PBGPU_NO_PARTNER 0xFFFFFFFFu
@@ -320,6 +321,8 @@ typedef struct {                 /* mirrors RangeOptions, src/option.rs:8-41    
   uint64_t sink_pairs;           /* overlap: pairs per ring slot of the streaming sink; a larger */
                                  /* result is emitted chunk by chunk from out->get_next with the */
                                  /* device state kept alive.  0 -> $PBGPU_SINK_PAIRS -> 1<<24    */
+  int64_t min_dist;              /* merge / cluster: rows closer than this are joined (>= 0;     */
+                                 /* range_op.py:599-700 -> operation.rs:352-430)                 */
 } PbRangeOptions;
 
 /* `left` / `right` are df1 / df2 exactly as the Python facade passes them to
@@ -328,7 +331,13 @@ typedef struct {                 /* mirrors RangeOptions, src/option.rs:8-41    
  * do_nearest does, operation.rs:143-158).
  * Ownership: the callee MOVES left/right (calls their release exactly once, on the calling
  * thread, before returning -- the GIL rule of src/lib.rs:63-72); the caller owns `out` and
- * calls out->release.  out->get_next may be called from another thread, not concurrently.   */
+ * calls out->release.  out->get_next may be called from another thread, not concurrently.
+ * Unary sweeps (do_merge / do_cluster / do_complement / do_subtract, operation.rs:352-510): `left` is the input table
+ * (cols1); merge and cluster ignore `right` (may be NULL); subtract takes the second table as `right` (cols2); complement
+ * takes the view table as `right` (cols2) or NULL = every contig present spans [0, INT64_MAX).  Output: merge -> contig,
+ * start, end (Int64, named like cols1), n_intervals; cluster -> every input column + cluster, cluster_start, cluster_end
+ * (Int64); complement -> contig, start, end; subtract -> every `left` column with the interval columns holding the
+ * remaining pieces (Int64).  Contigs are ordered by name.                                                              */
 PBGPU_API int pbgpu_range_op(struct ArrowArrayStream *left, struct ArrowArrayStream *right,
                              const PbRangeOptions *opts, struct ArrowArrayStream *out);
 

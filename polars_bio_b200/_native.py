@@ -44,6 +44,7 @@ class PbRangeOptions(ctypes.Structure):
         ("max_batch_rows", ctypes.c_uint32),
         ("device", ctypes.c_int32),
         ("sink_pairs", ctypes.c_uint64),
+        ("min_dist", ctypes.c_int64),
     ]
 
 

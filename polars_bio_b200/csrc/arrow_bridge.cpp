@@ -1982,18 +1982,324 @@ int run_iter(Table *L, Table *R, OutStream *os, std::shared_ptr<IndexSide> xs) {
   return PBGPU_OK;
 }
 
+
+// ================================================================================================================
+// Unary sweeps at the Arrow level: merge / cluster / complement / subtract -- the host glue of
+// /root/reference/src/operation.rs:352-510 (do_merge / do_cluster / do_complement / do_subtract) over the device calls
+// pbgpu_merge / pbgpu_cluster / pbgpu_subtract (unary.cuh).  Contig codes are ranked in lexicographic name order before
+// they go to the device, so merged intervals come out ordered by contig name and cluster ids count the way bioframe's do
+// (tests/test_bioframe.py:392-411).  Output schemas (positions always Int64, like the reference's providers):
+//   merge       contig, start, end (named like the input's interval columns), n_intervals    tests/_expected.py:174-181
+//   cluster     every input column (zero-copy) + cluster, cluster_start, cluster_end          ..._regressions.py:49-59
+//   complement  contig, start, end                                                            ..._regressions.py:33-39
+//   subtract    every df1 column, the interval columns holding the remaining pieces           ..._regressions.py:41-47
+// Rows with a null contig / start / end take no part (cluster drops them from its output as well): parity unpinned.
+// ================================================================================================================
+struct VecStream {  // a finished result: schema + batches handed out one by one
+  ArrowSchema schema{};
+  std::vector<ArrowArray> batches;
+  size_t next = 0;
+  ~VecStream() {
+    for (auto &b : batches) if (b.release) b.release(&b);
+    if (schema.release) schema.release(&schema);
+  }
+};
+int vs_get_schema(ArrowArrayStream *s, ArrowSchema *out) {
+  VecStream *v = (VecStream *)s->private_data;
+  *out = copy_schema(&v->schema, "");
+  return 0;
+}
+int vs_get_next(ArrowArrayStream *s, ArrowArray *out) {
+  VecStream *v = (VecStream *)s->private_data;
+  memset(out, 0, sizeof(*out));
+  if (v->next >= v->batches.size()) return 0;
+  *out = v->batches[v->next];
+  v->batches[v->next].release = nullptr;  // moved
+  ++v->next;
+  return 0;
+}
+const char *vs_last_error(ArrowArrayStream *) { return nullptr; }
+void vs_release(ArrowArrayStream *s) {
+  if (!s || !s->release) return;
+  delete (VecStream *)s->private_data;
+  s->release = nullptr;
+}
+
+// int64 column widened from int32 values; open_end: INT32_MAX stands for "no upper bound" (complement's default view)
+int widened_column(const int32_t *src, int64_t n, bool open_end, ArrowArray *out) {
+  std::unique_ptr<OwnedArray> o(new OwnedArray());
+  int64_t *v = (int64_t *)hmalloc(8 * (size_t)(n ? n : 1));
+  if (!v) return set_error(PBGPU_ENOMEM, "host allocation failed");
+  o->bufs.push_back(v);
+  for (int64_t i = 0; i < n; ++i) v[i] = (open_end && src[i] == INT32_MAX) ? INT64_MAX : (int64_t)src[i];
+  o->bptr = {nullptr, v};
+  *out = finish_array(o.release(), n, 0);
+  return PBGPU_OK;
+}
+
+struct UnaryKeys {  // (contig code, start, end) of one table on the host (page-locked, ordinary caching: they are read back)
+  PinnedHold hold;
+  int32_t *c = nullptr, *s = nullptr, *e = nullptr;
+  int64_t n = 0;
+  int alloc(int64_t rows) {
+    n = rows;
+    c = hold.get<int32_t>((size_t)(rows ? rows : 1)); s = hold.get<int32_t>((size_t)(rows ? rows : 1)); e = hold.get<int32_t>((size_t)(rows ? rows : 1));
+    return (c && s && e) ? PBGPU_OK : set_error(PBGPU_ENOMEM, "pinned staging allocation failed");
+  }
+};
+
+struct UnaryDev {  // stream + device columns of one unary call
+  int prev_dev = -1;
+  cudaStream_t s = nullptr;
+  DevBufs dev;
+  ~UnaryDev() {
+    if (s) cudaStreamSynchronize(s);
+    dev.release();
+    if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+    if (prev_dev >= 0) cudaSetDevice(prev_dev);
+  }
+  int open(int device) {
+    int cur = -1;
+    BR_CUDA(cudaGetDevice(&cur));
+    if (device >= 0 && device != cur) { BR_CUDA(cudaSetDevice(device)); prev_dev = cur; }
+    BR_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    dev.s = s;
+    return PBGPU_OK;
+  }
+  int upload(const UnaryKeys &k, int32_t **dc, int32_t **ds, int32_t **de) {
+    const size_t n = (size_t)k.n;
+    *dc = dev.get<int32_t>(n); *ds = dev.get<int32_t>(n); *de = dev.get<int32_t>(n);
+    if (!*dc || !*ds || !*de) return set_error(PBGPU_ENOMEM, "device allocation failed");
+    if (n) {
+      BR_CUDA(cudaMemcpyAsync(*dc, k.c, 4 * n, cudaMemcpyHostToDevice, s));
+      BR_CUDA(cudaMemcpyAsync(*ds, k.s, 4 * n, cudaMemcpyHostToDevice, s));
+      BR_CUDA(cudaMemcpyAsync(*de, k.e, 4 * n, cudaMemcpyHostToDevice, s));
+    }
+    return PBGPU_OK;
+  }
+  // device column -> freshly allocated host buffer owned by `keep`
+  template <typename T>
+  int download(const T *d_src, int64_t n, const std::shared_ptr<HostBufs> &keep, T **out) {
+    T *h = (T *)hmalloc(sizeof(T) * (size_t)(n ? n : 1));
+    if (!h) return set_error(PBGPU_ENOMEM, "host allocation failed");
+    keep->v.push_back(h);
+    if (n) BR_CUDA(cudaMemcpyAsync(h, d_src, sizeof(T) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    *out = h;
+    return PBGPU_OK;
+  }
+};
+
+int run_unary(const PbRangeOptions &o, std::shared_ptr<Table> L, std::shared_ptr<Table> R, ArrowArrayStream *out) {
+  const int op = o.range_op;
+  const bool two = R != nullptr;  // subtract: the right table; complement: the view table
+  if (op == PBGPU_OP_SUBTRACT && !two) return set_error(PBGPU_EINVAL, "subtract needs two tables");
+  if (o.min_dist < 0) return set_error(PBGPU_EINVAL, "min_dist must be >= 0");
+  // 1. keys of both tables against one dictionary, then codes re-ranked in lexicographic name order
+  ContigDict dict;
+  UnaryKeys kl, kr;
+  BR_TRY(kl.alloc(L->rows));
+  BR_TRY(encode_keys(*L, "left", dict, kl.c, kl.s, kl.e));
+  if (two) {
+    BR_TRY(kr.alloc(R->rows));
+    BR_TRY(encode_keys(*R, op == PBGPU_OP_COMPLEMENT ? "view" : "right", dict, kr.c, kr.s, kr.e));
+  }
+  const int32_t n_contigs = (int32_t)dict.map.size();
+  std::vector<std::string> by_code((size_t)n_contigs), names((size_t)n_contigs);
+  for (auto &kv : dict.map) by_code[(size_t)kv.second] = kv.first;
+  std::vector<int32_t> order((size_t)n_contigs), rank((size_t)n_contigs);
+  for (int32_t i = 0; i < n_contigs; ++i) order[(size_t)i] = i;
+  std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return by_code[(size_t)a] < by_code[(size_t)b]; });
+  for (int32_t r = 0; r < n_contigs; ++r) { rank[(size_t)order[(size_t)r]] = r; names[(size_t)r] = by_code[(size_t)order[(size_t)r]]; }
+  auto rerank = [&](UnaryKeys &k) {
+    const int64_t nch = (k.n + kChunk - 1) / kChunk;
+    Pool::get().parallel_for(nch, [&](int64_t ci) {
+      const int64_t lo = ci * kChunk, hi = std::min(k.n, lo + kChunk);
+      for (int64_t i = lo; i < hi; ++i) { const int32_t c = k.c[i]; k.c[i] = (c >= 0 && c < n_contigs) ? rank[(size_t)c] : -1; }
+    });
+  };
+  rerank(kl);
+  if (two) rerank(kr);
+  // complement without a view table: every contig present spans [0, INT64_MAX) (polars_bio/range_op.py:726-729); swept as
+  // [0, INT32_MAX] -- no int32 coordinate reaches that end -- and the open end is put back afterwards
+  bool open_end = false;
+  if (op == PBGPU_OP_COMPLEMENT && !two) {
+    std::vector<uint8_t> present((size_t)n_contigs, 0);
+    for (int64_t i = 0; i < kl.n; ++i) if (kl.c[i] >= 0) present[(size_t)kl.c[i]] = 1;
+    int64_t nv = 0;
+    for (auto v : present) nv += v;
+    BR_TRY(kr.alloc(nv));
+    int64_t j = 0;
+    for (int32_t c = 0; c < n_contigs; ++c) if (present[(size_t)c]) { kr.c[j] = c; kr.s[j] = 0; kr.e[j] = INT32_MAX; ++j; }
+    open_end = true;
+  }
+  // 2. device
+  UnaryDev ud;
+  BR_TRY(ud.open(o.device));
+  cudaStream_t s = ud.s;
+  auto keep = std::make_shared<HostBufs>();
+  std::unique_ptr<VecStream> vs(new VecStream());
+  std::vector<ArrowSchema> fields;
+  struct FieldGuard { std::vector<ArrowSchema> &f; bool armed = true; ~FieldGuard() { if (armed) for (auto &k : f) if (k.release) k.release(&k); } } fguard{fields};
+  const ArrowSchema *fc = L->schema.children[L->key[0]];
+  bool ok_fmt = true;
+  const std::string contig_fmt = out_format(fc, &ok_fmt);  // utf8 stays utf8; views / dictionaries come out as large_utf8
+  const bool contig_large = contig_fmt == "U";
+  auto name_of = [&](const Table &t, int c) { return std::string(t.schema.children[c]->name ? t.schema.children[c]->name : ""); };
+  auto push_batch = [&](std::unique_ptr<OwnedArray> &top, int64_t rows) {
+    top->bptr = {nullptr};
+    vs->batches.push_back(finish_array(top.release(), rows, 0));
+  };
+  int32_t *dlc = nullptr, *dls = nullptr, *dle = nullptr;
+  if (op == PBGPU_OP_MERGE) {
+    BR_TRY(ud.upload(kl, &dlc, &dls, &dle));
+    pbgpu_intervals *h = nullptr;
+    BR_TRY(pbgpu_merge(dlc, dls, dle, kl.n, n_contigs, o.filter_op, o.min_dist, s, &h));
+    struct Free { pbgpu_intervals *h; cudaStream_t s; ~Free() { pbgpu_intervals_free(h, s); } } fr{h, s};
+    const int64_t n = pbgpu_intervals_rows(h);
+    const int32_t *dc = nullptr, *ds = nullptr, *de = nullptr;
+    const int64_t *dn = nullptr;
+    BR_TRY(pbgpu_intervals_columns(h, &dc, nullptr, &ds, &de, &dn));
+    int32_t *hc = nullptr, *hs = nullptr, *he = nullptr;
+    int64_t *hn = nullptr;
+    BR_TRY(ud.download(dc, n, keep, &hc)); BR_TRY(ud.download(ds, n, keep, &hs)); BR_TRY(ud.download(de, n, keep, &he)); BR_TRY(ud.download(dn, n, keep, &hn));
+    BR_CUDA(cudaStreamSynchronize(s));
+    fields.push_back(make_schema(contig_fmt, name_of(*L, L->key[0]), nullptr, 0));
+    fields.push_back(make_schema("l", name_of(*L, L->key[1]), nullptr, 0));
+    fields.push_back(make_schema("l", name_of(*L, L->key[2]), nullptr, 0));
+    fields.push_back(make_schema("l", "n_intervals", nullptr, 0));
+    if (n > 0) {
+      std::unique_ptr<OwnedArray> top(new OwnedArray());
+      StrBufs sb;
+      BR_TRY(contig_buffers(hc, n, names, contig_large, &sb));
+      top->kids.push_back(str_view(sb, n));
+      ArrowArray a{};
+      int rc = widened_column(hs, n, false, &a);
+      if (rc == PBGPU_OK) { top->kids.push_back(a); rc = widened_column(he, n, false, &a); }
+      if (rc == PBGPU_OK) { top->kids.push_back(a); top->kids.push_back(view_buffer(keep, hn, n)); }
+      if (rc != PBGPU_OK) { for (auto &k : top->kids) if (k.release) k.release(&k); return rc; }
+      push_batch(top, n);
+    }
+  } else if (op == PBGPU_OP_CLUSTER) {
+    BR_TRY(ud.upload(kl, &dlc, &dls, &dle));
+    const int64_t n = kl.n;
+    int64_t *d_id = ud.dev.get<int64_t>((size_t)n);
+    int32_t *d_cs = ud.dev.get<int32_t>((size_t)n), *d_ce = ud.dev.get<int32_t>((size_t)n);
+    if (!d_id || !d_cs || !d_ce) return set_error(PBGPU_ENOMEM, "device allocation failed");
+    int64_t n_clusters = 0;
+    BR_TRY(pbgpu_cluster(dlc, dls, dle, n, n_contigs, o.filter_op, o.min_dist, d_id, d_cs, d_ce, &n_clusters, s));
+    int64_t *h_id = nullptr;
+    int32_t *h_cs = nullptr, *h_ce = nullptr;
+    BR_TRY(ud.download(d_id, n, keep, &h_id)); BR_TRY(ud.download(d_cs, n, keep, &h_cs)); BR_TRY(ud.download(d_ce, n, keep, &h_ce));
+    BR_CUDA(cudaStreamSynchronize(s));
+    int64_t *w_cs = (int64_t *)hmalloc(8 * (size_t)(n ? n : 1)), *w_ce = (int64_t *)hmalloc(8 * (size_t)(n ? n : 1));
+    if (!w_cs || !w_ce) { hfree(w_cs); hfree(w_ce); return set_error(PBGPU_ENOMEM, "host allocation failed"); }
+    keep->v.push_back(w_cs); keep->v.push_back(w_ce);
+    for (int64_t i = 0; i < n; ++i) { w_cs[i] = h_cs[i]; w_ce[i] = h_ce[i]; }
+    for (int64_t c = 0; c < L->schema.n_children; ++c) fields.push_back(copy_schema(L->schema.children[c], name_of(*L, (int)c)));
+    fields.push_back(make_schema("l", "cluster", nullptr, 0));
+    fields.push_back(make_schema("l", "cluster_start", nullptr, 0));
+    fields.push_back(make_schema("l", "cluster_end", nullptr, 0));
+    // the input columns are re-exported zero-copy: one output batch per maximal run of rows that take part inside an
+    // input batch (null-keyed rows, cluster id -1, are dropped; without them: one output batch per input batch)
+    for (int b = 0; b < (int)L->batches.size(); ++b) {
+      const int64_t g0 = L->start[(size_t)b], len = L->batches[(size_t)b].length;
+      int64_t a = 0;
+      while (a < len) {
+        while (a < len && h_id[g0 + a] < 0) ++a;
+        int64_t z = a;
+        while (z < len && h_id[g0 + z] >= 0) ++z;
+        if (z > a) {
+          std::unique_ptr<OwnedArray> top(new OwnedArray());
+          for (int c = 0; c < (int)L->n_cols(); ++c) top->kids.push_back(view_column(L, b, c, a, z - a));
+          top->kids.push_back(view_buffer(keep, h_id + g0 + a, z - a));
+          top->kids.push_back(view_buffer(keep, w_cs + g0 + a, z - a));
+          top->kids.push_back(view_buffer(keep, w_ce + g0 + a, z - a));
+          push_batch(top, z - a);
+        }
+        a = z;
+      }
+    }
+  } else {  // subtract / complement: pieces of every "left" row that no "right" row covers
+    const bool comp = op == PBGPU_OP_COMPLEMENT;
+    const UnaryKeys &ka = comp ? kr : kl, &kb = comp ? kl : kr;  // complement = subtract with the view table on the left
+    int32_t *dac = nullptr, *das = nullptr, *dae = nullptr, *dbc = nullptr, *dbs = nullptr, *dbe = nullptr;
+    BR_TRY(ud.upload(ka, &dac, &das, &dae));
+    BR_TRY(ud.upload(kb, &dbc, &dbs, &dbe));
+    pbgpu_intervals *h = nullptr;
+    BR_TRY(pbgpu_subtract(dac, das, dae, ka.n, dbc, dbs, dbe, kb.n, n_contigs, o.filter_op, s, &h));
+    struct Free { pbgpu_intervals *h; cudaStream_t s; ~Free() { pbgpu_intervals_free(h, s); } } fr{h, s};
+    const int64_t n = pbgpu_intervals_rows(h);
+    const uint32_t *dr = nullptr;
+    const int32_t *ds = nullptr, *de = nullptr;
+    BR_TRY(pbgpu_intervals_columns(h, nullptr, &dr, &ds, &de, nullptr));
+    uint32_t *hr = nullptr;
+    int32_t *hs = nullptr, *he = nullptr;
+    BR_TRY(ud.download(dr, n, keep, &hr)); BR_TRY(ud.download(ds, n, keep, &hs)); BR_TRY(ud.download(de, n, keep, &he));
+    BR_CUDA(cudaStreamSynchronize(s));
+    if (comp) {
+      fields.push_back(make_schema(contig_fmt, name_of(*L, L->key[0]), nullptr, 0));
+      fields.push_back(make_schema("l", name_of(*L, L->key[1]), nullptr, 0));
+      fields.push_back(make_schema("l", name_of(*L, L->key[2]), nullptr, 0));
+    } else {
+      for (int c = 0; c < (int)L->n_cols(); ++c) {
+        if (c == L->key[1] || c == L->key[2]) { fields.push_back(make_schema("l", name_of(*L, c), nullptr, 0)); continue; }
+        bool ok = true;
+        const std::string fmt = out_format(L->schema.children[c], &ok);
+        if (!ok) return set_error(PBGPU_ESCHEMA, "payload column '%s' has unsupported Arrow type '%s' for subtract", name_of(*L, c).c_str(), L->schema.children[c]->format);
+        fields.push_back(make_schema(fmt, name_of(*L, c), L->schema.children[c]->metadata, L->schema.children[c]->flags | ARROW_FLAG_NULLABLE));
+      }
+    }
+    if (n > 0) {
+      std::unique_ptr<OwnedArray> top(new OwnedArray());
+      int rc = PBGPU_OK;
+      ArrowArray a{};
+      if (comp) {
+        std::vector<int32_t> codes((size_t)n);
+        for (int64_t i = 0; i < n; ++i) codes[(size_t)i] = ka.c[hr[i]];  // the view row's contig
+        StrBufs sb;
+        rc = contig_buffers(codes.data(), n, names, contig_large, &sb);
+        if (rc == PBGPU_OK) { top->kids.push_back(str_view(sb, n)); rc = widened_column(hs, n, false, &a); }
+        if (rc == PBGPU_OK) { top->kids.push_back(a); rc = widened_column(he, n, open_end, &a); }
+        if (rc == PBGPU_OK) top->kids.push_back(a);
+      } else {
+        std::vector<GatherJob> jobs;
+        for (int c = 0; c < (int)L->n_cols(); ++c)
+          if (c != L->key[1] && c != L->key[2]) jobs.push_back(GatherJob{L.get(), c, hr});
+        std::vector<ArrowArray> cols;
+        if (!jobs.empty()) rc = gather_columns(jobs, n, &cols);
+        size_t next = 0;
+        for (int c = 0; c < (int)L->n_cols() && rc == PBGPU_OK; ++c) {
+          if (c == L->key[1]) { rc = widened_column(hs, n, false, &a); if (rc == PBGPU_OK) top->kids.push_back(a); }
+          else if (c == L->key[2]) { rc = widened_column(he, n, false, &a); if (rc == PBGPU_OK) top->kids.push_back(a); }
+          else top->kids.push_back(cols[next++]);
+        }
+        for (; next < cols.size(); ++next) if (cols[next].release) cols[next].release(&cols[next]);
+      }
+      if (rc != PBGPU_OK) { for (auto &k : top->kids) if (k.release) k.release(&k); return rc; }
+      push_batch(top, n);
+    }
+  }
+  fguard.armed = false;
+  vs->schema = make_schema("+s", "", nullptr, 0, std::move(fields));
+  out->get_schema = vs_get_schema;
+  out->get_next = vs_get_next;
+  out->get_last_error = vs_last_error;
+  out->release = vs_release;
+  out->private_data = vs.release();
+  return PBGPU_OK;
+}
 }  // namespace
 
 namespace {
 int check_opts(const PbRangeOptions *opts) {
   if (!opts) return set_error(PBGPU_EINVAL, "opts is NULL");
   if (opts->filter_op != PBGPU_FILTER_WEAK && opts->filter_op != PBGPU_FILTER_STRICT) return set_error(PBGPU_EINVAL, "bad filter_op %d", opts->filter_op);
-  if (opts->range_op != PBGPU_OP_OVERLAP && opts->range_op != PBGPU_OP_NEAREST && opts->range_op != PBGPU_OP_COVERAGE &&
-      opts->range_op != PBGPU_OP_COUNT_OVERLAPS_NAIVE)
-    return set_error(PBGPU_EINVAL, "range_op %d is not on the GPU hot path (overlap=0, nearest=3, coverage=4, count_overlaps=6)", opts->range_op);
+  if (opts->range_op < PBGPU_OP_OVERLAP || opts->range_op > PBGPU_OP_MERGE)
+    return set_error(PBGPU_EINVAL, "unknown range_op %d", opts->range_op);
   if (opts->output_mode < PBGPU_OUT_JOIN || opts->output_mode > PBGPU_OUT_LEFT_DISTINCT) return set_error(PBGPU_EINVAL, "bad output_mode %d", opts->output_mode);
   return PBGPU_OK;
 }
+bool is_unary_op(int op) { return op == PBGPU_OP_MERGE || op == PBGPU_OP_CLUSTER || op == PBGPU_OP_COMPLEMENT || op == PBGPU_OP_SUBTRACT; }
 std::unique_ptr<OutStream> new_outstream(const PbRangeOptions &opts, const std::string *sfx1, const std::string *sfx2) {
   std::unique_ptr<OutStream> os(new OutStream());
   os->opt = opts;
@@ -2030,6 +2336,7 @@ extern "C" int pbgpu_range_open(struct ArrowArrayStream *indexed, const PbRangeO
   *out = nullptr;
   int rc = check_opts(opts);
   if (rc != PBGPU_OK) return rc;
+  if (is_unary_op(opts->range_op)) return set_error(PBGPU_EINVAL, "range_op %d is a unary sweep: use pbgpu_range_op", opts->range_op);
   try {
     std::unique_ptr<pbgpu_range_session> ss(new pbgpu_range_session());
     ss->opt = *opts;
@@ -2098,6 +2405,21 @@ extern "C" int pbgpu_range_op(struct ArrowArrayStream *left, struct ArrowArraySt
   int rc0 = check_opts(opts);
   if (rc0 != PBGPU_OK) return rc0;
   try {
+    if (is_unary_op(opts->range_op)) {  // merge / cluster / complement / subtract: `right` is the second table (subtract), the
+      auto L = std::make_shared<Table>();  // view table (complement; may be NULL) or NULL
+      std::shared_ptr<Table> R;
+      int rc = drain(left, *L, "left");
+      for (int i = 0; i < 3 && rc == PBGPU_OK; ++i) rc = find_col(*L, opts->cols1[i], "left", &L->key[i]);
+      const bool want_right = right && right->get_schema && (opts->range_op == PBGPU_OP_SUBTRACT || opts->range_op == PBGPU_OP_COMPLEMENT);
+      if (rc == PBGPU_OK && want_right) {
+        R = std::make_shared<Table>();
+        rc = drain(right, *R, "right");
+        for (int i = 0; i < 3 && rc == PBGPU_OK; ++i) rc = find_col(*R, opts->cols2[i], "right", &R->key[i]);
+      }
+      if (rc != PBGPU_OK) return rc;
+      return run_unary(*opts, L, R, out);
+    }
+    if (!right) return set_error(PBGPU_EINVAL, "right stream is NULL");
     std::string sfx1 = opts->suffixes[0] ? opts->suffixes[0] : "_1", sfx2 = opts->suffixes[1] ? opts->suffixes[1] : "_2";
     std::unique_ptr<OutStream> os = new_outstream(*opts, &sfx1, &sfx2);
     os->left = std::make_shared<Table>();

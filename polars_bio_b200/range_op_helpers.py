@@ -152,26 +152,26 @@ def convert_result(result: RangeResult, output_type: str, zero_based: bool):
 
 
 def unary_operation(df1, df2, range_options: RangeOptions, output_type: str, ctx, view_df=None):
-    """merge / cluster / complement / subtract (range_op.py:599-868 -> operation.rs:352-510): every input kind is
-    collected into an Arrow table, the sweep runs on the device (unary_op.py), the result table is converted."""
-    from . import unary_op
-    from .range_op_io import _df_to_reader
+    """merge / cluster / complement / subtract (range_op.py:599-868 -> operation.rs:352-510): the tables go through
+    ``pbgpu_range_op`` like the binary operations (Arrow streams in, Arrow stream out; csrc/arrow_bridge.cpp
+    ``run_unary``); ``unary_op.py`` holds the same host logic over the device-level calls (tests compare the two)."""
+    import dataclasses
+
+    from .range_op_io import range_operation_unary
 
     ctx.sync_options()
     zero_based = range_options.filter_op == FilterOp.Strict
-    t1 = _df_to_reader(df1).read_all()
-    cols1 = list(range_options.columns_1 or ["chrom", "start", "end"])
     op = range_options.range_op
-    if op == RangeOp.Merge:
-        out = unary_op.merge_table(t1, cols1, range_options.filter_op, int(range_options.min_dist or 0))
-    elif op == RangeOp.Cluster:
-        out = unary_op.cluster_table(t1, cols1, range_options.filter_op, int(range_options.min_dist or 0))
+    cols1 = list(range_options.columns_1 or ["chrom", "start", "end"])
+    if op in (RangeOp.Merge, RangeOp.Cluster):
+        second = None
+        opts = dataclasses.replace(range_options, columns_1=cols1, columns_2=cols1)
     elif op == RangeOp.Complement:
-        view = None if view_df is None else _df_to_reader(view_df).read_all()
-        out = unary_op.complement_table(t1, cols1, range_options.filter_op, view, range_options.view_columns)
+        second = view_df
+        opts = dataclasses.replace(range_options, columns_1=cols1, columns_2=list(range_options.view_columns or cols1))
     elif op == RangeOp.Subtract:
-        t2 = _df_to_reader(df2).read_all()
-        out = unary_op.subtract_table(t1, t2, cols1, list(range_options.columns_2 or cols1), range_options.filter_op)
+        second = df2
+        opts = dataclasses.replace(range_options, columns_1=cols1, columns_2=list(range_options.columns_2 or cols1))
     else:
         raise ValueError(f"{op!r} is not a unary sweep")
-    return convert_result(RangeResult(out.to_reader()), output_type, zero_based)
+    return convert_result(range_operation_unary(ctx, df1, second, opts), output_type, zero_based)

@@ -178,6 +178,7 @@ def _c_opts(ro: RangeOptions, emit: int, limit: Optional[int], ctx) -> _native.P
         batch = int((ctx.get_option(BATCH_SIZE) if ctx is not None else None) or 8192)
     o.max_batch_rows = batch
     o.device = -1
+    o.min_dist = int(ro.min_dist or 0)
     return o
 
 
@@ -193,6 +194,23 @@ def range_operation_frame(py_ctx, df1, df2, range_options: RangeOptions, limit: 
     r2._export_to_c(ctypes.addressof(s2))
     opts = _c_opts(range_options, emit, limit, py_ctx)
     rc = _native.lib().pbgpu_range_op(ctypes.addressof(s1), ctypes.addressof(s2), ctypes.byref(opts), ctypes.addressof(so))
+    _native.check(rc)
+    return RangeResult(pa.RecordBatchReader._import_from_c(ctypes.addressof(so)))
+
+
+def range_operation_unary(py_ctx, df1, df2, range_options: RangeOptions) -> RangeResult:
+    """merge / cluster / complement / subtract through the same C entry as the binary operations (``pbgpu_range_op``;
+    reference: do_merge / do_cluster / do_complement / do_subtract, src/operation.rs:352-510).  ``df2``: the second
+    table of subtract, the view table of complement (its interval columns are ``columns_2``), else None."""
+    if range_options.range_op not in (RangeOp.Merge, RangeOp.Cluster, RangeOp.Complement, RangeOp.Subtract):
+        raise ValueError(f"{range_options.range_op!r} is not a unary sweep")
+    s1, s2, so = _CStream(), _CStream(), _CStream()
+    _df_to_reader(df1)._export_to_c(ctypes.addressof(s1))
+    if df2 is not None:
+        _df_to_reader(df2)._export_to_c(ctypes.addressof(s2))
+    opts = _c_opts(range_options, 0, None, py_ctx)
+    rc = _native.lib().pbgpu_range_op(ctypes.addressof(s1), ctypes.addressof(s2) if df2 is not None else None, ctypes.byref(opts),
+                                      ctypes.addressof(so))
     _native.check(rc)
     return RangeResult(pa.RecordBatchReader._import_from_c(ctypes.addressof(so)))
 

@@ -20,24 +20,10 @@ class _CS(ctypes.Structure):
 
 
 @pytest.fixture(scope="module")
-def lib(tmp_path_factory):
-    d = tmp_path_factory.mktemp("bridge")
-    src = open(os.path.join(ROOT, "polars_bio_b200", "csrc", "arrow_bridge.cpp")).read()
-    assert "#include <cuda_runtime.h>" in src
-    src = src.replace("#include <cuda_runtime.h>", '#include "stub_cuda.h"') + open(os.path.join(HARNESS, "harness_tail.inc")).read()
-    cpp = d / "bridge_host.cpp"
-    cpp.write_text(src)
-    so = d / "libbridge_host.so"
-    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    extra = os.environ.get("PB_BRIDGE_CXXFLAGS", "").split()  # e.g. -fsanitize=address,undefined (scripts/bridge_sanitize.sh)
-    r = subprocess.run([cxx, "-std=c++17", "-O1", *extra, "-fPIC", "-shared", "-I", HARNESS, "-I", os.path.join(ROOT, "include"),
-                        "-I", os.path.join(ROOT, "polars_bio_b200", "csrc"), "-o", str(so), str(cpp), "-lpthread"],
-                       capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr[-3000:]
-    L = ctypes.CDLL(str(so))
-    L.dbg_roundtrip.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64,
-                                ctypes.c_void_p, ctypes.c_void_p]
-    return L
+def lib():
+    from tests import _harness
+
+    return _harness.build()
 
 
 def _roundtrip(lib, table, rows, cols=("chrom", "start", "end")):
@@ -227,3 +213,125 @@ def test_gather_random_tables_equal_pyarrow_take(lib, seed):
         else:
             assert got_c.type == want_c.type, (name, got_c.type, want_c.type)
             assert got_c.to_pylist() == want_c.to_pylist(), name
+
+
+# ---- unary sweeps through pbgpu_range_op (run_unary) against the oracle, device calls = the harness's CPU doubles ----
+def _unary(lib, op, left, right=None, cols1=("chrom", "start", "end"), cols2=("chrom", "start", "end"), strict=True, min_dist=0):
+    from polars_bio_b200 import _native
+
+    lib.dbg_streams_ok(1)
+    try:
+        s1, s2, so = _CS(), _CS(), _CS()
+        (left if isinstance(left, pa.RecordBatchReader) else left.to_reader())._export_to_c(ctypes.addressof(s1))
+        if right is not None:
+            right.to_reader()._export_to_c(ctypes.addressof(s2))
+        o = _native.PbRangeOptions()
+        o.range_op, o.filter_op, o.min_dist, o.device = op, 1 if strict else 0, min_dist, -1
+        for i in range(3):
+            o.cols1[i] = cols1[i].encode()
+            o.cols2[i] = cols2[i].encode()
+        rc = lib.pbgpu_range_op(ctypes.addressof(s1), ctypes.addressof(s2) if right is not None else None, ctypes.addressof(o), ctypes.addressof(so))
+        assert rc == 0, (rc, lib.pbgpu_last_error())
+        return pa.RecordBatchReader._import_from_c(ctypes.addressof(so)).read_all()
+    finally:
+        lib.dbg_streams_ok(0)
+
+
+def _random_table(rng, n, contig_type, names, null_rate=0.1):
+    c = rng.integers(0, len(names), n)
+    s = rng.integers(0, 300, n)
+    e = s + rng.integers(1, 40, n)
+    chrom = [None if rng.random() < null_rate else names[k] for k in c]
+    start = [None if rng.random() < null_rate / 2 else int(v) for v in s]
+    arr = pa.array(chrom, type=pa.large_string())
+    if contig_type == "dict":
+        arr = pa.array(chrom, type=pa.string()).dictionary_encode()
+    elif contig_type == "utf8":
+        arr = arr.cast(pa.string())
+    elif contig_type == "view":  # built directly: pyarrow's exporter crashes on sliced views cast from large_string
+        arr = pa.array(chrom, type=pa.string_view())
+    return pa.table({"chrom": arr, "start": pa.array(start, pa.int64()), "end": pa.array(e.astype(np.int32)), "tag": pa.array([f"r{i}" for i in range(n)])})
+
+
+def _keys_np(t, names_sorted):
+    lut = {n: i for i, n in enumerate(names_sorted)}
+    chrom, start, end = t.column("chrom").to_pylist(), t.column("start").to_pylist(), t.column("end").to_pylist()
+    ok = [c is not None and s is not None and e is not None for c, s, e in zip(chrom, start, end)]
+    c = np.array([lut[x] if k else -1 for x, k in zip(chrom, ok)], np.int32)
+    return c, np.array([s if k else 0 for s, k in zip(start, ok)], np.int32), np.array([e if k else 0 for e, k in zip(end, ok)], np.int32)
+
+
+@pytest.mark.parametrize("contig_type", ["utf8", "large", "dict", "view"])
+@pytest.mark.parametrize("strict", [True, False])
+def test_unary_sweeps_through_the_c_entry_match_the_oracle(lib, contig_type, strict):
+    from oracle import unary_np as U
+
+    rng = np.random.default_rng(11 + (7 if strict else 0))
+    names = ["chr2", "chr10", "chrX", "chr1", "alt_7"]  # first-seen order differs from name order
+    for trial in range(6):
+        t = _random_table(rng, int(rng.integers(0, 60)), contig_type, names)
+        r = _random_table(rng, int(rng.integers(0, 40)), "utf8", names + ["only_right"])
+        batches = t.to_batches(max_chunksize=int(rng.integers(3, 20)))
+        reader = lambda: pa.RecordBatchReader.from_batches(t.schema, batches)
+        present = sorted({x for x in t.column("chrom").to_pylist() + r.column("chrom").to_pylist() if x is not None})
+        md = int(rng.integers(0, 3)) * 5
+        # merge: names of the merged table come from the left table only -> same relative (name) order
+        sorted_l = sorted({x for x in t.column("chrom").to_pylist() if x is not None})
+        c, s, e = _keys_np(t, sorted_l)
+        mc, ms, me, mn = U.merge(c, s, e, len(sorted_l), strict, md)
+        got = _unary(lib, 7, reader(), strict=strict, min_dist=md)
+        assert got.column_names == ["chrom", "start", "end", "n_intervals"]
+        assert got.column("chrom").to_pylist() == [sorted_l[k] for k in mc]
+        assert got.column("start").to_pylist() == ms.tolist() and got.column("end").to_pylist() == me.tolist() and got.column("n_intervals").to_pylist() == mn.tolist()
+        assert got.schema.field("start").type == pa.int64() and got.schema.field("chrom").type == (pa.string() if contig_type == "utf8" else pa.large_string())
+        # cluster: every input column passes through untouched (any type), null-keyed rows dropped
+        cid, cs, ce = U.cluster(c, s, e, len(sorted_l), strict, md)
+        keep = cid >= 0
+        got = _unary(lib, 2, reader(), strict=strict, min_dist=md)
+        assert got.column_names == ["chrom", "start", "end", "tag", "cluster", "cluster_start", "cluster_end"]
+        assert got.schema.field("chrom").type == t.schema.field("chrom").type
+        assert got.column("tag").to_pylist() == [x for x, k in zip(t.column("tag").to_pylist(), keep) if k]
+        assert got.column("cluster").to_pylist() == cid[keep].tolist()
+        assert got.column("cluster_start").to_pylist() == cs[keep].tolist() and got.column("cluster_end").to_pylist() == ce[keep].tolist()
+        # subtract: shared dictionary over both tables
+        lc, ls, le = _keys_np(t, present)
+        rc_, rs, re_ = _keys_np(r, present)
+        row, fs, fe = U.subtract(lc, ls, le, rc_, rs, re_, len(present), strict)
+        got = _unary(lib, 5, reader(), r, strict=strict)
+        assert got.column_names == ["chrom", "start", "end", "tag"]
+        want = sorted(zip([f"r{k}" for k in row], fs.tolist(), fe.tolist()))
+        assert sorted(zip(got.column("tag").to_pylist(), got.column("start").to_pylist(), got.column("end").to_pylist())) == want
+        tl = t.column("chrom").to_pylist()
+        assert got.column("chrom").to_pylist() == [tl[int(x[1:])] for x in got.column("tag").to_pylist()]
+        # complement inside a view table, and with the default view
+        view = pa.table({"chrom": pa.array(present), "start": pa.array([0] * len(present), pa.int64()), "end": pa.array([500] * len(present), pa.int64())})
+        vc = np.arange(len(present), dtype=np.int32)
+        kc, fs, fe = U.complement(lc, ls, le, len(present), strict, view=(vc, np.zeros(len(present), np.int32), np.full(len(present), 500, np.int32)))
+        got = _unary(lib, 1, reader(), view, strict=strict)
+        assert got.column_names == ["chrom", "start", "end"]
+        assert sorted(zip(got.column("chrom").to_pylist(), got.column("start").to_pylist(), got.column("end").to_pylist())) == \
+            sorted(zip([present[k] for k in kc], fs.tolist(), fe.tolist()))
+        kc, fs, fe = U.complement(c, s, e, len(sorted_l), strict)
+        got = _unary(lib, 1, reader(), strict=strict)
+        assert sorted(zip(got.column("chrom").to_pylist(), got.column("start").to_pylist(), got.column("end").to_pylist())) == \
+            sorted(zip([sorted_l[k] for k in kc], fs.tolist(), fe.tolist()))
+
+
+def test_unary_entry_errors(lib):
+    from polars_bio_b200 import _native
+
+    t = pa.table({"chrom": ["a"], "start": [1], "end": [5]})
+    lib.dbg_streams_ok(1)
+    try:
+        for op, right, cols, code in ((5, None, ("chrom", "start", "end"), 1), (7, None, ("chrom", "nope", "end"), 5)):
+            s1, so = _CS(), _CS()
+            t.to_reader()._export_to_c(ctypes.addressof(s1))
+            o = _native.PbRangeOptions()
+            o.range_op, o.filter_op, o.device = op, 1, -1
+            for i in range(3):
+                o.cols1[i] = cols[i].encode()
+                o.cols2[i] = cols[i].encode()
+            assert lib.pbgpu_range_op(ctypes.addressof(s1), None, ctypes.addressof(o), ctypes.addressof(so)) == code
+            assert s1.release is None  # the input was moved (released) although the call failed
+    finally:
+        lib.dbg_streams_ok(0)

@@ -208,3 +208,37 @@ def test_api_parquet_fixtures_against_oracle():
     want = pd.DataFrame({"contig": np.array(names)[vc], "pos_start": fs, "pos_end": fe})
     got = pb.complement(ex, view_df=view, cols=cols, view_cols=("chrom", "start", "end"), output_type="pandas.DataFrame")
     pd.testing.assert_frame_equal(sort_all(got), sort_all(want))
+
+
+@pytest.mark.parametrize("strict", [True, False])
+def test_arrow_level_entry_equals_the_device_level_host_layer(strict):
+    """pb.merge / cluster / complement / subtract run through pbgpu_range_op (csrc/arrow_bridge.cpp run_unary); the same
+    tables through polars_bio_b200/unary_op.py (pyarrow plumbing over pbgpu_merge / _cluster / _subtract) must give
+    identical tables: contig order by name, dropped null keys, payload columns, Int64 positions."""
+    import polars_bio_b200 as pb
+    from polars_bio_b200 import FilterOp, unary_op
+
+    rng = np.random.default_rng(5 if strict else 6)
+    names = np.array(["chr2", "chr10", "chrX", "chr1", "GL000219.1", "alt_7"])
+    fo = FilterOp.Strict if strict else FilterOp.Weak
+
+    def table(n, null_rate, ctype):
+        c = names[rng.integers(0, len(names), n)].tolist()
+        s = rng.integers(0, 200_000, n)
+        e = s + rng.integers(1, 3_000, n)
+        chrom = pa.array([None if rng.random() < null_rate else x for x in c], type=ctype)
+        start = pa.array([None if rng.random() < null_rate else int(v) for v in s], pa.int64())
+        return pb.set_coordinate_system(pa.table({"chrom": chrom, "start": start, "end": pa.array(e.astype(np.int32)),
+                                                  "score": pa.array(rng.random(n)), "tag": pa.array([f"row{i}" for i in range(n)])}), strict)
+
+    for n, m, ctype in ((5_000, 2_000, pa.string()), (40_000, 30_000, pa.large_string()), (0, 10, pa.string()), (300, 0, pa.string())):
+        t, r = table(n, 0.02, ctype), table(m, 0.02, pa.string())
+        cols = ["chrom", "start", "end"]
+        key = lambda x: x.sort_by([(c, "ascending") for c in x.column_names if c != "score"])
+        for md in (0, 50):
+            assert pb.merge(t, min_dist=md, output_type="pyarrow.Table").equals(unary_op.merge_table(t, cols, fo, md))
+            assert key(pb.cluster(t, min_dist=md, output_type="pyarrow.Table")).equals(key(unary_op.cluster_table(t, cols, fo, md)))
+        assert key(pb.subtract(t, r, output_type="pyarrow.Table")).equals(key(unary_op.subtract_table(t, r, cols, cols, fo)))
+        view = pb.set_coordinate_system(pa.table({"chrom": names.tolist(), "start": [0] * len(names), "end": [250_000] * len(names)}), strict)
+        assert key(pb.complement(t, view_df=view, output_type="pyarrow.Table")).equals(key(unary_op.complement_table(t, cols, fo, view, cols)))
+        assert key(pb.complement(t, output_type="pyarrow.Table")).equals(key(unary_op.complement_table(t, cols, fo)))

@@ -89,11 +89,28 @@ def test_oracle_twins_agree_on_parquet_fixture_sample():
     assert np.array_equal(ms, ms2) and np.array_equal(me, me2) and (mn2 == 1).all()
 
 
-# ---- host layer with the device replaced by the oracle ----------------------------------------------------------
-@pytest.fixture
-def fake_device(monkeypatch):
+# ---- the public calls end to end on the CPU, two routes ----------------------------------------------------------
+#   "c"  : the product route -- facade -> pbgpu_range_op of the harness build of csrc/arrow_bridge.cpp (tests/_harness.py),
+#          whose unary device calls are plain CPU doubles: the C++ glue (run_unary) is what runs
+#   "py" : polars_bio_b200/unary_op.py (the same host logic over the device-level calls) with the engine calls replaced
+#          by the oracle
+@pytest.fixture(params=["c", "py"])
+def fake_device(request, monkeypatch):
+    from polars_bio_b200 import _native, range_op_io
+
+    if request.param == "c":
+        from tests import _harness
+
+        H = _harness.build()
+        H.dbg_streams_ok(1)
+        monkeypatch.setattr(_native, "lib", lambda: H)
+        yield "c"
+        H.dbg_streams_ok(0)
+        return
     torch = pytest.importorskip("torch")
     from polars_bio_b200 import engine, unary_op
+    from polars_bio_b200.options import RangeOp
+    from polars_bio_b200.range_op_io import RangeResult, _df_to_reader
 
     t = lambda a, dt=np.int32: torch.from_numpy(np.ascontiguousarray(a, dtype=dt))
     monkeypatch.setattr(unary_op, "_to_device", lambda *cols: [t(c) for c in cols])
@@ -113,6 +130,22 @@ def fake_device(monkeypatch):
     monkeypatch.setattr(engine, "merge_intervals", merge_intervals)
     monkeypatch.setattr(engine, "cluster_intervals", cluster_intervals)
     monkeypatch.setattr(engine, "subtract_intervals", subtract_intervals)
+
+    def unary_py(ctx, df1, df2, ro):
+        t1 = _df_to_reader(df1).read_all()
+        t2 = None if df2 is None else _df_to_reader(df2).read_all()
+        if ro.range_op == RangeOp.Merge:
+            out = unary_op.merge_table(t1, ro.columns_1, ro.filter_op, int(ro.min_dist or 0))
+        elif ro.range_op == RangeOp.Cluster:
+            out = unary_op.cluster_table(t1, ro.columns_1, ro.filter_op, int(ro.min_dist or 0))
+        elif ro.range_op == RangeOp.Complement:
+            out = unary_op.complement_table(t1, ro.columns_1, ro.filter_op, t2, ro.columns_2)
+        else:
+            out = unary_op.subtract_table(t1, t2, ro.columns_1, ro.columns_2, ro.filter_op)
+        return RangeResult(out.to_reader())
+
+    monkeypatch.setattr(range_op_io, "range_operation_unary", unary_py)
+    yield "py"
 
 
 def _frame(d, zero_based=True):

@@ -3,6 +3,7 @@
 #pragma once
 #include <stdlib.h>
 #include <stdint.h>
+#include <string.h>
 typedef int cudaError_t; typedef void* cudaStream_t;
 #define cudaSuccess 0
 #define cudaHostAllocPortable 1
@@ -16,12 +17,16 @@ static inline cudaError_t cudaGetLastError() { return 0; }
 static inline const char* cudaGetErrorString(cudaError_t) { return "stub"; }
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }
 static inline cudaError_t cudaSetDevice(int) { return 0; }
-static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = 0; return 1; }
+// PB_STUB_STREAMS_OK: stream creation succeeds (the unary-sweep glue runs end to end against the CPU doubles of harness_tail.inc);
+// otherwise it fails, which keeps the binary operations from going anywhere near their (failing) device stubs
+extern int pb_stub_streams_ok;
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = 0; return pb_stub_streams_ok ? 0 : 1; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
 static inline cudaError_t cudaMallocAsync(void** p, size_t n, cudaStream_t) { *p = malloc(n); return 0; }
 static inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { free(p); return 0; }
-static inline cudaError_t cudaMemcpyAsync(void*, const void*, size_t, int, cudaStream_t) { return 0; }
+// "device" memory is malloc'ed host memory here (dev_alloc in harness_tail.inc), so a copy is a copy
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int, cudaStream_t) { if (n) memcpy(d, s, n); return 0; }
 typedef void* cudaEvent_t;
 #define cudaEventDisableTiming 2
 #define cudaHostRegisterPortable 1
