@@ -370,6 +370,49 @@ __global__ void __launch_bounds__(kSweepThreads) overlap_emit_staged_kernel(Inde
   const bool heavy = cnt >= kEmitHeavy && !generic;
   const unsigned lt = lanemask_lt();
   const long long thr = s - (STRICT ? 0 : 1);  // hit <=> indexed end > thr   (Strict: end > start; Weak: end >= start)
+  // Flat fast path.  cnt = (starts before the probe end) - (ends at or before the probe start), so the window [hi-cnt, hi)
+  // holds exactly cnt entries; when nothing BELOW it reaches past the probe start -- one load of the running maximum at
+  // hi-cnt-1 decides -- every hit lies inside it, hence every entry of it is a hit: the probe's pairs are a plain expansion
+  // of (hi, cnt), no candidate is looked at.  With shallow nesting (config 3: 10 % short indels) that is ~99.9 % of the
+  // probes; a warp whose 32 probes are all of that kind writes its pairs 32 consecutive slots at a time straight from the
+  // row column (the scheme of overlap_emit_flat_kernel) and skips the walk and the staging window.
+#ifndef PBGPU_EMIT_NOFLAT
+  {
+    bool clean = false;
+    const uint32_t first = hi - cnt;
+    if (cnt && !generic) {
+      const int32_t cc = BINNED ? c : pc[i];
+      clean = first <= (uint32_t)__ldg(ix.seg + cc) || (long long)__ldg(ix.pmax + first - 1) <= thr;
+    }
+    if (__all_sync(0xffffffffu, cnt == 0 || clean)) {
+      uint32_t incl_f = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl_f, d); if (lane >= d) incl_f += o; }
+      const uint32_t total = __shfl_sync(0xffffffffu, incl_f, 31);
+      const uint32_t excl_f = incl_f - cnt;
+      for (uint32_t j0 = 0; j0 < total; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        int p = 0;
+#pragma unroll
+        for (int step = 16; step; step >>= 1) {
+          const int cand = p + step;
+          const uint32_t e = __shfl_sync(0xffffffffu, excl_f, cand & 31);
+          if (e <= j) p = cand;  // the last lane whose exclusive offset is <= j owns slot j (cand <= 31 always)
+        }
+        const uint32_t e_p = __shfl_sync(0xffffffffu, excl_f, p);
+        const uint32_t f_p = __shfl_sync(0xffffffffu, first, p);
+        const uint32_t id_p = __shfl_sync(0xffffffffu, pid, p);
+        const unsigned long long pos_p = __shfl_sync(0xffffffffu, pos, p);
+        if (j < total) {
+          const unsigned long long g = pos_p + (j - e_p);
+          out_probe[g] = id_p;
+          out_build[g] = __ldg(ix.row + (f_p + (j - e_p)));
+        }
+      }
+      return;
+    }
+  }
+#endif
   // the warp's window holds the pairs of the lanes that go through the staging buffer
   const uint32_t mine = (cnt && !heavy) ? cnt : 0u;
   uint32_t incl = mine;
