@@ -24,6 +24,7 @@
 #include <condition_variable>
 #include <functional>
 #include <memory>
+#include <future>
 #include <mutex>
 #include <string>
 #include <string_view>
@@ -1193,11 +1194,18 @@ struct IndexSide {
   int32_t n_contigs = 0;
   int64_t m = 0;
   int32_t *dc_x = nullptr, *ds_x = nullptr, *de_x = nullptr;
+  int32_t *hc_x = nullptr, *hs_x = nullptr, *he_x = nullptr;  // encoded keys in pinned staging (until the upload has run)
   pbgpu_index *ix = nullptr;
+  // pbgpu_range_op runs the upload + index build on a helper thread while the calling thread encodes the iterated table
+  // (the build has host round trips of its own: on the calling thread it would keep the encoder waiting); index_ready()
+  // joins it.  The task holds a raw pointer to this object: the destructor waits for it first.
+  std::future<int> pending;
+  std::string pending_err;
   IndexSide() { stage_wc.wc = true; }
   IndexSide(const IndexSide &) = delete;
   IndexSide &operator=(const IndexSide &) = delete;
   ~IndexSide() {
+    if (pending.valid()) pending.wait();
     int prev = -1;
     if (device >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != device) cudaSetDevice(device); else prev = -1;
     if (s) cudaStreamSynchronize(s);
@@ -1724,7 +1732,8 @@ int upload_payload(const Table &t, int which, Sink &sk, CallState &cs) {
 }
 
 // Upload + index the indexed side.  `side`: what to call it in error messages.
-int prepare_index(const PbRangeOptions &o, std::shared_ptr<Table> IXt, const char *side, std::shared_ptr<IndexSide> *out) {
+// Indexed side, phase A (calling thread; uses the host pool): stream, staging, key encoding + the contig dictionary.
+int prepare_index_encode(const PbRangeOptions &o, std::shared_ptr<Table> IXt, const char *side, std::shared_ptr<IndexSide> *out) {
   auto xs = std::make_shared<IndexSide>();
   xs->tab = IXt;
   Table *IX = IXt.get();
@@ -1738,26 +1747,48 @@ int prepare_index(const PbRangeOptions &o, std::shared_ptr<Table> IXt, const cha
   BR_CUDA(cudaGetDevice(&xs->device));
   BR_CUDA(cudaStreamCreateWithFlags(&xs->s, cudaStreamNonBlocking));
   BR_CUDA(cudaEventCreateWithFlags(&xs->ready, cudaEventDisableTiming));
-  cudaStream_t s = xs->s;
-  xs->dev.s = s;
-  int32_t *hc_x = xs->stage_wc.get<int32_t>(m), *hs_x = xs->stage_wc.get<int32_t>(m), *he_x = xs->stage_wc.get<int32_t>(m);
-  if (!hc_x || !hs_x || !he_x) return set_error(PBGPU_ENOMEM, "pinned staging allocation failed");
+  xs->dev.s = xs->s;
+  xs->hc_x = xs->stage_wc.get<int32_t>(m); xs->hs_x = xs->stage_wc.get<int32_t>(m); xs->he_x = xs->stage_wc.get<int32_t>(m);
+  if (!xs->hc_x || !xs->hs_x || !xs->he_x) return set_error(PBGPU_ENOMEM, "pinned staging allocation failed");
   xs->dc_x = xs->dev.get<int32_t>(m); xs->ds_x = xs->dev.get<int32_t>(m); xs->de_x = xs->dev.get<int32_t>(m);
   if (!xs->dc_x || !xs->ds_x || !xs->de_x) return set_error(PBGPU_ENOMEM, "device allocation failed");
   // Contigs that only occur on the iterated side get codes >= n_contigs of the index and are treated as null keys by
   // the kernels (they cannot match anything anyway).
-  BR_TRY(encode_keys(*IX, side, xs->dict, hc_x, hs_x, he_x));
+  BR_TRY(encode_keys(*IX, side, xs->dict, xs->hc_x, xs->hs_x, xs->he_x));
   xs->n_contigs = (int32_t)xs->dict.map.size();
-  tr.lap_drained("  encode indexed side", s);
-  BR_CUDA(cudaMemcpyAsync(xs->dc_x, hc_x, 4 * (size_t)m, cudaMemcpyHostToDevice, s));
-  BR_CUDA(cudaMemcpyAsync(xs->ds_x, hs_x, 4 * (size_t)m, cudaMemcpyHostToDevice, s));
-  BR_CUDA(cudaMemcpyAsync(xs->de_x, he_x, 4 * (size_t)m, cudaMemcpyHostToDevice, s));
-  tr.lap_drained("  H2D indexed side", s);
-  tr.lap("encode + H2D indexed side");
+  tr.lap("encode indexed side");
+  *out = xs;
+  return PBGPU_OK;
+}
+// Phase B (any thread; no pool use): upload, index build, `ready` recorded behind it on the side's stream.
+int prepare_index_build(IndexSide *xs) {
+  Trace tr;
+  int prev_dev = -1;
+  BR_CUDA(cudaGetDevice(&prev_dev));
+  if (xs->device != prev_dev) BR_CUDA(cudaSetDevice(xs->device)); else prev_dev = -1;
+  struct DevRestore { int d; ~DevRestore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev};
+  cudaStream_t s = xs->s;
+  const int64_t m = xs->m;
+  BR_CUDA(cudaMemcpyAsync(xs->dc_x, xs->hc_x, 4 * (size_t)m, cudaMemcpyHostToDevice, s));
+  BR_CUDA(cudaMemcpyAsync(xs->ds_x, xs->hs_x, 4 * (size_t)m, cudaMemcpyHostToDevice, s));
+  BR_CUDA(cudaMemcpyAsync(xs->de_x, xs->he_x, 4 * (size_t)m, cudaMemcpyHostToDevice, s));
   BR_TRY(pbgpu_index_build(xs->dc_x, xs->ds_x, xs->de_x, m, xs->n_contigs, s, &xs->ix));
   BR_CUDA(cudaEventRecord(xs->ready, s));
-  tr.lap("index build");
+  tr.lap("H2D indexed side + index build");
+  return PBGPU_OK;
+}
+int prepare_index(const PbRangeOptions &o, std::shared_ptr<Table> IXt, const char *side, std::shared_ptr<IndexSide> *out) {
+  std::shared_ptr<IndexSide> xs;
+  BR_TRY(prepare_index_encode(o, IXt, side, &xs));
+  BR_TRY(prepare_index_build(xs.get()));
   *out = xs;
+  return PBGPU_OK;
+}
+// joins the helper thread of pbgpu_range_op (no-op for sessions): afterwards xs->ix is valid and `ready` is recorded
+int index_ready(IndexSide &xs) {
+  if (!xs.pending.valid()) return PBGPU_OK;
+  const int rc = xs.pending.get();
+  if (rc != PBGPU_OK) return set_error(rc, "%s", xs.pending_err.c_str());
   return PBGPU_OK;
 }
 
@@ -1771,7 +1802,17 @@ int run(Table *L, Table *R, OutStream *os) {
   //   count/coverage: index = left (s1), iterate = right (s2), rows of right returned   operation.rs:316-340
   const bool iter_is_left = (o.range_op == PBGPU_OP_OVERLAP || o.range_op == PBGPU_OP_NEAREST);
   std::shared_ptr<IndexSide> xs;
-  BR_TRY(prepare_index(o, iter_is_left ? os->right : os->left, iter_is_left ? "right" : "left", &xs));
+  BR_TRY(prepare_index_encode(o, iter_is_left ? os->right : os->left, iter_is_left ? "right" : "left", &xs));
+  static const bool async_build = [] { const char *e = getenv("PBGPU_ASYNC_BUILD"); return !(e && e[0] == '0'); }();
+  // a fresh thread allocates its own host mailbox and stage events (~0.3 ms): only worth it when the build it hides is longer
+  if (async_build && os->left->rows + os->right->rows >= (int64_t)4 << 20) {
+    IndexSide *px = xs.get();
+    xs->pending = std::async(std::launch::async, [px]() -> int {
+      const int rc = prepare_index_build(px);
+      if (rc != PBGPU_OK) px->pending_err = pbgpu::g_err;  // the message lives in this thread's buffer
+      return rc;
+    });
+  } else BR_TRY(prepare_index_build(xs.get()));
   return run_iter(L, R, os, xs);
 }
 
@@ -1798,7 +1839,6 @@ int run_iter(Table *L, Table *R, OutStream *os, std::shared_ptr<IndexSide> xs) {
   cs.device = xs->device;
   BR_CUDA(cudaStreamCreateWithFlags(&cs.s, cudaStreamNonBlocking));
   cudaStream_t s = cs.s;
-  BR_CUDA(cudaStreamWaitEvent(s, xs->ready, 0));  // uploads and the index build ran on the indexed side's stream
   cs.dev.s = s;
   DevBufs &dev = cs.dev;
   int32_t *dc_x = xs->dc_x, *ds_x = xs->ds_x, *de_x = xs->de_x;
@@ -1807,8 +1847,18 @@ int run_iter(Table *L, Table *R, OutStream *os, std::shared_ptr<IndexSide> xs) {
   if (!dc_i || !ds_i || !de_i) return set_error(PBGPU_ENOMEM, "device allocation failed");
   tr.lap_drained("  stream + device allocations", s);
   const int32_t n_contigs = xs->n_contigs;
-  pbgpu_index *ix = xs->ix;
-  cs.ix = ix;
+  // The index may still be under construction on the helper thread of pbgpu_range_op: encoding and uploading the iterated
+  // table needs only the dictionary.  need_index() joins the build and orders this call's stream behind it (the event must
+  // have been RECORDED before a wait on it is enqueued, hence join first).
+  pbgpu_index *ix = nullptr;
+  auto need_index = [&]() -> int {
+    if (ix) return PBGPU_OK;
+    BR_TRY(index_ready(*xs));
+    BR_CUDA(cudaStreamWaitEvent(s, xs->ready, 0));  // uploads and the index build ran on the indexed side's stream
+    ix = xs->ix;
+    cs.ix = ix;
+    return PBGPU_OK;
+  };
   // iterated side in slices: the DMA of slice k runs while the host encodes slice k+1.  With at most 255 indexed
   // contigs the contig codes travel as bytes and are widened on the device.
   // count_overlaps / coverage are row-local, so they join the pipeline: the kernel of slice k and the D2H of its
@@ -1851,6 +1901,7 @@ int run_iter(Table *L, Table *R, OutStream *os, std::shared_ptr<IndexSide> xs) {
       cudaMemcpyAsync(ds_i + lo, hs_i + lo, 4 * (size_t)(hi - lo), cudaMemcpyHostToDevice, s);
       cudaMemcpyAsync(de_i + lo, he_i + lo, 4 * (size_t)(hi - lo), cudaMemcpyHostToDevice, s);
       if (row_local) {
+        BR_TRY(need_index());
         slices.push_back({lo, hi, nullptr, nullptr});
         SliceOut &so = slices.back();
         BR_CUDA(cudaEventCreateWithFlags(&so.up, cudaEventDisableTiming));
@@ -1870,6 +1921,7 @@ int run_iter(Table *L, Table *R, OutStream *os, std::shared_ptr<IndexSide> xs) {
     if (cudaGetLastError() != cudaSuccess) return set_error(PBGPU_ECUDA, "H2D copy of the iterated table failed");
   }
   tr.lap("encode + H2D iterated side");
+  BR_TRY(need_index());
   const uint64_t limit = o.limit;
 
   if (row_local) {

@@ -28,7 +28,10 @@
 
 namespace pbgpu {
 
-constexpr int kBinThreads = 512, kBinItems = 8, kBinTile = kBinThreads * kBinItems, kBinRadix = 256, kBinWarps = kBinThreads / 32;
+#ifndef PBGPU_BIN_THREADS
+#define PBGPU_BIN_THREADS 512
+#endif
+constexpr int kBinThreads = PBGPU_BIN_THREADS, kBinItems = 8, kBinTile = kBinThreads * kBinItems, kBinRadix = 256, kBinWarps = kBinThreads / 32;
 
 __device__ __forceinline__ int4 make_probe_rec(const IndexView &ix, int32_t c, int32_t s, int32_t e, uint32_t row, bool strict) {
   if (c < 0 || c >= ix.n_contigs) return make_int4(0, 0, (int)row, -1);
@@ -81,7 +84,7 @@ __global__ void __launch_bounds__(512) bin_hist_kernel(IndexView ix, const int32
 // One stable radix pass over the probes (see radix_sort.cuh: rs_onesweep_kernel for the scheme).  Dynamic shared memory:
 // the tile's records in bin order (64 KB).  WRITE_POS: also pos[row] = destination of the row (count_overlaps un-binning).
 template <bool WRITE_POS, int OCC>
-__global__ void __launch_bounds__(kBinThreads, OCC) bin_partition_kernel(IndexView ix, const int32_t *__restrict__ pc,
+__global__ void __launch_bounds__(kBinThreads, OCC * (512 / kBinThreads)) bin_partition_kernel(IndexView ix, const int32_t *__restrict__ pc,
                                                                        const int32_t *__restrict__ ps, const int32_t *__restrict__ pe,
                                                                        const uint32_t *__restrict__ ids /*NULL: the row*/,
                                                                        int64_t n, int bin_shift, int strict,

@@ -15,7 +15,10 @@
 
 namespace pbgpu {
 
-constexpr int kRsThreads = 512;
+#ifndef PBGPU_RS_THREADS
+#define PBGPU_RS_THREADS 512
+#endif
+constexpr int kRsThreads = PBGPU_RS_THREADS;
 constexpr int kRsWarps = kRsThreads / 32;
 constexpr int kRsItems = 8;  // per thread
 constexpr int kRsTile = kRsThreads * kRsItems;
@@ -348,7 +351,7 @@ __device__ __forceinline__ void rs_onesweep_tile(RsShared &sm, const uint64_t *_
 }
 
 template <typename V, int OCC, int W>
-__global__ void __launch_bounds__(kRsThreads, OCC) rs_onesweep_kernel(const uint64_t *__restrict__ keys_in,
+__global__ void __launch_bounds__(kRsThreads, OCC * (512 / kRsThreads)) rs_onesweep_kernel(const uint64_t *__restrict__ keys_in,
                                                                     const V *__restrict__ vals_in,
                                                                     uint64_t *__restrict__ keys_out,
                                                                     V *__restrict__ vals_out, int64_t n, int shift,
