@@ -1880,6 +1880,21 @@ int run_iter(Table *L, Table *R, OutStream *os, std::shared_ptr<IndexSide> xs) {
     if (is_cov) { d_cov = dev.get<int64_t>(n); h_cov = cov_dma ? fin64 : stage.get<int64_t>(n); if (!d_cov || !h_cov) return set_error(PBGPU_ENOMEM, "allocation failed"); }
     else { d_cnt = dev.get<uint32_t>(n); h_cnt = stage.get<uint32_t>(n); if (!d_cnt || !h_cnt) return set_error(PBGPU_ENOMEM, "allocation failed"); }
   }
+  size_t launched = 0;  // row-local operations: slices whose kernel + D2H have been enqueued
+  auto launch_slice = [&](SliceOut &so) -> int {
+    const int64_t lo = so.lo, hi = so.hi;
+    BR_CUDA(cudaStreamWaitEvent(cs.s2, xs->ready, 0));  // the index build (its event is recorded: need_index() ran)
+    BR_CUDA(cudaStreamWaitEvent(cs.s2, so.up, 0));
+    if (is_cov) {
+      BR_TRY(pbgpu_coverage(ix, dc_i + lo, ds_i + lo, de_i + lo, hi - lo, o.filter_op, d_cov + lo, cs.s2));
+      BR_CUDA(cudaMemcpyAsync(h_cov + lo, d_cov + lo, 8 * (size_t)(hi - lo), cudaMemcpyDeviceToHost, cs.s2));
+    } else {
+      BR_TRY(pbgpu::count_overlaps_u32(ix, dc_i + lo, ds_i + lo, de_i + lo, hi - lo, o.filter_op, d_cnt + lo, cs.s2));
+      BR_CUDA(cudaMemcpyAsync(h_cnt + lo, d_cnt + lo, 4 * (size_t)(hi - lo), cudaMemcpyDeviceToHost, cs.s2));
+    }
+    BR_CUDA(cudaEventRecord(so.down, cs.s2));
+    return PBGPU_OK;
+  };
   {
     const bool narrow = n_contigs <= 255;
     int32_t *hc_i = narrow ? nullptr : stage_wc.get<int32_t>(n);
@@ -1901,21 +1916,19 @@ int run_iter(Table *L, Table *R, OutStream *os, std::shared_ptr<IndexSide> xs) {
       cudaMemcpyAsync(ds_i + lo, hs_i + lo, 4 * (size_t)(hi - lo), cudaMemcpyHostToDevice, s);
       cudaMemcpyAsync(de_i + lo, he_i + lo, 4 * (size_t)(hi - lo), cudaMemcpyHostToDevice, s);
       if (row_local) {
-        BR_TRY(need_index());
         slices.push_back({lo, hi, nullptr, nullptr});
         SliceOut &so = slices.back();
         BR_CUDA(cudaEventCreateWithFlags(&so.up, cudaEventDisableTiming));
         BR_CUDA(cudaEventCreateWithFlags(&so.down, cudaEventDisableTiming));
-        BR_CUDA(cudaEventRecord(so.up, s));  // also orders the index build (enqueued on s before) ahead of the kernel
-        BR_CUDA(cudaStreamWaitEvent(cs.s2, so.up, 0));
-        if (is_cov) {
-          BR_TRY(pbgpu_coverage(ix, dc_i + lo, ds_i + lo, de_i + lo, hi - lo, o.filter_op, d_cov + lo, cs.s2));
-          BR_CUDA(cudaMemcpyAsync(h_cov + lo, d_cov + lo, 8 * (size_t)(hi - lo), cudaMemcpyDeviceToHost, cs.s2));
-        } else {
-          BR_TRY(pbgpu::count_overlaps_u32(ix, dc_i + lo, ds_i + lo, de_i + lo, hi - lo, o.filter_op, d_cnt + lo, cs.s2));
-          BR_CUDA(cudaMemcpyAsync(h_cnt + lo, d_cnt + lo, 4 * (size_t)(hi - lo), cudaMemcpyDeviceToHost, cs.s2));
+        BR_CUDA(cudaEventRecord(so.up, s));
+        // kernels of the slices uploaded so far start as soon as the index is there; while it is still being built on the
+        // helper thread the loop keeps encoding and uploading (the last slice waits for it)
+        const bool last = hi >= n;
+        const bool ready = !xs->pending.valid() || xs->pending.wait_for(std::chrono::seconds(0)) == std::future_status::ready;
+        if (ready || last) {
+          BR_TRY(need_index());
+          for (; launched < slices.size(); ++launched) BR_TRY(launch_slice(slices[launched]));
         }
-        BR_CUDA(cudaEventRecord(so.down, cs.s2));
       }
     }
     if (cudaGetLastError() != cudaSuccess) return set_error(PBGPU_ECUDA, "H2D copy of the iterated table failed");

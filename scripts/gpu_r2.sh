@@ -32,6 +32,8 @@ ab2)
     timeout 600 env $vv python bench.py --steps 8 --warmup 3 --skip-e2e --no-cpu-baseline --skip-parity > $O/${TAG}_ab_${n}.json 2> $O/${TAG}_ab_${n}.err
     echo "-- $v"; python scripts/bench_brief.py $O/${TAG}_ab_${n}.json || tail -5 $O/${TAG}_ab_${n}.err
   done;;
+e2etrace)
+  echo "== e2e trace (config 3 through the public API)"; timeout 600 python scripts/e2e_trace3.py > /dev/null 2> $O/${TAG}_e2e_trace3.txt; echo rc=$?; grep -v "^\[pbgpu\]   \|get_next" $O/${TAG}_e2e_trace3.txt | tail -16;;
 share8)
   PB_WORLD=8 PB_RANK=0 timeout 300 python tests/tools/rank_share.py > $O/${TAG}_rank_share_w8.json 2> $O/${TAG}_rank_share_w8.err; echo rc=$?; cat $O/${TAG}_rank_share_w8.json; tail -3 $O/${TAG}_rank_share_w8.err;;
 ab)
