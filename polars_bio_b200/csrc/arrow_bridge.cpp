@@ -533,6 +533,45 @@ inline void nt_fill32(int32_t *dst, int32_t v, size_t n) { for (size_t i = 0; i 
 inline void nt_fence() {}
 #endif
 
+// Collision-free table for names of at most 7 bytes (key = the bytes as a little-endian word | length << 56; code >= 0).
+// slot = (key * mult) >> 54 over 1024 entries; when a new key lands on an occupied slot the multiplier is replaced until
+// all keys sit alone (a handful of tries for the few dozen contig names of a genome; beyond kMaxKeys names new ones simply
+// stay on the caller's slow path).  A lookup is then one multiply, one load and a compare that virtually always succeeds.
+struct ShortNames {
+  static constexpr int32_t kMiss = INT32_MIN;
+  static constexpr int kBits = 10, kMaxKeys = 56;
+  struct Ent { uint64_t key; int32_t code; };
+  Ent e[1 << kBits];
+  uint64_t mult = 0x9E3779B97F4A7C15ull;
+  uint64_t keys[kMaxKeys];
+  int32_t codes[kMaxKeys];
+  int n = 0;
+  ShortNames() { for (auto &x : e) { x.key = ~0ull; x.code = kMiss; } }
+  static inline uint64_t mask(size_t len) { return len >= 8 ? ~0ull : ((1ull << (8 * len)) - 1ull); }
+  inline unsigned slot(uint64_t key) const { return (unsigned)((key * mult) >> (64 - kBits)); }
+  inline int32_t find(uint64_t key) const { const Ent &x = e[slot(key)]; return x.key == key ? x.code : kMiss; }
+  void insert(uint64_t key, int32_t code) {
+    if (code < 0 || n >= kMaxKeys) return;
+    keys[n] = key; codes[n] = code; ++n;
+    Ent &x = e[slot(key)];
+    if (x.key == ~0ull) { x.key = key; x.code = code; return; }
+    for (int tries = 0; tries < 4096; ++tries) {  // occupied: clear what was placed, try another multiplier
+      for (int k = 0; k < n; ++k) { Ent &y = e[slot(keys[k])]; y.key = ~0ull; y.code = kMiss; }
+      mult = (mult * 6364136223846793005ull + 1442695040888963407ull) | 1ull;
+      bool ok = true;
+      int placed = 0;
+      for (; placed < n && ok; ++placed) {
+        Ent &y = e[slot(keys[placed])];
+        if (y.key != ~0ull) ok = false; else { y.key = keys[placed]; y.code = codes[placed]; }
+      }
+      if (ok) return;
+      for (int k = 0; k < placed - 1; ++k) { Ent &y = e[slot(keys[k])]; y.key = ~0ull; y.code = kMiss; }  // undo this try
+    }
+    --n;  // no luck (cannot happen in practice): leave the table without the new key
+    for (int k = 0; k < n; ++k) { Ent &y = e[slot(keys[k])]; if (y.key == ~0ull) { y.key = keys[k]; y.code = codes[k]; } }
+  }
+};
+
 int encode_keys(const Table &t, const char *side, ContigDict &dict, int32_t *code, int32_t *st, int32_t *en,
                 int64_t row_lo = 0, int64_t row_hi = INT64_MAX, uint8_t *code8 = nullptr) {
   const ArrowSchema *fc = t.schema.children[t.key[0]];
@@ -587,6 +626,8 @@ int encode_keys(const Table &t, const char *side, ContigDict &dict, int32_t *cod
       if (sk == StrKind::Utf8) {
         const int32_t *o = (const int32_t *)ac->buffers[1] + oc;
         const int32_t L = o[a + 1] - o[a];
+        if (o[a + 2] - o[a + 1] != L || memcmp((const char *)ac->buffers[2] + o[a], (const char *)ac->buffers[2] + o[a + 1], (size_t)L) != 0)
+          return false;  // the first two rows differ (mixed contigs): no need to look at the other 1022
         int bad = 0;
         for (int64_t i = a + 1; i < b; ++i) bad |= (o[i + 1] - o[i]) ^ L;
         if (bad) return false;
@@ -596,6 +637,8 @@ int encode_keys(const Table &t, const char *side, ContigDict &dict, int32_t *cod
       if (sk == StrKind::LargeUtf8) {
         const int64_t *o = (const int64_t *)ac->buffers[1] + oc;
         const int64_t L = o[a + 1] - o[a];
+        if (o[a + 2] - o[a + 1] != L || memcmp((const char *)ac->buffers[2] + o[a], (const char *)ac->buffers[2] + o[a + 1], (size_t)L) != 0)
+          return false;
         int64_t bad = 0;
         for (int64_t i = a + 1; i < b; ++i) bad |= (o[i + 1] - o[i]) ^ L;
         if (bad) return false;
@@ -615,11 +658,12 @@ int encode_keys(const Table &t, const char *side, ContigDict &dict, int32_t *cod
     };
     // Short names (<= 7 bytes: "chr1" .. "chrUn", "1" .. "MT") in arbitrary order -- rows of all contigs mixed, the shape
     // of BASELINE config 3 -- would pay a std::hash + compare per row (~40 ns); instead the string is read as ONE 64-bit
-    // word (length in the top byte) and looked up in a 128-entry direct-mapped table: ~3 ns per row.  The 8-byte read must
-    // stay inside the data buffer, so the last few bytes of it take the ordinary path.
-    struct SmallEnt { uint64_t key; int32_t code; };
-    SmallEnt small[128];
-    for (auto &e : small) { e.key = ~0ull; e.code = -1; }
+    // word (length in the top byte) and looked up in a COLLISION-FREE multiplicative hash table (ShortNames below): one
+    // multiply, one load, one always-taken compare per row.  (Round 2's first version was a 128-entry direct-mapped table:
+    // two of the 24 human contig names shared a slot and evicted each other on every alternation -- 20 % of the rows took
+    // the slow path, and the unpredictable hit / miss branch cost more than the lookup: 25 ns per row; now ~4.5.)  The
+    // 8-byte read must stay inside the data buffer, so the last few bytes of it take the ordinary path.
+    ShortNames small;
     const char *data_end = nullptr;
     if (!is_dict && (sk == StrKind::Utf8 || sk == StrKind::LargeUtf8) && ac->buffers[2]) {
       const int64_t last = ac->offset + ac->length;  // offsets[last] = end of the data this array can reference
@@ -631,11 +675,11 @@ int encode_keys(const Table &t, const char *side, ContigDict &dict, int32_t *cod
       if (L <= 7 && data_end && sv.data() + 8 <= data_end) {
         uint64_t w;
         memcpy(&w, sv.data(), 8);
-        const uint64_t key = (w & ((1ull << (8 * L)) - 1ull)) | ((uint64_t)L << 56);
-        SmallEnt &e = small[(key * 0x9E3779B97F4A7C15ull) >> 57];
-        if (e.key == key) return e.code;
+        const uint64_t key = (w & ShortNames::mask(L)) | ((uint64_t)L << 56);
+        const int32_t hit = small.find(key);
+        if (__builtin_expect(hit != ShortNames::kMiss, 1)) return hit;
         const int32_t c = lookup_slow(sv);
-        e.key = key; e.code = c;
+        small.insert(key, c);
         return c;
       }
       return lookup_slow(sv);
@@ -653,6 +697,32 @@ int encode_keys(const Table &t, const char *side, ContigDict &dict, int32_t *cod
       // row by row into block-local arrays (they stay in this core's cache), streamed out to staging afterwards
       int32_t tc[kRun], ts[kRun], te[kRun];
       uint8_t tc8[kRun];
+      if (run_ok) {  // the common shape (utf8 / large_utf8 contig without nulls, int32 positions already copied): a loop
+        auto tight = [&](auto *o) {  // with every pointer hoisted and nothing but the short-name lookup in it
+          const char *d = (const char *)ac->buffers[2];
+          for (int64_t i = blk; i < bhi; ++i) {
+            const int64_t off = (int64_t)o[i];
+            const size_t L = (size_t)((int64_t)o[i + 1] - off);
+            const char *p = d + off;
+            int32_t c;
+            if (L <= 7 && p + 8 <= data_end) {
+              uint64_t w;
+              memcpy(&w, p, 8);
+              const uint64_t key = (w & ShortNames::mask(L)) | ((uint64_t)L << 56);
+              c = small.find(key);
+              if (__builtin_expect(c == ShortNames::kMiss, 0)) { c = lookup_slow(std::string_view(p, L)); small.insert(key, c); }
+            } else c = lookup_slow(std::string_view(p, L));
+            tc[i - blk] = c;
+          }
+        };
+        if (sk == StrKind::Utf8) tight((const int32_t *)ac->buffers[1] + oc); else tight((const int64_t *)ac->buffers[1] + oc);
+        const size_t nb = (size_t)(bhi - blk);
+        if (code8) {
+          for (size_t k = 0; k < nb; ++k) tc8[k] = (uint8_t)(((uint32_t)tc[k] >= 255u) ? 255 : tc[k]);  // negative or >= 255 -> 255
+          nt_copy(code8 + g0 + blk, tc8, nb);
+        } else nt_copy(code + g0 + blk, tc, 4 * nb);
+        continue;
+      }
       for (int64_t i = blk; i < bhi; ++i) {
         const int64_t li = i - blk;
         int32_t c;

@@ -335,3 +335,25 @@ def test_unary_entry_errors(lib):
             assert s1.release is None  # the input was moved (released) although the call failed
     finally:
         lib.dbg_streams_ok(0)
+
+
+@pytest.mark.parametrize("n_names", [3, 24, 56, 57, 400])
+def test_encoder_codes_are_consistent_for_many_short_and_long_names(lib, n_names):
+    """The short-name table of the key encoder (collision-free multiplicative hash, at most 56 names; others take the slow
+    path): every row of a name gets the same code, different names get different codes, whatever the number of names,
+    their lengths (1 .. 12 bytes) and their order."""
+    rng = np.random.default_rng(n_names)
+    names = sorted({("c" * int(rng.integers(0, 5))) + str(int(rng.integers(0, 10**int(rng.integers(1, 8))))) for _ in range(3 * n_names)})[:n_names]
+    n = 40_000
+    pick = rng.integers(0, len(names), n)
+    for ctype in (pa.string(), pa.large_string()):
+        t = pa.table({"chrom": pa.array([names[k] for k in pick], type=ctype), "start": pa.array(np.arange(n, dtype=np.int32)),
+                      "end": pa.array(np.arange(n, dtype=np.int32) + 5)})
+        _, keys = _roundtrip(lib, t, [0])
+        codes = keys[:, 0]
+        assert codes.min() >= 0
+        first = {}
+        for k, c in zip(pick.tolist(), codes.tolist()):
+            assert first.setdefault(k, c) == c
+        assert len(set(first.values())) == len(first)
+        assert np.array_equal(keys[:, 1], np.arange(n)) and np.array_equal(keys[:, 2], np.arange(n) + 5)
