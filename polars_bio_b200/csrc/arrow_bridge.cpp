@@ -50,6 +50,7 @@ int gather_str_plan(const long long *d_off, const uint8_t *d_valid, const uint32
 int gather_str_bytes(const long long *d_off, const char *d_chars, const uint32_t *d_rows, int64_t n, const unsigned long long *d_pos,
                      const unsigned long long *d_total, void *d_out_off, int large, char *d_out_chars, void *stream);
 int rebase_offsets(const void *d_in, int large, int64_t len, long long base, long long *d_out, void *stream);
+void release_thread_state();  // pbgpu.cu: host mailbox + stage events of the calling (helper) thread
 int dev_alloc(void **p, size_t bytes, cudaStream_t s);  // stream-ordered device blocks through pbgpu.cu's block cache
 void dev_free(void *p, cudaStream_t s);
 }  // namespace pbgpu
@@ -1880,6 +1881,7 @@ int run(Table *L, Table *R, OutStream *os) {
     xs->pending = std::async(std::launch::async, [px]() -> int {
       const int rc = prepare_index_build(px);
       if (rc != PBGPU_OK) px->pending_err = pbgpu::g_err;  // the message lives in this thread's buffer
+      pbgpu::release_thread_state();
       return rc;
     });
   } else BR_TRY(prepare_index_build(xs.get()));

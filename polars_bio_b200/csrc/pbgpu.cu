@@ -270,6 +270,21 @@ int mailbox_wait(const MailboxSlot &slot, int n_words, unsigned long long *out, 
   for (int i = 0; i < n_words; ++i) out[i] = mb.h[i];
   return PBGPU_OK;
 }
+// Per-thread state (host mailbox, stage events) of a short-lived helper thread, released before it exits: the Arrow level
+// runs index builds on one (arrow_bridge.cpp); long-lived caller threads keep theirs for the life of the process.
+void release_thread_state() {
+  for (int i = 0; i < EV_N; ++i) {
+    if (g_ev.ev[i]) cudaEventDestroy(g_ev.ev[i]);
+    g_ev.ev[i] = nullptr;
+    g_ev.set[i] = false;
+  }
+  g_ev.device = -1;
+  Mailbox &mb = g_mailbox;
+  if (mb.h) cudaFreeHost((void *)mb.h);
+  mb.h = nullptr;
+  mb.d = nullptr;
+  mb.tried = false;
+}
 // copies n_words (<= 15) 64-bit words from device memory to `out`; returns after they have arrived
 int fetch_words(const void *d_src, int n_words, unsigned long long *out, cudaStream_t s) {
   const MailboxSlot slot = n_words <= kMailboxWords - 1 ? mailbox_open() : MailboxSlot{nullptr, 0};
