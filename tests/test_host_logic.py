@@ -116,3 +116,18 @@ def test_no_gpu_fails_loudly():
         pytest.skip("GPU present")
     with pytest.raises(pb._native.PbgpuError):  # no silent CPU fallback
         pb.overlap(_df(True), _df(True), output_type="pandas.DataFrame")
+
+
+def test_bench_roofline_names_the_longest_single_launch():
+    """bench.stage_roofline: with partitioned probes count_overlaps / pass 1 are four launches each, so the dominant KERNEL is
+    pass 2 even when a multi-launch stage takes longer; without a partition every stage is one kernel and the longest wins."""
+    import bench
+
+    n, m, pairs = 100_000_000, 90_000_000, 438_606_732
+    km = {"partition_sort_ns": 6.7, "count_ns": 2.5, "scan_ns": 0.02, "emit_ns": 2.3, "count_overlaps_ns": 2.9, "bin_ns": 1.4, "unbin_ns": 0.4}
+    r = bench.stage_roofline(n, m, pairs, km, 6534.8, "measured")
+    assert "emit" in r["kernel"] and abs(r["frac"] - (12.0 * (n + m) + 8.0 * pairs) / 2.3e-3 / 1e9 / 6534.8) < 1e-9
+    assert set(r["all_stages"]) >= {"count_overlaps (all kernels of the call)", "overlap pass 2 (emit)"}
+    km2 = dict(km, bin_ns=0.0, unbin_ns=0.0, count_overlaps_ns=0.066, count_ns=0.071, emit_ns=0.058)
+    r2 = bench.stage_roofline(10_000_000, 1_000_000, 6_024_485, km2, 6534.8, "measured")
+    assert "pass 1" in r2["kernel"]
