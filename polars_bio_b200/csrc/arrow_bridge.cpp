@@ -1876,7 +1876,8 @@ int run(Table *L, Table *R, OutStream *os) {
   BR_TRY(prepare_index_encode(o, iter_is_left ? os->right : os->left, iter_is_left ? "right" : "left", &xs));
   static const bool async_build = [] { const char *e = getenv("PBGPU_ASYNC_BUILD"); return !(e && e[0] == '0'); }();
   // a fresh thread allocates its own host mailbox and stage events (~0.3 ms): only worth it when the build it hides is longer
-  if (async_build && os->left->rows + os->right->rows >= (int64_t)4 << 20) {
+  static const int64_t async_min_rows = [] { const char *e = getenv("PBGPU_ASYNC_MIN_ROWS"); return e ? (int64_t)atoll(e) : (int64_t)4 << 20; }();
+  if (async_build && os->left->rows + os->right->rows >= async_min_rows) {
     IndexSide *px = xs.get();
     xs->pending = std::async(std::launch::async, [px]() -> int {
       const int rc = prepare_index_build(px);

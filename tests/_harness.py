@@ -1,7 +1,8 @@
 """Builds the CPU harness of the Arrow-level host code once per test session (TEST INFRASTRUCTURE): the product source
 polars_bio_b200/csrc/arrow_bridge.cpp compiled against tests/tools/bridge_harness/stub_cuda.h with harness_tail.inc
-appended.  The binary operations' device calls are stubs that fail; the unary sweeps have plain CPU doubles, so
-pbgpu_range_op runs end to end for merge / cluster / complement / subtract (after dbg_streams_ok(1))."""
+appended.  Most device calls of the binary operations are stubs that fail; the unary sweeps and the index build +
+count_overlaps have plain CPU doubles, so pbgpu_range_op runs end to end for merge / cluster / complement / subtract and
+count_overlaps (after dbg_streams_ok(1))."""
 import ctypes
 import os
 import subprocess
@@ -29,6 +30,7 @@ def build():
                         "-I", os.path.join(ROOT, "polars_bio_b200", "csrc"), "-o", so, cpp, "-lpthread"],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
+    os.environ.setdefault("PBGPU_ASYNC_MIN_ROWS", "0")  # the helper-thread index build also for the small tables of these tests
     L = ctypes.CDLL(so)
     L.dbg_roundtrip.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64,
                                 ctypes.c_void_p, ctypes.c_void_p]

@@ -357,3 +357,44 @@ def test_encoder_codes_are_consistent_for_many_short_and_long_names(lib, n_names
             assert first.setdefault(k, c) == c
         assert len(set(first.values())) == len(first)
         assert np.array_equal(keys[:, 1], np.arange(n)) and np.array_equal(keys[:, 2], np.arange(n) + 5)
+
+
+@pytest.mark.parametrize("strict", [True, False])
+def test_count_overlaps_through_the_c_entry_with_the_helper_thread_build(lib, strict):
+    """pbgpu_range_op(count_overlaps) end to end on the harness: the indexed side's upload + build run on a helper thread
+    (the double sleeps 3 ms) while this thread encodes the iterated table in three slices; slice kernels are started when
+    the index is ready; counts are widened and the iterated table's columns re-exported zero-copy.  Device calls are the
+    harness's brute-force doubles; expectation by numpy."""
+    from polars_bio_b200 import _native
+
+    rng = np.random.default_rng(21)
+    names = np.array(["chr1", "chr2", "chr3", "chrUn_long_name"])
+    n, m = 2_500_000, 40
+    ic, ps = rng.integers(0, 4, n), rng.integers(0, 10_000, n).astype(np.int32)
+    pe = (ps + rng.integers(1, 300, n)).astype(np.int32)
+    xc, xs = rng.integers(0, 3, m), rng.integers(0, 10_000, m).astype(np.int32)  # chrUn...: only on the iterated side
+    xe = (xs + rng.integers(1, 2_000, m)).astype(np.int32)
+    indexed = pa.table({"chrom": names[xc].tolist(), "start": xs, "end": xe})
+    iterated = pa.table({"chrom": pa.array(names[ic].tolist(), pa.large_string()), "start": ps, "end": pe, "tag": pa.array(np.arange(n, dtype=np.int64))})
+    want = np.zeros(n, np.int64)
+    for j in range(m):
+        hit = (ic == xc[j]) & ((ps < xe[j]) & (pe > xs[j]) if strict else (ps <= xe[j]) & (pe >= xs[j]))
+        want += hit
+    lib.dbg_streams_ok(1)
+    try:
+        s1, s2, so = _CS(), _CS(), _CS()
+        indexed.to_reader()._export_to_c(ctypes.addressof(s1))                        # count_overlaps: `left` is the indexed table,
+        pa.RecordBatchReader.from_batches(iterated.schema, iterated.to_batches(max_chunksize=700_001))._export_to_c(ctypes.addressof(s2))  # `right` the iterated one
+        o = _native.PbRangeOptions()
+        o.range_op, o.filter_op, o.device = 6, 1 if strict else 0, -1
+        for i, c in enumerate(("chrom", "start", "end")):
+            o.cols1[i] = c.encode()
+            o.cols2[i] = c.encode()
+        rc = lib.pbgpu_range_op(ctypes.addressof(s1), ctypes.addressof(s2), ctypes.addressof(o), ctypes.addressof(so))
+        assert rc == 0, (rc, lib.pbgpu_last_error())
+        out = pa.RecordBatchReader._import_from_c(ctypes.addressof(so)).read_all()
+    finally:
+        lib.dbg_streams_ok(0)
+    assert out.column_names == ["chrom", "start", "end", "tag", "count"] and out.num_rows == n
+    assert np.array_equal(out.column("count").to_numpy(), want)
+    assert np.array_equal(out.column("tag").to_numpy(), np.arange(n)) and out.schema.field("chrom").type == pa.large_string()
