@@ -310,13 +310,13 @@ def measure_e2e_api(args, probe, build, expect_pairs, dev):
         sec = float(np.mean(tp[1:]))
         with_payload = {"ms_per_call": sec * 1e3, "pairs_per_s": expect_pairs / sec,
                         "columns": "reads: read_id int64, mapq uint8; variants: variant_id int64, ref utf8 -> 10 output columns",
-                        "h2d_bytes": int(12 * m + 9 * n + 9 * n + 8 * m + 5 * m + 1), "d2h_bytes": int((17 + 8 + 1 + 8 + 4 + 1) * expect_pairs),
+                        "h2d_bytes": int(9 * m + 9 * n + 9 * n + 8 * m + 5 * m + 1), "d2h_bytes": int((17 + 8 + 1 + 8 + 4 + 1) * expect_pairs),
                         "note": "pb.overlap only, 2 timed calls after 1 warm-up; payload columns gathered on the device"}
         del reads_p, vars_p
     # bytes on the bus per step, counted from what the bridge copies: both calls upload the variants (3 x int32) and
     # the reads (contig code as uint8 + 2 x int32); count_overlaps brings back uint32 counts, overlap the key columns of
     # the result rows (contig code uint8 + 4 x int32 positions; no payload columns -> no row ids)
-    return {"value": expect_pairs / e2e_sec, "unit": "pairs/s", "h2d_bytes_per_step": 2 * (12 * m + 9 * n),
+    return {"value": expect_pairs / e2e_sec, "unit": "pairs/s", "h2d_bytes_per_step": 2 * (9 * m + 9 * n),  # both tables: contig code as a byte + two int32 positions per row
             "d2h_bytes_per_step": int(4 * n + 17 * expect_pairs), "ms_per_step": e2e_sec * 1e3,
             "api": "pb.count_overlaps + pb.overlap on host pyarrow Tables (utf8 contig); output frames materialised per batch "
                    "and consumed as a stream",

@@ -359,6 +359,40 @@ def test_encoder_codes_are_consistent_for_many_short_and_long_names(lib, n_names
         assert np.array_equal(keys[:, 1], np.arange(n)) and np.array_equal(keys[:, 2], np.arange(n) + 5)
 
 
+def test_count_overlaps_through_the_c_entry_with_more_than_255_indexed_contigs(lib):
+    """The indexed side's contig codes are staged as bytes; a table with more than 255 contigs is encoded again with 32-bit
+    codes.  300 contigs on the indexed side, 320 on the iterated one (20 of them unknown to the index)."""
+    from polars_bio_b200 import _native
+
+    rng = np.random.default_rng(4)
+    names = np.array([f"ctg{i}" for i in range(320)])
+    m, n = 900, 20_000
+    xc, xs = rng.integers(0, 300, m), rng.integers(0, 5_000, m).astype(np.int32)
+    xc[:300] = np.arange(300)  # every one of the 300 occurs
+    xe = (xs + rng.integers(1, 900, m)).astype(np.int32)
+    ic, ps = rng.integers(0, 320, n), rng.integers(0, 5_000, n).astype(np.int32)
+    pe = (ps + rng.integers(1, 200, n)).astype(np.int32)
+    want = np.zeros(n, np.int64)
+    for j in range(m):
+        want += (ic == xc[j]) & (ps < xe[j]) & (pe > xs[j])
+    lib.dbg_streams_ok(1)
+    try:
+        s1, s2, so = _CS(), _CS(), _CS()
+        pa.table({"chrom": names[xc].tolist(), "start": xs, "end": xe}).to_reader()._export_to_c(ctypes.addressof(s1))
+        pa.table({"chrom": names[ic].tolist(), "start": ps, "end": pe}).to_reader()._export_to_c(ctypes.addressof(s2))
+        o = _native.PbRangeOptions()
+        o.range_op, o.filter_op, o.device = 6, 1, -1
+        for i, c in enumerate(("chrom", "start", "end")):
+            o.cols1[i] = c.encode()
+            o.cols2[i] = c.encode()
+        rc = lib.pbgpu_range_op(ctypes.addressof(s1), ctypes.addressof(s2), ctypes.addressof(o), ctypes.addressof(so))
+        assert rc == 0, (rc, lib.pbgpu_last_error())
+        out = pa.RecordBatchReader._import_from_c(ctypes.addressof(so)).read_all()
+    finally:
+        lib.dbg_streams_ok(0)
+    assert np.array_equal(out.column("count").to_numpy(), want) and want.sum() > 0
+
+
 @pytest.mark.parametrize("strict", [True, False])
 def test_count_overlaps_through_the_c_entry_with_the_helper_thread_build(lib, strict):
     """pbgpu_range_op(count_overlaps) end to end on the harness: the indexed side's upload + build run on a helper thread
