@@ -72,7 +72,14 @@ def ncu_traffic(kernel_key: str):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel from the newest committed
     `ncu --set full` capture of THIS workload (profiles/*config3*_traffic.json, written by scripts/ncu_summary.py)."""
     import glob
-    for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "*config3*_traffic.json")), reverse=True):
+
+    def captured(path):  # newest capture first: the time recorded in the file (scripts/ncu_summary.py), else the name
+        try:
+            return (json.load(open(path)).get("_meta", {}).get("captured_unix", 0), os.path.basename(path))
+        except Exception:
+            return (0, os.path.basename(path))
+
+    for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "*config3*_traffic.json")), key=captured, reverse=True):
         try:
             t = json.load(open(p))
             for name, v in t.items():
