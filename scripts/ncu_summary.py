@@ -167,8 +167,8 @@ def main_config3(tag, title):
     rep = os.path.join(OUT, f"{tag}_config3_prof.ncu-rep")
     if os.path.exists(rep):
         cap = full_capture(rep)
-        cap["_meta"] = {"captured_unix": int(os.path.getmtime(rep)), "tag": tag}  # bench.py reports the newest capture
-        json.dump(cap, open(os.path.join(PROF, f"{tag}_config3_traffic.json"), "w"), indent=1)
+        meta = {"_meta": {"captured_unix": int(os.path.getmtime(rep)), "tag": tag}}  # bench.py reports the newest capture
+        json.dump({**cap, **meta}, open(os.path.join(PROF, f"{tag}_config3_traffic.json"), "w"), indent=1)
         lines += [f"## `ncu --set full --clock-control none --import-source on` ({tag}_config3_prof.ncu-rep; averages over the captured "
                   "launches; ncu flushes caches between replays, so DRAM traffic is the cold-cache worst case)", "",
                   "| kernel | n | time us | dram rd MB | dram wr MB | dram % | L2 hit % | lts % | l1tex % | l1tex->xbar req % | sm % | warps act % | regs | grid x block |",
